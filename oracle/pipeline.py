@@ -1,0 +1,94 @@
+"""
+Oracle restatement of the per-frame stacking loop.
+
+Follows /root/reference/core/pipeline/c_image_stacking_pipeline/c_image_stacking_pipeline.cc:
+  create_frame_accumulation   :450-466
+  process_input_sequence      :1358-1862  (ordering: weights -> register -> remap(frame, mask) ->
+                                           remap(weights) -> weights*mask -> add)
+  multiply_weights            :108-138, 1704-1714
+  weights_required            :2004-2011, compute_weights :2013-2020
+  finalise (compute)          :731-769 (average_pyramid_inpaint is out of scope: compared on W>0 before it)
+and the input scaling of c_image_stacking_pipeline_base.cc:271-276 (convertTo(CV_32F, 1/(1<<bpp))).
+
+Test infrastructure only (see oracle/__init__.py).
+"""
+from dataclasses import dataclass, field
+import numpy as np
+import cv2
+
+from .registration import FrameRegistration, ImageRegistrationOptions
+from .accumulation import WeightedAverage, BayerAverage
+from .weights import compute_local_variance_map
+
+f32 = np.float32
+
+ACC_AVERAGE = "average"
+ACC_WEIGHTED_AVERAGE = "weighted_average"
+ACC_BAYER_AVERAGE = "bayer_average"
+
+
+@dataclass
+class StackingOptions:
+    registration: ImageRegistrationOptions = field(default_factory=ImageRegistrationOptions)
+    accumulation_method: str = ACC_AVERAGE
+    # c_frame_accumulation_options::sharpness_measure (c_image_stacking_pipeline.h:94-99)
+    sm_dscale: int = 1
+    sm_kradius: int = 1
+    sm_uscale: int = 0
+    enable_registration: bool = True
+
+
+def to_float_frame(raw, bpp):
+    """c_image_stacking_pipeline_base.cc:271-276."""
+    if raw.dtype == np.float32:
+        return raw
+    return (raw.astype(np.float64) * (1.0 / (1 << bpp))).astype(f32)
+
+
+def weights_required(o: StackingOptions):
+    return o.accumulation_method == ACC_WEIGHTED_AVERAGE and o.sm_kradius > 0
+
+
+def process_frame(reg: FrameRegistration, acc, o: StackingOptions, frame, mask=None, raw_bayer=None):
+    """One iteration of process_input_sequence. Returns True if the frame was accumulated."""
+    weights = None
+    if weights_required(o):
+        _, weights = compute_local_variance_map(frame, o.sm_dscale, o.sm_kradius, o.sm_uscale)
+        if weights is not None and mask is not None:
+            weights[mask == 0] = 0
+    ro = o.registration
+    if o.enable_registration:
+        if not reg.register_frame(frame, mask):
+            return False            # c_image_stacking_pipeline.cc:1578-1581: frame dropped
+        rmap = reg.current_remap
+        frame, mask = reg.custom_remap(rmap, frame, mask, ro.interpolation, ro.border_mode, ro.border_value)
+        if weights is not None:
+            weights, _ = reg.custom_remap(rmap, weights, None, ro.interpolation, cv2.BORDER_CONSTANT, None,
+                                          want_mask=False)
+    if weights is not None:
+        if mask is not None:
+            weights = cv2.multiply(mask, weights, scale=(1.0 / 255 if mask.dtype == np.uint8 else 1.0),
+                                   dtype=cv2.CV_32F)
+        mask = weights
+    if isinstance(acc, BayerAverage):
+        acc.set_remap(reg.current_remap if o.enable_registration else None)
+        return acc.add(raw_bayer, mask)
+    return acc.add(frame, mask)
+
+
+def run_stacking(frames, o: StackingOptions, reference=None, collect=None):
+    """frames: iterable of CV_32F frames. reference defaults to frames[0].
+    Returns (avg, mask, accumulator, registration); per-frame records appended to `collect` if given."""
+    frames = list(frames)
+    reg = FrameRegistration(o.registration)
+    ref = frames[0] if reference is None else reference
+    if o.enable_registration:
+        reg.setup_reference_frame(ref, None)
+    acc = BayerAverage() if o.accumulation_method == ACC_BAYER_AVERAGE else WeightedAverage()
+    for f in frames:
+        ok = process_frame(reg, acc, o, f)
+        if collect is not None:
+            collect.append(dict(ok=ok, params=None if reg.image_transform is None else reg.image_transform.clone_parameters(),
+                                rho=reg.status.rho, eps=reg.status.eps, iterations=reg.status.num_iterations))
+    avg, mask = acc.compute()
+    return avg, mask, acc, reg
