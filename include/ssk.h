@@ -1,0 +1,296 @@
+/*
+ * ssk.h - C ABI of the B200-native SerStacker stacking hot path (register -> warp -> accumulate).
+ *
+ * The reference (amyznikov/SerStacker) has no FFI layer: the boundary of this path is the C++ class
+ * surface its pipelines call.  Each entry point below names the reference member it replaces
+ * (paths relative to the reference root).  A thin C++ adapter with the reference's class names lives in
+ * serstacker_b200/host/ssk_adapter.h and forwards to these functions; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - plain C, no C++/torch types; every function returns 0 (SSK_OK) or a negative ssk_status and never
+ *    throws; ssk_last_error() returns the message of the last failure on the calling thread
+ *    (reference: bool return + CF_ERROR log line, core/debug.h:88-95).
+ *  - images are described by ssk_mat: the memory layout of cv::Mat (row-major, `step` bytes per row,
+ *    interleaved channels, OpenCV type code).  `mem` says whether `data` is a host or a device pointer.
+ *    Inputs are borrowed for the duration of the call; outputs are written into caller-allocated buffers.
+ *  - handles are single-threaded (one CUDA stream per handle), like the reference objects.
+ *  - there is no CPU fallback: every call fails with SSK_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef SSK_H_
+#define SSK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSK_API __attribute__((visibility("default")))
+
+typedef enum ssk_status {
+  SSK_OK = 0,
+  SSK_ERR_INVALID = -1,      /* bad argument / unsupported combination */
+  SSK_ERR_CUDA = -2,         /* CUDA runtime failure (message in ssk_last_error) */
+  SSK_ERR_STATE = -3,        /* call order violated (e.g. no reference set) */
+  SSK_ERR_NOT_REGISTERED = -4, /* frame failed registration (low rho / singular H): reference returns false */
+  SSK_ERR_NCCL = -5
+} ssk_status;
+
+/* OpenCV type codes used by the path (CV_MAKETYPE(depth, cn)). */
+enum { SSK_8U = 0, SSK_16U = 2, SSK_32F = 5 };
+#define SSK_MAKETYPE(depth, cn) (((depth) & 7) + (((cn) - 1) << 3))
+#define SSK_8UC1 SSK_MAKETYPE(SSK_8U, 1)
+#define SSK_16UC1 SSK_MAKETYPE(SSK_16U, 1)
+#define SSK_32FC1 SSK_MAKETYPE(SSK_32F, 1)
+#define SSK_32FC2 SSK_MAKETYPE(SSK_32F, 2)
+#define SSK_32FC3 SSK_MAKETYPE(SSK_32F, 3)
+
+enum { SSK_MEM_HOST = 0, SSK_MEM_DEVICE = 1 };
+
+/* cv::Mat view. */
+typedef struct ssk_mat {
+  void *data;
+  int64_t step;   /* bytes per row */
+  int32_t rows, cols;
+  int32_t type;   /* OpenCV type code */
+  int32_t mem;    /* SSK_MEM_HOST / SSK_MEM_DEVICE */
+} ssk_mat;
+
+/* IMAGE_MOTION_TYPE, core/proc/image_registration/image_transform.h:14-25 (same values). */
+enum {
+  SSK_MOTION_TRANSLATION = 0,
+  SSK_MOTION_EUCLIDEAN = 1,
+  SSK_MOTION_SCALED_EUCLIDEAN = 2,
+  SSK_MOTION_AFFINE = 3,
+  SSK_MOTION_HOMOGRAPHY = 4
+};
+
+/* ECC_ALIGN_METHOD, ecc2.h:59-64 (same values). */
+enum {
+  SSK_ECC_FORWARD_ADDITIVE = 0,
+  SSK_ECC_INVERSE_COMPOSITIONAL = 1,
+  SSK_ECC_LM = 2,
+  SSK_ECC_INVERSE_COMPOSITIONAL_LM = 3
+};
+
+/* ECC_INTERPOLATION_METHOD / ECC_BORDER_MODE, ecc2.h:27-52 (cv::InterpolationFlags / cv::BorderTypes values). */
+enum { SSK_INTER_NEAREST = 0, SSK_INTER_LINEAR = 1, SSK_INTER_CUBIC = 2 };
+enum {
+  SSK_BORDER_CONSTANT = 0, SSK_BORDER_REPLICATE = 1, SSK_BORDER_REFLECT = 2, SSK_BORDER_WRAP = 3,
+  SSK_BORDER_REFLECT101 = 4, SSK_BORDER_TRANSPARENT = 5
+};
+
+/* COLORID, core/io/debayer.h:19-35 (same values). */
+enum { SSK_COLORID_MONO = 0, SSK_COLORID_BAYER_RGGB = 8, SSK_COLORID_BAYER_GRBG = 9,
+       SSK_COLORID_BAYER_GBRG = 10, SSK_COLORID_BAYER_BGGR = 11 };
+
+#define SSK_MAX_PARAMS 8
+
+/* c_ecch_options, ecc2.h:158-172 (same fields, same defaults via ssk_ecch_options_default). */
+typedef struct ssk_ecch_options {
+  double epsx;
+  double reference_smooth_sigma;
+  double input_smooth_sigma;
+  double update_step_scale;
+  int32_t method;
+  int32_t interpolation;
+  int32_t max_iterations;
+  int32_t minimum_image_size;
+  int32_t maxlevel;
+} ssk_ecch_options;
+
+/* c_ecc_registration_options, c_frame_registration.h:47-64. */
+typedef struct ssk_ecc_registration_options {
+  double scale;
+  double eps;
+  double min_rho;
+  double input_smooth_sigma;
+  double reference_smooth_sigma;
+  double update_step_scale;
+  int32_t se_radius;
+  int32_t ecc_method;
+  int32_t max_iterations;
+  int32_t ecch_max_level;
+  int32_t ecch_minimum_image_size;
+  double normalization_noise;
+  int32_t normalization_scale;
+  int32_t ecch_estimate_translation_first;
+  int32_t replace_planetary_disk_with_mask;
+} ssk_ecc_registration_options;
+
+/* c_image_registration_options, c_frame_registration.h:119-136 (ECC members; the sparse-feature and
+ * eccflow stages are out of scope and must stay disabled). */
+typedef struct ssk_registration_options {
+  int32_t motion_type;
+  int32_t interpolation;
+  int32_t border_mode;
+  double border_value[4];
+  ssk_ecc_registration_options ecc;
+  int32_t enable_ecc_registration;
+} ssk_registration_options;
+
+/* c_image_registration_status::ecc, c_frame_registration.h:198-207. */
+typedef struct ssk_ecc_status {
+  double rho;
+  double min_rho;
+  double eps;
+  int32_t num_iterations;
+  int32_t max_iterations;
+  int32_t ok;       /* 1: registered; 0: dropped (reference: register_frame() returned false) */
+  int32_t failed;   /* solver flagged failure (singular Hessian), c_ecc_align::failed() */
+} ssk_ecc_status;
+
+/* An image transform by value: what c_image_transform holds (c_image_transform.h:42-117).
+ * params layout = the reference's `parameters()` vector:
+ *   translation (tx,ty); euclidean (tx,ty,angle[,scale]); affine a00 a01 a02 a10 a11 a12;
+ *   homography a00..a21 (a22 kept in aux[2]).  aux = {Cx, Cy, a22, euclidean scale when fixed}. */
+typedef struct ssk_transform {
+  int32_t motion_type;
+  int32_t nparams;
+  float params[SSK_MAX_PARAMS];
+  float aux[4];
+} ssk_transform;
+
+SSK_API const char *ssk_last_error(void);
+SSK_API int ssk_version(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+SSK_API int64_t ssk_kernel_launch_count(void);
+
+SSK_API void ssk_ecch_options_default(ssk_ecch_options *o);                  /* ecc2.h:158-172 */
+SSK_API void ssk_registration_options_default(ssk_registration_options *o);  /* c_frame_registration.h:47-64,119-136 */
+SSK_API int ssk_transform_init(ssk_transform *t, int motion_type);           /* image_transform.cc:34-63 + reset() */
+
+/* ---------------------------------------------------------------------------------------------
+ * c_image_transform (stateless helpers; c_image_transform.cc)
+ * ------------------------------------------------------------------------------------------- */
+/* c_image_transform::create_remap(params, size, rmap): rmap is CV_32FC2 rows x cols. */
+SSK_API int ssk_transform_create_remap(const ssk_transform *t, int rows, int cols, ssk_mat *rmap);
+/* c_image_transform::scale_transfrom(factor). */
+SSK_API int ssk_transform_scale(ssk_transform *t, double factor);
+
+/* ---------------------------------------------------------------------------------------------
+ * cv::remap as the reference calls it (c_frame_registration::base_remap, c_frame_registration.cc:1265-1386):
+ * dst = remap(src); if dst_mask != NULL: dst_mask = erode5x5(remap(src_mask or all-255, interp, CONSTANT 0) >= 255).
+ * The map is either analytic (t != NULL) or explicit (rmap != NULL, CV_32FC2).
+ * ------------------------------------------------------------------------------------------- */
+SSK_API int ssk_remap(const ssk_transform *t, const ssk_mat *rmap,
+                      const ssk_mat *src, ssk_mat *dst,
+                      const ssk_mat *src_mask, ssk_mat *dst_mask,
+                      int interpolation, int border_mode, const double border_value[4]);
+
+/* ---------------------------------------------------------------------------------------------
+ * c_ecch (ecc2.h:193-308, ecc2.cc:695-1176): coarse-to-fine ECC against a fixed reference.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ssk_ecch ssk_ecch;
+SSK_API int ssk_ecch_create(const ssk_ecch_options *opts, ssk_ecch **out);
+SSK_API int ssk_ecch_destroy(ssk_ecch *h);
+/* c_ecch::set_reference_image(image, mask): image CV_32FC1 (or 8U/16U, converted), mask CV_8UC1 or NULL. */
+SSK_API int ssk_ecch_set_reference_image(ssk_ecch *h, const ssk_mat *image, const ssk_mat *mask);
+/* c_ecch::align(current_image, current_mask): t is the c_image_transform the reference binds with
+ * set_image_transform(); it is updated in place.  status may be NULL. */
+SSK_API int ssk_ecch_align(ssk_ecch *h, const ssk_mat *image, const ssk_mat *mask, ssk_transform *t,
+                           ssk_ecc_status *status);
+/* number of pyramid levels / size of level l (c_ecch::compute_next_pyramid_layer_size, ecc2.h:290-293). */
+SSK_API int ssk_ecch_num_levels(const ssk_ecch *h);
+SSK_API int ssk_ecch_level_size(const ssk_ecch *h, int level, int *cols, int *rows);
+/* c_ecch::reference_image()/current_image(): copies pyramid level `level` (CV_32FC1) into dst. */
+SSK_API int ssk_ecch_get_image(const ssk_ecch *h, int which /*0 reference, 1 current*/, int level, ssk_mat *dst);
+
+/* ---------------------------------------------------------------------------------------------
+ * c_frame_registration, ECC branch (c_frame_registration.h:210-354, c_frame_registration.cc:565-964).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ssk_reg ssk_reg;
+SSK_API int ssk_reg_create(const ssk_registration_options *opts, ssk_reg **out);
+SSK_API int ssk_reg_destroy(ssk_reg *h);
+/* c_frame_registration::setup_reference_frame(image, mask). Frames are what the pipeline feeds:
+ * CV_32F in [0,1) (or 8U/16U with `bpp`, normalised by 1/(1<<bpp) as c_image_stacking_pipeline_base.cc:271-276). */
+SSK_API int ssk_reg_setup_reference_frame(ssk_reg *h, const ssk_mat *image, const ssk_mat *mask, int bpp);
+/* c_frame_registration::register_frame(src, srcmask) without dst: estimates the transform only.
+ * Returns SSK_ERR_NOT_REGISTERED where the reference returns false. */
+SSK_API int ssk_reg_register_frame(ssk_reg *h, const ssk_mat *image, const ssk_mat *mask, int bpp,
+                                   ssk_transform *t_out, ssk_ecc_status *status);
+/* c_frame_registration::current_remap(): materialises the full-resolution CV_32FC2 map on request. */
+SSK_API int ssk_reg_get_current_remap(ssk_reg *h, ssk_mat *rmap);
+/* c_frame_registration::remap()/custom_remap() with the current transform (rmap==NULL) or an explicit map. */
+SSK_API int ssk_reg_remap(ssk_reg *h, const ssk_mat *rmap, const ssk_mat *src, ssk_mat *dst,
+                          const ssk_mat *src_mask, ssk_mat *dst_mask,
+                          int interpolation /*<0: options*/, int border_mode /*<0: options*/,
+                          const double border_value[4]);
+
+/* ---------------------------------------------------------------------------------------------
+ * c_frame_accumulation (core/average/c_frame_accumulation.h:14-63, 222-262).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ssk_acc ssk_acc;
+enum { SSK_ACC_WEIGHTED_AVERAGE = 0,   /* c_weigthed_average (also plain `average`) */
+       SSK_ACC_BAYER_AVERAGE = 1 };    /* c_bayer_average */
+SSK_API int ssk_acc_create(int kind, ssk_acc **out);
+SSK_API int ssk_acc_destroy(ssk_acc *h);
+SSK_API int ssk_acc_clear(ssk_acc *h);                                       /* clear() */
+/* add(src, mask_or_weights): weights NULL | CV_8UC1 mask | CV_32FC1 weights (c_frame_accumulation.cc:20-129). */
+SSK_API int ssk_acc_add(ssk_acc *h, const ssk_mat *src, const ssk_mat *weights, int bpp);
+/* compute(avg, mask, dscale, ddepth): avg CV_32F (cn channels), mask CV_8UC1 (NULL to skip). */
+SSK_API int ssk_acc_compute(ssk_acc *h, ssk_mat *avg, ssk_mat *mask, double dscale);
+SSK_API int ssk_acc_get_counters(ssk_acc *h, ssk_mat *accw);                  /* get_acc_counters() */
+SSK_API int ssk_acc_reinitialize(ssk_acc *h, const ssk_mat *src, const ssk_mat *accw); /* reinitialize() */
+SSK_API int ssk_acc_size(const ssk_acc *h, int *cols, int *rows, int *channels); /* accumulator_size() */
+SSK_API int ssk_acc_frames(const ssk_acc *h);                                 /* accumulated_frames() */
+/* c_bayer_average::set_bayer_pattern / set_remap (remap by transform or explicit CV_32FC2 map). */
+SSK_API int ssk_acc_set_bayer_pattern(ssk_acc *h, int colorid);
+SSK_API int ssk_acc_set_remap(ssk_acc *h, const ssk_transform *t, const ssk_mat *rmap);
+/* Device pointers of the state, for the multi-GPU combine: mean (or sum) planes and weight/counter planes. */
+SSK_API int ssk_acc_device_state(ssk_acc *h, void **acc, void **weights, int64_t *acc_bytes, int64_t *weights_bytes);
+/* Multi-GPU: convert the local running mean to sum form (A*W, W) in place / back (after an external
+ * reduce of both buffers, e.g. ncclReduce), so that A = sum(W_g A_g) / sum(W_g). */
+SSK_API int ssk_acc_to_sum_form(ssk_acc *h);
+SSK_API int ssk_acc_from_sum_form(ssk_acc *h, int accumulated_frames);
+
+/* ---------------------------------------------------------------------------------------------
+ * Weight maps (core/proc/sharpness_measure/c_local_variance_sharpness_measure.cc:193-247, core/proc/lpg.cc:223-290).
+ * ------------------------------------------------------------------------------------------- */
+SSK_API int ssk_local_variance_map(const ssk_mat *image, int bpp, int dscale, int kradius, int uscale,
+                                   ssk_mat *map /*CV_32FC1, full resolution*/, double *Q);
+
+/* ---------------------------------------------------------------------------------------------
+ * The fused per-frame loop of c_image_stacking_pipeline::process_input_sequence
+ * (c_image_stacking_pipeline.cc:1358-1862): weights -> register -> warp(frame, mask, weights) -> accumulate,
+ * for a batch of frames per call.  This is the data-parallel hot path; results are identical to calling
+ * ssk_local_variance_map / ssk_reg_register_frame / ssk_reg_remap / ssk_acc_add frame by frame.
+ * ------------------------------------------------------------------------------------------- */
+enum { SSK_STACK_AVERAGE = 0, SSK_STACK_WEIGHTED_AVERAGE = 1, SSK_STACK_BAYER_AVERAGE = 2 };
+typedef struct ssk_stack_options {
+  ssk_registration_options registration;
+  int32_t accumulation_method;
+  int32_t sm_dscale, sm_kradius, sm_uscale;  /* c_frame_accumulation_options::sharpness_measure, c_image_stacking_pipeline.h:94-99 */
+  int32_t enable_registration;               /* c_image_stacking_options::enable_registration */
+  int32_t bayer_colorid;                     /* for SSK_STACK_BAYER_AVERAGE */
+  int32_t max_batch;                         /* frames in flight per call (device scratch is sized for it) */
+} ssk_stack_options;
+
+typedef struct ssk_stack ssk_stack;
+SSK_API void ssk_stack_options_default(ssk_stack_options *o);
+SSK_API int ssk_stack_create(const ssk_stack_options *opts, ssk_stack **out);
+SSK_API int ssk_stack_destroy(ssk_stack *h);
+SSK_API int ssk_stack_set_reference(ssk_stack *h, const ssk_mat *image, const ssk_mat *mask, int bpp);
+/* Process `n` frames (all of the same geometry/type).  frames[i] may be host or device memory.
+ * transforms_out / status_out (arrays of n, may be NULL) receive the per-frame registration results. */
+SSK_API int ssk_stack_add_frames(ssk_stack *h, const ssk_mat *frames, int n, int bpp,
+                                 ssk_transform *transforms_out, ssk_ecc_status *status_out);
+/* Enqueue only (no host sync, results stay on the device): for steady-state throughput measurement. */
+SSK_API int ssk_stack_add_frames_async(ssk_stack *h, const ssk_mat *frames, int n, int bpp);
+SSK_API int ssk_stack_sync(ssk_stack *h);
+/* c_frame_accumulation::compute() of the pipeline's accumulator. */
+SSK_API int ssk_stack_compute(ssk_stack *h, ssk_mat *avg, ssk_mat *mask);
+SSK_API int ssk_stack_accumulated_frames(ssk_stack *h);
+SSK_API ssk_acc *ssk_stack_accumulator(ssk_stack *h);
+SSK_API ssk_reg *ssk_stack_registration(ssk_stack *h);
+/* CUDA stream the handle launches on (cudaStream_t as void*), for event timing by the caller. */
+SSK_API void *ssk_stack_stream(ssk_stack *h);
+/* Per-stage device time (ms) of the last ssk_stack_add_frames* call after ssk_stack_sync:
+ * [0] prep (convert+pyrDown+smooth+pyramid) [1] weights [2] ECC [3] warp+accumulate. */
+SSK_API int ssk_stack_stage_times(ssk_stack *h, float ms[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSK_H_ */

@@ -1,0 +1,154 @@
+"""
+Numpy model of the OpenCV primitives whose *exact* semantics the CUDA kernels reproduce
+(SURVEY.md Appendix B).  OpenCV is the reference's un-vendored, un-pinned third-party dependency
+(CMakeLists.txt:47-59, `find_package(OpenCV)` >= 4.2); its published algorithms for
+cv::remap / cv::pyrDown / cv::sepFilter2D are restated here and checked against cv2 4.13.0 in
+tests/test_cvmodel.py.  The model is the specification the kernels are written to.
+
+Test infrastructure only (see oracle/__init__.py).
+"""
+import numpy as np
+
+f32 = np.float32
+INTER_BITS = 5
+INTER_TAB_SIZE = 1 << INTER_BITS          # 32
+INTER_REMAP_COEF_BITS = 15
+INTER_REMAP_COEF_SCALE = 1 << INTER_REMAP_COEF_BITS
+
+BORDER_CONSTANT, BORDER_REPLICATE, BORDER_REFLECT, BORDER_WRAP, BORDER_REFLECT101, BORDER_TRANSPARENT = 0, 1, 2, 3, 4, 5
+
+
+def quantize(coord):
+    """cv::remap converts a CV_32FC2 map with cvRound(v * 32) (round-half-even, evaluated in float)."""
+    s = np.rint((coord.astype(f32) * f32(INTER_TAB_SIZE)).astype(f32)).astype(np.int64)
+    return s >> INTER_BITS, s & (INTER_TAB_SIZE - 1)
+
+
+def border_interpolate(p, n, border):
+    """cv::borderInterpolate for the modes used on the path; returns index or -1 (constant/transparent)."""
+    p = np.asarray(p, dtype=np.int64).copy()
+    if border == BORDER_REPLICATE:
+        return np.clip(p, 0, n - 1)
+    if border in (BORDER_REFLECT, BORDER_REFLECT101):
+        delta = 1 if border == BORDER_REFLECT101 else 0
+        if n == 1:
+            return np.zeros_like(p)
+        for _ in range(8):
+            neg = p < 0
+            p[neg] = -p[neg] - 1 + delta
+            big = p >= n
+            p[big] = n - 1 - (p[big] - n) - delta
+        return p
+    if border == BORDER_WRAP:
+        return np.mod(p, n)
+    out = p.copy()
+    out[(p < 0) | (p >= n)] = -1
+    return out
+
+
+def linear_coeffs():
+    """initInterTab1D(INTER_LINEAR): (1 - x, x) for x = i/32, float."""
+    t = np.arange(INTER_TAB_SIZE, dtype=f32) * f32(1.0 / INTER_TAB_SIZE)
+    return np.stack([f32(1) - t, t], axis=1).astype(f32)
+
+
+def cubic_coeffs():
+    """interpolateCubic, A = -0.75, evaluated in float at x = i/32."""
+    A = f32(-0.75)
+    x = np.arange(INTER_TAB_SIZE, dtype=f32) * f32(1.0 / INTER_TAB_SIZE)
+    c = np.empty((INTER_TAB_SIZE, 4), dtype=f32)
+    c[:, 0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A
+    c[:, 1] = ((A + 2) * x - (A + 3)) * x * x + 1
+    c[:, 2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1
+    c[:, 3] = f32(1) - c[:, 0] - c[:, 1] - c[:, 2]
+    return c
+
+
+def fixed_tab_2d(tab1d):
+    """initInterTab2D(..., fixpt=true): short weights with the sum forced to 32768.
+    Returns int array [fy, fx, ky, kx]."""
+    k = tab1d.shape[1]
+    out = np.zeros((INTER_TAB_SIZE, INTER_TAB_SIZE, k, k), dtype=np.int64)
+    for i in range(INTER_TAB_SIZE):
+        for j in range(INTER_TAB_SIZE):
+            v = (tab1d[i][:, None] * tab1d[j][None, :]).astype(f32)
+            it = np.clip(np.rint((v * f32(INTER_REMAP_COEF_SCALE)).astype(f32)), -32768, 32767).astype(np.int64)
+            isum = int(it.sum())
+            if isum != INTER_REMAP_COEF_SCALE:
+                diff = isum - INTER_REMAP_COEF_SCALE
+                k2 = k // 2
+                Mk = mk = (k2, k2)
+                for k1 in range(k2, min(k, k2 + 2)):
+                    for kk in range(k2, min(k, k2 + 2)):
+                        if it[k1, kk] < it[mk]:
+                            mk = (k1, kk)
+                        elif it[k1, kk] > it[Mk]:
+                            Mk = (k1, kk)
+                if diff < 0:
+                    it[Mk] -= diff
+                else:
+                    it[mk] -= diff
+            out[i, j] = it
+    return out
+
+
+def remap_f32(src, rmap, interp="linear", border=BORDER_REPLICATE, border_value=0.0, dst=None):
+    """cv::remap for CV_32FC1 source, CV_32FC2 map."""
+    h, w = src.shape
+    ix, fx = quantize(rmap[..., 0])
+    iy, fy = quantize(rmap[..., 1])
+    if interp == "nearest":
+        ix = np.rint(rmap[..., 0]).astype(np.int64)
+        iy = np.rint(rmap[..., 1]).astype(np.int64)
+        taps, off, cx, cy = 1, 0, None, None
+    elif interp == "linear":
+        taps, off = 2, 0
+        c = linear_coeffs()
+        cx, cy = c[fx], c[fy]
+    else:
+        taps, off = 4, -1
+        c = cubic_coeffs()
+        cx, cy = c[fx], c[fy]
+    out = np.zeros(rmap.shape[:2], dtype=f32)
+    # BORDER_TRANSPARENT: pixels whose anchor tap (ix, iy) is outside keep dst; the other taps are clamped
+    bm = BORDER_REPLICATE if border == BORDER_TRANSPARENT else border
+    anyin = np.zeros(rmap.shape[:2], dtype=bool)
+    for ky in range(taps):
+        yy = border_interpolate(iy + off + ky, h, bm)
+        row = np.zeros(rmap.shape[:2], dtype=f32)
+        for kx in range(taps):
+            xx = border_interpolate(ix + off + kx, w, bm)
+            ok = (xx >= 0) & (yy >= 0)
+            anyin |= ok
+            v = np.where(ok, src[np.clip(yy, 0, h - 1), np.clip(xx, 0, w - 1)], f32(border_value)).astype(f32)
+            if taps == 1:
+                row = v
+            else:
+                wgt = (cy[..., ky] * cx[..., kx]).astype(f32)
+                row = (row + v * wgt).astype(f32)
+        out = (out + row).astype(f32) if taps > 1 else row
+    if border == BORDER_TRANSPARENT and dst is not None:
+        outside = (ix < 0) | (ix >= w) | (iy < 0) | (iy >= h)
+        out = np.where(outside, dst, out)
+    return out
+
+
+def remap_u8_all255_valid(size, rmap, interp="linear", thresh=255):
+    """(cv::remap(Mat1b(size,255), rmap, interp, BORDER_CONSTANT 0) >= thresh) modelled with the
+    fixed-point tables: value = saturate_u8((255 * sum_inbounds(w) + 2^14) >> 15)."""
+    w, h = size
+    ix, fx = quantize(rmap[..., 0])
+    iy, fy = quantize(rmap[..., 1])
+    if interp == "linear":
+        taps, off, tab = 2, 0, fixed_tab_2d(linear_coeffs())
+    else:
+        taps, off, tab = 4, -1, fixed_tab_2d(cubic_coeffs())
+    S = np.zeros(rmap.shape[:2], dtype=np.int64)
+    for ky in range(taps):
+        yy = iy + off + ky
+        for kx in range(taps):
+            xx = ix + off + kx
+            ok = (xx >= 0) & (xx < w) & (yy >= 0) & (yy < h)
+            S += np.where(ok, tab[fy, fx, ky, kx], 0)
+    val = np.clip((255 * S + (1 << 14)) >> 15, 0, 255)
+    return val >= thresh, val

@@ -1,0 +1,364 @@
+"""
+Python harness over the C ABI that mirrors the reference's operator surface for the stacking hot path
+(same class / method names and argument meaning, see the citations), so the parity tests read like code
+written against the reference.  The product host layer is the C++ adapter (serstacker_b200/host/ssk_adapter.h);
+this module only marshals numpy arrays into ssk_mat and calls libssk.so.  No computation happens here.
+"""
+import ctypes as C
+import numpy as np
+
+from . import capi
+from .capi import (check, mat, ref, ssk_transform, ssk_ecc_status, ssk_mat, SskError)
+
+f32 = np.float32
+
+
+class c_image_transform:
+    """c_image_transform by value (core/proc/image_registration/c_image_transform.h:42-117)."""
+
+    def __init__(self, motion_type):
+        self.t = ssk_transform()
+        check(capi.lib.ssk_transform_init(C.byref(self.t), motion_type))
+
+    @property
+    def motion_type(self):
+        return self.t.motion_type
+
+    def parameters(self):
+        return self.t.parameters()
+
+    def set_parameters(self, p):
+        p = np.asarray(p, dtype=f32).reshape(-1)
+        assert p.size == self.t.nparams
+        for i, v in enumerate(p):
+            self.t.params[i] = float(v)
+        return True
+
+    def scale_transfrom(self, factor):
+        check(capi.lib.ssk_transform_scale(C.byref(self.t), float(factor)))
+
+    def create_remap(self, size):
+        w, h = size
+        rmap = np.empty((h, w, 2), dtype=f32)
+        m = mat(rmap)
+        check(capi.lib.ssk_transform_create_remap(C.byref(self.t), h, w, C.byref(m)))
+        return rmap
+
+
+def create_image_transform(motion_type):
+    """image_transform.cc:34-63."""
+    return c_image_transform(motion_type)
+
+
+def remap(transform, rmap, src, want_mask=False, src_mask=None, interpolation=capi.INTER_LINEAR,
+          border_mode=capi.BORDER_REFLECT101, border_value=(0, 0, 0, 0), dst=None, size=None):
+    """c_frame_registration::base_remap (c_frame_registration.cc:1265-1386) -> (dst, dst_mask)."""
+    if size is None:
+        size = rmap.shape[:2] if rmap is not None else src.shape[:2]
+    out = None
+    if src is not None:
+        out = dst if dst is not None else np.zeros(tuple(size) + src.shape[2:], dtype=f32)
+    omask = np.zeros(tuple(size), dtype=np.uint8) if want_mask else None
+    ms, mo, mm, mk, mr = mat(src), mat(out), mat(src_mask), mat(omask), mat(rmap)
+    bv = (C.c_double * 4)(*[float(v) for v in border_value])
+    check(capi.lib.ssk_remap(None if transform is None else C.byref(transform.t), ref(mr), ref(ms), ref(mo), ref(mm),
+                             ref(mk), interpolation, border_mode, bv))
+    return out, omask
+
+
+class c_ecch:
+    """c_ecch (ecc2.h:193-308)."""
+
+    def __init__(self, transform=None, method=capi.ECC_INVERSE_COMPOSITIONAL_LM, **opts):
+        o = capi.ssk_ecch_options()
+        capi.lib.ssk_ecch_options_default(C.byref(o))
+        o.method = method
+        for k, v in opts.items():
+            assert hasattr(o, k), k
+            setattr(o, k, v)
+        self._h = C.c_void_p()
+        check(capi.lib.ssk_ecch_create(C.byref(o), C.byref(self._h)))
+        self.transform = transform
+        self.status = ssk_ecc_status()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            capi.lib.ssk_ecch_destroy(self._h)
+            self._h = None
+
+    def set_image_transform(self, t):
+        self.transform = t
+
+    def set_reference_image(self, image, mask=None):
+        m = mat(np.ascontiguousarray(image))
+        check(capi.lib.ssk_ecch_set_reference_image(self._h, C.byref(m), ref(mat(mask))))
+        return True
+
+    def align(self, image, mask=None):
+        m = mat(np.ascontiguousarray(image))
+        check(capi.lib.ssk_ecch_align(self._h, C.byref(m), ref(mat(mask)), C.byref(self.transform.t), C.byref(self.status)))
+        return True
+
+    def eps(self):
+        return self.status.eps
+
+    def num_iterations(self):
+        return self.status.num_iterations
+
+    def num_levels(self):
+        return capi.lib.ssk_ecch_num_levels(self._h)
+
+    def level_size(self, level):
+        w, h = C.c_int(), C.c_int()
+        check(capi.lib.ssk_ecch_level_size(self._h, level, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def _image(self, which, level):
+        w, h = self.level_size(level)
+        out = np.empty((h, w), dtype=f32)
+        m = mat(out)
+        check(capi.lib.ssk_ecch_get_image(self._h, which, level, C.byref(m)))
+        return out
+
+    def reference_image(self, level=0):
+        return self._image(0, level)
+
+    def current_image(self, level=0):
+        return self._image(1, level)
+
+
+def registration_options(**kw):
+    """c_image_registration_options with the reference defaults (c_frame_registration.h:47-64, 119-136);
+    keyword `ecc` is a dict of c_ecc_registration_options fields."""
+    o = capi.ssk_registration_options()
+    capi.lib.ssk_registration_options_default(C.byref(o))
+    o.enable_ecc_registration = 1
+    ecc = kw.pop("ecc", {})
+    for k, v in kw.items():
+        if k == "border_value":
+            for i in range(4):
+                o.border_value[i] = float(v[i]) if i < len(v) else 0.0
+        else:
+            assert hasattr(o, k), k
+            setattr(o, k, v)
+    for k, v in ecc.items():
+        assert hasattr(o.ecc, k), k
+        setattr(o.ecc, k, v)
+    return o
+
+
+class c_frame_registration:
+    """c_frame_registration, ECC branch (c_frame_registration.h:210-354)."""
+
+    def __init__(self, options):
+        self.options = options
+        self._h = C.c_void_p()
+        check(capi.lib.ssk_reg_create(C.byref(options), C.byref(self._h)))
+        self.status = ssk_ecc_status()
+        self.transform = ssk_transform()
+        self._ref_shape = None
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            capi.lib.ssk_reg_destroy(self._h)
+            self._h = None
+
+    def setup_reference_frame(self, image, mask=None, bpp=0):
+        m = mat(np.ascontiguousarray(image))
+        check(capi.lib.ssk_reg_setup_reference_frame(self._h, C.byref(m), ref(mat(mask)), bpp))
+        self._ref_shape = image.shape[:2]
+        return True
+
+    def register_frame(self, image, mask=None, bpp=0):
+        """Returns True/False like the reference (False: low correlation / solver failure)."""
+        m = mat(np.ascontiguousarray(image))
+        rc = capi.lib.ssk_reg_register_frame(self._h, C.byref(m), ref(mat(mask)), bpp, C.byref(self.transform), C.byref(self.status))
+        if rc == capi.SSK_ERR_NOT_REGISTERED:
+            return False
+        check(rc)
+        return True
+
+    def image_transform_parameters(self):
+        return self.transform.parameters()
+
+    def current_remap(self):
+        h, w = self._ref_shape
+        rmap = np.empty((h, w, 2), dtype=f32)
+        m = mat(rmap)
+        check(capi.lib.ssk_reg_get_current_remap(self._h, C.byref(m)))
+        return rmap
+
+    def custom_remap(self, rmap, src, src_mask=None, want_mask=True, interpolation=-1, border_mode=-1,
+                     border_value=(0, 0, 0, 0)):
+        size = rmap.shape[:2] if rmap is not None else self._ref_shape
+        out = np.zeros(tuple(size) + src.shape[2:], dtype=f32) if src is not None else None
+        omask = np.zeros(tuple(size), dtype=np.uint8) if want_mask else None
+        bv = (C.c_double * 4)(*[float(v) for v in border_value])
+        check(capi.lib.ssk_reg_remap(self._h, ref(mat(rmap)), ref(mat(src)), ref(mat(out)), ref(mat(src_mask)), ref(mat(omask)),
+                                     interpolation, border_mode, bv))
+        return out, omask
+
+    def remap(self, src, src_mask=None, **kw):
+        return self.custom_remap(None, src, src_mask, **kw)
+
+
+class c_frame_accumulation:
+    """c_frame_accumulation (core/average/c_frame_accumulation.h:14-37)."""
+    kind = capi.ACC_WEIGHTED_AVERAGE
+
+    def __init__(self, handle=None):
+        self._own = handle is None
+        self._h = C.c_void_p()
+        if handle is None:
+            check(capi.lib.ssk_acc_create(self.kind, C.byref(self._h)))
+        else:
+            self._h = C.c_void_p(handle)
+
+    def __del__(self):
+        if getattr(self, "_own", False) and getattr(self, "_h", None):
+            capi.lib.ssk_acc_destroy(self._h)
+            self._h = None
+
+    def add(self, src, weights=None, bpp=0):
+        check(capi.lib.ssk_acc_add(self._h, C.byref(mat(np.ascontiguousarray(src))),
+                                   ref(mat(None if weights is None else np.ascontiguousarray(weights))), bpp))
+        return True
+
+    def accumulator_size(self):
+        w, h, c = C.c_int(), C.c_int(), C.c_int()
+        check(capi.lib.ssk_acc_size(self._h, C.byref(w), C.byref(h), C.byref(c)))
+        return w.value, h.value, c.value
+
+    def accumulated_frames(self):
+        return capi.lib.ssk_acc_frames(self._h)
+
+    def compute(self, dscale=1.0, want_mask=True):
+        w, h, c = self.accumulator_size()
+        avg = np.empty((h, w) if c == 1 else (h, w, c), dtype=f32)
+        mask = np.empty((h, w), dtype=np.uint8) if want_mask else None
+        check(capi.lib.ssk_acc_compute(self._h, C.byref(mat(avg)), ref(mat(mask)), float(dscale)))
+        return avg, mask
+
+    def get_acc_counters(self):
+        w, h, c = self.accumulator_size()
+        wc = 3 if self.kind == capi.ACC_BAYER_AVERAGE else 1
+        out = np.empty((h, w) if wc == 1 else (h, w, wc), dtype=f32)
+        check(capi.lib.ssk_acc_get_counters(self._h, C.byref(mat(out))))
+        return out
+
+    def reinitialize(self, src, accw):
+        check(capi.lib.ssk_acc_reinitialize(self._h, C.byref(mat(np.ascontiguousarray(src, dtype=f32))),
+                                            C.byref(mat(np.ascontiguousarray(accw, dtype=f32)))))
+        return True
+
+    def clear(self):
+        check(capi.lib.ssk_acc_clear(self._h))
+
+
+class c_weigthed_average(c_frame_accumulation):
+    """c_weigthed_average (c_frame_accumulation.h:39-63) [sic: the reference's spelling]."""
+    kind = capi.ACC_WEIGHTED_AVERAGE
+
+
+class c_bayer_average(c_frame_accumulation):
+    """c_bayer_average (c_frame_accumulation.h:222-262)."""
+    kind = capi.ACC_BAYER_AVERAGE
+
+    def set_bayer_pattern(self, colorid):
+        check(capi.lib.ssk_acc_set_bayer_pattern(self._h, colorid))
+
+    def set_remap(self, rmap=None, transform=None):
+        t = None if transform is None else C.byref(transform if isinstance(transform, ssk_transform) else transform.t)
+        check(capi.lib.ssk_acc_set_remap(self._h, t, ref(mat(rmap))))
+
+
+def compute_local_variance_map(image, dscale=1, kradius=1, uscale=0, bpp=0):
+    """compute_local_variance_map (c_local_variance_sharpness_measure.cc:193-247) -> (Q, map)."""
+    out = np.empty(image.shape[:2], dtype=f32)
+    q = C.c_double()
+    check(capi.lib.ssk_local_variance_map(C.byref(mat(np.ascontiguousarray(image))), bpp, dscale, kradius, uscale,
+                                          C.byref(mat(out)), C.byref(q)))
+    return q.value, out
+
+
+def stack_options(**kw):
+    o = capi.ssk_stack_options()
+    capi.lib.ssk_stack_options_default(C.byref(o))
+    reg = kw.pop("registration", None)
+    if reg is not None:
+        o.registration = reg
+    for k, v in kw.items():
+        assert hasattr(o, k), k
+        setattr(o, k, v)
+    return o
+
+
+class c_image_stacking_pipeline:
+    """The per-frame loop of c_image_stacking_pipeline::process_input_sequence
+    (c_image_stacking_pipeline.cc:1358-1862) + finalise (:731-769), batched on the device."""
+
+    def __init__(self, options):
+        self.options = options
+        self._h = C.c_void_p()
+        check(capi.lib.ssk_stack_create(C.byref(options), C.byref(self._h)))
+        self._shape = None
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            capi.lib.ssk_stack_destroy(self._h)
+            self._h = None
+
+    def set_reference(self, image, bpp=0):
+        m = image if isinstance(image, ssk_mat) else mat(np.ascontiguousarray(image))
+        check(capi.lib.ssk_stack_set_reference(self._h, C.byref(m), None, bpp))
+        self._shape = (m.rows, m.cols, (m.type >> 3) + 1)
+        self._bpp = bpp
+
+    def _mats(self, frames):
+        arr = (ssk_mat * len(frames))()
+        keep = []
+        for i, f in enumerate(frames):
+            m = f if isinstance(f, ssk_mat) else mat(np.ascontiguousarray(f))
+            keep.append(m)
+            arr[i] = m
+        return arr, keep
+
+    def add_frames(self, frames, want_results=True):
+        arr, keep = self._mats(frames)
+        n = len(frames)
+        ts = (ssk_transform * n)() if want_results else None
+        st = (ssk_ecc_status * n)() if want_results else None
+        check(capi.lib.ssk_stack_add_frames(self._h, arr, n, self._bpp, ts, st))
+        if not want_results:
+            return None
+        return [dict(ok=bool(st[i].ok), params=ts[i].parameters(), rho=st[i].rho, eps=st[i].eps,
+                     iterations=st[i].num_iterations) for i in range(n)]
+
+    def add_frames_async(self, frames):
+        arr, keep = self._mats(frames)
+        check(capi.lib.ssk_stack_add_frames_async(self._h, arr, len(frames), self._bpp))
+        return keep
+
+    def sync(self):
+        check(capi.lib.ssk_stack_sync(self._h))
+
+    def accumulated_frames(self):
+        return capi.lib.ssk_stack_accumulated_frames(self._h)
+
+    def compute(self):
+        h, w, c = self._shape
+        avg = np.empty((h, w) if c == 1 else (h, w, c), dtype=f32)
+        mask = np.empty((h, w), dtype=np.uint8)
+        check(capi.lib.ssk_stack_compute(self._h, C.byref(mat(avg)), C.byref(mat(mask))))
+        return avg, mask
+
+    def accumulator(self):
+        return c_weigthed_average(capi.lib.ssk_stack_accumulator(self._h))
+
+    def stream(self):
+        return capi.lib.ssk_stack_stream(self._h)
+
+    def stage_times(self):
+        ms = (C.c_float * 4)()
+        check(capi.lib.ssk_stack_stage_times(self._h, ms))
+        return list(ms)

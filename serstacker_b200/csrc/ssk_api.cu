@@ -1,0 +1,616 @@
+// C ABI (include/ssk.h) over the engine classes.  No torch / OpenCV types cross this boundary.
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <new>
+#include "ssk_engine.cuh"
+
+using namespace ssk;
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+int check_mat(const ssk_mat *m, const char *what) {
+  if (!m || !m->data || m->rows <= 0 || m->cols <= 0) { set_error(std::string(what) + ": empty image"); return SSK_ERR_INVALID; }
+  const int d = type_depth(m->type), cn = type_cn(m->type);
+  if (!depth_bytes(d) || cn < 1 || cn > 4) { set_error(std::string(what) + ": unsupported type"); return SSK_ERR_INVALID; }
+  if (m->step < (int64_t)m->cols * cn * depth_bytes(d)) { set_error(std::string(what) + ": step smaller than a row"); return SSK_ERR_INVALID; }
+  return SSK_OK;
+}
+
+int ensure_device() {
+  static thread_local bool checked = false;
+  if (checked) return SSK_OK;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n < 1) {
+    set_error(std::string("no CUDA device available: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)");
+    cudaGetLastError();
+    return SSK_ERR_CUDA;
+  }
+  checked = true;
+  return SSK_OK;
+}
+
+// make `m` available on the device as a dense image; host data goes through `staging`
+int to_device(const ssk_mat *m, DevBuf &staging, cudaStream_t s, Img *out, int bpp) {
+  const int d = type_depth(m->type), cn = type_cn(m->type);
+  out->rows = m->rows; out->cols = m->cols; out->depth = d; out->cn = cn; out->scale = bpp_scale(d, bpp);
+  if (m->mem == SSK_MEM_DEVICE) {
+    out->data = m->data; out->step = m->step;
+    return SSK_OK;
+  }
+  const size_t rowb = (size_t)m->cols * cn * depth_bytes(d);
+  if (int e = staging.ensure(rowb * m->rows)) return e;
+  SSK_CUDA(cudaMemcpy2DAsync(staging.p, rowb, m->data, m->step, rowb, m->rows, cudaMemcpyHostToDevice, s));
+  out->data = staging.p; out->step = (int64_t)rowb;
+  return SSK_OK;
+}
+
+// copy a dense device image into a caller buffer (host or device)
+int from_device(const void *dsrc, size_t rowb, int rows, ssk_mat *dst, cudaStream_t s) {
+  SSK_CUDA(cudaMemcpy2DAsync(dst->data, dst->step, dsrc, rowb, rowb, rows,
+                             dst->mem == SSK_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+  return SSK_OK;
+}
+
+__global__ void k_create_remap(MapCoef m, int rows, int cols, float2 *dst) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= cols || y >= rows) return;
+  float u, v;
+  map_xy(m, (float)x, (float)y, u, v);
+  dst[(int64_t)y * cols + x] = make_float2(u, v);
+}
+
+int create_remap_dense(const ssk_transform &t, int rows, int cols, float2 *d, cudaStream_t s) {
+  dim3 grid(div_up(cols, 32), div_up(rows, 8));
+  k_create_remap<<<grid, 256, 0, s>>>(make_mapcoef(t), rows, cols, d);
+  SSK_LAUNCH_CHECK();
+  return SSK_OK;
+}
+
+void fill_status(const EccFrame &f, const Ecch &e, ssk_ecc_status *st) {
+  if (!st) return;
+  st->rho = f.rho; st->min_rho = e.min_rho; st->eps = f.eps;
+  st->num_iterations = f.num_iterations; st->max_iterations = e.opts.max_iterations;
+  st->ok = f.ok; st->failed = f.failed;
+}
+
+// thread-local scratch for the stateless entry points
+struct Scratch {
+  cudaStream_t stream = nullptr;
+  DevBuf a, b, c, d, e;
+  int init() {
+    if (!stream) SSK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    return SSK_OK;
+  }
+};
+Scratch &scratch() { static thread_local Scratch s; return s; }
+
+// the general remap: shared by ssk_remap and ssk_reg_remap
+int do_remap(cudaStream_t s, DevBuf &st_src, DevBuf &st_map, DevBuf &st_mask, DevBuf &st_out, DevBuf &st_tmp,
+             const ssk_transform *t, const ssk_mat *rmap, const ssk_mat *src, ssk_mat *dst, const ssk_mat *src_mask,
+             ssk_mat *dst_mask, int interp, int border, const double bv[4]) {
+  Tables tab;
+  if (int e = get_tables(&tab)) return e;
+  SSK_REQUIRE(t || rmap, "remap: either a transform or an explicit map is required");
+  int rows, cols;
+  Img map_img = {};
+  const float2 *d_rmap = nullptr;
+  int64_t rmap_step = 0;
+  if (rmap) {
+    if (int e = check_mat(rmap, "remap map")) return e;
+    SSK_REQUIRE(rmap->type == SSK_32FC2, "remap: map must be CV_32FC2");
+    if (int e = to_device(rmap, st_map, s, &map_img, 0)) return e;
+    d_rmap = static_cast<const float2 *>(map_img.data);
+    rmap_step = map_img.step;
+    rows = rmap->rows; cols = rmap->cols;
+  } else {
+    const ssk_mat *g = dst ? dst : dst_mask;
+    SSK_REQUIRE(g, "remap: no output requested");
+    rows = g->rows; cols = g->cols;
+  }
+  const MapCoef mc = t ? make_mapcoef(*t) : MapCoef();
+  if (dst) {
+    if (int e = check_mat(src, "remap src")) return e;
+    if (int e = check_mat(dst, "remap dst")) return e;
+    SSK_REQUIRE(type_depth(src->type) == SSK_32F && dst->type == src->type, "remap: CV_32F source and destination of the same type");
+    SSK_REQUIRE(dst->rows == rows && dst->cols == cols, "remap: dst size must equal the map size");
+    Img sim;
+    if (int e = to_device(src, st_src, s, &sim, 0)) return e;
+    const size_t rowb = (size_t)cols * sim.cn * 4;
+    RemapArgs a = {};
+    a.src = sim; a.rows = rows; a.cols = cols; a.map = mc; a.rmap = d_rmap; a.rmap_step = rmap_step;
+    a.interp = interp; a.border = border;
+    for (int i = 0; i < 4; ++i) a.bval[i] = bv ? (float)bv[i] : 0.f;
+    if (dst->mem == SSK_MEM_DEVICE) {
+      a.dst = static_cast<float *>(dst->data); a.dst_step = dst->step;
+      if (int e = launch_remap(a, tab, s)) return e;
+    } else {
+      if (int e = st_out.ensure(rowb * rows)) return e;
+      if (border == SSK_BORDER_TRANSPARENT)   // dst content is an input in this mode
+        SSK_CUDA(cudaMemcpy2DAsync(st_out.p, rowb, dst->data, dst->step, rowb, rows, cudaMemcpyHostToDevice, s));
+      a.dst = st_out.as<float>(); a.dst_step = (int64_t)rowb;
+      if (int e = launch_remap(a, tab, s)) return e;
+      if (int e = from_device(st_out.p, rowb, rows, dst, s)) return e;
+    }
+  }
+  if (dst_mask) {
+    if (int e = check_mat(dst_mask, "remap dst_mask")) return e;
+    SSK_REQUIRE(dst_mask->type == SSK_8UC1 && dst_mask->rows == rows && dst_mask->cols == cols, "remap: dst_mask must be CV_8UC1 of the map size");
+    RemapMaskArgs m = {};
+    Img mim = {};
+    if (src_mask) {
+      if (int e = check_mat(src_mask, "remap src_mask")) return e;
+      SSK_REQUIRE(src_mask->type == SSK_8UC1, "remap: src_mask must be CV_8UC1");
+      if (int e = to_device(src_mask, st_mask, s, &mim, 0)) return e;
+      m.src_mask = static_cast<const uint8_t *>(mim.data); m.src_mask_step = mim.step;
+      m.src_rows = src_mask->rows; m.src_cols = src_mask->cols;
+    } else {
+      m.src_rows = src ? src->rows : rows; m.src_cols = src ? src->cols : cols;
+    }
+    if (int e = st_tmp.ensure((size_t)rows * cols * 2)) return e;
+    m.tmp = st_tmp.as<uint8_t>();
+    uint8_t *dense = st_tmp.as<uint8_t>() + (size_t)rows * cols;
+    m.rows = rows; m.cols = cols; m.map = mc; m.rmap = d_rmap; m.rmap_step = rmap_step; m.interp = interp;
+    if (dst_mask->mem == SSK_MEM_DEVICE) { m.dst = static_cast<uint8_t *>(dst_mask->data); m.dst_step = dst_mask->step; }
+    else { m.dst = dense; m.dst_step = cols; }
+    if (int e = launch_remap_mask(m, tab, s)) return e;
+    if (dst_mask->mem != SSK_MEM_DEVICE)
+      if (int e = from_device(dense, (size_t)cols, rows, dst_mask, s)) return e;
+  }
+  SSK_CUDA(cudaStreamSynchronize(s));
+  return SSK_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// handle types
+// ------------------------------------------------------------------------------------------------
+
+extern "C" {
+
+void ssk_ecch_options_default(ssk_ecch_options *o) {
+  o->epsx = 1e-5; o->reference_smooth_sigma = 1; o->input_smooth_sigma = 1; o->update_step_scale = 1;
+  o->method = SSK_ECC_INVERSE_COMPOSITIONAL_LM; o->interpolation = SSK_INTER_LINEAR;
+  o->max_iterations = 50; o->minimum_image_size = 8; o->maxlevel = 0;
+}
+
+void ssk_registration_options_default(ssk_registration_options *o) {
+  memset(o, 0, sizeof(*o));
+  o->motion_type = SSK_MOTION_AFFINE;
+  o->interpolation = SSK_INTER_LINEAR;
+  o->border_mode = SSK_BORDER_REFLECT101;
+  o->ecc.scale = 0.5; o->ecc.eps = 0.2; o->ecc.min_rho = 0.8;
+  o->ecc.input_smooth_sigma = 1.0; o->ecc.reference_smooth_sigma = 1.0; o->ecc.update_step_scale = 1.5;
+  o->ecc.se_radius = 5; o->ecc.ecc_method = SSK_ECC_LM; o->ecc.max_iterations = 50;
+  o->ecc.ecch_max_level = 0; o->ecc.ecch_minimum_image_size = 16;
+  o->ecc.normalization_noise = 0.01; o->ecc.normalization_scale = 0;
+  o->ecc.ecch_estimate_translation_first = 1; o->ecc.replace_planetary_disk_with_mask = 0;
+  o->enable_ecc_registration = 0;   // reference default (c_frame_registration.h:133); callers of this path set it
+}
+
+int ssk_transform_init(ssk_transform *t, int motion_type) { return make_transform(t, motion_type); }
+int ssk_transform_scale(ssk_transform *t, double factor) { return host_scale_transform(t, factor); }
+
+int ssk_transform_create_remap(const ssk_transform *t, int rows, int cols, ssk_mat *rmap) {
+  if (int e = ensure_device()) return e;
+  if (int e = check_mat(rmap, "create_remap")) return e;
+  SSK_REQUIRE(rmap->type == SSK_32FC2 && rmap->rows == rows && rmap->cols == cols, "create_remap: rmap must be CV_32FC2 rows x cols");
+  Scratch &sc = scratch();
+  if (int e = sc.init()) return e;
+  if (int e = sc.a.ensure((size_t)rows * cols * 8)) return e;
+  if (int e = create_remap_dense(*t, rows, cols, sc.a.as<float2>(), sc.stream)) return e;
+  if (int e = from_device(sc.a.p, (size_t)cols * 8, rows, rmap, sc.stream)) return e;
+  SSK_CUDA(cudaStreamSynchronize(sc.stream));
+  return SSK_OK;
+}
+
+int ssk_remap(const ssk_transform *t, const ssk_mat *rmap, const ssk_mat *src, ssk_mat *dst, const ssk_mat *src_mask,
+              ssk_mat *dst_mask, int interpolation, int border_mode, const double border_value[4]) {
+  if (int e = ensure_device()) return e;
+  Scratch &sc = scratch();
+  if (int e = sc.init()) return e;
+  return do_remap(sc.stream, sc.a, sc.b, sc.c, sc.d, sc.e, t, rmap, src, dst, src_mask, dst_mask, interpolation,
+                  border_mode, border_value);
+}
+
+// ---- c_ecch ------------------------------------------------------------------------------------
+int ssk_ecch_create(const ssk_ecch_options *opts, ssk_ecch **out) {
+  if (int e = ensure_device()) return e;
+  SSK_REQUIRE(opts && out, "ssk_ecch_create: null argument");
+  ssk_ecch *h = new (std::nothrow) ssk_ecch();
+  SSK_REQUIRE(h, "out of memory");
+  cudaError_t ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (ce != cudaSuccess) { delete h; return cuda_fail(ce, "cudaStreamCreate", __FILE__, __LINE__); }
+  h->e.init(*opts, h->stream);
+  *out = h;
+  return SSK_OK;
+}
+
+int ssk_ecch_destroy(ssk_ecch *h) { delete h; return SSK_OK; }
+
+static int ecch_image_to_gray(ssk_ecch *h, const ssk_mat *image, float *d_dst) {
+  // ecc_convert_input_image (ecc2.cc:345-382): convertTo(CV_32F) without scaling; colour -> cvtColor(BGR2GRAY)
+  Img im;
+  if (int e = to_device(image, h->staging, h->stream, &im, 0)) return e;
+  im.scale = 1.f;
+  SSK_REQUIRE(im.cn == 1 || im.cn == 3, "c_ecch: 1 or 3 channel images");
+  return launch_to_gray(im, nullptr, d_dst, nullptr, 1, h->stream);
+}
+
+int ssk_ecch_set_reference_image(ssk_ecch *h, const ssk_mat *image, const ssk_mat *mask) {
+  SSK_REQUIRE(h, "null handle");
+  if (int e = check_mat(image, "c_ecch::set_reference_image")) return e;
+  SSK_REQUIRE(!mask, "c_ecch: reference masks are not implemented yet");
+  if (int e = h->d_ptr.ensure((size_t)image->rows * image->cols * 4)) return e;
+  if (int e = ecch_image_to_gray(h, image, h->d_ptr.as<float>())) return e;
+  if (int e = h->e.set_reference(h->d_ptr.as<float>(), image->rows, image->cols)) return e;
+  SSK_CUDA(cudaStreamSynchronize(h->stream));
+  return SSK_OK;
+}
+
+int ssk_ecch_align(ssk_ecch *h, const ssk_mat *image, const ssk_mat *mask, ssk_transform *t, ssk_ecc_status *status) {
+  SSK_REQUIRE(h && t, "null argument");
+  SSK_REQUIRE(h->e.have_reference, "c_ecch: no reference image was set");
+  if (int e = check_mat(image, "c_ecch::align")) return e;
+  SSK_REQUIRE(!mask, "c_ecch: current masks are not implemented yet");
+  SSK_REQUIRE(image->rows == h->e.lh[0] && image->cols == h->e.lw[0], "c_ecch: current image size differs from the reference image size");
+  if (int e = h->e.reserve(1)) return e;
+  if (int e = ecch_image_to_gray(h, image, h->e.level0_scratch(0))) return e;
+  if (int e = h->e.prepare_current(h->e.level0_scratch_ptrs(), 1)) return e;
+  h->e.translation_first = 0; h->e.check_rho = 0; h->e.final_scale = 1.0;
+  if (int e = h->e.align(1, *t)) return e;
+  if (int e = h->e.download_frames(1)) return e;
+  SSK_CUDA(cudaStreamSynchronize(h->stream));
+  const EccFrame &f = h->e.host_frames()[0];
+  *t = f.t;
+  fill_status(f, h->e, status);
+  return SSK_OK;
+}
+
+int ssk_ecch_num_levels(const ssk_ecch *h) { return h ? h->e.nlevels : 0; }
+
+int ssk_ecch_level_size(const ssk_ecch *h, int level, int *cols, int *rows) {
+  SSK_REQUIRE(h && level >= 0 && level < h->e.nlevels, "c_ecch: bad level");
+  *cols = h->e.lw[level]; *rows = h->e.lh[level];
+  return SSK_OK;
+}
+
+int ssk_ecch_get_image(const ssk_ecch *h, int which, int level, ssk_mat *dst) {
+  SSK_REQUIRE(h && level >= 0 && level < h->e.nlevels, "c_ecch: bad level");
+  if (int e = check_mat(dst, "c_ecch::get_image")) return e;
+  SSK_REQUIRE(dst->type == SSK_32FC1 && dst->rows == h->e.lh[level] && dst->cols == h->e.lw[level], "c_ecch::get_image: dst must be CV_32FC1 of the level size");
+  SSK_REQUIRE(which == 0 || h->e.capacity > 0, "c_ecch: no current image");
+  const float *src = which == 0 ? h->e.reference_level(level) : h->e.current_level(0, level);
+  if (int e = from_device(src, (size_t)h->e.lw[level] * 4, h->e.lh[level], dst, h->stream)) return e;
+  SSK_CUDA(cudaStreamSynchronize(h->stream));
+  return SSK_OK;
+}
+
+// ---- c_frame_registration ----------------------------------------------------------------------
+int ssk_reg_create(const ssk_registration_options *opts, ssk_reg **out) {
+  if (int e = ensure_device()) return e;
+  SSK_REQUIRE(opts && out, "ssk_reg_create: null argument");
+  ssk_reg *h = new (std::nothrow) ssk_reg();
+  SSK_REQUIRE(h, "out of memory");
+  cudaStream_t s;
+  cudaError_t ce = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+  if (ce != cudaSuccess) { delete h; return cuda_fail(ce, "cudaStreamCreate", __FILE__, __LINE__); }
+  if (int e = h->r.init(*opts, s, true)) { delete h; return e; }
+  *out = h;
+  return SSK_OK;
+}
+
+int ssk_reg_destroy(ssk_reg *h) { delete h; return SSK_OK; }
+
+int ssk_reg_setup_reference_frame(ssk_reg *h, const ssk_mat *image, const ssk_mat *mask, int bpp) {
+  SSK_REQUIRE(h, "null handle");
+  if (int e = check_mat(image, "setup_reference_frame")) return e;
+  SSK_REQUIRE(!mask, "c_frame_registration: reference masks are not implemented yet");
+  Img im;
+  if (int e = to_device(image, h->staging, h->r.stream, &im, bpp)) return e;
+  SSK_REQUIRE(im.cn == 1 || im.cn == 3, "c_frame_registration: 1 or 3 channel frames");
+  if (int e = h->r.setup_reference(im)) return e;
+  SSK_CUDA(cudaStreamSynchronize(h->r.stream));
+  return SSK_OK;
+}
+
+int ssk_reg_register_frame(ssk_reg *h, const ssk_mat *image, const ssk_mat *mask, int bpp, ssk_transform *t_out,
+                           ssk_ecc_status *status) {
+  SSK_REQUIRE(h, "null handle");
+  if (int e = check_mat(image, "register_frame")) return e;
+  SSK_REQUIRE(!mask, "c_frame_registration: current masks are not implemented yet");
+  Img im;
+  if (int e = to_device(image, h->staging, h->r.stream, &im, bpp)) return e;
+  if (int e = h->d_ptr.ensure(sizeof(void *))) return e;
+  const void *p = im.data;
+  SSK_CUDA(cudaMemcpyAsync(h->d_ptr.p, &p, sizeof(p), cudaMemcpyHostToDevice, h->r.stream));
+  SSK_CUDA(cudaStreamSynchronize(h->r.stream));   // &p is a stack variable
+  if (int e = h->r.prepare(im, h->d_ptr.as<const void *>(), 1)) return e;
+  if (int e = h->r.register_batch(1)) return e;
+  if (int e = h->r.ecch.download_frames(1)) return e;
+  SSK_CUDA(cudaStreamSynchronize(h->r.stream));
+  const EccFrame &f = h->r.ecch.host_frames()[0];
+  h->r.current = f.t;
+  h->r.have_current = f.ok != 0;
+  if (t_out) *t_out = f.t;
+  fill_status(f, h->r.ecch, status);
+  if (!f.ok) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "Poor image correlation after align : rho = %g / %g", f.rho, h->r.opts.ecc.min_rho);
+    set_error(buf);
+    return SSK_ERR_NOT_REGISTERED;
+  }
+  return SSK_OK;
+}
+
+int ssk_reg_get_current_remap(ssk_reg *h, ssk_mat *rmap) {
+  SSK_REQUIRE(h && h->r.have_current, "c_frame_registration: no registered frame");
+  return ssk_transform_create_remap(&h->r.current, h->r.ref_rows, h->r.ref_cols, rmap);
+}
+
+int ssk_reg_remap(ssk_reg *h, const ssk_mat *rmap, const ssk_mat *src, ssk_mat *dst, const ssk_mat *src_mask,
+                  ssk_mat *dst_mask, int interpolation, int border_mode, const double border_value[4]) {
+  SSK_REQUIRE(h, "null handle");
+  SSK_REQUIRE(rmap || h->r.have_current, "c_frame_registration::remap: no current transform");
+  // c_frame_registration.cc:1299-1309
+  if (interpolation < 0) interpolation = h->r.opts.interpolation;
+  const double *bv = border_value;
+  if (border_mode < 0) { border_mode = h->r.opts.border_mode; bv = h->r.opts.border_value; }
+  return do_remap(h->r.stream, h->staging, h->st_map, h->st_mask, h->st_out, h->st_tmp, rmap ? nullptr : &h->r.current, rmap,
+                  src, dst, src_mask, dst_mask, interpolation, border_mode, bv);
+}
+
+// ---- c_frame_accumulation ----------------------------------------------------------------------
+int ssk_acc_create(int kind, ssk_acc **out) {
+  if (int e = ensure_device()) return e;
+  SSK_REQUIRE(out && (kind == SSK_ACC_WEIGHTED_AVERAGE || kind == SSK_ACC_BAYER_AVERAGE), "ssk_acc_create: bad kind");
+  ssk_acc *h = new (std::nothrow) ssk_acc();
+  SSK_REQUIRE(h, "out of memory");
+  h->a.kind = kind;
+  cudaError_t ce = cudaStreamCreateWithFlags(&h->a.stream, cudaStreamNonBlocking);
+  if (ce != cudaSuccess) { delete h; return cuda_fail(ce, "cudaStreamCreate", __FILE__, __LINE__); }
+  h->a.own_stream = true;
+  *out = h;
+  return SSK_OK;
+}
+
+int ssk_acc_destroy(ssk_acc *h) { delete h; return SSK_OK; }
+int ssk_acc_clear(ssk_acc *h) { SSK_REQUIRE(h, "null handle"); return h->a.clear(); }
+
+int ssk_acc_add(ssk_acc *h, const ssk_mat *src, const ssk_mat *weights, int bpp) {
+  SSK_REQUIRE(h, "null handle");
+  Acc &a = h->a;
+  if (int e = check_mat(src, "c_frame_accumulation::add")) return e;
+  Img im;
+  if (int e = to_device(src, a.staging, a.stream, &im, bpp)) return e;
+  int wtype = -1;
+  Img wim = {};
+  if (weights) {
+    if (int e = check_mat(weights, "c_frame_accumulation::add weights")) return e;
+    SSK_REQUIRE(weights->rows == src->rows && weights->cols == src->cols, "frame accumulation: image and weights sizes not match");
+    SSK_REQUIRE(weights->type == SSK_8UC1 || weights->type == SSK_32FC1, "frame accumulation: weights must be CV_8UC1 or CV_32FC1");
+    wtype = weights->type;
+    if (int e = to_device(weights, a.wstaging, a.stream, &wim, 0)) return e;
+  }
+  if (a.kind == SSK_ACC_BAYER_AVERAGE) {
+    SSK_REQUIRE(im.cn == 1, "c_bayer_average: single channel raw frames");
+    if (int e = a.ensure(im.rows, im.cols, 3)) return e;
+    BayerAccArgs b = {};
+    b.src = im; b.have_map = a.have_map ? 1 : 0;
+    if (a.have_map) {
+      if (a.rmap_explicit) { b.rmap = a.rmap.as<float2>(); b.rmap_step = (int64_t)im.cols * 8; }
+      else b.map = make_mapcoef(a.map_t);
+    }
+    b.weights = wim.data; b.w_step = wim.step; b.wtype = wtype; b.colorid = a.colorid;
+    b.acc = a.acc.as<float>(); b.cntr = a.wacc.as<float>();
+    if (int e = launch_bayer_add(b, a.stream)) return e;
+  } else {
+    if (int e = a.ensure(im.rows, im.cols, im.cn)) return e;
+    AccAddArgs x = {};
+    x.src = im; x.weights = wim.data; x.w_step = wim.step; x.wtype = wtype;
+    x.acc = a.acc.as<float>(); x.wacc = a.wacc.as<float>();
+    if (int e = launch_acc_add(x, a.stream)) return e;
+  }
+  ++a.frames;
+  SSK_CUDA(cudaStreamSynchronize(a.stream));   // the caller's host buffers are free again
+  return SSK_OK;
+}
+
+int ssk_acc_compute(ssk_acc *h, ssk_mat *avg, ssk_mat *mask, double dscale) {
+  SSK_REQUIRE(h, "null handle");
+  Acc &a = h->a;
+  if (a.frames < 1) { set_error("c_frame_accumulation::compute: no accumulated frames"); return SSK_ERR_STATE; }
+  const int ocn = a.kind == SSK_ACC_BAYER_AVERAGE ? 3 : a.cn;
+  const size_t rowb = (size_t)a.cols * ocn * 4;
+  if (avg) {
+    if (int e = check_mat(avg, "compute avg")) return e;
+    SSK_REQUIRE(type_depth(avg->type) == SSK_32F && type_cn(avg->type) == ocn && avg->rows == a.rows && avg->cols == a.cols,
+                "compute: avg must be CV_32F with the accumulator's size and channels");
+  }
+  if (mask) {
+    if (int e = check_mat(mask, "compute mask")) return e;
+    SSK_REQUIRE(mask->type == SSK_8UC1 && mask->rows == a.rows && mask->cols == a.cols, "compute: mask must be CV_8UC1 of the accumulator size");
+  }
+  if (int e = a.out_staging.ensure(rowb * a.rows + (size_t)a.rows * a.cols)) return e;
+  float *d_avg = a.out_staging.as<float>();
+  uint8_t *d_mask = reinterpret_cast<uint8_t *>(a.out_staging.as<char>() + rowb * a.rows);
+  if (a.kind == SSK_ACC_BAYER_AVERAGE) {
+    if (int e = launch_bayer_compute(a.acc.as<float>(), a.wacc.as<float>(), a.rows, a.cols, avg ? d_avg : nullptr, (int64_t)rowb,
+                                     mask ? d_mask : nullptr, a.cols, a.stream)) return e;
+  } else {
+    if (int e = launch_acc_compute(a.acc.as<float>(), a.wacc.as<float>(), a.rows, a.cols, a.cn, (float)dscale, avg ? d_avg : nullptr,
+                                   (int64_t)rowb, mask ? d_mask : nullptr, a.cols, a.stream)) return e;
+  }
+  if (avg) if (int e = from_device(d_avg, rowb, a.rows, avg, a.stream)) return e;
+  if (mask) if (int e = from_device(d_mask, (size_t)a.cols, a.rows, mask, a.stream)) return e;
+  SSK_CUDA(cudaStreamSynchronize(a.stream));
+  return SSK_OK;
+}
+
+int ssk_acc_get_counters(ssk_acc *h, ssk_mat *accw) {
+  SSK_REQUIRE(h, "null handle");
+  Acc &a = h->a;
+  SSK_REQUIRE(a.wacc.p, "get_acc_counters: empty accumulator");
+  if (int e = check_mat(accw, "get_acc_counters")) return e;
+  const int wcn = a.kind == SSK_ACC_BAYER_AVERAGE ? 3 : 1;
+  SSK_REQUIRE(type_depth(accw->type) == SSK_32F && type_cn(accw->type) == wcn && accw->rows == a.rows && accw->cols == a.cols,
+              "get_acc_counters: CV_32F buffer of the accumulator size (3 channels for bayer)");
+  // note: c_bayer_average::get_acc_counters scales G by 0.5 (c_frame_accumulation.cc:1240-1250); raw counters are returned here
+  if (int e = from_device(a.wacc.p, (size_t)a.cols * wcn * 4, a.rows, accw, a.stream)) return e;
+  SSK_CUDA(cudaStreamSynchronize(a.stream));
+  return SSK_OK;
+}
+
+int ssk_acc_reinitialize(ssk_acc *h, const ssk_mat *src, const ssk_mat *accw) {
+  SSK_REQUIRE(h, "null handle");
+  Acc &a = h->a;
+  SSK_REQUIRE(a.kind == SSK_ACC_WEIGHTED_AVERAGE, "c_bayer_average::reinitialize returns false in the reference");
+  if (int e = check_mat(src, "reinitialize src")) return e;
+  if (int e = check_mat(accw, "reinitialize accw")) return e;
+  SSK_REQUIRE(type_depth(src->type) == SSK_32F && accw->type == SSK_32FC1 && accw->rows == src->rows && accw->cols == src->cols,
+              "reinitialize: CV_32F image and CV_32FC1 weights of the same size");
+  a.clear();
+  if (int e = a.ensure(src->rows, src->cols, type_cn(src->type))) return e;
+  const size_t rowb = (size_t)src->cols * a.cn * 4;
+  const cudaMemcpyKind k1 = src->mem == SSK_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  const cudaMemcpyKind k2 = accw->mem == SSK_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  SSK_CUDA(cudaMemcpy2DAsync(a.acc.p, rowb, src->data, src->step, rowb, src->rows, k1, a.stream));
+  SSK_CUDA(cudaMemcpy2DAsync(a.wacc.p, (size_t)src->cols * 4, accw->data, accw->step, (size_t)src->cols * 4, src->rows, k2, a.stream));
+  SSK_CUDA(cudaStreamSynchronize(a.stream));
+  a.frames = 1;
+  return SSK_OK;
+}
+
+int ssk_acc_size(const ssk_acc *h, int *cols, int *rows, int *channels) {
+  SSK_REQUIRE(h, "null handle");
+  if (cols) *cols = h->a.cols;
+  if (rows) *rows = h->a.rows;
+  if (channels) *channels = h->a.kind == SSK_ACC_BAYER_AVERAGE && h->a.rows ? 3 : h->a.cn;
+  return SSK_OK;
+}
+
+int ssk_acc_frames(const ssk_acc *h) { return h ? h->a.frames : 0; }
+
+int ssk_acc_set_bayer_pattern(ssk_acc *h, int colorid) {
+  SSK_REQUIRE(h, "null handle");
+  SSK_REQUIRE(colorid >= SSK_COLORID_BAYER_RGGB && colorid <= SSK_COLORID_BAYER_BGGR, "set_bayer_pattern: RGGB/GRBG/GBRG/BGGR");
+  h->a.colorid = colorid;
+  return SSK_OK;
+}
+
+int ssk_acc_set_remap(ssk_acc *h, const ssk_transform *t, const ssk_mat *rmap) {
+  SSK_REQUIRE(h, "null handle");
+  Acc &a = h->a;
+  if (!t && !rmap) { a.have_map = false; a.rmap_explicit = false; return SSK_OK; }
+  if (rmap) {
+    if (int e = check_mat(rmap, "set_remap")) return e;
+    SSK_REQUIRE(rmap->type == SSK_32FC2, "set_remap: CV_32FC2 map");
+    const size_t rowb = (size_t)rmap->cols * 8;
+    if (int e = a.rmap.ensure(rowb * rmap->rows)) return e;
+    SSK_CUDA(cudaMemcpy2DAsync(a.rmap.p, rowb, rmap->data, rmap->step, rowb, rmap->rows,
+                               rmap->mem == SSK_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, a.stream));
+    SSK_CUDA(cudaStreamSynchronize(a.stream));
+    a.rmap_explicit = true;
+  } else {
+    a.map_t = *t;
+    a.rmap_explicit = false;
+  }
+  a.have_map = true;
+  return SSK_OK;
+}
+
+int ssk_acc_device_state(ssk_acc *h, void **acc, void **weights, int64_t *acc_bytes, int64_t *weights_bytes) {
+  SSK_REQUIRE(h && h->a.acc.p, "device_state: empty accumulator");
+  Acc &a = h->a;
+  const int64_t npix = (int64_t)a.rows * a.cols;
+  if (acc) *acc = a.acc.p;
+  if (weights) *weights = a.wacc.p;
+  if (acc_bytes) *acc_bytes = npix * (a.kind == SSK_ACC_BAYER_AVERAGE ? 3 : a.cn) * 4;
+  if (weights_bytes) *weights_bytes = npix * (a.kind == SSK_ACC_BAYER_AVERAGE ? 3 : 1) * 4;
+  return SSK_OK;
+}
+
+int ssk_acc_to_sum_form(ssk_acc *h) {
+  SSK_REQUIRE(h && h->a.acc.p, "to_sum_form: empty accumulator");
+  Acc &a = h->a;
+  if (a.kind == SSK_ACC_BAYER_AVERAGE) return SSK_OK;   // already sums
+  if (int e = launch_acc_sum_form(a.acc.as<float>(), a.wacc.as<float>(), (int64_t)a.rows * a.cols, a.cn, 1, a.stream)) return e;
+  SSK_CUDA(cudaStreamSynchronize(a.stream));
+  return SSK_OK;
+}
+
+int ssk_acc_from_sum_form(ssk_acc *h, int accumulated_frames) {
+  SSK_REQUIRE(h && h->a.acc.p, "from_sum_form: empty accumulator");
+  Acc &a = h->a;
+  if (a.kind != SSK_ACC_BAYER_AVERAGE) {
+    if (int e = launch_acc_sum_form(a.acc.as<float>(), a.wacc.as<float>(), (int64_t)a.rows * a.cols, a.cn, 0, a.stream)) return e;
+    SSK_CUDA(cudaStreamSynchronize(a.stream));
+  }
+  a.frames = accumulated_frames;
+  return SSK_OK;
+}
+
+// ---- weight maps ---------------------------------------------------------------------------------
+int ssk_local_variance_map(const ssk_mat *image, int bpp, int dscale, int kradius, int uscale, ssk_mat *map, double *Q) {
+  if (int e = ensure_device()) return e;
+  if (int e = check_mat(image, "compute_local_variance_map")) return e;
+  SSK_REQUIRE(uscale == 0, "compute_local_variance_map: uscale > 0 (INTER_AREA stage) is not implemented");
+  SSK_REQUIRE(dscale >= 0 && dscale <= 6, "compute_local_variance_map: dscale 0..6");
+  if (map) {
+    if (int e = check_mat(map, "compute_local_variance_map map")) return e;
+    SSK_REQUIRE(map->type == SSK_32FC1 && map->rows == image->rows && map->cols == image->cols, "map must be CV_32FC1 of the image size");
+  }
+  Scratch &sc = scratch();
+  if (int e = sc.init()) return e;
+  cudaStream_t s = sc.stream;
+  Img im;
+  if (int e = to_device(image, sc.a, s, &im, bpp)) return e;
+  SSK_REQUIRE(im.cn == 1 || im.cn == 3, "compute_local_variance_map: 1 or 3 channels");
+  // pdownscale (c_local_variance_sharpness_measure.cc:28-52)
+  const size_t n = (size_t)im.rows * im.cols;
+  if (int e = sc.b.ensure(n * 4 * 2)) return e;
+  float *bufA = sc.b.as<float>(), *bufB = bufA + n;
+  int r = im.rows, c = im.cols;
+  const float *M = nullptr;
+  if (dscale > 0 && std::min(r, c) >= 4) {
+    Img cur = im;
+    float *dst = bufA;
+    for (int l = 0; l < dscale; ++l) {
+      const int nr = (cur.rows + 1) / 2, nc = (cur.cols + 1) / 2;
+      PyrDownArgs pd = {};
+      pd.src = cur; pd.dst = dst; pd.dst_rows = nr; pd.dst_cols = nc; pd.batch = 1; pd.post_scale = 1.f;
+      if (int e = launch_pyrdown(pd, s)) return e;
+      cur.data = dst; cur.step = (int64_t)nc * 4; cur.rows = nr; cur.cols = nc; cur.depth = SSK_32F; cur.cn = 1; cur.scale = 1.f;
+      M = dst;
+      dst = dst == bufA ? bufB : bufA;
+      if (std::min(nr, nc) < 4) break;
+    }
+    r = cur.rows; c = cur.cols;
+  } else {
+    if (int e = launch_to_gray(im, nullptr, bufA, nullptr, 1, s)) return e;
+    M = bufA;
+  }
+  const int nb = w1_num_blocks(r, c);
+  if (int e = sc.c.ensure((size_t)r * c * 4)) return e;
+  if (int e = sc.d.ensure((size_t)nb * 2 * 8 + 4 * 8)) return e;
+  if (int e = sc.e.ensure(n * 4)) return e;
+  W1Args w = {};
+  w.M = M; w.rows = r; w.cols = c; w.kradius = std::max(1, kradius); w.depth_scale = 20.0;
+  w.gmap = sc.c.as<float>(); w.partials = sc.d.as<double>(); w.stats = sc.d.as<double>() + (size_t)nb * 2;
+  w.out = map ? sc.e.as<float>() : nullptr; w.full_rows = im.rows; w.full_cols = im.cols; w.batch = 1;
+  if (int e = launch_w1(w, s)) return e;
+  double stats[4];
+  SSK_CUDA(cudaMemcpyAsync(stats, w.stats, sizeof(stats), cudaMemcpyDeviceToHost, s));
+  if (map) if (int e = from_device(sc.e.p, (size_t)im.cols * 4, im.rows, map, s)) return e;
+  SSK_CUDA(cudaStreamSynchronize(s));
+  if (Q) *Q = stats[2];
+  if (!(stats[0] > 0)) { set_error("compute_local_variance_map: flat image (sum of gradients is zero), map released"); return SSK_ERR_STATE; }
+  return SSK_OK;
+}
+
+}  // extern "C"

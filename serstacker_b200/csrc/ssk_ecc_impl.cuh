@@ -1,0 +1,970 @@
+// K2/K3/K4: persistent, cluster-per-frame ECC registration.
+//
+// One thread-block cluster owns one frame and runs its complete coarse-to-fine alignment on the device:
+// every pyramid level, every Gauss-Newton / Levenberg-Marquardt iteration, the optional translation-first
+// pass and the correlation gate.  Per trial there is exactly ONE fused pass over the level (warp + residual
+// [+ warped-image gradient] + steepest-descent images + all normal-equation sums), one cluster barrier, a
+// DSMEM reduction in fixed order (deterministic) and a scalar solver step that every CTA of the cluster
+// executes redundantly in double precision, so no broadcast is needed.
+//
+// Reference semantics reproduced here (core/proc/image_registration/):
+//   c_ecch::align                               ecc2.cc:1133-1176
+//   c_ecc_forward_additive::align               ecc2.cc:1247-1365
+//   c_ecclm::align / compute_jac / compute_rhs  ecc2.cc:1444-1650
+//   c_ecc_inverse_compositional::align          ecc2.cc:1693-1788
+//   c_ecclm_inverse_compositional::align        ecc2.cc:1894-2086
+//   ecc_differentiate                           ecc2.cc:142-169
+//   compute_correlation                         ecc2.cc:65-137
+//   c_image_transform::{scale_transfrom, eps, invert_and_compose, create_steepest_descent_images}
+//                                               c_image_transform.cc / c_image_transform.h (per type)
+//   c_frame_registration::register_frame flow   c_frame_registration.cc:797-872
+#pragma once
+#include "ssk_ecc.cuh"
+#include <cooperative_groups.h>
+#include <float.h>
+
+namespace cg = cooperative_groups;
+
+namespace ssk {
+
+namespace {
+
+constexpr int NT = 512;
+constexpr int NW = NT / 32;
+constexpr int NSMAX = 72;
+constexpr int FT_W = 32, FT_H = 16;          // stencil tile of the forward methods (one pixel per thread)
+constexpr int FT_IW = FT_W + 4, FT_IH = FT_H + 4;
+
+template <int TYPE> struct NParams;
+template <> struct NParams<SSK_MOTION_TRANSLATION> { static constexpr int M = 2; };
+template <> struct NParams<SSK_MOTION_EUCLIDEAN> { static constexpr int M = 3; };
+template <> struct NParams<SSK_MOTION_SCALED_EUCLIDEAN> { static constexpr int M = 4; };
+template <> struct NParams<SSK_MOTION_AFFINE> { static constexpr int M = 6; };
+template <> struct NParams<SSK_MOTION_HOMOGRAPHY> { static constexpr int M = 8; };
+
+__host__ __device__ inline int nparams_of(int type) {
+  switch (type) {
+    case SSK_MOTION_TRANSLATION: return 2;
+    case SSK_MOTION_EUCLIDEAN: return 3;
+    case SSK_MOTION_SCALED_EUCLIDEAN: return 4;
+    case SSK_MOTION_AFFINE: return 6;
+    default: return 8;
+  }
+}
+
+// coefficients the steepest-descent images are evaluated with
+struct JCoef { float c[8]; };
+
+struct Shared {
+  double part[2][NSMAX];      // this CTA's partial sums (double buffered; peers read them through DSMEM)
+  double tot[NSMAX];          // cluster totals
+  double wpart[NW][NSMAX];
+  float gw[FT_IH][FT_IW + 1]; // warped-image tile of the forward methods
+  // ---- solver state: identical in every CTA of the cluster ----
+  ssk_transform t;            // transform being estimated (accepted parameters)
+  ssk_transform tq;           // parameters of the next pass
+  ssk_transform tmain;        // main transform parked during the translation-first pass
+  MapCoef map;                // map coefficients of tq
+  JCoef jc;                   // steepest-descent coefficients
+  float Hp[64];               // reference-side / current normal matrix (float, like cv::Mat1f)
+  float v[8];                 // projected error (float)
+  float vtrial[8];
+  float Htrial[64];
+  float deltap[8];
+  double err, newerr, lambda, dp, rmsold, eps;
+  int num_it, recompute, brk, converged, failed, level_ok, cont;
+  int total_iterations;
+  double rho;
+};
+
+struct Ctx {
+  const EccConfig *cfg;
+  const EccFrame *frame;
+  Shared *S;
+  int rank, csize, tid;
+  int buf;
+};
+
+// ------------------------------------------------------------------------------------------------
+// scalar parameter algebra (thread 0 of every CTA)
+// ------------------------------------------------------------------------------------------------
+__device__ void xf_scale(ssk_transform &t, double f) {
+  switch (t.motion_type) {
+    case SSK_MOTION_TRANSLATION:                       // c_image_transform.cc:130-134
+      t.params[0] = (float)(t.params[0] * f); t.params[1] = (float)(t.params[1] * f);
+      break;
+    case SSK_MOTION_EUCLIDEAN:
+    case SSK_MOTION_SCALED_EUCLIDEAN:                  // c_image_transform.cc:502-507 (T and C)
+      t.params[0] = (float)(t.params[0] * f); t.params[1] = (float)(t.params[1] * f);
+      t.aux[0] = (float)(t.aux[0] * f); t.aux[1] = (float)(t.aux[1] * f);
+      break;
+    case SSK_MOTION_AFFINE:                            // c_image_transform.cc:911-915
+      t.params[2] = (float)(t.params[2] * f); t.params[5] = (float)(t.params[5] * f);
+      break;
+    default:                                           // c_image_transform.cc:1186-1194
+      t.params[2] = (float)(t.params[2] * f); t.params[5] = (float)(t.params[5] * f);
+      t.params[6] = (float)(t.params[6] / f); t.params[7] = (float)(t.params[7] / f);
+      break;
+  }
+}
+
+__device__ void xf_get_translation(const ssk_transform &t, float &tx, float &ty) {
+  switch (t.motion_type) {
+    case SSK_MOTION_AFFINE: tx = t.params[2]; ty = t.params[5]; break;
+    case SSK_MOTION_HOMOGRAPHY: tx = t.params[2] / t.aux[2]; ty = t.params[5] / t.aux[2]; break;
+    default: tx = t.params[0]; ty = t.params[1]; break;
+  }
+}
+
+__device__ void xf_set_translation(ssk_transform &t, float tx, float ty) {
+  switch (t.motion_type) {
+    case SSK_MOTION_AFFINE: t.params[2] = tx; t.params[5] = ty; break;
+    case SSK_MOTION_HOMOGRAPHY: t.params[2] = tx * t.aux[2]; t.params[5] = ty * t.aux[2]; break;
+    default: t.params[0] = tx; t.params[1] = ty; break;
+  }
+}
+
+__device__ inline float sqf(float x) { return x * x; }
+
+// c_image_transform::eps(dp, size)
+__device__ double xf_eps(int type, const float *dp, int w, int h, float fixed_scale = 1.0f) {
+  switch (type) {
+    case SSK_MOTION_TRANSLATION:                       // c_image_transform.cc:136-139
+      return sqrt((double)(dp[0] * dp[0] + dp[1] * dp[1]));
+    case SSK_MOTION_EUCLIDEAN:
+    case SSK_MOTION_SCALED_EUCLIDEAN: {                // c_image_transform.cc:509-523
+      const float da = dp[2], ds = type == SSK_MOTION_SCALED_EUCLIDEAN ? dp[3] : fixed_scale;  // fixed scale: get_parameters returns _scale
+      const float sa = (float)sin((double)da);
+      return (double)sqrtf(sqf(dp[0]) + sqf(dp[1]) + sqf(w * sa) + sqf(h * sa) + sqf((float)max(w, h) * ds));
+    }
+    case SSK_MOTION_AFFINE:                            // c_image_transform.cc:917-924
+      return (double)sqrtf(sqf(w * dp[0]) + sqf(h * dp[1]) + sqf(dp[2]) + sqf(w * dp[3]) + sqf(h * dp[4]) + sqf(dp[5]));
+    default:                                           // c_image_transform.cc:1196-1205
+      return (double)sqrtf(sqf(dp[2]) + sqf(dp[5]) + sqf(w * dp[0]) + sqf(h * dp[1]) + sqf(w * dp[3]) + sqf(h * dp[4]));
+  }
+}
+
+// cv::invertAffineTransform on float data (double arithmetic inside)
+__device__ void invert_affine(const float *M, float *iM) {
+  double D = (double)M[0] * M[4] - (double)M[1] * M[3];
+  D = D != 0 ? 1. / D : 0;
+  const double A11 = M[4] * D, A22 = M[0] * D, A12 = -M[1] * D, A21 = -M[3] * D;
+  const double b1 = -A11 * M[2] - A12 * M[5], b2 = -A21 * M[2] - A22 * M[5];
+  iM[0] = (float)A11; iM[1] = (float)A12; iM[2] = (float)b1;
+  iM[3] = (float)A21; iM[4] = (float)A22; iM[5] = (float)b2;
+}
+
+// 3x3 inverse: cofactors and determinant in double, result float (cv::invert closed form)
+__device__ void invert3x3(const float *a, float *b) {
+  const double a00 = a[0], a01 = a[1], a02 = a[2], a10 = a[3], a11 = a[4], a12 = a[5], a20 = a[6], a21 = a[7], a22 = a[8];
+  double d = a00 * (a11 * a22 - a12 * a21) - a01 * (a10 * a22 - a12 * a20) + a02 * (a10 * a21 - a11 * a20);
+  d = d != 0 ? 1. / d : 0;
+  b[0] = (float)((a11 * a22 - a12 * a21) * d); b[1] = (float)((a02 * a21 - a01 * a22) * d); b[2] = (float)((a01 * a12 - a02 * a11) * d);
+  b[3] = (float)((a12 * a20 - a10 * a22) * d); b[4] = (float)((a00 * a22 - a02 * a20) * d); b[5] = (float)((a02 * a10 - a00 * a12) * d);
+  b[6] = (float)((a10 * a21 - a11 * a20) * d); b[7] = (float)((a01 * a20 - a00 * a21) * d); b[8] = (float)((a00 * a11 - a01 * a10) * d);
+}
+
+__device__ void euclid_matrix(float tX, float tY, float ang, float scl, float cX, float cY, float *M /*2x3*/) {
+  // lambda at c_image_transform.cc:768-782
+  const float sa = (float)sin((double)ang), ca = (float)cos((double)ang);
+  M[0] = scl * ca; M[1] = -scl * sa; M[2] = tX - scl * ca * cX + scl * sa * cY;
+  M[3] = scl * sa; M[4] = scl * ca;  M[5] = tY - scl * sa * cX - scl * ca * cY;
+}
+
+// newparams = transform->invert_and_compose(p, dp)
+__device__ void xf_invert_and_compose(const ssk_transform &t, const float *dp, float *out) {
+  switch (t.motion_type) {
+    case SSK_MOTION_TRANSLATION:                       // c_image_transform.h:164-167
+      out[0] = t.params[0] - dp[0]; out[1] = t.params[1] - dp[1];
+      break;
+    case SSK_MOTION_AFFINE: {                          // c_image_transform.h:312-318
+      float a[6], s[6];
+      invert_affine(t.params, a);
+      for (int i = 0; i < 6; ++i) s[i] = a[i] + dp[i];
+      invert_affine(s, out);
+      break;
+    }
+    case SSK_MOTION_HOMOGRAPHY: {                      // c_image_transform.h:379-384
+      float m[9], inv1[9], s[9], aii[9];
+      for (int i = 0; i < 8; ++i) m[i] = t.params[i];
+      m[8] = t.aux[2];
+      invert3x3(m, inv1);
+      for (int i = 0; i < 8; ++i) s[i] = inv1[i] + dp[i];
+      s[8] = inv1[8];
+      invert3x3(s, aii);
+      const float k = 1.0f / aii[8];
+      for (int i = 0; i < 8; ++i) out[i] = aii[i] * k;
+      break;
+    }
+    default: {                                         // c_image_transform.cc:736-833
+      const bool fix_scale = t.motion_type == SSK_MOTION_EUCLIDEAN;
+      const float Tx = t.params[0], Ty = t.params[1], angle = t.params[2];
+      const float scale = fix_scale ? t.aux[3] : t.params[3];
+      const float Cx = t.aux[0], Cy = t.aux[1];
+      const float scale_dp = fix_scale ? 1.0f : 1.0f + dp[3];
+      float Mp[6], Mdp[6], Mi[6];
+      euclid_matrix(Tx, Ty, angle, scale, Cx, Cy, Mp);
+      euclid_matrix(dp[0], dp[1], dp[2], scale_dp, Cx, Cy, Mdp);
+      invert_affine(Mdp, Mi);
+      // M_res = Mp * Mdp_inv (3x3 float product, last row 0 0 1)
+      const float m00 = Mp[0] * Mi[0] + Mp[1] * Mi[3];
+      const float m02 = Mp[0] * Mi[2] + Mp[1] * Mi[5] + Mp[2];
+      const float m10 = Mp[3] * Mi[0] + Mp[4] * Mi[3];
+      const float m12 = Mp[3] * Mi[2] + Mp[4] * Mi[5] + Mp[5];
+      const float rs = fix_scale ? scale : sqrtf(m00 * m00 + m10 * m10);
+      const float ra = (float)atan2((double)m10, (double)m00);
+      const float rca = (float)cos((double)ra), rsa = (float)sin((double)ra);
+      out[0] = m02 + rs * rca * Cx - rs * rsa * Cy;
+      out[1] = m12 + rs * rsa * Cx + rs * rca * Cy;
+      out[2] = ra;
+      if (!fix_scale) out[3] = rs;
+      break;
+    }
+  }
+}
+
+// Cholesky solve of the M x M float system in double; false (and x = 0) if not positive definite
+// (cv::solve(DECOMP_CHOLESKY) leaves dst zero-filled on failure).
+__device__ bool chol_solve(int M, const float *H, const float *b, float *x) {
+  double L[64], y[8];
+  for (int i = 0; i < M; ++i) {
+    for (int j = 0; j <= i; ++j) {
+      double s = H[i * M + j];
+      for (int k = 0; k < j; ++k) s -= L[i * M + k] * L[j * M + k];
+      if (i == j) {
+        if (!(s > 0)) { for (int q = 0; q < M; ++q) x[q] = 0.f; return false; }
+        L[i * M + i] = sqrt(s);
+      } else {
+        L[i * M + j] = s / L[j * M + j];
+      }
+    }
+  }
+  for (int i = 0; i < M; ++i) {
+    double s = b[i];
+    for (int k = 0; k < i; ++k) s -= L[i * M + k] * y[k];
+    y[i] = s / L[i * M + i];
+  }
+  for (int i = M - 1; i >= 0; --i) {
+    double s = y[i];
+    for (int k = i + 1; k < M; ++k) s -= L[k * M + i] * (double)x[k];
+    x[i] = (float)(s / L[i * M + i]);
+  }
+  return true;
+}
+
+__device__ void make_jcoef(const ssk_transform &t, JCoef &j) {
+  for (int i = 0; i < 8; ++i) j.c[i] = 0.f;
+  switch (t.motion_type) {
+    case SSK_MOTION_EUCLIDEAN:
+    case SSK_MOTION_SCALED_EUCLIDEAN:
+      j.c[0] = t.motion_type == SSK_MOTION_SCALED_EUCLIDEAN ? t.params[3] : t.aux[3];
+      j.c[1] = (float)cos((double)t.params[2]); j.c[2] = (float)sin((double)t.params[2]);
+      j.c[3] = t.aux[0]; j.c[4] = t.aux[1];
+      break;
+    case SSK_MOTION_HOMOGRAPHY:
+      for (int i = 0; i < 8; ++i) j.c[i] = t.params[i];
+      break;
+    default: break;
+  }
+}
+
+// c_image_transform::create_steepest_descent_images, one pixel
+template <int TYPE>
+__device__ __forceinline__ void eval_J(const JCoef &jc, float x, float y, float gx, float gy, float *J) {
+  if (TYPE == SSK_MOTION_TRANSLATION) {                // c_image_transform.cc:262-269
+    J[0] = gx; J[1] = gy;
+  } else if (TYPE == SSK_MOTION_AFFINE) {              // c_image_transform.cc:1054-1067
+    J[0] = gx * x; J[1] = gx * y; J[2] = gx; J[3] = gy * x; J[4] = gy * y; J[5] = gy;
+  } else if (TYPE == SSK_MOTION_HOMOGRAPHY) {          // c_image_transform.cc:1339-1363
+    const float den = 1.f / (x * jc.c[6] + y * jc.c[7] + 1.f);
+    const float hatX = -(x * jc.c[0] + y * jc.c[1] + jc.c[2]) * den;
+    const float hatY = -(x * jc.c[3] + y * jc.c[4] + jc.c[5]) * den;
+    const float ggx = gx * den, ggy = gy * den;
+    const float gg = hatX * ggx + hatY * ggy;
+    J[0] = ggx * x; J[1] = ggx * y; J[2] = ggx; J[3] = ggy * x; J[4] = ggy * y; J[5] = ggy; J[6] = gg * x; J[7] = gg * y;
+  } else {                                             // c_image_transform.cc:636-665
+    const float xx = x - jc.c[3], yy = y - jc.c[4];
+    const float ca = jc.c[1], sa = jc.c[2];
+    J[0] = gx; J[1] = gy;
+    J[2] = jc.c[0] * (-gx * (sa * xx + ca * yy) + gy * (ca * xx - sa * yy));
+    if (TYPE == SSK_MOTION_SCALED_EUCLIDEAN) J[3] = gx * (ca * xx - sa * yy) + gy * (sa * xx + ca * yy);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// cluster-wide deterministic reduction of NS per-thread partial sums
+// ------------------------------------------------------------------------------------------------
+template <int NS, typename T>
+__device__ void cluster_reduce(Ctx &c, const T (&acc)[NS]) {
+  Shared &S = *c.S;
+  const int lane = c.tid & 31, warp = c.tid >> 5;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) {
+    const double v = warp_sum((double)acc[k]);
+    if (lane == 0) S.wpart[warp][k] = v;
+  }
+  __syncthreads();
+  if (c.tid < NS) {
+    double s = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += S.wpart[w][c.tid];
+    S.part[c.buf][c.tid] = s;
+  }
+  cg::cluster_group cluster = cg::this_cluster();
+  cluster.sync();
+  if (c.tid < NS) {
+    double s = 0;
+    for (int r = 0; r < c.csize; ++r) s += *cluster.map_shared_rank(&S.part[c.buf][c.tid], r);
+    S.tot[c.tid] = s;
+  }
+  __syncthreads();
+  c.buf ^= 1;
+}
+
+__device__ __forceinline__ Img level_image(const Ctx &c, int lvl) {
+  const EccLevel &L = c.cfg->lv[lvl];
+  Img im;
+  im.data = c.frame->pyr + L.cur_off;
+  im.step = (int64_t)L.cols * 4; im.rows = L.rows; im.cols = L.cols; im.depth = SSK_32F; im.cn = 1; im.scale = 1.f;
+  return im;
+}
+
+// thread 0: publish the parameters of the next pass
+__device__ void set_pass_params(Shared &S, const ssk_transform &q) {
+  S.tq = q;
+  S.map = make_mapcoef(q);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass of the inverse-compositional solvers: sums = [ |rhs|^2, #valid, J_i . rhs ]
+//   lm_masks = true : c_ecclm_inverse_compositional::compute_rhs (ecc2.cc:1894-1917): mask by INTER_NEAREST remap of the
+//                     inverted current mask with constant border 255 -> a pixel is bad iff its rounded source
+//                     coordinate falls outside the current image (no user current mask)
+//   lm_masks = false: ecc_remap (ecc2.cc:178-219): bilinear remap of the all-255 mask >= 250
+// ------------------------------------------------------------------------------------------------
+template <int TYPE>
+__device__ void pass_ic(Ctx &c, int lvl, bool lm_masks) {
+  constexpr int M = NParams<TYPE>::M;
+  constexpr int NS = 2 + M;
+  Shared &S = *c.S;
+  const EccLevel &L = c.cfg->lv[lvl];
+  const Img cur = level_image(c, lvl);
+  const MapCoef m = S.map;
+  const JCoef jc = S.jc;
+  float acc[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) acc[k] = 0.f;
+  const int n = L.cols * L.rows;
+  for (int i = c.rank * NT + c.tid; i < n; i += c.csize * NT) {
+    const int y = i / L.cols, x = i - y * L.cols;
+    float u, v;
+    map_xy(m, (float)x, (float)y, u, v);
+    bool ok;
+    if (lm_masks) {
+      const int ix = __float2int_rn(u), iy = __float2int_rn(v);
+      ok = (unsigned)ix < (unsigned)L.cols && (unsigned)iy < (unsigned)L.rows;
+    } else {
+      ok = valid255_linear(u, v, L.cols, L.rows);
+    }
+    if (ok && L.refmask) ok = L.refmask[i] != 0;
+    if (!ok) continue;
+    const float g = sample_linear<SSK_32F>(cur, 0, u, v, SSK_BORDER_REPLICATE, 0.f);
+    const float rhs = g - __ldg(L.ref + i);
+    float J[M];
+    eval_J<TYPE>(jc, (float)x, (float)y, __ldg(L.gx + i), __ldg(L.gy + i), J);
+    acc[0] = fmaf(rhs, rhs, acc[0]);
+    acc[1] += 1.f;
+#pragma unroll
+    for (int k = 0; k < M; ++k) acc[2 + k] = fmaf(J[k], rhs, acc[2 + k]);
+  }
+  cluster_reduce<NS>(c, acc);
+}
+
+// reference-side normal matrix Hp = J^T J (ecc_compute_hessian_matrix, ecc2.cc:295-322): sums = lower triangle
+template <int TYPE>
+__device__ void pass_hp(Ctx &c, int lvl) {
+  constexpr int M = NParams<TYPE>::M;
+  constexpr int NS = M * (M + 1) / 2;
+  Shared &S = *c.S;
+  const EccLevel &L = c.cfg->lv[lvl];
+  const JCoef jc = S.jc;
+  float acc[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) acc[k] = 0.f;
+  const int n = L.cols * L.rows;
+  for (int i = c.rank * NT + c.tid; i < n; i += c.csize * NT) {
+    const int y = i / L.cols, x = i - y * L.cols;
+    float J[M];
+    eval_J<TYPE>(jc, (float)x, (float)y, __ldg(L.gx + i), __ldg(L.gy + i), J);
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < M; ++a)
+#pragma unroll
+      for (int b = 0; b <= a; ++b) { acc[q] = fmaf(J[a], J[b], acc[q]); ++q; }
+  }
+  cluster_reduce<NS>(c, acc);
+}
+
+// thread 0: unpack a lower triangle of sums into a symmetric float matrix (H stored as cv::Mat1f)
+__device__ void unpack_H(int M, const double *tri, float *H) {
+  int q = 0;
+  for (int a = 0; a < M; ++a)
+    for (int b = 0; b <= a; ++b) { H[a * M + b] = (float)tri[q]; H[b * M + a] = (float)tri[q]; ++q; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass of the forward methods (warped-image gradient needs a stencil -> tiles with a 2-px halo in smem)
+//   FA (c_ecc_forward_additive, ecc2.cc:1297-1347):
+//     sums = [ n, Sf, Sf2, Sg, Sg2, H (lower triangle), J_i.(g-f), J_i.f, sum J_i ]
+//     so that ep_i = J_i.(g - r f - (gm - r fm)) = J_i.(g-f) - (r-1) J_i.f - (gm - r fm) sum J_i  (benign cancellation)
+//   LM (c_ecclm::compute_jac, ecc2.cc:1482-1525):
+//     sums = [ |rhs|^2, #valid, v_i = J_i.rhs, H (lower triangle) ]
+// ------------------------------------------------------------------------------------------------
+template <int TYPE, bool FA>
+__device__ void pass_forward(Ctx &c, int lvl) {
+  constexpr int M = NParams<TYPE>::M;
+  constexpr int NH = M * (M + 1) / 2;
+  constexpr int NS = FA ? 5 + NH + 3 * M : 2 + M + NH;
+  Shared &S = *c.S;
+  const EccLevel &L = c.cfg->lv[lvl];
+  const Img cur = level_image(c, lvl);
+  const MapCoef m = S.map;
+  const JCoef jc = S.jc;
+  const int interp = FA ? c.cfg->interp : SSK_INTER_LINEAR;
+  float acc[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) acc[k] = 0.f;
+  const int ntx = (L.cols + FT_W - 1) / FT_W, nty = (L.rows + FT_H - 1) / FT_H;
+  const int tx = c.tid & 31, ty = c.tid >> 5;
+  for (int t = c.rank; t < ntx * nty; t += c.csize) {
+    const int x0 = (t % ntx) * FT_W, y0 = (t / ntx) * FT_H;
+    for (int k = c.tid; k < FT_IH * FT_IW; k += NT) {
+      const int r = k / FT_IW, cc = k - r * FT_IW;
+      const int gx_ = min(max(x0 - 2 + cc, 0), L.cols - 1), gy_ = min(max(y0 - 2 + r, 0), L.rows - 1);
+      float u, v;
+      map_xy(m, (float)gx_, (float)gy_, u, v);
+      float g;
+      if (interp == SSK_INTER_NEAREST) g = sample_nearest<SSK_32F>(cur, 0, u, v, SSK_BORDER_REPLICATE, 0.f);
+      else g = sample_linear<SSK_32F>(cur, 0, u, v, SSK_BORDER_REPLICATE, 0.f);
+      S.gw[r][cc] = g;
+    }
+    __syncthreads();
+    const int x = x0 + tx, y = y0 + ty;
+    if (x < L.cols && y < L.rows) {
+      const int i = y * L.cols + x;
+      float u, v;
+      map_xy(m, (float)x, (float)y, u, v);
+      bool ok = valid255_linear(u, v, L.cols, L.rows);
+      if (ok && L.refmask) ok = L.refmask[i] != 0;
+      if (ok) {
+        const int r = ty + 2, cc = tx + 2;
+        // gx = sepFilter2D(gw, d5 along x, s3 along y); gy = sepFilter2D(gw, s3 along x, d5 along y)
+        const float k1 = 2.f / 3.f, k2 = -1.f / 12.f;
+        float rd[3], rs[5];
+#pragma unroll
+        for (int d = -1; d <= 1; ++d)
+          rd[d + 1] = __fadd_rn(__fmul_rn(k1, __fsub_rn(S.gw[r + d][cc + 1], S.gw[r + d][cc - 1])),
+                                __fmul_rn(k2, __fsub_rn(S.gw[r + d][cc + 2], S.gw[r + d][cc - 2])));
+#pragma unroll
+        for (int d = -2; d <= 2; ++d)
+          rs[d + 2] = __fadd_rn(__fmul_rn(0.5f, S.gw[r + d][cc]), __fmul_rn(0.25f, __fadd_rn(S.gw[r + d][cc + 1], S.gw[r + d][cc - 1])));
+        const float gxw = __fadd_rn(__fmul_rn(0.5f, rd[1]), __fmul_rn(0.25f, __fadd_rn(rd[2], rd[0])));
+        const float gyw = __fadd_rn(__fmul_rn(k1, __fsub_rn(rs[3], rs[1])), __fmul_rn(k2, __fsub_rn(rs[4], rs[0])));
+        const float g = S.gw[r][cc], f = __ldg(L.ref + i);
+        float J[M];
+        eval_J<TYPE>(jc, (float)x, (float)y, gxw, gyw, J);
+        int q;
+        if (FA) {
+          acc[0] += 1.f; acc[1] += f; acc[2] = fmaf(f, f, acc[2]); acc[3] += g; acc[4] = fmaf(g, g, acc[4]);
+          q = 5;
+        } else {
+          const float rhs = g - f;
+          acc[0] = fmaf(rhs, rhs, acc[0]); acc[1] += 1.f;
+#pragma unroll
+          for (int k = 0; k < M; ++k) acc[2 + k] = fmaf(J[k], rhs, acc[2 + k]);
+          q = 2 + M;
+        }
+#pragma unroll
+        for (int a = 0; a < M; ++a)
+#pragma unroll
+          for (int b = 0; b <= a; ++b) { acc[q] = fmaf(J[a], J[b], acc[q]); ++q; }
+        if (FA) {
+          const float d = g - f;
+#pragma unroll
+          for (int k = 0; k < M; ++k) {
+            acc[5 + NH + k] = fmaf(J[k], d, acc[5 + NH + k]);
+            acc[5 + NH + M + k] = fmaf(J[k], f, acc[5 + NH + M + k]);
+            acc[5 + NH + 2 * M + k] += J[k];
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  cluster_reduce<NS>(c, acc);
+}
+
+// compute_correlation (ecc2.cc:65-137): sums = [ n, Sf, Sg, Sf2, Sg2, Sfg ] over (remap(255) >= 254) & refmask,
+// g = remap(current, INTER_LINEAR, BORDER_CONSTANT 0)
+__device__ void pass_rho(Ctx &c) {
+  Shared &S = *c.S;
+  const EccLevel &L = c.cfg->lv[0];
+  const Img cur = level_image(c, 0);
+  const MapCoef m = S.map;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  const int n = L.cols * L.rows;
+  for (int i = c.rank * NT + c.tid; i < n; i += c.csize * NT) {
+    const int y = i / L.cols, x = i - y * L.cols;
+    float u, v;
+    map_xy(m, (float)x, (float)y, u, v);
+    bool ok = valid255_linear(u, v, L.cols, L.rows);
+    if (ok && L.refmask) ok = L.refmask[i] != 0;
+    if (!ok) continue;
+    const double g = sample_linear<SSK_32F>(cur, 0, u, v, SSK_BORDER_CONSTANT, 0.f);
+    const double f = __ldg(L.ref + i);
+    acc[0] += 1.0; acc[1] += f; acc[2] += g; acc[3] += f * f; acc[4] += g * g; acc[5] += f * g;
+  }
+  cluster_reduce<6>(c, acc);
+}
+
+__device__ double rho_from_sums(const double *t) {
+  const double n = t[0];
+  if (!(n > 0)) return 0.0;
+  const double m1 = t[1] / n, m2 = t[2] / n;
+  const double v1 = fmax(t[3] / n - m1 * m1, 0.0), v2 = fmax(t[4] / n - m2 * m2, 0.0);
+  const double covar = t[5] / n - m1 * m2;
+  return covar / (sqrt(v1) * sqrt(v2));
+}
+
+// ------------------------------------------------------------------------------------------------
+// level solvers.  All threads run the control flow; scalar work is done by thread 0 of each CTA on the
+// CTA's own copy of the state, which stays identical across the cluster.
+// ------------------------------------------------------------------------------------------------
+#define T0_BEGIN __syncthreads(); if (c.tid == 0) {
+#define T0_END } __syncthreads();
+
+// reference-side Hp and steepest-descent coefficients of this level for the current transform
+template <int TYPE>
+__device__ void prepare_ic_level(Ctx &c, int lvl, bool main_pass) {
+  constexpr int M = NParams<TYPE>::M;
+  Shared &S = *c.S;
+  const EccConfig &cfg = *c.cfg;
+  const EccHpCache *cache = main_pass ? cfg.hp_main : cfg.hp_trans;
+  const int mode = main_pass ? cfg.hp_main_mode : 0;
+  if (mode == 0) {
+    T0_BEGIN
+    for (int i = 0; i < M * M; ++i) S.Hp[i] = cache->Hp[lvl][i];
+    ssk_transform jt = S.t;
+    for (int i = 0; i < 8; ++i) jt.params[i] = cache->jp[lvl][i];
+    for (int i = 0; i < 4; ++i) jt.aux[i] = cache->jp[lvl][8 + i];
+    make_jcoef(jt, S.jc);
+    T0_END
+  } else {
+    // jac is (re)built with the parameters the transform holds at this moment (ecc2.cc:1733-1738, 1985-1991)
+    T0_BEGIN
+    make_jcoef(S.t, S.jc);
+    T0_END
+    pass_hp<TYPE>(c, lvl);
+    T0_BEGIN
+    unpack_H(M, S.tot, S.Hp);
+    if (mode == 2 && c.rank == 0) {
+      EccHpCache *w = cfg.hp_main;
+      for (int i = 0; i < M * M; ++i) w->Hp[lvl][i] = S.Hp[i];
+      for (int i = 0; i < 8; ++i) w->jp[lvl][i] = S.t.params[i];
+      for (int i = 0; i < 4; ++i) w->jp[lvl][8 + i] = S.t.aux[i];
+      w->valid[lvl] = 1;
+    }
+    T0_END
+  }
+}
+
+// c_ecclm_inverse_compositional::align (ecc2.cc:1926-2086)
+template <int TYPE>
+__device__ bool align_iclm(Ctx &c, int lvl, double max_eps, bool main_pass) {
+  constexpr int M = NParams<TYPE>::M;
+  Shared &S = *c.S;
+  const EccConfig &cfg = *c.cfg;
+  const EccLevel &L = cfg.lv[lvl];
+  prepare_ic_level<TYPE>(c, lvl, main_pass);
+  T0_BEGIN
+  S.lambda = 0.001; S.dp = 0; S.recompute = 1; S.num_it = 0; S.eps = FLT_MAX; S.err = 0; S.newerr = 0;
+  T0_END
+  while (S.num_it < cfg.max_iterations) {
+    if (S.recompute) {
+      T0_BEGIN set_pass_params(S, S.t); T0_END
+      pass_ic<TYPE>(c, lvl, true);
+      T0_BEGIN
+      const double CMA = S.tot[1], RMA = L.RMA;
+      S.err = S.tot[0] * (RMA * RMA) / (CMA * CMA);
+      for (int i = 0; i < M; ++i) S.v[i] = (float)((double)(float)S.tot[2 + i] * (RMA / CMA));
+      T0_END
+    }
+    do {
+      T0_BEGIN
+      ++S.num_it;
+      S.recompute = 1;
+      float H[64], sdp[8], np[8];
+      for (int i = 0; i < M * M; ++i) H[i] = S.Hp[i];
+      for (int i = 0; i < M; ++i) H[i * M + i] = (float)((1 + S.lambda) * (double)S.Hp[i * M + i]);
+      chol_solve(M, H, S.v, S.deltap);
+      for (int i = 0; i < M; ++i) sdp[i] = (float)(cfg.update_step_scale * (double)S.deltap[i]);
+      xf_invert_and_compose(S.t, sdp, np);
+      ssk_transform q = S.t;
+      for (int i = 0; i < M; ++i) q.params[i] = np[i];
+      set_pass_params(S, q);
+      T0_END
+      pass_ic<TYPE>(c, lvl, true);
+      T0_BEGIN
+      const double CMA = S.tot[1], RMA = L.RMA;
+      S.newerr = S.tot[0] * (RMA * RMA) / (CMA * CMA);
+      for (int i = 0; i < M; ++i) S.vtrial[i] = (float)((double)(float)S.tot[2 + i] * (RMA / CMA));
+      S.dp = xf_eps(TYPE, S.deltap, L.cols, L.rows, S.t.aux[3]);
+      S.brk = 0;
+      if (S.dp < max_eps) {
+        S.brk = 1;
+      } else {
+        // temp_d = -Hp * deltap + 2 v ; dS = deltap . temp_d (cv::gemm on float data, dot in double)
+        double dS = 0;
+        for (int i = 0; i < M; ++i) {
+          float td = 0.f;
+          for (int k = 0; k < M; ++k) td += S.Hp[i * M + k] * S.deltap[k];
+          td = -td + 2.f * S.v[i];
+          dS += (double)S.deltap[i] * (double)td;
+        }
+        const double rho = (S.err - S.newerr) / (fabs(dS) > DBL_EPSILON ? dS : 1);
+        if (rho > 0.25) { if (S.lambda > 1e-6) S.lambda = fmax(1e-6, S.lambda / 5); }
+        else if (rho > 0.1) { }
+        else if (S.lambda < 1) S.lambda = 1;
+        else S.lambda *= 10;
+        if (S.newerr < S.err) S.brk = 1;
+      }
+      T0_END
+    } while (!S.brk && S.num_it < cfg.max_iterations);
+    T0_BEGIN
+    if (S.newerr < S.err) {
+      S.err = S.newerr;
+      S.recompute = 0;
+      for (int i = 0; i < M; ++i) { S.t.params[i] = S.tq.params[i]; S.v[i] = S.vtrial[i]; }
+    }
+    T0_END
+    if (S.dp < max_eps) break;
+  }
+  T0_BEGIN S.eps = S.dp; S.total_iterations += S.num_it; T0_END
+  return true;
+}
+
+// c_ecc_inverse_compositional::align (ecc2.cc:1693-1788)
+template <int TYPE>
+__device__ bool align_ic(Ctx &c, int lvl, double max_eps, bool main_pass) {
+  constexpr int M = NParams<TYPE>::M;
+  Shared &S = *c.S;
+  const EccConfig &cfg = *c.cfg;
+  const EccLevel &L = cfg.lv[lvl];
+  prepare_ic_level<TYPE>(c, lvl, main_pass);
+  T0_BEGIN S.num_it = 0; S.eps = FLT_MAX; S.rmsold = FLT_MAX; S.brk = 0; T0_END
+  while (true) {
+    T0_BEGIN
+    S.cont = S.num_it < cfg.max_iterations;
+    ++S.num_it;
+    if (S.cont) set_pass_params(S, S.t);
+    T0_END
+    if (!S.cont) break;
+    pass_ic<TYPE>(c, lvl, false);
+    T0_BEGIN
+    const double CMA = S.tot[1], RMA = L.RMA;
+    const double rmsnew = S.tot[0] * (RMA * RMA) / (CMA * CMA);
+    float vs[8];
+    for (int i = 0; i < M; ++i) vs[i] = (float)((double)(float)S.tot[2 + i] * (RMA / CMA));
+    chol_solve(M, S.Hp, vs, S.deltap);
+    S.brk = 0;
+    if (rmsnew >= S.rmsold) {
+      S.brk = 1;
+    } else {
+      float sdp[8], np[8];
+      for (int i = 0; i < M; ++i) sdp[i] = (float)cfg.update_step_scale * S.deltap[i];
+      xf_invert_and_compose(S.t, sdp, np);
+      S.rmsold = rmsnew;
+      for (int i = 0; i < M; ++i) S.t.params[i] = np[i];
+      S.eps = xf_eps(TYPE, S.deltap, L.cols, L.rows, S.t.aux[3]);
+      if (S.eps < max_eps) S.brk = 1;
+    }
+    T0_END
+    if (S.brk) break;
+  }
+  T0_BEGIN S.total_iterations += S.num_it; T0_END
+  return true;
+}
+
+// c_ecc_forward_additive::align (ecc2.cc:1247-1365)
+template <int TYPE>
+__device__ bool align_fa(Ctx &c, int lvl, double max_eps) {
+  constexpr int M = NParams<TYPE>::M;
+  constexpr int NH = M * (M + 1) / 2;
+  Shared &S = *c.S;
+  const EccConfig &cfg = *c.cfg;
+  const EccLevel &L = cfg.lv[lvl];
+  if (max_eps <= 0) max_eps = 1e-3;
+  T0_BEGIN S.num_it = 0; S.failed = 0; S.brk = 0; T0_END
+  while (true) {
+    T0_BEGIN
+    S.cont = S.num_it < cfg.max_iterations;
+    ++S.num_it;
+    if (S.cont) { set_pass_params(S, S.t); make_jcoef(S.t, S.jc); }
+    T0_END
+    if (!S.cont) break;
+    pass_forward<TYPE, true>(c, lvl);
+    T0_BEGIN
+    const double *t = S.tot;
+    const double n = t[0];
+    const double fMean = t[1] / n, gMean = t[3] / n;
+    const double fStd = sqrt(fmax(t[2] / n - fMean * fMean, 0.0)), gStd = sqrt(fmax(t[4] / n - gMean * gMean, 0.0));
+    const double r = gStd / fStd;
+    float H[64], ep[8], sol[8];
+    unpack_H(M, t + 5, H);
+    const double cst = gMean - r * fMean;
+    for (int i = 0; i < M; ++i)
+      ep[i] = (float)(t[5 + NH + i] - (r - 1.0) * t[5 + NH + M + i] - cst * t[5 + NH + 2 * M + i]);
+    S.brk = 0;
+    if (!(n > 0) || !chol_solve(M, H, ep, sol)) {
+      S.failed = 1;
+      S.brk = 1;
+    } else {
+      float dpv[8];
+      for (int i = 0; i < M; ++i) {
+        dpv[i] = (float)(-cfg.update_step_scale * (double)sol[i]);
+        S.t.params[i] = S.t.params[i] + dpv[i];
+      }
+      S.eps = xf_eps(TYPE, dpv, L.cols, L.rows, S.t.aux[3]);
+      if (S.eps < max_eps) S.brk = 1;
+    }
+    T0_END
+    if (S.brk) break;
+  }
+  T0_BEGIN S.total_iterations += S.num_it; T0_END
+  return !S.failed;
+}
+
+// c_ecclm::align (ecc2.cc:1528-1650)
+template <int TYPE>
+__device__ bool align_lm(Ctx &c, int lvl, double max_eps) {
+  constexpr int M = NParams<TYPE>::M;
+  Shared &S = *c.S;
+  const EccConfig &cfg = *c.cfg;
+  const EccLevel &L = cfg.lv[lvl];
+  T0_BEGIN S.lambda = 0.1; S.num_it = 0; S.converged = 0; S.recompute = 1; T0_END
+  while (S.num_it < cfg.max_iterations) {
+    if (S.recompute) {
+      T0_BEGIN set_pass_params(S, S.t); make_jcoef(S.t, S.jc); T0_END
+      pass_forward<TYPE, false>(c, lvl);
+      T0_BEGIN
+      S.err = S.tot[0];
+      for (int i = 0; i < M; ++i) S.v[i] = (float)S.tot[2 + i];
+      unpack_H(M, S.tot + 2 + M, S.Hp);
+      T0_END
+    } else {
+      // compute_jac(params, recompute_remap = false): reuse the accepted trial's image, rhs, H and v
+      T0_BEGIN
+      S.err = S.newerr;
+      for (int i = 0; i < M; ++i) S.v[i] = S.vtrial[i];
+      for (int i = 0; i < M * M; ++i) S.Hp[i] = S.Htrial[i];
+      T0_END
+    }
+    if (S.err < 1) { T0_BEGIN S.converged = 1; T0_END break; }
+    while (true) {
+      T0_BEGIN
+      S.cont = S.num_it < cfg.max_iterations;
+      ++S.num_it;
+      S.brk = 0;
+      if (S.cont) {
+        S.recompute = 1;
+        float H[64];
+        for (int i = 0; i < M * M; ++i) H[i] = S.Hp[i];
+        for (int i = 0; i < M; ++i) H[i * M + i] = (float)((1 + S.lambda) * (double)S.Hp[i * M + i]);
+        chol_solve(M, H, S.v, S.deltap);
+        ssk_transform q = S.t;
+        for (int i = 0; i < M; ++i) q.params[i] = (float)((double)S.deltap[i] * (-cfg.update_step_scale) + (double)S.t.params[i]);
+        S.eps = xf_eps(TYPE, S.deltap, L.cols, L.rows, S.t.aux[3]);
+        if (S.eps <= max_eps) {
+          for (int i = 0; i < M; ++i) S.t.params[i] = q.params[i];
+          S.converged = 1;
+          S.brk = 1;
+        } else {
+          set_pass_params(S, q);
+          make_jcoef(q, S.jc);
+        }
+      }
+      T0_END
+      if (!S.cont || S.brk) break;
+      pass_forward<TYPE, false>(c, lvl);
+      T0_BEGIN
+      S.newerr = S.tot[0];
+      S.brk = 0;
+      if (S.newerr > S.err) {
+        if (S.lambda > 1e6) S.brk = 1;
+        else S.lambda *= 10.0;
+      } else {
+        for (int i = 0; i < M; ++i) { S.t.params[i] = S.tq.params[i]; S.vtrial[i] = (float)S.tot[2 + i]; }
+        unpack_H(M, S.tot + 2 + M, S.Htrial);
+        S.recompute = 0;
+        const double diff = S.err - S.newerr;
+        if (diff < S.err * cfg.max_epse) {
+          S.converged = 1;
+        } else {
+          double dS = 0;
+          for (int i = 0; i < M; ++i) {
+            float td = 0.f;
+            for (int k = 0; k < M; ++k) td += S.Hp[i * M + k] * S.deltap[k];
+            td = -td + 2.f * S.v[i];
+            dS += (double)S.deltap[i] * (double)td;
+          }
+          const double rho = fabs(dS) > (double)1e-9f ? diff / fabs(dS) : diff;
+          if (rho > 0.25) S.lambda = fmax(1e-8, 0.2 * S.lambda);
+          else if (rho < 0.1) S.lambda = S.lambda < 1.0 ? 1.0 : S.lambda * 10.0;
+        }
+        S.brk = 1;
+      }
+      T0_END
+      if (S.brk) break;
+    }
+    if (S.converged) break;
+  }
+  T0_BEGIN S.total_iterations += S.num_it; T0_END
+  return S.converged != 0;
+}
+
+template <int METHOD, int TYPE>
+__device__ bool align_level(Ctx &c, int lvl, double max_eps, bool main_pass) {
+  if (METHOD == SSK_ECC_FORWARD_ADDITIVE) return align_fa<TYPE>(c, lvl, max_eps);
+  if (METHOD == SSK_ECC_INVERSE_COMPOSITIONAL) return align_ic<TYPE>(c, lvl, max_eps, main_pass);
+  if (METHOD == SSK_ECC_INVERSE_COMPOSITIONAL_LM) return align_iclm<TYPE>(c, lvl, max_eps, main_pass);
+  return align_lm<TYPE>(c, lvl, max_eps);
+}
+
+// c_ecch::align (ecc2.cc:1133-1176) for the transform currently held in S.t
+template <int METHOD, int TYPE>
+__device__ void ecch_align(Ctx &c, bool main_pass) {
+  Shared &S = *c.S;
+  const EccConfig &cfg = *c.cfg;
+  int lvl = cfg.nlevels - 1;
+  T0_BEGIN
+  S.total_iterations = 0;
+  if (lvl > 0) xf_scale(S.t, (double)cfg.lv[lvl].cols / (double)cfg.lv[0].cols);
+  T0_END
+  for (; lvl >= 0; --lvl) {
+    double max_eps = cfg.epsx;
+    for (int i = 0; i < lvl; ++i) max_eps *= 2;
+    const bool ok = align_level<METHOD, TYPE>(c, lvl, max_eps, main_pass);
+    T0_BEGIN
+    if (ok && lvl > 0) xf_scale(S.t, (double)cfg.lv[lvl - 1].cols / (double)cfg.lv[lvl].cols);
+    T0_END
+  }
+}
+
+__device__ double correlation(Ctx &c) {
+  Shared &S = *c.S;
+  T0_BEGIN set_pass_params(S, S.t); T0_END
+  pass_rho(c);
+  T0_BEGIN S.rho = rho_from_sums(S.tot); T0_END
+  return S.rho;
+}
+
+template <int METHOD, int TYPE>
+__global__ void __launch_bounds__(NT, 1) k_ecc(const __grid_constant__ EccConfig cfg, EccFrame *frames) {
+  __shared__ Shared S;
+  cg::cluster_group cluster = cg::this_cluster();
+  Ctx c;
+  c.cfg = &cfg;
+  c.csize = (int)cluster.num_blocks();
+  c.rank = (int)cluster.block_rank();
+  c.tid = threadIdx.x;
+  c.buf = 0;
+  c.S = &S;
+  EccFrame *fr = frames + blockIdx.x / c.csize;
+  c.frame = fr;
+
+  T0_BEGIN
+  S.t = fr->t;
+  S.failed = 0; S.rho = -1; S.eps = FLT_MAX; S.total_iterations = 0;
+  for (int i = 0; i < 8; ++i) S.jc.c[i] = 0.f;
+  T0_END
+
+  bool ok = true;
+  // c_frame_registration.cc:815-850: translation-only estimate first
+  if (TYPE != SSK_MOTION_TRANSLATION && cfg.translation_first) {
+    T0_BEGIN
+    float tx, ty;
+    xf_get_translation(S.t, tx, ty);
+    ssk_transform tt;
+    tt.motion_type = SSK_MOTION_TRANSLATION; tt.nparams = 2;
+    for (int i = 0; i < 8; ++i) tt.params[i] = 0.f;
+    for (int i = 0; i < 4; ++i) tt.aux[i] = 0.f;
+    tt.params[0] = tx; tt.params[1] = ty;
+    S.tmain = S.t;
+    S.t = tt;
+    T0_END
+    ecch_align<METHOD, SSK_MOTION_TRANSLATION>(c, false);
+    const double rho = correlation(c);
+    if (rho < 0.75 * cfg.min_rho) ok = false;
+    T0_BEGIN
+    const float tx = S.t.params[0], ty = S.t.params[1];
+    S.t = S.tmain;
+    if (ok) xf_set_translation(S.t, tx, ty);
+    T0_END
+  }
+  if (ok) {
+    ecch_align<METHOD, TYPE>(c, true);
+    if (cfg.check_rho) {
+      const double rho = correlation(c);
+      if (rho < cfg.min_rho) ok = false;
+    }
+  }
+  if (c.tid == 0 && c.rank == 0) {
+    ssk_transform t = S.t;
+    if (ok && cfg.final_scale != 1.0) xf_scale(t, cfg.final_scale);
+    fr->t = t;
+    fr->map = make_mapcoef(t);
+    fr->rho = S.rho;
+    fr->eps = S.eps;
+    fr->num_iterations = S.total_iterations;
+    fr->ok = ok ? 1 : 0;
+    fr->failed = S.failed;
+  }
+  cluster.sync();   // no CTA may exit while a peer can still read its shared memory
+}
+
+inline int launch_clustered(const void *kernel, void **args, int nclusters, int cluster_size, cudaStream_t s) {
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(nclusters * cluster_size);
+  lc.blockDim = dim3(NT);
+  lc.dynamicSmemBytes = 0;
+  lc.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_size;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  lc.attrs = attr;
+  lc.numAttrs = 1;
+  SSK_CUDA(cudaLaunchKernelExC(&lc, kernel, args));
+  count_launch();
+  return SSK_OK;
+}
+
+template <int METHOD>
+int launch_ecc_method(const EccConfig &cfg, EccFrame *frames, int nframes, int cluster_size, cudaStream_t s) {
+  void *args[2] = {(void *)&cfg, (void *)&frames};
+  const void *k;
+  switch (cfg.motion_type) {
+    case SSK_MOTION_TRANSLATION: k = (const void *)k_ecc<METHOD, SSK_MOTION_TRANSLATION>; break;
+    case SSK_MOTION_EUCLIDEAN: k = (const void *)k_ecc<METHOD, SSK_MOTION_EUCLIDEAN>; break;
+    case SSK_MOTION_SCALED_EUCLIDEAN: k = (const void *)k_ecc<METHOD, SSK_MOTION_SCALED_EUCLIDEAN>; break;
+    case SSK_MOTION_AFFINE: k = (const void *)k_ecc<METHOD, SSK_MOTION_AFFINE>; break;
+    case SSK_MOTION_HOMOGRAPHY: k = (const void *)k_ecc<METHOD, SSK_MOTION_HOMOGRAPHY>; break;
+    default: set_error("ECC: unsupported motion type"); return SSK_ERR_INVALID;
+  }
+  return launch_clustered(k, args, nframes, cluster_size, s);
+}
+
+}  // namespace
+
+}  // namespace ssk

@@ -1,0 +1,415 @@
+// Engine classes: device-resident c_ecch / c_frame_registration / accumulator state and batching.
+#include "ssk_engine.cuh"
+#include <cmath>
+#include <cstring>
+
+namespace ssk {
+
+int DevBuf::ensure(size_t n) {
+  if (n <= bytes && p) return SSK_OK;
+  release();
+  SSK_CUDA(cudaMalloc(&p, n ? n : 1));
+  bytes = n;
+  return SSK_OK;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  bytes = 0;
+}
+int PinnedBuf::ensure(size_t n) {
+  if (n <= bytes && p) return SSK_OK;
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+  SSK_CUDA(cudaMallocHost(&p, n ? n : 1));
+  bytes = n;
+  return SSK_OK;
+}
+
+int make_transform(ssk_transform *t, int motion_type) {
+  // image_transform.cc:34-63 followed by reset()
+  memset(t, 0, sizeof(*t));
+  t->motion_type = motion_type;
+  t->aux[2] = 1.f;   // homography a22
+  t->aux[3] = 1.f;   // euclidean scale when fixed
+  switch (motion_type) {
+    case SSK_MOTION_TRANSLATION: t->nparams = 2; break;
+    case SSK_MOTION_EUCLIDEAN: t->nparams = 3; break;
+    case SSK_MOTION_SCALED_EUCLIDEAN: t->nparams = 4; t->params[3] = 1.f; break;
+    case SSK_MOTION_AFFINE: t->nparams = 6; t->params[0] = 1.f; t->params[4] = 1.f; break;
+    case SSK_MOTION_HOMOGRAPHY: t->nparams = 8; t->params[0] = 1.f; t->params[4] = 1.f; break;
+    default: set_error("unsupported motion type"); return SSK_ERR_INVALID;
+  }
+  return SSK_OK;
+}
+
+int host_scale_transform(ssk_transform *t, double f) {
+  // c_image_transform::scale_transfrom (c_image_transform.cc:130-134, 502-507, 911-915, 1186-1194)
+  switch (t->motion_type) {
+    case SSK_MOTION_TRANSLATION:
+      t->params[0] = (float)(t->params[0] * f); t->params[1] = (float)(t->params[1] * f); break;
+    case SSK_MOTION_EUCLIDEAN:
+    case SSK_MOTION_SCALED_EUCLIDEAN:
+      t->params[0] = (float)(t->params[0] * f); t->params[1] = (float)(t->params[1] * f);
+      t->aux[0] = (float)(t->aux[0] * f); t->aux[1] = (float)(t->aux[1] * f); break;
+    case SSK_MOTION_AFFINE:
+      t->params[2] = (float)(t->params[2] * f); t->params[5] = (float)(t->params[5] * f); break;
+    case SSK_MOTION_HOMOGRAPHY:
+      t->params[2] = (float)(t->params[2] * f); t->params[5] = (float)(t->params[5] * f);
+      t->params[6] = (float)(t->params[6] / f); t->params[7] = (float)(t->params[7] / f); break;
+    default: set_error("unsupported motion type"); return SSK_ERR_INVALID;
+  }
+  return SSK_OK;
+}
+
+// cv::getGaussianKernel(ksize, sigma) -> float taps (sepFilter2D converts the kernel to the data type)
+static int gaussian_kernel(double sigma, float *k) {
+  const int n = std::max(3, 2 * ((int)(3 * sigma)) + 1);   // ecc2.cc:1001
+  double cf[kMaxTaps], sum = 0;
+  const double s2 = -0.5 / (sigma * sigma);
+  for (int i = 0; i < n; ++i) {
+    const double x = i - (n - 1) * 0.5;
+    cf[i] = std::exp(s2 * x * x);
+    sum += cf[i];
+  }
+  for (int i = 0; i < n; ++i) k[i] = (float)(cf[i] / sum);
+  return n;
+}
+
+static const float kD5[5] = {1.f / 12.f, -2.f / 3.f, 0.f, 2.f / 3.f, -1.f / 12.f};  // ecc2.cc:148
+static const float kS3[3] = {0.25f, 0.5f, 0.25f};                                   // ecc2.cc:149
+
+// ------------------------------------------------------------------------------------------------
+Ecch::~Ecch() {}
+
+int Ecch::init(const ssk_ecch_options &o, cudaStream_t s) {
+  opts = o;
+  stream = s;
+  have_reference = false;
+  return SSK_OK;
+}
+
+int Ecch::set_reference(const float *d_img, int rows, int cols) {
+  SSK_REQUIRE(opts.reference_smooth_sigma < 5.0 && opts.input_smooth_sigma < 5.0, "ECC smoothing sigma must be < 5");
+  // number of levels: ecc2.cc:1009-1026
+  const int min_image_size = std::max(4, opts.minimum_image_size);
+  int w = cols, h = rows, lv = 1;
+  lw[0] = w; lh[0] = h;
+  while (true) {
+    if (opts.maxlevel >= 0 && lv >= std::max(0, opts.maxlevel)) break;
+    const int nw = ((w + 1) >> 1) & ~1, nh = ((h + 1) >> 1) & ~1;   // ecc2.h:290-293
+    if (nw < min_image_size || nh < min_image_size) break;
+    if (lv >= kMaxLevels) break;
+    w = nw; h = nh;
+    lw[lv] = w; lh[lv] = h;
+    ++lv;
+  }
+  nlevels = lv;
+  pyr_floats = 0;
+  for (int l = 0; l < nlevels; ++l) {
+    loff[l] = pyr_floats;
+    pyr_floats += ((int64_t)lw[l] * lh[l] + 63) & ~(int64_t)63;   // keep levels 256-byte aligned
+  }
+  if (int e = ref_pyr.ensure(pyr_floats * 4)) return e;
+  float *rp = ref_pyr.as<float>();
+
+  SepFilterArgs sf = {};
+  sf.rows = rows; sf.cols = cols; sf.batch = 1;
+  sf.src = d_img; sf.dst = rp;
+  if (opts.reference_smooth_sigma > 0) {
+    gauss_ref_n = gaussian_kernel(opts.reference_smooth_sigma, gauss_ref);
+    sf.kxn = sf.kyn = gauss_ref_n;
+    memcpy(sf.kx, gauss_ref, sizeof(float) * gauss_ref_n);
+    memcpy(sf.ky, gauss_ref, sizeof(float) * gauss_ref_n);
+  } else {
+    sf.kxn = sf.kyn = 1; sf.kx[0] = sf.ky[0] = 1.f;
+  }
+  if (int e = launch_sepfilter(sf, stream)) return e;
+  for (int l = 1; l < nlevels; ++l) {
+    PyrDownArgs pd = {};
+    pd.src.data = rp + loff[l - 1]; pd.src.step = (int64_t)lw[l - 1] * 4; pd.src.rows = lh[l - 1]; pd.src.cols = lw[l - 1];
+    pd.src.depth = SSK_32F; pd.src.cn = 1; pd.src.scale = 1.f;
+    pd.dst = rp + loff[l]; pd.dst_rows = lh[l]; pd.dst_cols = lw[l]; pd.batch = 1; pd.post_scale = 1.f;
+    if (int e = launch_pyrdown(pd, stream)) return e;
+  }
+  const bool ic = opts.method == SSK_ECC_INVERSE_COMPOSITIONAL || opts.method == SSK_ECC_INVERSE_COMPOSITIONAL_LM;
+  if (ic) {
+    if (int e = ref_gx.ensure(pyr_floats * 4)) return e;
+    if (int e = ref_gy.ensure(pyr_floats * 4)) return e;
+    for (int l = 0; l < nlevels; ++l) {
+      // ecc_differentiate (ecc2.cc:142-169): gx = sepFilter2D(d5 along x, s3 along y), gy = (s3, d5)
+      SepFilterArgs g = {};
+      g.rows = lh[l]; g.cols = lw[l]; g.batch = 1; g.src = rp + loff[l];
+      g.dst = ref_gx.as<float>() + loff[l];
+      g.kxn = 5; g.kyn = 3; memcpy(g.kx, kD5, sizeof(kD5)); memcpy(g.ky, kS3, sizeof(kS3));
+      if (int e = launch_sepfilter(g, stream)) return e;
+      g.dst = ref_gy.as<float>() + loff[l];
+      g.kxn = 3; g.kyn = 5; memcpy(g.kx, kS3, sizeof(kS3)); memcpy(g.ky, kD5, sizeof(kD5));
+      if (int e = launch_sepfilter(g, stream)) return e;
+    }
+    if (int e = d_hp_trans.ensure(sizeof(EccHpCache))) return e;
+    if (int e = d_hp_main.ensure(sizeof(EccHpCache))) return e;
+    SSK_CUDA(cudaMemsetAsync(d_hp_trans.p, 0, sizeof(EccHpCache), stream));
+    SSK_CUDA(cudaMemsetAsync(d_hp_main.p, 0, sizeof(EccHpCache), stream));
+  }
+  if (opts.input_smooth_sigma > 0) gauss_cur_n = gaussian_kernel(opts.input_smooth_sigma, gauss_cur);
+  else { gauss_cur_n = 1; gauss_cur[0] = 1.f; }
+  have_reference = true;
+  capacity = 0;   // pointer tables depend on pyr_floats
+  if (int e = build_config()) return e;
+  hp_main_type = -1;
+  if (ic) {
+    if (int e = launch_ecc_precompute(cfg, d_hp_trans.as<EccHpCache>(), nullptr, stream)) return e;
+  }
+  return SSK_OK;
+}
+
+int Ecch::build_config() {
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.nlevels = nlevels;
+  for (int l = 0; l < nlevels; ++l) {
+    EccLevel &L = cfg.lv[l];
+    L.cols = lw[l]; L.rows = lh[l];
+    L.ref = ref_pyr.as<float>() + loff[l];
+    L.refmask = nullptr;
+    L.gx = ref_gx.p ? ref_gx.as<float>() + loff[l] : nullptr;
+    L.gy = ref_gy.p ? ref_gy.as<float>() + loff[l] : nullptr;
+    L.cur_off = loff[l];
+    L.RMA = (double)lw[l] * lh[l];
+  }
+  cfg.method = opts.method;
+  cfg.interp = opts.interpolation;
+  cfg.max_iterations = opts.max_iterations;
+  cfg.update_step_scale = opts.update_step_scale;
+  cfg.epsx = opts.epsx;
+  cfg.max_epse = 1e-4;
+  cfg.motion_type = motion_type;
+  cfg.translation_first = translation_first;
+  cfg.check_rho = check_rho;
+  cfg.min_rho = min_rho;
+  cfg.final_scale = final_scale;
+  cfg.hp_trans = d_hp_trans.as<EccHpCache>();
+  cfg.hp_main = d_hp_main.as<EccHpCache>();
+  cfg.hp_main_mode = 0;
+  return SSK_OK;
+}
+
+int Ecch::reserve(int batch) {
+  SSK_REQUIRE(have_reference, "c_ecch: reference image must be set first");
+  if (batch <= capacity) return SSK_OK;
+  const int64_t n0 = (int64_t)lw[0] * lh[0];
+  if (int e = cur_pyr.ensure((size_t)batch * pyr_floats * 4)) return e;
+  if (int e = src0.ensure((size_t)batch * n0 * 4)) return e;
+  if (int e = d_frames.ensure((size_t)batch * sizeof(EccFrame))) return e;
+  if (int e = h_frames.ensure((size_t)batch * sizeof(EccFrame))) return e;
+  // pointer tables: [level][slot] pyramid pointers, [slot] level-0 source scratch
+  std::vector<float *> tab((size_t)nlevels * batch), s0(batch);
+  for (int l = 0; l < nlevels; ++l)
+    for (int b = 0; b < batch; ++b) tab[(size_t)l * batch + b] = cur_pyr.as<float>() + (int64_t)b * pyr_floats + loff[l];
+  for (int b = 0; b < batch; ++b) s0[b] = src0.as<float>() + (int64_t)b * n0;
+  if (int e = d_lvl_ptrs.ensure(tab.size() * sizeof(float *))) return e;
+  if (int e = d_src0_ptrs.ensure(s0.size() * sizeof(float *))) return e;
+  SSK_CUDA(cudaMemcpyAsync(d_lvl_ptrs.p, tab.data(), tab.size() * sizeof(float *), cudaMemcpyHostToDevice, stream));
+  SSK_CUDA(cudaMemcpyAsync(d_src0_ptrs.p, s0.data(), s0.size() * sizeof(float *), cudaMemcpyHostToDevice, stream));
+  SSK_CUDA(cudaStreamSynchronize(stream));   // tab / s0 are stack-lifetime
+  capacity = batch;
+  memset(h_frames.p, 0, (size_t)batch * sizeof(EccFrame));
+  return SSK_OK;
+}
+
+int Ecch::prepare_current(const float *const *d_src_ptrs, int batch) {
+  SSK_REQUIRE(batch <= capacity, "c_ecch: batch exceeds reserved capacity");
+  float *const *lvl = d_lvl_ptrs.as<float *>();
+  SepFilterArgs sf = {};
+  sf.rows = lh[0]; sf.cols = lw[0]; sf.batch = batch;
+  sf.src_ptrs = d_src_ptrs; sf.dst_ptrs = lvl;
+  sf.kxn = sf.kyn = gauss_cur_n;
+  memcpy(sf.kx, gauss_cur, sizeof(float) * gauss_cur_n);
+  memcpy(sf.ky, gauss_cur, sizeof(float) * gauss_cur_n);
+  if (int e = launch_sepfilter(sf, stream)) return e;
+  for (int l = 1; l < nlevels; ++l) {
+    PyrDownArgs pd = {};
+    pd.src.step = (int64_t)lw[l - 1] * 4; pd.src.rows = lh[l - 1]; pd.src.cols = lw[l - 1];
+    pd.src.depth = SSK_32F; pd.src.cn = 1; pd.src.scale = 1.f;
+    pd.src_ptrs = reinterpret_cast<const void *const *>(lvl + (size_t)(l - 1) * capacity);
+    pd.dst_ptrs = lvl + (size_t)l * capacity;
+    pd.dst_rows = lh[l]; pd.dst_cols = lw[l]; pd.batch = batch; pd.post_scale = 1.f;
+    if (int e = launch_pyrdown(pd, stream)) return e;
+  }
+  return SSK_OK;
+}
+
+int Ecch::hp_mode_for_next_align() const {
+  const bool ic = opts.method == SSK_ECC_INVERSE_COMPOSITIONAL || opts.method == SSK_ECC_INVERSE_COMPOSITIONAL_LM;
+  if (!ic) return 0;
+  if (motion_type == SSK_MOTION_TRANSLATION || motion_type == SSK_MOTION_AFFINE) return 0;
+  // parameter-dependent steepest-descent images (euclidean, homography):
+  //  - with the translation-first pass the solvers see M=2 / M=main alternately and rebuild jac on every
+  //    align (jac.size() != M test, ecc2.cc:1733, 1985)  -> per frame
+  //  - otherwise jac is built once, by the first align after the reference changed -> capture, then reuse
+  if (translation_first) return 1;
+  return first_align_pending ? 2 : 0;
+}
+
+int Ecch::align(int batch, const ssk_transform &t0) {
+  SSK_REQUIRE(have_reference, "c_ecch: reference image must be set first");
+  SSK_REQUIRE(batch <= capacity, "c_ecch: batch exceeds reserved capacity");
+  motion_type = t0.motion_type;
+  if (int e = build_config()) return e;
+  const bool ic = opts.method == SSK_ECC_INVERSE_COMPOSITIONAL || opts.method == SSK_ECC_INVERSE_COMPOSITIONAL_LM;
+  if (ic && hp_main_type != motion_type) {
+    // reference-side jac / Hp of the main transform are (re)built when the parameter count changes (ecc2.cc:1733, 1985)
+    const bool param_free = motion_type == SSK_MOTION_TRANSLATION || motion_type == SSK_MOTION_AFFINE;
+    if (param_free) {
+      if (int e = launch_ecc_precompute(cfg, nullptr, d_hp_main.as<EccHpCache>(), stream)) return e;
+    }
+    first_align_pending = !param_free;
+    hp_main_type = motion_type;
+  }
+  // frame records are initialised on the device: no host staging, the call stays fully asynchronous
+  if (int e = launch_ecc_init_frames(device_frames(), batch, t0, cur_pyr.as<float>(), pyr_floats, stream)) return e;
+  int done = 0;
+  const int mode = hp_mode_for_next_align();
+  if (mode == 2) {
+    cfg.hp_main_mode = 2;
+    if (int e = launch_ecc(cfg, device_frames(), 1, cluster_size, stream)) return e;
+    first_align_pending = false;
+    done = 1;
+    cfg.hp_main_mode = 0;
+  } else {
+    cfg.hp_main_mode = mode;
+  }
+  if (batch > done)
+    if (int e = launch_ecc(cfg, device_frames() + done, batch - done, cluster_size, stream)) return e;
+  return SSK_OK;
+}
+
+int Ecch::download_frames(int batch) {
+  SSK_CUDA(cudaMemcpyAsync(h_frames.p, d_frames.p, (size_t)batch * sizeof(EccFrame), cudaMemcpyDeviceToHost, stream));
+  return SSK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+Acc::~Acc() {
+  if (own_stream && stream) cudaStreamDestroy(stream);
+}
+
+int Acc::ensure(int r, int c, int n) {
+  if (frames >= 1 || acc.p) {
+    SSK_REQUIRE(r == rows && c == cols, "frame accumulation: current frame and accumulator sizes not match");
+    SSK_REQUIRE(n == cn, "frame accumulation: current frame and accumulator channel count not match");
+    return SSK_OK;
+  }
+  rows = r; cols = c; cn = n;
+  const size_t npix = (size_t)r * c;
+  if (kind == SSK_ACC_BAYER_AVERAGE) {
+    if (int e = acc.ensure(npix * 3 * 4)) return e;
+    if (int e = wacc.ensure(npix * 3 * 4)) return e;
+    SSK_CUDA(cudaMemsetAsync(acc.p, 0, npix * 3 * 4, stream));
+    SSK_CUDA(cudaMemsetAsync(wacc.p, 0, npix * 3 * 4, stream));
+  } else {
+    if (int e = acc.ensure(npix * n * 4)) return e;
+    if (int e = wacc.ensure(npix * 4)) return e;
+    SSK_CUDA(cudaMemsetAsync(acc.p, 0, npix * n * 4, stream));
+    SSK_CUDA(cudaMemsetAsync(wacc.p, 0, npix * 4, stream));
+  }
+  frames = 0;
+  return SSK_OK;
+}
+
+int Acc::clear() {
+  acc.release();
+  wacc.release();
+  rmap.release();
+  rows = cols = cn = 0;
+  frames = 0;
+  have_map = false;
+  rmap_explicit = false;
+  return SSK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+Reg::~Reg() {
+  if (own_stream && stream) cudaStreamDestroy(stream);
+}
+
+int Reg::init(const ssk_registration_options &o, cudaStream_t s, bool own) {
+  opts = o;
+  stream = s;
+  own_stream = own;
+  SSK_REQUIRE(o.enable_ecc_registration, "only the ECC registration branch is implemented (enable_ecc_registration)");
+  if (int e = make_transform(&default_transform, o.motion_type)) return e;
+  current = default_transform;
+  ssk_ecch_options eo;
+  ssk_ecch_options_default(&eo);
+  // c_frame_registration.cc:602-612
+  eo.method = o.ecc.ecc_method;
+  eo.epsx = o.ecc.eps;
+  eo.input_smooth_sigma = o.ecc.input_smooth_sigma;
+  eo.reference_smooth_sigma = o.ecc.reference_smooth_sigma;
+  eo.update_step_scale = o.ecc.update_step_scale;
+  eo.max_iterations = o.ecc.max_iterations;
+  eo.maxlevel = o.ecc.ecch_max_level;
+  eo.minimum_image_size = o.ecc.ecch_minimum_image_size;
+  if (int e = ecch.init(eo, s)) return e;
+  ecch.motion_type = o.motion_type;
+  // c_frame_registration.cc:815-818
+  ecch.translation_first = o.motion_type != SSK_MOTION_TRANSLATION && o.ecc.ecch_estimate_translation_first &&
+                           o.ecc.ecch_max_level != 0;
+  ecch.check_rho = 1;
+  ecch.min_rho = o.ecc.min_rho;
+  ecch.final_scale = (o.ecc.scale > 0 && o.ecc.scale != 1) ? 1.0 / o.ecc.scale : 1.0;
+  return SSK_OK;
+}
+
+static int ecc_image_size(const ssk_registration_options &o, int rows, int cols, int *er, int *ec) {
+  if (o.ecc.scale > 0 && o.ecc.scale != 1) {
+    SSK_REQUIRE(std::fabs(o.ecc.scale - 0.5) < 1e-2, "ecc.scale must be 0.5 (cv::pyrDown branch of scaleImage) or 1");
+    *er = (rows + 1) / 2; *ec = (cols + 1) / 2;   // cv::pyrDown default dstsize
+  } else {
+    *er = rows; *ec = cols;
+  }
+  return SSK_OK;
+}
+
+int Reg::setup_reference(const Img &frame) {
+  SSK_REQUIRE(!(opts.ecc.normalization_scale > 0 && opts.ecc.normalization_noise > 0),
+              "ecc_normalize (normalization_scale > 0) is not implemented");
+  SSK_REQUIRE(!opts.ecc.replace_planetary_disk_with_mask, "replace_planetary_disk_with_mask is not implemented");
+  ref_rows = frame.rows; ref_cols = frame.cols;
+  if (int e = ecc_image_size(opts, frame.rows, frame.cols, &ecc_rows, &ecc_cols)) return e;
+  if (int e = staging.ensure((size_t)ecc_rows * ecc_cols * 4)) return e;
+  float *d_ecc = staging.as<float>();
+  if (ecc_rows != frame.rows) {
+    PyrDownArgs pd = {};
+    pd.src = frame; pd.dst = d_ecc; pd.dst_rows = ecc_rows; pd.dst_cols = ecc_cols; pd.batch = 1; pd.post_scale = 1.f;
+    if (int e = launch_pyrdown(pd, stream)) return e;
+  } else {
+    if (int e = launch_to_gray(frame, nullptr, d_ecc, nullptr, 1, stream)) return e;
+  }
+  if (int e = ecch.set_reference(d_ecc, ecc_rows, ecc_cols)) return e;
+  have_current = false;
+  return SSK_OK;
+}
+
+int Reg::prepare(const Img &geom, const void *const *d_frame_ptrs, int batch) {
+  SSK_REQUIRE(ecch.have_reference, "c_frame_registration: setup_reference_frame() must be called first");
+  SSK_REQUIRE(geom.rows == ref_rows && geom.cols == ref_cols, "current frame size differs from the reference frame size");
+  if (int e = ecch.reserve(batch)) return e;
+  if (ecc_rows != geom.rows) {
+    PyrDownArgs pd = {};
+    pd.src = geom; pd.src_ptrs = d_frame_ptrs;
+    pd.dst_ptrs = ecch.level0_scratch_ptrs(); pd.dst_rows = ecc_rows; pd.dst_cols = ecc_cols; pd.batch = batch; pd.post_scale = 1.f;
+    if (int e = launch_pyrdown(pd, stream)) return e;
+  } else {
+    if (int e = launch_to_gray(geom, d_frame_ptrs, nullptr, ecch.level0_scratch_ptrs(), batch, stream)) return e;
+  }
+  return ecch.prepare_current(ecch.level0_scratch_ptrs(), batch);
+}
+
+int Reg::register_batch(int batch) {
+  // c_frame_registration.cc:744: every frame restarts from the default parameters
+  return ecch.align(batch, default_transform);
+}
+
+}  // namespace ssk

@@ -1,0 +1,59 @@
+// Internal launch interface of the per-frame preparation and weight-map kernels (ssk_prep.cu).
+#pragma once
+#include "ssk_common.cuh"
+
+namespace ssk {
+
+constexpr int kMaxTaps = 31;
+
+// cv::pyrDown(src, dst, dstsize) ([1 4 6 4 1]/16 separable, BORDER_REFLECT_101, sample at 2x,2y).
+// Source: any depth/cn (colour is converted to gray first: cv::cvtColor(COLOR_BGR2GRAY)); destination CV_32FC1 dense.
+// Batched: src_ptrs[b] / dst_ptrs[b] are device arrays of per-frame pointers; if src_ptrs == null the single
+// pointers src.data / dst are used.
+struct PyrDownArgs {
+  Img src;                       // geometry/type (data used when src_ptrs == null)
+  const void *const *src_ptrs;   // device array [batch] or null
+  float *dst; float *const *dst_ptrs;
+  int dst_rows, dst_cols;
+  int batch;
+  float post_scale;              // multiplies the result (lpg: 1/(1+dscale)); 1 = none
+};
+int launch_pyrdown(const PyrDownArgs &a, cudaStream_t s);
+
+// cv::sepFilter2D(src, dst, CV_32F, kx, ky, anchor centre, BORDER_REPLICATE) on dense CV_32FC1 images.
+struct SepFilterArgs {
+  const float *src; const float *const *src_ptrs;
+  float *dst; float *const *dst_ptrs;
+  int rows, cols, batch;
+  int kxn, kyn;                  // odd tap counts
+  float kx[kMaxTaps], ky[kMaxTaps];
+};
+int launch_sepfilter(const SepFilterArgs &a, cudaStream_t s);
+
+// gray / depth conversion only (ecc.scale == 1): dst = CV_32FC1 dense
+int launch_to_gray(const Img &src, const void *const *src_ptrs, float *dst, float *const *dst_ptrs, int batch,
+                   cudaStream_t s);
+
+// W1: compute_local_variance_map (c_local_variance_sharpness_measure.cc:193-247) on a CV_32FC1 image M
+// (already pyrDown'ed `dscale` times):  G = morph-gradient(k x k, REPLICATE); map = G^3 s^3 + 0.05 Q;
+// out = resize(map, full size, INTER_LINEAR).
+struct W1Args {
+  const float *M; const float *const *M_ptrs;     // [batch] small images, rows x cols
+  int rows, cols;
+  int kradius;
+  double depth_scale;                             // 20 * 1 / maxval(depth)
+  float *gmap; float *const *gmap_ptrs;           // scratch rows x cols per frame
+  double *partials;                               // scratch [batch][2][nblocks]
+  double *stats;                                  // [batch][4]: sumG, sumG4, Q, add
+  float *out; float *const *out_ptrs;             // full_rows x full_cols per frame (dense)
+  int full_rows, full_cols;
+  int batch;
+};
+int w1_num_blocks(int rows, int cols);
+int launch_w1(const W1Args &a, cudaStream_t s);
+
+// erode 5x5 / 8U helpers for user masks
+int launch_erode5_u8(const uint8_t *src, int64_t sstep, uint8_t *dst, int64_t dstep, int rows, int cols,
+                     int border_replicate, cudaStream_t s);
+
+}  // namespace ssk

@@ -1,0 +1,101 @@
+// Process-wide runtime state: error string, launch counter, remap tables.
+#include "ssk_common.cuh"
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <mutex>
+#include <vector>
+
+namespace ssk {
+
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const std::string &msg) { g_err = msg; }
+const std::string &last_error() { return g_err; }
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  g_err = buf;
+  return SSK_ERR_CUDA;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int64_t launch_count() { return g_launches.load(); }
+
+// interpolateCubic (OpenCV imgproc, A = -0.75) evaluated in float; compiled with -ffp-contract=off
+static void cubic_coeffs_host(float x, float *c) {
+  const float A = -0.75f;
+  c[0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+  c[1] = ((A + 2) * x - (A + 3)) * x * x + 1;
+  c[2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+  c[3] = 1.f - c[0] - c[1] - c[2];
+}
+
+static int sat_short(float v) {
+  long r = lrintf(v);  // cvRound: round half to even
+  return (int)(r < -32768 ? -32768 : r > 32767 ? 32767 : r);
+}
+
+struct TableStore {
+  int device = -1;
+  float4 *cubic = nullptr;
+  short *itab = nullptr;
+};
+static std::mutex g_tab_mutex;
+static std::vector<TableStore> g_tabs;
+
+int get_tables(Tables *t) {
+  int dev = 0;
+  SSK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_tab_mutex);
+  for (auto &s : g_tabs) {
+    if (s.device == dev) { t->cubic = s.cubic; t->cubic_itab = s.itab; return SSK_OK; }
+  }
+  float coef[kInterTab][4];
+  for (int i = 0; i < kInterTab; ++i) cubic_coeffs_host((float)i * (1.0f / kInterTab), coef[i]);
+  // initInterTab2D(INTER_CUBIC, fixpt = true)
+  std::vector<short> itab(kInterTab * kInterTab * 16);
+  for (int i = 0; i < kInterTab; ++i) {
+    for (int j = 0; j < kInterTab; ++j) {
+      int it[4][4], isum = 0;
+      for (int k1 = 0; k1 < 4; ++k1)
+        for (int k2 = 0; k2 < 4; ++k2) {
+          const float v = coef[i][k1] * coef[j][k2];
+          isum += it[k1][k2] = sat_short(v * (float)kCoefScale);
+        }
+      if (isum != kCoefScale) {
+        const int diff = isum - kCoefScale;
+        int Mk1 = 2, Mk2 = 2, mk1 = 2, mk2 = 2;
+        for (int k1 = 2; k1 < 4; ++k1)
+          for (int k2 = 2; k2 < 4; ++k2) {
+            if (it[k1][k2] < it[mk1][mk2]) mk1 = k1, mk2 = k2;
+            else if (it[k1][k2] > it[Mk1][Mk2]) Mk1 = k1, Mk2 = k2;
+          }
+        if (diff < 0) it[Mk1][Mk2] -= diff;
+        else it[mk1][mk2] -= diff;
+      }
+      short *dst = &itab[(i * kInterTab + j) * 16];
+      for (int k = 0; k < 16; ++k) dst[k] = (short)it[k / 4][k % 4];
+    }
+  }
+  TableStore s;
+  s.device = dev;
+  SSK_CUDA(cudaMalloc(&s.cubic, sizeof(coef)));
+  SSK_CUDA(cudaMalloc(&s.itab, itab.size() * sizeof(short)));
+  SSK_CUDA(cudaMemcpy(s.cubic, coef, sizeof(coef), cudaMemcpyHostToDevice));
+  SSK_CUDA(cudaMemcpy(s.itab, itab.data(), itab.size() * sizeof(short), cudaMemcpyHostToDevice));
+  g_tabs.push_back(s);
+  t->cubic = s.cubic;
+  t->cubic_itab = s.itab;
+  return SSK_OK;
+}
+
+}  // namespace ssk
+
+extern "C" {
+const char *ssk_last_error(void) { return ssk::last_error().c_str(); }
+int ssk_version(void) { return 100; }
+int64_t ssk_kernel_launch_count(void) { return ssk::launch_count(); }
+}

@@ -1,0 +1,359 @@
+// ssk_stack_*: the per-frame loop of c_image_stacking_pipeline::process_input_sequence
+// (core/pipeline/c_image_stacking_pipeline/c_image_stacking_pipeline.cc:1358-1862) for batches of frames:
+//   compute_weights (:1466, 2013-2020) -> register_frame (:1539) -> custom_remap(frame, mask) (:1644-1651)
+//   -> custom_remap(weights, BORDER_CONSTANT) (:1653-1660) -> weights *= mask/255 (:1704-1714) -> add (:1753-1779)
+// Every stage is one batched kernel launch; frames never leave the device and the call is asynchronous.
+#include <cmath>
+#include <cstring>
+#include <new>
+#include "ssk_engine.cuh"
+
+using namespace ssk;
+
+namespace {
+
+__global__ void k_fill_jobs(const EccFrame *reg, const void *const *frame_ptrs, float *const *weight_ptrs, const double *w1_stats,
+                            FrameJob *jobs, int n, int *accumulated, int have_reg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  FrameJob j;
+  j.frame = frame_ptrs[i];
+  j.weights = weight_ptrs ? weight_ptrs[i] : nullptr;
+  // compute_local_variance_map releases the map for a flat frame (sum of gradients == 0): the pipeline then
+  // accumulates that frame with the plain 8U mask (current_weights.empty(), c_image_stacking_pipeline.cc:1704)
+  if (w1_stats && !(w1_stats[i * 4] > 0)) j.weights = nullptr;
+  if (have_reg) {
+    j.map = reg[i].map;
+    j.ok = reg[i].ok;
+  } else {
+    for (int k = 0; k < 9; ++k) j.map.c[k] = 0.f;
+    j.map.type = MAP_TRANSLATION;
+    j.ok = 1;
+  }
+  j.pad = 0;
+  jobs[i] = j;
+  if (j.ok) atomicAdd(accumulated, 1);
+}
+
+constexpr int kRing = 4;
+
+}  // namespace
+
+struct ssk_stack {
+  ssk_stack_options o;
+  cudaStream_t stream = nullptr;
+  ssk_reg reg_h;
+  ssk_acc acc_h;
+  Tables tab;
+  int max_batch = 0;
+  // geometry of the sequence (fixed by set_reference)
+  int rows = 0, cols = 0, type = -1, bpp = 0;
+  bool have_reference = false;
+  // per-slot device buffers
+  DevBuf frame_slots, weight_slots, half_slots, half2_slots, gmap_slots, partials, stats, jobs, counter;
+  DevBuf d_slot_ptrs, d_weight_ptrs, d_half_ptrs, d_half2_ptrs, d_gmap_ptrs;
+  DevBuf d_user_ptrs[kRing];
+  PinnedBuf h_user_ptrs[kRing];
+  cudaEvent_t ring_ev[kRing] = {};
+  int ring_pos = 0;
+  PinnedBuf h_counter;
+  int w1_rows = 0, w1_cols = 0, w1_nb = 0;
+  cudaEvent_t ev[5] = {};
+  DevBuf ref_staging;
+  ~ssk_stack() {
+    for (auto &e : ring_ev) if (e) cudaEventDestroy(e);
+    for (auto &e : ev) if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+static int stack_alloc_slots(ssk_stack *h) {
+  const int B = h->max_batch;
+  const int d = type_depth(h->type), cn = type_cn(h->type);
+  const size_t frame_bytes = (size_t)h->rows * h->cols * cn * depth_bytes(d);
+  const size_t npix = (size_t)h->rows * h->cols;
+  std::vector<void *> p(B);
+  if (int e = h->frame_slots.ensure(frame_bytes * B)) return e;
+  for (int b = 0; b < B; ++b) p[b] = h->frame_slots.as<char>() + frame_bytes * b;
+  if (int e = h->d_slot_ptrs.ensure(sizeof(void *) * B)) return e;
+  SSK_CUDA(cudaMemcpy(h->d_slot_ptrs.p, p.data(), sizeof(void *) * B, cudaMemcpyHostToDevice));
+  if (int e = h->jobs.ensure(sizeof(FrameJob) * B)) return e;
+  if (int e = h->counter.ensure(sizeof(int))) return e;
+  if (int e = h->h_counter.ensure(sizeof(int))) return e;
+  SSK_CUDA(cudaMemset(h->counter.p, 0, sizeof(int)));
+  for (int r = 0; r < kRing; ++r) {
+    if (int e = h->d_user_ptrs[r].ensure(sizeof(void *) * B)) return e;
+    if (int e = h->h_user_ptrs[r].ensure(sizeof(void *) * B)) return e;
+    if (!h->ring_ev[r]) SSK_CUDA(cudaEventCreateWithFlags(&h->ring_ev[r], cudaEventDisableTiming));
+  }
+  for (auto &e : h->ev) if (!e) SSK_CUDA(cudaEventCreate(&e));
+  if (h->o.accumulation_method == SSK_STACK_WEIGHTED_AVERAGE && h->o.sm_kradius > 0) {
+    // pdownscale chain sizes (c_local_variance_sharpness_measure.cc:28-52)
+    int r = h->rows, c = h->cols;
+    for (int l = 0; l < h->o.sm_dscale && std::min(r, c) >= 4; ++l) { r = (r + 1) / 2; c = (c + 1) / 2; }
+    h->w1_rows = r; h->w1_cols = c; h->w1_nb = w1_num_blocks(r, c);
+    const size_t half_px = (size_t)((h->rows + 1) / 2) * ((h->cols + 1) / 2);
+    if (int e = h->weight_slots.ensure(npix * 4 * B)) return e;
+    if (int e = h->half_slots.ensure(half_px * 4 * B)) return e;
+    if (int e = h->half2_slots.ensure(half_px * 4 * B)) return e;
+    if (int e = h->gmap_slots.ensure((size_t)r * c * 4 * B)) return e;
+    if (int e = h->partials.ensure((size_t)B * 2 * h->w1_nb * 8)) return e;
+    if (int e = h->stats.ensure((size_t)B * 4 * 8)) return e;
+    if (int e = h->d_weight_ptrs.ensure(sizeof(void *) * B)) return e;
+    if (int e = h->d_half_ptrs.ensure(sizeof(void *) * B)) return e;
+    if (int e = h->d_half2_ptrs.ensure(sizeof(void *) * B)) return e;
+    if (int e = h->d_gmap_ptrs.ensure(sizeof(void *) * B)) return e;
+    for (int b = 0; b < B; ++b) p[b] = h->weight_slots.as<float>() + npix * b;
+    SSK_CUDA(cudaMemcpy(h->d_weight_ptrs.p, p.data(), sizeof(void *) * B, cudaMemcpyHostToDevice));
+    for (int b = 0; b < B; ++b) p[b] = h->half_slots.as<float>() + half_px * b;
+    SSK_CUDA(cudaMemcpy(h->d_half_ptrs.p, p.data(), sizeof(void *) * B, cudaMemcpyHostToDevice));
+    for (int b = 0; b < B; ++b) p[b] = h->half2_slots.as<float>() + half_px * b;
+    SSK_CUDA(cudaMemcpy(h->d_half2_ptrs.p, p.data(), sizeof(void *) * B, cudaMemcpyHostToDevice));
+    for (int b = 0; b < B; ++b) p[b] = h->gmap_slots.as<float>() + (size_t)r * c * b;
+    SSK_CUDA(cudaMemcpy(h->d_gmap_ptrs.p, p.data(), sizeof(void *) * B, cudaMemcpyHostToDevice));
+  }
+  return SSK_OK;
+}
+
+extern "C" {
+
+void ssk_stack_options_default(ssk_stack_options *o) {
+  memset(o, 0, sizeof(*o));
+  ssk_registration_options_default(&o->registration);
+  o->registration.enable_ecc_registration = 1;
+  o->accumulation_method = SSK_STACK_AVERAGE;
+  o->sm_dscale = 1; o->sm_kradius = 1; o->sm_uscale = 0;   // c_image_stacking_pipeline.h:94-99
+  o->enable_registration = 1;
+  o->bayer_colorid = SSK_COLORID_BAYER_RGGB;
+  o->max_batch = 32;
+}
+
+int ssk_stack_create(const ssk_stack_options *opts, ssk_stack **out) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    cudaGetLastError();
+    set_error("no CUDA device available (this library has no CPU fallback)");
+    return SSK_ERR_CUDA;
+  }
+  SSK_REQUIRE(opts && out, "ssk_stack_create: null argument");
+  SSK_REQUIRE(opts->max_batch >= 1 && opts->max_batch <= 4096, "max_batch 1..4096");
+  SSK_REQUIRE(opts->accumulation_method == SSK_STACK_AVERAGE || opts->accumulation_method == SSK_STACK_WEIGHTED_AVERAGE,
+              "ssk_stack: average and weighted_average are fused; bayer_average goes through ssk_reg_* + ssk_acc_*");
+  SSK_REQUIRE(opts->sm_uscale == 0, "sharpness_measure.uscale > 0 is not implemented");
+  ssk_stack *h = new (std::nothrow) ssk_stack();
+  SSK_REQUIRE(h, "out of memory");
+  h->o = *opts;
+  h->max_batch = opts->max_batch;
+  cudaError_t ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (ce != cudaSuccess) { delete h; return cuda_fail(ce, "cudaStreamCreate", __FILE__, __LINE__); }
+  if (opts->enable_registration) {
+    if (int e = h->reg_h.r.init(opts->registration, h->stream, false)) { delete h; return e; }
+  }
+  h->acc_h.a.kind = SSK_ACC_WEIGHTED_AVERAGE;
+  h->acc_h.a.stream = h->stream;
+  if (int e = get_tables(&h->tab)) { delete h; return e; }
+  *out = h;
+  return SSK_OK;
+}
+
+int ssk_stack_destroy(ssk_stack *h) { delete h; return SSK_OK; }
+
+int ssk_stack_set_reference(ssk_stack *h, const ssk_mat *image, const ssk_mat *mask, int bpp) {
+  SSK_REQUIRE(h && image && image->data, "ssk_stack_set_reference: null argument");
+  SSK_REQUIRE(!mask, "reference masks are not implemented yet");
+  const int d = type_depth(image->type), cn = type_cn(image->type);
+  SSK_REQUIRE(depth_bytes(d) && (cn == 1 || cn == 3), "frames must be 8U/16U/32F with 1 or 3 channels");
+  h->rows = image->rows; h->cols = image->cols; h->type = image->type; h->bpp = bpp;
+  if (h->o.enable_registration) {
+    Img im;
+    im.rows = image->rows; im.cols = image->cols; im.depth = d; im.cn = cn; im.scale = bpp_scale(d, bpp);
+    const size_t rowb = (size_t)image->cols * cn * depth_bytes(d);
+    if (image->mem == SSK_MEM_DEVICE) { im.data = image->data; im.step = image->step; }
+    else {
+      if (int e = h->ref_staging.ensure(rowb * image->rows)) return e;
+      SSK_CUDA(cudaMemcpy2DAsync(h->ref_staging.p, rowb, image->data, image->step, rowb, image->rows, cudaMemcpyHostToDevice, h->stream));
+      im.data = h->ref_staging.p; im.step = (int64_t)rowb;
+    }
+    if (int e = h->reg_h.r.setup_reference(im)) return e;
+    if (int e = h->reg_h.r.ecch.reserve(h->max_batch)) return e;
+  }
+  if (int e = stack_alloc_slots(h)) return e;
+  if (int e = h->acc_h.a.ensure(h->rows, h->cols, cn)) return e;
+  SSK_CUDA(cudaStreamSynchronize(h->stream));
+  h->have_reference = true;
+  return SSK_OK;
+}
+
+static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n) {
+  const int d = type_depth(h->type), cn = type_cn(h->type);
+  const size_t rowb = (size_t)h->cols * cn * depth_bytes(d);
+  cudaStream_t s = h->stream;
+  Img geom;
+  geom.rows = h->rows; geom.cols = h->cols; geom.depth = d; geom.cn = cn; geom.scale = bpp_scale(d, h->bpp);
+  geom.data = nullptr;
+  const void *const *d_frame_ptrs;
+  if (frames[0].mem == SSK_MEM_DEVICE) {
+    // frames already resident: upload this chunk's pointer table through a small pinned ring
+    const int r = h->ring_pos;
+    h->ring_pos = (h->ring_pos + 1) % kRing;
+    SSK_CUDA(cudaEventSynchronize(h->ring_ev[r]));
+    void **hp = h->h_user_ptrs[r].as<void *>();
+    for (int i = 0; i < n; ++i) {
+      SSK_REQUIRE(frames[i].mem == SSK_MEM_DEVICE && frames[i].step == frames[0].step, "frames of a call must share memory space and step");
+      hp[i] = frames[i].data;
+    }
+    SSK_CUDA(cudaMemcpyAsync(h->d_user_ptrs[r].p, hp, sizeof(void *) * n, cudaMemcpyHostToDevice, s));
+    SSK_CUDA(cudaEventRecord(h->ring_ev[r], s));
+    d_frame_ptrs = h->d_user_ptrs[r].as<const void *>();
+    geom.step = frames[0].step;
+  } else {
+    for (int i = 0; i < n; ++i) {
+      SSK_REQUIRE(frames[i].mem == SSK_MEM_HOST, "frames of a call must share memory space");
+      SSK_CUDA(cudaMemcpy2DAsync(h->frame_slots.as<char>() + rowb * h->rows * i, rowb, frames[i].data, frames[i].step, rowb, h->rows,
+                                 cudaMemcpyHostToDevice, s));
+    }
+    d_frame_ptrs = h->d_slot_ptrs.as<const void *>();
+    geom.step = (int64_t)rowb;
+  }
+  SSK_CUDA(cudaEventRecord(h->ev[0], s));
+
+  // ---- registration prep + ECC
+  const bool weighted = h->o.accumulation_method == SSK_STACK_WEIGHTED_AVERAGE && h->o.sm_kradius > 0;
+  if (h->o.enable_registration) {
+    if (int e = h->reg_h.r.prepare(geom, d_frame_ptrs, n)) return e;
+  }
+  SSK_CUDA(cudaEventRecord(h->ev[1], s));
+
+  // ---- W1 weights on the unaligned frame
+  if (weighted) {
+    const float *const *Mptrs = nullptr;
+    if (h->o.sm_dscale > 0 && std::min(h->rows, h->cols) >= 4) {
+      Img cur = geom;
+      const void *const *src_ptrs = d_frame_ptrs;
+      float *const *dst_ptrs = h->d_half_ptrs.as<float *>();
+      for (int l = 0; l < h->o.sm_dscale; ++l) {
+        const int nr = (cur.rows + 1) / 2, nc = (cur.cols + 1) / 2;
+        PyrDownArgs pd = {};
+        pd.src = cur; pd.src_ptrs = src_ptrs; pd.dst_ptrs = dst_ptrs; pd.dst_rows = nr; pd.dst_cols = nc; pd.batch = n; pd.post_scale = 1.f;
+        if (int e = launch_pyrdown(pd, s)) return e;
+        cur.step = (int64_t)nc * 4; cur.rows = nr; cur.cols = nc; cur.depth = SSK_32F; cur.cn = 1; cur.scale = 1.f;
+        Mptrs = dst_ptrs;
+        src_ptrs = reinterpret_cast<const void *const *>(dst_ptrs);
+        dst_ptrs = dst_ptrs == h->d_half_ptrs.as<float *>() ? h->d_half2_ptrs.as<float *>() : h->d_half_ptrs.as<float *>();
+        if (std::min(nr, nc) < 4) break;
+      }
+    } else {
+      if (int e = launch_to_gray(geom, d_frame_ptrs, nullptr, h->d_half_ptrs.as<float *>(), n, s)) return e;
+      Mptrs = h->d_half_ptrs.as<float *>();
+    }
+    W1Args w = {};
+    w.M_ptrs = Mptrs; w.rows = h->w1_rows; w.cols = h->w1_cols; w.kradius = std::max(1, h->o.sm_kradius);
+    w.depth_scale = 20.0;   // frames are CV_32F when they reach compute_weights
+    w.gmap_ptrs = h->d_gmap_ptrs.as<float *>(); w.partials = h->partials.as<double>(); w.stats = h->stats.as<double>();
+    w.out_ptrs = h->d_weight_ptrs.as<float *>(); w.full_rows = h->rows; w.full_cols = h->cols; w.batch = n;
+    if (int e = launch_w1(w, s)) return e;
+  }
+  SSK_CUDA(cudaEventRecord(h->ev[2], s));
+
+  if (h->o.enable_registration) {
+    if (int e = h->reg_h.r.register_batch(n)) return e;
+  }
+  SSK_CUDA(cudaEventRecord(h->ev[3], s));
+
+  // ---- fused warp + mask + weights + accumulate
+  k_fill_jobs<<<div_up(n, 128), 128, 0, s>>>(h->o.enable_registration ? h->reg_h.r.ecch.device_frames() : nullptr, d_frame_ptrs,
+                                             weighted ? h->d_weight_ptrs.as<float *>() : nullptr,
+                                             weighted ? h->stats.as<double>() : nullptr, h->jobs.as<FrameJob>(), n,
+                                             h->counter.as<int>(), h->o.enable_registration ? 1 : 0);
+  SSK_LAUNCH_CHECK();
+  WarpAccArgs a = {};
+  a.jobs = h->jobs.as<FrameJob>(); a.njobs = n;
+  a.rows = h->rows; a.cols = h->cols; a.src_rows = h->rows; a.src_cols = h->cols;
+  a.src_step = geom.step; a.w_step = (int64_t)h->cols * 4;
+  a.depth = d; a.cn = cn; a.scale = geom.scale;
+  const ssk_registration_options &ro = h->o.registration;
+  a.interp = h->o.enable_registration ? ro.interpolation : SSK_INTER_NEAREST;
+  a.border = ro.border_mode;
+  for (int i = 0; i < 4; ++i) a.bval[i] = (float)ro.border_value[i];
+  a.use_weights = weighted ? 1 : 0;
+  a.acc = h->acc_h.a.acc.as<float>(); a.wacc = h->acc_h.a.wacc.as<float>();
+  if (int e = launch_warp_accumulate(a, h->tab, s)) return e;
+  SSK_CUDA(cudaEventRecord(h->ev[4], s));
+  return SSK_OK;
+}
+
+int ssk_stack_add_frames_async(ssk_stack *h, const ssk_mat *frames, int n, int bpp) {
+  SSK_REQUIRE(h && frames && n >= 0, "ssk_stack_add_frames: bad argument");
+  SSK_REQUIRE(h->have_reference, "ssk_stack: set_reference must be called first");
+  SSK_REQUIRE(bpp == h->bpp, "ssk_stack: bpp differs from the reference frame's");
+  for (int i = 0; i < n; ++i) {
+    SSK_REQUIRE(frames[i].data && frames[i].rows == h->rows && frames[i].cols == h->cols && frames[i].type == h->type,
+                "ssk_stack: frame geometry/type differs from the reference frame");
+  }
+  for (int i0 = 0; i0 < n; i0 += h->max_batch) {
+    const int m = std::min(h->max_batch, n - i0);
+    if (int e = stack_process_chunk(h, frames + i0, m)) return e;
+  }
+  return SSK_OK;
+}
+
+int ssk_stack_sync(ssk_stack *h) {
+  SSK_REQUIRE(h, "null handle");
+  SSK_CUDA(cudaMemcpyAsync(h->h_counter.p, h->counter.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  SSK_CUDA(cudaStreamSynchronize(h->stream));
+  h->acc_h.a.frames = *h->h_counter.as<int>();
+  return SSK_OK;
+}
+
+int ssk_stack_add_frames(ssk_stack *h, const ssk_mat *frames, int n, int bpp, ssk_transform *transforms_out,
+                         ssk_ecc_status *status_out) {
+  SSK_REQUIRE(h && frames && n >= 0, "ssk_stack_add_frames: bad argument");
+  SSK_REQUIRE(h->have_reference, "ssk_stack: set_reference must be called first");
+  for (int i0 = 0; i0 < n; i0 += h->max_batch) {
+    const int m = std::min(h->max_batch, n - i0);
+    if (int e = ssk_stack_add_frames_async(h, frames + i0, m, bpp)) return e;
+    if (h->o.enable_registration && (transforms_out || status_out)) {
+      if (int e = h->reg_h.r.ecch.download_frames(m)) return e;
+      SSK_CUDA(cudaStreamSynchronize(h->stream));
+      const EccFrame *f = h->reg_h.r.ecch.host_frames();
+      for (int i = 0; i < m; ++i) {
+        if (transforms_out) transforms_out[i0 + i] = f[i].t;
+        if (status_out) {
+          ssk_ecc_status &st = status_out[i0 + i];
+          st.rho = f[i].rho; st.min_rho = h->o.registration.ecc.min_rho; st.eps = f[i].eps;
+          st.num_iterations = f[i].num_iterations; st.max_iterations = h->o.registration.ecc.max_iterations;
+          st.ok = f[i].ok; st.failed = f[i].failed;
+        }
+      }
+    }
+  }
+  return ssk_stack_sync(h);
+}
+
+int ssk_stack_compute(ssk_stack *h, ssk_mat *avg, ssk_mat *mask) {
+  SSK_REQUIRE(h, "null handle");
+  if (int e = ssk_stack_sync(h)) return e;
+  return ssk_acc_compute(&h->acc_h, avg, mask, 1.0);
+}
+
+int ssk_stack_accumulated_frames(ssk_stack *h) {
+  if (!h) return 0;
+  if (ssk_stack_sync(h)) return -1;
+  return h->acc_h.a.frames;
+}
+
+ssk_acc *ssk_stack_accumulator(ssk_stack *h) { return h ? &h->acc_h : nullptr; }
+ssk_reg *ssk_stack_registration(ssk_stack *h) { return h ? &h->reg_h : nullptr; }
+
+void *ssk_stack_stream(ssk_stack *h) { return h ? (void *)h->stream : nullptr; }
+
+int ssk_stack_stage_times(ssk_stack *h, float ms[4]) {
+  SSK_REQUIRE(h && ms, "null argument");
+  SSK_CUDA(cudaStreamSynchronize(h->stream));
+  float t[4];
+  for (int i = 0; i < 4; ++i) SSK_CUDA(cudaEventElapsedTime(&t[i], h->ev[i], h->ev[i + 1]));
+  ms[0] = t[0]; ms[1] = t[1]; ms[2] = t[2]; ms[3] = t[3];
+  return SSK_OK;
+}
+
+}  // extern "C"

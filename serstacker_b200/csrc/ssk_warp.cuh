@@ -1,0 +1,84 @@
+// Internal launch interface of the warp / accumulate kernels (ssk_warp.cu).
+#pragma once
+#include "ssk_common.cuh"
+
+namespace ssk {
+
+// One frame of a batch as the fused warp+accumulate kernel sees it.  The registration kernel writes
+// `map` and `ok` on the device, so a batch never round-trips through the host.
+struct FrameJob {
+  const void *frame;      // device pointer, geometry/type common to the batch
+  const float *weights;   // full-resolution CV_32FC1 weight map (or null)
+  MapCoef map;            // reference pixel -> frame pixel
+  int ok;                 // 0: frame dropped (registration failed)
+  int pad;
+};
+
+struct WarpAccArgs {
+  const FrameJob *jobs;   // device array [njobs]
+  int njobs;
+  int rows, cols;         // output (= accumulator = reference frame) size
+  int src_rows, src_cols; // frame size
+  int64_t src_step;       // bytes
+  int64_t w_step;         // bytes (weight maps)
+  int depth, cn;
+  float scale;            // sample scale for integer frames
+  int interp;             // SSK_INTER_*
+  int border;             // SSK_BORDER_* for the frame
+  float bval[4];
+  int use_weights;        // 1: weighted_average (w = remap(weights, interp, CONSTANT 0) * mask)
+  float *acc;             // running mean, rows x cols x cn (dense)
+  float *wacc;            // running weight sum, rows x cols (dense)
+};
+
+int launch_warp_accumulate(const WarpAccArgs &a, const Tables &tab, cudaStream_t stream);
+
+// cv::remap of a CV_32F image (cn 1..4) by an analytic map or an explicit CV_32FC2 map.
+struct RemapArgs {
+  Img src;
+  float *dst; int64_t dst_step;          // CV_32F, same cn
+  int rows, cols;                        // dst size
+  MapCoef map; const float2 *rmap; int64_t rmap_step;   // rmap != null overrides map
+  int interp, border; float bval[4];
+};
+int launch_remap(const RemapArgs &a, const Tables &tab, cudaStream_t stream);
+
+// dst_mask = erode5x5(remap(src_mask or all-255, interp, CONSTANT 0) >= 255), border value 255.
+struct RemapMaskArgs {
+  const uint8_t *src_mask; int64_t src_mask_step;   // null => all-255 source
+  int src_rows, src_cols;
+  uint8_t *dst; int64_t dst_step;
+  uint8_t *tmp;                                    // rows*cols scratch (pre-erode)
+  int rows, cols;
+  MapCoef map; const float2 *rmap; int64_t rmap_step;
+  int interp;
+};
+int launch_remap_mask(const RemapMaskArgs &a, const Tables &tab, cudaStream_t stream);
+
+// c_weigthed_average::add without warp (c_frame_accumulation.cc:20-129)
+struct AccAddArgs {
+  Img src;
+  const void *weights; int64_t w_step; int wtype;  // -1 none, SSK_8UC1, SSK_32FC1
+  float *acc; float *wacc;
+};
+int launch_acc_add(const AccAddArgs &a, cudaStream_t stream);
+
+// compute(): avg = acc * dscale, mask = W > 0
+int launch_acc_compute(const float *acc, const float *wacc, int rows, int cols, int cn, float dscale,
+                       float *avg, int64_t avg_step, uint8_t *mask, int64_t mask_step, cudaStream_t stream);
+// running mean <-> sum form
+int launch_acc_sum_form(float *acc, const float *wacc, int64_t npix, int cn, int to_sum, cudaStream_t stream);
+
+// c_bayer_average (c_frame_accumulation.cc:988-1126 / 1205-1238)
+struct BayerAccArgs {
+  Img src;                                   // raw bayer, cn = 1
+  MapCoef map; const float2 *rmap; int64_t rmap_step; int have_map;
+  const void *weights; int64_t w_step; int wtype;
+  int colorid;
+  float *acc; float *cntr;                   // rows x cols x 3
+};
+int launch_bayer_add(const BayerAccArgs &a, cudaStream_t stream);
+int launch_bayer_compute(const float *acc, const float *cntr, int rows, int cols, float *avg, int64_t avg_step,
+                         uint8_t *mask, int64_t mask_step, cudaStream_t stream);
+
+}  // namespace ssk

@@ -1,0 +1,68 @@
+"""CPU: the numpy model of cv::remap (oracle/cvmodel.py) - the specification the CUDA samplers are written
+to - against cv2 itself."""
+import numpy as np
+import cv2
+import pytest
+
+from oracle import cvmodel as m
+from oracle import transforms as tf
+
+
+def _maps(rng, w, h, n=4):
+    t = tf.AffineTransform()
+    for _ in range(n):
+        p = np.array([1 + rng.normal(0, 0.02), rng.normal(0, 0.02), rng.normal(0, 5),
+                      rng.normal(0, 0.02), 1 + rng.normal(0, 0.02), rng.normal(0, 5)], np.float32)
+        yield t.create_remap((w, h), p)
+
+
+@pytest.mark.parametrize("interp,ci", [("linear", cv2.INTER_LINEAR), ("cubic", cv2.INTER_CUBIC), ("nearest", cv2.INTER_NEAREST)])
+@pytest.mark.parametrize("border", [m.BORDER_REPLICATE, m.BORDER_REFLECT101, m.BORDER_CONSTANT, m.BORDER_REFLECT])
+def test_remap_f32_model_matches_cv2(interp, ci, border):
+    rng = np.random.default_rng(1)
+    h, w = 47, 61
+    src = rng.random((h, w)).astype(np.float32)
+    for rmap in _maps(rng, w, h):
+        ref = cv2.remap(src, rmap, None, ci, borderMode=border, borderValue=0.25)
+        mine = m.remap_f32(src, rmap, interp, border, 0.25)
+        assert np.abs(ref - mine).max() <= (1e-6 if interp == "cubic" else 2e-7)
+
+
+@pytest.mark.parametrize("interp,ci", [("linear", cv2.INTER_LINEAR), ("nearest", cv2.INTER_NEAREST)])
+def test_remap_transparent_model_matches_cv2(interp, ci):
+    rng = np.random.default_rng(2)
+    h, w = 40, 52
+    src = rng.random((h, w)).astype(np.float32)
+    for rmap in _maps(rng, w, h):
+        dst0 = np.full((h, w), 7.0, np.float32)
+        ref = cv2.remap(src, rmap, None, ci, dst=dst0.copy(), borderMode=cv2.BORDER_TRANSPARENT)
+        mine = m.remap_f32(src, rmap, interp, m.BORDER_TRANSPARENT, 0.0, dst=dst0)
+        assert np.abs(ref - mine).max() <= 2e-7
+
+
+@pytest.mark.parametrize("interp,ci", [("linear", cv2.INTER_LINEAR), ("cubic", cv2.INTER_CUBIC)])
+def test_mask_fixed_point_model_matches_cv2(interp, ci):
+    rng = np.random.default_rng(3)
+    h, w = 45, 57
+    for rmap in _maps(rng, w, h, n=6):
+        ref = cv2.remap(np.full((h, w), 255, np.uint8), rmap, None, ci, borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+        for th in (255, 254, 250):
+            v, val = m.remap_u8_all255_valid((w, h), rmap, interp, th)
+            assert np.array_equal(ref >= th, v)
+            assert np.array_equal(ref.astype(int), val)
+
+
+def test_bilinear_all255_thresholds_coincide():
+    """With an all-255 source the >=250 / >=254 / >=255 tests select the same pixels (bilinear): the CUDA
+    kernels use one closed form for all three call sites (ecc2.cc:128, 215, 1312)."""
+    rng = np.random.default_rng(4)
+    h, w = 33, 41
+    for rmap in _maps(rng, w, h, n=8):
+        a, _ = m.remap_u8_all255_valid((w, h), rmap, "linear", 255)
+        b, _ = m.remap_u8_all255_valid((w, h), rmap, "linear", 254)
+        c, _ = m.remap_u8_all255_valid((w, h), rmap, "linear", 250)
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+        ix, fx = m.quantize(rmap[..., 0])
+        iy, fy = m.quantize(rmap[..., 1])
+        closed = (ix >= 0) & (iy >= 0) & (ix < w) & (iy < h) & ((fx == 0) | (ix + 1 < w)) & ((fy == 0) | (iy + 1 < h))
+        assert np.array_equal(a, closed)

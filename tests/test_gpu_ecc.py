@@ -1,0 +1,92 @@
+"""GPU parity: the persistent ECC kernel (K2/K3/K4) against the oracle solvers, per method and transform."""
+import numpy as np
+import cv2
+import pytest
+
+from oracle import ecc as oecc
+from oracle import transforms as otf
+from oracle import registration as oreg
+from serstacker_b200 import synth
+from helpers import map_diff_px
+
+pytestmark = pytest.mark.gpu
+
+METHODS = [oecc.ECC_ALIGN_FORWARD_ADDITIVE, oecc.ECC_ALIGN_INVERSE_COMPOSITIONAL, oecc.ECC_ALIGN_LM,
+           oecc.ECC_ALIGN_INVERSE_COMPOSITIONAL_LM]
+
+
+def _seq(w, h, n, seed, rot=0.0, scale=0.0, sigma_t=2.0):
+    frames, mats, _ = synth.make_planet_sequence(w, h, n, seed, sigma_t=sigma_t, sigma_rot_deg=rot, sigma_scale=scale, dtype="f32")
+    return frames, mats
+
+
+@pytest.mark.parametrize("method", METHODS)
+@pytest.mark.parametrize("motion", [0, 3, 1, 2, 4])
+@pytest.mark.parametrize("maxlevel", [0, -1])
+def test_ecch_align_matches_oracle(gpu, method, motion, maxlevel):
+    """c_ecch::align on a half-resolution-like image: same trajectory => same parameters (<= 1e-3 px)."""
+    from serstacker_b200 import api
+    frames, _ = _seq(320, 240, 4, seed=11 + motion, rot=0.2 if motion else 0.0, scale=0.002 if motion in (2, 3, 4) else 0.0)
+    kw = dict(maxlevel=maxlevel, minimum_image_size=16, epsx=0.05, max_iterations=30, update_step_scale=1.0)
+    ot = otf.create_image_transform(motion)
+    o = oecc.EccH(ot, method=method, **kw)
+    o.set_reference_image(frames[0], None)
+    gt = api.create_image_transform(motion)
+    g = api.c_ecch(gt, method=method, **kw)
+    g.set_reference_image(frames[0])
+    worst = 0.0
+    for f in frames[1:]:
+        ot.reset()
+        gt.set_parameters(ot.parameters())
+        o.align(f, None)
+        g.align(f)
+        d = map_diff_px(motion, gt.parameters(), ot.parameters(), (320, 240))
+        worst = max(worst, d)
+        assert g.num_iterations() == o.num_iterations, (g.num_iterations(), o.num_iterations, d)
+    assert worst <= 1e-3, worst
+
+
+@pytest.mark.parametrize("method", METHODS)
+@pytest.mark.parametrize("motion,tfirst", [(0, True), (3, True), (3, False), (4, True), (1, True), (2, False)])
+def test_register_frame_matches_oracle(gpu, method, motion, tfirst):
+    """c_frame_registration::register_frame incl. scaleImage, translation-first, rho gate, scale back."""
+    from serstacker_b200 import api
+    frames, _ = _seq(400, 300, 5, seed=31 + motion, rot=0.15 if motion else 0.0, scale=0.002 if motion in (2, 3, 4) else 0.0, sigma_t=3.0)
+    oo = oreg.ImageRegistrationOptions(motion_type=motion)
+    oo.ecc.ecc_method = method
+    oo.ecc.ecch_max_level = -1
+    oo.ecc.ecch_estimate_translation_first = tfirst
+    oo.ecc.update_step_scale = 1.0 if method in (oecc.ECC_ALIGN_LM,) else 1.5
+    o = oreg.FrameRegistration(oo)
+    o.setup_reference_frame(frames[0])
+    go = api.registration_options(motion_type=motion, ecc=dict(ecc_method=method, ecch_max_level=-1,
+                                                               ecch_estimate_translation_first=int(tfirst),
+                                                               update_step_scale=oo.ecc.update_step_scale))
+    g = api.c_frame_registration(go)
+    g.setup_reference_frame(frames[0])
+    for f in frames:
+        ok_o = o.register_frame(f)
+        ok_g = g.register_frame(f)
+        assert ok_o == ok_g
+        assert abs(g.status.rho - o.status.rho) <= 1e-4
+        if ok_o:
+            d = map_diff_px(motion, g.image_transform_parameters(), o.image_transform.parameters(), (400, 300))
+            assert d <= 1e-3, (d, g.status.num_iterations, o.status.num_iterations)
+            assert g.status.num_iterations == o.status.num_iterations
+
+
+def test_low_correlation_frame_is_dropped(gpu):
+    from serstacker_b200 import api
+    frames, _ = _seq(320, 240, 2, seed=5)
+    rng = np.random.default_rng(0)
+    junk = rng.random((240, 320)).astype(np.float32)
+    go = api.registration_options(motion_type=0, ecc=dict(ecc_method=oecc.ECC_ALIGN_FORWARD_ADDITIVE))
+    g = api.c_frame_registration(go)
+    g.setup_reference_frame(frames[0])
+    assert g.register_frame(frames[1]) is True
+    assert g.register_frame(junk) is False
+    oo = oreg.ImageRegistrationOptions(motion_type=0)
+    oo.ecc.ecc_method = oecc.ECC_ALIGN_FORWARD_ADDITIVE
+    o = oreg.FrameRegistration(oo)
+    o.setup_reference_frame(frames[0])
+    assert o.register_frame(junk) is False

@@ -1,0 +1,60 @@
+"""GPU parity: K1 (ECC image preparation, pyramids) and K6 (W1 weight map) against the oracle / cv2."""
+import numpy as np
+import cv2
+import pytest
+
+from oracle import ecc as oecc
+from oracle import weights as ow
+from serstacker_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _frame(w, h, seed, dtype="f32"):
+    frames, _, bpp = synth.make_planet_sequence(w, h, 1, seed, sigma_t=0, dtype=dtype)
+    return frames[0], bpp
+
+
+@pytest.mark.parametrize("size", [(320, 240), (333, 251), (960, 540)])
+@pytest.mark.parametrize("sigma", [1.0, 0.0, 1.7])
+def test_reference_pyramid_matches_oracle(gpu, size, sigma):
+    from serstacker_b200 import api
+    img, _ = _frame(size[0], size[1], 3)
+    o = oecc.EccH(oecc_transform(), maxlevel=-1, minimum_image_size=16, reference_smooth_sigma=sigma)
+    o.set_reference_image(img, None)
+    g = api.c_ecch(None, maxlevel=-1, minimum_image_size=16, reference_smooth_sigma=sigma)
+    g.set_reference_image(img)
+    assert g.num_levels() == len(o.pyramid)
+    for l, e in enumerate(o.pyramid):
+        want = e.reference_image
+        assert g.level_size(l) == (want.shape[1], want.shape[0])
+        got = g.reference_image(l)
+        assert np.abs(got - want).max() <= 2e-6, (l, np.abs(got - want).max())
+
+
+def oecc_transform():
+    from oracle import transforms as otf
+    return otf.TranslationTransform()
+
+
+def test_single_level_default(gpu):
+    """ecch_max_level = 0 yields a single-level pyramid (ecc2.cc:1015)."""
+    from serstacker_b200 import api
+    img, _ = _frame(200, 160, 4)
+    g = api.c_ecch(None, maxlevel=0)
+    g.set_reference_image(img)
+    assert g.num_levels() == 1
+
+
+@pytest.mark.parametrize("size", [(320, 240), (301, 203), (1920, 1080)])
+@pytest.mark.parametrize("kradius,dscale", [(1, 1), (2, 1), (1, 0), (1, 2)])
+def test_local_variance_map_matches_oracle(gpu, size, kradius, dscale):
+    from serstacker_b200 import api
+    if size[0] > 1000 and (kradius, dscale) != (1, 1):
+        pytest.skip("full size only for the default options")
+    img, _ = _frame(size[0], size[1], 7)
+    Qo, Mo = ow.compute_local_variance_map(img, dscale=dscale, kradius=kradius, uscale=0)
+    Qg, Mg = api.compute_local_variance_map(img, dscale=dscale, kradius=kradius, uscale=0)
+    assert abs(Qg - Qo) <= 2e-5 * abs(Qo)
+    scale = np.abs(Mo).max()
+    assert np.abs(Mg - Mo).max() <= 5e-6 * scale, np.abs(Mg - Mo).max() / scale

@@ -1,0 +1,160 @@
+"""GPU parity: accumulators and the fused per-frame loop (K5, P1) against the oracle pipeline."""
+import numpy as np
+import cv2
+import pytest
+
+from oracle import accumulation as oacc
+from oracle import ecc as oecc
+from oracle import pipeline as opl
+from oracle import transforms as otf
+from serstacker_b200 import synth
+from helpers import map_diff_px, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype,cn", [(np.float32, 1), (np.float32, 3), (np.uint16, 1), (np.uint8, 3)])
+@pytest.mark.parametrize("wmode", ["none", "mask", "weights"])
+def test_weighted_average_add_matches_oracle(gpu, dtype, cn, wmode):
+    from serstacker_b200 import api
+    rng = np.random.default_rng(1)
+    h, w = 37, 53
+    o, g = oacc.WeightedAverage(), api.c_weigthed_average()
+    bpp = {np.float32: 0, np.uint16: 16, np.uint8: 8}[dtype]
+    for i in range(6):
+        if dtype == np.float32:
+            f = rng.random((h, w, cn)).astype(np.float32)
+        else:
+            f = rng.integers(0, np.iinfo(dtype).max, (h, w, cn)).astype(dtype)
+        f = f.reshape(h, w) if cn == 1 else f
+        wts = None
+        if wmode == "mask":
+            wts = ((rng.random((h, w)) > 0.3) * 255).astype(np.uint8)
+        elif wmode == "weights":
+            wts = (rng.random((h, w)) - 0.2).astype(np.float32)   # some non-positive weights are skipped
+        o.add(opl.to_float_frame(f, bpp) if dtype != np.float32 else f, wts)
+        g.add(f, wts, bpp=bpp)
+    ao, mo = o.compute()
+    ag, mg = g.compute()
+    assert g.accumulated_frames() == 6
+    assert np.array_equal(mo, mg)
+    assert np.abs(ag - ao).max() <= 2e-6 * max(1.0, np.abs(ao).max())
+    assert np.allclose(g.get_acc_counters(), o.get_acc_counters(), rtol=1e-6, atol=1e-6)
+
+
+def test_accumulator_reinitialize_and_sum_form(gpu):
+    from serstacker_b200 import api, capi
+    rng = np.random.default_rng(2)
+    a = rng.random((20, 30)).astype(np.float32)
+    w = (rng.random((20, 30)) * 5).astype(np.float32)
+    g = api.c_weigthed_average()
+    g.reinitialize(a, w)
+    capi.check(capi.lib.ssk_acc_to_sum_form(g._h))
+    s, _ = g.compute()
+    assert np.allclose(s, a * w, rtol=1e-6)
+    capi.check(capi.lib.ssk_acc_from_sum_form(g._h, 3))
+    b, _ = g.compute()
+    assert np.allclose(b, a, rtol=1e-6, atol=1e-7)
+    assert g.accumulated_frames() == 3
+
+
+@pytest.mark.parametrize("colorid", [8, 9, 10, 11])
+@pytest.mark.parametrize("mapped", [False, True])
+def test_bayer_average_matches_oracle(gpu, colorid, mapped):
+    from serstacker_b200 import api
+    frames, shifts, bpp = synth.make_bayer_sequence(96, 64, 4, seed=3)
+    o, g = oacc.BayerAverage(), api.c_bayer_average()
+    o.set_bayer_pattern(colorid)
+    g.set_bayer_pattern(colorid)
+    rng = np.random.default_rng(4)
+    for f, (tx, ty) in zip(frames, shifts):
+        ff = opl.to_float_frame(f, bpp)
+        mask = ((rng.random(f.shape) > 0.1) * 255).astype(np.uint8)
+        if mapped:
+            t = otf.TranslationTransform(-tx + 0.3, -ty - 0.4)
+            rmap = t.create_remap((96, 64))
+            o.set_remap(rmap)
+            g.set_remap(rmap=rmap)
+        o.add(ff, mask)
+        g.add(f, mask, bpp=bpp)
+    ao, mo = o.compute()
+    ag, mg = g.compute()
+    assert np.array_equal(mo, mg)
+    assert np.abs(ag - ao).max() <= 1e-6
+
+
+def _config1_like(n=10, size=(320, 240)):
+    frames, mats, bpp = synth.make_planet_sequence(size[0], size[1], n, seed=1, radius=min(size) * 0.31, sigma_t=3.0, dtype="u16")
+    return frames, bpp
+
+
+@pytest.mark.parametrize("method", [oecc.ECC_ALIGN_FORWARD_ADDITIVE, oecc.ECC_ALIGN_INVERSE_COMPOSITIONAL_LM])
+@pytest.mark.parametrize("maxlevel", [0, -1])
+def test_stack_average_translation_matches_oracle(gpu, method, maxlevel):
+    """Config #1 shape: mono16 SER frames, translation ECC, LINEAR/REFLECT101 warp, average."""
+    from serstacker_b200 import api
+    frames, bpp = _config1_like()
+    so = opl.StackingOptions()
+    so.registration.motion_type = otf.IMAGE_MOTION_TRANSLATION
+    so.registration.ecc.ecc_method = method
+    so.registration.ecc.ecch_max_level = maxlevel
+    rec = []
+    avg_o, mask_o, acc_o, _ = opl.run_stacking([opl.to_float_frame(f, bpp) for f in frames], so, collect=rec)
+
+    ro = api.registration_options(motion_type=0, ecc=dict(ecc_method=method, ecch_max_level=maxlevel))
+    p = api.c_image_stacking_pipeline(api.stack_options(registration=ro, accumulation_method=0, max_batch=4))
+    p.set_reference(frames[0], bpp=bpp)
+    res = p.add_frames(frames)
+    avg_g, mask_g = p.compute()
+    assert p.accumulated_frames() == sum(r["ok"] for r in rec)
+    for rg, r in zip(res, rec):
+        assert rg["ok"] == r["ok"]
+        assert map_diff_px(0, rg["params"], r["params"], (320, 240)) <= 1e-3
+        assert rg["iterations"] == r["iterations"]
+    assert np.array_equal(mask_g, mask_o)
+    m = mask_o > 0
+    assert rel_l2(avg_g, avg_o, m) <= 1e-4
+    wg = p.accumulator().get_acc_counters()
+    assert np.array_equal(wg, acc_o.weights)
+
+
+@pytest.mark.parametrize("method", [oecc.ECC_ALIGN_INVERSE_COMPOSITIONAL_LM, oecc.ECC_ALIGN_FORWARD_ADDITIVE])
+def test_stack_weighted_affine_cubic_matches_oracle(gpu, method):
+    """Config #2 shape: mono 32F, affine ECCH with translation-first, CUBIC warp, sharpness-weighted average."""
+    from serstacker_b200 import api
+    frames, mats, _ = synth.make_planet_sequence(480, 270, 8, seed=2, radius=100, sigma_t=4.0, sigma_rot_deg=0.2,
+                                                 sigma_scale=0.002, blur_range=(0.8, 2.5), dtype="f32")
+    so = opl.StackingOptions(accumulation_method=opl.ACC_WEIGHTED_AVERAGE)
+    so.registration.motion_type = otf.IMAGE_MOTION_AFFINE
+    so.registration.interpolation = cv2.INTER_CUBIC
+    so.registration.ecc.ecc_method = method
+    so.registration.ecc.ecch_max_level = -1
+    rec = []
+    avg_o, mask_o, acc_o, _ = opl.run_stacking(frames, so, collect=rec)
+
+    ro = api.registration_options(motion_type=3, interpolation=2, ecc=dict(ecc_method=method, ecch_max_level=-1))
+    p = api.c_image_stacking_pipeline(api.stack_options(registration=ro, accumulation_method=1, max_batch=8))
+    p.set_reference(frames[0])
+    res = p.add_frames(frames)
+    avg_g, mask_g = p.compute()
+    for rg, r in zip(res, rec):
+        assert rg["ok"] == r["ok"]
+        assert map_diff_px(3, rg["params"], r["params"], (480, 270)) <= 1e-3, (rg, r)
+    assert np.array_equal(mask_g, mask_o)
+    m = mask_o > 0
+    assert rel_l2(avg_g, avg_o, m) <= 1e-4
+    assert rel_l2(p.accumulator().get_acc_counters(), acc_o.weights, m) <= 1e-4
+
+
+def test_batched_equals_frame_by_frame(gpu):
+    """Batching must not change the result: the accumulation order inside a batch is the frame order."""
+    from serstacker_b200 import api
+    frames, bpp = _config1_like(n=9)
+    outs = []
+    for mb in (1, 4, 16):
+        ro = api.registration_options(motion_type=0, ecc=dict(ecc_method=oecc.ECC_ALIGN_FORWARD_ADDITIVE))
+        p = api.c_image_stacking_pipeline(api.stack_options(registration=ro, accumulation_method=0, max_batch=mb))
+        p.set_reference(frames[0], bpp=bpp)
+        p.add_frames(frames, want_results=False)
+        outs.append(p.compute()[0])
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
