@@ -191,6 +191,12 @@ SSK_API int ssk_ecch_set_reference_image(ssk_ecch *h, const ssk_mat *image, cons
  * set_image_transform(); it is updated in place.  status may be NULL. */
 SSK_API int ssk_ecch_align(ssk_ecch *h, const ssk_mat *image, const ssk_mat *mask, ssk_transform *t,
                            ssk_ecc_status *status);
+/* Debug aid (the reference dumps registration artefacts under <out>/debug, c_image_stacking_pipeline.cc:1511-1530):
+ * record every solver trial of the next align() calls: SSK_TRACE_REC floats per record =
+ * level, pass, num_it, err, newerr, lambda, eps, n_valid | accepted params[8] | trial params[8] | deltap[8] | v[8]. */
+#define SSK_TRACE_REC 40
+SSK_API int ssk_ecch_set_trace(ssk_ecch *h, int max_records);
+SSK_API int ssk_ecch_get_trace(ssk_ecch *h, float *records, int max_records, int *n);
 /* number of pyramid levels / size of level l (c_ecch::compute_next_pyramid_layer_size, ecc2.h:290-293). */
 SSK_API int ssk_ecch_num_levels(const ssk_ecch *h);
 SSK_API int ssk_ecch_level_size(const ssk_ecch *h, int level, int *cols, int *rows);
@@ -210,6 +216,8 @@ SSK_API int ssk_reg_setup_reference_frame(ssk_reg *h, const ssk_mat *image, cons
  * Returns SSK_ERR_NOT_REGISTERED where the reference returns false. */
 SSK_API int ssk_reg_register_frame(ssk_reg *h, const ssk_mat *image, const ssk_mat *mask, int bpp,
                                    ssk_transform *t_out, ssk_ecc_status *status);
+SSK_API int ssk_reg_set_trace(ssk_reg *h, int max_records);
+SSK_API int ssk_reg_get_trace(ssk_reg *h, float *records, int max_records, int *n);
 /* c_frame_registration::current_remap(): materialises the full-resolution CV_32FC2 map on request. */
 SSK_API int ssk_reg_get_current_remap(ssk_reg *h, ssk_mat *rmap);
 /* c_frame_registration::remap()/custom_remap() with the current transform (rmap==NULL) or an explicit map. */

@@ -123,10 +123,17 @@ def remap_f32(src, rmap, interp="linear", border=BORDER_REPLICATE, border_value=
             v = np.where(ok, src[np.clip(yy, 0, h - 1), np.clip(xx, 0, w - 1)], f32(border_value)).astype(f32)
             if taps == 1:
                 row = v
+            elif taps == 2:
+                # remapBilinear: ((S00*w00 + S01*w01) + S10*w10) + S11*w11 -- bit-exact against cv2
+                term = (v * (cy[..., ky] * cx[..., kx]).astype(f32)).astype(f32)
+                out = term if (ky == 0 and kx == 0) else (out + term).astype(f32)
             else:
                 wgt = (cy[..., ky] * cx[..., kx]).astype(f32)
                 row = (row + v * wgt).astype(f32)
-        out = (out + row).astype(f32) if taps > 1 else row
+        if taps == 1:
+            out = row
+        elif taps == 4:
+            out = (out + row).astype(f32)
     if border == BORDER_TRANSPARENT and dst is not None:
         outside = (ix < 0) | (ix >= w) | (iy < 0) | (iy >= h)
         out = np.where(outside, dst, out)
@@ -152,3 +159,51 @@ def remap_u8_all255_valid(size, rmap, interp="linear", thresh=255):
             S += np.where(ok, tab[fy, fx, ky, kx], 0)
     val = np.clip((255 * S + (1 << 14)) >> 15, 0, 255)
     return val >= thresh, val
+
+
+def chol_solve_f32(A, B):
+    """cv::solve / cv::invert with DECOMP_CHOLESKY on CV_32F data for n > 3: hal::Cholesky32f (CholImpl<float>,
+    modules/core/src/matrix_decomp.cpp): float storage, float products, double accumulators, the diagonal of L
+    kept as its reciprocal.  Returns (ok, X) with X float32; B may hold several right-hand sides."""
+    L = np.array(A, dtype=f32, copy=True)
+    b = np.array(B, dtype=f32, copy=True).reshape(L.shape[0], -1)
+    m, n = L.shape[0], b.shape[1]
+    eps = float(np.finfo(np.float32).eps)
+    for i in range(m):
+        for j in range(i):
+            s = float(L[i, j])
+            for k in range(j):
+                s -= float(f32(L[i, k] * L[j, k]))
+            L[i, j] = f32(s * float(L[j, j]))
+        s = float(L[i, i])
+        for k in range(i):
+            t = float(L[i, k])
+            s -= t * t
+        if s < eps:
+            return False, np.zeros_like(b)
+        L[i, i] = f32(1.0 / np.sqrt(s))
+    for i in range(m):
+        for j in range(n):
+            s = float(b[i, j])
+            for k in range(i):
+                s -= float(f32(L[i, k] * b[k, j]))
+            b[i, j] = f32(s * float(L[i, i]))
+    for i in range(m - 1, -1, -1):
+        for j in range(n):
+            s = float(b[i, j])
+            for k in range(m - 1, i, -1):
+                s -= float(f32(L[k, i] * b[k, j]))
+            b[i, j] = f32(s * float(L[i, i]))
+    return True, b
+
+
+def invert_affine_f32(M):
+    """cv::invertAffineTransform on CV_32F data as cv2 4.13 evaluates it (bit-exact, tests/test_cvmodel.py)."""
+    M = np.asarray(M, dtype=f32).reshape(2, 3)
+    D = f32(f32(M[0, 0] * M[1, 1]) - f32(M[0, 1] * M[1, 0]))
+    Di = f32(f32(1.0) / D) if D != 0 else f32(0)
+    A11, A22 = f32(M[1, 1] * Di), f32(M[0, 0] * Di)
+    A12, A21 = f32(-M[0, 1] * Di), f32(-M[1, 0] * Di)
+    b1 = f32(-(float(A11) * float(M[0, 2]) + float(A12) * float(M[1, 2])))
+    b2 = f32(-(float(A21) * float(M[0, 2]) + float(A22) * float(M[1, 2])))
+    return np.array([[A11, A12, b1], [A21, A22, b2]], dtype=f32)

@@ -273,7 +273,7 @@ class EccForwardAdditive(EccAlign):
             rhs = cv2.subtract(rhs, (float(gMean[0, 0]) - stdev_ratio * float(fMean[0, 0]), 0, 0, 0))
             rhs[iw] = 0
             ep = ecc_project_error_image(jac, rhs)
-            dp = (f32(-self.update_step_scale) * (Hinv @ ep)).astype(f32)
+            dp = cv2.gemm(Hinv, ep, -self.update_step_scale, None, 0)   # -_update_step_scale * (H * ep)
             if self.trace is not None:
                 self.trace.append(dict(H=H.copy(), ep=ep.copy(), dp=dp.copy(), p=t.parameters().copy(),
                                        r=stdev_ratio))
@@ -537,7 +537,7 @@ class EccLMInverseCompositional(EccAlign):
                 dp = t.eps(deltap, size)
                 if self.trace is not None:
                     self.trace.append(dict(v=v.copy(), dp=deltap.copy(), p=params.copy(), lam=lam, err=err,
-                                           newerr=newerr, eps=dp))
+                                           newerr=newerr, eps=dp, cma=self._CMA, newp=np.asarray(newparams).copy()))
                 if dp < self.max_eps:
                     break
                 temp_d = cv2.gemm(Hp, deltap, -1, v, 2)

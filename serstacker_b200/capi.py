@@ -95,6 +95,10 @@ _sigs = {
     "ssk_ecch_destroy": (C.c_int, [C.c_void_p]),
     "ssk_ecch_set_reference_image": (C.c_int, [C.c_void_p, _P(ssk_mat), _P(ssk_mat)]),
     "ssk_ecch_align": (C.c_int, [C.c_void_p, _P(ssk_mat), _P(ssk_mat), _P(ssk_transform), _P(ssk_ecc_status)]),
+    "ssk_ecch_set_trace": (C.c_int, [C.c_void_p, C.c_int]),
+    "ssk_ecch_get_trace": (C.c_int, [C.c_void_p, _P(C.c_float), C.c_int, _P(C.c_int)]),
+    "ssk_reg_set_trace": (C.c_int, [C.c_void_p, C.c_int]),
+    "ssk_reg_get_trace": (C.c_int, [C.c_void_p, _P(C.c_float), C.c_int, _P(C.c_int)]),
     "ssk_ecch_num_levels": (C.c_int, [C.c_void_p]),
     "ssk_ecch_level_size": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_int), _P(C.c_int)]),
     "ssk_ecch_get_image": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _P(ssk_mat)]),

@@ -272,6 +272,26 @@ int ssk_ecch_align(ssk_ecch *h, const ssk_mat *image, const ssk_mat *mask, ssk_t
   return SSK_OK;
 }
 
+int ssk_ecch_set_trace(ssk_ecch *h, int max_records) {
+  SSK_REQUIRE(h, "null handle");
+  return h->e.enable_trace(max_records);
+}
+
+int ssk_ecch_get_trace(ssk_ecch *h, float *records, int max_records, int *n) {
+  SSK_REQUIRE(h && records && n, "null argument");
+  return h->e.fetch_trace(records, max_records, n);
+}
+
+int ssk_reg_set_trace(ssk_reg *h, int max_records) {
+  SSK_REQUIRE(h, "null handle");
+  return h->r.ecch.enable_trace(max_records);
+}
+
+int ssk_reg_get_trace(ssk_reg *h, float *records, int max_records, int *n) {
+  SSK_REQUIRE(h && records && n, "null argument");
+  return h->r.ecch.fetch_trace(records, max_records, n);
+}
+
 int ssk_ecch_num_levels(const ssk_ecch *h) { return h ? h->e.nlevels : 0; }
 
 int ssk_ecch_level_size(const ssk_ecch *h, int level, int *cols, int *rows) {

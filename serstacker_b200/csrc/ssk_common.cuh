@@ -187,19 +187,17 @@ __device__ __forceinline__ float sample_linear(const Img &im, int c, float u, fl
   quant32(v, iy, fy);
   const float tx = (float)fx * 0.03125f, ty = (float)fy * 0.03125f;
   const float wx[2] = {1.0f - tx, tx}, wy[2] = {1.0f - ty, ty};
-  float out = 0.f;
-#pragma unroll
-  for (int ky = 0; ky < 2; ++ky) {
-    const int yy = border_idx(iy + ky, im.rows, border);
-    float row = 0.f;
-#pragma unroll
-    for (int kx = 0; kx < 2; ++kx) {
-      const int xx = border_idx(ix + kx, im.cols, border);
-      const float s = (xx >= 0 && yy >= 0) ? load_px<DEPTH>(im, yy, xx, c) : bval;
-      row = __fadd_rn(row, __fmul_rn(s, __fmul_rn(wy[ky], wx[kx])));
-    }
-    out = __fadd_rn(out, row);
-  }
+  // cv::remapBilinear (scalar float path): ((S00*w00 + S01*w01) + S10*w10) + S11*w11, no contraction
+  // (bit-exact against cv2 4.13, tests/test_cvmodel.py)
+  const int y0 = border_idx(iy, im.rows, border), y1 = border_idx(iy + 1, im.rows, border);
+  const int x0 = border_idx(ix, im.cols, border), x1 = border_idx(ix + 1, im.cols, border);
+  const float s00 = (x0 >= 0 && y0 >= 0) ? load_px<DEPTH>(im, y0, x0, c) : bval;
+  const float s01 = (x1 >= 0 && y0 >= 0) ? load_px<DEPTH>(im, y0, x1, c) : bval;
+  const float s10 = (x0 >= 0 && y1 >= 0) ? load_px<DEPTH>(im, y1, x0, c) : bval;
+  const float s11 = (x1 >= 0 && y1 >= 0) ? load_px<DEPTH>(im, y1, x1, c) : bval;
+  float out = __fadd_rn(__fmul_rn(s00, __fmul_rn(wy[0], wx[0])), __fmul_rn(s01, __fmul_rn(wy[0], wx[1])));
+  out = __fadd_rn(out, __fmul_rn(s10, __fmul_rn(wy[1], wx[0])));
+  out = __fadd_rn(out, __fmul_rn(s11, __fmul_rn(wy[1], wx[1])));
   return out;
 }
 

@@ -5,6 +5,7 @@
 namespace ssk {
 
 constexpr int kMaxLevels = 12;
+constexpr int kTraceRec = 40;   // level, pass, num_it, err, newerr, lambda, eps, n | t[8] | tq[8] | deltap[8] | v[8]
 
 // One pyramid level, reference side (shared by every frame of every batch).
 struct EccLevel {
@@ -42,6 +43,8 @@ struct EccConfig {
   const EccHpCache *hp_trans; // translation-first pass (M = 2)
   EccHpCache *hp_main;        // main transform
   int hp_main_mode;           // 0: use cache; 1: recompute per frame at level start; 2: recompute and store (first frame)
+  // optional per-trial trace of frame 0 (debug aid, like the reference's debug dumps): kTraceRec floats per record
+  float *trace; int trace_capacity; int *trace_count;
 };
 
 // Per-frame input/output record (device memory).

@@ -144,14 +144,15 @@ __device__ double xf_eps(int type, const float *dp, int w, int h, float fixed_sc
   }
 }
 
-// cv::invertAffineTransform on float data (double arithmetic inside)
+// cv::invertAffineTransform on CV_32F data, bit-exact against cv2 4.13 (oracle/cvmodel.py::invert_affine_f32):
+// determinant, its reciprocal and the 2x2 part in float; the translation from double products of the rounded
+// 2x2 entries.
 __device__ void invert_affine(const float *M, float *iM) {
-  double D = (double)M[0] * M[4] - (double)M[1] * M[3];
-  D = D != 0 ? 1. / D : 0;
-  const double A11 = M[4] * D, A22 = M[0] * D, A12 = -M[1] * D, A21 = -M[3] * D;
-  const double b1 = -A11 * M[2] - A12 * M[5], b2 = -A21 * M[2] - A22 * M[5];
-  iM[0] = (float)A11; iM[1] = (float)A12; iM[2] = (float)b1;
-  iM[3] = (float)A21; iM[4] = (float)A22; iM[5] = (float)b2;
+  const float D = __fsub_rn(__fmul_rn(M[0], M[4]), __fmul_rn(M[1], M[3]));
+  const float Di = D != 0.f ? __fdiv_rn(1.0f, D) : 0.f;
+  const float A11 = __fmul_rn(M[4], Di), A22 = __fmul_rn(M[0], Di), A12 = __fmul_rn(-M[1], Di), A21 = __fmul_rn(-M[3], Di);
+  iM[0] = A11; iM[1] = A12; iM[2] = (float)(-((double)A11 * (double)M[2] + (double)A12 * (double)M[5]));
+  iM[3] = A21; iM[4] = A22; iM[5] = (float)(-((double)A21 * (double)M[2] + (double)A22 * (double)M[5]));
 }
 
 // 3x3 inverse: cofactors and determinant in double, result float (cv::invert closed form)
@@ -223,33 +224,92 @@ __device__ void xf_invert_and_compose(const ssk_transform &t, const float *dp, f
   }
 }
 
-// Cholesky solve of the M x M float system in double; false (and x = 0) if not positive definite
-// (cv::solve(DECOMP_CHOLESKY) leaves dst zero-filled on failure).
-__device__ bool chol_solve(int M, const float *H, const float *b, float *x) {
-  double L[64], y[8];
-  for (int i = 0; i < M; ++i) {
-    for (int j = 0; j <= i; ++j) {
-      double s = H[i * M + j];
-      for (int k = 0; k < j; ++k) s -= L[i * M + k] * L[j * M + k];
-      if (i == j) {
-        if (!(s > 0)) { for (int q = 0; q < M; ++q) x[q] = 0.f; return false; }
-        L[i * M + i] = sqrt(s);
-      } else {
-        L[i * M + j] = s / L[j * M + j];
-      }
+// hal::Cholesky32f (CholImpl<float>, OpenCV modules/core/src/matrix_decomp.cpp), bit-exact emulation
+// (oracle/cvmodel.py::chol_solve_f32 is checked against cv2.solve / cv2.invert): float storage, float
+// products, double accumulators, reciprocal diagonal.  A (m x m) is overwritten, b (m x n) holds the solution.
+__device__ bool cv_cholesky32f(float *A, int m, float *b, int n) {
+  for (int i = 0; i < m; ++i) {
+    for (int j = 0; j < i; ++j) {
+      double s = A[i * m + j];
+      for (int k = 0; k < j; ++k) s -= (double)__fmul_rn(A[i * m + k], A[j * m + k]);
+      A[i * m + j] = (float)(s * (double)A[j * m + j]);
     }
+    double s = A[i * m + i];
+    for (int k = 0; k < i; ++k) { const double t = A[i * m + k]; s -= t * t; }
+    if (s < (double)FLT_EPSILON) return false;
+    A[i * m + i] = (float)(1. / sqrt(s));
   }
-  for (int i = 0; i < M; ++i) {
-    double s = b[i];
-    for (int k = 0; k < i; ++k) s -= L[i * M + k] * y[k];
-    y[i] = s / L[i * M + i];
-  }
-  for (int i = M - 1; i >= 0; --i) {
-    double s = y[i];
-    for (int k = i + 1; k < M; ++k) s -= L[k * M + i] * (double)x[k];
-    x[i] = (float)(s / L[i * M + i]);
-  }
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < n; ++j) {
+      double s = b[i * n + j];
+      for (int k = 0; k < i; ++k) s -= (double)__fmul_rn(A[i * m + k], b[k * n + j]);
+      b[i * n + j] = (float)(s * (double)A[i * m + i]);
+    }
+  for (int i = m - 1; i >= 0; --i)
+    for (int j = 0; j < n; ++j) {
+      double s = b[i * n + j];
+      for (int k = m - 1; k > i; --k) s -= (double)__fmul_rn(A[k * m + i], b[k * n + j]);
+      b[i * n + j] = (float)(s * (double)A[i * m + i]);
+    }
   return true;
+}
+
+__device__ inline double det3d(const float *m) {
+  return (double)m[0] * ((double)m[4] * m[8] - (double)m[5] * m[7]) - (double)m[1] * ((double)m[3] * m[8] - (double)m[5] * m[6]) +
+         (double)m[2] * ((double)m[3] * m[7] - (double)m[4] * m[6]);
+}
+
+// cv::solve(H, b, x, DECOMP_CHOLESKY) on CV_32F data: closed forms in double for n <= 3 (bit-exact for n = 2;
+// the n = 3 form is evaluated entirely in double here), hal::Cholesky32f otherwise.  x = 0 on failure.
+__device__ bool cv_solve(int M, const float *H, const float *b, float *x) {
+  if (M == 2) {
+    double d = (double)H[0] * H[3] - (double)H[1] * H[2];
+    if (d == 0.) { x[0] = x[1] = 0.f; return false; }
+    d = 1. / d;
+    x[0] = (float)(((double)b[0] * H[3] - (double)b[1] * H[1]) * d);
+    x[1] = (float)(((double)b[1] * H[0] - (double)b[0] * H[2]) * d);
+    return true;
+  }
+  if (M == 3) {
+    double d = det3d(H);
+    if (d == 0.) { x[0] = x[1] = x[2] = 0.f; return false; }
+    d = 1. / d;
+    const double S00 = H[0], S01 = H[1], S02 = H[2], S10 = H[3], S11 = H[4], S12 = H[5], S20 = H[6], S21 = H[7], S22 = H[8];
+    const double b0 = b[0], b1 = b[1], b2 = b[2];
+    x[0] = (float)(d * (b0 * (S11 * S22 - S12 * S21) - S01 * (b1 * S22 - S12 * b2) + S02 * (b1 * S21 - S11 * b2)));
+    x[1] = (float)(d * (S00 * (b1 * S22 - S12 * b2) - b0 * (S10 * S22 - S12 * S20) + S02 * (S10 * b2 - b1 * S20)));
+    x[2] = (float)(d * (S00 * (S11 * b2 - b1 * S21) - S01 * (S10 * b2 - b1 * S20) + b0 * (S10 * S21 - S11 * S20)));
+    return true;
+  }
+  float A[64];
+  for (int i = 0; i < M * M; ++i) A[i] = H[i];
+  for (int i = 0; i < M; ++i) x[i] = b[i];
+  if (!cv_cholesky32f(A, M, x, 1)) { for (int i = 0; i < M; ++i) x[i] = 0.f; return false; }
+  return true;
+}
+
+// cv::invert(H, Hinv, DECOMP_CHOLESKY) on CV_32F data
+__device__ bool cv_invert(int M, const float *H, float *Hi) {
+  if (M == 2) {
+    const double d = (double)H[0] * H[3] - (double)H[1] * H[2];
+    if (d == 0.) return false;
+    const float di = (float)(1. / d);   // the SIMD path multiplies in float
+    Hi[0] = __fmul_rn(H[3], di); Hi[1] = -__fmul_rn(H[1], di); Hi[2] = -__fmul_rn(H[2], di); Hi[3] = __fmul_rn(H[0], di);
+    return true;
+  }
+  if (M == 3) {
+    double d = det3d(H);
+    if (d == 0.) return false;
+    d = 1. / d;
+    const double S00 = H[0], S01 = H[1], S02 = H[2], S10 = H[3], S11 = H[4], S12 = H[5], S20 = H[6], S21 = H[7], S22 = H[8];
+    Hi[0] = (float)((S11 * S22 - S12 * S21) * d); Hi[1] = (float)((S02 * S21 - S01 * S22) * d); Hi[2] = (float)((S01 * S12 - S02 * S11) * d);
+    Hi[3] = (float)((S12 * S20 - S10 * S22) * d); Hi[4] = (float)((S00 * S22 - S02 * S20) * d); Hi[5] = (float)((S02 * S10 - S00 * S12) * d);
+    Hi[6] = (float)((S10 * S21 - S11 * S20) * d); Hi[7] = (float)((S01 * S20 - S00 * S21) * d); Hi[8] = (float)((S00 * S11 - S01 * S10) * d);
+    return true;
+  }
+  float A[64];
+  for (int i = 0; i < M * M; ++i) { A[i] = H[i]; Hi[i] = (i / M == i % M) ? 1.f : 0.f; }
+  return cv_cholesky32f(A, M, Hi, M);
 }
 
 __device__ void make_jcoef(const ssk_transform &t, JCoef &j) {
@@ -329,6 +389,31 @@ __device__ __forceinline__ Img level_image(const Ctx &c, int lvl) {
   return im;
 }
 
+// thread 0 of rank 0, frame 0: append a trace record
+__device__ void trace_rec(const Ctx &c, int lvl, int pass) {
+  const EccConfig &cfg = *c.cfg;
+  if (!cfg.trace || c.rank != 0 || blockIdx.x / c.csize != 0) return;
+  const int i = *cfg.trace_count;
+  if (i >= cfg.trace_capacity) return;
+  *cfg.trace_count = i + 1;
+  const Shared &S = *c.S;
+  float *r = cfg.trace + (size_t)i * kTraceRec;
+  r[0] = (float)lvl; r[1] = (float)pass; r[2] = (float)S.num_it; r[3] = (float)S.err; r[4] = (float)S.newerr;
+  r[5] = (float)S.lambda; r[6] = (float)S.eps; r[7] = (float)S.tot[1];
+  for (int k = 0; k < 8; ++k) { r[8 + k] = S.t.params[k]; r[16 + k] = S.tq.params[k]; r[24 + k] = S.deltap[k]; r[32 + k] = S.v[k]; }
+}
+
+__device__ void trace_hp(const Ctx &c, int lvl, int M) {
+  const EccConfig &cfg = *c.cfg;
+  if (!cfg.trace || c.rank != 0 || blockIdx.x / c.csize != 0) return;
+  const int i = *cfg.trace_count;
+  if (i >= cfg.trace_capacity) return;
+  *cfg.trace_count = i + 1;
+  float *r = cfg.trace + (size_t)i * kTraceRec;
+  r[0] = (float)lvl; r[1] = 9.f; r[2] = (float)M; r[3] = 0.f;
+  for (int k = 0; k < 36; ++k) r[4 + k] = k < M * M ? c.S->Hp[k] : 0.f;
+}
+
 // thread 0: publish the parameters of the next pass
 __device__ void set_pass_params(Shared &S, const ssk_transform &q) {
   S.tq = q;
@@ -351,9 +436,9 @@ __device__ void pass_ic(Ctx &c, int lvl, bool lm_masks) {
   const Img cur = level_image(c, lvl);
   const MapCoef m = S.map;
   const JCoef jc = S.jc;
-  float acc[NS];
+  double acc[NS];   // Mat::dot / norm accumulate in double
 #pragma unroll
-  for (int k = 0; k < NS; ++k) acc[k] = 0.f;
+  for (int k = 0; k < NS; ++k) acc[k] = 0.0;
   const int n = L.cols * L.rows;
   for (int i = c.rank * NT + c.tid; i < n; i += c.csize * NT) {
     const int y = i / L.cols, x = i - y * L.cols;
@@ -372,10 +457,10 @@ __device__ void pass_ic(Ctx &c, int lvl, bool lm_masks) {
     const float rhs = g - __ldg(L.ref + i);
     float J[M];
     eval_J<TYPE>(jc, (float)x, (float)y, __ldg(L.gx + i), __ldg(L.gy + i), J);
-    acc[0] = fmaf(rhs, rhs, acc[0]);
-    acc[1] += 1.f;
+    acc[0] += (double)rhs * (double)rhs;
+    acc[1] += 1.0;
 #pragma unroll
-    for (int k = 0; k < M; ++k) acc[2 + k] = fmaf(J[k], rhs, acc[2 + k]);
+    for (int k = 0; k < M; ++k) acc[2 + k] += (double)J[k] * (double)rhs;
   }
   cluster_reduce<NS>(c, acc);
 }
@@ -388,9 +473,9 @@ __device__ void pass_hp(Ctx &c, int lvl) {
   Shared &S = *c.S;
   const EccLevel &L = c.cfg->lv[lvl];
   const JCoef jc = S.jc;
-  float acc[NS];
+  double acc[NS];
 #pragma unroll
-  for (int k = 0; k < NS; ++k) acc[k] = 0.f;
+  for (int k = 0; k < NS; ++k) acc[k] = 0.0;
   const int n = L.cols * L.rows;
   for (int i = c.rank * NT + c.tid; i < n; i += c.csize * NT) {
     const int y = i / L.cols, x = i - y * L.cols;
@@ -400,7 +485,7 @@ __device__ void pass_hp(Ctx &c, int lvl) {
 #pragma unroll
     for (int a = 0; a < M; ++a)
 #pragma unroll
-      for (int b = 0; b <= a; ++b) { acc[q] = fmaf(J[a], J[b], acc[q]); ++q; }
+      for (int b = 0; b <= a; ++b) { acc[q] += (double)J[a] * (double)J[b]; ++q; }
   }
   cluster_reduce<NS>(c, acc);
 }
@@ -463,13 +548,13 @@ __device__ void pass_forward(Ctx &c, int lvl) {
         float rd[3], rs[5];
 #pragma unroll
         for (int d = -1; d <= 1; ++d)
-          rd[d + 1] = __fadd_rn(__fmul_rn(k1, __fsub_rn(S.gw[r + d][cc + 1], S.gw[r + d][cc - 1])),
-                                __fmul_rn(k2, __fsub_rn(S.gw[r + d][cc + 2], S.gw[r + d][cc - 2])));
+          rd[d + 1] = __fmaf_rn(__fsub_rn(S.gw[r + d][cc + 2], S.gw[r + d][cc - 2]), k2,
+                                __fmul_rn(__fsub_rn(S.gw[r + d][cc + 1], S.gw[r + d][cc - 1]), k1));
 #pragma unroll
         for (int d = -2; d <= 2; ++d)
           rs[d + 2] = __fadd_rn(__fmul_rn(0.5f, S.gw[r + d][cc]), __fmul_rn(0.25f, __fadd_rn(S.gw[r + d][cc + 1], S.gw[r + d][cc - 1])));
         const float gxw = __fadd_rn(__fmul_rn(0.5f, rd[1]), __fmul_rn(0.25f, __fadd_rn(rd[2], rd[0])));
-        const float gyw = __fadd_rn(__fmul_rn(k1, __fsub_rn(rs[3], rs[1])), __fmul_rn(k2, __fsub_rn(rs[4], rs[0])));
+        const float gyw = __fmaf_rn(__fsub_rn(rs[4], rs[0]), k2, __fmul_rn(__fsub_rn(rs[3], rs[1]), k1));
         const float g = S.gw[r][cc], f = __ldg(L.ref + i);
         float J[M];
         eval_J<TYPE>(jc, (float)x, (float)y, gxw, gyw, J);
@@ -558,6 +643,7 @@ __device__ void prepare_ic_level(Ctx &c, int lvl, bool main_pass) {
     for (int i = 0; i < 8; ++i) jt.params[i] = cache->jp[lvl][i];
     for (int i = 0; i < 4; ++i) jt.aux[i] = cache->jp[lvl][8 + i];
     make_jcoef(jt, S.jc);
+    trace_hp(c, lvl, M);
     T0_END
   } else {
     // jac is (re)built with the parameters the transform holds at this moment (ecc2.cc:1733-1738, 1985-1991)
@@ -596,7 +682,7 @@ __device__ bool align_iclm(Ctx &c, int lvl, double max_eps, bool main_pass) {
       T0_BEGIN
       const double CMA = S.tot[1], RMA = L.RMA;
       S.err = S.tot[0] * (RMA * RMA) / (CMA * CMA);
-      for (int i = 0; i < M; ++i) S.v[i] = (float)((double)(float)S.tot[2 + i] * (RMA / CMA));
+      for (int i = 0; i < M; ++i) S.v[i] = __fmul_rn((float)S.tot[2 + i], (float)(RMA / CMA));
       T0_END
     }
     do {
@@ -606,7 +692,7 @@ __device__ bool align_iclm(Ctx &c, int lvl, double max_eps, bool main_pass) {
       float H[64], sdp[8], np[8];
       for (int i = 0; i < M * M; ++i) H[i] = S.Hp[i];
       for (int i = 0; i < M; ++i) H[i * M + i] = (float)((1 + S.lambda) * (double)S.Hp[i * M + i]);
-      chol_solve(M, H, S.v, S.deltap);
+      cv_solve(M, H, S.v, S.deltap);
       for (int i = 0; i < M; ++i) sdp[i] = (float)(cfg.update_step_scale * (double)S.deltap[i]);
       xf_invert_and_compose(S.t, sdp, np);
       ssk_transform q = S.t;
@@ -617,7 +703,7 @@ __device__ bool align_iclm(Ctx &c, int lvl, double max_eps, bool main_pass) {
       T0_BEGIN
       const double CMA = S.tot[1], RMA = L.RMA;
       S.newerr = S.tot[0] * (RMA * RMA) / (CMA * CMA);
-      for (int i = 0; i < M; ++i) S.vtrial[i] = (float)((double)(float)S.tot[2 + i] * (RMA / CMA));
+      for (int i = 0; i < M; ++i) S.vtrial[i] = __fmul_rn((float)S.tot[2 + i], (float)(RMA / CMA));
       S.dp = xf_eps(TYPE, S.deltap, L.cols, L.rows, S.t.aux[3]);
       S.brk = 0;
       if (S.dp < max_eps) {
@@ -626,9 +712,9 @@ __device__ bool align_iclm(Ctx &c, int lvl, double max_eps, bool main_pass) {
         // temp_d = -Hp * deltap + 2 v ; dS = deltap . temp_d (cv::gemm on float data, dot in double)
         double dS = 0;
         for (int i = 0; i < M; ++i) {
-          float td = 0.f;
-          for (int k = 0; k < M; ++k) td += S.Hp[i * M + k] * S.deltap[k];
-          td = -td + 2.f * S.v[i];
+          double hd = 0;
+          for (int k = 0; k < M; ++k) hd += (double)S.Hp[i * M + k] * (double)S.deltap[k];
+          const float td = (float)(-hd + 2.0 * (double)S.v[i]);   // cv::gemm(Hp, deltap, -1, v, 2)
           dS += (double)S.deltap[i] * (double)td;
         }
         const double rho = (S.err - S.newerr) / (fabs(dS) > DBL_EPSILON ? dS : 1);
@@ -638,6 +724,8 @@ __device__ bool align_iclm(Ctx &c, int lvl, double max_eps, bool main_pass) {
         else S.lambda *= 10;
         if (S.newerr < S.err) S.brk = 1;
       }
+      S.eps = S.dp;
+      trace_rec(c, lvl, 3);
       T0_END
     } while (!S.brk && S.num_it < cfg.max_iterations);
     T0_BEGIN
@@ -674,8 +762,8 @@ __device__ bool align_ic(Ctx &c, int lvl, double max_eps, bool main_pass) {
     const double CMA = S.tot[1], RMA = L.RMA;
     const double rmsnew = S.tot[0] * (RMA * RMA) / (CMA * CMA);
     float vs[8];
-    for (int i = 0; i < M; ++i) vs[i] = (float)((double)(float)S.tot[2 + i] * (RMA / CMA));
-    chol_solve(M, S.Hp, vs, S.deltap);
+    for (int i = 0; i < M; ++i) vs[i] = __fmul_rn((float)S.tot[2 + i], (float)(RMA / CMA));
+    cv_solve(M, S.Hp, vs, S.deltap);
     S.brk = 0;
     if (rmsnew >= S.rmsold) {
       S.brk = 1;
@@ -688,6 +776,8 @@ __device__ bool align_ic(Ctx &c, int lvl, double max_eps, bool main_pass) {
       S.eps = xf_eps(TYPE, S.deltap, L.cols, L.rows, S.t.aux[3]);
       if (S.eps < max_eps) S.brk = 1;
     }
+    S.err = rmsnew;
+    trace_rec(c, lvl, 1);
     T0_END
     if (S.brk) break;
   }
@@ -719,24 +809,30 @@ __device__ bool align_fa(Ctx &c, int lvl, double max_eps) {
     const double fMean = t[1] / n, gMean = t[3] / n;
     const double fStd = sqrt(fmax(t[2] / n - fMean * fMean, 0.0)), gStd = sqrt(fmax(t[4] / n - gMean * gMean, 0.0));
     const double r = gStd / fStd;
-    float H[64], ep[8], sol[8];
+    float H[64], Hi[64], ep[8];
     unpack_H(M, t + 5, H);
     const double cst = gMean - r * fMean;
     for (int i = 0; i < M; ++i)
       ep[i] = (float)(t[5 + NH + i] - (r - 1.0) * t[5 + NH + M + i] - cst * t[5 + NH + 2 * M + i]);
     S.brk = 0;
-    if (!(n > 0) || !chol_solve(M, H, ep, sol)) {
+    if (!(n > 0) || !cv_invert(M, H, Hi)) {
       S.failed = 1;
       S.brk = 1;
     } else {
+      // dp = -update_step_scale * (Hinv * ep): cv::gemm with alpha (double accumulation, one rounding)
       float dpv[8];
       for (int i = 0; i < M; ++i) {
-        dpv[i] = (float)(-cfg.update_step_scale * (double)sol[i]);
+        double acc = 0;
+        for (int k = 0; k < M; ++k) acc += (double)Hi[i * M + k] * (double)ep[k];
+        dpv[i] = (float)(acc * -cfg.update_step_scale);
         S.t.params[i] = S.t.params[i] + dpv[i];
       }
       S.eps = xf_eps(TYPE, dpv, L.cols, L.rows, S.t.aux[3]);
       if (S.eps < max_eps) S.brk = 1;
+      for (int i = 0; i < M; ++i) { S.deltap[i] = dpv[i]; S.v[i] = ep[i]; }
     }
+    S.err = r;
+    trace_rec(c, lvl, 0);
     T0_END
     if (S.brk) break;
   }
@@ -780,9 +876,9 @@ __device__ bool align_lm(Ctx &c, int lvl, double max_eps) {
         float H[64];
         for (int i = 0; i < M * M; ++i) H[i] = S.Hp[i];
         for (int i = 0; i < M; ++i) H[i * M + i] = (float)((1 + S.lambda) * (double)S.Hp[i * M + i]);
-        chol_solve(M, H, S.v, S.deltap);
+        cv_solve(M, H, S.v, S.deltap);
         ssk_transform q = S.t;
-        for (int i = 0; i < M; ++i) q.params[i] = (float)((double)S.deltap[i] * (-cfg.update_step_scale) + (double)S.t.params[i]);
+        for (int i = 0; i < M; ++i) q.params[i] = __fadd_rn(__fmul_rn(S.deltap[i], (float)(-cfg.update_step_scale)), S.t.params[i]);   // cv::scaleAdd
         S.eps = xf_eps(TYPE, S.deltap, L.cols, L.rows, S.t.aux[3]);
         if (S.eps <= max_eps) {
           for (int i = 0; i < M; ++i) S.t.params[i] = q.params[i];

@@ -191,6 +191,9 @@ int Ecch::build_config() {
   cfg.hp_trans = d_hp_trans.as<EccHpCache>();
   cfg.hp_main = d_hp_main.as<EccHpCache>();
   cfg.hp_main_mode = 0;
+  cfg.trace = trace_capacity ? d_trace.as<float>() + 4 : nullptr;
+  cfg.trace_capacity = trace_capacity;
+  cfg.trace_count = trace_capacity ? reinterpret_cast<int *>(d_trace.p) : nullptr;
   return SSK_OK;
 }
 
@@ -281,6 +284,27 @@ int Ecch::align(int batch, const ssk_transform &t0) {
   }
   if (batch > done)
     if (int e = launch_ecc(cfg, device_frames() + done, batch - done, cluster_size, stream)) return e;
+  return SSK_OK;
+}
+
+int Ecch::enable_trace(int max_records) {
+  trace_capacity = max_records > 0 ? max_records : 0;
+  if (!trace_capacity) return SSK_OK;
+  if (int e = d_trace.ensure(16 + (size_t)trace_capacity * kTraceRec * 4)) return e;
+  SSK_CUDA(cudaMemsetAsync(d_trace.p, 0, 16, stream));
+  return SSK_OK;
+}
+
+int Ecch::fetch_trace(float *out, int max_records, int *n) {
+  *n = 0;
+  if (!trace_capacity) return SSK_OK;
+  int cnt = 0;
+  SSK_CUDA(cudaMemcpyAsync(&cnt, d_trace.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  SSK_CUDA(cudaStreamSynchronize(stream));
+  cnt = std::min(cnt, std::min(max_records, trace_capacity));
+  if (cnt > 0) SSK_CUDA(cudaMemcpy(out, d_trace.as<float>() + 4, (size_t)cnt * kTraceRec * 4, cudaMemcpyDeviceToHost));
+  SSK_CUDA(cudaMemsetAsync(d_trace.p, 0, 16, stream));
+  *n = cnt;
   return SSK_OK;
 }
 

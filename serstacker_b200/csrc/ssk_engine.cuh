@@ -84,12 +84,16 @@ class Ecch {
   float *level0_scratch(int slot) { return src0.as<float>() + (int64_t)slot * lw[0] * lh[0]; }
   float *const *level0_scratch_ptrs() { return d_src0_ptrs.as<float *>(); }
   int capacity = 0;
+  // debug trace of frame 0 of every align (kTraceRec floats per solver trial)
+  int enable_trace(int max_records);
+  int fetch_trace(float *out, int max_records, int *n);
 
  private:
   int build_config();
   int hp_mode_for_next_align() const;
   DevBuf ref_pyr, ref_gx, ref_gy, cur_pyr, src0, tmp;
-  DevBuf d_hp_trans, d_hp_main, d_frames;
+  DevBuf d_hp_trans, d_hp_main, d_frames, d_trace;
+  int trace_capacity = 0;
   DevBuf d_lvl_ptrs, d_src0_ptrs, d_tmp_ptrs;    // per-level pointer tables for the batched kernels
   PinnedBuf h_frames;
   EccConfig cfg;

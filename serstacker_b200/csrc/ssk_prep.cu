@@ -45,15 +45,18 @@ __global__ void __launch_bounds__(256) k_pyrdown(const PyrDownArgs a) {
   for (int k = threadIdx.x; k < PD_IH * PD_OW; k += blockDim.x) {
     const int r = k / PD_OW, x = k - r * PD_OW;
     const float *p = &s_in[r][2 * x];   // p[0] = s[2x-2]
-    s_h[r][x] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(p[2], 6.f), __fmul_rn(__fadd_rn(p[1], p[3]), 4.f)), p[0]), p[4]);
+    // PyrDownVecH<float>: (s[-2] + s[2]) + (s[-1] + s[1])*4, then + s[0]*6 (bit-exact in the interior vs cv2 4.13)
+    s_h[r][x] = __fadd_rn(__fadd_rn(__fadd_rn(p[0], p[4]), __fmul_rn(__fadd_rn(p[1], p[3]), 4.f)), __fmul_rn(p[2], 6.f));
   }
   __syncthreads();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int ox = ox0 + tx, oy = oy0 + ty;
   if (ox < a.dst_cols && oy < a.dst_rows) {
     const int r = 2 * ty;
-    float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s_h[r + 2][tx], 6.f), __fmul_rn(__fadd_rn(s_h[r + 1][tx], s_h[r + 3][tx]), 4.f)),
-                                  s_h[r][tx]), s_h[r + 4][tx]);
+    // PyrDownVecV<float>: fma(r1 + r3 + r2, 4, r0 + r4 + (r2 + r2)) * (1/256)
+    const float c2 = s_h[r + 2][tx];
+    float v = __fmaf_rn(__fadd_rn(__fadd_rn(s_h[r + 1][tx], s_h[r + 3][tx]), c2), 4.f,
+                        __fadd_rn(__fadd_rn(s_h[r][tx], s_h[r + 4][tx]), __fadd_rn(c2, c2)));
     v = __fmul_rn(v, 1.0f / 256.0f);
     if (a.post_scale != 1.f) v = __fmul_rn(v, a.post_scale);
     dst[(int64_t)oy * a.dst_cols + ox] = v;
@@ -87,15 +90,26 @@ __global__ void __launch_bounds__(256) k_sepfilter(const SepFilterArgs a) {
     s_in[r][c] = __ldg(src + (int64_t)yy * a.cols + xx);
   }
   __syncthreads();
-  // row filter: symmetric -> k0*s0 + sum k_i*(s+i + s-i); antisymmetric -> sum k_i*(s+i - s-i)
+  // row / column arithmetic follows OpenCV's filter engine (found bit-exact against cv2 4.13 for the kernels of this
+  // path: 5-tap derivative, 3-tap smoothing, 7-tap Gaussian)
   const bool xsym = a.kx[0] == a.kx[a.kxn - 1];
   for (int k = threadIdx.x; k < ih * SF_W; k += blockDim.x) {
     const int r = k / SF_W, x = k - r * SF_W;
     const float *p = &s_in[r][x + rx];
-    float acc = xsym ? __fmul_rn(a.kx[rx], p[0]) : 0.f;
-    for (int i = 1; i <= rx; ++i) {
-      const float pr = xsym ? __fadd_rn(p[i], p[-i]) : __fsub_rn(p[i], p[-i]);
-      acc = __fadd_rn(acc, __fmul_rn(a.kx[rx + i], pr));
+    float acc;
+    if (a.kxn <= 5) {
+      // SymmRowSmallFilter: k0*x0 then fma over the (anti)symmetric pairs
+      if (xsym) {
+        acc = __fmul_rn(a.kx[rx], p[0]);
+        for (int i = 1; i <= rx; ++i) acc = __fmaf_rn(__fadd_rn(p[i], p[-i]), a.kx[rx + i], acc);
+      } else {
+        acc = rx >= 1 ? __fmul_rn(__fsub_rn(p[1], p[-1]), a.kx[rx + 1]) : 0.f;
+        for (int i = 2; i <= rx; ++i) acc = __fmaf_rn(__fsub_rn(p[i], p[-i]), a.kx[rx + i], acc);
+      }
+    } else {
+      // RowFilter (RowVec_32f): taps in order, fma chain
+      acc = __fmul_rn(p[-rx], a.kx[0]);
+      for (int i = 1; i < a.kxn; ++i) acc = __fmaf_rn(p[i - rx], a.kx[i], acc);
     }
     s_h[r][x] = acc;
   }
@@ -105,10 +119,14 @@ __global__ void __launch_bounds__(256) k_sepfilter(const SepFilterArgs a) {
   const int x = x0 + tx, y = y0 + ty;
   if (x < a.cols && y < a.rows) {
     const int r = ty + ry;
-    float acc = ysym ? __fmul_rn(a.ky[ry], s_h[r][tx]) : 0.f;
-    for (int i = 1; i <= ry; ++i) {
-      const float pr = ysym ? __fadd_rn(s_h[r + i][tx], s_h[r - i][tx]) : __fsub_rn(s_h[r + i][tx], s_h[r - i][tx]);
-      acc = __fadd_rn(acc, __fmul_rn(a.ky[ry + i], pr));
+    // SymmColumnFilter (SymmColumnVec_32f): centre tap then fma over the (anti)symmetric pairs
+    float acc;
+    if (ysym) {
+      acc = __fmul_rn(a.ky[ry], s_h[r][tx]);
+      for (int i = 1; i <= ry; ++i) acc = __fmaf_rn(__fadd_rn(s_h[r + i][tx], s_h[r - i][tx]), a.ky[ry + i], acc);
+    } else {
+      acc = ry >= 1 ? __fmul_rn(__fsub_rn(s_h[r + 1][tx], s_h[r - 1][tx]), a.ky[ry + 1]) : 0.f;
+      for (int i = 2; i <= ry; ++i) acc = __fmaf_rn(__fsub_rn(s_h[r + i][tx], s_h[r - i][tx]), a.ky[ry + i], acc);
     }
     dst[(int64_t)y * a.cols + x] = acc;
   }

@@ -25,7 +25,10 @@ def test_remap_f32_model_matches_cv2(interp, ci, border):
     for rmap in _maps(rng, w, h):
         ref = cv2.remap(src, rmap, None, ci, borderMode=border, borderValue=0.25)
         mine = m.remap_f32(src, rmap, interp, border, 0.25)
-        assert np.abs(ref - mine).max() <= (1e-6 if interp == "cubic" else 2e-7)
+        if interp == "cubic":
+            assert np.abs(ref - mine).max() <= 1e-6
+        else:
+            assert np.array_equal(ref, mine)      # bilinear / nearest: bit-exact
 
 
 @pytest.mark.parametrize("interp,ci", [("linear", cv2.INTER_LINEAR), ("nearest", cv2.INTER_NEAREST)])
@@ -66,3 +69,24 @@ def test_bilinear_all255_thresholds_coincide():
         iy, fy = m.quantize(rmap[..., 1])
         closed = (ix >= 0) & (iy >= 0) & (ix < w) & (iy < h) & ((fx == 0) | (ix + 1 < w)) & ((fy == 0) | (iy + 1 < h))
         assert np.array_equal(a, closed)
+
+
+def test_small_matrix_models_bit_exact():
+    """The device-side solver algebra is written to these models: hal::Cholesky32f, cv::invertAffineTransform."""
+    rng = np.random.default_rng(5)
+    for M in (4, 6, 8):
+        for _ in range(50):
+            J = rng.normal(size=(50, M)) * np.array([300, 200, 1, 300, 200, 1, 90000, 60000][:M])
+            H = (J.T @ J).astype(np.float32)
+            v = (J.T @ rng.normal(size=(50, 1))).astype(np.float32)
+            ok, x = cv2.solve(H, v, flags=cv2.DECOMP_CHOLESKY)
+            ok2, x2 = m.chol_solve_f32(H, v)
+            assert bool(ok) == ok2 and np.array_equal(x, x2)
+            oki, Hi = cv2.invert(H, flags=cv2.DECOMP_CHOLESKY)
+            ok3, Hi2 = m.chol_solve_f32(H, np.eye(M, dtype=np.float32))
+            assert (oki != 0) == ok3 and np.array_equal(Hi, Hi2)
+    for _ in range(500):
+        s = rng.choice([0.01, 0.2, 1.0])
+        A = np.array([[1 + rng.normal(0, s), rng.normal(0, s), rng.normal(0, 50)],
+                      [rng.normal(0, s), 1 + rng.normal(0, s), rng.normal(0, 50)]], np.float32)
+        assert np.array_equal(cv2.invertAffineTransform(A), m.invert_affine_f32(A))

@@ -58,3 +58,15 @@ def test_local_variance_map_matches_oracle(gpu, size, kradius, dscale):
     assert abs(Qg - Qo) <= 2e-5 * abs(Qo)
     scale = np.abs(Mo).max()
     assert np.abs(Mg - Mo).max() <= 5e-6 * scale, np.abs(Mg - Mo).max() / scale
+
+
+def test_level0_smoothing_bit_exact(gpu):
+    """The 7-tap Gaussian sepFilter2D (and the 5/3-tap derivative filters) follow OpenCV's filter-engine
+    arithmetic exactly, so the reference-side Hessian sees the same gradients as the oracle."""
+    from serstacker_b200 import api
+    img, _ = _frame(320, 240, 9)
+    o = oecc.EccH(oecc_transform(), maxlevel=0, reference_smooth_sigma=1.0)
+    o.set_reference_image(img, None)
+    g = api.c_ecch(None, maxlevel=0, reference_smooth_sigma=1.0)
+    g.set_reference_image(img)
+    assert np.array_equal(g.reference_image(0), o.pyramid[0].reference_image)

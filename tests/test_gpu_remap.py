@@ -113,3 +113,16 @@ def test_remap_mask_matches_base_remap(gpu, interp):
     _, want = reg.base_remap(rmap, src, m, interpolation=interp, border_mode=cv2.BORDER_REFLECT101)
     _, got = api.remap(t, None, src, want_mask=True, src_mask=m, interpolation=interp)
     assert np.array_equal(got, want)
+
+
+def test_bilinear_remap_bit_exact(gpu):
+    """Bilinear sampling reproduces cv::remap's scalar float path bit for bit (translation / affine maps)."""
+    from serstacker_b200 import api
+    rng = np.random.default_rng(77)
+    src = rng.random((83, 131)).astype(np.float32)
+    for motion in (0, 3):
+        for border in (cv2.BORDER_REPLICATE, cv2.BORDER_CONSTANT, cv2.BORDER_REFLECT101):
+            t, o = _rand_transform(rng, motion)
+            want = cv2.remap(src, o.create_remap((131, 83)), None, cv2.INTER_LINEAR, borderMode=border, borderValue=0.0)
+            got, _ = api.remap(t, None, src, interpolation=cv2.INTER_LINEAR, border_mode=border)
+            assert np.array_equal(got, want)
