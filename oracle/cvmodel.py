@@ -207,3 +207,38 @@ def invert_affine_f32(M):
     b1 = f32(-(float(A11) * float(M[0, 2]) + float(A12) * float(M[1, 2])))
     b2 = f32(-(float(A21) * float(M[0, 2]) + float(A22) * float(M[1, 2])))
     return np.array([[A11, A12, b1], [A21, A22, b2]], dtype=f32)
+
+
+def pyrdown_f32(src, dsize=None):
+    """cv::pyrDown(CV_32FC1, BORDER_REFLECT_101) as cv2 4.13 evaluates it (bit-exact, tests/test_cvmodel.py):
+    4-lane universal-intrinsic loops without FMA for the bulk, scalar expressions for the left border column,
+    the tail columns and the right border (PyrDownInvoker, modules/imgproc/src/pyramids.cpp). dsize = (w, h)."""
+    src = np.asarray(src, dtype=f32)
+    h, w = src.shape
+    dw, dh = dsize if dsize else ((w + 1) // 2, (h + 1) // 2)
+    width0 = min((w - 3) // 2 + 1, dw)
+
+    def refl(p, n):
+        p = np.asarray(p).copy()
+        for _ in range(4):
+            p = np.where(p < 0, -p, p)
+            p = np.where(p >= n, 2 * (n - 1) - p, p)
+        return p
+
+    xs = np.arange(dw)
+    col = lambda d: src[:, refl(2 * xs + d, w)]
+    c, l1, r1, l2, r2 = col(0), col(-1), col(1), col(-2), col(2)
+    a1 = ((l1 + r1).astype(f32) * f32(4)).astype(f32)
+    c6 = (c * f32(6)).astype(f32)
+    simd = (c6 + (a1 + (l2 + r2).astype(f32)).astype(f32)).astype(f32)
+    scal = (((c6 + a1).astype(f32) + l2).astype(f32) + r2).astype(f32)
+    use = (xs >= 1) & (xs < 1 + 4 * ((width0 - 1) // 4))
+    rows = np.where(use[None, :], simd, scal)
+    ys = np.arange(dh)
+    rw = lambda d: rows[refl(2 * ys + d, h), :]
+    c, u1, d1, u2, d2 = rw(0), rw(-1), rw(1), rw(-2), rw(2)
+    a13 = (u1 + d1).astype(f32)
+    vs = (((a13 + c).astype(f32) * f32(4)).astype(f32) + ((u2 + d2).astype(f32) + (c + c).astype(f32)).astype(f32)).astype(f32)
+    vc = ((((c * f32(6)).astype(f32) + (a13 * f32(4)).astype(f32)).astype(f32) + u2).astype(f32) + d2).astype(f32)
+    out = np.where((xs < 4 * (dw // 4))[None, :], vs, vc)
+    return (out * f32(1.0 / 256.0)).astype(f32)

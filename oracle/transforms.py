@@ -261,7 +261,14 @@ class EuclideanTransform(ImageTransform):
         Mdp = self._matrix3x3(dTx, dTy, dAngle, scale_dp, Cx, Cy)
         Mdp_inv = np.eye(3, dtype=f32)
         Mdp_inv[:2, :] = cv2.invertAffineTransform(np.ascontiguousarray(Mdp[:2, :]))
-        M_res = (Mp @ Mdp_inv).astype(f32)
+        # Matx33f product (s += a(i,k)*b(k,j), float, in order)
+        M_res = np.zeros((3, 3), dtype=f32)
+        for i in range(3):
+            for j in range(3):
+                acc = f32(0)
+                for k in range(3):
+                    acc = f32(acc + f32(Mp[i, k] * Mdp_inv[k, j]))
+                M_res[i, j] = acc
         m00, m10 = M_res[0, 0], M_res[1, 0]
         res_scale = scale if self._fix_scale else f32(np.sqrt(f32(m00 * m00 + m10 * m10)))
         res_angle = angle if self._fix_rotation else f32(math.atan2(float(m10), float(m00)))

@@ -71,6 +71,7 @@ struct Shared {
   float vtrial[8];
   float Htrial[64];
   float deltap[8];
+  float fa_a, fa_c;           // forward-additive residual coefficients: rhs = fma(f, fa_a, g) - fa_c
   double err, newerr, lambda, dp, rmsold, eps;
   int num_it, recompute, brk, converged, failed, level_ok, cont;
   int total_iterations;
@@ -168,8 +169,9 @@ __device__ void invert3x3(const float *a, float *b) {
 __device__ void euclid_matrix(float tX, float tY, float ang, float scl, float cX, float cY, float *M /*2x3*/) {
   // lambda at c_image_transform.cc:768-782
   const float sa = (float)sin((double)ang), ca = (float)cos((double)ang);
-  M[0] = scl * ca; M[1] = -scl * sa; M[2] = tX - scl * ca * cX + scl * sa * cY;
-  M[3] = scl * sa; M[4] = scl * ca;  M[5] = tY - scl * sa * cX - scl * ca * cY;
+  const float sc = __fmul_rn(scl, ca), ss = __fmul_rn(scl, sa);
+  M[0] = sc; M[1] = -ss; M[2] = __fadd_rn(__fsub_rn(tX, __fmul_rn(sc, cX)), __fmul_rn(ss, cY));
+  M[3] = ss; M[4] = sc;  M[5] = __fsub_rn(__fsub_rn(tY, __fmul_rn(ss, cX)), __fmul_rn(sc, cY));
 }
 
 // newparams = transform->invert_and_compose(p, dp)
@@ -208,15 +210,16 @@ __device__ void xf_invert_and_compose(const ssk_transform &t, const float *dp, f
       euclid_matrix(dp[0], dp[1], dp[2], scale_dp, Cx, Cy, Mdp);
       invert_affine(Mdp, Mi);
       // M_res = Mp * Mdp_inv (3x3 float product, last row 0 0 1)
-      const float m00 = Mp[0] * Mi[0] + Mp[1] * Mi[3];
-      const float m02 = Mp[0] * Mi[2] + Mp[1] * Mi[5] + Mp[2];
-      const float m10 = Mp[3] * Mi[0] + Mp[4] * Mi[3];
-      const float m12 = Mp[3] * Mi[2] + Mp[4] * Mi[5] + Mp[5];
-      const float rs = fix_scale ? scale : sqrtf(m00 * m00 + m10 * m10);
+      // Matx33f product, s += a(i,k)*b(k,j) in order (third row of Mdp_inv is 0 0 1)
+      const float m00 = __fadd_rn(__fmul_rn(Mp[0], Mi[0]), __fmul_rn(Mp[1], Mi[3]));
+      const float m02 = __fadd_rn(__fadd_rn(__fmul_rn(Mp[0], Mi[2]), __fmul_rn(Mp[1], Mi[5])), Mp[2]);
+      const float m10 = __fadd_rn(__fmul_rn(Mp[3], Mi[0]), __fmul_rn(Mp[4], Mi[3]));
+      const float m12 = __fadd_rn(__fadd_rn(__fmul_rn(Mp[3], Mi[2]), __fmul_rn(Mp[4], Mi[5])), Mp[5]);
+      const float rs = fix_scale ? scale : __fsqrt_rn(__fadd_rn(__fmul_rn(m00, m00), __fmul_rn(m10, m10)));
       const float ra = (float)atan2((double)m10, (double)m00);
       const float rca = (float)cos((double)ra), rsa = (float)sin((double)ra);
-      out[0] = m02 + rs * rca * Cx - rs * rsa * Cy;
-      out[1] = m12 + rs * rsa * Cx + rs * rca * Cy;
+      out[0] = __fsub_rn(__fadd_rn(m02, __fmul_rn(__fmul_rn(rs, rca), Cx)), __fmul_rn(__fmul_rn(rs, rsa), Cy));
+      out[1] = __fadd_rn(__fadd_rn(m12, __fmul_rn(__fmul_rn(rs, rsa), Cx)), __fmul_rn(__fmul_rn(rs, rca), Cy));
       out[2] = ra;
       if (!fix_scale) out[3] = rs;
       break;
@@ -328,26 +331,32 @@ __device__ void make_jcoef(const ssk_transform &t, JCoef &j) {
   }
 }
 
-// c_image_transform::create_steepest_descent_images, one pixel
+// c_image_transform::create_steepest_descent_images, one pixel.  Explicit single-rounding operations in the
+// reference's operand order (no FMA contraction), so that J is bit-identical to the oracle's float arithmetic.
 template <int TYPE>
 __device__ __forceinline__ void eval_J(const JCoef &jc, float x, float y, float gx, float gy, float *J) {
   if (TYPE == SSK_MOTION_TRANSLATION) {                // c_image_transform.cc:262-269
     J[0] = gx; J[1] = gy;
   } else if (TYPE == SSK_MOTION_AFFINE) {              // c_image_transform.cc:1054-1067
-    J[0] = gx * x; J[1] = gx * y; J[2] = gx; J[3] = gy * x; J[4] = gy * y; J[5] = gy;
+    J[0] = __fmul_rn(gx, x); J[1] = __fmul_rn(gx, y); J[2] = gx;
+    J[3] = __fmul_rn(gy, x); J[4] = __fmul_rn(gy, y); J[5] = gy;
   } else if (TYPE == SSK_MOTION_HOMOGRAPHY) {          // c_image_transform.cc:1339-1363
-    const float den = 1.f / (x * jc.c[6] + y * jc.c[7] + 1.f);
-    const float hatX = -(x * jc.c[0] + y * jc.c[1] + jc.c[2]) * den;
-    const float hatY = -(x * jc.c[3] + y * jc.c[4] + jc.c[5]) * den;
-    const float ggx = gx * den, ggy = gy * den;
-    const float gg = hatX * ggx + hatY * ggy;
-    J[0] = ggx * x; J[1] = ggx * y; J[2] = ggx; J[3] = ggy * x; J[4] = ggy * y; J[5] = ggy; J[6] = gg * x; J[7] = gg * y;
+    const float den = __fdiv_rn(1.f, __fadd_rn(__fadd_rn(__fmul_rn(x, jc.c[6]), __fmul_rn(y, jc.c[7])), 1.f));
+    const float hatX = __fmul_rn(-__fadd_rn(__fadd_rn(__fmul_rn(x, jc.c[0]), __fmul_rn(y, jc.c[1])), jc.c[2]), den);
+    const float hatY = __fmul_rn(-__fadd_rn(__fadd_rn(__fmul_rn(x, jc.c[3]), __fmul_rn(y, jc.c[4])), jc.c[5]), den);
+    const float ggx = __fmul_rn(gx, den), ggy = __fmul_rn(gy, den);
+    const float gg = __fadd_rn(__fmul_rn(hatX, ggx), __fmul_rn(hatY, ggy));
+    J[0] = __fmul_rn(ggx, x); J[1] = __fmul_rn(ggx, y); J[2] = ggx;
+    J[3] = __fmul_rn(ggy, x); J[4] = __fmul_rn(ggy, y); J[5] = ggy;
+    J[6] = __fmul_rn(gg, x); J[7] = __fmul_rn(gg, y);
   } else {                                             // c_image_transform.cc:636-665
-    const float xx = x - jc.c[3], yy = y - jc.c[4];
+    const float xx = __fsub_rn(x, jc.c[3]), yy = __fsub_rn(y, jc.c[4]);
     const float ca = jc.c[1], sa = jc.c[2];
+    const float t1 = __fadd_rn(__fmul_rn(sa, xx), __fmul_rn(ca, yy));   // sa*xx + ca*yy
+    const float t2 = __fsub_rn(__fmul_rn(ca, xx), __fmul_rn(sa, yy));   // ca*xx - sa*yy
     J[0] = gx; J[1] = gy;
-    J[2] = jc.c[0] * (-gx * (sa * xx + ca * yy) + gy * (ca * xx - sa * yy));
-    if (TYPE == SSK_MOTION_SCALED_EUCLIDEAN) J[3] = gx * (ca * xx - sa * yy) + gy * (sa * xx + ca * yy);
+    J[2] = __fmul_rn(jc.c[0], __fadd_rn(__fmul_rn(-gx, t1), __fmul_rn(gy, t2)));
+    if (TYPE == SSK_MOTION_SCALED_EUCLIDEAN) J[3] = __fadd_rn(__fmul_rn(gx, t2), __fmul_rn(gy, t1));
   }
 }
 
@@ -498,27 +507,60 @@ __device__ void unpack_H(int M, const double *tri, float *H) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// pass of the forward methods (warped-image gradient needs a stencil -> tiles with a 2-px halo in smem)
-//   FA (c_ecc_forward_additive, ecc2.cc:1297-1347):
-//     sums = [ n, Sf, Sf2, Sg, Sg2, H (lower triangle), J_i.(g-f), J_i.f, sum J_i ]
-//     so that ep_i = J_i.(g - r f - (gm - r fm)) = J_i.(g-f) - (r-1) J_i.f - (gm - r fm) sum J_i  (benign cancellation)
-//   LM (c_ecclm::compute_jac, ecc2.cc:1482-1525):
-//     sums = [ |rhs|^2, #valid, v_i = J_i.rhs, H (lower triangle) ]
+// passes of the forward methods (the warped-image gradient needs a stencil -> tiles with a 2-px halo in smem)
+//   FA (c_ecc_forward_additive, ecc2.cc:1297-1347) runs two passes per iteration so that the residual is formed
+//   exactly as the reference forms it:
+//     pass_fa_stats : [ n, Sf, Sf2, Sg, Sg2 ] over wmask -> r = sg/sf, c = gm - r fm          (cv::meanStdDev)
+//     pass_forward  : rhs = fma(f, (float)-r, g) - (float)c  (cv::scaleAdd, cv::subtract with a Scalar);
+//                     sums = [ H (lower triangle), ep_i = J_i.rhs ]
+//   LM (c_ecclm::compute_jac, ecc2.cc:1482-1525): sums = [ |rhs|^2, #valid, v_i = J_i.rhs, H (lower triangle) ]
+//   All sums are accumulated in double like cv::Mat::dot / cv::norm.
 // ------------------------------------------------------------------------------------------------
+template <int DUMMY>
+__device__ __forceinline__ float fa_sample(const Img &cur, int interp, float u, float v) {
+  if (interp == SSK_INTER_NEAREST) return sample_nearest<SSK_32F>(cur, 0, u, v, SSK_BORDER_REPLICATE, 0.f);
+  return sample_linear<SSK_32F>(cur, 0, u, v, SSK_BORDER_REPLICATE, 0.f);
+}
+
+__device__ void pass_fa_stats(Ctx &c, int lvl) {
+  Shared &S = *c.S;
+  const EccLevel &L = c.cfg->lv[lvl];
+  const Img cur = level_image(c, lvl);
+  const MapCoef m = S.map;
+  const int interp = c.cfg->interp;
+  double acc[5] = {0, 0, 0, 0, 0};
+  const int n = L.cols * L.rows;
+  for (int i = c.rank * NT + c.tid; i < n; i += c.csize * NT) {
+    const int y = i / L.cols, x = i - y * L.cols;
+    float u, v;
+    map_xy(m, (float)x, (float)y, u, v);
+    bool ok = valid255_linear(u, v, L.cols, L.rows);
+    if (ok && L.refmask) ok = L.refmask[i] != 0;
+    if (!ok) continue;
+    const double g = fa_sample<0>(cur, interp, u, v);
+    const double f = __ldg(L.ref + i);
+    acc[0] += 1.0; acc[1] += f; acc[2] += f * f; acc[3] += g; acc[4] += g * g;
+  }
+  cluster_reduce<5>(c, acc);
+}
+
 template <int TYPE, bool FA>
 __device__ void pass_forward(Ctx &c, int lvl) {
   constexpr int M = NParams<TYPE>::M;
   constexpr int NH = M * (M + 1) / 2;
-  constexpr int NS = FA ? 5 + NH + 3 * M : 2 + M + NH;
+  constexpr int NS = FA ? NH + M : 2 + M + NH;
+  constexpr int OH = FA ? 0 : 2 + M;     // offset of the H triangle
+  constexpr int OV = FA ? NH : 2;        // offset of J.rhs
   Shared &S = *c.S;
   const EccLevel &L = c.cfg->lv[lvl];
   const Img cur = level_image(c, lvl);
   const MapCoef m = S.map;
   const JCoef jc = S.jc;
   const int interp = FA ? c.cfg->interp : SSK_INTER_LINEAR;
-  float acc[NS];
+  const float fa_a = S.fa_a, fa_c = S.fa_c;
+  double acc[NS];
 #pragma unroll
-  for (int k = 0; k < NS; ++k) acc[k] = 0.f;
+  for (int k = 0; k < NS; ++k) acc[k] = 0.0;
   const int ntx = (L.cols + FT_W - 1) / FT_W, nty = (L.rows + FT_H - 1) / FT_H;
   const int tx = c.tid & 31, ty = c.tid >> 5;
   for (int t = c.rank; t < ntx * nty; t += c.csize) {
@@ -528,10 +570,7 @@ __device__ void pass_forward(Ctx &c, int lvl) {
       const int gx_ = min(max(x0 - 2 + cc, 0), L.cols - 1), gy_ = min(max(y0 - 2 + r, 0), L.rows - 1);
       float u, v;
       map_xy(m, (float)gx_, (float)gy_, u, v);
-      float g;
-      if (interp == SSK_INTER_NEAREST) g = sample_nearest<SSK_32F>(cur, 0, u, v, SSK_BORDER_REPLICATE, 0.f);
-      else g = sample_linear<SSK_32F>(cur, 0, u, v, SSK_BORDER_REPLICATE, 0.f);
-      S.gw[r][cc] = g;
+      S.gw[r][cc] = fa_sample<0>(cur, interp, u, v);
     }
     __syncthreads();
     const int x = x0 + tx, y = y0 + ty;
@@ -543,6 +582,7 @@ __device__ void pass_forward(Ctx &c, int lvl) {
       if (ok && L.refmask) ok = L.refmask[i] != 0;
       if (ok) {
         const int r = ty + 2, cc = tx + 2;
+        // ecc_differentiate (ecc2.cc:142-169) with OpenCV's filter-engine arithmetic:
         // gx = sepFilter2D(gw, d5 along x, s3 along y); gy = sepFilter2D(gw, s3 along x, d5 along y)
         const float k1 = 2.f / 3.f, k2 = -1.f / 12.f;
         float rd[3], rs[5];
@@ -552,36 +592,27 @@ __device__ void pass_forward(Ctx &c, int lvl) {
                                 __fmul_rn(__fsub_rn(S.gw[r + d][cc + 1], S.gw[r + d][cc - 1]), k1));
 #pragma unroll
         for (int d = -2; d <= 2; ++d)
-          rs[d + 2] = __fadd_rn(__fmul_rn(0.5f, S.gw[r + d][cc]), __fmul_rn(0.25f, __fadd_rn(S.gw[r + d][cc + 1], S.gw[r + d][cc - 1])));
-        const float gxw = __fadd_rn(__fmul_rn(0.5f, rd[1]), __fmul_rn(0.25f, __fadd_rn(rd[2], rd[0])));
+          rs[d + 2] = __fmaf_rn(__fadd_rn(S.gw[r + d][cc + 1], S.gw[r + d][cc - 1]), 0.25f, __fmul_rn(0.5f, S.gw[r + d][cc]));
+        const float gxw = __fmaf_rn(__fadd_rn(rd[2], rd[0]), 0.25f, __fmul_rn(0.5f, rd[1]));
         const float gyw = __fmaf_rn(__fsub_rn(rs[4], rs[0]), k2, __fmul_rn(__fsub_rn(rs[3], rs[1]), k1));
         const float g = S.gw[r][cc], f = __ldg(L.ref + i);
         float J[M];
         eval_J<TYPE>(jc, (float)x, (float)y, gxw, gyw, J);
-        int q;
+        float rhs;
         if (FA) {
-          acc[0] += 1.f; acc[1] += f; acc[2] = fmaf(f, f, acc[2]); acc[3] += g; acc[4] = fmaf(g, g, acc[4]);
-          q = 5;
+          rhs = __fsub_rn(__fmaf_rn(f, fa_a, g), fa_c);
         } else {
-          const float rhs = g - f;
-          acc[0] = fmaf(rhs, rhs, acc[0]); acc[1] += 1.f;
-#pragma unroll
-          for (int k = 0; k < M; ++k) acc[2 + k] = fmaf(J[k], rhs, acc[2 + k]);
-          q = 2 + M;
+          rhs = __fsub_rn(g, f);
+          acc[0] += (double)rhs * (double)rhs;
+          acc[1] += 1.0;
         }
+#pragma unroll
+        for (int k = 0; k < M; ++k) acc[OV + k] += (double)J[k] * (double)rhs;
+        int q = OH;
 #pragma unroll
         for (int a = 0; a < M; ++a)
 #pragma unroll
-          for (int b = 0; b <= a; ++b) { acc[q] = fmaf(J[a], J[b], acc[q]); ++q; }
-        if (FA) {
-          const float d = g - f;
-#pragma unroll
-          for (int k = 0; k < M; ++k) {
-            acc[5 + NH + k] = fmaf(J[k], d, acc[5 + NH + k]);
-            acc[5 + NH + M + k] = fmaf(J[k], f, acc[5 + NH + M + k]);
-            acc[5 + NH + 2 * M + k] += J[k];
-          }
-        }
+          for (int b = 0; b <= a; ++b) { acc[q] += (double)J[a] * (double)J[b]; ++q; }
       }
     }
     __syncthreads();
@@ -802,18 +833,28 @@ __device__ bool align_fa(Ctx &c, int lvl, double max_eps) {
     if (S.cont) { set_pass_params(S, S.t); make_jcoef(S.t, S.jc); }
     T0_END
     if (!S.cont) break;
+    pass_fa_stats(c, lvl);
+    T0_BEGIN
+    {
+      // cv::meanStdDev over wmask (ecc2.cc:1324-1326)
+      const double *t = S.tot;
+      const double n = t[0];
+      const double fMean = t[1] / n, gMean = t[3] / n;
+      const double fStd = sqrt(fmax(t[2] / n - fMean * fMean, 0.0)), gStd = sqrt(fmax(t[4] / n - gMean * gMean, 0.0));
+      const double r = gStd / fStd;
+      S.err = r;
+      S.newerr = n;
+      S.fa_a = (float)(-r);                      // cv::scaleAdd(f, -r, gw)
+      S.fa_c = (float)(gMean - r * fMean);        // cv::subtract(rhs, Scalar)
+    }
+    T0_END
     pass_forward<TYPE, true>(c, lvl);
     T0_BEGIN
     const double *t = S.tot;
-    const double n = t[0];
-    const double fMean = t[1] / n, gMean = t[3] / n;
-    const double fStd = sqrt(fmax(t[2] / n - fMean * fMean, 0.0)), gStd = sqrt(fmax(t[4] / n - gMean * gMean, 0.0));
-    const double r = gStd / fStd;
+    const double n = S.newerr, r = S.err;
     float H[64], Hi[64], ep[8];
-    unpack_H(M, t + 5, H);
-    const double cst = gMean - r * fMean;
-    for (int i = 0; i < M; ++i)
-      ep[i] = (float)(t[5 + NH + i] - (r - 1.0) * t[5 + NH + M + i] - cst * t[5 + NH + 2 * M + i]);
+    unpack_H(M, t, H);
+    for (int i = 0; i < M; ++i) ep[i] = (float)t[NH + i];
     S.brk = 0;
     if (!(n > 0) || !cv_invert(M, H, Hi)) {
       S.failed = 1;

@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(256) k_pyrdown(const PyrDownArgs a) {
   float *dst = a.dst_ptrs ? a.dst_ptrs[b] : a.dst;
   const int ox0 = blockIdx.x * PD_OW, oy0 = blockIdx.y * PD_OH;
   const int ix0 = 2 * ox0 - 2, iy0 = 2 * oy0 - 2;
+  const int width0 = min((src.cols - 3) / 2 + 1, a.dst_cols);   // PyrDownInvoker: columns free of border handling
+  const int nsimd_h = 4 * ((width0 - 1) / 4);
   for (int k = threadIdx.x; k < PD_IH * PD_IW; k += blockDim.x) {
     const int r = k / PD_IW, c = k - r * PD_IW;
     const int yy = border_idx(iy0 + r, src.rows, SSK_BORDER_REFLECT101);
@@ -45,18 +47,26 @@ __global__ void __launch_bounds__(256) k_pyrdown(const PyrDownArgs a) {
   for (int k = threadIdx.x; k < PD_IH * PD_OW; k += blockDim.x) {
     const int r = k / PD_OW, x = k - r * PD_OW;
     const float *p = &s_in[r][2 * x];   // p[0] = s[2x-2]
-    // PyrDownVecH<float>: (s[-2] + s[2]) + (s[-1] + s[1])*4, then + s[0]*6 (bit-exact in the interior vs cv2 4.13)
-    s_h[r][x] = __fadd_rn(__fadd_rn(__fadd_rn(p[0], p[4]), __fmul_rn(__fadd_rn(p[1], p[3]), 4.f)), __fmul_rn(p[2], 6.f));
+    // cv::pyrDown, bit-exact against cv2 4.13 (oracle/cvmodel.py::pyrdown_f32): columns covered by the 4-lane
+    // PyrDownVecH loop use s0*6 + ((s-1 + s1)*4 + (s-2 + s2)); the border column and the scalar tail use
+    // ((s0*6 + (s-1 + s1)*4) + s-2) + s2
+    const int gx = ox0 + x;
+    const float a1 = __fmul_rn(__fadd_rn(p[1], p[3]), 4.f), c6 = __fmul_rn(p[2], 6.f);
+    s_h[r][x] = (gx >= 1 && gx < 1 + nsimd_h) ? __fadd_rn(c6, __fadd_rn(a1, __fadd_rn(p[0], p[4])))
+                                              : __fadd_rn(__fadd_rn(__fadd_rn(c6, a1), p[0]), p[4]);
   }
   __syncthreads();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int ox = ox0 + tx, oy = oy0 + ty;
   if (ox < a.dst_cols && oy < a.dst_rows) {
     const int r = 2 * ty;
-    // PyrDownVecV<float>: fma(r1 + r3 + r2, 4, r0 + r4 + (r2 + r2)) * (1/256)
-    const float c2 = s_h[r + 2][tx];
-    float v = __fmaf_rn(__fadd_rn(__fadd_rn(s_h[r + 1][tx], s_h[r + 3][tx]), c2), 4.f,
-                        __fadd_rn(__fadd_rn(s_h[r][tx], s_h[r + 4][tx]), __fadd_rn(c2, c2)));
+    // PyrDownVecV (4 lanes): ((r1 + r3) + r2)*4 + ((r0 + r4) + (r2 + r2)); scalar tail: ((r2*6 + (r1 + r3)*4) + r0) + r4
+    const float c2 = s_h[r + 2][tx], a13 = __fadd_rn(s_h[r + 1][tx], s_h[r + 3][tx]);
+    float v;
+    if (ox < (a.dst_cols & ~3))
+      v = __fadd_rn(__fmul_rn(__fadd_rn(a13, c2), 4.f), __fadd_rn(__fadd_rn(s_h[r][tx], s_h[r + 4][tx]), __fadd_rn(c2, c2)));
+    else
+      v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(c2, 6.f), __fmul_rn(a13, 4.f)), s_h[r][tx]), s_h[r + 4][tx]);
     v = __fmul_rn(v, 1.0f / 256.0f);
     if (a.post_scale != 1.f) v = __fmul_rn(v, a.post_scale);
     dst[(int64_t)oy * a.dst_cols + ox] = v;

@@ -90,3 +90,11 @@ def test_small_matrix_models_bit_exact():
         A = np.array([[1 + rng.normal(0, s), rng.normal(0, s), rng.normal(0, 50)],
                       [rng.normal(0, s), 1 + rng.normal(0, s), rng.normal(0, 50)]], np.float32)
         assert np.array_equal(cv2.invertAffineTransform(A), m.invert_affine_f32(A))
+
+
+def test_pyrdown_model_bit_exact():
+    rng = np.random.default_rng(6)
+    for (h, w, ds) in [(64, 80, None), (61, 83, None), (240, 320, None), (270, 480, (240, 134)), (33, 47, None), (134, 240, (120, 66))]:
+        src = rng.random((h, w)).astype(np.float32)
+        ref = cv2.pyrDown(src) if ds is None else cv2.pyrDown(src, dstsize=ds)
+        assert np.array_equal(ref, m.pyrdown_f32(src, ds)), (h, w, ds)

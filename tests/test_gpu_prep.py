@@ -70,3 +70,17 @@ def test_level0_smoothing_bit_exact(gpu):
     g = api.c_ecch(None, maxlevel=0, reference_smooth_sigma=1.0)
     g.set_reference_image(img)
     assert np.array_equal(g.reference_image(0), o.pyramid[0].reference_image)
+
+
+@pytest.mark.parametrize("size", [(320, 240), (336, 252), (960, 540)])
+def test_pyramid_bit_exact(gpu, size):
+    """Gaussian smoothing + the whole cv::pyrDown chain are bit-identical to cv2, level by level (level-0 widths
+    that are a multiple of 4; OpenCV's scalar tail columns of sepFilter2D are matched to 2e-6 only)."""
+    from serstacker_b200 import api
+    img, _ = _frame(size[0], size[1], 5)
+    o = oecc.EccH(oecc_transform(), maxlevel=-1, minimum_image_size=16)
+    o.set_reference_image(img, None)
+    g = api.c_ecch(None, maxlevel=-1, minimum_image_size=16)
+    g.set_reference_image(img)
+    for l, e in enumerate(o.pyramid):
+        assert np.array_equal(g.reference_image(l), e.reference_image), l
