@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""
+bench.py - frames/s of the stacking hot path (register + warp + stack) on BASELINE.json config #2:
+synthetic 1920x1080 mono 32F frames, ECCH pyramid registration (AFFINE, INVERSE_COMPOSITIONAL_LM, translation first),
+bicubic remap, sharpness-weighted average.  One process per GPU; frames shard across ranks (weak scaling), one
+reduce of (sum w*I, sum w) at the end.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of B frames per GPU.  `value` is measured with the frames
+resident in HBM; `e2e` goes through the C ABI with pinned HOST buffers (H2D inside the timed region, D2H of the
+per-frame registration results).  `--impl reference` times the CPU restatement of the reference (oracle/, the same
+OpenCV kernels through cv2) on the host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 1080, 1920
+NPIX = H * W
+WORKLOAD = "config#2: 1920x1080 mono32F, ECCH(IC-LM, affine, translation-first, full pyramid) + bicubic remap + sharpness-weighted average"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# synthetic frames (torch on the GPU: data generation only, not part of the measured path)
+# ------------------------------------------------------------------------------------------------------------
+def make_frames_gpu(n, seed, device, radius=400.0):
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    yy, xx = torch.meshgrid(torch.arange(H, device=device, dtype=torch.float32),
+                            torch.arange(W, device=device, dtype=torch.float32), indexing="ij")
+    cx, cy = (W - 1) / 2.0, (H - 1) / 2.0
+    belts = [(rng.uniform(-0.8, 0.8) * radius, rng.uniform(0.03, 0.08) * radius, rng.uniform(-0.25, 0.25)) for _ in range(6)]
+    spots = [(rng.uniform(-0.7, 0.7) * radius, rng.uniform(-0.7, 0.7) * radius, rng.uniform(2.0, 6.0) * radius / 150.0,
+              rng.uniform(-0.3, 0.3)) for _ in range(40)]
+    out = torch.empty((n, H, W), device=device, dtype=torch.float32)
+    for i in range(n):
+        if i == 0:
+            A = np.array([[1.0, 0, 0], [0, 1.0, 0]])
+            sig = 0.8
+        else:
+            tx, ty = np.clip(rng.normal(0.0, 4.0, 2), -10, 10)
+            a = math.radians(rng.normal(0.0, 0.2))
+            s = rng.normal(1.0, 0.002)
+            ca, sa = s * math.cos(a), s * math.sin(a)
+            A = np.array([[ca, -sa, cx - ca * cx + sa * cy + tx], [sa, ca, cy - sa * cx - ca * cy + ty]])
+            sig = rng.uniform(0.8, 2.5)
+        sx = A[0, 0] * xx + A[0, 1] * yy + (A[0, 2] - cx)
+        sy = A[1, 0] * xx + A[1, 1] * yy + (A[1, 2] - cy)
+        r2 = (sx * sx + sy * sy) / (radius * radius)
+        mu = torch.sqrt(torch.clamp(1.0 - r2, 0.0, 1.0))
+        img = 0.8 * (1.0 - 0.6 * (1.0 - mu))
+        tex = torch.zeros_like(img)
+        for (by, bs, ba) in belts:
+            tex += ba * torch.exp(-0.5 * ((sy - by) / bs) ** 2)
+        for (px, py, ps, pa) in spots:
+            tex += pa * torch.exp(-0.5 * (((sx - px) / ps) ** 2 + ((sy - py) / ps) ** 2))
+        img = img * (1.0 + tex)
+        edge = torch.clamp((1.0 - torch.sqrt(r2)) * radius + 0.5, 0.0, 1.0)
+        img = 0.02 + (img - 0.02) * edge
+        # defocus blur (separable Gaussian) + noise
+        k = int(2 * math.ceil(3 * sig) + 1)
+        t = torch.arange(k, device=device, dtype=torch.float32) - k // 2
+        kern = torch.exp(-0.5 * (t / sig) ** 2)
+        kern = kern / kern.sum()
+        im4 = img[None, None]
+        im4 = torch.nn.functional.conv2d(torch.nn.functional.pad(im4, (k // 2, k // 2, 0, 0), mode="replicate"), kern.view(1, 1, 1, k))
+        im4 = torch.nn.functional.conv2d(torch.nn.functional.pad(im4, (0, 0, k // 2, k // 2), mode="replicate"), kern.view(1, 1, k, 1))
+        noise = torch.randn((H, W), generator=g).to(device) * 0.01
+        out[i] = torch.clamp(im4[0, 0] + noise, 0.0, 1.0)
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([c.strip() for c in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def oracle_options():
+    import cv2
+    from oracle import pipeline as opl, transforms as otf, ecc as oecc
+    so = opl.StackingOptions(accumulation_method=opl.ACC_WEIGHTED_AVERAGE)
+    so.registration.motion_type = otf.IMAGE_MOTION_AFFINE
+    so.registration.interpolation = cv2.INTER_CUBIC
+    so.registration.ecc.ecc_method = oecc.ECC_ALIGN_INVERSE_COMPOSITIONAL_LM
+    so.registration.ecc.ecch_max_level = -1
+    return so
+
+
+def run_cpu(frames_np, threads):
+    """The reference's CPU path (oracle restatement over cv2) on `frames_np`; returns frames/s."""
+    import cv2
+    from oracle import pipeline as opl
+    cv2.setNumThreads(threads)
+    so = oracle_options()
+    t0 = time.perf_counter()
+    opl.run_stacking(frames_np[1:], so, reference=frames_np[0])
+    dt = time.perf_counter() - t0
+    return (len(frames_np) - 1) / dt, dt
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=64, help="frames per step per GPU")
+    ap.add_argument("--pool", type=int, default=256, help="distinct synthetic frames resident per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=24, help="frames of the CPU baseline sample")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        import torch
+        ncores = os.cpu_count() or 1
+        dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+        per_step = 6
+        n = 1 + per_step * (args.steps + args.warmup)
+        pool = make_frames_gpu(min(n, 1 + per_step * 4), 2, dev).cpu().numpy()
+        fr = [pool[0]] + [pool[1 + (i % (len(pool) - 1))] for i in range(n - 1)]
+        for w in range(args.warmup):
+            run_cpu([fr[0]] + fr[1 + w * per_step:1 + (w + 1) * per_step], ncores)
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            k0 = 1 + (args.warmup + s) * per_step
+            run_cpu([fr[0]] + fr[k0:k0 + per_step], ncores)
+        dt = time.perf_counter() - t0
+        fps = args.steps * per_step / dt
+        print(json.dumps({
+            "impl": "reference", "metric": "frames/sec register+warp+stack 1080p", "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step": per_step},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": ncores, "kind": "port",
+                             "sample": "%d frames per step x %d steps of the same workload (oracle/ = reference restated over cv2 %s)" % (per_step, args.steps, __import__("cv2").__version__)},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from serstacker_b200 import api, capi
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    pool_n = max(args.pool, B + 1)
+    pool = make_frames_gpu(pool_n, 2 + 1000 * rank, dev)       # frame 0 = unjittered reference scene
+    ref = make_frames_gpu(1, 2, dev)[0] if rank != 0 else pool[0]   # every rank uses the same reference frame
+    if rank != 0:
+        pool[0] = ref
+
+    ro = api.registration_options(motion_type=capi.MOTION_AFFINE, interpolation=capi.INTER_CUBIC,
+                                  ecc=dict(ecc_method=capi.ECC_INVERSE_COMPOSITIONAL_LM, ecch_max_level=-1))
+    so = api.stack_options(registration=ro, accumulation_method=capi.STACK_WEIGHTED_AVERAGE, max_batch=B)
+    pipe = api.c_image_stacking_pipeline(so)
+    pipe.set_reference(capi.device_mat(ref.data_ptr(), H, W, np.float32))
+    stream = torch.cuda.ExternalStream(pipe.stream(), device=dev)
+
+    def dev_batch(step):
+        idx = [1 + ((step * B + i) % (pool_n - 1)) for i in range(B)]
+        return [capi.device_mat(pool[j].data_ptr(), H, W, np.float32) for j in idx]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def combine():
+        """multi-GPU epilogue: (sum w*I, sum w) reduced to rank 0 over NCCL, then back to the running mean."""
+        if world == 1:
+            return
+        acc_h = capi.lib.ssk_stack_accumulator(pipe._h)
+        pa, pw, ba, bw = C.c_void_p(), C.c_void_p(), C.c_int64(), C.c_int64()
+        capi.check(capi.lib.ssk_acc_device_state(acc_h, C.byref(pa), C.byref(pw), C.byref(ba), C.byref(bw)))
+        capi.check(capi.lib.ssk_acc_to_sum_form(acc_h))
+
+        class _View:
+            def __init__(self, ptr, nbytes):
+                self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+        ta = torch.as_tensor(_View(pa.value, ba.value), device=dev)
+        tw = torch.as_tensor(_View(pw.value, bw.value), device=dev)
+        dist.reduce(ta, 0)
+        dist.reduce(tw, 0)
+        nfr = torch.tensor([pipe.accumulated_frames()], device=dev)
+        dist.reduce(nfr, 0)
+        torch.cuda.synchronize()
+        capi.check(capi.lib.ssk_acc_from_sum_form(acc_h, int(nfr.item())))
+
+    # ---------------- device-resident throughput --------------------------------------------------------
+    for s in range(args.warmup):
+        pipe.add_frames_async(dev_batch(s))
+    pipe.sync()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = capi.lib.ssk_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    keep = []
+    for s in range(args.steps):
+        keep.append(pipe.add_frames_async(dev_batch(args.warmup + s)))
+    e1.record(stream)
+    pipe.sync()
+    combine()
+    barrier()
+    launches = capi.lib.ssk_kernel_launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    stage = pipe.stage_times()                      # last chunk: prep, weights, ECC, warp+accumulate (ms)
+    t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    accumulated = pipe.accumulated_frames()
+    value = world * args.steps * B / (ms * 1e-3)
+
+    # ---------------- end to end through the C ABI with host buffers ------------------------------------
+    n_host = min(2 * B, 128)
+    host = torch.empty((n_host, H, W), dtype=torch.float32).pin_memory()
+    host.copy_(pool[1:1 + n_host])
+    host_np = host.numpy()
+    pipe2 = api.c_image_stacking_pipeline(so)
+    pipe2.set_reference(ref.cpu().numpy())
+    e2e_steps = max(3, min(args.steps, 8))
+
+    def host_batch(step):
+        return [host_np[(step * B + i) % n_host] for i in range(B)]
+    for s in range(2):
+        pipe2.add_frames(host_batch(s))
+    barrier()
+    t0 = time.perf_counter()
+    ok_frames = 0
+    for s in range(e2e_steps):
+        res = pipe2.add_frames(host_batch(s))       # H2D of B frames + D2H of B registration records per step
+        ok_frames += sum(1 for r in res if r["ok"])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t_e = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e = world * e2e_steps * B / float(t_e.item())
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    # ---------------- roofline of the fused warp+accumulate kernel --------------------------------------
+    peak, peak_src = peaks()
+    t_k = stage[3] * 1e-3                            # device time of k_fill_jobs + k_warp_acc for one batch
+    bytes_kernel = NPIX * (4 + 4) * B + NPIX * 16    # frame + weight map read per frame; mean + weight RMW once per batch
+    bytes_survey = NPIX * 24 * B                     # N*(4 + 8 + 8 + 4) per frame (un-batched RMW)
+    achieved = bytes_kernel / t_k / 1e9
+
+    # ---------------- CPU baseline (rank 0, N=1 only) ---------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1:
+        ncores = os.cpu_count() or 1
+        sample = pool[:1 + args.cpu_sample].cpu().numpy()
+        run_cpu(list(sample[:3]), ncores)
+        fps_cpu, dt_cpu = run_cpu(list(sample), ncores)
+        cpu = {"value": fps_cpu, "unit": "frames/s", "cores": ncores, "kind": "port",
+               "sample": "%d frames of the same workload in %.1f s (oracle/: reference restated over cv2 %s, cv2 threads=%d)" % (
+                   args.cpu_sample, dt_cpu, __import__("cv2").__version__, ncores)}
+
+    if rank == 0:
+        line = {
+            "metric": "frames/sec register+warp+stack 1080p", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "resident_pool_frames": pool_n,
+                       "l2_policy": "inputs larger than L2: %d distinct frames (%.1f GB) cycled, %.0f MB touched per step" % (
+                           pool_n, pool_n * NPIX * 4 / 1e9, B * NPIX * 4 / 1e6),
+                       "accumulated_frames_rank0": accumulated},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * NPIX * 4,
+                    "d2h_bytes_per_step": B * (C.sizeof(capi.ssk_transform) + C.sizeof(capi.ssk_ecc_status)) + 4,
+                    "steps": e2e_steps, "registered_frames": ok_frames},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "k_warp_acc (fused bicubic warp + mask + weights + running weighted mean, one launch per batch)",
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "launch_ms": stage[3], "frames_per_launch": B,
+                         "algorithmic_bytes_per_launch": bytes_kernel,
+                         "frac_with_survey_bytes": bytes_survey / t_k / 1e9 / peak},
+            "stage_ms_per_batch": {"prep": stage[0], "weights": stage[1], "ecc": stage[2], "warp_accumulate": stage[3]},
+            "cpu_baseline": cpu,
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
