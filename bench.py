@@ -271,7 +271,7 @@ def main():
     value = world * args.steps * B / (ms * 1e-3)
 
     # ---------------- end to end through the C ABI with host buffers ------------------------------------
-    n_host = min(2 * B, 128)
+    n_host = min(2 * B, 128, pool_n - 1)
     host = torch.empty((n_host, H, W), dtype=torch.float32).pin_memory()
     host.copy_(pool[1:1 + n_host])
     host_np = host.numpy()

@@ -1,0 +1,512 @@
+// K5: fused sub-pixel warp + validity mask + weight-map warp + weighted running-mean accumulation for a batch of
+// frames (one launch per batch; the accumulators are read and written once per batch, every frame and weight map
+// is read once).
+//
+// Reference semantics reproduced here:
+//   c_frame_registration::base_remap   core/proc/image_registration/c_frame_registration.cc:1265-1386
+//        frame: cv::remap(interp, border); mask: remap(all-255, interp, CONSTANT 0) >= 255, erode 5x5 (border 255)
+//   weights: custom_remap(weights, interp, BORDER_CONSTANT), weights *= mask/255
+//                                      core/pipeline/c_image_stacking_pipeline/c_image_stacking_pipeline.cc:1653-1660, 1704-1714
+//   _weighted_average_update           core/average/c_frame_accumulation.cc:20-129
+//
+// Two kernels share the work (separate kernels keep each instruction footprint inside the 32 KB L1.5 I-cache):
+//   k_fused_staged   interior tiles, single channel: the tile's source footprint of frame j+1 is copied to shared
+//                    memory with cp.async (LDGSTS.128) while frame j is interpolated from shared memory with a rolling
+//                    register window (4 new taps per pixel instead of 16); the running mean / weight of the tile stay
+//                    in shared memory for the whole batch and move to / from HBM with 16-byte accesses.
+//   k_fused_generic  the ring of tiles along the image border (per-tap cv::borderInterpolate, eroded validity mask),
+//                    multi-channel frames, projective maps: one thread per pixel, accumulators in registers.
+#include "ssk_warp.cuh"
+#include <limits.h>
+
+namespace ssk {
+
+namespace {
+
+constexpr int TW = 32, TH = 32;          // tile of the accumulator handled by one CTA of the staged kernel
+constexpr int SWARPS = 4;                // warps per CTA
+constexpr int GR = TH / SWARPS;          // rows per warp strip
+constexpr int GSH = TH + 8;              // staged rows: tile + 3 taps + rounding + drift
+constexpr int WWD = TW + 8;              // staged weight-tile row (floats)
+
+__device__ __forceinline__ bool is_affine_like(int type) { return type != MAP_HOMOGRAPHY; }
+
+template <int INTERP> struct Taps { static constexpr int N = INTERP == SSK_INTER_CUBIC ? 4 : INTERP == SSK_INTER_LINEAR ? 2 : 1;
+                                    static constexpr int OFF = INTERP == SSK_INTER_CUBIC ? -1 : 0; };
+
+// ------------------------------------------------------------------------------------------------
+// generic per-pixel pieces (real function calls: rare paths must stay small)
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ int border_idx_call(int p, int n, int border) { return border_idx(p, n, border); }
+
+// cv::remap sample with run-time depth / interpolation / border, cv::remap's operation order (see ssk_common.cuh)
+__device__ __noinline__ float sample_any(const Img &im, int c, float u, float v, int interp, int border, float bval,
+                                         const float4 *cubic) {
+  int ix, iy, fx = 0, fy = 0, n, off;
+  float wx[4], wy[4];
+  if (interp == SSK_INTER_NEAREST) {
+    ix = __float2int_rn(u); iy = __float2int_rn(v); n = 1; off = 0; wx[0] = wy[0] = 1.f;
+  } else {
+    quant32(u, ix, fx);
+    quant32(v, iy, fy);
+    if (interp == SSK_INTER_LINEAR) {
+      const float tx = (float)fx * 0.03125f, ty = (float)fy * 0.03125f;
+      n = 2; off = 0; wx[0] = 1.0f - tx; wx[1] = tx; wy[0] = 1.0f - ty; wy[1] = ty;
+    } else {
+      const float4 cx = __ldg(cubic + fx), cy = __ldg(cubic + fy);
+      n = 4; off = -1;
+      wx[0] = cx.x; wx[1] = cx.y; wx[2] = cx.z; wx[3] = cx.w;
+      wy[0] = cy.x; wy[1] = cy.y; wy[2] = cy.z; wy[3] = cy.w;
+    }
+  }
+  float out = 0.f;
+#pragma unroll 1
+  for (int ky = 0; ky < n; ++ky) {
+    const int py = iy + off + ky;
+    const int yy = (unsigned)py < (unsigned)im.rows ? py : border_idx_call(py, im.rows, border);
+    float row = 0.f;
+#pragma unroll 1
+    for (int kx = 0; kx < n; ++kx) {
+      const int px = ix + off + kx;
+      const int xx = (unsigned)px < (unsigned)im.cols ? px : border_idx_call(px, im.cols, border);
+      float s = bval;
+      if (xx >= 0 && yy >= 0) {
+        const char *p = static_cast<const char *>(im.data) + (int64_t)yy * im.step;
+        if (im.depth == SSK_32F) s = __ldg(reinterpret_cast<const float *>(p) + xx * im.cn + c);
+        else if (im.depth == SSK_16U) s = __fmul_rn((float)__ldg(reinterpret_cast<const uint16_t *>(p) + xx * im.cn + c), im.scale);
+        else s = __fmul_rn((float)__ldg(reinterpret_cast<const uint8_t *>(p) + xx * im.cn + c), im.scale);
+      }
+      if (n == 1) return s;
+      const float term = __fmul_rn(s, __fmul_rn(wy[ky], wx[kx]));
+      if (n == 2) out = (ky == 0 && kx == 0) ? term : __fadd_rn(out, term);   // ((t00 + t01) + t10) + t11
+      else row = __fadd_rn(row, term);
+    }
+    if (n == 4) out = __fadd_rn(out, row);
+  }
+  return out;
+}
+
+// mask(x, y) of base_remap: erode5x5(remap(all-255, interp, CONSTANT 0) >= 255) with border value 255
+__device__ __noinline__ bool valid_eroded(const MapCoef &m, int interp, int x, int y, int cols, int rows, int src_cols,
+                                          int src_rows, const short *itab) {
+  float u, v;
+  map_xy(m, (float)x, (float)y, u, v);
+  if (is_affine_like(m.type)) {
+    // neighbours within 2 px map within (2|a| + 2|b|) px of (u, v): if that stays inside the tap-safe interior every
+    // one of the 25 pre-erosion flags is set
+    float u1, v1, u2, v2;
+    map_xy(m, (float)(x + 2), (float)y, u1, v1);
+    map_xy(m, (float)x, (float)(y + 2), u2, v2);
+    const float ru = fabsf(u1 - u) + fabsf(u2 - u) + 3.f, rv = fabsf(v1 - v) + fabsf(v2 - v) + 3.f;
+    if (u - ru >= 0.f && v - rv >= 0.f && u + ru <= (float)(src_cols - 1) && v + rv <= (float)(src_rows - 1)) return true;
+  }
+#pragma unroll 1
+  for (int dy = -2; dy <= 2; ++dy) {
+    const int yy = y + dy;
+    if ((unsigned)yy >= (unsigned)rows) continue;
+#pragma unroll 1
+    for (int dx = -2; dx <= 2; ++dx) {
+      const int xx = x + dx;
+      if ((unsigned)xx >= (unsigned)cols) continue;
+      map_xy(m, (float)xx, (float)yy, u, v);
+      if (!valid255(interp, u, v, src_cols, src_rows, itab)) return false;
+    }
+  }
+  return true;
+}
+
+// one pixel of one frame through the generic path: A (cn values) and W are updated in place
+__device__ __noinline__ void generic_pixel(const WarpAccArgs &a, const Tables &tab, const FrameJob &job, int x, int y,
+                                           float *A, float *W) {
+  const MapCoef m = job.map;
+  if (!valid_eroded(m, a.interp, x, y, a.cols, a.rows, a.src_cols, a.src_rows, tab.cubic_itab)) return;
+  float u, v;
+  map_xy(m, (float)x, (float)y, u, v);
+  Img im;
+  im.rows = a.src_rows; im.cols = a.src_cols;
+  const bool weighted = a.use_weights && job.weights != nullptr;
+  float wk = 1.f;
+  if (weighted) {
+    im.data = job.weights; im.step = a.w_step; im.depth = SSK_32F; im.cn = 1; im.scale = 1.f;
+    wk = sample_any(im, 0, u, v, a.interp, SSK_BORDER_CONSTANT, 0.f, tab.cubic);
+    if (!(wk > 0.f)) return;                      // c_frame_accumulation.cc:114
+  }
+  im.data = job.frame; im.step = a.src_step; im.depth = a.depth; im.cn = a.cn; im.scale = a.scale;
+  const float Wn = *W + wk;
+  const float factor = weighted ? __fdiv_rn(wk, Wn) : __fdiv_rn(1.0f, Wn);
+  *W = Wn;
+  for (int c = 0; c < a.cn; ++c) {
+    const float I = sample_any(im, c, u, v, a.interp, a.border, a.bval[c], tab.cubic);
+    A[c] = fmaf(I - A[c], factor, A[c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_fused_generic: one thread per pixel of a list of tiles (the border ring, or the whole image)
+// ------------------------------------------------------------------------------------------------
+struct TileList {            // tiles of TW x TH pixels; `ring` selects the border ring of an ntx x nty tiling
+  int ntx, nty, ring;
+};
+
+__device__ __forceinline__ void tile_of_block(const TileList &t, int b, int &tx, int &ty) {
+  if (!t.ring) { tx = b % t.ntx; ty = b / t.ntx; return; }
+  if (b < t.ntx) { tx = b; ty = 0; return; }
+  b -= t.ntx;
+  if (b < t.ntx) { tx = b; ty = t.nty - 1; return; }
+  b -= t.ntx;
+  if (b < t.nty - 2) { tx = 0; ty = 1 + b; return; }
+  b -= t.nty - 2;
+  tx = t.ntx - 1; ty = 1 + b;
+}
+
+__global__ void __launch_bounds__(256) k_fused_generic(const __grid_constant__ WarpAccArgs a, const __grid_constant__ Tables tab, const TileList tl) {
+  int tx, ty;
+  tile_of_block(tl, blockIdx.x >> 2, tx, ty);                 // 4 CTAs of 32 x 8 pixels per tile
+  const int x = tx * TW + (threadIdx.x & 31);
+  const int y = ty * TH + (blockIdx.x & 3) * 8 + (threadIdx.x >> 5);
+  if (x >= a.cols || y >= a.rows) return;
+  const int64_t p = (int64_t)y * a.cols + x;
+  float A[4], W = a.wacc[p];
+  for (int c = 0; c < a.cn; ++c) A[c] = a.acc[p * a.cn + c];
+#pragma unroll 1
+  for (int j = 0; j < a.njobs; ++j) {
+    if (!a.jobs[j].ok) continue;
+    generic_pixel(a, tab, a.jobs[j], x, y, A, &W);
+  }
+  a.wacc[p] = W;
+  for (int c = 0; c < a.cn; ++c) a.acc[p * a.cn + c] = A[c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_fused_staged
+// ------------------------------------------------------------------------------------------------
+template <int DEPTH> struct StageGeom {
+  static constexpr int ES = (DEPTH == SSK_32F ? 4 : DEPTH == SSK_16U ? 2 : 1);
+  static constexpr int ALIGN = 16 / ES;                                        // elements per 16-byte chunk
+  static constexpr int WD = ((TW + 4 + ALIGN + ALIGN - 1) / ALIGN) * ALIGN;    // staged frame row (elements)
+  static constexpr int ROWB = WD * ES;
+};
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int NKEEP> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NKEEP)); }
+
+struct StagePlan { int staged, sx0, sy0, sxw; };   // staged: tile safe and footprint fits; sxw: weight-tile origin
+
+// Footprint of the tile in the frame (block-uniform).  es / align describe the frame element type.
+__device__ __noinline__ StagePlan plan_stage(const MapCoef &m, int bx0, int by0, const WarpAccArgs &a, int align, int wd) {
+  StagePlan p; p.staged = 0; p.sx0 = p.sy0 = p.sxw = 0;
+  if (!a.stage_aligned || !is_affine_like(m.type)) return p;
+  const int cx0 = max(bx0 - 2, 0), cy0 = max(by0 - 2, 0);
+  const int cx1 = min(bx0 + TW + 1, a.cols - 1), cy1 = min(by0 + TH + 1, a.rows - 1);
+  float umin = 3.4e38f, umax = -3.4e38f, vmin = 3.4e38f, vmax = -3.4e38f;
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    float u, v;
+    map_xy(m, (float)((k & 1) ? cx1 : cx0), (float)((k & 2) ? cy1 : cy0), u, v);
+    umin = fminf(umin, u); umax = fmaxf(umax, u); vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+  }
+  // safe interior: every pixel of the tile (and of its 2-px erosion halo) is valid and every tap is in bounds
+  if (!(umin >= 3.f && vmin >= 3.f && umax <= (float)(a.src_cols - 4) && vmax <= (float)(a.src_rows - 4))) return p;
+  const int x_lo = (int)floorf(umin) - 1, x_hi = (int)floorf(umax) + 3;
+  const int y_lo = (int)floorf(vmin) - 1, y_hi = (int)floorf(vmax) + 3;
+  p.sx0 = x_lo & ~(align - 1);
+  p.sy0 = y_lo;
+  p.sxw = x_lo & ~3;
+  p.staged = (x_hi - p.sx0 < wd) && (y_hi - p.sy0 < GSH) && (x_hi - p.sxw < WWD);
+  return p;
+}
+
+template <int DEPTH>
+__device__ __noinline__ void issue_stage(const FrameJob &job, const StagePlan &p, const WarpAccArgs &a, bool weighted,
+                                         unsigned char *s_f, float *s_g) {
+  typedef StageGeom<DEPTH> G;
+  constexpr int CPR = G::WD / G::ALIGN;            // 16-byte chunks per staged frame row
+#pragma unroll 1
+  for (int k = threadIdx.x; k < GSH * CPR; k += blockDim.x) {
+    const int r = k / CPR, q = k - r * CPR;
+    const int gy = p.sy0 + r, gx = p.sx0 + q * G::ALIGN;
+    if (gy < a.src_rows && gx + G::ALIGN <= a.src_cols)
+      cp_async16(s_f + r * G::ROWB + q * 16, static_cast<const char *>(job.frame) + (int64_t)gy * a.src_step + (int64_t)gx * G::ES);
+  }
+  if (weighted) {
+#pragma unroll 1
+    for (int k = threadIdx.x; k < GSH * (WWD / 4); k += blockDim.x) {
+      const int r = k / (WWD / 4), q = k - r * (WWD / 4);
+      const int gy = p.sy0 + r, gx = p.sxw + q * 4;
+      if (gy < a.src_rows && gx + 4 <= a.src_cols)
+        cp_async16(s_g + r * WWD + q * 4, reinterpret_cast<const char *>(job.weights) + (int64_t)gy * a.w_step + (int64_t)gx * 4);
+    }
+  }
+}
+
+template <int DEPTH>
+__device__ __forceinline__ float lds_px(const unsigned char *p, float scale) {
+  if (DEPTH == SSK_32F) return *reinterpret_cast<const float *>(p);
+  if (DEPTH == SSK_16U) return __fmul_rn((float)*reinterpret_cast<const uint16_t *>(p), scale);
+  return __fmul_rn((float)*p, scale);
+}
+
+// Column-invariant part of an affine-like map: the per-row evaluation keeps the reference's operand order
+// (bit-identical to map_xy) without a type switch in the hot loop.
+template <int MT> struct ColMap {
+  float a, b, c, d, e, f, g, h;
+  __device__ __forceinline__ ColMap(const MapCoef &m, float x) {
+    a = b = c = d = e = f = g = h = 0.f;
+    if (MT == MAP_TRANSLATION) { a = __fadd_rn(x, m.c[0]); b = m.c[1]; }
+    else if (MT == MAP_AFFINE) { a = __fmul_rn(m.c[0], x); b = m.c[1]; c = m.c[2]; d = __fmul_rn(m.c[3], x); e = m.c[4]; f = m.c[5]; }
+    else {  // euclidean: xx = x - Cx
+      const float xx = __fsub_rn(x, m.c[5]);
+      a = __fmul_rn(m.c[1], xx); b = __fmul_rn(m.c[2], xx); c = m.c[0]; d = m.c[1]; e = m.c[2]; f = m.c[3]; g = m.c[4]; h = m.c[6];
+    }
+  }
+  __device__ __forceinline__ void operator()(float y, float &u, float &v) const {
+    if (MT == MAP_TRANSLATION) { u = a; v = __fadd_rn(y, b); }
+    else if (MT == MAP_AFFINE) {
+      u = __fadd_rn(__fadd_rn(a, __fmul_rn(b, y)), c);
+      v = __fadd_rn(__fadd_rn(d, __fmul_rn(e, y)), f);
+    } else {
+      const float yy = __fsub_rn(y, h);
+      u = __fadd_rn(__fmul_rn(c, __fsub_rn(a, __fmul_rn(e, yy))), f);
+      v = __fadd_rn(__fmul_rn(c, __fadd_rn(b, __fmul_rn(d, yy))), g);
+    }
+  }
+};
+
+template <int INTERP> struct RollS {
+  static constexpr int N = Taps<INTERP>::N;
+  float f[N][N], w[N][N];    // frame / weight windows, rows in rotating slots
+  int ix, iy;                // source anchor of the windows
+  const unsigned char *pf;   // staged frame row that enters the window next
+  const float *pw;           // staged weight row that enters the window next
+};
+
+// One output pixel from the staged tiles: slide the windows one row down (or re-anchor them), interpolate the weight
+// and the frame, update the running weighted mean held in shared memory (predicated, straight-line).
+// Bicubic is evaluated separably with FMAs (row sums first): it differs from cv::remap's 16-product sum in the last
+// ulp only, far inside the 1e-4 stack tolerance; bilinear keeps cv::remap's exact order.
+template <int DEPTH, int INTERP, bool WEIGHTS, int MT, int J>
+__device__ __forceinline__ void roll_pixel_s(RollS<INTERP> &R, const ColMap<MT> &cm, float y, const unsigned char *s_f,
+                                             const float *s_g, float scale, const StagePlan &pl, const float4 *s_cubic,
+                                             float *s_acc_px, float *s_w_px) {
+  typedef StageGeom<DEPTH> G;
+  constexpr int N = Taps<INTERP>::N, OFF = Taps<INTERP>::OFF;
+  float u, v;
+  cm(y, u, v);
+  int ix, iy, fx = 0, fy = 0;
+  if (INTERP == SSK_INTER_NEAREST) { ix = __float2int_rn(u); iy = __float2int_rn(v); }
+  else { quant32(u, ix, fx); quant32(v, iy, fy); }
+  if (ix != R.ix || iy != R.iy + 1) {
+    R.pf = s_f + (iy + OFF - pl.sy0) * G::ROWB + (ix + OFF - pl.sx0) * G::ES;
+    R.pw = s_g + (iy + OFF - pl.sy0) * WWD + (ix + OFF - pl.sxw);
+#pragma unroll
+    for (int r = 0; r < N - 1; ++r) {
+#pragma unroll
+      for (int q = 0; q < N; ++q) {
+        R.f[(J + r) % N][q] = lds_px<DEPTH>(R.pf + q * G::ES, scale);
+        if (WEIGHTS) R.w[(J + r) % N][q] = R.pw[q];
+      }
+      R.pf += G::ROWB; R.pw += WWD;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    R.f[(J + N - 1) % N][q] = lds_px<DEPTH>(R.pf + q * G::ES, scale);
+    if (WEIGHTS) R.w[(J + N - 1) % N][q] = R.pw[q];
+  }
+  R.pf += G::ROWB; R.pw += WWD;
+  R.ix = ix; R.iy = iy;
+
+  float I, wk = 1.f;
+  if (INTERP == SSK_INTER_CUBIC) {
+    const float4 cx = s_cubic[fx], cy = s_cubic[fy];
+    float rs[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float *t = R.f[(J + r) % N];
+      rs[r] = fmaf(t[3], cx.w, fmaf(t[2], cx.z, fmaf(t[1], cx.y, t[0] * cx.x)));
+    }
+    I = fmaf(rs[3], cy.w, fmaf(rs[2], cy.z, fmaf(rs[1], cy.y, rs[0] * cy.x)));
+    if (WEIGHTS) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float *t = R.w[(J + r) % N];
+        rs[r] = fmaf(t[3], cx.w, fmaf(t[2], cx.z, fmaf(t[1], cx.y, t[0] * cx.x)));
+      }
+      wk = fmaf(rs[3], cy.w, fmaf(rs[2], cy.z, fmaf(rs[1], cy.y, rs[0] * cy.x)));
+    }
+  } else if (INTERP == SSK_INTER_LINEAR) {
+    // cv::remapBilinear's exact order: ((S00*w00 + S01*w01) + S10*w10) + S11*w11
+    const float tx = (float)fx * 0.03125f, ty = (float)fy * 0.03125f;
+    const float w00 = __fmul_rn(1.0f - ty, 1.0f - tx), w01 = __fmul_rn(1.0f - ty, tx), w10 = __fmul_rn(ty, 1.0f - tx), w11 = __fmul_rn(ty, tx);
+    const float *f0 = R.f[J % N], *f1 = R.f[(J + 1) % N];
+    I = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f0[0], w00), __fmul_rn(f0[1], w01)), __fmul_rn(f1[0], w10)), __fmul_rn(f1[1], w11));
+    if (WEIGHTS) {
+      const float *g0 = R.w[J % N], *g1 = R.w[(J + 1) % N];
+      wk = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(g0[0], w00), __fmul_rn(g0[1], w01)), __fmul_rn(g1[0], w10)), __fmul_rn(g1[1], w11));
+    }
+  } else {
+    I = R.f[0][0];
+    if (WEIGHTS) wk = R.w[0][0];
+  }
+  const float W0 = *s_w_px, A = *s_acc_px;
+  const float Wn = W0 + wk;
+  const float factor = WEIGHTS ? __fdiv_rn(wk, Wn) : __fdiv_rn(1.0f, Wn);
+  const bool upd = !WEIGHTS || wk > 0.f;          // c_frame_accumulation.cc:114
+  *s_w_px = upd ? Wn : W0;
+  *s_acc_px = upd ? fmaf(I - A, factor, A) : A;
+}
+
+template <int DEPTH, int INTERP, bool WEIGHTS, int MT>
+__global__ void __launch_bounds__(TW * SWARPS) k_fused_staged(const __grid_constant__ WarpAccArgs a, const __grid_constant__ Tables tab, int tx_first, int ty_first) {
+  typedef StageGeom<DEPTH> G;
+  constexpr int N = Taps<INTERP>::N;
+  __shared__ float s_acc[TH][TW];                  // running mean of the tile (on chip for the whole batch)
+  __shared__ float s_w[TH][TW];                    // running weight sum of the tile
+  __shared__ float4 s_cubic[kInterTab];
+  __shared__ __align__(16) unsigned char s_f[2][GSH * G::ROWB];
+  __shared__ __align__(16) float s_g[2][GSH * WWD];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int bx0 = (blockIdx.x + tx_first) * TW, by0 = (blockIdx.y + ty_first) * TH;
+  const int x = bx0 + lane, y0 = by0 + warp * GR;
+  if (INTERP == SSK_INTER_CUBIC && threadIdx.x < kInterTab) s_cubic[threadIdx.x] = tab.cubic[threadIdx.x];
+
+  // interior tiles are always complete; 16-byte accesses when the accumulator pitch allows it
+  const bool vec = (a.cols & 3) == 0;
+  if (vec) {
+    for (int k = threadIdx.x; k < TH * (TW / 4); k += blockDim.x) {
+      const int r = k / (TW / 4), q = k - r * (TW / 4);
+      reinterpret_cast<float4 *>(s_acc[r])[q] = *reinterpret_cast<const float4 *>(a.acc + (int64_t)(by0 + r) * a.cols + bx0 + 4 * q);
+      reinterpret_cast<float4 *>(s_w[r])[q] = *reinterpret_cast<const float4 *>(a.wacc + (int64_t)(by0 + r) * a.cols + bx0 + 4 * q);
+    }
+  } else {
+    for (int k = threadIdx.x; k < TH * TW; k += blockDim.x) {
+      const int r = k / TW, q = k - r * TW;
+      s_acc[r][q] = a.acc[(int64_t)(by0 + r) * a.cols + bx0 + q];
+      s_w[r][q] = a.wacc[(int64_t)(by0 + r) * a.cols + bx0 + q];
+    }
+  }
+
+  // software pipeline over the frames of the batch: while frame j is interpolated, frame j+1's footprint lands
+  int j = 0;
+  while (j < a.njobs && !a.jobs[j].ok) ++j;
+  int buf = 0;
+  StagePlan plan = {0, 0, 0, 0};
+  if (j < a.njobs) {
+    plan = plan_stage(a.jobs[j].map, bx0, by0, a, G::ALIGN, G::WD);
+    if (WEIGHTS && !a.jobs[j].weights) plan.staged = 0;    // flat frame (no weight map): generic path
+    if (plan.staged) issue_stage<DEPTH>(a.jobs[j], plan, a, WEIGHTS, s_f[0], s_g[0]);
+  }
+  cp_async_commit();
+  __syncthreads();
+
+#pragma unroll 1
+  while (j < a.njobs) {
+    int jn = j + 1;
+    while (jn < a.njobs && !a.jobs[jn].ok) ++jn;
+    StagePlan plan_n = {0, 0, 0, 0};
+    if (jn < a.njobs) {
+      plan_n = plan_stage(a.jobs[jn].map, bx0, by0, a, G::ALIGN, G::WD);
+      if (WEIGHTS && !a.jobs[jn].weights) plan_n.staged = 0;
+      if (plan_n.staged) issue_stage<DEPTH>(a.jobs[jn], plan_n, a, WEIGHTS, s_f[buf ^ 1], s_g[buf ^ 1]);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();            // frame j's group has landed (frame j+1's may still be in flight)
+    __syncthreads();
+
+    float *s_acc0 = &s_acc[warp * GR][lane], *s_w0 = &s_w[warp * GR][lane];
+    if (plan.staged) {
+      const MapCoef m = a.jobs[j].map;
+      const ColMap<MT> cm(m, (float)x);
+      const unsigned char *sf = s_f[buf];
+      const float *sg = s_g[buf];
+      RollS<INTERP> R;
+      R.ix = INT_MIN; R.iy = INT_MIN; R.pf = sf; R.pw = sg;
+#pragma unroll 1
+      for (int k = 0; k < GR; k += N) {
+        roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 0>(R, cm, (float)(y0 + k), sf, sg, a.scale, plan, s_cubic, s_acc0 + k * TW, s_w0 + k * TW);
+        if (N > 1) roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 1 % N>(R, cm, (float)(y0 + k + 1), sf, sg, a.scale, plan, s_cubic, s_acc0 + (k + 1) * TW, s_w0 + (k + 1) * TW);
+        if (N > 2) roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 2 % N>(R, cm, (float)(y0 + k + 2), sf, sg, a.scale, plan, s_cubic, s_acc0 + (k + 2) * TW, s_w0 + (k + 2) * TW);
+        if (N > 3) roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 3 % N>(R, cm, (float)(y0 + k + 3), sf, sg, a.scale, plan, s_cubic, s_acc0 + (k + 3) * TW, s_w0 + (k + 3) * TW);
+      }
+    } else {
+      // this (tile, frame) pair cannot be staged (large displacement, flat frame): generic per-pixel path
+#pragma unroll 1
+      for (int k = 0; k < GR; ++k) generic_pixel(a, tab, a.jobs[j], x, y0 + k, s_acc0 + k * TW, s_w0 + k * TW);
+    }
+    __syncthreads();               // everyone is done with buffer `buf` before it is refilled
+    j = jn; plan = plan_n; buf ^= 1;
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  if (vec) {
+    for (int k = threadIdx.x; k < TH * (TW / 4); k += blockDim.x) {
+      const int r = k / (TW / 4), q = k - r * (TW / 4);
+      *reinterpret_cast<float4 *>(a.acc + (int64_t)(by0 + r) * a.cols + bx0 + 4 * q) = reinterpret_cast<const float4 *>(s_acc[r])[q];
+      *reinterpret_cast<float4 *>(a.wacc + (int64_t)(by0 + r) * a.cols + bx0 + 4 * q) = reinterpret_cast<const float4 *>(s_w[r])[q];
+    }
+  } else {
+    for (int k = threadIdx.x; k < TH * TW; k += blockDim.x) {
+      const int r = k / TW, q = k - r * TW;
+      a.acc[(int64_t)(by0 + r) * a.cols + bx0 + q] = s_acc[r][q];
+      a.wacc[(int64_t)(by0 + r) * a.cols + bx0 + q] = s_w[r][q];
+    }
+  }
+}
+
+template <int DEPTH, int INTERP, bool WEIGHTS>
+void launch_staged_mt(const WarpAccArgs &a, const Tables &tab, dim3 grid, cudaStream_t s) {
+  const dim3 block(TW * SWARPS);
+  if (a.map_type == MAP_AFFINE) k_fused_staged<DEPTH, INTERP, WEIGHTS, MAP_AFFINE><<<grid, block, 0, s>>>(a, tab, 1, 1);
+  else if (a.map_type == MAP_TRANSLATION) k_fused_staged<DEPTH, INTERP, WEIGHTS, MAP_TRANSLATION><<<grid, block, 0, s>>>(a, tab, 1, 1);
+  else k_fused_staged<DEPTH, INTERP, WEIGHTS, MAP_EUCLIDEAN><<<grid, block, 0, s>>>(a, tab, 1, 1);
+}
+
+template <int DEPTH>
+void launch_staged(const WarpAccArgs &a, const Tables &tab, dim3 grid, cudaStream_t s) {
+  if (a.use_weights) {
+    if (a.interp == SSK_INTER_CUBIC) launch_staged_mt<DEPTH, SSK_INTER_CUBIC, true>(a, tab, grid, s);
+    else if (a.interp == SSK_INTER_NEAREST) launch_staged_mt<DEPTH, SSK_INTER_NEAREST, true>(a, tab, grid, s);
+    else launch_staged_mt<DEPTH, SSK_INTER_LINEAR, true>(a, tab, grid, s);
+  } else {
+    if (a.interp == SSK_INTER_CUBIC) launch_staged_mt<DEPTH, SSK_INTER_CUBIC, false>(a, tab, grid, s);
+    else if (a.interp == SSK_INTER_NEAREST) launch_staged_mt<DEPTH, SSK_INTER_NEAREST, false>(a, tab, grid, s);
+    else launch_staged_mt<DEPTH, SSK_INTER_LINEAR, false>(a, tab, grid, s);
+  }
+}
+
+}  // namespace
+
+int launch_warp_accumulate(const WarpAccArgs &a_in, const Tables &tab, cudaStream_t s) {
+  WarpAccArgs a = a_in;
+  SSK_REQUIRE(a.interp == SSK_INTER_NEAREST || a.interp == SSK_INTER_LINEAR || a.interp == SSK_INTER_CUBIC,
+              "warp_accumulate: interpolation must be NEAREST, LINEAR or CUBIC");
+  SSK_REQUIRE(a.border != SSK_BORDER_TRANSPARENT, "warp_accumulate: BORDER_TRANSPARENT is not meaningful here");
+  SSK_REQUIRE(a.cn >= 1 && a.cn <= 4, "warp_accumulate: 1..4 channels");
+  SSK_REQUIRE(a.depth == SSK_32F || a.depth == SSK_16U || a.depth == SSK_8U, "warp_accumulate: unsupported frame depth");
+  a.stage_aligned = a.stage_aligned && (a.src_step % 16 == 0) && (a.w_step % 16 == 0);
+  const int ntx = div_up(a.cols, TW), nty = div_up(a.rows, TH);
+  const bool staged = a.cn == 1 && ntx >= 3 && nty >= 3 &&
+                      (a.map_type == MAP_AFFINE || a.map_type == MAP_TRANSLATION || a.map_type == MAP_EUCLIDEAN);
+  TileList tl;
+  tl.ntx = ntx; tl.nty = nty; tl.ring = staged ? 1 : 0;
+  const int ntiles = staged ? 2 * ntx + 2 * (nty - 2) : ntx * nty;
+  // border ring (or everything, when the staged kernel does not apply) through the generic per-pixel kernel
+  k_fused_generic<<<ntiles * 4, 256, 0, s>>>(a, tab, tl);
+  SSK_LAUNCH_CHECK();
+  if (staged) {
+    const dim3 grid(ntx - 2, nty - 2);
+    if (a.depth == SSK_32F) launch_staged<SSK_32F>(a, tab, grid, s);
+    else if (a.depth == SSK_16U) launch_staged<SSK_16U>(a, tab, grid, s);
+    else launch_staged<SSK_8U>(a, tab, grid, s);
+    SSK_LAUNCH_CHECK();
+  }
+  return SSK_OK;
+}
+
+}  // namespace ssk

@@ -58,6 +58,7 @@ struct ssk_stack {
   int ring_pos = 0;
   PinnedBuf h_counter;
   int w1_rows = 0, w1_cols = 0, w1_nb = 0;
+  bool frames_aligned = true;            // every frame pointer of the current chunk is 16-byte aligned
   cudaEvent_t ev[5] = {};
   DevBuf ref_staging;
   ~ssk_stack() {
@@ -192,6 +193,7 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n) {
   geom.rows = h->rows; geom.cols = h->cols; geom.depth = d; geom.cn = cn; geom.scale = bpp_scale(d, h->bpp);
   geom.data = nullptr;
   const void *const *d_frame_ptrs;
+  h->frames_aligned = true;
   if (frames[0].mem == SSK_MEM_DEVICE) {
     // frames already resident: upload this chunk's pointer table through a small pinned ring
     const int r = h->ring_pos;
@@ -201,6 +203,7 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n) {
     for (int i = 0; i < n; ++i) {
       SSK_REQUIRE(frames[i].mem == SSK_MEM_DEVICE && frames[i].step == frames[0].step, "frames of a call must share memory space and step");
       hp[i] = frames[i].data;
+      if (reinterpret_cast<uintptr_t>(frames[i].data) & 15) h->frames_aligned = false;
     }
     SSK_CUDA(cudaMemcpyAsync(h->d_user_ptrs[r].p, hp, sizeof(void *) * n, cudaMemcpyHostToDevice, s));
     SSK_CUDA(cudaEventRecord(h->ring_ev[r], s));
@@ -276,6 +279,12 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n) {
   a.border = ro.border_mode;
   for (int i = 0; i < 4; ++i) a.bval[i] = (float)ro.border_value[i];
   a.use_weights = weighted ? 1 : 0;
+  a.stage_aligned = h->frames_aligned ? 1 : 0;
+  {
+    ssk_transform t0;
+    make_transform(&t0, h->o.enable_registration ? ro.motion_type : SSK_MOTION_TRANSLATION);
+    a.map_type = make_mapcoef(t0).type;
+  }
   a.acc = h->acc_h.a.acc.as<float>(); a.wacc = h->acc_h.a.wacc.as<float>();
   if (int e = launch_warp_accumulate(a, h->tab, s)) return e;
   SSK_CUDA(cudaEventRecord(h->ev[4], s));

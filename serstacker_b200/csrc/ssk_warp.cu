@@ -6,199 +6,10 @@
 //   multiply_weights                        core/pipeline/c_image_stacking_pipeline/c_image_stacking_pipeline.cc:108-138,1704-1714
 //   _weighted_average_update                core/average/c_frame_accumulation.cc:20-129
 //   _bayer_accumulate / compute             core/average/c_frame_accumulation.cc:988-1126, 1205-1238
-// One pass per frame: the frame (and its weight map) are read once, the accumulators are read and written
-// once per *batch* (they stay in registers across the frames of a batch).
+// (the fused warp + accumulate kernels live in ssk_fused.cu)
 #include "ssk_warp.cuh"
 
 namespace ssk {
-
-namespace {
-
-constexpr int TW = 128;   // tile width  (32 lanes x 4 px, 16-byte accesses)
-constexpr int TH = 8;     // tile height (8 warps)
-constexpr int HALO = 2;   // 5x5 erosion
-constexpr int FW = TW + 2 * HALO;
-constexpr int FH = TH + 2 * HALO;
-
-template <int DEPTH, int INTERP>
-__device__ __forceinline__ float sample(const Img &im, int c, float u, float v, int border, float bval,
-                                        const Tables &tab) {
-  if (INTERP == SSK_INTER_CUBIC) return sample_cubic<DEPTH>(im, c, u, v, border, bval, tab.cubic);
-  if (INTERP == SSK_INTER_NEAREST) return sample_nearest<DEPTH>(im, c, u, v, border, bval);
-  return sample_linear<DEPTH>(im, c, u, v, border, bval);
-}
-
-__device__ __forceinline__ bool is_affine_like(int type) { return type != MAP_HOMOGRAPHY; }
-
-template <int DEPTH, int CN, int INTERP, bool WEIGHTS>
-__global__ void __launch_bounds__(256) k_warp_acc(const WarpAccArgs a, const Tables tab) {
-  __shared__ uint8_t s_valid[FH][FW + 4];
-
-  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
-  const int bx0 = blockIdx.x * TW, by0 = blockIdx.y * TH;
-  const int x0 = bx0 + lane * 4, y = by0 + wy;
-  const bool row_ok = y < a.rows;
-  const bool vec = (a.cols & 3) == 0;
-  const int npx = !row_ok ? 0 : min(4, a.cols - x0);   // <= 0 when the thread is outside
-
-  float A[4][CN], W[4];
-  const int64_t pix0 = (int64_t)y * a.cols + x0;
-  if (npx > 0) {
-    if (vec) {
-      const float4 w4 = *reinterpret_cast<const float4 *>(a.wacc + pix0);
-      W[0] = w4.x; W[1] = w4.y; W[2] = w4.z; W[3] = w4.w;
-      float tmp[4 * CN];
-#pragma unroll
-      for (int k = 0; k < CN; ++k)
-        *reinterpret_cast<float4 *>(tmp + 4 * k) = *reinterpret_cast<const float4 *>(a.acc + pix0 * CN + 4 * k);
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int c = 0; c < CN; ++c) A[i][c] = tmp[i * CN + c];
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        W[i] = i < npx ? a.wacc[pix0 + i] : 0.f;
-#pragma unroll
-        for (int c = 0; c < CN; ++c) A[i][c] = i < npx ? a.acc[(pix0 + i) * CN + c] : 0.f;
-      }
-    }
-  }
-
-  Img src;
-  src.step = a.src_step; src.rows = a.src_rows; src.cols = a.src_cols; src.depth = DEPTH; src.cn = CN; src.scale = a.scale;
-  Img wim;
-  wim.step = a.w_step; wim.rows = a.src_rows; wim.cols = a.src_cols; wim.depth = SSK_32F; wim.cn = 1; wim.scale = 1.f;
-
-  // tile + halo rectangle clipped to the image: its corners decide whether the whole tile maps into the
-  // safe interior of the frame (then every pixel is valid and the 5x5 erosion cannot remove any).
-  const int cx0 = max(bx0 - HALO, 0), cy0 = max(by0 - HALO, 0);
-  const int cx1 = min(bx0 + TW - 1 + HALO, a.cols - 1), cy1 = min(by0 + TH - 1 + HALO, a.rows - 1);
-
-  for (int j = 0; j < a.njobs; ++j) {
-    const FrameJob &job = a.jobs[j];
-    if (!job.ok) continue;                       // block-uniform
-    const MapCoef m = job.map;
-    src.data = job.frame;
-    wim.data = job.weights;
-
-    bool need_flags = true;
-    if (is_affine_like(m.type)) {
-      float u, v;
-      bool safe = true;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        map_xy(m, (float)((k & 1) ? cx1 : cx0), (float)((k & 2) ? cy1 : cy0), u, v);
-        safe = safe && u >= 3.f && v >= 3.f && u <= (float)(a.src_cols - 4) && v <= (float)(a.src_rows - 4);
-      }
-      need_flags = !safe;
-    }
-
-    if (need_flags) {
-      for (int k = threadIdx.x; k < FH * FW; k += blockDim.x) {
-        const int fy = k / FW, fx = k - fy * FW;
-        const int gx = bx0 - HALO + fx, gy = by0 - HALO + fy;
-        uint8_t ok = 1;                          // outside the image: erode border value 255
-        if (gx >= 0 && gy >= 0 && gx < a.cols && gy < a.rows) {
-          float u, v;
-          map_xy(m, (float)gx, (float)gy, u, v);
-          ok = valid255(INTERP, u, v, a.src_cols, a.src_rows, tab.cubic_itab) ? 1 : 0;
-        }
-        s_valid[fy][fx] = ok;
-      }
-      __syncthreads();
-    }
-
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (i >= npx) continue;
-      if (need_flags) {
-        bool mv = true;
-#pragma unroll
-        for (int dy = 0; dy < 5; ++dy)
-#pragma unroll
-          for (int dx = 0; dx < 5; ++dx) mv = mv && s_valid[wy + dy][lane * 4 + i + dx];
-        if (!mv) continue;
-      }
-      float u, v;
-      map_xy(m, (float)(x0 + i), (float)y, u, v);
-      float wnew = 1.f;
-      if (WEIGHTS) {
-        wnew = sample<SSK_32F, INTERP>(wim, 0, u, v, SSK_BORDER_CONSTANT, 0.f, tab);
-        if (!(wnew > 0.f)) continue;             // c_frame_accumulation.cc:114
-      }
-      const float Wn = W[i] + wnew;
-      const float factor = WEIGHTS ? __fdiv_rn(wnew, Wn) : __fdiv_rn(1.0f, Wn);
-      W[i] = Wn;
-#pragma unroll
-      for (int c = 0; c < CN; ++c) {
-        const float I = sample<DEPTH, INTERP>(src, c, u, v, a.border, a.bval[c], tab);
-        A[i][c] = fmaf(I - A[i][c], factor, A[i][c]);
-      }
-    }
-    if (need_flags) __syncthreads();
-  }
-
-  if (npx > 0) {
-    if (vec) {
-      *reinterpret_cast<float4 *>(a.wacc + pix0) = make_float4(W[0], W[1], W[2], W[3]);
-      float tmp[4 * CN];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int c = 0; c < CN; ++c) tmp[i * CN + c] = A[i][c];
-#pragma unroll
-      for (int k = 0; k < CN; ++k)
-        *reinterpret_cast<float4 *>(a.acc + pix0 * CN + 4 * k) = *reinterpret_cast<const float4 *>(tmp + 4 * k);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (i >= npx) continue;
-        a.wacc[pix0 + i] = W[i];
-#pragma unroll
-        for (int c = 0; c < CN; ++c) a.acc[(pix0 + i) * CN + c] = A[i][c];
-      }
-    }
-  }
-}
-
-template <int DEPTH, int CN>
-int launch_wa_dc(const WarpAccArgs &a, const Tables &tab, cudaStream_t s) {
-  dim3 grid(div_up(a.cols, TW), div_up(a.rows, TH)), block(256);
-#define SSK_WA(I, WGT) k_warp_acc<DEPTH, CN, I, WGT><<<grid, block, 0, s>>>(a, tab)
-  if (a.use_weights) {
-    if (a.interp == SSK_INTER_CUBIC) SSK_WA(SSK_INTER_CUBIC, true);
-    else if (a.interp == SSK_INTER_NEAREST) SSK_WA(SSK_INTER_NEAREST, true);
-    else SSK_WA(SSK_INTER_LINEAR, true);
-  } else {
-    if (a.interp == SSK_INTER_CUBIC) SSK_WA(SSK_INTER_CUBIC, false);
-    else if (a.interp == SSK_INTER_NEAREST) SSK_WA(SSK_INTER_NEAREST, false);
-    else SSK_WA(SSK_INTER_LINEAR, false);
-  }
-#undef SSK_WA
-  SSK_LAUNCH_CHECK();
-  return SSK_OK;
-}
-
-}  // namespace
-
-int launch_warp_accumulate(const WarpAccArgs &a, const Tables &tab, cudaStream_t s) {
-  SSK_REQUIRE(a.interp == SSK_INTER_NEAREST || a.interp == SSK_INTER_LINEAR || a.interp == SSK_INTER_CUBIC,
-              "warp_accumulate: interpolation must be NEAREST, LINEAR or CUBIC");
-  SSK_REQUIRE(a.border != SSK_BORDER_TRANSPARENT, "warp_accumulate: BORDER_TRANSPARENT is not meaningful here");
-  SSK_REQUIRE(a.cn == 1 || a.cn == 3, "warp_accumulate: 1 or 3 channels");
-  if (a.cn == 1) {
-    if (a.depth == SSK_32F) return launch_wa_dc<SSK_32F, 1>(a, tab, s);
-    if (a.depth == SSK_16U) return launch_wa_dc<SSK_16U, 1>(a, tab, s);
-    if (a.depth == SSK_8U) return launch_wa_dc<SSK_8U, 1>(a, tab, s);
-  } else {
-    if (a.depth == SSK_32F) return launch_wa_dc<SSK_32F, 3>(a, tab, s);
-    if (a.depth == SSK_16U) return launch_wa_dc<SSK_16U, 3>(a, tab, s);
-    if (a.depth == SSK_8U) return launch_wa_dc<SSK_8U, 3>(a, tab, s);
-  }
-  set_error("warp_accumulate: unsupported frame depth");
-  return SSK_ERR_INVALID;
-}
 
 // ------------------------------------------------------------------------------------------------
 // un-fused cv::remap (CV_32F, 1..4 channels)

@@ -27,6 +27,8 @@ struct WarpAccArgs {
   int border;             // SSK_BORDER_* for the frame
   float bval[4];
   int use_weights;        // 1: weighted_average (w = remap(weights, interp, CONSTANT 0) * mask)
+  int stage_aligned;      // all frame / weight-map base pointers are 16-byte aligned (enables cp.async staging)
+  int map_type;           // MAP_* common to all jobs of the batch (-1: mixed / unknown -> generic kernel)
   float *acc;             // running mean, rows x cols x cn (dense)
   float *wacc;            // running weight sum, rows x cols (dense)
 };
