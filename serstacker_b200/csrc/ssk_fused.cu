@@ -211,6 +211,14 @@ __device__ __noinline__ StagePlan plan_stage(const MapCoef &m, int bx0, int by0,
   }
   // safe interior: every pixel of the tile (and of its 2-px erosion halo) is valid and every tap is in bounds
   if (!(umin >= 3.f && vmin >= 3.f && umax <= (float)(a.src_cols - 4) && vmax <= (float)(a.src_rows - 4))) return p;
+  // footprint of the tile proper (the halo only served the safety test)
+  umin = vmin = 3.4e38f; umax = vmax = -3.4e38f;
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    float u, v;
+    map_xy(m, (float)((k & 1) ? bx0 + TW - 1 : bx0), (float)((k & 2) ? by0 + TH - 1 : by0), u, v);
+    umin = fminf(umin, u); umax = fmaxf(umax, u); vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+  }
   const int x_lo = (int)floorf(umin) - 1, x_hi = (int)floorf(umax) + 3;
   const int y_lo = (int)floorf(vmin) - 1, y_hi = (int)floorf(vmax) + 3;
   p.sx0 = x_lo & ~(align - 1);
@@ -360,8 +368,110 @@ __device__ __forceinline__ void roll_pixel_s(RollS<INTERP> &R, const ColMap<MT> 
   *s_acc_px = upd ? fmaf(I - A, factor, A) : A;
 }
 
+// cv::borderInterpolate for the modes whose mapped index stays near the border (a single reflection suffices for
+// the few pixels of overhang a tile can have); -1: BORDER_CONSTANT (use the border value)
+__device__ __forceinline__ int bmap(int p, int n, int border) {
+  if ((unsigned)p < (unsigned)n) return p;
+  if (border == SSK_BORDER_REPLICATE) return p < 0 ? 0 : n - 1;
+  if (border == SSK_BORDER_REFLECT101) return p < 0 ? -p : 2 * (n - 1) - p;
+  if (border == SSK_BORDER_REFLECT) return p < 0 ? -p - 1 : 2 * n - 1 - p;
+  return -1;
+}
+
+// One output pixel of a border-ring tile from the staged (clipped) footprint: all taps are fetched from shared memory
+// through cv::borderInterpolate, the weight taps with BORDER_CONSTANT 0; `ok` is the eroded validity mask.
 template <int DEPTH, int INTERP, bool WEIGHTS, int MT>
-__global__ void __launch_bounds__(TW * SWARPS) k_fused_staged(const __grid_constant__ WarpAccArgs a, const __grid_constant__ Tables tab, int tx_first, int ty_first) {
+__device__ __forceinline__ void ring_pixel_s(const ColMap<MT> &cm, float y, const unsigned char *s_f, const float *s_g,
+                                             const WarpAccArgs &a, const StagePlan &pl, const float4 *s_cubic, bool ok,
+                                             float *s_acc_px, float *s_w_px) {
+  typedef StageGeom<DEPTH> G;
+  constexpr int N = Taps<INTERP>::N, OFF = Taps<INTERP>::OFF;
+  float u, v;
+  cm(y, u, v);
+  int ix, iy, fx = 0, fy = 0;
+  if (INTERP == SSK_INTER_NEAREST) { ix = __float2int_rn(u); iy = __float2int_rn(v); }
+  else { quant32(u, ix, fx); quant32(v, iy, fy); }
+  int xm[N], ym[N];
+  bool xin[N], yin[N];
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    xm[q] = bmap(ix + OFF + q, a.src_cols, a.border); xin[q] = (unsigned)(ix + OFF + q) < (unsigned)a.src_cols;
+    ym[q] = bmap(iy + OFF + q, a.src_rows, a.border); yin[q] = (unsigned)(iy + OFF + q) < (unsigned)a.src_rows;
+  }
+  float F[N][N], Wt[N][N];
+#pragma unroll
+  for (int r = 0; r < N; ++r)
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+      F[r][q] = (xm[q] >= 0 && ym[r] >= 0) ? lds_px<DEPTH>(s_f + (ym[r] - pl.sy0) * G::ROWB + (xm[q] - pl.sx0) * G::ES, a.scale) : a.bval[0];
+      if (WEIGHTS) Wt[r][q] = (xin[q] && yin[r]) ? s_g[(iy + OFF + r - pl.sy0) * WWD + (ix + OFF + q - pl.sxw)] : 0.f;
+    }
+  float I, wk = 1.f;
+  if (INTERP == SSK_INTER_CUBIC) {
+    // cv::remap's order on the ring (16 products, row sums, then the sum of rows), as in sample_cubic
+    const float4 cx4 = s_cubic[fx], cy4 = s_cubic[fy];
+    const float wx[4] = {cx4.x, cx4.y, cx4.z, cx4.w}, wy[4] = {cy4.x, cy4.y, cy4.z, cy4.w};
+    I = 0.f; wk = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float rowf = 0.f, roww = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float wgt = __fmul_rn(wy[r], wx[q]);
+        rowf = __fadd_rn(rowf, __fmul_rn(F[r % N][q % N], wgt));
+        if (WEIGHTS) roww = __fadd_rn(roww, __fmul_rn(Wt[r % N][q % N], wgt));
+      }
+      I = __fadd_rn(I, rowf);
+      if (WEIGHTS) wk = __fadd_rn(wk, roww);
+    }
+    if (!WEIGHTS) wk = 1.f;
+  } else if (INTERP == SSK_INTER_LINEAR) {
+    const float tx = (float)fx * 0.03125f, ty = (float)fy * 0.03125f;
+    const float w00 = __fmul_rn(1.0f - ty, 1.0f - tx), w01 = __fmul_rn(1.0f - ty, tx), w10 = __fmul_rn(ty, 1.0f - tx), w11 = __fmul_rn(ty, tx);
+    I = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(F[0][0], w00), __fmul_rn(F[0][1 % N], w01)), __fmul_rn(F[1 % N][0], w10)), __fmul_rn(F[1 % N][1 % N], w11));
+    if (WEIGHTS) wk = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(Wt[0][0], w00), __fmul_rn(Wt[0][1 % N], w01)), __fmul_rn(Wt[1 % N][0], w10)), __fmul_rn(Wt[1 % N][1 % N], w11));
+  } else {
+    I = F[0][0];
+    if (WEIGHTS) wk = Wt[0][0];
+  }
+  const float W0 = *s_w_px, A = *s_acc_px;
+  const float Wn = W0 + wk;
+  const float factor = WEIGHTS ? __fdiv_rn(wk, Wn) : __fdiv_rn(1.0f, Wn);
+  const bool upd = ok && (!WEIGHTS || wk > 0.f);
+  *s_w_px = upd ? Wn : W0;
+  *s_acc_px = upd ? fmaf(I - A, factor, A) : A;
+}
+
+// Staging plan of a border-ring tile: the footprint is clipped to the frame; reflected / replicated taps then fall
+// inside the clipped region.  Not staged (generic path) for BORDER_WRAP, projective maps, oversize footprints.
+__device__ __noinline__ StagePlan plan_stage_ring(const MapCoef &m, int bx0, int by0, const WarpAccArgs &a, int align, int wd) {
+  StagePlan p; p.staged = 0; p.sx0 = p.sy0 = p.sxw = 0;
+  if (!a.stage_aligned || !is_affine_like(m.type) || a.border == SSK_BORDER_WRAP) return p;
+  const int cx1 = min(bx0 + TW - 1, a.cols - 1), cy1 = min(by0 + TH - 1, a.rows - 1);
+  float umin = 3.4e38f, umax = -3.4e38f, vmin = 3.4e38f, vmax = -3.4e38f;
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    float u, v;
+    map_xy(m, (float)((k & 1) ? cx1 : bx0), (float)((k & 2) ? cy1 : by0), u, v);
+    umin = fminf(umin, u); umax = fmaxf(umax, u); vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+  }
+  if (!(umax - umin < 64.f && vmax - vmin < 64.f)) return p;
+  int x_lo = (int)floorf(umin) - 1, x_hi = (int)floorf(umax) + 3;
+  int y_lo = (int)floorf(vmin) - 1, y_hi = (int)floorf(vmax) + 3;
+  // overhang beyond the frame must be small enough for its reflection to lie inside the clipped footprint
+  const int ovx = max(max(-x_lo, x_hi - (a.src_cols - 1)), 0), ovy = max(max(-y_lo, y_hi - (a.src_rows - 1)), 0);
+  x_lo = max(x_lo, 0); y_lo = max(y_lo, 0); x_hi = min(x_hi, a.src_cols - 1); y_hi = min(y_hi, a.src_rows - 1);
+  if (x_hi - x_lo < ovx + 1 || y_hi - y_lo < ovy + 1) return p;
+  p.sx0 = x_lo & ~(align - 1);
+  p.sy0 = y_lo;
+  p.sxw = x_lo & ~3;
+  p.staged = (x_hi - p.sx0 < wd) && (y_hi - p.sy0 < GSH) && (x_hi - p.sxw < WWD);
+  return p;
+}
+
+template <int DEPTH, int INTERP, bool WEIGHTS, int MT, bool RING>
+__global__ void __launch_bounds__(TW * SWARPS) k_fused_staged(const __grid_constant__ WarpAccArgs a, const __grid_constant__ Tables tab,
+                                                               const TileList tl) {
   typedef StageGeom<DEPTH> G;
   constexpr int N = Taps<INTERP>::N;
   __shared__ float s_acc[TH][TW];                  // running mean of the tile (on chip for the whole batch)
@@ -369,23 +479,29 @@ __global__ void __launch_bounds__(TW * SWARPS) k_fused_staged(const __grid_const
   __shared__ float4 s_cubic[kInterTab];
   __shared__ __align__(16) unsigned char s_f[2][GSH * G::ROWB];
   __shared__ __align__(16) float s_g[2][GSH * WWD];
+  __shared__ uint8_t s_flag[RING ? TH + 4 : 1][RING ? TW + 8 : 1];   // pre-erosion validity of tile + 2-px halo
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int bx0 = (blockIdx.x + tx_first) * TW, by0 = (blockIdx.y + ty_first) * TH;
+  int tx, ty;
+  if (RING) tile_of_block(tl, blockIdx.x, tx, ty);
+  else { tx = blockIdx.x + 1; ty = blockIdx.y + 1; }
+  const int bx0 = tx * TW, by0 = ty * TH;
   const int x = bx0 + lane, y0 = by0 + warp * GR;
+  const int tw = min(TW, a.cols - bx0), th = min(TH, a.rows - by0);
+  const int nrow = lane < tw ? max(0, min(GR, th - warp * GR)) : 0;
   if (INTERP == SSK_INTER_CUBIC && threadIdx.x < kInterTab) s_cubic[threadIdx.x] = tab.cubic[threadIdx.x];
 
-  // interior tiles are always complete; 16-byte accesses when the accumulator pitch allows it
-  const bool vec = (a.cols & 3) == 0;
+  // accumulator tile -> shared memory; 16-byte accesses when the tile is complete and the pitch allows it
+  const bool vec = (a.cols & 3) == 0 && tw == TW;
   if (vec) {
-    for (int k = threadIdx.x; k < TH * (TW / 4); k += blockDim.x) {
+    for (int k = threadIdx.x; k < th * (TW / 4); k += blockDim.x) {
       const int r = k / (TW / 4), q = k - r * (TW / 4);
       reinterpret_cast<float4 *>(s_acc[r])[q] = *reinterpret_cast<const float4 *>(a.acc + (int64_t)(by0 + r) * a.cols + bx0 + 4 * q);
       reinterpret_cast<float4 *>(s_w[r])[q] = *reinterpret_cast<const float4 *>(a.wacc + (int64_t)(by0 + r) * a.cols + bx0 + 4 * q);
     }
   } else {
-    for (int k = threadIdx.x; k < TH * TW; k += blockDim.x) {
-      const int r = k / TW, q = k - r * TW;
+    for (int k = threadIdx.x; k < th * tw; k += blockDim.x) {
+      const int r = k / tw, q = k - r * tw;
       s_acc[r][q] = a.acc[(int64_t)(by0 + r) * a.cols + bx0 + q];
       s_w[r][q] = a.wacc[(int64_t)(by0 + r) * a.cols + bx0 + q];
     }
@@ -397,7 +513,7 @@ __global__ void __launch_bounds__(TW * SWARPS) k_fused_staged(const __grid_const
   int buf = 0;
   StagePlan plan = {0, 0, 0, 0};
   if (j < a.njobs) {
-    plan = plan_stage(a.jobs[j].map, bx0, by0, a, G::ALIGN, G::WD);
+    plan = RING ? plan_stage_ring(a.jobs[j].map, bx0, by0, a, G::ALIGN, G::WD) : plan_stage(a.jobs[j].map, bx0, by0, a, G::ALIGN, G::WD);
     if (WEIGHTS && !a.jobs[j].weights) plan.staged = 0;    // flat frame (no weight map): generic path
     if (plan.staged) issue_stage<DEPTH>(a.jobs[j], plan, a, WEIGHTS, s_f[0], s_g[0]);
   }
@@ -410,11 +526,27 @@ __global__ void __launch_bounds__(TW * SWARPS) k_fused_staged(const __grid_const
     while (jn < a.njobs && !a.jobs[jn].ok) ++jn;
     StagePlan plan_n = {0, 0, 0, 0};
     if (jn < a.njobs) {
-      plan_n = plan_stage(a.jobs[jn].map, bx0, by0, a, G::ALIGN, G::WD);
+      plan_n = RING ? plan_stage_ring(a.jobs[jn].map, bx0, by0, a, G::ALIGN, G::WD) : plan_stage(a.jobs[jn].map, bx0, by0, a, G::ALIGN, G::WD);
       if (WEIGHTS && !a.jobs[jn].weights) plan_n.staged = 0;
       if (plan_n.staged) issue_stage<DEPTH>(a.jobs[jn], plan_n, a, WEIGHTS, s_f[buf ^ 1], s_g[buf ^ 1]);
     }
     cp_async_commit();
+    if (RING && plan.staged) {
+      // pre-erosion validity of the tile and its 2-px halo (outside the image: erode border value 255)
+      const MapCoef m = a.jobs[j].map;
+#pragma unroll 1
+      for (int k = threadIdx.x; k < (TH + 4) * (TW + 4); k += blockDim.x) {
+        const int fy = k / (TW + 4), fxx = k - fy * (TW + 4);
+        const int gx = bx0 - 2 + fxx, gy = by0 - 2 + fy;
+        uint8_t okf = 1;
+        if (gx >= 0 && gy >= 0 && gx < a.cols && gy < a.rows) {
+          float u, v;
+          map_xy(m, (float)gx, (float)gy, u, v);
+          okf = valid255(INTERP, u, v, a.src_cols, a.src_rows, tab.cubic_itab) ? 1 : 0;
+        }
+        s_flag[fy][fxx] = okf;
+      }
+    }
     cp_async_wait<1>();            // frame j's group has landed (frame j+1's may still be in flight)
     __syncthreads();
 
@@ -424,59 +556,79 @@ __global__ void __launch_bounds__(TW * SWARPS) k_fused_staged(const __grid_const
       const ColMap<MT> cm(m, (float)x);
       const unsigned char *sf = s_f[buf];
       const float *sg = s_g[buf];
-      RollS<INTERP> R;
-      R.ix = INT_MIN; R.iy = INT_MIN; R.pf = sf; R.pw = sg;
+      if (RING) {
 #pragma unroll 1
-      for (int k = 0; k < GR; k += N) {
-        roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 0>(R, cm, (float)(y0 + k), sf, sg, a.scale, plan, s_cubic, s_acc0 + k * TW, s_w0 + k * TW);
-        if (N > 1) roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 1 % N>(R, cm, (float)(y0 + k + 1), sf, sg, a.scale, plan, s_cubic, s_acc0 + (k + 1) * TW, s_w0 + (k + 1) * TW);
-        if (N > 2) roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 2 % N>(R, cm, (float)(y0 + k + 2), sf, sg, a.scale, plan, s_cubic, s_acc0 + (k + 2) * TW, s_w0 + (k + 2) * TW);
-        if (N > 3) roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 3 % N>(R, cm, (float)(y0 + k + 3), sf, sg, a.scale, plan, s_cubic, s_acc0 + (k + 3) * TW, s_w0 + (k + 3) * TW);
+        for (int k = 0; k < nrow; ++k) {
+          bool ok = true;
+#pragma unroll
+          for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx) ok = ok && s_flag[warp * GR + k + dy][lane + dx];
+          ring_pixel_s<DEPTH, INTERP, WEIGHTS, MT>(cm, (float)(y0 + k), sf, sg, a, plan, s_cubic, ok, s_acc0 + k * TW, s_w0 + k * TW);
+        }
+      } else {
+        RollS<INTERP> R;
+        R.ix = INT_MIN; R.iy = INT_MIN; R.pf = sf; R.pw = sg;
+#pragma unroll 1
+        for (int k = 0; k < GR; k += N) {
+          roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 0>(R, cm, (float)(y0 + k), sf, sg, a.scale, plan, s_cubic, s_acc0 + k * TW, s_w0 + k * TW);
+          if (N > 1) roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 1 % N>(R, cm, (float)(y0 + k + 1), sf, sg, a.scale, plan, s_cubic, s_acc0 + (k + 1) * TW, s_w0 + (k + 1) * TW);
+          if (N > 2) roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 2 % N>(R, cm, (float)(y0 + k + 2), sf, sg, a.scale, plan, s_cubic, s_acc0 + (k + 2) * TW, s_w0 + (k + 2) * TW);
+          if (N > 3) roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 3 % N>(R, cm, (float)(y0 + k + 3), sf, sg, a.scale, plan, s_cubic, s_acc0 + (k + 3) * TW, s_w0 + (k + 3) * TW);
+        }
       }
     } else {
-      // this (tile, frame) pair cannot be staged (large displacement, flat frame): generic per-pixel path
+      // this (tile, frame) pair cannot be staged (large displacement, flat frame, BORDER_WRAP): generic per-pixel path
 #pragma unroll 1
-      for (int k = 0; k < GR; ++k) generic_pixel(a, tab, a.jobs[j], x, y0 + k, s_acc0 + k * TW, s_w0 + k * TW);
+      for (int k = 0; k < nrow; ++k) generic_pixel(a, tab, a.jobs[j], x, y0 + k, s_acc0 + k * TW, s_w0 + k * TW);
     }
-    __syncthreads();               // everyone is done with buffer `buf` before it is refilled
+    __syncthreads();               // everyone is done with buffer `buf` (and the flags) before they are refilled
     j = jn; plan = plan_n; buf ^= 1;
   }
   cp_async_wait<0>();
   __syncthreads();
 
   if (vec) {
-    for (int k = threadIdx.x; k < TH * (TW / 4); k += blockDim.x) {
+    for (int k = threadIdx.x; k < th * (TW / 4); k += blockDim.x) {
       const int r = k / (TW / 4), q = k - r * (TW / 4);
       *reinterpret_cast<float4 *>(a.acc + (int64_t)(by0 + r) * a.cols + bx0 + 4 * q) = reinterpret_cast<const float4 *>(s_acc[r])[q];
       *reinterpret_cast<float4 *>(a.wacc + (int64_t)(by0 + r) * a.cols + bx0 + 4 * q) = reinterpret_cast<const float4 *>(s_w[r])[q];
     }
   } else {
-    for (int k = threadIdx.x; k < TH * TW; k += blockDim.x) {
-      const int r = k / TW, q = k - r * TW;
+    for (int k = threadIdx.x; k < th * tw; k += blockDim.x) {
+      const int r = k / tw, q = k - r * tw;
       a.acc[(int64_t)(by0 + r) * a.cols + bx0 + q] = s_acc[r][q];
       a.wacc[(int64_t)(by0 + r) * a.cols + bx0 + q] = s_w[r][q];
     }
   }
 }
 
-template <int DEPTH, int INTERP, bool WEIGHTS>
-void launch_staged_mt(const WarpAccArgs &a, const Tables &tab, dim3 grid, cudaStream_t s) {
+template <int DEPTH, int INTERP, bool WEIGHTS, int MT>
+void launch_staged_ring(const WarpAccArgs &a, const Tables &tab, const TileList &tl, int nring, cudaStream_t s) {
   const dim3 block(TW * SWARPS);
-  if (a.map_type == MAP_AFFINE) k_fused_staged<DEPTH, INTERP, WEIGHTS, MAP_AFFINE><<<grid, block, 0, s>>>(a, tab, 1, 1);
-  else if (a.map_type == MAP_TRANSLATION) k_fused_staged<DEPTH, INTERP, WEIGHTS, MAP_TRANSLATION><<<grid, block, 0, s>>>(a, tab, 1, 1);
-  else k_fused_staged<DEPTH, INTERP, WEIGHTS, MAP_EUCLIDEAN><<<grid, block, 0, s>>>(a, tab, 1, 1);
+  // border ring first (fewer, heavier CTAs), then the interior tiles
+  k_fused_staged<DEPTH, INTERP, WEIGHTS, MT, true><<<nring, block, 0, s>>>(a, tab, tl);
+  count_launch();
+  k_fused_staged<DEPTH, INTERP, WEIGHTS, MT, false><<<dim3(tl.ntx - 2, tl.nty - 2), block, 0, s>>>(a, tab, tl);
+}
+
+template <int DEPTH, int INTERP, bool WEIGHTS>
+void launch_staged_mt(const WarpAccArgs &a, const Tables &tab, const TileList &tl, int nring, cudaStream_t s) {
+  if (a.map_type == MAP_AFFINE) launch_staged_ring<DEPTH, INTERP, WEIGHTS, MAP_AFFINE>(a, tab, tl, nring, s);
+  else if (a.map_type == MAP_TRANSLATION) launch_staged_ring<DEPTH, INTERP, WEIGHTS, MAP_TRANSLATION>(a, tab, tl, nring, s);
+  else launch_staged_ring<DEPTH, INTERP, WEIGHTS, MAP_EUCLIDEAN>(a, tab, tl, nring, s);
 }
 
 template <int DEPTH>
-void launch_staged(const WarpAccArgs &a, const Tables &tab, dim3 grid, cudaStream_t s) {
+void launch_staged(const WarpAccArgs &a, const Tables &tab, const TileList &tl, int nring, cudaStream_t s) {
   if (a.use_weights) {
-    if (a.interp == SSK_INTER_CUBIC) launch_staged_mt<DEPTH, SSK_INTER_CUBIC, true>(a, tab, grid, s);
-    else if (a.interp == SSK_INTER_NEAREST) launch_staged_mt<DEPTH, SSK_INTER_NEAREST, true>(a, tab, grid, s);
-    else launch_staged_mt<DEPTH, SSK_INTER_LINEAR, true>(a, tab, grid, s);
+    if (a.interp == SSK_INTER_CUBIC) launch_staged_mt<DEPTH, SSK_INTER_CUBIC, true>(a, tab, tl, nring, s);
+    else if (a.interp == SSK_INTER_NEAREST) launch_staged_mt<DEPTH, SSK_INTER_NEAREST, true>(a, tab, tl, nring, s);
+    else launch_staged_mt<DEPTH, SSK_INTER_LINEAR, true>(a, tab, tl, nring, s);
   } else {
-    if (a.interp == SSK_INTER_CUBIC) launch_staged_mt<DEPTH, SSK_INTER_CUBIC, false>(a, tab, grid, s);
-    else if (a.interp == SSK_INTER_NEAREST) launch_staged_mt<DEPTH, SSK_INTER_NEAREST, false>(a, tab, grid, s);
-    else launch_staged_mt<DEPTH, SSK_INTER_LINEAR, false>(a, tab, grid, s);
+    if (a.interp == SSK_INTER_CUBIC) launch_staged_mt<DEPTH, SSK_INTER_CUBIC, false>(a, tab, tl, nring, s);
+    else if (a.interp == SSK_INTER_NEAREST) launch_staged_mt<DEPTH, SSK_INTER_NEAREST, false>(a, tab, tl, nring, s);
+    else launch_staged_mt<DEPTH, SSK_INTER_LINEAR, false>(a, tab, tl, nring, s);
   }
 }
 
@@ -495,15 +647,15 @@ int launch_warp_accumulate(const WarpAccArgs &a_in, const Tables &tab, cudaStrea
                       (a.map_type == MAP_AFFINE || a.map_type == MAP_TRANSLATION || a.map_type == MAP_EUCLIDEAN);
   TileList tl;
   tl.ntx = ntx; tl.nty = nty; tl.ring = staged ? 1 : 0;
-  const int ntiles = staged ? 2 * ntx + 2 * (nty - 2) : ntx * nty;
-  // border ring (or everything, when the staged kernel does not apply) through the generic per-pixel kernel
-  k_fused_generic<<<ntiles * 4, 256, 0, s>>>(a, tab, tl);
-  SSK_LAUNCH_CHECK();
   if (staged) {
-    const dim3 grid(ntx - 2, nty - 2);
-    if (a.depth == SSK_32F) launch_staged<SSK_32F>(a, tab, grid, s);
-    else if (a.depth == SSK_16U) launch_staged<SSK_16U>(a, tab, grid, s);
-    else launch_staged<SSK_8U>(a, tab, grid, s);
+    const int nring = 2 * ntx + 2 * (nty - 2);
+    if (a.depth == SSK_32F) launch_staged<SSK_32F>(a, tab, tl, nring, s);
+    else if (a.depth == SSK_16U) launch_staged<SSK_16U>(a, tab, tl, nring, s);
+    else launch_staged<SSK_8U>(a, tab, tl, nring, s);
+    SSK_LAUNCH_CHECK();
+  } else {
+    // multi-channel frames, projective maps, tiny images: one thread per pixel
+    k_fused_generic<<<ntx * nty * 4, 256, 0, s>>>(a, tab, tl);
     SSK_LAUNCH_CHECK();
   }
   return SSK_OK;
