@@ -606,10 +606,19 @@ __global__ void __launch_bounds__(TW * SWARPS) k_fused_staged(const __grid_const
 template <int DEPTH, int INTERP, bool WEIGHTS, int MT>
 void launch_staged_ring(const WarpAccArgs &a, const Tables &tab, const TileList &tl, int nring, cudaStream_t s) {
   const dim3 block(TW * SWARPS);
-  // border ring first (fewer, heavier CTAs), then the interior tiles
-  k_fused_staged<DEPTH, INTERP, WEIGHTS, MT, true><<<nring, block, 0, s>>>(a, tab, tl);
+  // The border ring (few, heavier CTAs) runs on a side stream so that it overlaps the interior tiles; the two
+  // kernels write disjoint accumulator tiles.
+  cudaStream_t ring_stream = s;
+  if (a.side_stream) {
+    ring_stream = static_cast<cudaStream_t>(a.side_stream);
+    cudaEventRecord(static_cast<cudaEvent_t>(a.ev_fork), s);
+    cudaStreamWaitEvent(ring_stream, static_cast<cudaEvent_t>(a.ev_fork), 0);
+  }
+  k_fused_staged<DEPTH, INTERP, WEIGHTS, MT, true><<<nring, block, 0, ring_stream>>>(a, tab, tl);
   count_launch();
+  if (a.side_stream) cudaEventRecord(static_cast<cudaEvent_t>(a.ev_join), ring_stream);
   k_fused_staged<DEPTH, INTERP, WEIGHTS, MT, false><<<dim3(tl.ntx - 2, tl.nty - 2), block, 0, s>>>(a, tab, tl);
+  if (a.side_stream) cudaStreamWaitEvent(s, static_cast<cudaEvent_t>(a.ev_join), 0);
 }
 
 template <int DEPTH, int INTERP, bool WEIGHTS>

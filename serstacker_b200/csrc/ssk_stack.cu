@@ -60,10 +60,15 @@ struct ssk_stack {
   int w1_rows = 0, w1_cols = 0, w1_nb = 0;
   bool frames_aligned = true;            // every frame pointer of the current chunk is 16-byte aligned
   cudaEvent_t ev[5] = {};
+  cudaStream_t side = nullptr;           // border-ring kernel of the fused warp+accumulate stage
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   DevBuf ref_staging;
   ~ssk_stack() {
     for (auto &e : ring_ev) if (e) cudaEventDestroy(e);
     for (auto &e : ev) if (e) cudaEventDestroy(e);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (side) cudaStreamDestroy(side);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -88,6 +93,11 @@ static int stack_alloc_slots(ssk_stack *h) {
     if (!h->ring_ev[r]) SSK_CUDA(cudaEventCreateWithFlags(&h->ring_ev[r], cudaEventDisableTiming));
   }
   for (auto &e : h->ev) if (!e) SSK_CUDA(cudaEventCreate(&e));
+  if (!h->side) {
+    SSK_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    SSK_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    SSK_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  }
   if (h->o.accumulation_method == SSK_STACK_WEIGHTED_AVERAGE && h->o.sm_kradius > 0) {
     // pdownscale chain sizes (c_local_variance_sharpness_measure.cc:28-52)
     int r = h->rows, c = h->cols;
@@ -234,7 +244,18 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n) {
       Img cur = geom;
       const void *const *src_ptrs = d_frame_ptrs;
       float *const *dst_ptrs = h->d_half_ptrs.as<float *>();
-      for (int l = 0; l < h->o.sm_dscale; ++l) {
+      int l0 = 0;
+      if (h->o.enable_registration && h->reg_h.r.ecc_rows != h->rows) {
+        // the first cv::pyrDown of the gray frame is exactly the ECC image scaleImage() just produced
+        // (c_frame_registration.cc:236-237 vs c_local_variance_sharpness_measure.cc:36): reuse it
+        const int nr = (cur.rows + 1) / 2, nc = (cur.cols + 1) / 2;
+        float *const *e0 = h->reg_h.r.ecch.level0_scratch_ptrs();
+        cur.step = (int64_t)nc * 4; cur.rows = nr; cur.cols = nc; cur.depth = SSK_32F; cur.cn = 1; cur.scale = 1.f;
+        Mptrs = e0;
+        src_ptrs = reinterpret_cast<const void *const *>(e0);
+        l0 = (std::min(nr, nc) < 4) ? h->o.sm_dscale : 1;
+      }
+      for (int l = l0; l < h->o.sm_dscale; ++l) {
         const int nr = (cur.rows + 1) / 2, nc = (cur.cols + 1) / 2;
         PyrDownArgs pd = {};
         pd.src = cur; pd.src_ptrs = src_ptrs; pd.dst_ptrs = dst_ptrs; pd.dst_rows = nr; pd.dst_cols = nc; pd.batch = n; pd.post_scale = 1.f;
@@ -280,6 +301,7 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n) {
   for (int i = 0; i < 4; ++i) a.bval[i] = (float)ro.border_value[i];
   a.use_weights = weighted ? 1 : 0;
   a.stage_aligned = h->frames_aligned ? 1 : 0;
+  a.side_stream = h->side; a.ev_fork = h->ev_fork; a.ev_join = h->ev_join;
   {
     ssk_transform t0;
     make_transform(&t0, h->o.enable_registration ? ro.motion_type : SSK_MOTION_TRANSLATION);

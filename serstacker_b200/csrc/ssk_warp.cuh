@@ -29,6 +29,7 @@ struct WarpAccArgs {
   int use_weights;        // 1: weighted_average (w = remap(weights, interp, CONSTANT 0) * mask)
   int stage_aligned;      // all frame / weight-map base pointers are 16-byte aligned (enables cp.async staging)
   int map_type;           // MAP_* common to all jobs of the batch (-1: mixed / unknown -> generic kernel)
+  void *side_stream, *ev_fork, *ev_join;   // host only: optional side stream (+2 events) for the border-ring kernel
   float *acc;             // running mean, rows x cols x cn (dense)
   float *wacc;            // running weight sum, rows x cols (dense)
 };
