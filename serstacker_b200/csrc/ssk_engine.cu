@@ -1,6 +1,7 @@
 // Engine classes: device-resident c_ecch / c_frame_registration / accumulator state and batching.
 #include "ssk_engine.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace ssk {
@@ -86,6 +87,10 @@ int Ecch::init(const ssk_ecch_options &o, cudaStream_t s) {
   opts = o;
   stream = s;
   have_reference = false;
+  if (const char *e = getenv("SSK_ECC_CLUSTER")) {   // tuning knob: CTAs per frame (thread-block cluster size)
+    const int c = atoi(e);
+    if (c == 1 || c == 2 || c == 4 || c == 8) cluster_size = c;
+  }
   return SSK_OK;
 }
 

@@ -51,7 +51,7 @@ class Ecch {
  public:
   ssk_ecch_options opts;
   cudaStream_t stream = nullptr;
-  int cluster_size = 8;
+  int cluster_size = 4;   // CTAs per frame; 4 measured best on config #2 (profiles/r01_summary.md)
 
   int nlevels = 0;
   int lw[kMaxLevels], lh[kMaxLevels];
