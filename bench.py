@@ -190,7 +190,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from serstacker_b200 import api, capi
+    from serstacker_b200 import api, capi, multi
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -223,24 +223,7 @@ def main():
 
     def combine():
         """multi-GPU epilogue: (sum w*I, sum w) reduced to rank 0 over NCCL, then back to the running mean."""
-        if world == 1:
-            return
-        acc_h = capi.lib.ssk_stack_accumulator(pipe._h)
-        pa, pw, ba, bw = C.c_void_p(), C.c_void_p(), C.c_int64(), C.c_int64()
-        capi.check(capi.lib.ssk_acc_device_state(acc_h, C.byref(pa), C.byref(pw), C.byref(ba), C.byref(bw)))
-        capi.check(capi.lib.ssk_acc_to_sum_form(acc_h))
-
-        class _View:
-            def __init__(self, ptr, nbytes):
-                self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False), "version": 3}
-        ta = torch.as_tensor(_View(pa.value, ba.value), device=dev)
-        tw = torch.as_tensor(_View(pw.value, bw.value), device=dev)
-        dist.reduce(ta, 0)
-        dist.reduce(tw, 0)
-        nfr = torch.tensor([pipe.accumulated_frames()], device=dev)
-        dist.reduce(nfr, 0)
-        torch.cuda.synchronize()
-        capi.check(capi.lib.ssk_acc_from_sum_form(acc_h, int(nfr.item())))
+        multi.combine_pipeline(pipe, dev, dst=0)
 
     # ---------------- device-resident throughput --------------------------------------------------------
     for s in range(args.warmup):
