@@ -430,6 +430,50 @@ __device__ void set_pass_params(Shared &S, const ssk_transform &q) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// per-pixel plumbing of the passes
+// ------------------------------------------------------------------------------------------------
+// Strided row-major walk over a level (pixel i = start, start + stride, ...) that keeps (x, y) incrementally:
+// no per-pixel integer division.
+struct Walk {
+  int i, x, y, dx, dy, stride, cols;
+  __device__ __forceinline__ Walk(int start, int stride_, int cols_) : stride(stride_), cols(cols_) {
+    i = start; y = start / cols_; x = start - y * cols_;
+    dy = stride_ / cols_; dx = stride_ - dy * cols_;
+  }
+  __device__ __forceinline__ void next() {
+    i += stride; x += dx; y += dy;
+    if (x >= cols) { x -= cols; ++y; }
+  }
+};
+
+__device__ __forceinline__ int cvround32(float v) { return __float2int_rn(__fmul_rn(v, 32.0f)); }
+
+// valid255_linear on pre-quantised coordinates (sx, sy = cvRound(32 u), cvRound(32 v))
+__device__ __forceinline__ bool lin_valid(int sx, int sy, int cols, int rows) {
+  const int ix = sx >> 5, iy = sy >> 5;
+  return (unsigned)ix < (unsigned)cols && (unsigned)iy < (unsigned)rows &&
+         ((sx & 31) == 0 || ix + 1 < cols) && ((sy & 31) == 0 || iy + 1 < rows);
+}
+
+// cv::remap INTER_LINEAR of a dense CV_32FC1 level with BORDER_REPLICATE: clamped tap coordinates are the
+// replicate border, the arithmetic is sample_linear's (bit-exact against cv2).  Unconditionally safe to call
+// (every address is in bounds), which lets the passes run branch-free.  For pixels that passed lin_valid the
+// out-of-range taps carry zero weight, so the result also equals the BORDER_CONSTANT sample.
+__device__ __forceinline__ float lin_sample(const float *__restrict__ p, int cols, int rows, int sx, int sy) {
+  const int ix = sx >> 5, iy = sy >> 5;
+  const float tx = (float)(sx & 31) * 0.03125f, ty = (float)(sy & 31) * 0.03125f;
+  const float wx0 = 1.0f - tx, wy0 = 1.0f - ty;
+  const int x0 = min(max(ix, 0), cols - 1), x1 = min(max(ix + 1, 0), cols - 1);
+  const int y0 = min(max(iy, 0), rows - 1), y1 = min(max(iy + 1, 0), rows - 1);
+  const float *r0 = p + y0 * cols, *r1 = p + y1 * cols;
+  const float s00 = __ldg(r0 + x0), s01 = __ldg(r0 + x1), s10 = __ldg(r1 + x0), s11 = __ldg(r1 + x1);
+  float out = __fadd_rn(__fmul_rn(s00, __fmul_rn(wy0, wx0)), __fmul_rn(s01, __fmul_rn(wy0, tx)));
+  out = __fadd_rn(out, __fmul_rn(s10, __fmul_rn(ty, wx0)));
+  out = __fadd_rn(out, __fmul_rn(s11, __fmul_rn(ty, tx)));
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------------
 // pass of the inverse-compositional solvers: sums = [ |rhs|^2, #valid, J_i . rhs ]
 //   lm_masks = true : c_ecclm_inverse_compositional::compute_rhs (ecc2.cc:1894-1917): mask by INTER_NEAREST remap of the
 //                     inverted current mask with constant border 255 -> a pixel is bad iff its rounded source
@@ -442,35 +486,49 @@ __device__ void pass_ic(Ctx &c, int lvl, bool lm_masks) {
   constexpr int NS = 2 + M;
   Shared &S = *c.S;
   const EccLevel &L = c.cfg->lv[lvl];
-  const Img cur = level_image(c, lvl);
+  const float *__restrict__ cur = c.frame->pyr + L.cur_off;
+  const float *__restrict__ ref = L.ref, *__restrict__ gxp = L.gx, *__restrict__ gyp = L.gy;
+  const uint8_t *__restrict__ rmask = L.refmask;
+  const int cols = L.cols, rows = L.rows;
   const MapCoef m = S.map;
   const JCoef jc = S.jc;
   double acc[NS];   // Mat::dot / norm accumulate in double
 #pragma unroll
   for (int k = 0; k < NS; ++k) acc[k] = 0.0;
-  const int n = L.cols * L.rows;
-  for (int i = c.rank * NT + c.tid; i < n; i += c.csize * NT) {
-    const int y = i / L.cols, x = i - y * L.cols;
+  int nvalid = 0;
+  const int n = cols * rows;
+  // Branch-free body (invalid pixels contribute an exact 0.0), so that two pixels per thread are in flight.
+  Walk w(c.rank * NT + c.tid, c.csize * NT, cols);
+#pragma unroll 2
+  for (; w.i < n; w.next()) {
+    const float x = (float)w.x, y = (float)w.y;
     float u, v;
-    map_xy(m, (float)x, (float)y, u, v);
+    map_xy(m, x, y, u, v);
+    const int sx = cvround32(u), sy = cvround32(v);
     bool ok;
-    if (lm_masks) {
-      const int ix = __float2int_rn(u), iy = __float2int_rn(v);
-      ok = (unsigned)ix < (unsigned)L.cols && (unsigned)iy < (unsigned)L.rows;
-    } else {
-      ok = valid255_linear(u, v, L.cols, L.rows);
-    }
-    if (ok && L.refmask) ok = L.refmask[i] != 0;
-    if (!ok) continue;
-    const float g = sample_linear<SSK_32F>(cur, 0, u, v, SSK_BORDER_REPLICATE, 0.f);
-    const float rhs = g - __ldg(L.ref + i);
+    if (lm_masks) ok = (unsigned)__float2int_rn(u) < (unsigned)cols && (unsigned)__float2int_rn(v) < (unsigned)rows;
+    else ok = lin_valid(sx, sy, cols, rows);
+    if (rmask) ok = ok && rmask[w.i] != 0;
+    const float g = lin_sample(cur, cols, rows, sx, sy);
+    const float rhs = g - __ldg(ref + w.i);
     float J[M];
-    eval_J<TYPE>(jc, (float)x, (float)y, __ldg(L.gx + i), __ldg(L.gy + i), J);
-    acc[0] += (double)rhs * (double)rhs;
-    acc[1] += 1.0;
+    eval_J<TYPE>(jc, x, y, __ldg(gxp + w.i), __ldg(gyp + w.i), J);
+    if (TYPE == SSK_MOTION_HOMOGRAPHY) {   // J may be non-finite at a vanishing denominator: keep the branch
+      if (ok) {
+        acc[0] += (double)rhs * (double)rhs;
+        ++nvalid;
 #pragma unroll
-    for (int k = 0; k < M; ++k) acc[2 + k] += (double)J[k] * (double)rhs;
+        for (int k = 0; k < M; ++k) acc[2 + k] += (double)J[k] * (double)rhs;
+      }
+    } else {
+      const double r = ok ? (double)rhs : 0.0;
+      acc[0] += r * r;
+      nvalid += ok ? 1 : 0;
+#pragma unroll
+      for (int k = 0; k < M; ++k) acc[2 + k] += (double)J[k] * r;
+    }
   }
+  acc[1] = (double)nvalid;
   cluster_reduce<NS>(c, acc);
 }
 
@@ -486,10 +544,10 @@ __device__ void pass_hp(Ctx &c, int lvl) {
 #pragma unroll
   for (int k = 0; k < NS; ++k) acc[k] = 0.0;
   const int n = L.cols * L.rows;
-  for (int i = c.rank * NT + c.tid; i < n; i += c.csize * NT) {
-    const int y = i / L.cols, x = i - y * L.cols;
+  for (Walk w(c.rank * NT + c.tid, c.csize * NT, L.cols); w.i < n; w.next()) {
+    const int i = w.i;
     float J[M];
-    eval_J<TYPE>(jc, (float)x, (float)y, __ldg(L.gx + i), __ldg(L.gy + i), J);
+    eval_J<TYPE>(jc, (float)w.x, (float)w.y, __ldg(L.gx + i), __ldg(L.gy + i), J);
     int q = 0;
 #pragma unroll
     for (int a = 0; a < M; ++a)
@@ -519,7 +577,7 @@ __device__ void unpack_H(int M, const double *tri, float *H) {
 template <int DUMMY>
 __device__ __forceinline__ float fa_sample(const Img &cur, int interp, float u, float v) {
   if (interp == SSK_INTER_NEAREST) return sample_nearest<SSK_32F>(cur, 0, u, v, SSK_BORDER_REPLICATE, 0.f);
-  return sample_linear<SSK_32F>(cur, 0, u, v, SSK_BORDER_REPLICATE, 0.f);
+  return lin_sample(static_cast<const float *>(cur.data), cur.cols, cur.rows, cvround32(u), cvround32(v));
 }
 
 __device__ void pass_fa_stats(Ctx &c, int lvl) {
@@ -530,10 +588,10 @@ __device__ void pass_fa_stats(Ctx &c, int lvl) {
   const int interp = c.cfg->interp;
   double acc[5] = {0, 0, 0, 0, 0};
   const int n = L.cols * L.rows;
-  for (int i = c.rank * NT + c.tid; i < n; i += c.csize * NT) {
-    const int y = i / L.cols, x = i - y * L.cols;
+  for (Walk w(c.rank * NT + c.tid, c.csize * NT, L.cols); w.i < n; w.next()) {
+    const int i = w.i;
     float u, v;
-    map_xy(m, (float)x, (float)y, u, v);
+    map_xy(m, (float)w.x, (float)w.y, u, v);
     bool ok = valid255_linear(u, v, L.cols, L.rows);
     if (ok && L.refmask) ok = L.refmask[i] != 0;
     if (!ok) continue;
@@ -625,21 +683,29 @@ __device__ void pass_forward(Ctx &c, int lvl) {
 __device__ void pass_rho(Ctx &c) {
   Shared &S = *c.S;
   const EccLevel &L = c.cfg->lv[0];
-  const Img cur = level_image(c, 0);
+  const float *__restrict__ cur = c.frame->pyr + L.cur_off;
+  const float *__restrict__ ref = L.ref;
+  const uint8_t *__restrict__ rmask = L.refmask;
+  const int cols = L.cols, rows = L.rows;
   const MapCoef m = S.map;
   double acc[6] = {0, 0, 0, 0, 0, 0};
-  const int n = L.cols * L.rows;
-  for (int i = c.rank * NT + c.tid; i < n; i += c.csize * NT) {
-    const int y = i / L.cols, x = i - y * L.cols;
+  int nvalid = 0;
+  const int n = cols * rows;
+  Walk w(c.rank * NT + c.tid, c.csize * NT, cols);
+#pragma unroll 2
+  for (; w.i < n; w.next()) {
     float u, v;
-    map_xy(m, (float)x, (float)y, u, v);
-    bool ok = valid255_linear(u, v, L.cols, L.rows);
-    if (ok && L.refmask) ok = L.refmask[i] != 0;
-    if (!ok) continue;
-    const double g = sample_linear<SSK_32F>(cur, 0, u, v, SSK_BORDER_CONSTANT, 0.f);
-    const double f = __ldg(L.ref + i);
-    acc[0] += 1.0; acc[1] += f; acc[2] += g; acc[3] += f * f; acc[4] += g * g; acc[5] += f * g;
+    map_xy(m, (float)w.x, (float)w.y, u, v);
+    const int sx = cvround32(u), sy = cvround32(v);
+    bool ok = lin_valid(sx, sy, cols, rows);
+    if (rmask) ok = ok && rmask[w.i] != 0;
+    // valid pixels have every non-zero-weight tap in bounds: the clamped sample equals BORDER_CONSTANT 0
+    const double g = ok ? (double)lin_sample(cur, cols, rows, sx, sy) : 0.0;
+    const double f = ok ? (double)__ldg(ref + w.i) : 0.0;
+    nvalid += ok ? 1 : 0;
+    acc[1] += f; acc[2] += g; acc[3] += f * f; acc[4] += g * g; acc[5] += f * g;
   }
+  acc[0] = (double)nvalid;
   cluster_reduce<6>(c, acc);
 }
 

@@ -21,55 +21,80 @@ __device__ __forceinline__ float load_gray(const Img &im, int y, int x) {
   return fmaf(r, 0.299f, fmaf(g, 0.587f, b * 0.114f));
 }
 
-constexpr int PD_OW = 32, PD_OH = 8;
-constexpr int PD_IW = 2 * PD_OW + 3, PD_IH = 2 * PD_OH + 3;
+// Visits the (ih x iw) elements of a CTA tile with one warp per row and lanes along x (coalesced, no div/mod).
+template <class F>
+__device__ __forceinline__ void for_tile(int ih, int iw, F f) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int r = warp; r < ih; r += nw)
+    for (int c = lane; c < iw; c += 32) f(r, c);
+}
+
+constexpr int PD_OW = 64, PD_OH = 16, PD_RPT = 4;   // CTA tile (outputs) and output rows per thread
+
+// cv::pyrDown, bit-exact against cv2 4.13 (oracle/cvmodel.py::pyrdown_f32).
+//   horizontal: columns covered by the 4-lane PyrDownVecH loop use s0*6 + ((s-1 + s1)*4 + (s-2 + s2)); the border
+//               column and the scalar tail use ((s0*6 + (s-1 + s1)*4) + s-2) + s2
+//   vertical  : PyrDownVecV (4 lanes): ((r1 + r3) + r2)*4 + ((r0 + r4) + (r2 + r2));
+//               scalar tail: ((r2*6 + (r1 + r3)*4) + r0) + r4
+// One thread owns one output column and PD_RPT consecutive output rows: it forms the 2*PD_RPT+3 horizontally
+// filtered input rows in registers (interior: three 8-byte loads per row, coalesced across the warp) and then the
+// vertical taps.  No shared memory, no barrier.
+__device__ __forceinline__ float pd_hform(float p0, float p1, float p2, float p3, float p4, bool simd) {
+  const float a1 = __fmul_rn(__fadd_rn(p1, p3), 4.f), c6 = __fmul_rn(p2, 6.f);
+  return simd ? __fadd_rn(c6, __fadd_rn(a1, __fadd_rn(p0, p4))) : __fadd_rn(__fadd_rn(__fadd_rn(c6, a1), p0), p4);
+}
 
 template <int DEPTH>
 __global__ void __launch_bounds__(256) k_pyrdown(const PyrDownArgs a) {
-  __shared__ float s_in[PD_IH][PD_IW + 1];
-  __shared__ float s_h[PD_IH][PD_OW + 1];
+  constexpr int NR = 2 * PD_RPT + 3;
   const int b = blockIdx.z;
   Img src = a.src;
   if (a.src_ptrs) src.data = a.src_ptrs[b];
   float *dst = a.dst_ptrs ? a.dst_ptrs[b] : a.dst;
-  const int ox0 = blockIdx.x * PD_OW, oy0 = blockIdx.y * PD_OH;
-  const int ix0 = 2 * ox0 - 2, iy0 = 2 * oy0 - 2;
+  const int ox = blockIdx.x * PD_OW + (threadIdx.x & (PD_OW - 1));
+  const int oy0 = blockIdx.y * PD_OH + (threadIdx.x / PD_OW) * PD_RPT;
+  if (ox >= a.dst_cols || oy0 >= a.dst_rows) return;
   const int width0 = min((src.cols - 3) / 2 + 1, a.dst_cols);   // PyrDownInvoker: columns free of border handling
-  const int nsimd_h = 4 * ((width0 - 1) / 4);
-  for (int k = threadIdx.x; k < PD_IH * PD_IW; k += blockDim.x) {
-    const int r = k / PD_IW, c = k - r * PD_IW;
-    const int yy = border_idx(iy0 + r, src.rows, SSK_BORDER_REFLECT101);
-    const int xx = border_idx(ix0 + c, src.cols, SSK_BORDER_REFLECT101);
-    s_in[r][c] = load_gray<DEPTH>(src, yy, xx);
+  const bool hsimd = ox >= 1 && ox < 1 + 4 * ((width0 - 1) / 4);
+  const bool vsimd = ox < (a.dst_cols & ~3);
+  const int ix = 2 * ox - 2, iy = 2 * oy0 - 2;
+  float h[NR];
+  const bool fast = DEPTH == SSK_32F && src.cn == 1 && ix >= 0 && ix + 5 < src.cols && iy >= 0 && iy + NR - 1 < src.rows &&
+                    (src.step & 7) == 0 && (reinterpret_cast<uintptr_t>(src.data) & 7) == 0;
+  if (fast) {
+    const char *p = static_cast<const char *>(src.data) + (int64_t)iy * src.step + (int64_t)ix * 4;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const float2 *q = reinterpret_cast<const float2 *>(p + (int64_t)r * src.step);
+      const float2 A = __ldg(q), B = __ldg(q + 1);
+      const float p4 = __ldg(reinterpret_cast<const float *>(q + 2));
+      h[r] = pd_hform(A.x, A.y, B.x, B.y, p4, hsimd);
+    }
+  } else {
+    int xx[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) xx[c] = border_idx(ix + c, src.cols, SSK_BORDER_REFLECT101);
+#pragma unroll 1
+    for (int r = 0; r < NR; ++r) {
+      const int yy = border_idx(iy + r, src.rows, SSK_BORDER_REFLECT101);
+      const float v = pd_hform(load_gray<DEPTH>(src, yy, xx[0]), load_gray<DEPTH>(src, yy, xx[1]), load_gray<DEPTH>(src, yy, xx[2]),
+                               load_gray<DEPTH>(src, yy, xx[3]), load_gray<DEPTH>(src, yy, xx[4]), hsimd);
+      // h[] must stay in registers: write through a fully unrolled select instead of a dynamic index
+#pragma unroll
+      for (int k = 0; k < NR; ++k) if (k == r) h[k] = v;
+    }
   }
-  __syncthreads();
-  // horizontal: row[x] = s[2x]*6 + (s[2x-1] + s[2x+1])*4 + s[2x-2] + s[2x+2]
-  for (int k = threadIdx.x; k < PD_IH * PD_OW; k += blockDim.x) {
-    const int r = k / PD_OW, x = k - r * PD_OW;
-    const float *p = &s_in[r][2 * x];   // p[0] = s[2x-2]
-    // cv::pyrDown, bit-exact against cv2 4.13 (oracle/cvmodel.py::pyrdown_f32): columns covered by the 4-lane
-    // PyrDownVecH loop use s0*6 + ((s-1 + s1)*4 + (s-2 + s2)); the border column and the scalar tail use
-    // ((s0*6 + (s-1 + s1)*4) + s-2) + s2
-    const int gx = ox0 + x;
-    const float a1 = __fmul_rn(__fadd_rn(p[1], p[3]), 4.f), c6 = __fmul_rn(p[2], 6.f);
-    s_h[r][x] = (gx >= 1 && gx < 1 + nsimd_h) ? __fadd_rn(c6, __fadd_rn(a1, __fadd_rn(p[0], p[4])))
-                                              : __fadd_rn(__fadd_rn(__fadd_rn(c6, a1), p[0]), p[4]);
-  }
-  __syncthreads();
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int ox = ox0 + tx, oy = oy0 + ty;
-  if (ox < a.dst_cols && oy < a.dst_rows) {
-    const int r = 2 * ty;
-    // PyrDownVecV (4 lanes): ((r1 + r3) + r2)*4 + ((r0 + r4) + (r2 + r2)); scalar tail: ((r2*6 + (r1 + r3)*4) + r0) + r4
-    const float c2 = s_h[r + 2][tx], a13 = __fadd_rn(s_h[r + 1][tx], s_h[r + 3][tx]);
+#pragma unroll
+  for (int j = 0; j < PD_RPT; ++j) {
+    if (oy0 + j >= a.dst_rows) break;
+    const float r0 = h[2 * j], r1 = h[2 * j + 1], r2 = h[2 * j + 2], r3 = h[2 * j + 3], r4 = h[2 * j + 4];
+    const float a13 = __fadd_rn(r1, r3);
     float v;
-    if (ox < (a.dst_cols & ~3))
-      v = __fadd_rn(__fmul_rn(__fadd_rn(a13, c2), 4.f), __fadd_rn(__fadd_rn(s_h[r][tx], s_h[r + 4][tx]), __fadd_rn(c2, c2)));
-    else
-      v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(c2, 6.f), __fmul_rn(a13, 4.f)), s_h[r][tx]), s_h[r + 4][tx]);
+    if (vsimd) v = __fadd_rn(__fmul_rn(__fadd_rn(a13, r2), 4.f), __fadd_rn(__fadd_rn(r0, r4), __fadd_rn(r2, r2)));
+    else v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2, 6.f), __fmul_rn(a13, 4.f)), r0), r4);
     v = __fmul_rn(v, 1.0f / 256.0f);
     if (a.post_scale != 1.f) v = __fmul_rn(v, a.post_scale);
-    dst[(int64_t)oy * a.dst_cols + ox] = v;
+    dst[(int64_t)(oy0 + j) * a.dst_cols + ox] = v;
   }
 }
 
@@ -83,67 +108,73 @@ __global__ void __launch_bounds__(256) k_to_gray(const Img im, const void *const
   if (x < src.cols && y < src.rows) d[(int64_t)y * src.cols + x] = load_gray<DEPTH>(src, y, x);
 }
 
-constexpr int SF_W = 32, SF_H = 8, SF_R = (kMaxTaps - 1) / 2;
+constexpr int SF_W = 64, SF_H = 16, SF_R = (kMaxTaps - 1) / 2;
 
+// KXN / KYN > 0: tap counts known at compile time (loops unroll); 0: taken from the arguments
+template <int KXN, int KYN>
 __global__ void __launch_bounds__(256) k_sepfilter(const SepFilterArgs a) {
-  __shared__ float s_in[SF_H + 2 * SF_R][SF_W + 2 * SF_R + 1];
-  __shared__ float s_h[SF_H + 2 * SF_R][SF_W + 1];
+  constexpr int RMAX = (KXN && KYN) ? ((KXN > KYN ? KXN : KYN) >> 1) : SF_R;
+  __shared__ float s_in[SF_H + 2 * RMAX][SF_W + 2 * RMAX + 1];
+  __shared__ float s_h[SF_H + 2 * RMAX][SF_W];
   const int b = blockIdx.z;
   const float *src = a.src_ptrs ? a.src_ptrs[b] : a.src;
   float *dst = a.dst_ptrs ? a.dst_ptrs[b] : a.dst;
-  const int rx = a.kxn >> 1, ry = a.kyn >> 1;
+  const int kxn = KXN ? KXN : a.kxn, kyn = KYN ? KYN : a.kyn;
+  const int rx = kxn >> 1, ry = kyn >> 1;
   const int x0 = blockIdx.x * SF_W, y0 = blockIdx.y * SF_H;
-  const int iw = SF_W + 2 * rx, ih = SF_H + 2 * ry;
-  for (int k = threadIdx.x; k < ih * iw; k += blockDim.x) {
-    const int r = k / iw, c = k - r * iw;
+  const int ow = min(SF_W, a.cols - x0), oh = min(SF_H, a.rows - y0);
+  const int iw = ow + 2 * rx, ih = oh + 2 * ry;
+  for_tile(ih, iw, [&](int r, int c) {
     const int yy = min(max(y0 - ry + r, 0), a.rows - 1), xx = min(max(x0 - rx + c, 0), a.cols - 1);
     s_in[r][c] = __ldg(src + (int64_t)yy * a.cols + xx);
-  }
+  });
   __syncthreads();
   // row / column arithmetic follows OpenCV's filter engine (found bit-exact against cv2 4.13 for the kernels of this
   // path: 5-tap derivative, 3-tap smoothing, 7-tap Gaussian)
-  const bool xsym = a.kx[0] == a.kx[a.kxn - 1];
-  for (int k = threadIdx.x; k < ih * SF_W; k += blockDim.x) {
-    const int r = k / SF_W, x = k - r * SF_W;
+  const bool xsym = a.kx[0] == a.kx[kxn - 1];
+  for_tile(ih, ow, [&](int r, int x) {
     const float *p = &s_in[r][x + rx];
     float acc;
-    if (a.kxn <= 5) {
+    if (kxn <= 5) {
       // SymmRowSmallFilter: k0*x0 then fma over the (anti)symmetric pairs
       if (xsym) {
         acc = __fmul_rn(a.kx[rx], p[0]);
+#pragma unroll
         for (int i = 1; i <= rx; ++i) acc = __fmaf_rn(__fadd_rn(p[i], p[-i]), a.kx[rx + i], acc);
       } else {
         acc = rx >= 1 ? __fmul_rn(__fsub_rn(p[1], p[-1]), a.kx[rx + 1]) : 0.f;
+#pragma unroll
         for (int i = 2; i <= rx; ++i) acc = __fmaf_rn(__fsub_rn(p[i], p[-i]), a.kx[rx + i], acc);
       }
     } else {
       // RowFilter (RowVec_32f): taps in order, fma chain
       acc = __fmul_rn(p[-rx], a.kx[0]);
-      for (int i = 1; i < a.kxn; ++i) acc = __fmaf_rn(p[i - rx], a.kx[i], acc);
+#pragma unroll
+      for (int i = 1; i < kxn; ++i) acc = __fmaf_rn(p[i - rx], a.kx[i], acc);
     }
     s_h[r][x] = acc;
-  }
+  });
   __syncthreads();
-  const bool ysym = a.ky[0] == a.ky[a.kyn - 1];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int x = x0 + tx, y = y0 + ty;
-  if (x < a.cols && y < a.rows) {
+  const bool ysym = a.ky[0] == a.ky[kyn - 1];
+  for_tile(oh, ow, [&](int ty, int tx) {
     const int r = ty + ry;
     // SymmColumnFilter (SymmColumnVec_32f): centre tap then fma over the (anti)symmetric pairs
     float acc;
     if (ysym) {
       acc = __fmul_rn(a.ky[ry], s_h[r][tx]);
+#pragma unroll
       for (int i = 1; i <= ry; ++i) acc = __fmaf_rn(__fadd_rn(s_h[r + i][tx], s_h[r - i][tx]), a.ky[ry + i], acc);
     } else {
       acc = ry >= 1 ? __fmul_rn(__fsub_rn(s_h[r + 1][tx], s_h[r - 1][tx]), a.ky[ry + 1]) : 0.f;
+#pragma unroll
       for (int i = 2; i <= ry; ++i) acc = __fmaf_rn(__fsub_rn(s_h[r + i][tx], s_h[r - i][tx]), a.ky[ry + i], acc);
     }
-    dst[(int64_t)y * a.cols + x] = acc;
-  }
+    dst[(int64_t)(y0 + ty) * a.cols + x0 + tx] = acc;
+  });
 }
 
 // ---- W1 ------------------------------------------------------------------------------------------
-constexpr int W1_W = 32, W1_H = 8, W1_RMAX = 4;
+constexpr int W1_W = 64, W1_H = 16, W1_RMAX = 4;
 
 __global__ void __launch_bounds__(256) k_w1_grad(const W1Args a, int nblocks) {
   __shared__ float s_in[W1_H + 2 * W1_RMAX][W1_W + 2 * W1_RMAX + 1];
@@ -153,17 +184,15 @@ __global__ void __launch_bounds__(256) k_w1_grad(const W1Args a, int nblocks) {
   float *gmap = a.gmap_ptrs ? a.gmap_ptrs[b] : a.gmap;
   const int r = a.kradius;
   const int x0 = blockIdx.x * W1_W, y0 = blockIdx.y * W1_H;
-  const int iw = W1_W + 2 * r, ih = W1_H + 2 * r;
-  for (int k = threadIdx.x; k < ih * iw; k += blockDim.x) {
-    const int rr = k / iw, c = k - rr * iw;
+  const int ow = min(W1_W, a.cols - x0), oh = min(W1_H, a.rows - y0);
+  for_tile(oh + 2 * r, ow + 2 * r, [&](int rr, int c) {
     const int yy = min(max(y0 - r + rr, 0), a.rows - 1), xx = min(max(x0 - r + c, 0), a.cols - 1);
     s_in[rr][c] = __ldg(M + (int64_t)yy * a.cols + xx);
-  }
+  });
   __syncthreads();
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int x = x0 + tx, y = y0 + ty;
+  const float ms = (float)(a.depth_scale * a.depth_scale * a.depth_scale);
   double sg = 0.0, sg4 = 0.0;
-  if (x < a.cols && y < a.rows) {
+  for_tile(oh, ow, [&](int ty, int tx) {
     float mx = -3.4e38f, mn = 3.4e38f;
     for (int dy = 0; dy <= 2 * r; ++dy)
       for (int dx = 0; dx <= 2 * r; ++dx) {
@@ -172,14 +201,14 @@ __global__ void __launch_bounds__(256) k_w1_grad(const W1Args a, int nblocks) {
         mn = fminf(mn, v);
       }
     const float g = __fsub_rn(mx, mn);
-    const float ms = (float)(a.depth_scale * a.depth_scale * a.depth_scale);
-    gmap[(int64_t)y * a.cols + x] = __fmul_rn(__fmul_rn(__fmul_rn(g, g), g), ms);
-    sg = (double)fabsf(g);
-    sg4 = (double)__fmul_rn(__fmul_rn(__fmul_rn(g, g), g), g);
-  }
+    gmap[(int64_t)(y0 + ty) * a.cols + x0 + tx] = __fmul_rn(__fmul_rn(__fmul_rn(g, g), g), ms);
+    sg += (double)fabsf(g);
+    sg4 += (double)__fmul_rn(__fmul_rn(__fmul_rn(g, g), g), g);
+  });
   sg = warp_sum(sg);
   sg4 = warp_sum(sg4);
-  if (tx == 0) { s_red[0][ty] = sg; s_red[1][ty] = sg4; }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_red[0][warp] = sg; s_red[1][warp] = sg4; }
   __syncthreads();
   if (threadIdx.x == 0) {
     double t0 = 0, t1 = 0;
@@ -217,32 +246,47 @@ __global__ void __launch_bounds__(256) k_w1_final(const W1Args a, int nblocks) {
 }
 
 // cv::resize(map + 0.05 Q, full size, INTER_LINEAR) (c_local_variance_sharpness_measure.cc:176-184, 239-243)
-__global__ void __launch_bounds__(256) k_w1_upsample(const W1Args a) {
+// One thread per 4 consecutive output pixels (one 16-byte store when the row allows it).
+__global__ void __launch_bounds__(256) k_w1_upsample(const W1Args a, double scx, double scy) {
   const int b = blockIdx.z;
-  const float *g = a.gmap_ptrs ? a.gmap_ptrs[b] : a.gmap;
-  float *out = a.out_ptrs ? a.out_ptrs[b] : a.out;
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x >= a.full_cols || y >= a.full_rows) return;
+  const float *__restrict__ g = a.gmap_ptrs ? a.gmap_ptrs[b] : a.gmap;
+  float *__restrict__ out = a.out_ptrs ? a.out_ptrs[b] : a.out;
+  const int x4 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4, y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x4 >= a.full_cols || y >= a.full_rows) return;
   const float add = (float)a.stats[b * 4 + 3];
-  if (a.full_cols == a.cols && a.full_rows == a.rows) {
-    out[(int64_t)y * a.full_cols + x] = __fadd_rn(g[(int64_t)y * a.cols + x], add);
-    return;
-  }
-  const double scx = (double)a.cols / a.full_cols, scy = (double)a.rows / a.full_rows;
-  float fx = (float)((x + 0.5) * scx - 0.5), fy = (float)((y + 0.5) * scy - 0.5);
-  int sx = (int)floorf(fx), sy = (int)floorf(fy);
-  fx -= sx; fy -= sy;
-  if (sx < 0) { fx = 0; sx = 0; }
-  if (sx >= a.cols - 1) { fx = 0; sx = a.cols - 1; }
+  const bool same = a.full_cols == a.cols && a.full_rows == a.rows;
+  float fy = (float)((y + 0.5) * scy - 0.5);
+  int sy = (int)floorf(fy);
+  fy -= sy;
   if (sy < 0) { fy = 0; sy = 0; }
   if (sy >= a.rows - 1) { fy = 0; sy = a.rows - 1; }
-  const int sx1 = min(sx + 1, a.cols - 1), sy1 = min(sy + 1, a.rows - 1);
-  const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
-  const float v00 = __fadd_rn(g[(int64_t)sy * a.cols + sx], add), v01 = __fadd_rn(g[(int64_t)sy * a.cols + sx1], add);
-  const float v10 = __fadd_rn(g[(int64_t)sy1 * a.cols + sx], add), v11 = __fadd_rn(g[(int64_t)sy1 * a.cols + sx1], add);
-  const float r0 = __fadd_rn(__fmul_rn(v00, a0), __fmul_rn(v01, a1));
-  const float r1 = __fadd_rn(__fmul_rn(v10, a0), __fmul_rn(v11, a1));
-  out[(int64_t)y * a.full_cols + x] = __fadd_rn(__fmul_rn(r0, b0), __fmul_rn(r1, b1));
+  const int sy1 = min(sy + 1, a.rows - 1);
+  const float b0 = 1.f - fy, b1 = fy;
+  const float *__restrict__ g0 = g + (int64_t)sy * a.cols, *__restrict__ g1 = g + (int64_t)sy1 * a.cols;
+  float v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = min(x4 + k, a.full_cols - 1);
+    if (same) { v[k] = __fadd_rn(__ldg(g + (int64_t)y * a.cols + x), add); continue; }
+    float fx = (float)((x + 0.5) * scx - 0.5);
+    int sx = (int)floorf(fx);
+    fx -= sx;
+    if (sx < 0) { fx = 0; sx = 0; }
+    if (sx >= a.cols - 1) { fx = 0; sx = a.cols - 1; }
+    const int sx1 = min(sx + 1, a.cols - 1);
+    const float a0 = 1.f - fx, a1 = fx;
+    const float v00 = __fadd_rn(__ldg(g0 + sx), add), v01 = __fadd_rn(__ldg(g0 + sx1), add);
+    const float v10 = __fadd_rn(__ldg(g1 + sx), add), v11 = __fadd_rn(__ldg(g1 + sx1), add);
+    const float r0 = __fadd_rn(__fmul_rn(v00, a0), __fmul_rn(v01, a1));
+    const float r1 = __fadd_rn(__fmul_rn(v10, a0), __fmul_rn(v11, a1));
+    v[k] = __fadd_rn(__fmul_rn(r0, b0), __fmul_rn(r1, b1));
+  }
+  float *o = out + (int64_t)y * a.full_cols + x4;
+  if (x4 + 3 < a.full_cols && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+    *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+    for (int k = 0; k < 4 && x4 + k < a.full_cols; ++k) o[k] = v[k];
+  }
 }
 
 __global__ void __launch_bounds__(256) k_erode5_u8(const uint8_t *src, int64_t sstep, uint8_t *dst, int64_t dstep, int rows,
@@ -286,7 +330,10 @@ int launch_to_gray(const Img &src, const void *const *src_ptrs, float *dst, floa
 int launch_sepfilter(const SepFilterArgs &a, cudaStream_t s) {
   SSK_REQUIRE((a.kxn & 1) && (a.kyn & 1) && a.kxn <= kMaxTaps && a.kyn <= kMaxTaps, "sepFilter2D: odd kernels up to 31 taps");
   dim3 grid(div_up(a.cols, SF_W), div_up(a.rows, SF_H), a.batch);
-  k_sepfilter<<<grid, 256, 0, s>>>(a);
+  if (a.kxn == 7 && a.kyn == 7) k_sepfilter<7, 7><<<grid, 256, 0, s>>>(a);          // Gaussian, sigma = 1
+  else if (a.kxn == 5 && a.kyn == 3) k_sepfilter<5, 3><<<grid, 256, 0, s>>>(a);     // ecc_differentiate, d/dx
+  else if (a.kxn == 3 && a.kyn == 5) k_sepfilter<3, 5><<<grid, 256, 0, s>>>(a);     // ecc_differentiate, d/dy
+  else k_sepfilter<0, 0><<<grid, 256, 0, s>>>(a);
   SSK_LAUNCH_CHECK();
   return SSK_OK;
 }
@@ -302,8 +349,8 @@ int launch_w1(const W1Args &a, cudaStream_t s) {
   k_w1_final<<<a.batch, 256, 0, s>>>(a, nblocks);
   SSK_LAUNCH_CHECK();
   if (a.out || a.out_ptrs) {
-    dim3 g2(div_up(a.full_cols, 32), div_up(a.full_rows, 8), a.batch);
-    k_w1_upsample<<<g2, 256, 0, s>>>(a);
+    dim3 g2(div_up(a.full_cols, 128), div_up(a.full_rows, 8), a.batch);
+    k_w1_upsample<<<g2, 256, 0, s>>>(a, (double)a.cols / a.full_cols, (double)a.rows / a.full_rows);
     SSK_LAUNCH_CHECK();
   }
   return SSK_OK;

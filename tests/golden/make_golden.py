@@ -57,7 +57,9 @@ def cv_vectors():
     for i, (h, w) in enumerate(((64, 96), (45, 61), (7, 9), (33, 130))):
         a = rng.random((h, w)).astype(f32)
         d["pyr_src%d" % i] = a
-        d["pyr_dst%d" % i] = cv2.pyrDown(a)   # BORDER_DEFAULT (REFLECT101), as ecc2.cc:622 calls it
+        d["pyr_dst%d" % i] = cv2.pyrDown(a)   # BORDER_DEFAULT (REFLECT101), default size
+        # as c_ecch::downscale_image calls it (ecc2.cc:972-982): dstsize from compute_next_pyramid_layer_size (ecc2.h:290-293)
+        d["pyr_ecc%d" % i] = cv2.pyrDown(a, dstsize=(((w + 1) >> 1) & ~1, ((h + 1) >> 1) & ~1))
     # --- cv::sepFilter2D with the ECC gradient kernels (ecc2.cc:148-149), widths % 4 == 0
     a = rng.random((40, 64)).astype(f32)
     kd = np.array([1 / 12, -2 / 3, 0, 2 / 3, -1 / 12], f32)

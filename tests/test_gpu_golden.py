@@ -48,7 +48,7 @@ def test_pyramid_matches_opencv_golden(gpu, cvp, i):
     g = api.c_ecch(None, maxlevel=2, minimum_image_size=4, reference_smooth_sigma=0.0)
     g.set_reference_image(src)
     assert g.num_levels() == 2
-    assert np.array_equal(g.reference_image(1), cvp["pyr_dst%d" % i])
+    assert np.array_equal(g.reference_image(1), cvp["pyr_ecc%d" % i])
 
 
 @pytest.mark.parametrize("path", STACKS, ids=[os.path.basename(p)[6:-4] for p in STACKS])
