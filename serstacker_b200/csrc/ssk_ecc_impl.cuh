@@ -448,6 +448,33 @@ struct Walk {
 
 __device__ __forceinline__ int cvround32(float v) { return __float2int_rn(__fmul_rn(v, 32.0f)); }
 
+// map_xy with the map kind fixed at compile time (the passes are instantiated per transform type)
+template <int TYPE> struct MapKind { static constexpr int MT = MAP_EUCLIDEAN; };
+template <> struct MapKind<SSK_MOTION_TRANSLATION> { static constexpr int MT = MAP_TRANSLATION; };
+template <> struct MapKind<SSK_MOTION_AFFINE> { static constexpr int MT = MAP_AFFINE; };
+template <> struct MapKind<SSK_MOTION_HOMOGRAPHY> { static constexpr int MT = MAP_HOMOGRAPHY; };
+
+template <int MT>
+__device__ __forceinline__ void map_xy_t(const MapCoef &m, float x, float y, float &u, float &v) {
+  if (MT == MAP_TRANSLATION) {
+    u = __fadd_rn(x, m.c[0]);
+    v = __fadd_rn(y, m.c[1]);
+  } else if (MT == MAP_AFFINE) {
+    u = __fadd_rn(__fadd_rn(__fmul_rn(m.c[0], x), __fmul_rn(m.c[1], y)), m.c[2]);
+    v = __fadd_rn(__fadd_rn(__fmul_rn(m.c[3], x), __fmul_rn(m.c[4], y)), m.c[5]);
+  } else {
+    map_xy(m, x, y, u, v);
+  }
+}
+
+// (unsigned)cvRound(u) < n without the conversion: cvRound rounds half to even, so u = -0.5 maps to 0 (valid) and
+// u = n - 0.5 maps to n - 1 only when n is odd.
+struct RoundRange {
+  float hi; bool hi_incl;
+  __device__ __forceinline__ explicit RoundRange(int n) : hi((float)n - 0.5f), hi_incl((n & 1) != 0) {}
+  __device__ __forceinline__ bool operator()(float u) const { return u >= -0.5f && (hi_incl ? u <= hi : u < hi); }
+};
+
 // valid255_linear on pre-quantised coordinates (sx, sy = cvRound(32 u), cvRound(32 v))
 __device__ __forceinline__ bool lin_valid(int sx, int sy, int cols, int rows) {
   const int ix = sx >> 5, iy = sy >> 5;
@@ -465,8 +492,8 @@ __device__ __forceinline__ float lin_sample(const float *__restrict__ p, int col
   const float wx0 = 1.0f - tx, wy0 = 1.0f - ty;
   const int x0 = min(max(ix, 0), cols - 1), x1 = min(max(ix + 1, 0), cols - 1);
   const int y0 = min(max(iy, 0), rows - 1), y1 = min(max(iy + 1, 0), rows - 1);
-  const float *r0 = p + y0 * cols, *r1 = p + y1 * cols;
-  const float s00 = __ldg(r0 + x0), s01 = __ldg(r0 + x1), s10 = __ldg(r1 + x0), s11 = __ldg(r1 + x1);
+  const int o0 = y0 * cols, o1 = y1 * cols;     // 32-bit offsets: a level has far fewer than 2^31 pixels
+  const float s00 = __ldg(p + (o0 + x0)), s01 = __ldg(p + (o0 + x1)), s10 = __ldg(p + (o1 + x0)), s11 = __ldg(p + (o1 + x1));
   float out = __fadd_rn(__fmul_rn(s00, __fmul_rn(wy0, wx0)), __fmul_rn(s01, __fmul_rn(wy0, tx)));
   out = __fadd_rn(out, __fmul_rn(s10, __fmul_rn(ty, wx0)));
   out = __fadd_rn(out, __fmul_rn(s11, __fmul_rn(ty, tx)));
@@ -498,15 +525,16 @@ __device__ void pass_ic(Ctx &c, int lvl, bool lm_masks) {
   int nvalid = 0;
   const int n = cols * rows;
   // Branch-free body (invalid pixels contribute an exact 0.0), so that two pixels per thread are in flight.
+  const RoundRange in_x(cols), in_y(rows);
   Walk w(c.rank * NT + c.tid, c.csize * NT, cols);
 #pragma unroll 2
   for (; w.i < n; w.next()) {
     const float x = (float)w.x, y = (float)w.y;
     float u, v;
-    map_xy(m, x, y, u, v);
+    map_xy_t<MapKind<TYPE>::MT>(m, x, y, u, v);
     const int sx = cvround32(u), sy = cvround32(v);
     bool ok;
-    if (lm_masks) ok = (unsigned)__float2int_rn(u) < (unsigned)cols && (unsigned)__float2int_rn(v) < (unsigned)rows;
+    if (lm_masks) ok = in_x(u) && in_y(v);
     else ok = lin_valid(sx, sy, cols, rows);
     if (rmask) ok = ok && rmask[w.i] != 0;
     const float g = lin_sample(cur, cols, rows, sx, sy);

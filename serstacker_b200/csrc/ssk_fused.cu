@@ -24,10 +24,11 @@ namespace ssk {
 namespace {
 
 constexpr int TW = 32, TH = 32;          // tile of the accumulator handled by one CTA of the staged kernel
-constexpr int SWARPS = 4;                // warps per CTA
-constexpr int GR = TH / SWARPS;          // rows per warp strip
+constexpr int SWARPS = 4;                // warps per CTA, interior tiles (throughput: 8-row strips amortise the window fill)
+constexpr int RING_WARPS = 16;           // warps per CTA, border-ring tiles (few CTAs: latency-bound, so more warps per tile)
 constexpr int GSH = TH + 8;              // staged rows: tile + 3 taps + rounding + drift
 constexpr int WWD = TW + 8;              // staged weight-tile row (floats)
+constexpr int kItabBytes = kInterTab * kInterTab * 16 * (int)sizeof(short);   // fixed-point bicubic table
 
 __device__ __forceinline__ bool is_affine_like(int type) { return type != MAP_HOMOGRAPHY; }
 
@@ -299,7 +300,7 @@ template <int INTERP> struct RollS {
 template <int DEPTH, int INTERP, bool WEIGHTS, int MT, int J>
 __device__ __forceinline__ void roll_pixel_s(RollS<INTERP> &R, const ColMap<MT> &cm, float y, const unsigned char *s_f,
                                              const float *s_g, float scale, const StagePlan &pl, const float4 *s_cubic,
-                                             float *s_acc_px, float *s_w_px) {
+                                             float *s_acc_px, float *s_w_px, bool ok = true) {
   typedef StageGeom<DEPTH> G;
   constexpr int N = Taps<INTERP>::N, OFF = Taps<INTERP>::OFF;
   float u, v;
@@ -363,7 +364,7 @@ __device__ __forceinline__ void roll_pixel_s(RollS<INTERP> &R, const ColMap<MT> 
   const float W0 = *s_w_px, A = *s_acc_px;
   const float Wn = W0 + wk;
   const float factor = WEIGHTS ? __fdiv_rn(wk, Wn) : __fdiv_rn(1.0f, Wn);
-  const bool upd = !WEIGHTS || wk > 0.f;          // c_frame_accumulation.cc:114
+  const bool upd = ok && (!WEIGHTS || wk > 0.f);  // eroded validity mask (ring tiles); c_frame_accumulation.cc:114
   *s_w_px = upd ? Wn : W0;
   *s_acc_px = upd ? fmaf(I - A, factor, A) : A;
 }
@@ -378,75 +379,63 @@ __device__ __forceinline__ int bmap(int p, int n, int border) {
   return -1;
 }
 
-// One output pixel of a border-ring tile from the staged (clipped) footprint: all taps are fetched from shared memory
-// through cv::borderInterpolate, the weight taps with BORDER_CONSTANT 0; `ok` is the eroded validity mask.
-template <int DEPTH, int INTERP, bool WEIGHTS, int MT>
-__device__ __forceinline__ void ring_pixel_s(const ColMap<MT> &cm, float y, const unsigned char *s_f, const float *s_g,
-                                             const WarpAccArgs &a, const StagePlan &pl, const float4 *s_cubic, bool ok,
-                                             float *s_acc_px, float *s_w_px) {
+// Staging of a border-ring tile: the (unclipped) footprint is materialised in shared memory as a virtually padded
+// image - in-range 16-byte chunks by cp.async like the interior tiles, the overhang element-wise through
+// cv::borderInterpolate (frame) or as zeros (weights: remapped with BORDER_CONSTANT 0).  The interpolation code is
+// then the interior one.
+template <int DEPTH>
+__device__ __noinline__ void issue_stage_ring(const FrameJob &job, const StagePlan &p, const WarpAccArgs &a, bool weighted,
+                                              unsigned char *s_f, float *s_g) {
   typedef StageGeom<DEPTH> G;
-  constexpr int N = Taps<INTERP>::N, OFF = Taps<INTERP>::OFF;
-  float u, v;
-  cm(y, u, v);
-  int ix, iy, fx = 0, fy = 0;
-  if (INTERP == SSK_INTER_NEAREST) { ix = __float2int_rn(u); iy = __float2int_rn(v); }
-  else { quant32(u, ix, fx); quant32(v, iy, fy); }
-  int xm[N], ym[N];
-  bool xin[N], yin[N];
+  typedef typename PixT<DEPTH>::type T;
+  constexpr int CPR = G::WD / G::ALIGN;
+#pragma unroll 1
+  for (int k = threadIdx.x; k < GSH * CPR; k += blockDim.x) {
+    const int r = k / CPR, q = k - r * CPR;
+    const int gy = p.sy0 + r, gx = p.sx0 + q * G::ALIGN;
+    unsigned char *d = s_f + r * G::ROWB + q * 16;
+    if ((unsigned)gy < (unsigned)a.src_rows && gx >= 0 && gx + G::ALIGN <= a.src_cols) {
+      cp_async16(d, static_cast<const char *>(job.frame) + (int64_t)gy * a.src_step + (int64_t)gx * G::ES);
+    } else {
+      const int my = bmap(gy, a.src_rows, a.border);
+      const T *row = reinterpret_cast<const T *>(static_cast<const char *>(job.frame) + (int64_t)max(my, 0) * a.src_step);
 #pragma unroll
-  for (int q = 0; q < N; ++q) {
-    xm[q] = bmap(ix + OFF + q, a.src_cols, a.border); xin[q] = (unsigned)(ix + OFF + q) < (unsigned)a.src_cols;
-    ym[q] = bmap(iy + OFF + q, a.src_rows, a.border); yin[q] = (unsigned)(iy + OFF + q) < (unsigned)a.src_rows;
-  }
-  float F[N][N], Wt[N][N];
-#pragma unroll
-  for (int r = 0; r < N; ++r)
-#pragma unroll
-    for (int q = 0; q < N; ++q) {
-      F[r][q] = (xm[q] >= 0 && ym[r] >= 0) ? lds_px<DEPTH>(s_f + (ym[r] - pl.sy0) * G::ROWB + (xm[q] - pl.sx0) * G::ES, a.scale) : a.bval[0];
-      if (WEIGHTS) Wt[r][q] = (xin[q] && yin[r]) ? s_g[(iy + OFF + r - pl.sy0) * WWD + (ix + OFF + q - pl.sxw)] : 0.f;
-    }
-  float I, wk = 1.f;
-  if (INTERP == SSK_INTER_CUBIC) {
-    // cv::remap's order on the ring (16 products, row sums, then the sum of rows), as in sample_cubic
-    const float4 cx4 = s_cubic[fx], cy4 = s_cubic[fy];
-    const float wx[4] = {cx4.x, cx4.y, cx4.z, cx4.w}, wy[4] = {cy4.x, cy4.y, cy4.z, cy4.w};
-    I = 0.f; wk = 0.f;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      float rowf = 0.f, roww = 0.f;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float wgt = __fmul_rn(wy[r], wx[q]);
-        rowf = __fadd_rn(rowf, __fmul_rn(F[r % N][q % N], wgt));
-        if (WEIGHTS) roww = __fadd_rn(roww, __fmul_rn(Wt[r % N][q % N], wgt));
+      for (int e = 0; e < G::ALIGN; ++e) {     // independent loads: one memory latency per chunk, not one per element
+        const int mx = bmap(gx + e, a.src_cols, a.border);
+        T v;
+        if (mx >= 0 && my >= 0) v = row[mx];
+        else if (DEPTH == SSK_32F) v = (T)a.bval[0];
+        else v = (T)0;                                   // constant border of integer frames: staged only for value 0
+        reinterpret_cast<T *>(d)[e] = v;
       }
-      I = __fadd_rn(I, rowf);
-      if (WEIGHTS) wk = __fadd_rn(wk, roww);
     }
-    if (!WEIGHTS) wk = 1.f;
-  } else if (INTERP == SSK_INTER_LINEAR) {
-    const float tx = (float)fx * 0.03125f, ty = (float)fy * 0.03125f;
-    const float w00 = __fmul_rn(1.0f - ty, 1.0f - tx), w01 = __fmul_rn(1.0f - ty, tx), w10 = __fmul_rn(ty, 1.0f - tx), w11 = __fmul_rn(ty, tx);
-    I = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(F[0][0], w00), __fmul_rn(F[0][1 % N], w01)), __fmul_rn(F[1 % N][0], w10)), __fmul_rn(F[1 % N][1 % N], w11));
-    if (WEIGHTS) wk = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(Wt[0][0], w00), __fmul_rn(Wt[0][1 % N], w01)), __fmul_rn(Wt[1 % N][0], w10)), __fmul_rn(Wt[1 % N][1 % N], w11));
-  } else {
-    I = F[0][0];
-    if (WEIGHTS) wk = Wt[0][0];
   }
-  const float W0 = *s_w_px, A = *s_acc_px;
-  const float Wn = W0 + wk;
-  const float factor = WEIGHTS ? __fdiv_rn(wk, Wn) : __fdiv_rn(1.0f, Wn);
-  const bool upd = ok && (!WEIGHTS || wk > 0.f);
-  *s_w_px = upd ? Wn : W0;
-  *s_acc_px = upd ? fmaf(I - A, factor, A) : A;
+  if (weighted) {
+#pragma unroll 1
+    for (int k = threadIdx.x; k < GSH * (WWD / 4); k += blockDim.x) {
+      const int r = k / (WWD / 4), q = k - r * (WWD / 4);
+      const int gy = p.sy0 + r, gx = p.sxw + q * 4;
+      float *d = s_g + r * WWD + q * 4;
+      if ((unsigned)gy < (unsigned)a.src_rows && gx >= 0 && gx + 4 <= a.src_cols) {
+        cp_async16(d, reinterpret_cast<const char *>(job.weights) + (int64_t)gy * a.w_step + (int64_t)gx * 4);
+      } else {
+        const bool yin = (unsigned)gy < (unsigned)a.src_rows;
+        const float *row = reinterpret_cast<const float *>(reinterpret_cast<const char *>(job.weights) + (int64_t)(yin ? gy : 0) * a.w_step);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) d[e] = (yin && (unsigned)(gx + e) < (unsigned)a.src_cols) ? row[gx + e] : 0.f;
+      }
+    }
+  }
 }
 
-// Staging plan of a border-ring tile: the footprint is clipped to the frame; reflected / replicated taps then fall
-// inside the clipped region.  Not staged (generic path) for BORDER_WRAP, projective maps, oversize footprints.
+// Staging plan of a border-ring tile: like plan_stage but without the in-bounds requirement.  Not staged (generic
+// path) for BORDER_WRAP, projective maps, oversize footprints, overhang beyond one reflection, and a non-zero
+// constant border on integer frames.
 __device__ __noinline__ StagePlan plan_stage_ring(const MapCoef &m, int bx0, int by0, const WarpAccArgs &a, int align, int wd) {
   StagePlan p; p.staged = 0; p.sx0 = p.sy0 = p.sxw = 0;
   if (!a.stage_aligned || !is_affine_like(m.type) || a.border == SSK_BORDER_WRAP) return p;
+  const bool constant = a.border != SSK_BORDER_REPLICATE && a.border != SSK_BORDER_REFLECT && a.border != SSK_BORDER_REFLECT101;
+  if (constant && a.depth != SSK_32F && a.bval[0] != 0.f) return p;
   const int cx1 = min(bx0 + TW - 1, a.cols - 1), cy1 = min(by0 + TH - 1, a.rows - 1);
   float umin = 3.4e38f, umax = -3.4e38f, vmin = 3.4e38f, vmax = -3.4e38f;
 #pragma unroll 1
@@ -456,30 +445,37 @@ __device__ __noinline__ StagePlan plan_stage_ring(const MapCoef &m, int bx0, int
     umin = fminf(umin, u); umax = fmaxf(umax, u); vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
   }
   if (!(umax - umin < 64.f && vmax - vmin < 64.f)) return p;
-  int x_lo = (int)floorf(umin) - 1, x_hi = (int)floorf(umax) + 3;
-  int y_lo = (int)floorf(vmin) - 1, y_hi = (int)floorf(vmax) + 3;
-  // overhang beyond the frame must be small enough for its reflection to lie inside the clipped footprint
-  const int ovx = max(max(-x_lo, x_hi - (a.src_cols - 1)), 0), ovy = max(max(-y_lo, y_hi - (a.src_rows - 1)), 0);
-  x_lo = max(x_lo, 0); y_lo = max(y_lo, 0); x_hi = min(x_hi, a.src_cols - 1); y_hi = min(y_hi, a.src_rows - 1);
-  if (x_hi - x_lo < ovx + 1 || y_hi - y_lo < ovy + 1) return p;
+  if (!(umin > -1.0e6f && vmin > -1.0e6f && umax < 1.0e6f && vmax < 1.0e6f)) return p;
+  const int x_lo = (int)floorf(umin) - 1, x_hi = (int)floorf(umax) + 3;
+  const int y_lo = (int)floorf(vmin) - 1, y_hi = (int)floorf(vmax) + 3;
   p.sx0 = x_lo & ~(align - 1);
   p.sy0 = y_lo;
   p.sxw = x_lo & ~3;
+  // a single reflection must land inside the frame for every staged position
+  const int lo_x = min(p.sx0, p.sxw), hi_x = max(p.sx0 + wd, p.sxw + WWD), hi_y = p.sy0 + GSH;
+  if (-lo_x >= a.src_cols || hi_x - a.src_cols >= a.src_cols || -p.sy0 >= a.src_rows || hi_y - a.src_rows >= a.src_rows) return p;
   p.staged = (x_hi - p.sx0 < wd) && (y_hi - p.sy0 < GSH) && (x_hi - p.sxw < WWD);
   return p;
 }
 
 template <int DEPTH, int INTERP, bool WEIGHTS, int MT, bool RING>
-__global__ void __launch_bounds__(TW * SWARPS) k_fused_staged(const __grid_constant__ WarpAccArgs a, const __grid_constant__ Tables tab,
+__global__ void __launch_bounds__(TW * (RING ? RING_WARPS : SWARPS)) k_fused_staged(const __grid_constant__ WarpAccArgs a, const __grid_constant__ Tables tab,
                                                                const TileList tl) {
   typedef StageGeom<DEPTH> G;
   constexpr int N = Taps<INTERP>::N;
+  constexpr int NWARP = RING ? RING_WARPS : SWARPS;   // warps per CTA
+  constexpr int GR = TH / NWARP;                      // rows per warp strip
   __shared__ float s_acc[TH][TW];                  // running mean of the tile (on chip for the whole batch)
   __shared__ float s_w[TH][TW];                    // running weight sum of the tile
   __shared__ float4 s_cubic[kInterTab];
   __shared__ __align__(16) unsigned char s_f[2][GSH * G::ROWB];
   __shared__ __align__(16) float s_g[2][GSH * WWD];
-  __shared__ uint8_t s_flag[RING ? TH + 4 : 1][RING ? TW + 8 : 1];   // pre-erosion validity of tile + 2-px halo
+  // ring tiles: per row of the tile + 2-px halo, the horizontally eroded validity of the tile columns (bit x = AND of
+  // the pre-erosion flags of columns x-2 .. x+2)
+  __shared__ unsigned long long s_hmask[RING ? TH + 4 : 1];
+  // ring tiles: the fixed-point bicubic table behind the validity test (32 KB, dynamic shared memory) so that the
+  // per-frame flag evaluation never waits on global memory
+  extern __shared__ __align__(16) short s_itab[];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int tx, ty;
@@ -490,6 +486,10 @@ __global__ void __launch_bounds__(TW * SWARPS) k_fused_staged(const __grid_const
   const int tw = min(TW, a.cols - bx0), th = min(TH, a.rows - by0);
   const int nrow = lane < tw ? max(0, min(GR, th - warp * GR)) : 0;
   if (INTERP == SSK_INTER_CUBIC && threadIdx.x < kInterTab) s_cubic[threadIdx.x] = tab.cubic[threadIdx.x];
+  if (RING && INTERP == SSK_INTER_CUBIC) {
+    const int4 *g = reinterpret_cast<const int4 *>(tab.cubic_itab);
+    for (int k = threadIdx.x; k < kItabBytes / 16; k += blockDim.x) reinterpret_cast<int4 *>(s_itab)[k] = __ldg(g + k);
+  }
 
   // accumulator tile -> shared memory; 16-byte accesses when the tile is complete and the pitch allows it
   const bool vec = (a.cols & 3) == 0 && tw == TW;
@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(TW * SWARPS) k_fused_staged(const __grid_const
   if (j < a.njobs) {
     plan = RING ? plan_stage_ring(a.jobs[j].map, bx0, by0, a, G::ALIGN, G::WD) : plan_stage(a.jobs[j].map, bx0, by0, a, G::ALIGN, G::WD);
     if (WEIGHTS && !a.jobs[j].weights) plan.staged = 0;    // flat frame (no weight map): generic path
-    if (plan.staged) issue_stage<DEPTH>(a.jobs[j], plan, a, WEIGHTS, s_f[0], s_g[0]);
+    if (plan.staged) { if (RING) issue_stage_ring<DEPTH>(a.jobs[j], plan, a, WEIGHTS, s_f[0], s_g[0]); else issue_stage<DEPTH>(a.jobs[j], plan, a, WEIGHTS, s_f[0], s_g[0]); }
   }
   cp_async_commit();
   __syncthreads();
@@ -528,23 +528,29 @@ __global__ void __launch_bounds__(TW * SWARPS) k_fused_staged(const __grid_const
     if (jn < a.njobs) {
       plan_n = RING ? plan_stage_ring(a.jobs[jn].map, bx0, by0, a, G::ALIGN, G::WD) : plan_stage(a.jobs[jn].map, bx0, by0, a, G::ALIGN, G::WD);
       if (WEIGHTS && !a.jobs[jn].weights) plan_n.staged = 0;
-      if (plan_n.staged) issue_stage<DEPTH>(a.jobs[jn], plan_n, a, WEIGHTS, s_f[buf ^ 1], s_g[buf ^ 1]);
+      if (plan_n.staged) { if (RING) issue_stage_ring<DEPTH>(a.jobs[jn], plan_n, a, WEIGHTS, s_f[buf ^ 1], s_g[buf ^ 1]); else issue_stage<DEPTH>(a.jobs[jn], plan_n, a, WEIGHTS, s_f[buf ^ 1], s_g[buf ^ 1]); }
     }
     cp_async_commit();
     if (RING && plan.staged) {
-      // pre-erosion validity of the tile and its 2-px halo (outside the image: erode border value 255)
+      // pre-erosion validity of the tile and its 2-px halo (outside the image: erode border value 255), one warp
+      // per row, packed by ballots
       const MapCoef m = a.jobs[j].map;
 #pragma unroll 1
-      for (int k = threadIdx.x; k < (TH + 4) * (TW + 4); k += blockDim.x) {
-        const int fy = k / (TW + 4), fxx = k - fy * (TW + 4);
-        const int gx = bx0 - 2 + fxx, gy = by0 - 2 + fy;
-        uint8_t okf = 1;
-        if (gx >= 0 && gy >= 0 && gx < a.cols && gy < a.rows) {
-          float u, v;
-          map_xy(m, (float)gx, (float)gy, u, v);
-          okf = valid255(INTERP, u, v, a.src_cols, a.src_rows, tab.cubic_itab) ? 1 : 0;
+      for (int fy = warp; fy < TH + 4; fy += NWARP) {
+        const int gy = by0 - 2 + fy;
+        unsigned long long bits = 0;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const int gx = bx0 - 2 + half * 32 + lane;
+          bool okf = true;
+          if ((half == 0 || lane < 4) && gx >= 0 && gy >= 0 && gx < a.cols && gy < a.rows) {
+            float u, v;
+            map_xy(m, (float)gx, (float)gy, u, v);
+            okf = valid255(INTERP, u, v, a.src_cols, a.src_rows, s_itab);
+          }
+          bits |= (unsigned long long)__ballot_sync(0xffffffffu, okf) << (32 * half);
         }
-        s_flag[fy][fxx] = okf;
+        if (lane == 0) s_hmask[fy] = bits & (bits >> 1) & (bits >> 2) & (bits >> 3) & (bits >> 4);
       }
     }
     cp_async_wait<1>();            // frame j's group has landed (frame j+1's may still be in flight)
@@ -557,14 +563,24 @@ __global__ void __launch_bounds__(TW * SWARPS) k_fused_staged(const __grid_const
       const unsigned char *sf = s_f[buf];
       const float *sg = s_g[buf];
       if (RING) {
+        RollS<INTERP> R;
+        R.ix = INT_MIN; R.iy = INT_MIN; R.pf = sf; R.pw = sg;
+        const unsigned long long *hm = &s_hmask[warp * GR];
+        unsigned long long m0 = hm[0], m1 = hm[1], m2 = hm[2], m3 = hm[3];
 #pragma unroll 1
-        for (int k = 0; k < nrow; ++k) {
-          bool ok = true;
+        for (int k = 0; k < GR; k += N) {
 #pragma unroll
-          for (int dy = 0; dy < 5; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 5; ++dx) ok = ok && s_flag[warp * GR + k + dy][lane + dx];
-          ring_pixel_s<DEPTH, INTERP, WEIGHTS, MT>(cm, (float)(y0 + k), sf, sg, a, plan, s_cubic, ok, s_acc0 + k * TW, s_w0 + k * TW);
+          for (int jj = 0; jj < N; ++jj) {
+            const unsigned long long m4 = k + jj < GR ? hm[k + jj + 4] : 0ull;
+            const bool ok = ((m0 & m1 & m2 & m3 & m4) >> lane) & 1ull;
+            m0 = m1; m1 = m2; m2 = m3; m3 = m4;
+            if (k + jj < nrow) {
+              if (jj == 0) roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 0>(R, cm, (float)(y0 + k), sf, sg, a.scale, plan, s_cubic, s_acc0 + k * TW, s_w0 + k * TW, ok);
+              if (jj == 1) roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 1 % N>(R, cm, (float)(y0 + k + 1), sf, sg, a.scale, plan, s_cubic, s_acc0 + (k + 1) * TW, s_w0 + (k + 1) * TW, ok);
+              if (jj == 2) roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 2 % N>(R, cm, (float)(y0 + k + 2), sf, sg, a.scale, plan, s_cubic, s_acc0 + (k + 2) * TW, s_w0 + (k + 2) * TW, ok);
+              if (jj == 3) roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 3 % N>(R, cm, (float)(y0 + k + 3), sf, sg, a.scale, plan, s_cubic, s_acc0 + (k + 3) * TW, s_w0 + (k + 3) * TW, ok);
+            }
+          }
         }
       } else {
         RollS<INTERP> R;
@@ -605,7 +621,7 @@ __global__ void __launch_bounds__(TW * SWARPS) k_fused_staged(const __grid_const
 
 template <int DEPTH, int INTERP, bool WEIGHTS, int MT>
 void launch_staged_ring(const WarpAccArgs &a, const Tables &tab, const TileList &tl, int nring, cudaStream_t s) {
-  const dim3 block(TW * SWARPS);
+  const dim3 block(TW * SWARPS), ring_block(TW * RING_WARPS);
   // The border ring (few, heavier CTAs) runs on a side stream so that it overlaps the interior tiles; the two
   // kernels write disjoint accumulator tiles.
   cudaStream_t ring_stream = s;
@@ -614,7 +630,13 @@ void launch_staged_ring(const WarpAccArgs &a, const Tables &tab, const TileList 
     cudaEventRecord(static_cast<cudaEvent_t>(a.ev_fork), s);
     cudaStreamWaitEvent(ring_stream, static_cast<cudaEvent_t>(a.ev_fork), 0);
   }
-  k_fused_staged<DEPTH, INTERP, WEIGHTS, MT, true><<<nring, block, 0, ring_stream>>>(a, tab, tl);
+  const int ring_smem = INTERP == SSK_INTER_CUBIC ? kItabBytes : 0;
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set && ring_smem) {
+    cudaFuncSetAttribute(k_fused_staged<DEPTH, INTERP, WEIGHTS, MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_smem);
+    attr_set = true;
+  }
+  k_fused_staged<DEPTH, INTERP, WEIGHTS, MT, true><<<nring, ring_block, ring_smem, ring_stream>>>(a, tab, tl);
   count_launch();
   if (a.side_stream) cudaEventRecord(static_cast<cudaEvent_t>(a.ev_join), ring_stream);
   k_fused_staged<DEPTH, INTERP, WEIGHTS, MT, false><<<dim3(tl.ntx - 2, tl.nty - 2), block, 0, s>>>(a, tab, tl);

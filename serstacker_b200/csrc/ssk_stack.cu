@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstring>
 #include <new>
+#include <cstdlib>
 #include "ssk_engine.cuh"
 
 using namespace ssk;
@@ -302,6 +303,7 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n) {
   a.use_weights = weighted ? 1 : 0;
   a.stage_aligned = h->frames_aligned ? 1 : 0;
   a.side_stream = h->side; a.ev_fork = h->ev_fork; a.ev_join = h->ev_join;
+  if (getenv("SSK_NO_SIDE_STREAM")) a.side_stream = nullptr;   // tuning knob: border-ring kernel in stream order
   {
     ssk_transform t0;
     make_transform(&t0, h->o.enable_registration ? ro.motion_type : SSK_MOTION_TRANSLATION);
