@@ -35,10 +35,12 @@ WORKLOAD = "config#2: 1920x1080 mono32F, ECCH(IC-LM, affine, translation-first, 
 # ------------------------------------------------------------------------------------------------------------
 # synthetic frames (torch on the GPU: data generation only, not part of the measured path)
 # ------------------------------------------------------------------------------------------------------------
-def make_frames_gpu(n, seed, device, radius=400.0):
+def make_frames_gpu(n, seed, device, radius=400.0, scene_seed=2):
+    """Synthetic planetary sequence: one scene (scene_seed: belts, spots) seen through per-frame jitter, defocus and
+    noise (seed).  Ranks share the scene - they stack shards of the same sequence - and differ in the jitter."""
     import torch
     g = torch.Generator(device="cpu").manual_seed(seed)
-    rng = np.random.default_rng(seed)
+    rng = np.random.default_rng(scene_seed)
     yy, xx = torch.meshgrid(torch.arange(H, device=device, dtype=torch.float32),
                             torch.arange(W, device=device, dtype=torch.float32), indexing="ij")
     cx, cy = (W - 1) / 2.0, (H - 1) / 2.0
@@ -46,6 +48,7 @@ def make_frames_gpu(n, seed, device, radius=400.0):
     spots = [(rng.uniform(-0.7, 0.7) * radius, rng.uniform(-0.7, 0.7) * radius, rng.uniform(2.0, 6.0) * radius / 150.0,
               rng.uniform(-0.3, 0.3)) for _ in range(40)]
     out = torch.empty((n, H, W), device=device, dtype=torch.float32)
+    rng = np.random.default_rng(seed + 7919)
     for i in range(n):
         if i == 0:
             A = np.array([[1.0, 0, 0], [0, 1.0, 0]])
@@ -154,6 +157,7 @@ def main():
     ap.add_argument("--pool", type=int, default=256, help="distinct synthetic frames resident per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=24, help="frames of the CPU baseline sample")
+    ap.add_argument("--seed", type=int, default=2, help="seed of the synthetic frame pool (rank r uses seed + 1000 r)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -199,7 +203,7 @@ def main():
 
     B = args.batch
     pool_n = max(args.pool, B + 1)
-    pool = make_frames_gpu(pool_n, 2 + 1000 * rank, dev)       # frame 0 = unjittered reference scene
+    pool = make_frames_gpu(pool_n, args.seed + 1000 * rank, dev)       # frame 0 = unjittered reference scene
     ref = make_frames_gpu(1, 2, dev)[0] if rank != 0 else pool[0]   # every rank uses the same reference frame
     if rank != 0:
         pool[0] = ref

@@ -308,9 +308,10 @@ class c_image_stacking_pipeline:
             capi.lib.ssk_stack_destroy(self._h)
             self._h = None
 
-    def set_reference(self, image, bpp=0):
+    def set_reference(self, image, bpp=0, mask=None):
         m = image if isinstance(image, ssk_mat) else mat(np.ascontiguousarray(image))
-        check(capi.lib.ssk_stack_set_reference(self._h, C.byref(m), None, bpp))
+        mm = mask if (mask is None or isinstance(mask, ssk_mat)) else mat(np.ascontiguousarray(mask))
+        check(capi.lib.ssk_stack_set_reference(self._h, C.byref(m), ref(mm), bpp))
         self._shape = (m.rows, m.cols, (m.type >> 3) + 1)
         self._bpp = bpp
 

@@ -245,10 +245,21 @@ static int ecch_image_to_gray(ssk_ecch *h, const ssk_mat *image, float *d_dst) {
 int ssk_ecch_set_reference_image(ssk_ecch *h, const ssk_mat *image, const ssk_mat *mask) {
   SSK_REQUIRE(h, "null handle");
   if (int e = check_mat(image, "c_ecch::set_reference_image")) return e;
-  SSK_REQUIRE(!mask, "c_ecch: reference masks are not implemented yet");
   if (int e = h->d_ptr.ensure((size_t)image->rows * image->cols * 4)) return e;
   if (int e = ecch_image_to_gray(h, image, h->d_ptr.as<float>())) return e;
-  if (int e = h->e.set_reference(h->d_ptr.as<float>(), image->rows, image->cols)) return e;
+  const uint8_t *d_mask = nullptr;
+  if (mask) {
+    int64_t step = 0;
+    const uint8_t *dm = nullptr;
+    if (int e = mask_to_device(mask, image->rows, image->cols, h->st_mask, h->stream, &dm, &step)) return e;
+    if (step != image->cols) {     // Ecch wants a dense mask
+      if (int e = h->st_mask2.ensure((size_t)image->rows * image->cols)) return e;
+      SSK_CUDA(cudaMemcpy2DAsync(h->st_mask2.p, image->cols, dm, step, image->cols, image->rows, cudaMemcpyDeviceToDevice, h->stream));
+      dm = h->st_mask2.as<uint8_t>();
+    }
+    d_mask = dm;
+  }
+  if (int e = h->e.set_reference(h->d_ptr.as<float>(), image->rows, image->cols, d_mask)) return e;
   SSK_CUDA(cudaStreamSynchronize(h->stream));
   return SSK_OK;
 }
@@ -330,11 +341,13 @@ int ssk_reg_destroy(ssk_reg *h) { delete h; return SSK_OK; }
 int ssk_reg_setup_reference_frame(ssk_reg *h, const ssk_mat *image, const ssk_mat *mask, int bpp) {
   SSK_REQUIRE(h, "null handle");
   if (int e = check_mat(image, "setup_reference_frame")) return e;
-  SSK_REQUIRE(!mask, "c_frame_registration: reference masks are not implemented yet");
   Img im;
   if (int e = to_device(image, h->staging, h->r.stream, &im, bpp)) return e;
   SSK_REQUIRE(im.cn == 1 || im.cn == 3, "c_frame_registration: 1 or 3 channel frames");
-  if (int e = h->r.setup_reference(im)) return e;
+  const uint8_t *d_mask = nullptr;
+  int64_t mstep = 0;
+  if (mask) { if (int e = mask_to_device(mask, image->rows, image->cols, h->st_mask, h->r.stream, &d_mask, &mstep)) return e; }
+  if (int e = h->r.setup_reference(im, d_mask, mstep)) return e;
   SSK_CUDA(cudaStreamSynchronize(h->r.stream));
   return SSK_OK;
 }

@@ -515,7 +515,9 @@ __device__ void pass_ic(Ctx &c, int lvl, bool lm_masks) {
   const EccLevel &L = c.cfg->lv[lvl];
   const float *__restrict__ cur = c.frame->pyr + L.cur_off;
   const float *__restrict__ ref = L.ref, *__restrict__ gxp = L.gx, *__restrict__ gyp = L.gy;
-  const uint8_t *__restrict__ rmask = L.refmask;
+  // c_ecc_inverse_compositional leaves the reference mask out of rhs / CMA (ecc2.cc:1752-1763: only the remapped
+  // current mask); c_ecclm_inverse_compositional ORs it in (ecc2.cc:1901-1904)
+  const uint8_t *__restrict__ rmask = lm_masks ? L.refmask : nullptr;
   const int cols = L.cols, rows = L.rows;
   const MapCoef m = S.map;
   const JCoef jc = S.jc;

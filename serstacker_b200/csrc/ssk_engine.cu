@@ -81,6 +81,20 @@ static const float kD5[5] = {1.f / 12.f, -2.f / 3.f, 0.f, 2.f / 3.f, -1.f / 12.f
 static const float kS3[3] = {0.25f, 0.5f, 0.25f};                                   // ecc2.cc:149
 
 // ------------------------------------------------------------------------------------------------
+int mask_to_device(const ssk_mat *mask, int rows, int cols, DevBuf &staging, cudaStream_t s, const uint8_t **d_mask, int64_t *step) {
+  SSK_REQUIRE(mask && mask->data, "mask: null data");
+  SSK_REQUIRE(mask->type == SSK_8UC1, "mask must be CV_8UC1");
+  SSK_REQUIRE(mask->rows == rows && mask->cols == cols, "mask size differs from the image size");
+  if (mask->mem == SSK_MEM_DEVICE) {
+    *d_mask = static_cast<const uint8_t *>(mask->data); *step = mask->step;
+    return SSK_OK;
+  }
+  if (int e = staging.ensure((size_t)rows * cols)) return e;
+  SSK_CUDA(cudaMemcpy2DAsync(staging.p, cols, mask->data, mask->step, cols, rows, cudaMemcpyHostToDevice, s));
+  *d_mask = staging.as<uint8_t>(); *step = cols;
+  return SSK_OK;
+}
+
 Ecch::~Ecch() {}
 
 int Ecch::init(const ssk_ecch_options &o, cudaStream_t s) {
@@ -94,7 +108,7 @@ int Ecch::init(const ssk_ecch_options &o, cudaStream_t s) {
   return SSK_OK;
 }
 
-int Ecch::set_reference(const float *d_img, int rows, int cols) {
+int Ecch::set_reference(const float *d_img, int rows, int cols, const uint8_t *d_mask) {
   SSK_REQUIRE(opts.reference_smooth_sigma < 5.0 && opts.input_smooth_sigma < 5.0, "ECC smoothing sigma must be < 5");
   // number of levels: ecc2.cc:1009-1026
   const int min_image_size = std::max(4, opts.minimum_image_size);
@@ -154,6 +168,36 @@ int Ecch::set_reference(const float *d_img, int rows, int cols) {
     }
     if (int e = d_hp_trans.ensure(sizeof(EccHpCache))) return e;
     if (int e = d_hp_main.ensure(sizeof(EccHpCache))) return e;
+  }
+  // reference mask: pyramid by cv::resize(INTER_NEAREST) (c_ecch::downscale_image, ecc2.cc:972-982); the forward
+  // solvers erode it 5x5 (ecc2.cc:1211-1221, 1425-1431), the inverse-compositional ones use it as given and zero the
+  // reference gradients under it (ecc2.cc:162-166, 1855-1860)
+  have_ref_mask = d_mask != nullptr;
+  for (int l = 0; l < nlevels; ++l) rma[l] = (double)lw[l] * lh[l];
+  if (have_ref_mask) {
+    if (int e = ref_mask.ensure(pyr_floats)) return e;
+    if (int e = ref_mask_tmp.ensure((size_t)lw[0] * lh[0])) return e;
+    if (int e = d_count.ensure(sizeof(int) * kMaxLevels)) return e;
+    uint8_t *mp = ref_mask.as<uint8_t>();
+    SSK_CUDA(cudaMemcpyAsync(mp, d_mask, (size_t)lw[0] * lh[0], cudaMemcpyDeviceToDevice, stream));
+    for (int l = 1; l < nlevels; ++l)
+      if (int e = launch_resize_nearest_u8(mp + loff[l - 1], lh[l - 1], lw[l - 1], mp + loff[l], lh[l], lw[l], stream)) return e;
+    SSK_CUDA(cudaMemsetAsync(d_count.p, 0, sizeof(int) * kMaxLevels, stream));
+    for (int l = 0; l < nlevels; ++l) {
+      const int n = lw[l] * lh[l];
+      if (!ic) {   // erode in place through the scratch buffer
+        SSK_CUDA(cudaMemcpyAsync(ref_mask_tmp.p, mp + loff[l], n, cudaMemcpyDeviceToDevice, stream));
+        if (int e = launch_erode5_u8(ref_mask_tmp.as<uint8_t>(), lw[l], mp + loff[l], lw[l], lh[l], lw[l], 1, stream)) return e;
+      }
+      if (int e = launch_apply_refmask(mp + loff[l], n, ic ? ref_gx.as<float>() + loff[l] : nullptr,
+                                       ic ? ref_gy.as<float>() + loff[l] : nullptr, d_count.as<int>() + l, stream)) return e;
+    }
+    int counts[kMaxLevels];
+    SSK_CUDA(cudaMemcpyAsync(counts, d_count.p, sizeof(int) * kMaxLevels, cudaMemcpyDeviceToHost, stream));
+    SSK_CUDA(cudaStreamSynchronize(stream));
+    for (int l = 0; l < nlevels; ++l) rma[l] = (double)counts[l];
+  }
+  if (ic) {
     SSK_CUDA(cudaMemsetAsync(d_hp_trans.p, 0, sizeof(EccHpCache), stream));
     SSK_CUDA(cudaMemsetAsync(d_hp_main.p, 0, sizeof(EccHpCache), stream));
   }
@@ -176,11 +220,11 @@ int Ecch::build_config() {
     EccLevel &L = cfg.lv[l];
     L.cols = lw[l]; L.rows = lh[l];
     L.ref = ref_pyr.as<float>() + loff[l];
-    L.refmask = nullptr;
+    L.refmask = have_ref_mask ? ref_mask.as<uint8_t>() + loff[l] : nullptr;
     L.gx = ref_gx.p ? ref_gx.as<float>() + loff[l] : nullptr;
     L.gy = ref_gy.p ? ref_gy.as<float>() + loff[l] : nullptr;
     L.cur_off = loff[l];
-    L.RMA = (double)lw[l] * lh[l];
+    L.RMA = rma[l];
   }
   cfg.method = opts.method;
   cfg.interp = opts.interpolation;
@@ -401,7 +445,7 @@ static int ecc_image_size(const ssk_registration_options &o, int rows, int cols,
   return SSK_OK;
 }
 
-int Reg::setup_reference(const Img &frame) {
+int Reg::setup_reference(const Img &frame, const uint8_t *d_mask, int64_t mask_step) {
   SSK_REQUIRE(!(opts.ecc.normalization_scale > 0 && opts.ecc.normalization_noise > 0),
               "ecc_normalize (normalization_scale > 0) is not implemented");
   SSK_REQUIRE(!opts.ecc.replace_planetary_disk_with_mask, "replace_planetary_disk_with_mask is not implemented");
@@ -416,7 +460,17 @@ int Reg::setup_reference(const Img &frame) {
   } else {
     if (int e = launch_to_gray(frame, nullptr, d_ecc, nullptr, 1, stream)) return e;
   }
-  if (int e = ecch.set_reference(d_ecc, ecc_rows, ecc_cols)) return e;
+  const uint8_t *d_ecc_mask = nullptr;
+  if (d_mask) {
+    if (int e = mask_tmp.ensure((size_t)ecc_rows * ecc_cols)) return e;
+    if (ecc_rows != frame.rows) {   // scaleImage: pyrDown(mask) >= 250 (c_frame_registration.cc:237-241)
+      if (int e = launch_pyrdown_mask_u8(d_mask, mask_step, frame.rows, frame.cols, mask_tmp.as<uint8_t>(), ecc_rows, ecc_cols, 250, stream)) return e;
+    } else {
+      SSK_CUDA(cudaMemcpy2DAsync(mask_tmp.p, ecc_cols, d_mask, mask_step, ecc_cols, ecc_rows, cudaMemcpyDeviceToDevice, stream));
+    }
+    d_ecc_mask = mask_tmp.as<uint8_t>();
+  }
+  if (int e = ecch.set_reference(d_ecc, ecc_rows, ecc_cols, d_ecc_mask)) return e;
   have_current = false;
   return SSK_OK;
 }

@@ -47,6 +47,9 @@ struct DeviceImage {
 // ------------------------------------------------------------------------------------------------
 // c_ecch: reference pyramid + batched alignment of current images
 // ------------------------------------------------------------------------------------------------
+// Validates a CV_8UC1 mask of the given size and makes it available on the device (host data is staged, dense).
+int mask_to_device(const ssk_mat *mask, int rows, int cols, DevBuf &staging, cudaStream_t s, const uint8_t **d_mask, int64_t *step);
+
 class Ecch {
  public:
   ssk_ecch_options opts;
@@ -69,7 +72,8 @@ class Ecch {
   ~Ecch();
   int init(const ssk_ecch_options &o, cudaStream_t s);
   // reference: dense CV_32FC1 device image of level-0 size (already scaled to the ECC resolution)
-  int set_reference(const float *d_img, int rows, int cols);
+  // d_mask: dense CV_8UC1 reference mask of the same size on the device, or null
+  int set_reference(const float *d_img, int rows, int cols, const uint8_t *d_mask = nullptr);
   // scratch for `batch` frames in flight
   int reserve(int batch);
   // level-0 source images (dense CV_32FC1, device) of the frames of a batch -> smoothed pyramids
@@ -92,6 +96,9 @@ class Ecch {
   int build_config();
   int hp_mode_for_next_align() const;
   DevBuf ref_pyr, ref_gx, ref_gy, cur_pyr, src0, tmp;
+  DevBuf ref_mask, ref_mask_tmp, d_count;          // reference-mask pyramid (bytes, level l at loff[l]), erode scratch, counters
+  bool have_ref_mask = false;
+  double rma[kMaxLevels];                          // reference mask area per level
   DevBuf d_hp_trans, d_hp_main, d_frames, d_trace;
   int trace_capacity = 0;
   DevBuf d_lvl_ptrs, d_src0_ptrs, d_tmp_ptrs;    // per-level pointer tables for the batched kernels
@@ -141,7 +148,8 @@ class Reg {
   DevBuf d_one_ptr;                    // 1-entry pointer tables for the single-frame path
   ~Reg();
   int init(const ssk_registration_options &o, cudaStream_t s, bool own);
-  int setup_reference(const Img &frame);
+  // d_mask / mask_step: full-resolution CV_8UC1 reference mask on the device, or null
+  int setup_reference(const Img &frame, const uint8_t *d_mask = nullptr, int64_t mask_step = 0);
   // frames (device, common geometry) -> ECC images -> pyramids.  d_frame_ptrs: device array of frame pointers.
   int prepare(const Img &geom, const void *const *d_frame_ptrs, int batch);
   int register_batch(int batch);       // launches the ECC kernel; results in ecch.device_frames()
@@ -158,7 +166,7 @@ int host_scale_transform(ssk_transform *t, double f);
 struct ssk_ecch {
   ssk::Ecch e;
   cudaStream_t stream = nullptr;
-  ssk::DevBuf staging, d_ptr;
+  ssk::DevBuf staging, d_ptr, st_mask, st_mask2;
   ~ssk_ecch() { if (stream) cudaStreamDestroy(stream); }
 };
 

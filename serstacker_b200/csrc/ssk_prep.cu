@@ -304,6 +304,49 @@ __global__ void __launch_bounds__(256) k_erode5_u8(const uint8_t *src, int64_t s
   dst[(int64_t)y * dstep + x] = m;
 }
 
+
+// ---- reference masks -----------------------------------------------------------------------------
+// cv::pyrDown on CV_8UC1 (PyrDownInvoker with FixPtCast<uchar, 8>: integer taps, (sum + 128) >> 8, REFLECT101)
+// followed by cv::compare(>= thresh): scaleImage's mask branch (c_frame_registration.cc:237-241)
+__global__ void __launch_bounds__(256) k_pyrdown_mask_u8(const uint8_t *src, int64_t sstep, int rows, int cols, uint8_t *dst,
+                                                         int drows, int dcols, int thresh) {
+  const int ox = blockIdx.x * 32 + (threadIdx.x & 31), oy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (ox >= dcols || oy >= drows) return;
+  const int kw[5] = {1, 4, 6, 4, 1};
+  int sum = 0;
+#pragma unroll
+  for (int dy = 0; dy < 5; ++dy) {
+    const int yy = border_idx(2 * oy - 2 + dy, rows, SSK_BORDER_REFLECT101);
+    int rsum = 0;
+#pragma unroll
+    for (int dx = 0; dx < 5; ++dx) rsum += kw[dx] * src[(int64_t)yy * sstep + border_idx(2 * ox - 2 + dx, cols, SSK_BORDER_REFLECT101)];
+    sum += kw[dy] * rsum;
+  }
+  const int v = (sum + 128) >> 8;
+  dst[(int64_t)oy * dcols + ox] = v >= thresh ? 255 : 0;
+}
+
+// cv::resize(INTER_NEAREST) on CV_8UC1: sx = min(cvFloor(x * ifx), cols - 1), ifx = 1 / ((double)dcols / cols)
+__global__ void __launch_bounds__(256) k_resize_nearest_u8(const uint8_t *src, int rows, int cols, uint8_t *dst, int drows, int dcols,
+                                                           double ifx, double ify) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= dcols || y >= drows) return;
+  const int sx = min((int)floor(x * ifx), cols - 1), sy = min((int)floor(y * ify), rows - 1);
+  dst[(int64_t)y * dcols + x] = src[(int64_t)sy * cols + sx];
+}
+
+// gradients are zeroed where the reference mask is zero (ecc_differentiate, ecc2.cc:162-166); *count += #nonzero
+__global__ void __launch_bounds__(256) k_apply_refmask(const uint8_t *mask, int n, float *gx, float *gy, int *count) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  bool nz = false;
+  if (i < n) {
+    nz = mask[i] != 0;
+    if (!nz && gx) { gx[i] = 0.f; gy[i] = 0.f; }
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, nz);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, __popc(b));
+}
+
 }  // namespace
 
 int launch_pyrdown(const PyrDownArgs &a, cudaStream_t s) {
@@ -353,6 +396,28 @@ int launch_w1(const W1Args &a, cudaStream_t s) {
     k_w1_upsample<<<g2, 256, 0, s>>>(a, (double)a.cols / a.full_cols, (double)a.rows / a.full_rows);
     SSK_LAUNCH_CHECK();
   }
+  return SSK_OK;
+}
+
+int launch_pyrdown_mask_u8(const uint8_t *src, int64_t sstep, int rows, int cols, uint8_t *dst, int drows, int dcols, int thresh,
+                           cudaStream_t s) {
+  dim3 grid(div_up(dcols, 32), div_up(drows, 8));
+  k_pyrdown_mask_u8<<<grid, 256, 0, s>>>(src, sstep, rows, cols, dst, drows, dcols, thresh);
+  SSK_LAUNCH_CHECK();
+  return SSK_OK;
+}
+
+int launch_resize_nearest_u8(const uint8_t *src, int rows, int cols, uint8_t *dst, int drows, int dcols, cudaStream_t s) {
+  dim3 grid(div_up(dcols, 32), div_up(drows, 8));
+  const double fx = (double)dcols / cols, fy = (double)drows / rows;
+  k_resize_nearest_u8<<<grid, 256, 0, s>>>(src, rows, cols, dst, drows, dcols, 1.0 / fx, 1.0 / fy);
+  SSK_LAUNCH_CHECK();
+  return SSK_OK;
+}
+
+int launch_apply_refmask(const uint8_t *mask, int n, float *gx, float *gy, int *d_count, cudaStream_t s) {
+  k_apply_refmask<<<div_up(n, 256), 256, 0, s>>>(mask, n, gx, gy, d_count);
+  SSK_LAUNCH_CHECK();
   return SSK_OK;
 }
 

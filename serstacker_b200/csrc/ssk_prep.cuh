@@ -52,6 +52,12 @@ struct W1Args {
 int w1_num_blocks(int rows, int cols);
 int launch_w1(const W1Args &a, cudaStream_t s);
 
+// reference-mask helpers: 8U pyrDown + threshold, INTER_NEAREST resize, gradient masking + non-zero count
+int launch_pyrdown_mask_u8(const uint8_t *src, int64_t sstep, int rows, int cols, uint8_t *dst, int drows, int dcols, int thresh,
+                           cudaStream_t s);
+int launch_resize_nearest_u8(const uint8_t *src, int rows, int cols, uint8_t *dst, int drows, int dcols, cudaStream_t s);
+int launch_apply_refmask(const uint8_t *mask, int n, float *gx, float *gy, int *d_count, cudaStream_t s);
+
 // erode 5x5 / 8U helpers for user masks
 int launch_erode5_u8(const uint8_t *src, int64_t sstep, uint8_t *dst, int64_t dstep, int rows, int cols,
                      int border_replicate, cudaStream_t s);

@@ -172,7 +172,6 @@ int ssk_stack_destroy(ssk_stack *h) { delete h; return SSK_OK; }
 
 int ssk_stack_set_reference(ssk_stack *h, const ssk_mat *image, const ssk_mat *mask, int bpp) {
   SSK_REQUIRE(h && image && image->data, "ssk_stack_set_reference: null argument");
-  SSK_REQUIRE(!mask, "reference masks are not implemented yet");
   const int d = type_depth(image->type), cn = type_cn(image->type);
   SSK_REQUIRE(depth_bytes(d) && (cn == 1 || cn == 3), "frames must be 8U/16U/32F with 1 or 3 channels");
   h->rows = image->rows; h->cols = image->cols; h->type = image->type; h->bpp = bpp;
@@ -186,7 +185,10 @@ int ssk_stack_set_reference(ssk_stack *h, const ssk_mat *image, const ssk_mat *m
       SSK_CUDA(cudaMemcpy2DAsync(h->ref_staging.p, rowb, image->data, image->step, rowb, image->rows, cudaMemcpyHostToDevice, h->stream));
       im.data = h->ref_staging.p; im.step = (int64_t)rowb;
     }
-    if (int e = h->reg_h.r.setup_reference(im)) return e;
+    const uint8_t *d_mask = nullptr;
+    int64_t mstep = 0;
+    if (mask) { if (int e = mask_to_device(mask, image->rows, image->cols, h->reg_h.st_mask, h->stream, &d_mask, &mstep)) return e; }
+    if (int e = h->reg_h.r.setup_reference(im, d_mask, mstep)) return e;
     if (int e = h->reg_h.r.ecch.reserve(h->max_batch)) return e;
   }
   if (int e = stack_alloc_slots(h)) return e;

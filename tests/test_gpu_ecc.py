@@ -112,3 +112,75 @@ def test_low_correlation_frame_is_dropped(gpu):
     o = oreg.FrameRegistration(oo)
     o.setup_reference_frame(frames[0])
     assert o.register_frame(junk) is False
+
+
+def _disk_mask(w, h, rx, ry, cx=None, cy=None):
+    """Elliptical reference mask (planetary disk ROI), CV_8UC1 0/255."""
+    cx = (w - 1) / 2 if cx is None else cx
+    cy = (h - 1) / 2 if cy is None else cy
+    yy, xx = np.mgrid[0:h, 0:w]
+    return ((((xx - cx) / rx) ** 2 + ((yy - cy) / ry) ** 2 <= 1.0) * 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("method", METHODS)
+@pytest.mark.parametrize("motion", [0, 3])
+def test_ecch_reference_mask_matches_oracle(gpu, method, motion):
+    """c_ecch::set_reference_image(image, mask): mask pyramid by INTER_NEAREST, per-solver erosion, masked reference
+    gradients, RMA = countNonZero (ecc2.cc:972-1057, 1211-1221, 1425-1431, 1855-1860)."""
+    from serstacker_b200 import api
+    frames, _ = _seq(320, 240, 3, seed=51 + motion, rot=0.2 if motion else 0.0, scale=0.002 if motion else 0.0)
+    mask = _disk_mask(320, 240, 120, 90, cx=165, cy=118)
+    kw = dict(maxlevel=-1, minimum_image_size=16, epsx=0.05, max_iterations=30, update_step_scale=1.0)
+    ot = otf.create_image_transform(motion)
+    o = oecc.EccH(ot, method=method, **kw)
+    o.set_reference_image(frames[0], mask)
+    gt = api.create_image_transform(motion)
+    g = api.c_ecch(gt, method=method, **kw)
+    g.set_reference_image(frames[0], mask)
+    for f in frames[1:]:
+        ot.reset()
+        gt.set_parameters(ot.parameters())
+        o.align(f, None)
+        g.align(f)
+        p_o = ot.parameters().copy()
+        d = map_diff_px(motion, gt.parameters(), p_o, (320, 240))
+        if strict_case(motion, method):
+            assert g.num_iterations() == o.num_iterations, (g.num_iterations(), o.num_iterations, d)
+            assert d <= 1e-3, d
+        else:
+            ot.reset()
+            with dot_noise():
+                o.align(f, None)
+            env = map_diff_px(motion, ot.parameters(), p_o, (320, 240))
+            assert d <= max(1e-3, 4 * env), (d, env)
+    # the mask must matter: the unmasked alignment of the last frame follows a different trajectory
+    o2 = oecc.EccH(otf.create_image_transform(motion), method=method, **kw)
+    o2.set_reference_image(frames[0], None)
+    o2.align(frames[-1], None)
+    assert not np.array_equal(o2.transform.parameters(), p_o)
+
+
+@pytest.mark.parametrize("method", [oecc.ECC_ALIGN_INVERSE_COMPOSITIONAL_LM, oecc.ECC_ALIGN_LM])
+def test_register_frame_with_reference_mask(gpu, method):
+    """setup_reference_frame(image, mask): scaleImage's mask branch (pyrDown of the 8-bit mask, >= 250) feeds c_ecch
+    (c_frame_registration.cc:230-250, 565-719); the correlation gate uses the same mask (ecc2.cc:65-137)."""
+    from serstacker_b200 import api
+    frames, _ = _seq(401, 300, 4, seed=77, rot=0.15, scale=0.002, sigma_t=3.0)
+    mask = _disk_mask(401, 300, 150, 110)
+    oo = oreg.ImageRegistrationOptions(motion_type=3)
+    oo.ecc.ecc_method = method
+    oo.ecc.ecch_max_level = -1
+    oo.ecc.update_step_scale = 1.0 if method == oecc.ECC_ALIGN_LM else 1.5
+    o = oreg.FrameRegistration(oo)
+    o.setup_reference_frame(frames[0], mask)
+    g = api.c_frame_registration(api.registration_options(motion_type=3, ecc=dict(
+        ecc_method=method, ecch_max_level=-1, update_step_scale=oo.ecc.update_step_scale)))
+    g.setup_reference_frame(frames[0], mask)
+    for f in frames:
+        ok_o = o.register_frame(f)
+        ok_g = g.register_frame(f)
+        assert ok_o == ok_g
+        assert abs(g.status.rho - o.status.rho) <= 1e-4
+        if ok_o:
+            d = map_diff_px(3, g.image_transform_parameters(), o.image_transform.parameters(), (401, 300))
+            assert d <= 1e-3, (d, g.status.num_iterations, o.status.num_iterations)
