@@ -64,7 +64,18 @@ struct ssk_stack {
   cudaStream_t side = nullptr;           // border-ring kernel of the fused warp+accumulate stage
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   DevBuf ref_staging;
+  // host frames: sub-chunks of `host_chunk` frames rotate through `nsets` sets of frame slots; a copy stream uploads
+  // sub-chunk k+1 while sub-chunk k is processed
+  cudaStream_t copy_stream = nullptr;
+  static constexpr int kMaxSets = 8;
+  cudaEvent_t set_free[kMaxSets] = {}, set_full[kMaxSets] = {};
+  int host_chunk = 0, nsets = 1, set_pos = 0;
+  DevBuf rec_all;                        // registration records of the current max_batch chunk
+  PinnedBuf h_rec_all;
   ~ssk_stack() {
+    for (auto &e : set_free) if (e) cudaEventDestroy(e);
+    for (auto &e : set_full) if (e) cudaEventDestroy(e);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     for (auto &e : ring_ev) if (e) cudaEventDestroy(e);
     for (auto &e : ev) if (e) cudaEventDestroy(e);
     if (ev_fork) cudaEventDestroy(ev_fork);
@@ -94,6 +105,17 @@ static int stack_alloc_slots(ssk_stack *h) {
     if (!h->ring_ev[r]) SSK_CUDA(cudaEventCreateWithFlags(&h->ring_ev[r], cudaEventDisableTiming));
   }
   for (auto &e : h->ev) if (!e) SSK_CUDA(cudaEventCreate(&e));
+  if (int e = h->rec_all.ensure(sizeof(EccFrame) * B)) return e;
+  if (int e = h->h_rec_all.ensure(sizeof(EccFrame) * B)) return e;
+  // sub-chunk of host frames: large enough to keep the kernels efficient, small enough for >= 2 sets in flight
+  h->host_chunk = B >= 32 ? std::max(16, B / 4) : B;
+  if (const char *e = getenv("SSK_HOST_CHUNK")) { const int c = atoi(e); if (c >= 1 && c <= B) h->host_chunk = c; }
+  h->nsets = std::max(1, std::min<int>(ssk_stack::kMaxSets, B / h->host_chunk));
+  if (!h->copy_stream) {
+    SSK_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (auto &e : h->set_free) SSK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : h->set_full) SSK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   if (!h->side) {
     SSK_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
     SSK_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -198,7 +220,24 @@ int ssk_stack_set_reference(ssk_stack *h, const ssk_mat *image, const ssk_mat *m
   return SSK_OK;
 }
 
-static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n) {
+// Uploads `n` host frames into slot set `set` on the copy stream (after the set's previous user has finished).
+static int stack_upload(ssk_stack *h, const ssk_mat *frames, int n, int set) {
+  const int d = type_depth(h->type), cn = type_cn(h->type);
+  const size_t rowb = (size_t)h->cols * cn * depth_bytes(d);
+  SSK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->set_free[set], 0));
+  char *base = h->frame_slots.as<char>() + rowb * h->rows * (size_t)set * h->host_chunk;
+  for (int i = 0; i < n; ++i) {
+    SSK_REQUIRE(frames[i].mem == SSK_MEM_HOST, "frames of a call must share memory space");
+    SSK_CUDA(cudaMemcpy2DAsync(base + rowb * h->rows * i, rowb, frames[i].data, frames[i].step, rowb, h->rows,
+                               cudaMemcpyHostToDevice, h->copy_stream));
+  }
+  SSK_CUDA(cudaEventRecord(h->set_full[set], h->copy_stream));
+  return SSK_OK;
+}
+
+// One chunk of frames through the per-frame loop.  set >= 0: host frames already being uploaded into slot set `set`;
+// set < 0: device frames.  The registration records land in rec_all[rec_off ...].
+static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int set, int rec_off) {
   const int d = type_depth(h->type), cn = type_cn(h->type);
   const size_t rowb = (size_t)h->cols * cn * depth_bytes(d);
   cudaStream_t s = h->stream;
@@ -223,12 +262,9 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n) {
     d_frame_ptrs = h->d_user_ptrs[r].as<const void *>();
     geom.step = frames[0].step;
   } else {
-    for (int i = 0; i < n; ++i) {
-      SSK_REQUIRE(frames[i].mem == SSK_MEM_HOST, "frames of a call must share memory space");
-      SSK_CUDA(cudaMemcpy2DAsync(h->frame_slots.as<char>() + rowb * h->rows * i, rowb, frames[i].data, frames[i].step, rowb, h->rows,
-                                 cudaMemcpyHostToDevice, s));
-    }
-    d_frame_ptrs = h->d_slot_ptrs.as<const void *>();
+    SSK_REQUIRE(set >= 0, "internal: host frames without a slot set");
+    SSK_CUDA(cudaStreamWaitEvent(s, h->set_full[set], 0));
+    d_frame_ptrs = h->d_slot_ptrs.as<const void *>() + (size_t)set * h->host_chunk;
     geom.step = (int64_t)rowb;
   }
   SSK_CUDA(cudaEventRecord(h->ev[0], s));
@@ -314,6 +350,10 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n) {
   a.acc = h->acc_h.a.acc.as<float>(); a.wacc = h->acc_h.a.wacc.as<float>();
   if (int e = launch_warp_accumulate(a, h->tab, s)) return e;
   SSK_CUDA(cudaEventRecord(h->ev[4], s));
+  if (set >= 0) SSK_CUDA(cudaEventRecord(h->set_free[set], s));
+  if (h->o.enable_registration)
+    SSK_CUDA(cudaMemcpyAsync(h->rec_all.as<EccFrame>() + rec_off, h->reg_h.r.ecch.device_frames(), sizeof(EccFrame) * n,
+                             cudaMemcpyDeviceToDevice, s));
   return SSK_OK;
 }
 
@@ -327,7 +367,24 @@ int ssk_stack_add_frames_async(ssk_stack *h, const ssk_mat *frames, int n, int b
   }
   for (int i0 = 0; i0 < n; i0 += h->max_batch) {
     const int m = std::min(h->max_batch, n - i0);
-    if (int e = stack_process_chunk(h, frames + i0, m)) return e;
+    if (frames[i0].mem == SSK_MEM_DEVICE) {
+      if (int e = stack_process_chunk(h, frames + i0, m, -1, 0)) return e;
+      continue;
+    }
+    // host frames: upload sub-chunk k+1 on the copy stream while sub-chunk k is processed
+    const int hc = h->host_chunk;
+    int set = h->set_pos;
+    if (int e = stack_upload(h, frames + i0, std::min(hc, m), set)) return e;
+    for (int k0 = 0; k0 < m; k0 += hc) {
+      const int mk = std::min(hc, m - k0);
+      const int next_set = (set + 1) % h->nsets;
+      if (k0 + hc < m) {
+        if (int e = stack_upload(h, frames + i0 + k0 + hc, std::min(hc, m - k0 - hc), next_set)) return e;
+      }
+      if (int e = stack_process_chunk(h, frames + i0 + k0, mk, set, k0)) return e;
+      set = next_set;
+    }
+    h->set_pos = set;
   }
   return SSK_OK;
 }
@@ -348,9 +405,9 @@ int ssk_stack_add_frames(ssk_stack *h, const ssk_mat *frames, int n, int bpp, ss
     const int m = std::min(h->max_batch, n - i0);
     if (int e = ssk_stack_add_frames_async(h, frames + i0, m, bpp)) return e;
     if (h->o.enable_registration && (transforms_out || status_out)) {
-      if (int e = h->reg_h.r.ecch.download_frames(m)) return e;
+      SSK_CUDA(cudaMemcpyAsync(h->h_rec_all.p, h->rec_all.p, sizeof(EccFrame) * m, cudaMemcpyDeviceToHost, h->stream));
       SSK_CUDA(cudaStreamSynchronize(h->stream));
-      const EccFrame *f = h->reg_h.r.ecch.host_frames();
+      const EccFrame *f = h->h_rec_all.as<EccFrame>();
       for (int i = 0; i < m; ++i) {
         if (transforms_out) transforms_out[i0 + i] = f[i].t;
         if (status_out) {

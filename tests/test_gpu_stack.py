@@ -170,3 +170,23 @@ def test_batched_equals_frame_by_frame(gpu):
         p.add_frames(frames, want_results=False)
         outs.append(p.compute()[0])
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
+def test_host_frames_pipelined_upload_equals_device_frames(gpu):
+    """Host frames go through sub-chunks whose upload overlaps the previous sub-chunk's processing (two slot sets at
+    max_batch 32): results - records and stack - must equal the unpipelined path, for a frame count that leaves a
+    ragged tail."""
+    from serstacker_b200 import api
+    frames, bpp = _config1_like(n=45, size=(160, 120))
+    outs, recs = [], []
+    for mb in (1, 32):
+        ro = api.registration_options(motion_type=3, interpolation=2, ecc=dict(ecc_method=3, ecch_max_level=-1))
+        p = api.c_image_stacking_pipeline(api.stack_options(registration=ro, accumulation_method=1, max_batch=mb))
+        p.set_reference(frames[0], bpp=bpp)
+        recs.append(p.add_frames(frames))
+        outs.append(p.compute())
+    assert [r["ok"] for r in recs[0]] == [r["ok"] for r in recs[1]]
+    for a, b in zip(recs[0], recs[1]):
+        assert np.array_equal(a["params"], b["params"]) and a["iterations"] == b["iterations"]
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][0], outs[1][0])
