@@ -242,3 +242,39 @@ def pyrdown_f32(src, dsize=None):
     vc = ((((c * f32(6)).astype(f32) + (a13 * f32(4)).astype(f32)).astype(f32) + u2).astype(f32) + d2).astype(f32)
     out = np.where((xs < 4 * (dw // 4))[None, :], vs, vc)
     return (out * f32(1.0 / 256.0)).astype(f32)
+
+
+def pyrup_f32(src, dsize):
+    """cv::pyrUp(CV_32FC1, dstsize=(w, h)) as cv2 4.13 evaluates it (bit-exact, tests/test_cvmodel.py):
+    row pass  even column 2x = (s[x-1] + 6 s[x]) + s[x+1] (x = 0: 6 s0 + 2 s1; x = w-1: s[w-2] + 7 s[w-1]),
+              odd column 2x+1 = 4 (s[x] + s[x+1]) (x = w-1: 8 s[w-1]); a dst wider than 2w repeats the last column;
+    col pass  even row = (6 r[y] + r[y-1]) + r[y+1], odd row = 4 (r[y] + r[y+1]) with r[-1] = r[1], r[h] = r[h-1];
+    the result is scaled by 1/64 (PyrUpInvoker, modules/imgproc/src/pyramids.cpp)."""
+    s = np.asarray(src, dtype=f32)
+    h, w = s.shape
+    dw, dh = dsize
+    xs = np.arange(w)
+    left = s[:, np.where(xs - 1 < 0, 1, xs - 1)]
+    right = s[:, np.minimum(xs + 1, w - 1)]
+    t0 = ((left + (s * f32(6)).astype(f32)).astype(f32) + right).astype(f32)
+    t1 = ((s + right).astype(f32) * f32(4)).astype(f32)
+    t0[:, 0] = ((s[:, 0] * f32(6)).astype(f32) + (s[:, 1] * f32(2)).astype(f32)).astype(f32)
+    t0[:, w - 1] = (s[:, w - 2] + (s[:, w - 1] * f32(7)).astype(f32)).astype(f32)
+    t1[:, w - 1] = (s[:, w - 1] * f32(8)).astype(f32)
+    R = np.zeros((h, 2 * w), f32)
+    R[:, 0::2] = t0
+    R[:, 1::2] = t1
+    if dw > 2 * w:
+        R = np.concatenate([R, R[:, -1:]], 1)
+    R = R[:, :dw]
+    ys = np.arange(h)
+    up = R[np.where(ys - 1 < 0, 1, ys - 1)]
+    dn = R[np.minimum(ys + 1, h - 1)]
+    d0 = (((R * f32(6)).astype(f32) + up).astype(f32) + dn).astype(f32)
+    d1 = ((R + dn).astype(f32) * f32(4)).astype(f32)
+    D = np.zeros((2 * h, dw), f32)
+    D[0::2] = d0
+    D[1::2] = d1
+    if dh > 2 * h:
+        D = np.concatenate([D, D[-1:]], 0)
+    return (D[:dh] * f32(1.0 / 64.0)).astype(f32)

@@ -446,8 +446,6 @@ static int ecc_image_size(const ssk_registration_options &o, int rows, int cols,
 }
 
 int Reg::setup_reference(const Img &frame, const uint8_t *d_mask, int64_t mask_step) {
-  SSK_REQUIRE(!(opts.ecc.normalization_scale > 0 && opts.ecc.normalization_noise > 0),
-              "ecc_normalize (normalization_scale > 0) is not implemented");
   SSK_REQUIRE(!opts.ecc.replace_planetary_disk_with_mask, "replace_planetary_disk_with_mask is not implemented");
   ref_rows = frame.rows; ref_cols = frame.cols;
   if (int e = ecc_image_size(opts, frame.rows, frame.cols, &ecc_rows, &ecc_cols)) return e;
@@ -470,6 +468,12 @@ int Reg::setup_reference(const Img &frame, const uint8_t *d_mask, int64_t mask_s
     }
     d_ecc_mask = mask_tmp.as<uint8_t>();
   }
+  if (normalize_enabled()) {
+    if (int e = d_one_ptr.ensure(sizeof(float *))) return e;
+    SSK_CUDA(cudaMemcpyAsync(d_one_ptr.p, &d_ecc, sizeof(float *), cudaMemcpyHostToDevice, stream));
+    SSK_CUDA(cudaStreamSynchronize(stream));   // &d_ecc is a stack address
+    if (int e = normalize(d_one_ptr.as<float *>(), 1, d_ecc_mask)) return e;
+  }
   if (int e = ecch.set_reference(d_ecc, ecc_rows, ecc_cols, d_ecc_mask)) return e;
   have_current = false;
   return SSK_OK;
@@ -487,7 +491,57 @@ int Reg::prepare(const Img &geom, const void *const *d_frame_ptrs, int batch) {
   } else {
     if (int e = launch_to_gray(geom, d_frame_ptrs, nullptr, ecch.level0_scratch_ptrs(), batch, stream)) return e;
   }
+  if (normalize_enabled()) {
+    if (int e = normalize(ecch.level0_scratch_ptrs(), batch, nullptr)) return e;
+  }
   return ecch.prepare_current(ecch.level0_scratch_ptrs(), batch);
+}
+
+// ecc_normalize (ecc2.cc:385-397): dst = src - ecc_upscale(ecc_downscale(src, level, BORDER_REPLICATE), src.size()),
+// zero under the mask.  The pyrDown chain of every frame lives in norm_buf; pyrUp results overwrite the chain on the
+// way back up and the last pyrUp is fused with the subtraction.
+int Reg::normalize(float *const *d_img_ptrs, int batch, const uint8_t *d_mask) {
+  const int L = opts.ecc.normalization_scale;
+  SSK_REQUIRE(L >= 1 && L <= 12, "ecc_normalize: normalization_scale 1..12");
+  int cw[16], ch[16];
+  int64_t off[16], total = 0;
+  cw[0] = ecc_cols; ch[0] = ecc_rows;
+  for (int k = 1; k <= L; ++k) {
+    cw[k] = (cw[k - 1] + 1) / 2; ch[k] = (ch[k - 1] + 1) / 2;
+    SSK_REQUIRE(std::min(cw[k], ch[k]) >= 2, "ecc_normalize: normalization_scale too deep for this image size");
+    off[k] = total;
+    total += ((int64_t)cw[k] * ch[k] + 63) & ~(int64_t)63;
+  }
+  if (batch > norm_capacity) {
+    if (int e = norm_buf.ensure((size_t)batch * total * 4)) return e;
+    std::vector<float *> tab((size_t)(L + 1) * batch);
+    for (int k = 1; k <= L; ++k)
+      for (int b = 0; b < batch; ++b) tab[(size_t)k * batch + b] = norm_buf.as<float>() + (int64_t)b * total + off[k];
+    if (int e = norm_ptrs.ensure(tab.size() * sizeof(float *))) return e;
+    SSK_CUDA(cudaStreamSynchronize(stream));
+    SSK_CUDA(cudaMemcpy(norm_ptrs.p, tab.data(), tab.size() * sizeof(float *), cudaMemcpyHostToDevice));
+    norm_capacity = batch;
+  }
+  float *const *lv = norm_ptrs.as<float *>();
+  const int cap = norm_capacity;
+  for (int k = 1; k <= L; ++k) {
+    PyrDownArgs pd = {};
+    pd.src.step = (int64_t)cw[k - 1] * 4; pd.src.rows = ch[k - 1]; pd.src.cols = cw[k - 1];
+    pd.src.depth = SSK_32F; pd.src.cn = 1; pd.src.scale = 1.f;
+    pd.src_ptrs = reinterpret_cast<const void *const *>(k == 1 ? d_img_ptrs : lv + (size_t)(k - 1) * cap);
+    pd.dst_ptrs = lv + (size_t)k * cap; pd.dst_rows = ch[k]; pd.dst_cols = cw[k]; pd.batch = batch; pd.post_scale = 1.f;
+    pd.border = SSK_BORDER_REPLICATE;
+    if (int e = launch_pyrdown(pd, stream)) return e;
+  }
+  for (int k = L; k >= 1; --k) {
+    PyrUpArgs pu = {};
+    pu.src_ptrs = lv + (size_t)k * cap; pu.rows = ch[k]; pu.cols = cw[k];
+    pu.dst_rows = ch[k - 1]; pu.dst_cols = cw[k - 1]; pu.batch = batch;
+    if (k == 1) { pu.dst_ptrs = d_img_ptrs; pu.minuend_ptrs = d_img_ptrs; pu.mask = d_mask; }
+    else pu.dst_ptrs = lv + (size_t)(k - 1) * cap;
+    if (int e = launch_pyrup(pu, stream)) return e;
+  }
+  return SSK_OK;
 }
 
 int Reg::register_batch(int batch) {

@@ -146,6 +146,11 @@ class Reg {
   ssk_transform default_transform;     // _image_transform_defaut_parameters
   DevBuf staging, mask_tmp, out_staging;
   DevBuf d_one_ptr;                    // 1-entry pointer tables for the single-frame path
+  DevBuf norm_buf, norm_ptrs;          // ecc_normalize: per-frame pyrDown chain + per-level pointer tables
+  int norm_capacity = 0;
+  bool normalize_enabled() const { return opts.ecc.normalization_scale > 0 && opts.ecc.normalization_noise > 0; }
+  // ecc_normalize (ecc2.cc:385-397) in place on `batch` dense ecc_rows x ecc_cols images; d_mask: dense mask or null
+  int normalize(float *const *d_img_ptrs, int batch, const uint8_t *d_mask);
   ~Reg();
   int init(const ssk_registration_options &o, cudaStream_t s, bool own);
   // d_mask / mask_step: full-resolution CV_8UC1 reference mask on the device, or null

@@ -71,12 +71,13 @@ __global__ void __launch_bounds__(256) k_pyrdown(const PyrDownArgs a) {
       h[r] = pd_hform(A.x, A.y, B.x, B.y, p4, hsimd);
     }
   } else {
+    const int border = a.border ? a.border : SSK_BORDER_REFLECT101;
     int xx[5];
 #pragma unroll
-    for (int c = 0; c < 5; ++c) xx[c] = border_idx(ix + c, src.cols, SSK_BORDER_REFLECT101);
+    for (int c = 0; c < 5; ++c) xx[c] = border_idx(ix + c, src.cols, border);
 #pragma unroll 1
     for (int r = 0; r < NR; ++r) {
-      const int yy = border_idx(iy + r, src.rows, SSK_BORDER_REFLECT101);
+      const int yy = border_idx(iy + r, src.rows, border);
       const float v = pd_hform(load_gray<DEPTH>(src, yy, xx[0]), load_gray<DEPTH>(src, yy, xx[1]), load_gray<DEPTH>(src, yy, xx[2]),
                                load_gray<DEPTH>(src, yy, xx[3]), load_gray<DEPTH>(src, yy, xx[4]), hsimd);
       // h[] must stay in registers: write through a fully unrolled select instead of a dynamic index
@@ -305,6 +306,45 @@ __global__ void __launch_bounds__(256) k_erode5_u8(const uint8_t *src, int64_t s
 }
 
 
+// ---- pyrUp ---------------------------------------------------------------------------------------
+// cv::pyrUp on CV_32FC1, bit-exact against cv2 4.13 (tests/test_cvmodel.py::test_pyrup_model):
+//   row pass : even column 2x = (s[x-1] + 6 s[x]) + s[x+1]   (x = 0: 6 s0 + 2 s1;  x = w-1: s[w-2] + 7 s[w-1])
+//              odd  column 2x+1 = 4 (s[x] + s[x+1])            (x = w-1: 8 s[w-1]); an extra last column repeats it
+//   col pass : even row 2y = (6 r[y] + r[y-1]) + r[y+1], odd row = 4 (r[y] + r[y+1]) with r[-1] = r[1], r[h] = r[h-1];
+//              result * 1/64
+__device__ __forceinline__ float pu_row(const float *__restrict__ p, int w, int ox) {
+  const int x = min(ox >> 1, w - 1);
+  const bool odd = (ox & 1) || (ox >> 1) >= w;
+  if (odd) return x == w - 1 ? __fmul_rn(p[x], 8.f) : __fmul_rn(__fadd_rn(p[x], p[x + 1]), 4.f);
+  if (x == 0) return __fadd_rn(__fmul_rn(p[0], 6.f), __fmul_rn(p[1], 2.f));
+  if (x == w - 1) return __fadd_rn(p[x - 1], __fmul_rn(p[x], 7.f));
+  return __fadd_rn(__fadd_rn(p[x - 1], __fmul_rn(p[x], 6.f)), p[x + 1]);
+}
+
+__global__ void __launch_bounds__(256) k_pyrup(const PyrUpArgs a) {
+  const int b = blockIdx.z;
+  const float *__restrict__ src = a.src_ptrs ? a.src_ptrs[b] : a.src;
+  float *__restrict__ dst = a.dst_ptrs ? a.dst_ptrs[b] : a.dst;
+  const int ox = blockIdx.x * 32 + (threadIdx.x & 31), oy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (ox >= a.dst_cols || oy >= a.dst_rows) return;
+  const int w = a.cols, h = a.rows;
+  const int y = min(oy >> 1, h - 1);
+  const bool odd = (oy & 1) || (oy >> 1) >= h;
+  const int yd = min(y + 1, h - 1), yu = y == 0 ? 1 : y - 1;
+  const float r1 = pu_row(src + (int64_t)y * w, w, ox), r2 = pu_row(src + (int64_t)yd * w, w, ox);
+  float v;
+  if (odd) v = __fmul_rn(__fadd_rn(r1, r2), 4.f);
+  else v = __fadd_rn(__fadd_rn(__fmul_rn(r1, 6.f), pu_row(src + (int64_t)yu * w, w, ox)), r2);
+  v = __fmul_rn(v, 1.0f / 64.0f);
+  const int64_t o = (int64_t)oy * a.dst_cols + ox;
+  if (a.minuend_ptrs || a.minuend) {
+    const float *m = a.minuend_ptrs ? a.minuend_ptrs[b] : a.minuend;
+    v = __fsub_rn(m[o], v);
+    if (a.mask && a.mask[o] == 0) v = 0.f;
+  }
+  dst[o] = v;
+}
+
 // ---- reference masks -----------------------------------------------------------------------------
 // cv::pyrDown on CV_8UC1 (PyrDownInvoker with FixPtCast<uchar, 8>: integer taps, (sum + 128) >> 8, REFLECT101)
 // followed by cv::compare(>= thresh): scaleImage's mask branch (c_frame_registration.cc:237-241)
@@ -396,6 +436,15 @@ int launch_w1(const W1Args &a, cudaStream_t s) {
     k_w1_upsample<<<g2, 256, 0, s>>>(a, (double)a.cols / a.full_cols, (double)a.rows / a.full_rows);
     SSK_LAUNCH_CHECK();
   }
+  return SSK_OK;
+}
+
+int launch_pyrup(const PyrUpArgs &a, cudaStream_t s) {
+  SSK_REQUIRE(a.cols >= 2 && a.rows >= 2, "pyrUp: source smaller than 2x2");
+  SSK_REQUIRE(abs(a.dst_cols - 2 * a.cols) <= 1 && abs(a.dst_rows - 2 * a.rows) <= 1, "pyrUp: bad dstsize");
+  dim3 grid(div_up(a.dst_cols, 32), div_up(a.dst_rows, 8), a.batch);
+  k_pyrup<<<grid, 256, 0, s>>>(a);
+  SSK_LAUNCH_CHECK();
   return SSK_OK;
 }
 

@@ -17,8 +17,20 @@ struct PyrDownArgs {
   int dst_rows, dst_cols;
   int batch;
   float post_scale;              // multiplies the result (lpg: 1/(1+dscale)); 1 = none
+  int border;                    // 0 (default): BORDER_REFLECT101 (cv::pyrDown's default); SSK_BORDER_REPLICATE: ecc_downscale
 };
 int launch_pyrdown(const PyrDownArgs &a, cudaStream_t s);
+
+// cv::pyrUp(src, dst, dstsize) on dense CV_32FC1 images (dst_cols in {2*cols - 1, 2*cols, 2*cols + 1}, same for rows),
+// optionally fused with ecc_normalize's subtraction: dst = minuend - pyrUp(src), zeroed where mask == 0.
+struct PyrUpArgs {
+  const float *src; const float *const *src_ptrs;
+  float *dst; float *const *dst_ptrs;
+  int rows, cols, dst_rows, dst_cols, batch;
+  const float *const *minuend_ptrs; const float *minuend;   // null: plain pyrUp
+  const uint8_t *mask;                                      // dense dst-size mask shared by the batch, or null
+};
+int launch_pyrup(const PyrUpArgs &a, cudaStream_t s);
 
 // cv::sepFilter2D(src, dst, CV_32F, kx, ky, anchor centre, BORDER_REPLICATE) on dense CV_32FC1 images.
 struct SepFilterArgs {

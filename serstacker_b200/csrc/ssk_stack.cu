@@ -284,7 +284,7 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
       const void *const *src_ptrs = d_frame_ptrs;
       float *const *dst_ptrs = h->d_half_ptrs.as<float *>();
       int l0 = 0;
-      if (h->o.enable_registration && h->reg_h.r.ecc_rows != h->rows) {
+      if (h->o.enable_registration && h->reg_h.r.ecc_rows != h->rows && !h->reg_h.r.normalize_enabled()) {
         // the first cv::pyrDown of the gray frame is exactly the ECC image scaleImage() just produced
         // (c_frame_registration.cc:236-237 vs c_local_variance_sharpness_measure.cc:36): reuse it
         const int nr = (cur.rows + 1) / 2, nc = (cur.cols + 1) / 2;

@@ -98,3 +98,20 @@ def test_pyrdown_model_bit_exact():
         src = rng.random((h, w)).astype(np.float32)
         ref = cv2.pyrDown(src) if ds is None else cv2.pyrDown(src, dstsize=ds)
         assert np.array_equal(ref, m.pyrdown_f32(src, ds)), (h, w, ds)
+
+
+def test_pyrup_model():
+    """cv::pyrUp restated (ecc_normalize / lpg up-scaling): bit-exact for even, odd and +1 destination sizes."""
+    rng = np.random.default_rng(9)
+    for (h, w, dh, dw) in [(30, 40, 60, 80), (31, 41, 61, 81), (31, 41, 62, 82), (17, 23, 33, 45), (64, 96, 128, 192), (5, 4, 9, 8)]:
+        a = rng.random((h, w)).astype(np.float32)
+        assert np.array_equal(m.pyrup_f32(a, (dw, dh)), cv2.pyrUp(a, dstsize=(dw, dh))), (h, w, dh, dw)
+
+
+def test_pyrdown_replicate_model_is_border_independent_inside():
+    """ecc_downscale uses BORDER_REPLICATE: interior outputs equal the REFLECT101 ones; only the border taps differ."""
+    rng = np.random.default_rng(10)
+    a = rng.random((41, 57)).astype(np.float32)
+    r = cv2.pyrDown(a, borderType=cv2.BORDER_REPLICATE)
+    d = cv2.pyrDown(a)
+    assert np.array_equal(r[1:-1, 1:-1], d[1:-1, 1:-1])

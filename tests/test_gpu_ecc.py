@@ -184,3 +184,40 @@ def test_register_frame_with_reference_mask(gpu, method):
         if ok_o:
             d = map_diff_px(3, g.image_transform_parameters(), o.image_transform.parameters(), (401, 300))
             assert d <= 1e-3, (d, g.status.num_iterations, o.status.num_iterations)
+
+
+@pytest.mark.parametrize("method", [oecc.ECC_ALIGN_INVERSE_COMPOSITIONAL_LM, oecc.ECC_ALIGN_FORWARD_ADDITIVE])
+@pytest.mark.parametrize("nscale,size", [(2, (400, 300)), (3, (401, 299))])
+def test_register_frame_with_ecc_normalize(gpu, method, nscale, size):
+    """ecc.normalization_scale > 0: ecc_normalize (pyrDown BORDER_REPLICATE chain, pyrUp back, subtract; ecc2.cc:385-397)
+    on the reference and on every current ECC image (c_frame_registration.cc:640-660, 790-810)."""
+    from serstacker_b200 import api
+    w, h = size
+    frames, _ = _seq(w, h, 4, seed=91, rot=0.1, scale=0.001, sigma_t=2.5)
+    mask = _disk_mask(w, h, w * 0.4, h * 0.4)
+    oo = oreg.ImageRegistrationOptions(motion_type=3)
+    oo.ecc.ecc_method = method
+    oo.ecc.ecch_max_level = -1
+    oo.ecc.normalization_scale = nscale
+    oo.ecc.normalization_noise = 0.01
+    oo.ecc.update_step_scale = 1.0
+    o = oreg.FrameRegistration(oo)
+    o.setup_reference_frame(frames[0], mask)
+    g = api.c_frame_registration(api.registration_options(motion_type=3, ecc=dict(
+        ecc_method=method, ecch_max_level=-1, normalization_scale=nscale, normalization_noise=0.01, update_step_scale=1.0)))
+    g.setup_reference_frame(frames[0], mask)
+    for f in frames:
+        ok_o = o.register_frame(f)
+        ok_g = g.register_frame(f)
+        assert ok_o == ok_g
+        assert abs(g.status.rho - o.status.rho) <= 1e-4
+        if ok_o:
+            p_o = o.image_transform.parameters().copy()
+            d = map_diff_px(3, g.image_transform_parameters(), p_o, size)
+            if method == oecc.ECC_ALIGN_INVERSE_COMPOSITIONAL_LM:
+                assert d <= 1e-3, (d, g.status.num_iterations, o.status.num_iterations)
+            else:
+                with dot_noise():
+                    o.register_frame(f)
+                env = map_diff_px(3, o.image_transform.parameters(), p_o, size)
+                assert d <= max(1e-3, 4 * env), (d, env)
