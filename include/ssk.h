@@ -258,6 +258,9 @@ SSK_API int ssk_acc_from_sum_form(ssk_acc *h, int accumulated_frames);
  * ------------------------------------------------------------------------------------------- */
 SSK_API int ssk_local_variance_map(const ssk_mat *image, int bpp, int dscale, int kradius, int uscale,
                                    ssk_mat *map /*CV_32FC1, full resolution*/, double *Q);
+/* lpg(image, k, p, dscale, uscale, map) (core/proc/lpg.cc:223-290; callers c_jdr_pipeline.cc:1211, c_sdr_pipeline.cc:1205):
+ * Laplacian + gradient energy weight map, CV_32FC1 of the image size.  Integer powers p only. */
+SSK_API int ssk_lpg(const ssk_mat *image, double k, double p, int dscale, int uscale, ssk_mat *map /*CV_32FC1*/);
 
 /* ---------------------------------------------------------------------------------------------
  * The fused per-frame loop of c_image_stacking_pipeline::process_input_sequence

@@ -281,6 +281,15 @@ def compute_local_variance_map(image, dscale=1, kradius=1, uscale=0, bpp=0):
     return q.value, out
 
 
+def lpg(image, k=2.0, p=2.0, dscale=2, uscale=6):
+    """lpg (core/proc/lpg.cc:223-290) -> CV_32FC1 weight map of the image size."""
+    image = np.ascontiguousarray(image)
+    out = np.zeros(image.shape[:2], dtype=f32)
+    mo = mat(out)
+    check(capi.lib.ssk_lpg(C.byref(mat(image)), float(k), float(p), int(dscale), int(uscale), C.byref(mo)))
+    return out
+
+
 def stack_options(**kw):
     o = capi.ssk_stack_options()
     capi.lib.ssk_stack_options_default(C.byref(o))

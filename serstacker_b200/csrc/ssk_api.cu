@@ -646,4 +646,88 @@ int ssk_local_variance_map(const ssk_mat *image, int bpp, int dscale, int kradiu
   return SSK_OK;
 }
 
+// lpg (core/proc/lpg.cc:223-290): float conversion by 1/maxval(depth), channel average, pdownscale(dscale) * 1/(1+dscale),
+// compute_lpg_5x5(k/(k+1), 1/(k+1), 1e-9), pdownscale(uscale - dscale) * (uscale - dscale), pow(p), pyrUp chain back
+// to the image size.
+int ssk_lpg(const ssk_mat *image, double k, double p, int dscale, int uscale, ssk_mat *map) {
+  if (int e = ensure_device()) return e;
+  if (int e = check_mat(image, "lpg")) return e;
+  if (int e = check_mat(map, "lpg map")) return e;
+  SSK_REQUIRE(map->type == SSK_32FC1 && map->rows == image->rows && map->cols == image->cols, "lpg: map must be CV_32FC1 of the image size");
+  SSK_REQUIRE(dscale >= 0 && dscale <= 10 && uscale >= 0 && uscale <= 12, "lpg: dscale 0..10, uscale 0..12");
+  SSK_REQUIRE(p >= 0 && p == std::floor(p) && p <= 16, "lpg: only integer powers p are implemented (cv::pow's iPow path)");
+  Scratch &sc = scratch();
+  if (int e = sc.init()) return e;
+  cudaStream_t s = sc.stream;
+  Img im;
+  if (int e = to_device(image, sc.a, s, &im, 0)) return e;
+  SSK_REQUIRE(im.cn == 1, "lpg: single-channel images (the callers pass the gray frame)");
+  // lpg.cc:184-200: integer samples are scaled by 1 / max value of the depth
+  im.scale = im.depth == SSK_8U ? (float)(1.0 / 255.0) : im.depth == SSK_16U ? (float)(1.0 / 65535.0) : 1.f;
+  const size_t n = (size_t)im.rows * im.cols;
+  if (int e = sc.b.ensure(n * 4 * 2)) return e;
+  float *bufA = sc.b.as<float>(), *bufB = bufA + n;
+  // pdownscale (lpg.cc:132-156): `level` pyrDowns, stopping once a side drops below 4
+  auto pdown = [&](Img cur, int level, float post, float **out, int *orows, int *ocols) -> int {
+    float *dst = static_cast<const void *>(cur.data) == bufA ? bufB : bufA;
+    if (std::min(cur.rows, cur.cols) < 4) { *out = nullptr; return SSK_OK; }
+    for (int l = 0; l < level; ++l) {
+      const int nr = (cur.rows + 1) / 2, nc = (cur.cols + 1) / 2;
+      PyrDownArgs pd = {};
+      pd.src = cur; pd.dst = dst; pd.dst_rows = nr; pd.dst_cols = nc; pd.batch = 1; pd.post_scale = 1.f;
+      if (int e = launch_pyrdown(pd, s)) return e;
+      cur.data = dst; cur.step = (int64_t)nc * 4; cur.rows = nr; cur.cols = nc; cur.depth = SSK_32F; cur.cn = 1; cur.scale = 1.f;
+      *out = dst;
+      dst = dst == bufA ? bufB : bufA;
+      if (std::min(nr, nc) < 4) break;
+    }
+    *orows = cur.rows; *ocols = cur.cols;
+    if (post != 1.f) return launch_scale_ipow(*out, (int64_t)cur.rows * cur.cols, post, true, 1, s);
+    return SSK_OK;
+  };
+  float *S = nullptr;
+  int r = im.rows, c = im.cols;
+  if (dscale > 0) {
+    if (int e = pdown(im, dscale, (float)(1.0 / (1 + dscale)), &S, &r, &c)) return e;
+  }
+  if (!S) {   // no down-scaling: plain float copy of the image
+    if (int e = launch_to_gray(im, nullptr, bufA, nullptr, 1, s)) return e;
+    S = bufA; r = im.rows; c = im.cols;
+    if (dscale > 0) { if (int e = launch_scale_ipow(S, (int64_t)r * c, (float)(1.0 / (1 + dscale)), true, 1, s)) return e; }
+  }
+  float *M = S == bufA ? bufB : bufA;
+  if (int e = launch_lpg5x5(S, r, c, M, (float)((float)(k / (k + 1)) * (25.f * 25.f)), (float)((float)(1.0 / (k + 1)) * ((float)(100.0 / 36.0) * (float)(100.0 / 36.0))), 1e-9f, s)) return e;
+  if (uscale > 0 && uscale > dscale) {
+    Img cur = {};
+    cur.data = M; cur.step = (int64_t)c * 4; cur.rows = r; cur.cols = c; cur.depth = SSK_32F; cur.cn = 1; cur.scale = 1.f;
+    float *D = nullptr;
+    if (int e = pdown(cur, uscale - dscale, (float)(uscale - dscale), &D, &r, &c)) return e;
+    if (D) M = D;
+    else { if (int e = launch_scale_ipow(M, (int64_t)r * c, (float)(uscale - dscale), true, 1, s)) return e; }
+  }
+  const int ip = (int)p;
+  if (ip != 0 && ip != 1) { if (int e = launch_scale_ipow(M, (int64_t)r * c, 1.f, false, ip, s)) return e; }
+  // pupscale (lpg.cc:158-182): the (w+1)/2 size chain from the image size down to the map size, walked back by cv::pyrUp
+  if (r != im.rows || c != im.cols) {
+    int cw[32], chh[32], nl = 0;
+    cw[0] = im.cols; chh[0] = im.rows;
+    while (true) {
+      const int nw = (cw[nl] + 1) / 2, nh = (chh[nl] + 1) / 2;
+      if (nw == c && nh == r) break;
+      SSK_REQUIRE(nw >= c && nh >= r && nl < 30, "lpg: invalid up-scaling size chain");
+      ++nl; cw[nl] = nw; chh[nl] = nh;
+    }
+    for (int l = nl; l >= 0; --l) {
+      float *dst = M == bufA ? bufB : bufA;
+      PyrUpArgs pu = {};
+      pu.src = M; pu.rows = r; pu.cols = c; pu.dst = dst; pu.dst_rows = chh[l]; pu.dst_cols = cw[l]; pu.batch = 1;
+      if (int e = launch_pyrup(pu, s)) return e;
+      M = dst; r = chh[l]; c = cw[l];
+    }
+  }
+  if (int e = from_device(M, (size_t)im.cols * 4, im.rows, map, s)) return e;
+  SSK_CUDA(cudaStreamSynchronize(s));
+  return SSK_OK;
+}
+
 }  // extern "C"

@@ -345,6 +345,49 @@ __global__ void __launch_bounds__(256) k_pyrup(const PyrUpArgs a) {
   dst[o] = v;
 }
 
+// ---- W2: lpg --------------------------------------------------------------------------------------
+// compute_lpg_5x5 (lpg.cc:60-129): alpha * laplacian^2 + beta * |gradient|^2 + eps with the 5x5 operators of the
+// reference, single-rounded float operations in its evaluation order; the two border rows / columns repeat the
+// nearest interior value.
+__global__ void __launch_bounds__(256) k_lpg5x5(const float *__restrict__ src, int rows, int cols, float *__restrict__ dst,
+                                                float alpha, float beta, float eps) {
+  const int ox = blockIdx.x * 32 + (threadIdx.x & 31), oy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (ox >= cols || oy >= rows) return;
+  const int x = min(max(ox, 2), cols - 3), y = min(max(oy, 2), rows - 3);
+  auto r = [&](int dy, int dx) { return __ldg(src + (int64_t)(y + dy) * cols + (x + dx)); };
+  auto add = [](float a, float b) { return __fadd_rn(a, b); };
+  auto sub = [](float a, float b) { return __fsub_rn(a, b); };
+  auto mul = [](float a, float b) { return __fmul_rn(a, b); };
+  auto col5 = [&](int dx) { return add(add(add(add(r(-2, dx), mul(2.f, r(-1, dx))), mul(4.f, r(0, dx))), mul(2.f, r(1, dx))), r(2, dx)); };
+  auto col3 = [&](int dx) { return add(add(r(-1, dx), mul(2.f, r(0, dx))), r(1, dx)); };
+  auto row5 = [&](int dy) { return add(add(add(add(r(dy, -2), mul(2.f, r(dy, -1))), mul(4.f, r(dy, 0))), mul(2.f, r(dy, 1))), r(dy, 2)); };
+  auto row3 = [&](int dy) { return add(add(r(dy, -1), mul(2.f, r(dy, 0))), r(dy, 1)); };
+  const float gx = add(sub(col5(2), col5(-2)), mul(2.f, sub(col3(1), col3(-1))));
+  const float gy = add(sub(row5(2), row5(-2)), mul(2.f, sub(row3(1), row3(-1))));
+  const float grad = add(mul(gx, gx), mul(gy, gy));
+  const float s4 = add(add(add(r(-1, 0), r(1, 0)), r(0, -1)), r(0, 1));
+  const float d4 = add(add(add(r(-1, -1), r(-1, 1)), r(1, -1)), r(1, 1));
+  const float f4 = add(add(add(r(-2, 0), r(2, 0)), r(0, -2)), r(0, 2));
+  const float lap = sub(sub(sub(mul(16.f, r(0, 0)), mul(2.f, s4)), d4), f4);
+  const float lapl = mul(lap, lap);
+  dst[(int64_t)oy * cols + ox] = add(add(mul(alpha, lapl), mul(beta, grad)), eps);
+}
+
+// v = cv::pow(v * scale, ipow) for integer ipow >= 1 (cv::multiply by a scalar, then iPow32f's square-and-multiply)
+__global__ void __launch_bounds__(256) k_scale_ipow(float *buf, int64_t n, float scale, int apply_scale, int ipow) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  float v = buf[i];
+  if (apply_scale) v = __fmul_rn(v, scale);
+  if (ipow > 1) {
+    float a = 1.f, b = v;
+    int p = ipow;
+    while (p > 1) { if (p & 1) a = __fmul_rn(a, b); b = __fmul_rn(b, b); p >>= 1; }
+    v = __fmul_rn(a, b);
+  }
+  buf[i] = v;
+}
+
 // ---- reference masks -----------------------------------------------------------------------------
 // cv::pyrDown on CV_8UC1 (PyrDownInvoker with FixPtCast<uchar, 8>: integer taps, (sum + 128) >> 8, REFLECT101)
 // followed by cv::compare(>= thresh): scaleImage's mask branch (c_frame_registration.cc:237-241)
@@ -436,6 +479,20 @@ int launch_w1(const W1Args &a, cudaStream_t s) {
     k_w1_upsample<<<g2, 256, 0, s>>>(a, (double)a.cols / a.full_cols, (double)a.rows / a.full_rows);
     SSK_LAUNCH_CHECK();
   }
+  return SSK_OK;
+}
+
+int launch_lpg5x5(const float *src, int rows, int cols, float *dst, float alpha, float beta, float eps, cudaStream_t s) {
+  SSK_REQUIRE(rows >= 5 && cols >= 5, "lpg: image smaller than 5x5 at the working scale");
+  dim3 grid(div_up(cols, 32), div_up(rows, 8));
+  k_lpg5x5<<<grid, 256, 0, s>>>(src, rows, cols, dst, alpha, beta, eps);
+  SSK_LAUNCH_CHECK();
+  return SSK_OK;
+}
+
+int launch_scale_ipow(float *buf, int64_t n, float scale, bool apply_scale, int ipow, cudaStream_t s) {
+  k_scale_ipow<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(buf, n, scale, apply_scale ? 1 : 0, ipow);
+  SSK_LAUNCH_CHECK();
   return SSK_OK;
 }
 

@@ -64,6 +64,10 @@ struct W1Args {
 int w1_num_blocks(int rows, int cols);
 int launch_w1(const W1Args &a, cudaStream_t s);
 
+// W2 (lpg.cc): 5x5 Laplacian/gradient energy; in-place scale + integer power
+int launch_lpg5x5(const float *src, int rows, int cols, float *dst, float alpha, float beta, float eps, cudaStream_t s);
+int launch_scale_ipow(float *buf, int64_t n, float scale, bool apply_scale, int ipow, cudaStream_t s);
+
 // reference-mask helpers: 8U pyrDown + threshold, INTER_NEAREST resize, gradient masking + non-zero count
 int launch_pyrdown_mask_u8(const uint8_t *src, int64_t sstep, int rows, int cols, uint8_t *dst, int drows, int dcols, int thresh,
                            cudaStream_t s);

@@ -84,3 +84,23 @@ def test_pyramid_bit_exact(gpu, size):
     g.set_reference_image(img)
     for l, e in enumerate(o.pyramid):
         assert np.array_equal(g.reference_image(l), e.reference_image), l
+
+
+@pytest.mark.parametrize("size", [(320, 240), (333, 251)])
+@pytest.mark.parametrize("k,p,dscale,uscale", [(2.0, 2.0, 2, 6), (2.0, 1.0, 0, 0), (1.0, 3.0, 1, 3), (3.0, 2.0, 2, 2)])
+def test_lpg_matches_oracle(gpu, size, k, p, dscale, uscale):
+    """W2: lpg (lpg.cc:223-290) = pdownscale, 5x5 Laplacian/gradient energy, pdownscale, pow, pyrUp chain."""
+    from serstacker_b200 import api
+    img, _ = _frame(size[0], size[1], 5)
+    want = ow.lpg(img, k, p, dscale, uscale)
+    got = api.lpg(img, k, p, dscale, uscale)
+    assert got.shape == want.shape
+    scale = float(np.abs(want).max())
+    assert np.abs(got - want).max() <= 2e-6 * scale, (np.abs(got - want).max(), scale)
+
+
+def test_lpg_rejects_fractional_power(gpu):
+    from serstacker_b200 import api, capi
+    img, _ = _frame(64, 48, 6)
+    with pytest.raises(capi.SskError):
+        api.lpg(img, 2.0, 1.5, 1, 2)
