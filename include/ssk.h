@@ -263,6 +263,19 @@ SSK_API int ssk_local_variance_map(const ssk_mat *image, int bpp, int dscale, in
 SSK_API int ssk_lpg(const ssk_mat *image, double k, double p, int dscale, int uscale, ssk_mat *map /*CV_32FC1*/);
 
 /* ---------------------------------------------------------------------------------------------
+ * Jovian derotation map: compute_ellipsoid_zrotation_remap (core/proc/feature2d/ellipsoid.cc:206-277), called by
+ * c_jovian_derotation_remap::compute_derotation_for_angle (c_jovian_derotation_remap.cc:47-60).
+ * R1 = pose of the ellipsoid as imaged, R2 = target pose (row-major 3x3, XYZscreen = R * XYZplanet); ebox_angle_deg and
+ * crop_box {x, y, width, height} are ellipsoid_bbox(center, A, B, C, R2).angle and ellipse_crop_box(ebox, size), which
+ * the caller computes (scalar geometry, ellipsoid.cc:16-84, 299-328).  Outputs: rmap CV_32FC2 (identity outside the
+ * disk, (-1,-1) on the hidden side), wmap CV_32FC1 (limb weight wscale*sqrt(1-r^2), remapped by rmap), rmask CV_8UC1.
+ * ------------------------------------------------------------------------------------------- */
+SSK_API int ssk_ellipsoid_zrotation_remap(int rows, int cols, const double center[2], const double axes[3],
+                                          const double R1[9], const double R2[9], double ebox_angle_deg,
+                                          const int crop_box[4], double wscale,
+                                          ssk_mat *rmap, ssk_mat *wmap, ssk_mat *rmask);
+
+/* ---------------------------------------------------------------------------------------------
  * The fused per-frame loop of c_image_stacking_pipeline::process_input_sequence
  * (c_image_stacking_pipeline.cc:1358-1862): weights -> register -> warp(frame, mask, weights) -> accumulate,
  * for a batch of frames per call.  This is the data-parallel hot path; results are identical to calling

@@ -290,6 +290,21 @@ def lpg(image, k=2.0, p=2.0, dscale=2, uscale=6):
     return out
 
 
+def compute_ellipsoid_zrotation_remap(size, center, axes, R1, R2, ebox_angle_deg, crop_box, wscale=1.0):
+    """compute_ellipsoid_zrotation_remap (core/proc/feature2d/ellipsoid.cc:206-277); size = (w, h), crop_box = (x, y, w, h)
+    -> (rmap HxWx2 float32, wmap HxW float32, rmask HxW uint8)."""
+    w, h = size
+    rmap = np.zeros((h, w, 2), f32)
+    wmap = np.zeros((h, w), f32)
+    rmask = np.zeros((h, w), np.uint8)
+    mr, mw, mm = mat(rmap), mat(wmap), mat(rmask)
+    d = lambda v, n: (C.c_double * n)(*[float(x) for x in np.asarray(v, dtype=np.float64).reshape(-1)])
+    check(capi.lib.ssk_ellipsoid_zrotation_remap(h, w, d(center, 2), d(axes, 3), d(R1, 9), d(R2, 9), float(ebox_angle_deg),
+                                                 (C.c_int * 4)(*[int(v) for v in crop_box]), float(wscale),
+                                                 C.byref(mr), C.byref(mw), C.byref(mm)))
+    return rmap, wmap, rmask
+
+
 def stack_options(**kw):
     o = capi.ssk_stack_options()
     capi.lib.ssk_stack_options_default(C.byref(o))

@@ -124,6 +124,8 @@ _sigs = {
     "ssk_acc_from_sum_form": (C.c_int, [C.c_void_p, C.c_int]),
     "ssk_local_variance_map": (C.c_int, [_P(ssk_mat), C.c_int, C.c_int, C.c_int, C.c_int, _P(ssk_mat), _P(C.c_double)]),
     "ssk_lpg": (C.c_int, [_P(ssk_mat), C.c_double, C.c_double, C.c_int, C.c_int, _P(ssk_mat)]),
+    "ssk_ellipsoid_zrotation_remap": (C.c_int, [C.c_int, C.c_int, _P(C.c_double), _P(C.c_double), _P(C.c_double), _P(C.c_double),
+                                                C.c_double, _P(C.c_int), C.c_double, _P(ssk_mat), _P(ssk_mat), _P(ssk_mat)]),
     "ssk_stack_options_default": (None, [_P(ssk_stack_options)]),
     "ssk_stack_create": (C.c_int, [_P(ssk_stack_options), _P(C.c_void_p)]),
     "ssk_stack_destroy": (C.c_int, [C.c_void_p]),

@@ -730,4 +730,51 @@ int ssk_lpg(const ssk_mat *image, double k, double p, int dscale, int uscale, ss
   return SSK_OK;
 }
 
+// compute_ellipsoid_zrotation_remap (ellipsoid.cc:206-277).  The scalar geometry of the bounding ellipse
+// (ellipsoid_bbox / ellipse_crop_box, ellipsoid.cc:16-84, 299-328) stays with the caller.
+int ssk_ellipsoid_zrotation_remap(int rows, int cols, const double center[2], const double axes[3], const double R1[9],
+                                  const double R2[9], double ebox_angle_deg, const int crop_box[4], double wscale,
+                                  ssk_mat *rmap, ssk_mat *wmap, ssk_mat *rmask) {
+  if (int e = ensure_device()) return e;
+  SSK_REQUIRE(center && axes && R1 && R2 && crop_box, "ellipsoid remap: null argument");
+  SSK_REQUIRE(rows > 0 && cols > 0 && axes[0] > 0 && axes[1] > 0 && axes[2] > 0, "ellipsoid remap: bad geometry");
+  if (int e = check_mat(rmap, "ellipsoid rmap")) return e;
+  if (int e = check_mat(wmap, "ellipsoid wmap")) return e;
+  if (int e = check_mat(rmask, "ellipsoid rmask")) return e;
+  SSK_REQUIRE(rmap->type == SSK_32FC2 && wmap->type == SSK_32FC1 && rmask->type == SSK_8UC1, "ellipsoid remap: rmap CV_32FC2, wmap CV_32FC1, rmask CV_8UC1");
+  SSK_REQUIRE(rmap->rows == rows && rmap->cols == cols && wmap->rows == rows && wmap->cols == cols && rmask->rows == rows && rmask->cols == cols,
+              "ellipsoid remap: output size differs from the frame size");
+  Scratch &sc = scratch();
+  if (int e = sc.init()) return e;
+  cudaStream_t s = sc.stream;
+  Tables tab;
+  if (int e = get_tables(&tab)) return e;
+  const size_t n = (size_t)rows * cols;
+  if (int e = sc.a.ensure(n * 8)) return e;
+  if (int e = sc.b.ensure(n * 4)) return e;
+  if (int e = sc.c.ensure(n)) return e;
+  if (int e = sc.d.ensure(n * 4)) return e;
+  EllipsoidArgs a = {};
+  a.rows = rows; a.cols = cols; a.cx = center[0]; a.cy = center[1]; a.A = axes[0]; a.B = axes[1]; a.C = axes[2];
+  for (int i = 0; i < 9; ++i) { a.R1[i] = R1[i]; a.R2[i] = R2[i]; }
+  a.bx = crop_box[0]; a.by = crop_box[1]; a.bw = crop_box[2]; a.bh = crop_box[3];
+  const double ang = ebox_angle_deg * 3.1415926535897932384626433832795 / 180;
+  a.ca = std::cos(ang); a.sa = std::sin(ang);
+  a.wscale = wscale;
+  a.rmap = sc.a.as<float2>(); a.wmap = sc.b.as<float>(); a.rmask = sc.c.as<uint8_t>();
+  if (int e = launch_ellipsoid_remap(a, s)) return e;
+  // cv::remap(wmap, wmap, rmap, INTER_LINEAR, BORDER_CONSTANT)
+  RemapArgs ra = {};
+  ra.src.data = sc.b.p; ra.src.step = (int64_t)cols * 4; ra.src.rows = rows; ra.src.cols = cols; ra.src.depth = SSK_32F; ra.src.cn = 1; ra.src.scale = 1.f;
+  ra.dst = sc.d.as<float>(); ra.dst_step = (int64_t)cols * 4; ra.rows = rows; ra.cols = cols;
+  ra.rmap = sc.a.as<float2>(); ra.rmap_step = (int64_t)cols * 8;
+  ra.interp = SSK_INTER_LINEAR; ra.border = SSK_BORDER_CONSTANT;
+  if (int e = launch_remap(ra, tab, s)) return e;
+  if (int e = from_device(sc.a.p, (size_t)cols * 8, rows, rmap, s)) return e;
+  if (int e = from_device(sc.d.p, (size_t)cols * 4, rows, wmap, s)) return e;
+  if (int e = from_device(sc.c.p, (size_t)cols, rows, rmask, s)) return e;
+  SSK_CUDA(cudaStreamSynchronize(s));
+  return SSK_OK;
+}
+
 }  // extern "C"

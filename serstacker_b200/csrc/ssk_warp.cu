@@ -126,6 +126,75 @@ int launch_remap_mask(const RemapMaskArgs &a, const Tables &tab, cudaStream_t s)
 }
 
 // ------------------------------------------------------------------------------------------------
+// D1: ellipsoid derotation map.  Double precision, single-rounded operations in the reference's evaluation order
+// (no FMA contraction), so that the hit / visibility decisions at the limb match the CPU code.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ double dm(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double da(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double ds(double a, double b) { return __dsub_rn(a, b); }
+
+__global__ void __launch_bounds__(256) k_ellipsoid_remap(const EllipsoidArgs a) {
+  const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (ix >= a.cols || iy >= a.rows) return;
+  const int64_t o = (int64_t)iy * a.cols + ix;
+  float2 m = make_float2((float)ix, (float)iy);
+  uint8_t mask = 0;
+  float w = 0.f;
+  if (iy >= a.by && iy <= a.by + a.bh && ix >= a.bx && ix <= a.bx + a.bw) {
+    // ellipsoid_from_cart2d (ellipsoid.h:107-158) under the target pose R2
+    const double *R = a.R2;
+    const double xs = ds((double)ix, a.cx), ys = ds((double)iy, a.cy);
+    const double x_stat = da(dm(R[0], xs), dm(R[3], ys));
+    const double y_stat = da(dm(R[1], xs), dm(R[4], ys));
+    const double z_stat = da(dm(R[2], xs), dm(R[5], ys));
+    const double rzx = R[6], rzy = R[7], rzz = R[8];
+    const double iA = __ddiv_rn(1.0, dm(a.A, a.A)), iB = __ddiv_rn(1.0, dm(a.B, a.B)), iC = __ddiv_rn(1.0, dm(a.C, a.C));
+    const double K2 = da(da(dm(dm(rzx, rzx), iA), dm(dm(rzy, rzy), iB)), dm(dm(rzz, rzz), iC));
+    const double K1 = da(da(dm(dm(x_stat, rzx), iA), dm(dm(y_stat, rzy), iB)), dm(dm(z_stat, rzz), iC));
+    const double K0 = ds(da(da(dm(dm(x_stat, x_stat), iA), dm(dm(y_stat, y_stat), iB)), dm(dm(z_stat, z_stat), iC)), 1.0);
+    const double disc = ds(dm(K1, K1), dm(K2, K0));
+    if (!(disc < 0.0)) {
+      mask = 255;
+      const double sq = __dsqrt_rn(disc);
+      const double zs1 = __ddiv_rn(ds(-K1, sq), K2), zs2 = __ddiv_rn(da(-K1, sq), K2);
+      const double zs = fmin(zs1, zs2);
+      // v = R2^T * (xs, ys, zs); vcam = R1 * v  (cv::Matx products: sums in index order)
+      const double vx = da(da(dm(R[0], xs), dm(R[3], ys)), dm(R[6], zs));
+      const double vy = da(da(dm(R[1], xs), dm(R[4], ys)), dm(R[7], zs));
+      const double vz = da(da(dm(R[2], xs), dm(R[5], ys)), dm(R[8], zs));
+      const double *Q = a.R1;
+      const double px = da(da(dm(Q[0], vx), dm(Q[1], vy)), dm(Q[2], vz));
+      const double py = da(da(dm(Q[3], vx), dm(Q[4], vy)), dm(Q[5], vz));
+      const double pz = da(da(dm(Q[6], vx), dm(Q[7], vy)), dm(Q[8], vz));
+      if (pz <= 0.0) m = make_float2((float)da(px, a.cx), (float)da(py, a.cy));
+      else m = make_float2(-1.f, -1.f);
+      // limb weight (ellipsoid.cc:250-272), rows / columns of the crop box proper
+      if (iy < a.by + a.bh && ix < a.bx + a.bw) {
+        const double dx = xs, dy = ys;
+        const double xx = dm(da(dm(dx, a.ca), dm(dy, a.sa)), __ddiv_rn(1.0, a.A));
+        const double yy = dm(da(dm(-dx, a.sa), dm(dy, a.ca)), __ddiv_rn(1.0, a.B));
+        const double rr = da(dm(xx, xx), dm(yy, yy));
+        if (rr <= 1.0) w = (float)dm(a.wscale, __dsqrt_rn(fmax(0.0, ds(1.0, rr))));
+      }
+    }
+  }
+  a.rmap[o] = m;
+  a.rmask[o] = mask;
+  a.wmap[o] = w;
+}
+
+}  // namespace
+
+int launch_ellipsoid_remap(const EllipsoidArgs &a, cudaStream_t s) {
+  dim3 grid(div_up(a.cols, 32), div_up(a.rows, 8));
+  k_ellipsoid_remap<<<grid, 256, 0, s>>>(a);
+  SSK_LAUNCH_CHECK();
+  return SSK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // accumulator kernels
 // ------------------------------------------------------------------------------------------------
 namespace {

@@ -58,6 +58,19 @@ struct RemapMaskArgs {
 };
 int launch_remap_mask(const RemapMaskArgs &a, const Tables &tab, cudaStream_t stream);
 
+// compute_ellipsoid_zrotation_remap (core/proc/feature2d/ellipsoid.cc:206-277): derotation map of a planetary
+// ellipsoid from pose R1 (as imaged) to pose R2 (target), disk mask and limb-darkening weight (before its remap).
+struct EllipsoidArgs {
+  int rows, cols;
+  double cx, cy, A, B, C;
+  double R1[9], R2[9];            // row-major 3x3, XYZscreen = R * XYZplanet
+  int bx, by, bw, bh;             // ellipse crop box (ellipse_crop_box of ellipsoid_bbox under R2)
+  double ca, sa;                  // cos / sin of the bounding ellipse angle
+  double wscale;
+  float2 *rmap; float *wmap; uint8_t *rmask;   // dense outputs
+};
+int launch_ellipsoid_remap(const EllipsoidArgs &a, cudaStream_t s);
+
 // c_weigthed_average::add without warp (c_frame_accumulation.cc:20-129)
 struct AccAddArgs {
   Img src;
