@@ -196,6 +196,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int NKEEP> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NKEEP)); }
 
 struct StagePlan { int staged, sx0, sy0, sxw; };   // staged: tile safe and footprint fits; sxw: weight-tile origin
+// Plans of all frames of a launch are computed once per CTA (one frame per thread) and kept in shared memory.
+constexpr int KPLAN = 256;                          // frames per launch (longer batches are split by the launcher)
+struct PackedPlan { short sx0, sy0, sxw, staged; }; // staged: 1 staged, 0 generic path, -1 frame dropped by registration
 
 // Footprint of the tile in the frame (block-uniform).  es / align describe the frame element type.
 __device__ __noinline__ StagePlan plan_stage(const MapCoef &m, int bx0, int by0, const WarpAccArgs &a, int align, int wd) {
@@ -473,6 +476,7 @@ __global__ void __launch_bounds__(TW * (RING ? RING_WARPS : SWARPS)) k_fused_sta
   // ring tiles: per row of the tile + 2-px halo, the horizontally eroded validity of the tile columns (bit x = AND of
   // the pre-erosion flags of columns x-2 .. x+2)
   __shared__ unsigned long long s_hmask[RING ? TH + 4 : 1];
+  __shared__ PackedPlan s_plan[KPLAN];
   // ring tiles: the fixed-point bicubic table behind the validity test (32 KB, dynamic shared memory) so that the
   // per-frame flag evaluation never waits on global memory
   extern __shared__ __align__(16) short s_itab[];
@@ -507,14 +511,26 @@ __global__ void __launch_bounds__(TW * (RING ? RING_WARPS : SWARPS)) k_fused_sta
     }
   }
 
+  // staging plans of every frame of the launch, one frame per thread
+  for (int jj = threadIdx.x; jj < a.njobs; jj += blockDim.x) {
+    PackedPlan pp = {0, 0, 0, -1};
+    if (a.jobs[jj].ok) {
+      StagePlan p = RING ? plan_stage_ring(a.jobs[jj].map, bx0, by0, a, G::ALIGN, G::WD) : plan_stage(a.jobs[jj].map, bx0, by0, a, G::ALIGN, G::WD);
+      if (WEIGHTS && !a.jobs[jj].weights) p.staged = 0;    // flat frame (no weight map): generic path
+      pp.sx0 = (short)p.sx0; pp.sy0 = (short)p.sy0; pp.sxw = (short)p.sxw; pp.staged = (short)p.staged;
+    }
+    s_plan[jj] = pp;
+  }
+  __syncthreads();
+  auto plan_of = [&](int jj) { const PackedPlan q = s_plan[jj]; StagePlan p; p.staged = q.staged; p.sx0 = q.sx0; p.sy0 = q.sy0; p.sxw = q.sxw; return p; };
+
   // software pipeline over the frames of the batch: while frame j is interpolated, frame j+1's footprint lands
   int j = 0;
-  while (j < a.njobs && !a.jobs[j].ok) ++j;
+  while (j < a.njobs && s_plan[j].staged < 0) ++j;
   int buf = 0;
   StagePlan plan = {0, 0, 0, 0};
   if (j < a.njobs) {
-    plan = RING ? plan_stage_ring(a.jobs[j].map, bx0, by0, a, G::ALIGN, G::WD) : plan_stage(a.jobs[j].map, bx0, by0, a, G::ALIGN, G::WD);
-    if (WEIGHTS && !a.jobs[j].weights) plan.staged = 0;    // flat frame (no weight map): generic path
+    plan = plan_of(j);
     if (plan.staged) { if (RING) issue_stage_ring<DEPTH>(a.jobs[j], plan, a, WEIGHTS, s_f[0], s_g[0]); else issue_stage<DEPTH>(a.jobs[j], plan, a, WEIGHTS, s_f[0], s_g[0]); }
   }
   cp_async_commit();
@@ -523,11 +539,10 @@ __global__ void __launch_bounds__(TW * (RING ? RING_WARPS : SWARPS)) k_fused_sta
 #pragma unroll 1
   while (j < a.njobs) {
     int jn = j + 1;
-    while (jn < a.njobs && !a.jobs[jn].ok) ++jn;
+    while (jn < a.njobs && s_plan[jn].staged < 0) ++jn;
     StagePlan plan_n = {0, 0, 0, 0};
     if (jn < a.njobs) {
-      plan_n = RING ? plan_stage_ring(a.jobs[jn].map, bx0, by0, a, G::ALIGN, G::WD) : plan_stage(a.jobs[jn].map, bx0, by0, a, G::ALIGN, G::WD);
-      if (WEIGHTS && !a.jobs[jn].weights) plan_n.staged = 0;
+      plan_n = plan_of(jn);
       if (plan_n.staged) { if (RING) issue_stage_ring<DEPTH>(a.jobs[jn], plan_n, a, WEIGHTS, s_f[buf ^ 1], s_g[buf ^ 1]); else issue_stage<DEPTH>(a.jobs[jn], plan_n, a, WEIGHTS, s_f[buf ^ 1], s_g[buf ^ 1]); }
     }
     cp_async_commit();
@@ -674,16 +689,21 @@ int launch_warp_accumulate(const WarpAccArgs &a_in, const Tables &tab, cudaStrea
   SSK_REQUIRE(a.depth == SSK_32F || a.depth == SSK_16U || a.depth == SSK_8U, "warp_accumulate: unsupported frame depth");
   a.stage_aligned = a.stage_aligned && (a.src_step % 16 == 0) && (a.w_step % 16 == 0);
   const int ntx = div_up(a.cols, TW), nty = div_up(a.rows, TH);
-  const bool staged = a.cn == 1 && ntx >= 3 && nty >= 3 &&
+  const bool staged = a.cn == 1 && ntx >= 3 && nty >= 3 && a.src_cols < 32000 && a.src_rows < 32000 &&
                       (a.map_type == MAP_AFFINE || a.map_type == MAP_TRANSLATION || a.map_type == MAP_EUCLIDEAN);
   TileList tl;
   tl.ntx = ntx; tl.nty = nty; tl.ring = staged ? 1 : 0;
   if (staged) {
     const int nring = 2 * ntx + 2 * (nty - 2);
-    if (a.depth == SSK_32F) launch_staged<SSK_32F>(a, tab, tl, nring, s);
-    else if (a.depth == SSK_16U) launch_staged<SSK_16U>(a, tab, tl, nring, s);
-    else launch_staged<SSK_8U>(a, tab, tl, nring, s);
-    SSK_LAUNCH_CHECK();
+    const FrameJob *jobs = a.jobs;
+    const int njobs = a.njobs;
+    for (int j0 = 0; j0 < njobs; j0 += KPLAN) {     // the per-CTA plan table holds KPLAN frames
+      a.jobs = jobs + j0; a.njobs = std::min(KPLAN, njobs - j0);
+      if (a.depth == SSK_32F) launch_staged<SSK_32F>(a, tab, tl, nring, s);
+      else if (a.depth == SSK_16U) launch_staged<SSK_16U>(a, tab, tl, nring, s);
+      else launch_staged<SSK_8U>(a, tab, tl, nring, s);
+      SSK_LAUNCH_CHECK();
+    }
   } else {
     // multi-channel frames, projective maps, tiny images: one thread per pixel
     k_fused_generic<<<ntx * nty * 4, 256, 0, s>>>(a, tab, tl);
