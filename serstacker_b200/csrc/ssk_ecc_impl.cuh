@@ -1102,7 +1102,7 @@ __device__ double correlation(Ctx &c) {
 }
 
 template <int METHOD, int TYPE>
-__global__ void __launch_bounds__(NT, 1) k_ecc(const __grid_constant__ EccConfig cfg, EccFrame *frames) {
+__global__ void __launch_bounds__(NT, 2) k_ecc(const __grid_constant__ EccConfig cfg, EccFrame *frames) {
   __shared__ Shared S;
   cg::cluster_group cluster = cg::this_cluster();
   Ctx c;

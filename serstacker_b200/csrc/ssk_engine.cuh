@@ -54,7 +54,7 @@ class Ecch {
  public:
   ssk_ecch_options opts;
   cudaStream_t stream = nullptr;
-  int cluster_size = 4;   // CTAs per frame; 4 measured best on config #2 (profiles/r01_summary.md)
+  int cluster_size = 8;   // CTAs per frame (SSK_ECC_CLUSTER overrides); 8 x 512 threads, 2 CTAs per SM measured best on config #2
 
   int nlevels = 0;
   int lw[kMaxLevels], lh[kMaxLevels];
