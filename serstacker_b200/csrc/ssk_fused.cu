@@ -237,20 +237,29 @@ __device__ __noinline__ void issue_stage(const FrameJob &job, const StagePlan &p
                                          unsigned char *s_f, float *s_g) {
   typedef StageGeom<DEPTH> G;
   constexpr int CPR = G::WD / G::ALIGN;            // 16-byte chunks per staged frame row
-#pragma unroll 1
-  for (int k = threadIdx.x; k < GSH * CPR; k += blockDim.x) {
+  // one 64-bit base per tile; chunk offsets stay in 32 bits (a staged window spans GSH rows)
+  const char *fbase = static_cast<const char *>(job.frame) + (int64_t)p.sy0 * a.src_step + (int64_t)p.sx0 * G::ES;
+  const unsigned sf = (unsigned)__cvta_generic_to_shared(s_f);
+  const int rows_left = a.src_rows - p.sy0, chunks_left = (a.src_cols - p.sx0) / G::ALIGN;   // in-bounds rows / whole chunks
+  const int step = (int)a.src_step;
+#pragma unroll
+  for (int i = 0; i < (GSH * CPR + TW * SWARPS - 1) / (TW * SWARPS); ++i) {
+    const int k = threadIdx.x + i * TW * SWARPS;
     const int r = k / CPR, q = k - r * CPR;
-    const int gy = p.sy0 + r, gx = p.sx0 + q * G::ALIGN;
-    if (gy < a.src_rows && gx + G::ALIGN <= a.src_cols)
-      cp_async16(s_f + r * G::ROWB + q * 16, static_cast<const char *>(job.frame) + (int64_t)gy * a.src_step + (int64_t)gx * G::ES);
+    if (k < GSH * CPR && r < rows_left && q < chunks_left)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sf + r * G::ROWB + q * 16), "l"(fbase + (r * step + q * 16)));
   }
   if (weighted) {
-#pragma unroll 1
-    for (int k = threadIdx.x; k < GSH * (WWD / 4); k += blockDim.x) {
+    const char *wbase = reinterpret_cast<const char *>(job.weights) + (int64_t)p.sy0 * a.w_step + (int64_t)p.sxw * 4;
+    const unsigned sg = (unsigned)__cvta_generic_to_shared(s_g);
+    const int wchunks_left = (a.src_cols - p.sxw) / 4;
+    const int wstep = (int)a.w_step;
+#pragma unroll
+    for (int i = 0; i < (GSH * (WWD / 4) + TW * SWARPS - 1) / (TW * SWARPS); ++i) {
+      const int k = threadIdx.x + i * TW * SWARPS;
       const int r = k / (WWD / 4), q = k - r * (WWD / 4);
-      const int gy = p.sy0 + r, gx = p.sxw + q * 4;
-      if (gy < a.src_rows && gx + 4 <= a.src_cols)
-        cp_async16(s_g + r * WWD + q * 4, reinterpret_cast<const char *>(job.weights) + (int64_t)gy * a.w_step + (int64_t)gx * 4);
+      if (k < GSH * (WWD / 4) && r < rows_left && q < wchunks_left)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sg + (r * WWD + q * 4) * 4), "l"(wbase + (r * wstep + q * 16)));
     }
   }
 }
@@ -462,7 +471,7 @@ __device__ __noinline__ StagePlan plan_stage_ring(const MapCoef &m, int bx0, int
 }
 
 template <int DEPTH, int INTERP, bool WEIGHTS, int MT, bool RING>
-__global__ void __launch_bounds__(TW * (RING ? RING_WARPS : SWARPS)) k_fused_staged(const __grid_constant__ WarpAccArgs a, const __grid_constant__ Tables tab,
+__global__ void __launch_bounds__(TW * (RING ? RING_WARPS : SWARPS), RING ? 1 : 6) k_fused_staged(const __grid_constant__ WarpAccArgs a, const __grid_constant__ Tables tab,
                                                                const TileList tl) {
   typedef StageGeom<DEPTH> G;
   constexpr int N = Taps<INTERP>::N;
