@@ -630,12 +630,13 @@ int ssk_local_variance_map(const ssk_mat *image, int bpp, int dscale, int kradiu
   }
   const int nb = w1_num_blocks(r, c);
   if (int e = sc.c.ensure((size_t)r * c * 4)) return e;
-  if (int e = sc.d.ensure((size_t)nb * 2 * 8 + 4 * 8)) return e;
+  if (int e = sc.d.ensure((size_t)nb * 2 * 8 + 4 * 8 + (size_t)(im.rows + im.cols) * sizeof(int2))) return e;
   if (int e = sc.e.ensure(n * 4)) return e;
   W1Args w = {};
   w.M = M; w.rows = r; w.cols = c; w.kradius = std::max(1, kradius); w.depth_scale = 20.0;
   w.gmap = sc.c.as<float>(); w.partials = sc.d.as<double>(); w.stats = sc.d.as<double>() + (size_t)nb * 2;
   w.out = map ? sc.e.as<float>() : nullptr; w.full_rows = im.rows; w.full_cols = im.cols; w.batch = 1;
+  w.axis_tab = reinterpret_cast<int2 *>(sc.d.as<double>() + (size_t)nb * 2 + 4);
   if (int e = launch_w1(w, s)) return e;
   double stats[4];
   SSK_CUDA(cudaMemcpyAsync(stats, w.stats, sizeof(stats), cudaMemcpyDeviceToHost, s));

@@ -246,41 +246,49 @@ __global__ void __launch_bounds__(256) k_w1_final(const W1Args a, int nblocks) {
   }
 }
 
-// cv::resize(map + 0.05 Q, full size, INTER_LINEAR) (c_local_variance_sharpness_measure.cc:176-184, 239-243)
+// cv::resize(map + 0.05 Q, full size, INTER_LINEAR) (c_local_variance_sharpness_measure.cc:176-184, 239-243).
+// The source index and fraction of an output column / row do not depend on the frame: a tiny kernel tabulates them
+// (fx = (float)((dx + 0.5) * scale - 0.5) in double, clamped like cv::resize), the up-sampling kernel reads them.
+__global__ void __launch_bounds__(256) k_w1_axis(int n_full, int n_small, double sc, int2 *tab) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n_full) return;
+  float f = (float)((i + 0.5) * sc - 0.5);
+  int s = (int)floorf(f);
+  f -= s;
+  if (s < 0) { f = 0; s = 0; }
+  if (s >= n_small - 1) { f = 0; s = n_small - 1; }
+  tab[i] = make_int2(s, __float_as_int(f));
+}
+
 // One thread per 4 consecutive output pixels (one 16-byte store when the row allows it).
-__global__ void __launch_bounds__(256) k_w1_upsample(const W1Args a, double scx, double scy) {
+__global__ void __launch_bounds__(256) k_w1_upsample(const W1Args a) {
   const int b = blockIdx.z;
   const float *__restrict__ g = a.gmap_ptrs ? a.gmap_ptrs[b] : a.gmap;
   float *__restrict__ out = a.out_ptrs ? a.out_ptrs[b] : a.out;
   const int x4 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4, y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x4 >= a.full_cols || y >= a.full_rows) return;
   const float add = (float)a.stats[b * 4 + 3];
-  const bool same = a.full_cols == a.cols && a.full_rows == a.rows;
-  float fy = (float)((y + 0.5) * scy - 0.5);
-  int sy = (int)floorf(fy);
-  fy -= sy;
-  if (sy < 0) { fy = 0; sy = 0; }
-  if (sy >= a.rows - 1) { fy = 0; sy = a.rows - 1; }
-  const int sy1 = min(sy + 1, a.rows - 1);
-  const float b0 = 1.f - fy, b1 = fy;
-  const float *__restrict__ g0 = g + (int64_t)sy * a.cols, *__restrict__ g1 = g + (int64_t)sy1 * a.cols;
   float v[4];
+  if (a.full_cols == a.cols && a.full_rows == a.rows) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int x = min(x4 + k, a.full_cols - 1);
-    if (same) { v[k] = __fadd_rn(__ldg(g + (int64_t)y * a.cols + x), add); continue; }
-    float fx = (float)((x + 0.5) * scx - 0.5);
-    int sx = (int)floorf(fx);
-    fx -= sx;
-    if (sx < 0) { fx = 0; sx = 0; }
-    if (sx >= a.cols - 1) { fx = 0; sx = a.cols - 1; }
-    const int sx1 = min(sx + 1, a.cols - 1);
-    const float a0 = 1.f - fx, a1 = fx;
-    const float v00 = __fadd_rn(__ldg(g0 + sx), add), v01 = __fadd_rn(__ldg(g0 + sx1), add);
-    const float v10 = __fadd_rn(__ldg(g1 + sx), add), v11 = __fadd_rn(__ldg(g1 + sx1), add);
-    const float r0 = __fadd_rn(__fmul_rn(v00, a0), __fmul_rn(v01, a1));
-    const float r1 = __fadd_rn(__fmul_rn(v10, a0), __fmul_rn(v11, a1));
-    v[k] = __fadd_rn(__fmul_rn(r0, b0), __fmul_rn(r1, b1));
+    for (int k = 0; k < 4; ++k) v[k] = __fadd_rn(__ldg(g + (int64_t)y * a.cols + min(x4 + k, a.cols - 1)), add);
+  } else {
+    const int2 *__restrict__ xt = a.axis_tab, *__restrict__ yt = a.axis_tab + a.full_cols;
+    const int2 ey = __ldg(yt + y);
+    const int sy = ey.x, sy1 = min(sy + 1, a.rows - 1);
+    const float b1 = __int_as_float(ey.y), b0 = 1.f - b1;
+    const float *__restrict__ g0 = g + sy * a.cols, *__restrict__ g1 = g + sy1 * a.cols;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int2 ex = __ldg(xt + min(x4 + k, a.full_cols - 1));
+      const int sx = ex.x, sx1 = min(sx + 1, a.cols - 1);
+      const float a1 = __int_as_float(ex.y), a0 = 1.f - a1;
+      const float v00 = __fadd_rn(__ldg(g0 + sx), add), v01 = __fadd_rn(__ldg(g0 + sx1), add);
+      const float v10 = __fadd_rn(__ldg(g1 + sx), add), v11 = __fadd_rn(__ldg(g1 + sx1), add);
+      const float r0 = __fadd_rn(__fmul_rn(v00, a0), __fmul_rn(v01, a1));
+      const float r1 = __fadd_rn(__fmul_rn(v10, a0), __fmul_rn(v11, a1));
+      v[k] = __fadd_rn(__fmul_rn(r0, b0), __fmul_rn(r1, b1));
+    }
   }
   float *o = out + (int64_t)y * a.full_cols + x4;
   if (x4 + 3 < a.full_cols && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
@@ -475,8 +483,15 @@ int launch_w1(const W1Args &a, cudaStream_t s) {
   k_w1_final<<<a.batch, 256, 0, s>>>(a, nblocks);
   SSK_LAUNCH_CHECK();
   if (a.out || a.out_ptrs) {
+    if (a.full_cols != a.cols || a.full_rows != a.rows) {
+      SSK_REQUIRE(a.axis_tab, "local variance map: axis table scratch missing");
+      k_w1_axis<<<div_up(a.full_cols, 256), 256, 0, s>>>(a.full_cols, a.cols, (double)a.cols / a.full_cols, a.axis_tab);
+      SSK_LAUNCH_CHECK();
+      k_w1_axis<<<div_up(a.full_rows, 256), 256, 0, s>>>(a.full_rows, a.rows, (double)a.rows / a.full_rows, a.axis_tab + a.full_cols);
+      SSK_LAUNCH_CHECK();
+    }
     dim3 g2(div_up(a.full_cols, 128), div_up(a.full_rows, 8), a.batch);
-    k_w1_upsample<<<g2, 256, 0, s>>>(a, (double)a.cols / a.full_cols, (double)a.rows / a.full_rows);
+    k_w1_upsample<<<g2, 256, 0, s>>>(a);
     SSK_LAUNCH_CHECK();
   }
   return SSK_OK;

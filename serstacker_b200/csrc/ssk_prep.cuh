@@ -60,6 +60,7 @@ struct W1Args {
   float *out; float *const *out_ptrs;             // full_rows x full_cols per frame (dense)
   int full_rows, full_cols;
   int batch;
+  int2 *axis_tab;                                 // scratch [full_cols + full_rows]: per output column / row source index + fraction
 };
 int w1_num_blocks(int rows, int cols);
 int launch_w1(const W1Args &a, cudaStream_t s);
