@@ -292,6 +292,9 @@ def main():
     bytes_kernel = NPIX * (4 + 4) * B + NPIX * 16    # frame + weight map read per frame; mean + weight RMW once per batch
     bytes_survey = NPIX * 24 * B                     # N*(4 + 8 + 8 + 4) per frame (un-batched RMW)
     achieved = bytes_kernel / t_k / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of the two fused launches (border ring + interior) of one 64-frame
+    # batch, from profiles/r01_fused_warp_accumulate_ncu.txt (ncu --set full); only valid for that batch size
+    traffic = 1.0555e9 + 22.5e6 + 0.1191e9 + 4.9e6 if B == 64 else None
 
     # ---------------- CPU baseline (rank 0, N=1 only) ---------------------------------------------------
     cpu = None
@@ -317,9 +320,9 @@ def main():
                     "d2h_bytes_per_step": B * (C.sizeof(capi.ssk_transform) + C.sizeof(capi.ssk_ecc_status)) + 4,
                     "steps": e2e_steps, "registered_frames": ok_frames},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "k_warp_acc (fused bicubic warp + mask + weights + running weighted mean, one launch per batch)",
+            "roofline": {"kernel": "k_fused_staged (fused bicubic warp + eroded mask + weight warp + running weighted mean; interior + border-ring launch per batch)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "launch_ms": stage[3], "frames_per_launch": B,
+                         "traffic": traffic, "peak_source": peak_src, "launch_ms": stage[3], "frames_per_launch": B,
                          "algorithmic_bytes_per_launch": bytes_kernel,
                          "frac_with_survey_bytes": bytes_survey / t_k / 1e9 / peak},
             "stage_ms_per_batch": {"prep": stage[0], "weights": stage[1], "ecc": stage[2], "warp_accumulate": stage[3]},

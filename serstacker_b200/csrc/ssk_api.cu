@@ -630,7 +630,7 @@ int ssk_local_variance_map(const ssk_mat *image, int bpp, int dscale, int kradiu
   }
   const int nb = w1_num_blocks(r, c);
   if (int e = sc.c.ensure((size_t)r * c * 4)) return e;
-  if (int e = sc.d.ensure((size_t)nb * 2 * 8 + 4 * 8 + (size_t)(im.rows + im.cols) * sizeof(int2))) return e;
+  if (int e = sc.d.ensure((size_t)nb * 2 * 8 + 4 * 8 + (size_t)(im.rows + im.cols + 8) * sizeof(int2) + 16)) return e;
   if (int e = sc.e.ensure(n * 4)) return e;
   W1Args w = {};
   w.M = M; w.rows = r; w.cols = c; w.kradius = std::max(1, kradius); w.depth_scale = 20.0;

@@ -249,7 +249,8 @@ __global__ void __launch_bounds__(256) k_w1_final(const W1Args a, int nblocks) {
 // cv::resize(map + 0.05 Q, full size, INTER_LINEAR) (c_local_variance_sharpness_measure.cc:176-184, 239-243).
 // The source index and fraction of an output column / row do not depend on the frame: a tiny kernel tabulates them
 // (fx = (float)((dx + 0.5) * scale - 0.5) in double, clamped like cv::resize), the up-sampling kernel reads them.
-__global__ void __launch_bounds__(256) k_w1_axis(int n_full, int n_small, double sc, int2 *tab) {
+// Layout: idx[npad] then frac[npad] (npad = n_full rounded up to 4), so that a thread's 4 entries are one 16-byte load.
+__global__ void __launch_bounds__(256) k_w1_axis(int n_full, int n_small, double sc, int *idx, float *frac) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= n_full) return;
   float f = (float)((i + 0.5) * sc - 0.5);
@@ -257,7 +258,8 @@ __global__ void __launch_bounds__(256) k_w1_axis(int n_full, int n_small, double
   f -= s;
   if (s < 0) { f = 0; s = 0; }
   if (s >= n_small - 1) { f = 0; s = n_small - 1; }
-  tab[i] = make_int2(s, __float_as_int(f));
+  idx[i] = s;
+  frac[i] = f;
 }
 
 // One thread per 4 consecutive output pixels (one 16-byte store when the row allows it).
@@ -273,16 +275,22 @@ __global__ void __launch_bounds__(256) k_w1_upsample(const W1Args a) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) v[k] = __fadd_rn(__ldg(g + (int64_t)y * a.cols + min(x4 + k, a.cols - 1)), add);
   } else {
-    const int2 *__restrict__ xt = a.axis_tab, *__restrict__ yt = a.axis_tab + a.full_cols;
-    const int2 ey = __ldg(yt + y);
-    const int sy = ey.x, sy1 = min(sy + 1, a.rows - 1);
-    const float b1 = __int_as_float(ey.y), b0 = 1.f - b1;
+    const int xpad = (a.full_cols + 3) & ~3, ypad = (a.full_rows + 3) & ~3;
+    const int *__restrict__ xi = reinterpret_cast<const int *>(a.axis_tab);
+    const float *__restrict__ xf = reinterpret_cast<const float *>(xi + xpad);
+    const int *__restrict__ yi = xi + 2 * xpad;
+    const float *__restrict__ yf = reinterpret_cast<const float *>(yi + ypad);
+    const int sy = __ldg(yi + y), sy1 = min(sy + 1, a.rows - 1);
+    const float b1 = __ldg(yf + y), b0 = 1.f - b1;
+    const int4 sx4 = __ldg(reinterpret_cast<const int4 *>(xi + x4));        // x4 is a multiple of 4, tables are padded
+    const float4 fx4 = __ldg(reinterpret_cast<const float4 *>(xf + x4));
+    const int sxs[4] = {sx4.x, sx4.y, sx4.z, sx4.w};
+    const float fxs[4] = {fx4.x, fx4.y, fx4.z, fx4.w};
     const float *__restrict__ g0 = g + sy * a.cols, *__restrict__ g1 = g + sy1 * a.cols;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int2 ex = __ldg(xt + min(x4 + k, a.full_cols - 1));
-      const int sx = ex.x, sx1 = min(sx + 1, a.cols - 1);
-      const float a1 = __int_as_float(ex.y), a0 = 1.f - a1;
+      const int sx = min(max(sxs[k], 0), a.cols - 1), sx1 = min(sx + 1, a.cols - 1);   // padding entries are clamped
+      const float a1 = fxs[k], a0 = 1.f - a1;
       const float v00 = __fadd_rn(__ldg(g0 + sx), add), v01 = __fadd_rn(__ldg(g0 + sx1), add);
       const float v10 = __fadd_rn(__ldg(g1 + sx), add), v11 = __fadd_rn(__ldg(g1 + sx1), add);
       const float r0 = __fadd_rn(__fmul_rn(v00, a0), __fmul_rn(v01, a1));
@@ -485,9 +493,12 @@ int launch_w1(const W1Args &a, cudaStream_t s) {
   if (a.out || a.out_ptrs) {
     if (a.full_cols != a.cols || a.full_rows != a.rows) {
       SSK_REQUIRE(a.axis_tab, "local variance map: axis table scratch missing");
-      k_w1_axis<<<div_up(a.full_cols, 256), 256, 0, s>>>(a.full_cols, a.cols, (double)a.cols / a.full_cols, a.axis_tab);
+      const int xpad = (a.full_cols + 3) & ~3, ypad = (a.full_rows + 3) & ~3;
+      int *xi = reinterpret_cast<int *>(a.axis_tab), *yi = xi + 2 * xpad;
+      cudaMemsetAsync(a.axis_tab, 0, (size_t)(2 * xpad + 2 * ypad) * 4, s);
+      k_w1_axis<<<div_up(a.full_cols, 256), 256, 0, s>>>(a.full_cols, a.cols, (double)a.cols / a.full_cols, xi, reinterpret_cast<float *>(xi + xpad));
       SSK_LAUNCH_CHECK();
-      k_w1_axis<<<div_up(a.full_rows, 256), 256, 0, s>>>(a.full_rows, a.rows, (double)a.rows / a.full_rows, a.axis_tab + a.full_cols);
+      k_w1_axis<<<div_up(a.full_rows, 256), 256, 0, s>>>(a.full_rows, a.rows, (double)a.rows / a.full_rows, yi, reinterpret_cast<float *>(yi + ypad));
       SSK_LAUNCH_CHECK();
     }
     dim3 g2(div_up(a.full_cols, 128), div_up(a.full_rows, 8), a.batch);

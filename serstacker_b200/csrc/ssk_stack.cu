@@ -133,7 +133,7 @@ static int stack_alloc_slots(ssk_stack *h) {
     if (int e = h->gmap_slots.ensure((size_t)r * c * 4 * B)) return e;
     if (int e = h->partials.ensure((size_t)B * 2 * h->w1_nb * 8)) return e;
     if (int e = h->stats.ensure((size_t)B * 4 * 8)) return e;
-    if (int e = h->axis_tab.ensure((size_t)(h->rows + h->cols) * sizeof(int2))) return e;
+    if (int e = h->axis_tab.ensure((size_t)(h->rows + h->cols + 8) * sizeof(int2))) return e;
     if (int e = h->d_weight_ptrs.ensure(sizeof(void *) * B)) return e;
     if (int e = h->d_half_ptrs.ensure(sizeof(void *) * B)) return e;
     if (int e = h->d_half2_ptrs.ensure(sizeof(void *) * B)) return e;

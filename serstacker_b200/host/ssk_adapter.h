@@ -299,6 +299,27 @@ inline bool compute_local_variance_map(const image_t &image, image_t &map, int d
   return ok;
 }
 
+// lpg (core/proc/lpg.cc:223-290): Laplacian + gradient energy weight map (integer powers p)
+inline bool lpg(const image_t &image, image_t &map, double k = 2.0, double p = 2.0, int dscale = 2, int uscale = 6) {
+  ssk_mat s = detail::view(image);
+  create_like(map, s.rows, s.cols, SSK_32FC1);
+  ssk_mat m = detail::view(map);
+  return ssk_lpg(&s, k, p, dscale, uscale, &m) == SSK_OK;
+}
+
+// compute_ellipsoid_zrotation_remap (core/proc/feature2d/ellipsoid.cc:206-277).  R1 / R2: row-major 3x3 doubles;
+// ebox_angle_deg / crop_box {x, y, w, h}: ellipsoid_bbox(center, A, B, C, R2).angle and ellipse_crop_box(ebox, size).
+inline bool compute_ellipsoid_zrotation_remap(int rows, int cols, const double center[2], const double axes[3],
+                                              const double R1[9], const double R2[9], double ebox_angle_deg,
+                                              const int crop_box[4], double wscale, image_t &rmap, image_t &wmap,
+                                              image_t &rmask) {
+  create_like(rmap, rows, cols, SSK_32FC2);
+  create_like(wmap, rows, cols, SSK_32FC1);
+  create_like(rmask, rows, cols, SSK_8UC1);
+  ssk_mat a = detail::view(rmap), b = detail::view(wmap), c = detail::view(rmask);
+  return ssk_ellipsoid_zrotation_remap(rows, cols, center, axes, R1, R2, ebox_angle_deg, crop_box, wscale, &a, &b, &c) == SSK_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // The batched per-frame loop of c_image_stacking_pipeline::process_input_sequence
 // (c_image_stacking_pipeline.cc:1358-1862): one call registers, warps and accumulates a batch of frames.

@@ -38,6 +38,7 @@ int main(int argc, char **argv) {
   const int W = 192, H = 144, N = 5;
   const float sx[N] = {0.f, 1.37f, -2.21f, 0.52f, 3.08f}, sy[N] = {0.f, -0.83f, 1.46f, 2.65f, -1.91f};
   ro.motion_type = SSK_MOTION_TRANSLATION;
+  ro.enable_ecc_registration = 1;   // c_image_registration_options: the ECC stage is opt-in, as in the reference
   ro.ecc.ecch_max_level = -1;
   ssk::c_frame_registration reg(ro);
   ssk::c_weigthed_average acc;
