@@ -227,7 +227,7 @@ def main():
 
     def combine():
         """multi-GPU epilogue: (sum w*I, sum w) reduced to rank 0 over NCCL, then back to the running mean."""
-        multi.combine_pipeline(pipe, dev, dst=0)
+        return multi.combine_pipeline(pipe, dev, dst=0)
 
     # ---------------- device-resident throughput --------------------------------------------------------
     for s in range(args.warmup):
@@ -245,7 +245,7 @@ def main():
         keep.append(pipe.add_frames_async(dev_batch(args.warmup + s)))
     e1.record(stream)
     pipe.sync()
-    combine()
+    combined_frames = combine()
     barrier()
     launches = capi.lib.ssk_kernel_launch_count() - launches0
     ms = e0.elapsed_time(e1)
@@ -254,7 +254,7 @@ def main():
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms = float(t_ms.item())
-    accumulated = pipe.accumulated_frames()
+    accumulated = combined_frames if world > 1 else pipe.accumulated_frames()   # after the reduce: frames of all ranks
     value = world * args.steps * B / (ms * 1e-3)
 
     # ---------------- end to end through the C ABI with host buffers ------------------------------------
@@ -315,7 +315,7 @@ def main():
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "resident_pool_frames": pool_n,
                        "l2_policy": "inputs larger than L2: %d distinct frames (%.1f GB) cycled, %.0f MB touched per step" % (
                            pool_n, pool_n * NPIX * 4 / 1e9, B * NPIX * 4 / 1e6),
-                       "accumulated_frames_rank0": accumulated},
+                       "accumulated_frames": accumulated},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * NPIX * 4,
                     "d2h_bytes_per_step": B * (C.sizeof(capi.ssk_transform) + C.sizeof(capi.ssk_ecc_status)) + 4,
                     "steps": e2e_steps, "registered_frames": ok_frames},
