@@ -264,18 +264,25 @@ def main():
     host_np = host.numpy()
     pipe2 = api.c_image_stacking_pipeline(so)
     pipe2.set_reference(ref.cpu().numpy())
-    e2e_steps = max(3, min(args.steps, 8))
+    e2e_steps = max(4, min(args.steps, 16))
 
     def host_batch(step):
         return [host_np[(step * B + i) % n_host] for i in range(B)]
     for s in range(2):
         pipe2.add_frames(host_batch(s))
     barrier()
+    # streaming use of the public API: step s is submitted (H2D of its B frames from pinned memory + processing
+    # enqueued), then the per-frame registration results of step s-1 are read back (D2H) while step s runs
     t0 = time.perf_counter()
     ok_frames = 0
+    prev = None
     for s in range(e2e_steps):
-        res = pipe2.add_frames(host_batch(s))       # H2D of B frames + D2H of B registration records per step
-        ok_frames += sum(1 for r in res if r["ok"])
+        ticket = pipe2.submit(host_batch(s))
+        if prev is not None:
+            ok_frames += sum(1 for r in pipe2.wait(prev) if r["ok"])
+        prev = ticket
+    ok_frames += sum(1 for r in pipe2.wait(prev) if r["ok"])
+    pipe2.sync()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t_e = torch.tensor([dt], device=dev, dtype=torch.float64)

@@ -302,6 +302,13 @@ SSK_API int ssk_stack_add_frames(ssk_stack *h, const ssk_mat *frames, int n, int
                                  ssk_transform *transforms_out, ssk_ecc_status *status_out);
 /* Enqueue only (no host sync, results stay on the device): for steady-state throughput measurement. */
 SSK_API int ssk_stack_add_frames_async(ssk_stack *h, const ssk_mat *frames, int n, int bpp);
+/* Streaming form: enqueue 1..max_batch frames and return at once; *ticket names the chunk.  Host frames must stay valid
+ * and unchanged until ssk_stack_wait(ticket) returns.  Uploads of the next call overlap the processing of this one. */
+SSK_API int ssk_stack_submit(ssk_stack *h, const ssk_mat *frames, int n, int bpp, int64_t *ticket);
+/* Waits for chunk `ticket` and returns its per-frame registration results (*n_out frames).  Only the last 4 chunks
+ * are kept. */
+SSK_API int ssk_stack_wait(ssk_stack *h, int64_t ticket, ssk_transform *transforms_out, ssk_ecc_status *status_out,
+                           int capacity, int *n_out);
 SSK_API int ssk_stack_sync(ssk_stack *h);
 /* c_frame_accumulation::compute() of the pipeline's accumulator. */
 SSK_API int ssk_stack_compute(ssk_stack *h, ssk_mat *avg, ssk_mat *mask);

@@ -359,6 +359,24 @@ class c_image_stacking_pipeline:
         return [dict(ok=bool(st[i].ok), params=ts[i].parameters(), rho=st[i].rho, eps=st[i].eps,
                      iterations=st[i].num_iterations) for i in range(n)]
 
+    def submit(self, frames):
+        """Streaming form: enqueue up to max_batch frames, return a ticket at once (ssk_stack_submit)."""
+        arr, keep = self._mats(frames)
+        t = C.c_int64(-1)
+        check(capi.lib.ssk_stack_submit(self._h, arr, len(frames), self._bpp, C.byref(t)))
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[t.value] = (keep, frames)      # host frames must outlive the upload
+        return t.value
+
+    def wait(self, ticket):
+        """Results of the chunk `ticket` (ssk_stack_wait)."""
+        n = len(self._inflight[ticket][1])
+        ts, st, m = (ssk_transform * n)(), (ssk_ecc_status * n)(), C.c_int(0)
+        check(capi.lib.ssk_stack_wait(self._h, ticket, ts, st, n, C.byref(m)))
+        del self._inflight[ticket]
+        return [dict(ok=bool(st[i].ok), params=ts[i].parameters(), rho=st[i].rho, eps=st[i].eps,
+                     iterations=st[i].num_iterations) for i in range(m.value)]
+
     def add_frames_async(self, frames):
         arr, keep = self._mats(frames)
         check(capi.lib.ssk_stack_add_frames_async(self._h, arr, len(frames), self._bpp))

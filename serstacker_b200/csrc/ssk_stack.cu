@@ -70,9 +70,16 @@ struct ssk_stack {
   static constexpr int kMaxSets = 8;
   cudaEvent_t set_free[kMaxSets] = {}, set_full[kMaxSets] = {};
   int host_chunk = 0, nsets = 1, set_pos = 0;
-  DevBuf rec_all;                        // registration records of the current max_batch chunk
+  // registration records of the last kRecRing chunks (chunk `ticket` lives in slot ticket % kRecRing)
+  static constexpr int kRecRing = 4;
+  DevBuf rec_all;
   PinnedBuf h_rec_all;
+  cudaEvent_t rec_ev[kRecRing] = {};
+  int rec_n[kRecRing] = {};
+  int64_t rec_ticket[kRecRing] = {-1, -1, -1, -1};
+  int64_t next_ticket = 0;
   ~ssk_stack() {
+    for (auto &e : rec_ev) if (e) cudaEventDestroy(e);
     for (auto &e : set_free) if (e) cudaEventDestroy(e);
     for (auto &e : set_full) if (e) cudaEventDestroy(e);
     if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -105,8 +112,9 @@ static int stack_alloc_slots(ssk_stack *h) {
     if (!h->ring_ev[r]) SSK_CUDA(cudaEventCreateWithFlags(&h->ring_ev[r], cudaEventDisableTiming));
   }
   for (auto &e : h->ev) if (!e) SSK_CUDA(cudaEventCreate(&e));
-  if (int e = h->rec_all.ensure(sizeof(EccFrame) * B)) return e;
-  if (int e = h->h_rec_all.ensure(sizeof(EccFrame) * B)) return e;
+  if (int e = h->rec_all.ensure(sizeof(EccFrame) * B * ssk_stack::kRecRing)) return e;
+  if (int e = h->h_rec_all.ensure(sizeof(EccFrame) * B * ssk_stack::kRecRing)) return e;
+  for (auto &e : h->rec_ev) if (!e) SSK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   // sub-chunk of host frames: large enough to keep the kernels efficient, small enough for >= 2 sets in flight
   h->host_chunk = B >= 32 ? std::max(16, B / 4) : B;
   if (const char *e = getenv("SSK_HOST_CHUNK")) { const int c = atoi(e); if (c >= 1 && c <= B) h->host_chunk = c; }
@@ -359,7 +367,40 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
   return SSK_OK;
 }
 
-int ssk_stack_add_frames_async(ssk_stack *h, const ssk_mat *frames, int n, int bpp) {
+// One chunk of <= max_batch frames: enqueue everything, snapshot the registration records into the chunk's ring slot.
+static int stack_submit_chunk(ssk_stack *h, const ssk_mat *frames, int m, int64_t *ticket) {
+  const int64_t t = h->next_ticket++;
+  const int slot = (int)(t % ssk_stack::kRecRing);
+  const int base = slot * h->max_batch;
+  SSK_CUDA(cudaEventSynchronize(h->rec_ev[slot]));   // the slot's previous download has landed (no-op if never used)
+  if (frames[0].mem == SSK_MEM_DEVICE) {
+    if (int e = stack_process_chunk(h, frames, m, -1, base)) return e;
+  } else {
+    // host frames: upload sub-chunk k+1 on the copy stream while sub-chunk k is processed
+    const int hc = h->host_chunk;
+    int set = h->set_pos;
+    if (int e = stack_upload(h, frames, std::min(hc, m), set)) return e;
+    for (int k0 = 0; k0 < m; k0 += hc) {
+      const int mk = std::min(hc, m - k0);
+      const int next_set = (set + 1) % h->nsets;
+      if (k0 + hc < m) {
+        if (int e = stack_upload(h, frames + k0 + hc, std::min(hc, m - k0 - hc), next_set)) return e;
+      }
+      if (int e = stack_process_chunk(h, frames + k0, mk, set, base + k0)) return e;
+      set = next_set;
+    }
+    h->set_pos = set;
+  }
+  if (h->o.enable_registration)
+    SSK_CUDA(cudaMemcpyAsync(h->h_rec_all.as<EccFrame>() + base, h->rec_all.as<EccFrame>() + base, sizeof(EccFrame) * m,
+                             cudaMemcpyDeviceToHost, h->stream));
+  SSK_CUDA(cudaEventRecord(h->rec_ev[slot], h->stream));
+  h->rec_n[slot] = m; h->rec_ticket[slot] = t;
+  if (ticket) *ticket = t;
+  return SSK_OK;
+}
+
+static int stack_check_frames(ssk_stack *h, const ssk_mat *frames, int n, int bpp) {
   SSK_REQUIRE(h && frames && n >= 0, "ssk_stack_add_frames: bad argument");
   SSK_REQUIRE(h->have_reference, "ssk_stack: set_reference must be called first");
   SSK_REQUIRE(bpp == h->bpp, "ssk_stack: bpp differs from the reference frame's");
@@ -367,26 +408,43 @@ int ssk_stack_add_frames_async(ssk_stack *h, const ssk_mat *frames, int n, int b
     SSK_REQUIRE(frames[i].data && frames[i].rows == h->rows && frames[i].cols == h->cols && frames[i].type == h->type,
                 "ssk_stack: frame geometry/type differs from the reference frame");
   }
-  for (int i0 = 0; i0 < n; i0 += h->max_batch) {
-    const int m = std::min(h->max_batch, n - i0);
-    if (frames[i0].mem == SSK_MEM_DEVICE) {
-      if (int e = stack_process_chunk(h, frames + i0, m, -1, 0)) return e;
-      continue;
-    }
-    // host frames: upload sub-chunk k+1 on the copy stream while sub-chunk k is processed
-    const int hc = h->host_chunk;
-    int set = h->set_pos;
-    if (int e = stack_upload(h, frames + i0, std::min(hc, m), set)) return e;
-    for (int k0 = 0; k0 < m; k0 += hc) {
-      const int mk = std::min(hc, m - k0);
-      const int next_set = (set + 1) % h->nsets;
-      if (k0 + hc < m) {
-        if (int e = stack_upload(h, frames + i0 + k0 + hc, std::min(hc, m - k0 - hc), next_set)) return e;
+  return SSK_OK;
+}
+
+int ssk_stack_submit(ssk_stack *h, const ssk_mat *frames, int n, int bpp, int64_t *ticket) {
+  if (int e = stack_check_frames(h, frames, n, bpp)) return e;
+  SSK_REQUIRE(n >= 1 && n <= h->max_batch, "ssk_stack_submit: 1..max_batch frames per call");
+  return stack_submit_chunk(h, frames, n, ticket);
+}
+
+int ssk_stack_wait(ssk_stack *h, int64_t ticket, ssk_transform *transforms_out, ssk_ecc_status *status_out, int capacity,
+                   int *n_out) {
+  SSK_REQUIRE(h, "null handle");
+  const int slot = (int)(ticket % ssk_stack::kRecRing);
+  SSK_REQUIRE(ticket >= 0 && h->rec_ticket[slot] == ticket, "ssk_stack_wait: unknown ticket (only the last 4 chunks are kept)");
+  SSK_CUDA(cudaEventSynchronize(h->rec_ev[slot]));
+  const int m = h->rec_n[slot];
+  if (n_out) *n_out = m;
+  if (h->o.enable_registration && (transforms_out || status_out)) {
+    SSK_REQUIRE(capacity >= m, "ssk_stack_wait: result arrays too small");
+    const EccFrame *f = h->h_rec_all.as<EccFrame>() + (size_t)slot * h->max_batch;
+    for (int i = 0; i < m; ++i) {
+      if (transforms_out) transforms_out[i] = f[i].t;
+      if (status_out) {
+        ssk_ecc_status &st = status_out[i];
+        st.rho = f[i].rho; st.min_rho = h->o.registration.ecc.min_rho; st.eps = f[i].eps;
+        st.num_iterations = f[i].num_iterations; st.max_iterations = h->o.registration.ecc.max_iterations;
+        st.ok = f[i].ok; st.failed = f[i].failed;
       }
-      if (int e = stack_process_chunk(h, frames + i0 + k0, mk, set, k0)) return e;
-      set = next_set;
     }
-    h->set_pos = set;
+  }
+  return SSK_OK;
+}
+
+int ssk_stack_add_frames_async(ssk_stack *h, const ssk_mat *frames, int n, int bpp) {
+  if (int e = stack_check_frames(h, frames, n, bpp)) return e;
+  for (int i0 = 0; i0 < n; i0 += h->max_batch) {
+    if (int e = stack_submit_chunk(h, frames + i0, std::min(h->max_batch, n - i0), nullptr)) return e;
   }
   return SSK_OK;
 }
@@ -401,25 +459,12 @@ int ssk_stack_sync(ssk_stack *h) {
 
 int ssk_stack_add_frames(ssk_stack *h, const ssk_mat *frames, int n, int bpp, ssk_transform *transforms_out,
                          ssk_ecc_status *status_out) {
-  SSK_REQUIRE(h && frames && n >= 0, "ssk_stack_add_frames: bad argument");
-  SSK_REQUIRE(h->have_reference, "ssk_stack: set_reference must be called first");
+  if (int e = stack_check_frames(h, frames, n, bpp)) return e;
   for (int i0 = 0; i0 < n; i0 += h->max_batch) {
     const int m = std::min(h->max_batch, n - i0);
-    if (int e = ssk_stack_add_frames_async(h, frames + i0, m, bpp)) return e;
-    if (h->o.enable_registration && (transforms_out || status_out)) {
-      SSK_CUDA(cudaMemcpyAsync(h->h_rec_all.p, h->rec_all.p, sizeof(EccFrame) * m, cudaMemcpyDeviceToHost, h->stream));
-      SSK_CUDA(cudaStreamSynchronize(h->stream));
-      const EccFrame *f = h->h_rec_all.as<EccFrame>();
-      for (int i = 0; i < m; ++i) {
-        if (transforms_out) transforms_out[i0 + i] = f[i].t;
-        if (status_out) {
-          ssk_ecc_status &st = status_out[i0 + i];
-          st.rho = f[i].rho; st.min_rho = h->o.registration.ecc.min_rho; st.eps = f[i].eps;
-          st.num_iterations = f[i].num_iterations; st.max_iterations = h->o.registration.ecc.max_iterations;
-          st.ok = f[i].ok; st.failed = f[i].failed;
-        }
-      }
-    }
+    int64_t t = -1;
+    if (int e = stack_submit_chunk(h, frames + i0, m, &t)) return e;
+    if (int e = ssk_stack_wait(h, t, transforms_out ? transforms_out + i0 : nullptr, status_out ? status_out + i0 : nullptr, m, nullptr)) return e;
   }
   return ssk_stack_sync(h);
 }

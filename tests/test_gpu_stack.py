@@ -190,3 +190,31 @@ def test_host_frames_pipelined_upload_equals_device_frames(gpu):
         assert np.array_equal(a["params"], b["params"]) and a["iterations"] == b["iterations"]
     assert np.array_equal(outs[0][1], outs[1][1])
     assert np.array_equal(outs[0][0], outs[1][0])
+
+
+def test_streaming_submit_wait_equals_add_frames(gpu):
+    """ssk_stack_submit / ssk_stack_wait: chunks in flight, results fetched one chunk late, same records and stack."""
+    from serstacker_b200 import api
+    frames, bpp = _config1_like(n=41, size=(160, 120))
+    ro = api.registration_options(motion_type=3, interpolation=2, ecc=dict(ecc_method=3, ecch_max_level=-1))
+    so = api.stack_options(registration=ro, accumulation_method=1, max_batch=8)
+    a = api.c_image_stacking_pipeline(so)
+    a.set_reference(frames[0], bpp=bpp)
+    want = a.add_frames(frames)
+    b = api.c_image_stacking_pipeline(so)
+    b.set_reference(frames[0], bpp=bpp)
+    got, prev = [], None
+    for i in range(0, len(frames), 8):
+        t = b.submit(frames[i:i + 8])
+        if prev is not None:
+            got += b.wait(prev)
+        prev = t
+    got += b.wait(prev)
+    assert len(got) == len(want)
+    for x, y in zip(got, want):
+        assert x["ok"] == y["ok"] and np.array_equal(x["params"], y["params"]) and x["iterations"] == y["iterations"]
+    (avg_a, mask_a), (avg_b, mask_b) = a.compute(), b.compute()
+    assert np.array_equal(mask_a, mask_b) and np.array_equal(avg_a, avg_b)
+    assert a.accumulated_frames() == b.accumulated_frames()
+    from serstacker_b200 import capi
+    assert capi.lib.ssk_stack_wait(b._h, 0, None, None, 0, None) != 0      # ticket 0 left the 4-chunk ring long ago
