@@ -261,6 +261,9 @@ SSK_API int ssk_local_variance_map(const ssk_mat *image, int bpp, int dscale, in
 /* lpg(image, k, p, dscale, uscale, map) (core/proc/lpg.cc:223-290; callers c_jdr_pipeline.cc:1211, c_sdr_pipeline.cc:1205):
  * Laplacian + gradient energy weight map, CV_32FC1 of the image size.  Integer powers p only. */
 SSK_API int ssk_lpg(const ssk_mat *image, double k, double p, int dscale, int uscale, ssk_mat *map /*CV_32FC1*/);
+/* cv::GaussianBlur(src, dst, Size(), sigma_x, sigma_y, BORDER_REPLICATE) on CV_32FC1: the smoothing of the per-frame
+ * weights in c_jdr_pipeline::derotate_and_average_frames (c_jdr_pipeline.cc:1228). sigma_y <= 0: sigma_x. */
+SSK_API int ssk_gaussian_blur(const ssk_mat *src, double sigma_x, double sigma_y, ssk_mat *dst);
 
 /* ---------------------------------------------------------------------------------------------
  * Jovian derotation map: compute_ellipsoid_zrotation_remap (core/proc/feature2d/ellipsoid.cc:206-277), called by

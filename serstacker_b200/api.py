@@ -290,6 +290,15 @@ def lpg(image, k=2.0, p=2.0, dscale=2, uscale=6):
     return out
 
 
+def gaussian_blur(src, sigma_x, sigma_y=0.0):
+    """cv::GaussianBlur(src, dst, Size(), sigma_x, sigma_y, BORDER_REPLICATE) on CV_32FC1 (c_jdr_pipeline.cc:1228)."""
+    src = np.ascontiguousarray(src, dtype=f32)
+    out = np.zeros_like(src)
+    mo = mat(out)
+    check(capi.lib.ssk_gaussian_blur(C.byref(mat(src)), float(sigma_x), float(sigma_y), C.byref(mo)))
+    return out
+
+
 def compute_ellipsoid_zrotation_remap(size, center, axes, R1, R2, ebox_angle_deg, crop_box, wscale=1.0):
     """compute_ellipsoid_zrotation_remap (core/proc/feature2d/ellipsoid.cc:206-277); size = (w, h), crop_box = (x, y, w, h)
     -> (rmap HxWx2 float32, wmap HxW float32, rmask HxW uint8)."""

@@ -778,4 +778,43 @@ int ssk_ellipsoid_zrotation_remap(int rows, int cols, const double center[2], co
   return SSK_OK;
 }
 
+// cv::GaussianBlur(src, dst, Size(), sigma_x, sigma_y, BORDER_REPLICATE) on CV_32FC1 (the weight post-processing of
+// c_jdr_pipeline.cc:1228): equals cv::sepFilter2D with getGaussianKernel(cvRound(8 sigma + 1) | 1, sigma, CV_32F).
+int ssk_gaussian_blur(const ssk_mat *src, double sigma_x, double sigma_y, ssk_mat *dst) {
+  if (int e = ensure_device()) return e;
+  if (int e = check_mat(src, "GaussianBlur src")) return e;
+  if (int e = check_mat(dst, "GaussianBlur dst")) return e;
+  SSK_REQUIRE(src->type == SSK_32FC1 && dst->type == SSK_32FC1 && dst->rows == src->rows && dst->cols == src->cols,
+              "GaussianBlur: CV_32FC1 source and destination of the same size");
+  if (sigma_y <= 0) sigma_y = sigma_x;
+  SSK_REQUIRE(sigma_x > 0 && sigma_x <= 3.5 && sigma_y <= 3.5, "GaussianBlur: 0 < sigma <= 3.5 (kernels up to 31 taps)");
+  Scratch &sc = scratch();
+  if (int e = sc.init()) return e;
+  cudaStream_t s = sc.stream;
+  Img im;
+  if (int e = to_device(src, sc.a, s, &im, 0)) return e;
+  const size_t n = (size_t)im.rows * im.cols;
+  if (int e = sc.b.ensure(n * 4 * 2)) return e;
+  const float *d_src = static_cast<const float *>(im.data);
+  if (im.step != (int64_t)im.cols * 4) {   // sepFilter works on dense images
+    SSK_CUDA(cudaMemcpy2DAsync(sc.b.p, (size_t)im.cols * 4, im.data, im.step, (size_t)im.cols * 4, im.rows, cudaMemcpyDeviceToDevice, s));
+    d_src = sc.b.as<float>();
+  }
+  auto taps = [](double sigma, float *k) {
+    int n = ((int)std::lrint(sigma * 4 * 2 + 1)) | 1;
+    double cf[kMaxTaps], sum = 0;
+    const double s2 = -0.5 / (sigma * sigma);
+    for (int i = 0; i < n; ++i) { const double x = i - (n - 1) * 0.5; cf[i] = std::exp(s2 * x * x); sum += cf[i]; }
+    for (int i = 0; i < n; ++i) k[i] = (float)(cf[i] / sum);
+    return n;
+  };
+  SepFilterArgs f = {};
+  f.src = d_src; f.dst = sc.b.as<float>() + n; f.rows = im.rows; f.cols = im.cols; f.batch = 1;
+  f.kxn = taps(sigma_x, f.kx); f.kyn = taps(sigma_y, f.ky);
+  if (int e = launch_sepfilter(f, s)) return e;
+  if (int e = from_device(f.dst, (size_t)im.cols * 4, im.rows, dst, s)) return e;
+  SSK_CUDA(cudaStreamSynchronize(s));
+  return SSK_OK;
+}
+
 }  // extern "C"

@@ -29,7 +29,13 @@ namespace ssk {
 
 namespace {
 
-constexpr int NT = 512;
+#ifndef SSK_ECC_NT
+#define SSK_ECC_NT 256
+#endif
+#ifndef SSK_ECC_MINB
+#define SSK_ECC_MINB 2
+#endif
+constexpr int NT = SSK_ECC_NT;
 constexpr int NW = NT / 32;
 constexpr int NSMAX = 72;
 constexpr int FT_W = 32, FT_H = 16;          // stencil tile of the forward methods (one pixel per thread)
@@ -467,14 +473,6 @@ __device__ __forceinline__ void map_xy_t(const MapCoef &m, float x, float y, flo
   }
 }
 
-// (unsigned)cvRound(u) < n without the conversion: cvRound rounds half to even, so u = -0.5 maps to 0 (valid) and
-// u = n - 0.5 maps to n - 1 only when n is odd.
-struct RoundRange {
-  float hi; bool hi_incl;
-  __device__ __forceinline__ explicit RoundRange(int n) : hi((float)n - 0.5f), hi_incl((n & 1) != 0) {}
-  __device__ __forceinline__ bool operator()(float u) const { return u >= -0.5f && (hi_incl ? u <= hi : u < hi); }
-};
-
 // valid255_linear on pre-quantised coordinates (sx, sy = cvRound(32 u), cvRound(32 v))
 __device__ __forceinline__ bool lin_valid(int sx, int sy, int cols, int rows) {
   const int ix = sx >> 5, iy = sy >> 5;
@@ -527,7 +525,6 @@ __device__ void pass_ic(Ctx &c, int lvl, bool lm_masks) {
   int nvalid = 0;
   const int n = cols * rows;
   // Branch-free body (invalid pixels contribute an exact 0.0), so that two pixels per thread are in flight.
-  const RoundRange in_x(cols), in_y(rows);
   Walk w(c.rank * NT + c.tid, c.csize * NT, cols);
 #pragma unroll 2
   for (; w.i < n; w.next()) {
@@ -536,7 +533,7 @@ __device__ void pass_ic(Ctx &c, int lvl, bool lm_masks) {
     map_xy_t<MapKind<TYPE>::MT>(m, x, y, u, v);
     const int sx = cvround32(u), sy = cvround32(v);
     bool ok;
-    if (lm_masks) ok = in_x(u) && in_y(v);
+    if (lm_masks) ok = (unsigned)__float2int_rn(u) < (unsigned)cols && (unsigned)__float2int_rn(v) < (unsigned)rows;
     else ok = lin_valid(sx, sy, cols, rows);
     if (rmask) ok = ok && rmask[w.i] != 0;
     const float g = lin_sample(cur, cols, rows, sx, sy);
@@ -1102,7 +1099,7 @@ __device__ double correlation(Ctx &c) {
 }
 
 template <int METHOD, int TYPE>
-__global__ void __launch_bounds__(NT, 2) k_ecc(const __grid_constant__ EccConfig cfg, EccFrame *frames) {
+__global__ void __launch_bounds__(NT, SSK_ECC_MINB) k_ecc(const __grid_constant__ EccConfig cfg, EccFrame *frames) {
   __shared__ Shared S;
   cg::cluster_group cluster = cg::this_cluster();
   Ctx c;

@@ -104,3 +104,14 @@ def test_lpg_rejects_fractional_power(gpu):
     img, _ = _frame(64, 48, 6)
     with pytest.raises(capi.SskError):
         api.lpg(img, 2.0, 1.5, 1, 2)
+
+
+@pytest.mark.parametrize("size", [(320, 240), (333, 251)])
+@pytest.mark.parametrize("sigma", [1.0, 1.7])
+def test_gaussian_blur_matches_opencv(gpu, size, sigma):
+    """W3: cv::GaussianBlur(weights, Size(), sigma, sigma, BORDER_REPLICATE) of c_jdr_pipeline.cc:1228."""
+    from serstacker_b200 import api
+    img, _ = _frame(size[0], size[1], 7)
+    want = cv2.GaussianBlur(img, (0, 0), sigma, None, sigma, cv2.BORDER_REPLICATE)
+    got = api.gaussian_blur(img, sigma, sigma)
+    assert np.abs(got - want).max() <= 2e-7 * max(1.0, float(np.abs(want).max()))
