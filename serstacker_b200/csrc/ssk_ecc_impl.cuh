@@ -38,7 +38,7 @@ namespace {
 constexpr int NT = SSK_ECC_NT;
 constexpr int NW = NT / 32;
 constexpr int NSMAX = 72;
-constexpr int FT_W = 32, FT_H = 16;          // stencil tile of the forward methods (one pixel per thread)
+constexpr int FT_W = 32, FT_H = NT / 32;     // stencil tile of the forward methods (one pixel per thread)
 constexpr int FT_IW = FT_W + 4, FT_IH = FT_H + 4;
 
 template <int TYPE> struct NParams;
