@@ -220,6 +220,57 @@ __global__ void __launch_bounds__(256) k_w1_grad(const W1Args a, int nblocks) {
   }
 }
 
+// kradius = 1 (the default): one thread owns one column and W1_H / 4 consecutive rows of the 64 x 16 tile, keeps the
+// horizontal 3-tap max / min of its rows in registers (neighbours by warp shuffle) and combines them vertically.
+// No shared-memory tile; the per-block partial sums keep the layout of k_w1_grad.
+__global__ void __launch_bounds__(256) k_w1_grad_r1(const W1Args a, int nblocks) {
+  constexpr int RPT = W1_H / 4;
+  __shared__ double s_red[2][8];
+  const int b = blockIdx.z;
+  const float *__restrict__ M = a.M_ptrs ? a.M_ptrs[b] : a.M;
+  float *__restrict__ gmap = a.gmap_ptrs ? a.gmap_ptrs[b] : a.gmap;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x = blockIdx.x * W1_W + (threadIdx.x & (W1_W - 1));
+  const int y0 = blockIdx.y * W1_H + (threadIdx.x / W1_W) * RPT;
+  const int xc = min(x, a.cols - 1), xl = max(xc - 1, 0), xr = min(xc + 1, a.cols - 1);
+  float hmax[RPT + 2], hmin[RPT + 2];
+#pragma unroll
+  for (int r = 0; r < RPT + 2; ++r) {
+    const int yy = min(max(y0 - 1 + r, 0), a.rows - 1);
+    const float *row = M + (int64_t)yy * a.cols;
+    const float c = __ldg(row + xc);
+    float l = __shfl_up_sync(0xffffffffu, c, 1), rt = __shfl_down_sync(0xffffffffu, c, 1);
+    if (lane == 0 || x >= a.cols) l = __ldg(row + xl);          // columns past the image edge replicate the last one
+    if (lane == 31 || x + 1 >= a.cols) rt = __ldg(row + xr);
+    hmax[r] = fmaxf(fmaxf(l, c), rt);
+    hmin[r] = fminf(fminf(l, c), rt);
+  }
+  const float ms = (float)(a.depth_scale * a.depth_scale * a.depth_scale);
+  double sg = 0.0, sg4 = 0.0;
+  if (x < a.cols) {
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      if (y0 + j >= a.rows) break;
+      const float mx = fmaxf(fmaxf(hmax[j], hmax[j + 1]), hmax[j + 2]), mn = fminf(fminf(hmin[j], hmin[j + 1]), hmin[j + 2]);
+      const float g = __fsub_rn(mx, mn);
+      gmap[(int64_t)(y0 + j) * a.cols + x] = __fmul_rn(__fmul_rn(__fmul_rn(g, g), g), ms);
+      sg += (double)fabsf(g);
+      sg4 += (double)__fmul_rn(__fmul_rn(__fmul_rn(g, g), g), g);
+    }
+  }
+  sg = warp_sum(sg);
+  sg4 = warp_sum(sg4);
+  if (lane == 0) { s_red[0][warp] = sg; s_red[1][warp] = sg4; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0, t1 = 0;
+    for (int i = 0; i < 8; ++i) { t0 += s_red[0][i]; t1 += s_red[1][i]; }
+    const int blk = blockIdx.y * gridDim.x + blockIdx.x;
+    a.partials[((int64_t)b * 2 + 0) * nblocks + blk] = t0;
+    a.partials[((int64_t)b * 2 + 1) * nblocks + blk] = t1;
+  }
+}
+
 __global__ void __launch_bounds__(256) k_w1_final(const W1Args a, int nblocks) {
   __shared__ double s0[256], s1[256];
   const int b = blockIdx.x;
@@ -486,7 +537,8 @@ int launch_w1(const W1Args &a, cudaStream_t s) {
   SSK_REQUIRE(a.kradius >= 1 && a.kradius <= W1_RMAX, "local variance map: kradius 1..4");
   const int nblocks = w1_num_blocks(a.rows, a.cols);
   dim3 grid(div_up(a.cols, W1_W), div_up(a.rows, W1_H), a.batch);
-  k_w1_grad<<<grid, 256, 0, s>>>(a, nblocks);
+  if (a.kradius == 1) k_w1_grad_r1<<<grid, 256, 0, s>>>(a, nblocks);
+  else k_w1_grad<<<grid, 256, 0, s>>>(a, nblocks);
   SSK_LAUNCH_CHECK();
   k_w1_final<<<a.batch, 256, 0, s>>>(a, nblocks);
   SSK_LAUNCH_CHECK();
