@@ -278,6 +278,17 @@ SSK_API int ssk_ellipsoid_zrotation_remap(int rows, int cols, const double cente
                                           const int crop_box[4], double wscale,
                                           ssk_mat *rmap, ssk_mat *wmap, ssk_mat *rmask);
 
+/* One frame of c_jdr_pipeline::derotate_and_average_frames (core/pipeline/c_jdr_pipeline/c_jdr_pipeline.cc:1184-1236),
+ * after preproc_align_and_remap: derotation map for R_current -> R_target (ssk_ellipsoid_zrotation_remap arguments),
+ * weight = limb weight * wscale, 0 below 1e-5 [, * lpg(frame) remapped with BORDER_TRANSPARENT when
+ * enable_weighted_average], 1 outside the disk for the master frame, 0 under the frame mask, GaussianBlur(1, REPLICATE);
+ * frame remapped in place (INTER_LINEAR, BORDER_TRANSPARENT); acc.add(frame, weight).  frame: CV_32FC1, mask: CV_8UC1 / NULL. */
+SSK_API int ssk_jdr_derotate_and_add(ssk_acc *acc, const ssk_mat *frame, const ssk_mat *mask, const double center[2],
+                                     const double axes[3], const double R_current[9], const double R_target[9],
+                                     double ebox_angle_deg, const int crop_box[4], double wscale, int is_master,
+                                     int enable_weighted_average, double lpg_k, double lpg_p, int lpg_dscale,
+                                     int lpg_uscale);
+
 /* ---------------------------------------------------------------------------------------------
  * The fused per-frame loop of c_image_stacking_pipeline::process_input_sequence
  * (c_image_stacking_pipeline.cc:1358-1862): weights -> register -> warp(frame, mask, weights) -> accumulate,

@@ -129,3 +129,28 @@ def compute_derotation_for_angle(size, center, axes, target_pose, longitude_rota
     Rt = build_ellipsoid_rotation(*target_pose)
     Rc = build_ellipsoid_rotation(target_pose[0] + longitude_rotation_radians, target_pose[1], target_pose[2])
     return compute_ellipsoid_zrotation_remap(size, center, axes, Rc, Rt, wscale)
+
+
+def jdr_derotate_and_add(acc, frame, mask, size, center, axes, target_pose, longitude_rotation_radians, wscale, is_master,
+                         enable_weighted_average=True, lpg_opts=None):
+    """One iteration of c_jdr_pipeline::derotate_and_average_frames after preproc_align_and_remap
+    (c_jdr_pipeline.cc:1184-1236): returns (derotated frame, weights) and adds them to `acc`."""
+    from .weights import lpg
+    rmap, wmap, rmask, ebox, cbox = compute_derotation_for_angle(size, center, axes, target_pose,
+                                                                 longitude_rotation_radians, wscale)
+    w = wmap.copy()
+    w[w < 1e-5] = 0
+    if enable_weighted_average:
+        l = lpg(frame, **(lpg_opts or {}))
+        ld = l.copy()                                           # cv::remap in place: the destination starts as the source
+        cv2.remap(l, rmap, None, cv2.INTER_LINEAR, dst=ld, borderMode=cv2.BORDER_TRANSPARENT)
+        w = cv2.multiply(w, ld)
+    if is_master:
+        w[rmask == 0] = 1
+    if mask is not None:
+        w[mask == 0] = 0
+    w = cv2.GaussianBlur(w, (0, 0), 1, None, 1, cv2.BORDER_REPLICATE)
+    f = frame.copy()
+    cv2.remap(frame, rmap, None, cv2.INTER_LINEAR, dst=f, borderMode=cv2.BORDER_TRANSPARENT)
+    acc.add(f, w)
+    return f, w

@@ -314,6 +314,19 @@ def compute_ellipsoid_zrotation_remap(size, center, axes, R1, R2, ebox_angle_deg
     return rmap, wmap, rmask
 
 
+def jdr_derotate_and_add(acc, frame, mask, center, axes, R_current, R_target, ebox_angle_deg, crop_box, wscale, is_master,
+                         enable_weighted_average=True, lpg_k=2.0, lpg_p=2.0, lpg_dscale=2, lpg_uscale=6):
+    """One frame of c_jdr_pipeline::derotate_and_average_frames (c_jdr_pipeline.cc:1184-1236) into the accumulator `acc`."""
+    d = lambda v, n: (C.c_double * n)(*[float(x) for x in np.asarray(v, dtype=np.float64).reshape(-1)])
+    frame = np.ascontiguousarray(frame, dtype=f32)
+    mm = None if mask is None else mat(np.ascontiguousarray(mask))
+    check(capi.lib.ssk_jdr_derotate_and_add(acc._h, C.byref(mat(frame)), ref(mm), d(center, 2), d(axes, 3), d(R_current, 9),
+                                            d(R_target, 9), float(ebox_angle_deg), (C.c_int * 4)(*[int(v) for v in crop_box]),
+                                            float(wscale), int(is_master), int(enable_weighted_average), float(lpg_k),
+                                            float(lpg_p), int(lpg_dscale), int(lpg_uscale)))
+    return True
+
+
 def stack_options(**kw):
     o = capi.ssk_stack_options()
     capi.lib.ssk_stack_options_default(C.byref(o))

@@ -647,21 +647,11 @@ int ssk_local_variance_map(const ssk_mat *image, int bpp, int dscale, int kradiu
   return SSK_OK;
 }
 
-// lpg (core/proc/lpg.cc:223-290): float conversion by 1/maxval(depth), channel average, pdownscale(dscale) * 1/(1+dscale),
-// compute_lpg_5x5(k/(k+1), 1/(k+1), 1e-9), pdownscale(uscale - dscale) * (uscale - dscale), pow(p), pyrUp chain back
-// to the image size.
-int ssk_lpg(const ssk_mat *image, double k, double p, int dscale, int uscale, ssk_mat *map) {
-  if (int e = ensure_device()) return e;
-  if (int e = check_mat(image, "lpg")) return e;
-  if (int e = check_mat(map, "lpg map")) return e;
-  SSK_REQUIRE(map->type == SSK_32FC1 && map->rows == image->rows && map->cols == image->cols, "lpg: map must be CV_32FC1 of the image size");
-  SSK_REQUIRE(dscale >= 0 && dscale <= 10 && uscale >= 0 && uscale <= 12, "lpg: dscale 0..10, uscale 0..12");
-  SSK_REQUIRE(p >= 0 && p == std::floor(p) && p <= 16, "lpg: only integer powers p are implemented (cv::pow's iPow path)");
-  Scratch &sc = scratch();
-  if (int e = sc.init()) return e;
+}  // extern "C"
+
+// lpg on a device image; the result (dense, image size) lives in sc.b until the next call that uses sc.b
+static int lpg_device(Scratch &sc, Img im, double k, double p, int dscale, int uscale, float **out) {
   cudaStream_t s = sc.stream;
-  Img im;
-  if (int e = to_device(image, sc.a, s, &im, 0)) return e;
   SSK_REQUIRE(im.cn == 1, "lpg: single-channel images (the callers pass the gray frame)");
   // lpg.cc:184-200: integer samples are scaled by 1 / max value of the depth
   im.scale = im.depth == SSK_8U ? (float)(1.0 / 255.0) : im.depth == SSK_16U ? (float)(1.0 / 65535.0) : 1.f;
@@ -726,6 +716,29 @@ int ssk_lpg(const ssk_mat *image, double k, double p, int dscale, int uscale, ss
       M = dst; r = chh[l]; c = cw[l];
     }
   }
+  *out = M;
+  return SSK_OK;
+}
+
+extern "C" {
+
+// lpg (core/proc/lpg.cc:223-290): float conversion by 1/maxval(depth), channel average, pdownscale(dscale) * 1/(1+dscale),
+// compute_lpg_5x5(k/(k+1), 1/(k+1), 1e-9), pdownscale(uscale - dscale) * (uscale - dscale), pow(p), pyrUp chain back
+// to the image size.
+int ssk_lpg(const ssk_mat *image, double k, double p, int dscale, int uscale, ssk_mat *map) {
+  if (int e = ensure_device()) return e;
+  if (int e = check_mat(image, "lpg")) return e;
+  if (int e = check_mat(map, "lpg map")) return e;
+  SSK_REQUIRE(map->type == SSK_32FC1 && map->rows == image->rows && map->cols == image->cols, "lpg: map must be CV_32FC1 of the image size");
+  SSK_REQUIRE(dscale >= 0 && dscale <= 10 && uscale >= 0 && uscale <= 12, "lpg: dscale 0..10, uscale 0..12");
+  SSK_REQUIRE(p >= 0 && p == std::floor(p) && p <= 16, "lpg: only integer powers p are implemented (cv::pow's iPow path)");
+  Scratch &sc = scratch();
+  if (int e = sc.init()) return e;
+  cudaStream_t s = sc.stream;
+  Img im;
+  if (int e = to_device(image, sc.a, s, &im, 0)) return e;
+  float *M = nullptr;
+  if (int e = lpg_device(sc, im, k, p, dscale, uscale, &M)) return e;
   if (int e = from_device(M, (size_t)im.cols * 4, im.rows, map, s)) return e;
   SSK_CUDA(cudaStreamSynchronize(s));
   return SSK_OK;
@@ -815,6 +828,89 @@ int ssk_gaussian_blur(const ssk_mat *src, double sigma_x, double sigma_y, ssk_ma
   if (int e = from_device(f.dst, (size_t)im.cols * 4, im.rows, dst, s)) return e;
   SSK_CUDA(cudaStreamSynchronize(s));
   return SSK_OK;
+}
+
+// One frame of c_jdr_pipeline::derotate_and_average_frames (c_jdr_pipeline.cc:1184-1236): derotation map for the frame's
+// longitude offset, per-frame weight (limb weight * time weight [* remapped lpg], master-frame and mask rules),
+// GaussianBlur(1, REPLICATE) of the weight, derotation of the frame (INTER_LINEAR, BORDER_TRANSPARENT in place) and
+// c_weigthed_average::add(frame, weights) - all on the device.
+int ssk_jdr_derotate_and_add(ssk_acc *acc, const ssk_mat *frame, const ssk_mat *mask, const double center[2],
+                             const double axes[3], const double R_current[9], const double R_target[9],
+                             double ebox_angle_deg, const int crop_box[4], double wscale, int is_master,
+                             int enable_weighted_average, double lpg_k, double lpg_p, int lpg_dscale, int lpg_uscale) {
+  if (int e = ensure_device()) return e;
+  SSK_REQUIRE(acc && center && axes && R_current && R_target && crop_box, "jdr: null argument");
+  if (int e = check_mat(frame, "jdr frame")) return e;
+  SSK_REQUIRE(frame->type == SSK_32FC1, "jdr: CV_32FC1 frames (the pipeline's aligned gray frame)");
+  SSK_REQUIRE(!enable_weighted_average || (lpg_p >= 0 && lpg_p == std::floor(lpg_p) && lpg_p <= 16), "jdr: integer lpg power");
+  const int rows = frame->rows, cols = frame->cols;
+  Scratch &sc = scratch();
+  if (int e = sc.init()) return e;
+  cudaStream_t s = sc.stream;
+  static thread_local DevBuf d_frame, d_mask, d_rmap, d_wpre, d_w, d_rmask, d_lpg, d_wblur, d_out;
+  Tables tab;
+  if (int e = get_tables(&tab)) return e;
+  const size_t n = (size_t)rows * cols;
+  if (int e = d_frame.ensure(n * 4)) return e;
+  if (int e = d_rmap.ensure(n * 8)) return e;
+  if (int e = d_wpre.ensure(n * 4)) return e;
+  if (int e = d_w.ensure(n * 4)) return e;
+  if (int e = d_rmask.ensure(n)) return e;
+  if (int e = d_wblur.ensure(n * 4)) return e;
+  if (int e = d_out.ensure(n * 4)) return e;
+  SSK_CUDA(cudaMemcpy2DAsync(d_frame.p, (size_t)cols * 4, frame->data, frame->step, (size_t)cols * 4, rows,
+                             frame->mem == SSK_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  const uint8_t *dm = nullptr;
+  int64_t mstep = 0;
+  if (mask) { if (int e = mask_to_device(mask, rows, cols, d_mask, s, &dm, &mstep)) return e; }
+  // derotation map, disk mask, limb weight
+  EllipsoidArgs a = {};
+  a.rows = rows; a.cols = cols; a.cx = center[0]; a.cy = center[1]; a.A = axes[0]; a.B = axes[1]; a.C = axes[2];
+  for (int i = 0; i < 9; ++i) { a.R1[i] = R_current[i]; a.R2[i] = R_target[i]; }
+  a.bx = crop_box[0]; a.by = crop_box[1]; a.bw = crop_box[2]; a.bh = crop_box[3];
+  const double ang = ebox_angle_deg * 3.1415926535897932384626433832795 / 180;
+  a.ca = std::cos(ang); a.sa = std::sin(ang); a.wscale = wscale;
+  a.rmap = d_rmap.as<float2>(); a.wmap = d_wpre.as<float>(); a.rmask = d_rmask.as<uint8_t>();
+  if (int e = launch_ellipsoid_remap(a, s)) return e;
+  RemapArgs ra = {};
+  ra.src.data = d_wpre.p; ra.src.step = (int64_t)cols * 4; ra.src.rows = rows; ra.src.cols = cols; ra.src.depth = SSK_32F; ra.src.cn = 1; ra.src.scale = 1.f;
+  ra.dst = d_w.as<float>(); ra.dst_step = (int64_t)cols * 4; ra.rows = rows; ra.cols = cols;
+  ra.rmap = d_rmap.as<float2>(); ra.rmap_step = (int64_t)cols * 8;
+  ra.interp = SSK_INTER_LINEAR; ra.border = SSK_BORDER_CONSTANT;
+  if (int e = launch_remap(ra, tab, s)) return e;
+  // lpg(frame) remapped in place with BORDER_TRANSPARENT (outliers keep the unmapped value)
+  const float *d_l = nullptr;
+  if (enable_weighted_average) {
+    Img im;
+    im.data = d_frame.p; im.step = (int64_t)cols * 4; im.rows = rows; im.cols = cols; im.depth = SSK_32F; im.cn = 1; im.scale = 1.f;
+    float *L = nullptr;
+    if (int e = lpg_device(sc, im, lpg_k, lpg_p, lpg_dscale, lpg_uscale, &L)) return e;
+    if (int e = d_lpg.ensure(n * 4)) return e;
+    SSK_CUDA(cudaMemcpyAsync(d_lpg.p, L, n * 4, cudaMemcpyDeviceToDevice, s));
+    ra.src.data = L; ra.dst = d_lpg.as<float>(); ra.border = SSK_BORDER_TRANSPARENT;
+    if (int e = launch_remap(ra, tab, s)) return e;
+    d_l = d_lpg.as<float>();
+  }
+  if (int e = launch_jdr_weights(d_w.as<float>(), d_l, d_rmask.as<uint8_t>(), dm, mstep, rows, cols, is_master, s)) return e;
+  // cv::GaussianBlur(weights, Size(), 1, 1, BORDER_REPLICATE): 9 taps
+  SepFilterArgs f = {};
+  f.src = d_w.as<float>(); f.dst = d_wblur.as<float>(); f.rows = rows; f.cols = cols; f.batch = 1;
+  {
+    double cf[9], sum = 0;
+    for (int i = 0; i < 9; ++i) { const double x = i - 4.0; cf[i] = std::exp(-0.5 * x * x); sum += cf[i]; }
+    for (int i = 0; i < 9; ++i) f.kx[i] = f.ky[i] = (float)(cf[i] / sum);
+    f.kxn = f.kyn = 9;
+  }
+  if (int e = launch_sepfilter(f, s)) return e;
+  // derotate the frame in place (INTER_LINEAR, BORDER_TRANSPARENT)
+  SSK_CUDA(cudaMemcpyAsync(d_out.p, d_frame.p, n * 4, cudaMemcpyDeviceToDevice, s));
+  ra.src.data = d_frame.p; ra.dst = d_out.as<float>(); ra.border = SSK_BORDER_TRANSPARENT;
+  if (int e = launch_remap(ra, tab, s)) return e;
+  SSK_CUDA(cudaStreamSynchronize(s));    // the accumulator works on its own stream
+  ssk_mat fm, wm;
+  fm.data = d_out.p; fm.step = (int64_t)cols * 4; fm.rows = rows; fm.cols = cols; fm.type = SSK_32FC1; fm.mem = SSK_MEM_DEVICE;
+  wm = fm; wm.data = d_wblur.p;
+  return ssk_acc_add(acc, &fm, &wm, 0);
 }
 
 }  // extern "C"

@@ -187,6 +187,29 @@ __global__ void __launch_bounds__(256) k_ellipsoid_remap(const EllipsoidArgs a) 
 
 }  // namespace
 
+namespace {
+__global__ void __launch_bounds__(256) k_jdr_weights(float *w, const float *lpg_map, const uint8_t *rmask, const uint8_t *mask,
+                                                     int64_t mask_step, int rows, int cols, int is_master) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= cols || y >= rows) return;
+  const int64_t o = (int64_t)y * cols + x;
+  float v = w[o];
+  if (v < 1e-5f) v = 0.f;                      // current_weights.setTo(0, current_weights < 1e-5): scalar taken as float
+  if (lpg_map) v = __fmul_rn(v, lpg_map[o]);   // cv::multiply(current_weights, lpg_map)
+  if (is_master && !rmask[o]) v = 1.f;         // setTo(1, ~rmask)
+  if (mask && !mask[(int64_t)y * mask_step + x]) v = 0.f;
+  w[o] = v;
+}
+}  // namespace
+
+int launch_jdr_weights(float *w, const float *lpg_map, const uint8_t *rmask, const uint8_t *mask, int64_t mask_step, int rows,
+                       int cols, int is_master, cudaStream_t s) {
+  dim3 grid(div_up(cols, 32), div_up(rows, 8));
+  k_jdr_weights<<<grid, 256, 0, s>>>(w, lpg_map, rmask, mask, mask_step, rows, cols, is_master);
+  SSK_LAUNCH_CHECK();
+  return SSK_OK;
+}
+
 int launch_ellipsoid_remap(const EllipsoidArgs &a, cudaStream_t s) {
   dim3 grid(div_up(a.cols, 32), div_up(a.rows, 8));
   k_ellipsoid_remap<<<grid, 256, 0, s>>>(a);

@@ -71,6 +71,11 @@ struct EllipsoidArgs {
 };
 int launch_ellipsoid_remap(const EllipsoidArgs &a, cudaStream_t s);
 
+// Per-frame weight of c_jdr_pipeline::derotate_and_average_frames before its smoothing (c_jdr_pipeline.cc:1207-1227):
+// w = wmap (0 below 1e-5) [* lpg]; master frame: 1 outside the disk mask; 0 where the frame mask is 0.  In place on w.
+int launch_jdr_weights(float *w, const float *lpg_map, const uint8_t *rmask, const uint8_t *mask, int64_t mask_step,
+                       int rows, int cols, int is_master, cudaStream_t s);
+
 // c_weigthed_average::add without warp (c_frame_accumulation.cc:20-129)
 struct AccAddArgs {
   Img src;

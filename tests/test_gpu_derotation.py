@@ -6,6 +6,7 @@ import cv2
 import pytest
 
 from oracle import derotation as od
+from helpers import rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -29,3 +30,63 @@ def test_ellipsoid_zrotation_remap_matches_oracle(gpu, size, center, axes, pose,
     assert np.array_equal(rmap_g, rmap_o)
     assert np.abs(wmap_g - wmap_o).max() <= 1e-6
     assert np.isfinite(wmap_g).all()
+
+
+def _jovian_frame(size, center, axes, pose, seed):
+    """Synthetic planet: limb-darkened ellipsoid with longitude/latitude texture, rendered at `pose`."""
+    w, h = size
+    R = od.build_ellipsoid_rotation(*pose)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    xs, ys = xx - center[0], yy - center[1]
+    A, B, C = axes
+    iA, iB, iC = 1 / (A * A), 1 / (B * B), 1 / (C * C)
+    xst, yst, zst = R[0, 0] * xs + R[1, 0] * ys, R[0, 1] * xs + R[1, 1] * ys, R[0, 2] * xs + R[1, 2] * ys
+    K2 = R[2, 0] ** 2 * iA + R[2, 1] ** 2 * iB + R[2, 2] ** 2 * iC
+    K1 = xst * R[2, 0] * iA + yst * R[2, 1] * iB + zst * R[2, 2] * iC
+    K0 = xst ** 2 * iA + yst ** 2 * iB + zst ** 2 * iC - 1
+    disc = K1 * K1 - K2 * K0
+    hit = disc >= 0
+    zs = (-K1 - np.sqrt(np.where(hit, disc, 0))) / K2
+    px, py, pz = xst + R[2, 0] * zs, yst + R[2, 1] * zs, zst + R[2, 2] * zs
+    lon, lat = np.arctan2(px / A, -pz / C), np.arcsin(np.clip(py / B, -1, 1))
+    tex = 0.5 + 0.2 * np.sin(7 * lat) + 0.15 * np.sin(9 * lon + 3 * lat) + 0.1 * np.cos(23 * lon) * np.cos(11 * lat)
+    limb = np.sqrt(np.clip(1 - ((xs / A) ** 2 + (ys / B) ** 2), 0, 1))
+    rng = np.random.default_rng(seed)
+    img = np.where(hit, tex * (0.4 + 0.6 * limb), 0.02) + rng.normal(0, 0.003, (h, w))
+    return cv2.GaussianBlur(img.astype(np.float32), (0, 0), 1.0)
+
+
+@pytest.mark.parametrize("weighted", [True, False])
+def test_jdr_derotate_and_average_matches_oracle(gpu, weighted):
+    """D2: c_jdr_pipeline::derotate_and_average_frames over a short sequence (master frame in the middle, a frame mask on
+    one frame): derotation map, lpg-weighted limb weights, GaussianBlur, TRANSPARENT remap, weighted average."""
+    from serstacker_b200 import api
+    from oracle import accumulation as oacc
+    size, center, axes = (480, 400), (241.3, 198.6), (150.0, 140.0, 150.0)
+    target = (0.4, math.radians(2.5), math.radians(-8.0))
+    dlons = [math.radians(v) for v in (-5.0, -2.0, 0.0, 3.0, 6.5)]
+    lpg_opts = dict(k=2.0, p=2.0, dscale=1, uscale=3)
+    o, g = oacc.WeightedAverage(), api.c_weigthed_average()
+    Rt = od.build_ellipsoid_rotation(*target)
+    for i, dl in enumerate(dlons):
+        pose = (target[0] + dl, target[1], target[2])
+        frame = _jovian_frame(size, center, axes, pose, seed=i)
+        mask = None
+        if i == 1:
+            mask = np.full((size[1], size[0]), 255, np.uint8)
+            mask[:, :150] = 0
+        wscale = 1.0 / (1.0 + abs(dl) * 20)
+        od.jdr_derotate_and_add(o, frame, mask, size, center, axes, target, dl, wscale, is_master=(i == 2),
+                                enable_weighted_average=weighted, lpg_opts=lpg_opts)
+        _, _, _, ebox, cbox = od.compute_derotation_for_angle(size, center, axes, target, dl, wscale)
+        Rc = od.build_ellipsoid_rotation(*pose)
+        api.jdr_derotate_and_add(g, frame, mask, center, axes, Rc, Rt, float(ebox[2]), cbox, wscale, i == 2,
+                                 enable_weighted_average=weighted, lpg_k=2.0, lpg_p=2.0, lpg_dscale=1, lpg_uscale=3)
+    ao, mo = o.compute()
+    ag, mg = g.compute()
+    assert g.accumulated_frames() == len(dlons)
+    assert np.mean(mo != mg) < 1e-4
+    m = (mo > 0) & (mg > 0)
+    assert rel_l2(ag, ao, m) <= 1e-4
+    wg, wo = g.get_acc_counters(), o.weights
+    assert rel_l2(wg, wo, m) <= 1e-4
