@@ -381,6 +381,76 @@ __device__ __forceinline__ void roll_pixel_s(RollS<INTERP> &R, const ColMap<MT> 
   *s_acc_px = upd ? fmaf(I - A, factor, A) : A;
 }
 
+// ---- packed (frame, weight) pairs: one FFMA2 / FMUL2 interpolates both images (sm_100 f32x2 arithmetic) ----
+typedef unsigned long long pair_t;
+__device__ __forceinline__ pair_t pk2(float lo, float hi) { pair_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ pair_t mul2s(pair_t a, float s) {
+  pair_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(pk2(s, s))); return r;
+}
+__device__ __forceinline__ pair_t fma2s(pair_t a, float s, pair_t c) {
+  pair_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(pk2(s, s)), "l"(c)); return r;
+}
+__device__ __forceinline__ float lds_f32(unsigned addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ float4 lds_f32x4(unsigned addr) {
+  float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr)); return v;
+}
+__device__ __forceinline__ void sts_f32(unsigned addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v)); }
+
+struct RollC2 {
+  pair_t fw[4][4];           // (frame, weight) taps, rows in rotating slots
+  int ix, iy;                // source anchor of the window
+  const unsigned char *pf;   // staged frame row that enters the window next
+  const float *pw;           // staged weight row that enters the window next
+};
+
+// Bicubic + weight map specialisation of roll_pixel_s: the frame and weight windows travel as packed pairs, so the
+// 20 multiply-adds of the separable bicubic serve both images; the accumulator tile and the coefficient table are
+// addressed through 32-bit shared addresses computed once per thread; the running-mean factor w/(W+w) uses the
+// approximate reciprocal (the reference itself is built with -ffast-math; <= 2 ulp on the factor).
+template <int DEPTH, int MT, int J>
+__device__ __forceinline__ void roll_pixel_c2(RollC2 &R, const ColMap<MT> &cm, float y, const unsigned char *s_f, const float *s_g,
+                                              float scale, const StagePlan &pl, unsigned cub_a, unsigned acc_a, unsigned w_a, bool ok = true) {
+  typedef StageGeom<DEPTH> G;
+  float u, v;
+  cm(y, u, v);
+  const int su = __float2int_rn(__fmul_rn(u, 32.0f)), sv = __float2int_rn(__fmul_rn(v, 32.0f));
+  const int ix = su >> kInterBits, iy = sv >> kInterBits;
+  if (ix != R.ix || iy != R.iy + 1) {
+    R.pf = s_f + (iy - 1 - pl.sy0) * G::ROWB + (ix - 1 - pl.sx0) * G::ES;
+    R.pw = s_g + (iy - 1 - pl.sy0) * WWD + (ix - 1 - pl.sxw);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) R.fw[(J + r) % 4][q] = pk2(lds_px<DEPTH>(R.pf + q * G::ES, scale), R.pw[q]);
+      R.pf += G::ROWB; R.pw += WWD;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) R.fw[(J + 3) % 4][q] = pk2(lds_px<DEPTH>(R.pf + q * G::ES, scale), R.pw[q]);
+  R.pf += G::ROWB; R.pw += WWD;
+  R.ix = ix; R.iy = iy;
+
+  const float4 cx = lds_f32x4(cub_a + ((su & (kInterTab - 1)) << 4)), cy = lds_f32x4(cub_a + ((sv & (kInterTab - 1)) << 4));
+  pair_t rs[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const pair_t *t = R.fw[(J + r) % 4];
+    rs[r] = fma2s(t[3], cx.w, fma2s(t[2], cx.z, fma2s(t[1], cx.y, mul2s(t[0], cx.x))));
+  }
+  const pair_t res = fma2s(rs[3], cy.w, fma2s(rs[2], cy.z, fma2s(rs[1], cy.y, mul2s(rs[0], cy.x))));
+  float I, wk;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(I), "=f"(wk) : "l"(res));
+  const float W0 = lds_f32(w_a), A = lds_f32(acc_a);
+  const float Wn = W0 + wk;
+  float rW;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rW) : "f"(Wn));
+  const float factor = wk * rW;
+  if (ok && wk > 0.f) {              // eroded validity mask (ring tiles); c_frame_accumulation.cc:114
+    sts_f32(w_a, Wn);
+    sts_f32(acc_a, fmaf(I - A, factor, A));
+  }
+}
+
 // cv::borderInterpolate for the modes whose mapped index stays near the border (a single reflection suffices for
 // the few pixels of overhang a tile can have); -1: BORDER_CONSTANT (use the border value)
 __device__ __forceinline__ int bmap(int p, int n, int border) {
@@ -586,9 +656,15 @@ __global__ void __launch_bounds__(TW * (RING ? RING_WARPS : SWARPS), RING ? 1 : 
       const ColMap<MT> cm(m, (float)x);
       const unsigned char *sf = s_f[buf];
       const float *sg = s_g[buf];
+      constexpr bool C2 = INTERP == SSK_INTER_CUBIC && WEIGHTS;   // packed (frame, weight) bicubic
+      const unsigned acc_a = (unsigned)__cvta_generic_to_shared(s_acc0), w_a = (unsigned)__cvta_generic_to_shared(s_w0);
+      const unsigned cub_a = (unsigned)__cvta_generic_to_shared(s_cubic);
+      const float y0f = (float)y0;
       if (RING) {
         RollS<INTERP> R;
+        RollC2 R2;
         R.ix = INT_MIN; R.iy = INT_MIN; R.pf = sf; R.pw = sg;
+        R2.ix = INT_MIN; R2.iy = INT_MIN; R2.pf = sf; R2.pw = sg;
         const unsigned long long *hm = &s_hmask[warp * GR];
         unsigned long long m0 = hm[0], m1 = hm[1], m2 = hm[2], m3 = hm[3];
 #pragma unroll 1
@@ -599,12 +675,30 @@ __global__ void __launch_bounds__(TW * (RING ? RING_WARPS : SWARPS), RING ? 1 : 
             const bool ok = ((m0 & m1 & m2 & m3 & m4) >> lane) & 1ull;
             m0 = m1; m1 = m2; m2 = m3; m3 = m4;
             if (k + jj < nrow) {
-              if (jj == 0) roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 0>(R, cm, (float)(y0 + k), sf, sg, a.scale, plan, s_cubic, s_acc0 + k * TW, s_w0 + k * TW, ok);
-              if (jj == 1) roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 1 % N>(R, cm, (float)(y0 + k + 1), sf, sg, a.scale, plan, s_cubic, s_acc0 + (k + 1) * TW, s_w0 + (k + 1) * TW, ok);
-              if (jj == 2) roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 2 % N>(R, cm, (float)(y0 + k + 2), sf, sg, a.scale, plan, s_cubic, s_acc0 + (k + 2) * TW, s_w0 + (k + 2) * TW, ok);
-              if (jj == 3) roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 3 % N>(R, cm, (float)(y0 + k + 3), sf, sg, a.scale, plan, s_cubic, s_acc0 + (k + 3) * TW, s_w0 + (k + 3) * TW, ok);
+              if (C2) {
+                const unsigned o = (unsigned)((k + jj) * TW * 4);
+                if (jj == 0) roll_pixel_c2<DEPTH, MT, 0>(R2, cm, y0f + (float)k, sf, sg, a.scale, plan, cub_a, acc_a + o, w_a + o, ok);
+                if (jj == 1) roll_pixel_c2<DEPTH, MT, 1>(R2, cm, y0f + (float)(k + 1), sf, sg, a.scale, plan, cub_a, acc_a + o, w_a + o, ok);
+                if (jj == 2) roll_pixel_c2<DEPTH, MT, 2>(R2, cm, y0f + (float)(k + 2), sf, sg, a.scale, plan, cub_a, acc_a + o, w_a + o, ok);
+                if (jj == 3) roll_pixel_c2<DEPTH, MT, 3>(R2, cm, y0f + (float)(k + 3), sf, sg, a.scale, plan, cub_a, acc_a + o, w_a + o, ok);
+              } else {
+                if (jj == 0) roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 0>(R, cm, (float)(y0 + k), sf, sg, a.scale, plan, s_cubic, s_acc0 + k * TW, s_w0 + k * TW, ok);
+                if (jj == 1) roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 1 % N>(R, cm, (float)(y0 + k + 1), sf, sg, a.scale, plan, s_cubic, s_acc0 + (k + 1) * TW, s_w0 + (k + 1) * TW, ok);
+                if (jj == 2) roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 2 % N>(R, cm, (float)(y0 + k + 2), sf, sg, a.scale, plan, s_cubic, s_acc0 + (k + 2) * TW, s_w0 + (k + 2) * TW, ok);
+                if (jj == 3) roll_pixel_s<DEPTH, INTERP, WEIGHTS, MT, 3 % N>(R, cm, (float)(y0 + k + 3), sf, sg, a.scale, plan, s_cubic, s_acc0 + (k + 3) * TW, s_w0 + (k + 3) * TW, ok);
+              }
             }
           }
+        }
+      } else if (C2) {
+        RollC2 R2;
+        R2.ix = INT_MIN; R2.iy = INT_MIN; R2.pf = sf; R2.pw = sg;
+#pragma unroll
+        for (int k = 0; k < GR; k += 4) {
+          roll_pixel_c2<DEPTH, MT, 0>(R2, cm, y0f + (float)k, sf, sg, a.scale, plan, cub_a, acc_a + k * TW * 4, w_a + k * TW * 4);
+          roll_pixel_c2<DEPTH, MT, 1>(R2, cm, y0f + (float)(k + 1), sf, sg, a.scale, plan, cub_a, acc_a + (k + 1) * TW * 4, w_a + (k + 1) * TW * 4);
+          roll_pixel_c2<DEPTH, MT, 2>(R2, cm, y0f + (float)(k + 2), sf, sg, a.scale, plan, cub_a, acc_a + (k + 2) * TW * 4, w_a + (k + 2) * TW * 4);
+          roll_pixel_c2<DEPTH, MT, 3>(R2, cm, y0f + (float)(k + 3), sf, sg, a.scale, plan, cub_a, acc_a + (k + 3) * TW * 4, w_a + (k + 3) * TW * 4);
         }
       } else {
         RollS<INTERP> R;
