@@ -259,18 +259,21 @@ __device__ __forceinline__ bool valid255_cubic(float u, float v, int cols, int r
   quant32(u, ix, fx);
   quant32(v, iy, fy);
   if (ix >= 1 && iy >= 1 && ix + 2 < cols && iy + 2 < rows) return true;
-  const short *w = itab + ((fy << kInterBits) + fx) * 16;
+  // sum of the in-bounds taps of the 4x4 fixed-point table: two 16-byte loads, byte-masked 16-bit dot products
+  const uint4 *w = reinterpret_cast<const uint4 *>(itab + ((fy << kInterBits) + fx) * 16);
+  const uint4 wa = __ldg(w), wb = __ldg(w + 1);
+  unsigned cm = 0;
+#pragma unroll
+  for (int kx = 0; kx < 4; ++kx) cm |= ((unsigned)(ix - 1 + kx) < (unsigned)cols ? 1u : 0u) << (8 * kx);
+  const int r0 = __dp2a_hi((int)wa.y, (int)cm, __dp2a_lo((int)wa.x, (int)cm, 0));
+  const int r1 = __dp2a_hi((int)wa.w, (int)cm, __dp2a_lo((int)wa.z, (int)cm, 0));
+  const int r2 = __dp2a_hi((int)wb.y, (int)cm, __dp2a_lo((int)wb.x, (int)cm, 0));
+  const int r3 = __dp2a_hi((int)wb.w, (int)cm, __dp2a_lo((int)wb.z, (int)cm, 0));
   int S = 0;
-#pragma unroll
-  for (int ky = 0; ky < 4; ++ky) {
-    const int yy = iy - 1 + ky;
-    if ((unsigned)yy >= (unsigned)rows) continue;
-#pragma unroll
-    for (int kx = 0; kx < 4; ++kx) {
-      const int xx = ix - 1 + kx;
-      if ((unsigned)xx < (unsigned)cols) S += w[ky * 4 + kx];
-    }
-  }
+  if ((unsigned)(iy - 1) < (unsigned)rows) S += r0;
+  if ((unsigned)iy < (unsigned)rows) S += r1;
+  if ((unsigned)(iy + 1) < (unsigned)rows) S += r2;
+  if ((unsigned)(iy + 2) < (unsigned)rows) S += r3;
   int val = (255 * S + (1 << (kCoefBits - 1))) >> kCoefBits;
   return val >= 255;
 }

@@ -25,10 +25,15 @@ namespace {
 
 constexpr int TW = 32, TH = 32;          // tile of the accumulator handled by one CTA of the staged kernel
 constexpr int SWARPS = 4;                // warps per CTA, interior tiles (throughput: 8-row strips amortise the window fill)
-constexpr int RING_WARPS = 16;           // warps per CTA, border-ring tiles (few CTAs: latency-bound, so more warps per tile)
+#ifndef SSK_RING_WARPS
+#define SSK_RING_WARPS 8
+#endif
+#ifndef SSK_RING_MINB
+#define SSK_RING_MINB 2
+#endif
+constexpr int RING_WARPS = SSK_RING_WARPS;            // warps per CTA, border-ring tiles (heavier per frame than interior tiles: shorter chain per CTA)
 constexpr int GSH = TH + 8;              // staged rows: tile + 3 taps + rounding + drift
 constexpr int WWD = TW + 8;              // staged weight-tile row (floats)
-constexpr int kItabBytes = kInterTab * kInterTab * 16 * (int)sizeof(short);   // fixed-point bicubic table
 
 __device__ __forceinline__ bool is_affine_like(int type) { return type != MAP_HOMOGRAPHY; }
 
@@ -191,6 +196,10 @@ template <int DEPTH> struct StageGeom {
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int NKEEP> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NKEEP)); }
@@ -479,16 +488,19 @@ __device__ __noinline__ void issue_stage_ring(const FrameJob &job, const StagePl
     if ((unsigned)gy < (unsigned)a.src_rows && gx >= 0 && gx + G::ALIGN <= a.src_cols) {
       cp_async16(d, static_cast<const char *>(job.frame) + (int64_t)gy * a.src_step + (int64_t)gx * G::ES);
     } else {
+      // overhang: each element comes from its cv::borderInterpolate position (asynchronously, like the in-range
+      // chunks) or is the constant border value
       const int my = bmap(gy, a.src_rows, a.border);
-      const T *row = reinterpret_cast<const T *>(static_cast<const char *>(job.frame) + (int64_t)max(my, 0) * a.src_step);
+      const char *row = static_cast<const char *>(job.frame) + (int64_t)max(my, 0) * a.src_step;
 #pragma unroll
-      for (int e = 0; e < G::ALIGN; ++e) {     // independent loads: one memory latency per chunk, not one per element
+      for (int e = 0; e < G::ALIGN; ++e) {
         const int mx = bmap(gx + e, a.src_cols, a.border);
-        T v;
-        if (mx >= 0 && my >= 0) v = row[mx];
-        else if (DEPTH == SSK_32F) v = (T)a.bval[0];
-        else v = (T)0;                                   // constant border of integer frames: staged only for value 0
-        reinterpret_cast<T *>(d)[e] = v;
+        if (mx >= 0 && my >= 0) {
+          if (G::ES == 4) cp_async4(d + e * 4, row + (int64_t)mx * 4);
+          else reinterpret_cast<T *>(d)[e] = reinterpret_cast<const T *>(row)[mx];
+        } else {
+          reinterpret_cast<T *>(d)[e] = DEPTH == SSK_32F ? (T)a.bval[0] : (T)0;   // integer frames: staged only for value 0
+        }
       }
     }
   }
@@ -502,9 +514,12 @@ __device__ __noinline__ void issue_stage_ring(const FrameJob &job, const StagePl
         cp_async16(d, reinterpret_cast<const char *>(job.weights) + (int64_t)gy * a.w_step + (int64_t)gx * 4);
       } else {
         const bool yin = (unsigned)gy < (unsigned)a.src_rows;
-        const float *row = reinterpret_cast<const float *>(reinterpret_cast<const char *>(job.weights) + (int64_t)(yin ? gy : 0) * a.w_step);
+        const char *row = reinterpret_cast<const char *>(job.weights) + (int64_t)(yin ? gy : 0) * a.w_step;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) d[e] = (yin && (unsigned)(gx + e) < (unsigned)a.src_cols) ? row[gx + e] : 0.f;
+        for (int e = 0; e < 4; ++e) {
+          if (yin && (unsigned)(gx + e) < (unsigned)a.src_cols) cp_async4(d + e, row + (int64_t)(gx + e) * 4);
+          else d[e] = 0.f;
+        }
       }
     }
   }
@@ -541,7 +556,7 @@ __device__ __noinline__ StagePlan plan_stage_ring(const MapCoef &m, int bx0, int
 }
 
 template <int DEPTH, int INTERP, bool WEIGHTS, int MT, bool RING>
-__global__ void __launch_bounds__(TW * (RING ? RING_WARPS : SWARPS), RING ? 1 : 6) k_fused_staged(const __grid_constant__ WarpAccArgs a, const __grid_constant__ Tables tab,
+__global__ void __launch_bounds__(TW * (RING ? RING_WARPS : SWARPS), RING ? SSK_RING_MINB : 6) k_fused_staged(const __grid_constant__ WarpAccArgs a, const __grid_constant__ Tables tab,
                                                                const TileList tl) {
   typedef StageGeom<DEPTH> G;
   constexpr int N = Taps<INTERP>::N;
@@ -556,10 +571,6 @@ __global__ void __launch_bounds__(TW * (RING ? RING_WARPS : SWARPS), RING ? 1 : 
   // the pre-erosion flags of columns x-2 .. x+2)
   __shared__ unsigned long long s_hmask[RING ? TH + 4 : 1];
   __shared__ PackedPlan s_plan[KPLAN];
-  // ring tiles: the fixed-point bicubic table behind the validity test (32 KB, dynamic shared memory) so that the
-  // per-frame flag evaluation never waits on global memory
-  extern __shared__ __align__(16) short s_itab[];
-
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int tx, ty;
   if (RING) tile_of_block(tl, blockIdx.x, tx, ty);
@@ -569,10 +580,6 @@ __global__ void __launch_bounds__(TW * (RING ? RING_WARPS : SWARPS), RING ? 1 : 
   const int tw = min(TW, a.cols - bx0), th = min(TH, a.rows - by0);
   const int nrow = lane < tw ? max(0, min(GR, th - warp * GR)) : 0;
   if (INTERP == SSK_INTER_CUBIC && threadIdx.x < kInterTab) s_cubic[threadIdx.x] = tab.cubic[threadIdx.x];
-  if (RING && INTERP == SSK_INTER_CUBIC) {
-    const int4 *g = reinterpret_cast<const int4 *>(tab.cubic_itab);
-    for (int k = threadIdx.x; k < kItabBytes / 16; k += blockDim.x) reinterpret_cast<int4 *>(s_itab)[k] = __ldg(g + k);
-  }
 
   // accumulator tile -> shared memory; 16-byte accesses when the tile is complete and the pitch allows it
   const bool vec = (a.cols & 3) == 0 && tw == TW;
@@ -628,23 +635,43 @@ __global__ void __launch_bounds__(TW * (RING ? RING_WARPS : SWARPS), RING ? 1 : 
     if (RING && plan.staged) {
       // pre-erosion validity of the tile and its 2-px halo (outside the image: erode border value 255), one warp
       // per row, packed by ballots
+      // columns -2 .. 29 of a row go through one ballot; columns 30 .. 33 of all rows of this warp share one more
       const MapCoef m = a.jobs[j].map;
-#pragma unroll 1
-      for (int fy = warp; fy < TH + 4; fy += NWARP) {
-        const int gy = by0 - 2 + fy;
-        unsigned long long bits = 0;
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          const int gx = bx0 - 2 + half * 32 + lane;
-          bool okf = true;
-          if ((half == 0 || lane < 4) && gx >= 0 && gy >= 0 && gx < a.cols && gy < a.rows) {
-            float u, v;
-            map_xy(m, (float)gx, (float)gy, u, v);
-            okf = valid255(INTERP, u, v, a.src_cols, a.src_rows, s_itab);
-          }
-          bits |= (unsigned long long)__ballot_sync(0xffffffffu, okf) << (32 * half);
+      constexpr int NR = (TH + 4 + NWARP - 1) / NWARP;     // rows of the flag field per warp
+      static_assert(!RING || NR <= 8, "ring flags: one nibble per row in the second ballot");
+      unsigned lo[NR];
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const int gy = by0 - 2 + warp + i * NWARP, gx = bx0 - 2 + lane;
+        bool okf = true;
+        if (warp + i * NWARP < TH + 4 && gx >= 0 && gy >= 0 && gx < a.cols && gy < a.rows) {
+          float u, v;
+          const ColMap<MT> cmf(m, (float)gx);
+          cmf((float)gy, u, v);
+          okf = valid255(INTERP, u, v, a.src_cols, a.src_rows, tab.cubic_itab);
         }
-        if (lane == 0) s_hmask[fy] = bits & (bits >> 1) & (bits >> 2) & (bits >> 3) & (bits >> 4);
+        lo[i] = __ballot_sync(0xffffffffu, okf);
+      }
+      unsigned hi;
+      {
+        const int i = lane >> 2, fy = warp + i * NWARP;
+        const int gy = by0 - 2 + fy, gx = bx0 + 30 + (lane & 3);
+        bool okf = true;
+        if (i < NR && fy < TH + 4 && gy >= 0 && gx < a.cols && gy < a.rows) {
+          float u, v;
+          const ColMap<MT> cmf(m, (float)gx);
+          cmf((float)gy, u, v);
+          okf = valid255(INTERP, u, v, a.src_cols, a.src_rows, tab.cubic_itab);
+        }
+        hi = __ballot_sync(0xffffffffu, okf);
+      }
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const int fy = warp + i * NWARP;
+        if (lane == 0 && fy < TH + 4) {
+          const unsigned long long bits = (unsigned long long)lo[i] | ((unsigned long long)((hi >> (4 * i)) & 0xFu) << 32);
+          s_hmask[fy] = bits & (bits >> 1) & (bits >> 2) & (bits >> 3) & (bits >> 4);
+        }
       }
     }
     cp_async_wait<1>();            // frame j's group has landed (frame j+1's may still be in flight)
@@ -748,13 +775,7 @@ void launch_staged_ring(const WarpAccArgs &a, const Tables &tab, const TileList 
     cudaEventRecord(static_cast<cudaEvent_t>(a.ev_fork), s);
     cudaStreamWaitEvent(ring_stream, static_cast<cudaEvent_t>(a.ev_fork), 0);
   }
-  const int ring_smem = INTERP == SSK_INTER_CUBIC ? kItabBytes : 0;
-  static bool attr_set = false;   // per instantiation
-  if (!attr_set && ring_smem) {
-    cudaFuncSetAttribute(k_fused_staged<DEPTH, INTERP, WEIGHTS, MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_smem);
-    attr_set = true;
-  }
-  k_fused_staged<DEPTH, INTERP, WEIGHTS, MT, true><<<nring, ring_block, ring_smem, ring_stream>>>(a, tab, tl);
+  k_fused_staged<DEPTH, INTERP, WEIGHTS, MT, true><<<nring, ring_block, 0, ring_stream>>>(a, tab, tl);
   count_launch();
   if (a.side_stream) cudaEventRecord(static_cast<cudaEvent_t>(a.ev_join), ring_stream);
   k_fused_staged<DEPTH, INTERP, WEIGHTS, MT, false><<<dim3(tl.ntx - 2, tl.nty - 2), block, 0, s>>>(a, tab, tl);
