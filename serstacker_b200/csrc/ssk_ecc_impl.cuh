@@ -452,6 +452,9 @@ struct Walk {
   }
 };
 
+// keeps a base pointer as one 64-bit register value (stops the compiler from re-adding its parts per access)
+template <typename T> __device__ __forceinline__ const T *opaque_ptr(const T *p) { asm volatile("" : "+l"(p)); return p; }
+
 __device__ __forceinline__ int cvround32(float v) { return __float2int_rn(__fmul_rn(v, 32.0f)); }
 
 // map_xy with the map kind fixed at compile time (the passes are instantiated per transform type)
@@ -490,8 +493,9 @@ __device__ __forceinline__ float lin_sample(const float *__restrict__ p, int col
   const float wx0 = 1.0f - tx, wy0 = 1.0f - ty;
   const int x0 = min(max(ix, 0), cols - 1), x1 = min(max(ix + 1, 0), cols - 1);
   const int y0 = min(max(iy, 0), rows - 1), y1 = min(max(iy + 1, 0), rows - 1);
-  const int o0 = y0 * cols, o1 = y1 * cols;     // 32-bit offsets: a level has far fewer than 2^31 pixels
-  const float s00 = __ldg(p + (o0 + x0)), s01 = __ldg(p + (o0 + x1)), s10 = __ldg(p + (o1 + x0)), s11 = __ldg(p + (o1 + x1));
+  // unsigned 32-bit offsets (a level has far fewer than 2^31 pixels): one wide multiply-add per tap address
+  const unsigned o0 = (unsigned)(y0 * cols), o1 = (unsigned)(y1 * cols);
+  const float s00 = __ldg(p + (o0 + (unsigned)x0)), s01 = __ldg(p + (o0 + (unsigned)x1)), s10 = __ldg(p + (o1 + (unsigned)x0)), s11 = __ldg(p + (o1 + (unsigned)x1));
   float out = __fadd_rn(__fmul_rn(s00, __fmul_rn(wy0, wx0)), __fmul_rn(s01, __fmul_rn(wy0, tx)));
   out = __fadd_rn(out, __fmul_rn(s10, __fmul_rn(ty, wx0)));
   out = __fadd_rn(out, __fmul_rn(s11, __fmul_rn(ty, tx)));
@@ -511,7 +515,7 @@ __device__ void pass_ic(Ctx &c, int lvl, bool lm_masks) {
   constexpr int NS = 2 + M;
   Shared &S = *c.S;
   const EccLevel &L = c.cfg->lv[lvl];
-  const float *__restrict__ cur = c.frame->pyr + L.cur_off;
+  const float *__restrict__ cur = opaque_ptr(c.frame->pyr + L.cur_off);
   const float *__restrict__ ref = L.ref, *__restrict__ gxp = L.gx, *__restrict__ gyp = L.gy;
   // c_ecc_inverse_compositional leaves the reference mask out of rhs / CMA (ecc2.cc:1752-1763: only the remapped
   // current mask); c_ecclm_inverse_compositional ORs it in (ecc2.cc:1901-1904)
@@ -707,10 +711,11 @@ __device__ void pass_forward(Ctx &c, int lvl) {
 
 // compute_correlation (ecc2.cc:65-137): sums = [ n, Sf, Sg, Sf2, Sg2, Sfg ] over (remap(255) >= 254) & refmask,
 // g = remap(current, INTER_LINEAR, BORDER_CONSTANT 0)
+template <int MT>
 __device__ void pass_rho(Ctx &c) {
   Shared &S = *c.S;
   const EccLevel &L = c.cfg->lv[0];
-  const float *__restrict__ cur = c.frame->pyr + L.cur_off;
+  const float *__restrict__ cur = opaque_ptr(c.frame->pyr + L.cur_off);
   const float *__restrict__ ref = L.ref;
   const uint8_t *__restrict__ rmask = L.refmask;
   const int cols = L.cols, rows = L.rows;
@@ -722,7 +727,7 @@ __device__ void pass_rho(Ctx &c) {
 #pragma unroll 2
   for (; w.i < n; w.next()) {
     float u, v;
-    map_xy(m, (float)w.x, (float)w.y, u, v);
+    map_xy_t<MT>(m, (float)w.x, (float)w.y, u, v);
     const int sx = cvround32(u), sy = cvround32(v);
     bool ok = lin_valid(sx, sy, cols, rows);
     if (rmask) ok = ok && rmask[w.i] != 0;
@@ -1090,10 +1095,11 @@ __device__ void ecch_align(Ctx &c, bool main_pass) {
   }
 }
 
+template <int MT>
 __device__ double correlation(Ctx &c) {
   Shared &S = *c.S;
   T0_BEGIN set_pass_params(S, S.t); T0_END
-  pass_rho(c);
+  pass_rho<MT>(c);
   T0_BEGIN S.rho = rho_from_sums(S.tot); T0_END
   return S.rho;
 }
@@ -1133,7 +1139,7 @@ __global__ void __launch_bounds__(NT, SSK_ECC_MINB) k_ecc(const __grid_constant_
     S.t = tt;
     T0_END
     ecch_align<METHOD, SSK_MOTION_TRANSLATION>(c, false);
-    const double rho = correlation(c);
+    const double rho = correlation<MAP_TRANSLATION>(c);
     if (rho < 0.75 * cfg.min_rho) ok = false;
     T0_BEGIN
     const float tx = S.t.params[0], ty = S.t.params[1];
@@ -1144,7 +1150,7 @@ __global__ void __launch_bounds__(NT, SSK_ECC_MINB) k_ecc(const __grid_constant_
   if (ok) {
     ecch_align<METHOD, TYPE>(c, true);
     if (cfg.check_rho) {
-      const double rho = correlation(c);
+      const double rho = correlation<MapKind<TYPE>::MT>(c);
       if (rho < cfg.min_rho) ok = false;
     }
   }
