@@ -61,6 +61,7 @@ struct W1Args {
   int full_rows, full_cols;
   int batch;
   int2 *axis_tab;                                 // scratch [full_cols + full_rows]: per output column / row source index + fraction
+  int *axis_tab_built;                            // host flag (optional): the tables in axis_tab are already those of this geometry
 };
 int w1_num_blocks(int rows, int cols);
 int launch_w1(const W1Args &a, cudaStream_t s);

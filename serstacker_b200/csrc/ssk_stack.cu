@@ -64,6 +64,7 @@ struct ssk_stack {
   cudaStream_t side = nullptr;           // border-ring kernel of the fused warp+accumulate stage
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   DevBuf ref_staging, axis_tab;
+  int axis_tab_built = 0;                // W1 up-sampling tables of this geometry are in axis_tab
   // host frames: sub-chunks of `host_chunk` frames rotate through `nsets` sets of frame slots; a copy stream uploads
   // sub-chunk k+1 while sub-chunk k is processed
   cudaStream_t copy_stream = nullptr;
@@ -142,6 +143,7 @@ static int stack_alloc_slots(ssk_stack *h) {
     if (int e = h->partials.ensure((size_t)B * 2 * h->w1_nb * 8)) return e;
     if (int e = h->stats.ensure((size_t)B * 4 * 8)) return e;
     if (int e = h->axis_tab.ensure((size_t)(h->rows + h->cols + 8) * sizeof(int2))) return e;
+    h->axis_tab_built = 0;
     if (int e = h->d_weight_ptrs.ensure(sizeof(void *) * B)) return e;
     if (int e = h->d_half_ptrs.ensure(sizeof(void *) * B)) return e;
     if (int e = h->d_half2_ptrs.ensure(sizeof(void *) * B)) return e;
@@ -323,7 +325,7 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
     w.depth_scale = 20.0;   // frames are CV_32F when they reach compute_weights
     w.gmap_ptrs = h->d_gmap_ptrs.as<float *>(); w.partials = h->partials.as<double>(); w.stats = h->stats.as<double>();
     w.out_ptrs = h->d_weight_ptrs.as<float *>(); w.full_rows = h->rows; w.full_cols = h->cols; w.batch = n;
-    w.axis_tab = h->axis_tab.as<int2>();
+    w.axis_tab = h->axis_tab.as<int2>(); w.axis_tab_built = &h->axis_tab_built;
     if (int e = launch_w1(w, s)) return e;
   }
   SSK_CUDA(cudaEventRecord(h->ev[2], s));
