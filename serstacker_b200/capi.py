@@ -24,7 +24,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 
 MOTION_TRANSLATION, MOTION_EUCLIDEAN, MOTION_SCALED_EUCLIDEAN, MOTION_AFFINE, MOTION_HOMOGRAPHY = 0, 1, 2, 3, 4
 ECC_FORWARD_ADDITIVE, ECC_INVERSE_COMPOSITIONAL, ECC_LM, ECC_INVERSE_COMPOSITIONAL_LM = 0, 1, 2, 3
-INTER_NEAREST, INTER_LINEAR, INTER_CUBIC = 0, 1, 2
+INTER_NEAREST, INTER_LINEAR, INTER_CUBIC, INTER_AREA = 0, 1, 2, 3
 BORDER_CONSTANT, BORDER_REPLICATE, BORDER_REFLECT, BORDER_WRAP, BORDER_REFLECT101, BORDER_TRANSPARENT = 0, 1, 2, 3, 4, 5
 ACC_WEIGHTED_AVERAGE, ACC_BAYER_AVERAGE = 0, 1
 STACK_AVERAGE, STACK_WEIGHTED_AVERAGE, STACK_BAYER_AVERAGE = 0, 1, 2

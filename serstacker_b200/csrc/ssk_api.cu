@@ -93,6 +93,7 @@ Scratch &scratch() { static thread_local Scratch s; return s; }
 int do_remap(cudaStream_t s, DevBuf &st_src, DevBuf &st_map, DevBuf &st_mask, DevBuf &st_out, DevBuf &st_tmp,
              const ssk_transform *t, const ssk_mat *rmap, const ssk_mat *src, ssk_mat *dst, const ssk_mat *src_mask,
              ssk_mat *dst_mask, int interp, int border, const double bv[4]) {
+  interp = remap_interp(interp);
   Tables tab;
   if (int e = get_tables(&tab)) return e;
   SSK_REQUIRE(t || rmap, "remap: either a transform or an explicit map is required");

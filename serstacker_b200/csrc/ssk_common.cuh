@@ -297,5 +297,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
+// cv::remap: `if (interpolation == INTER_AREA) interpolation = INTER_LINEAR`
+inline int remap_interp(int v) { return v == SSK_INTER_AREA ? SSK_INTER_LINEAR : v; }
 
 }  // namespace ssk

@@ -227,7 +227,7 @@ int Ecch::build_config() {
     L.RMA = rma[l];
   }
   cfg.method = opts.method;
-  cfg.interp = opts.interpolation;
+  cfg.interp = remap_interp(opts.interpolation);
   cfg.max_iterations = opts.max_iterations;
   cfg.update_step_scale = opts.update_step_scale;
   cfg.epsx = opts.epsx;

@@ -347,7 +347,7 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
   a.src_step = geom.step; a.w_step = (int64_t)h->cols * 4;
   a.depth = d; a.cn = cn; a.scale = geom.scale;
   const ssk_registration_options &ro = h->o.registration;
-  a.interp = h->o.enable_registration ? ro.interpolation : SSK_INTER_NEAREST;
+  a.interp = h->o.enable_registration ? remap_interp(ro.interpolation) : SSK_INTER_NEAREST;
   a.border = ro.border_mode;
   for (int i = 0; i < 4; ++i) a.bval[i] = (float)ro.border_value[i];
   a.use_weights = weighted ? 1 : 0;

@@ -66,6 +66,18 @@ def test_remap_matches_cv2(gpu, interp, border):
         assert np.abs(got2 - want).max() <= 2e-6
 
 
+def test_remap_inter_area_is_linear(gpu):
+    """cv::remap replaces INTER_AREA by INTER_LINEAR (ECC_INTER_AREA, ecc2.h:37): same through the C ABI."""
+    from serstacker_b200 import api
+    rng = np.random.default_rng(77)
+    src = rng.random((83, 131)).astype(np.float32)
+    t, o = _rand_transform(rng, 3)
+    rmap = o.create_remap((131, 83))
+    want = cv2.remap(src, rmap, None, cv2.INTER_AREA, borderMode=cv2.BORDER_REFLECT101)
+    got, _ = api.remap(t, None, src, interpolation=cv2.INTER_AREA, border_mode=cv2.BORDER_REFLECT101, border_value=(0, 0, 0, 0))
+    assert np.array_equal(got, want)
+
+
 def test_remap_transparent_linear(gpu):
     from serstacker_b200 import api
     rng = np.random.default_rng(5)
