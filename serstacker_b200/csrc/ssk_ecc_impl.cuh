@@ -528,9 +528,10 @@ __device__ void pass_ic(Ctx &c, int lvl, bool lm_masks) {
   for (int k = 0; k < NS; ++k) acc[k] = 0.0;
   int nvalid = 0;
   const int n = cols * rows;
-  // Branch-free body (invalid pixels contribute an exact 0.0), so that two pixels per thread are in flight.
+  // Branch-free body (invalid pixels contribute an exact 0.0), so that several pixels per thread are in flight.
   Walk w(c.rank * NT + c.tid, c.csize * NT, cols);
-#pragma unroll 2
+  constexpr int kUnroll = 3;   // pixels in flight per thread (measured: 2 -> 3 is -4 % on the pass, 4 is slower)
+#pragma unroll kUnroll
   for (; w.i < n; w.next()) {
     const float x = (float)w.x, y = (float)w.y;
     float u, v;
