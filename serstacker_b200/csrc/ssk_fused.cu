@@ -204,6 +204,35 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int NKEEP> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NKEEP)); }
 
+// ---- TMA staging (interior tiles, 32F frame + weight map): one elected thread asks the tensor copy engine for the
+// whole GSH x WD window of both images; completion is counted on an mbarrier every thread of the CTA waits on.
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "SSK_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra SSK_MBAR_DONE;\n"
+      "bra SSK_MBAR_WAIT;\n"
+      "SSK_MBAR_DONE:\n"
+      "}\n" ::"r"(mbar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(unsigned smem_dst, const void *tmap, int x, int y, unsigned mbar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_dst),
+               "l"(tmap), "r"(x), "r"(y), "r"(mbar)
+               : "memory");
+}
+// the tensor maps live in global memory and are rewritten by the host between launches: make the copy engine re-read them
+__device__ __forceinline__ void tmap_acquire(const void *tmap) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
+}
+
 struct StagePlan { int staged, sx0, sy0, sxw; };   // staged: tile safe and footprint fits; sxw: weight-tile origin
 // Plans of all frames of a launch are computed once per CTA (one frame per thread) and kept in shared memory.
 constexpr int KPLAN = 256;                          // frames per launch (longer batches are split by the launcher)
@@ -565,8 +594,9 @@ __global__ void __launch_bounds__(TW * (RING ? RING_WARPS : SWARPS), RING ? SSK_
   __shared__ float s_acc[TH][TW];                  // running mean of the tile (on chip for the whole batch)
   __shared__ float s_w[TH][TW];                    // running weight sum of the tile
   __shared__ float4 s_cubic[kInterTab];
-  __shared__ __align__(16) unsigned char s_f[2][GSH * G::ROWB];
-  __shared__ __align__(16) float s_g[2][GSH * WWD];
+  __shared__ __align__(128) unsigned char s_f[2][GSH * G::ROWB];   // 128-byte alignment: TMA destination
+  __shared__ __align__(128) float s_g[2][GSH * WWD];
+  __shared__ __align__(8) unsigned long long s_mbar[2];           // TMA path: one transaction barrier per buffer
   // ring tiles: per row of the tile + 2-px halo, the horizontally eroded validity of the tile columns (bit x = AND of
   // the pre-erosion flags of columns x-2 .. x+2)
   __shared__ unsigned long long s_hmask[RING ? TH + 4 : 1];
@@ -607,6 +637,26 @@ __global__ void __launch_bounds__(TW * (RING ? RING_WARPS : SWARPS), RING ? SSK_
     }
     s_plan[jj] = pp;
   }
+  // TMA staging: interior tiles of 32F frames with weight maps when the host supplied tensor maps (ssk_stack.cu)
+  const bool use_tma = !RING && DEPTH == SSK_32F && WEIGHTS && a.tmap_frames != nullptr && a.tmap_weights != nullptr;
+  const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(&s_mbar[0]);
+  if (use_tma && threadIdx.x == 0) {
+    mbar_init(mbar0, 1);
+    mbar_init(mbar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  unsigned phase = 0;   // bit b: parity the next wait on buffer b expects
+  auto tma_stage = [&](int jj, const StagePlan &p, int b) {
+    if (threadIdx.x == 0) {
+      const char *tf = static_cast<const char *>(a.tmap_frames) + (size_t)jj * 128, *tw = static_cast<const char *>(a.tmap_weights) + (size_t)jj * 128;
+      tmap_acquire(tf);
+      tmap_acquire(tw);
+      const unsigned mb = mbar0 + 8 * b;
+      mbar_expect_tx(mb, (unsigned)(GSH * G::ROWB + GSH * WWD * 4));
+      tma_load_2d((unsigned)__cvta_generic_to_shared(s_f[b]), tf, p.sx0, p.sy0, mb);
+      tma_load_2d((unsigned)__cvta_generic_to_shared(s_g[b]), tw, p.sxw, p.sy0, mb);
+    }
+  };
   __syncthreads();
   auto plan_of = [&](int jj) { const PackedPlan q = s_plan[jj]; StagePlan p; p.staged = q.staged; p.sx0 = q.sx0; p.sy0 = q.sy0; p.sxw = q.sxw; return p; };
 
@@ -617,7 +667,11 @@ __global__ void __launch_bounds__(TW * (RING ? RING_WARPS : SWARPS), RING ? SSK_
   StagePlan plan = {0, 0, 0, 0};
   if (j < a.njobs) {
     plan = plan_of(j);
-    if (plan.staged) { if (RING) issue_stage_ring<DEPTH>(a.jobs[j], plan, a, WEIGHTS, s_f[0], s_g[0]); else issue_stage<DEPTH>(a.jobs[j], plan, a, WEIGHTS, s_f[0], s_g[0]); }
+    if (plan.staged) {
+      if (RING) issue_stage_ring<DEPTH>(a.jobs[j], plan, a, WEIGHTS, s_f[0], s_g[0]);
+      else if (use_tma) tma_stage(j, plan, 0);
+      else issue_stage<DEPTH>(a.jobs[j], plan, a, WEIGHTS, s_f[0], s_g[0]);
+    }
   }
   cp_async_commit();
   __syncthreads();
@@ -629,7 +683,11 @@ __global__ void __launch_bounds__(TW * (RING ? RING_WARPS : SWARPS), RING ? SSK_
     StagePlan plan_n = {0, 0, 0, 0};
     if (jn < a.njobs) {
       plan_n = plan_of(jn);
-      if (plan_n.staged) { if (RING) issue_stage_ring<DEPTH>(a.jobs[jn], plan_n, a, WEIGHTS, s_f[buf ^ 1], s_g[buf ^ 1]); else issue_stage<DEPTH>(a.jobs[jn], plan_n, a, WEIGHTS, s_f[buf ^ 1], s_g[buf ^ 1]); }
+      if (plan_n.staged) {
+        if (RING) issue_stage_ring<DEPTH>(a.jobs[jn], plan_n, a, WEIGHTS, s_f[buf ^ 1], s_g[buf ^ 1]);
+        else if (use_tma) tma_stage(jn, plan_n, buf ^ 1);
+        else issue_stage<DEPTH>(a.jobs[jn], plan_n, a, WEIGHTS, s_f[buf ^ 1], s_g[buf ^ 1]);
+      }
     }
     cp_async_commit();
     if (RING && plan.staged) {
@@ -674,8 +732,13 @@ __global__ void __launch_bounds__(TW * (RING ? RING_WARPS : SWARPS), RING ? SSK_
         }
       }
     }
-    cp_async_wait<1>();            // frame j's group has landed (frame j+1's may still be in flight)
-    __syncthreads();
+    if (use_tma) {
+      // the copy engine signals the buffer's barrier when both windows of frame j have landed: no CTA barrier needed
+      if (plan.staged) { mbar_wait(mbar0 + 8 * buf, (phase >> buf) & 1u); phase ^= 1u << buf; }
+    } else {
+      cp_async_wait<1>();          // frame j's group has landed (frame j+1's may still be in flight)
+      __syncthreads();
+    }
 
     float *s_acc0 = &s_acc[warp * GR][lane], *s_w0 = &s_w[warp * GR][lane];
     if (plan.staged) {
@@ -804,6 +867,9 @@ void launch_staged(const WarpAccArgs &a, const Tables &tab, const TileList &tl, 
 
 }  // namespace
 
+int staged_box_w() { return StageGeom<SSK_32F>::WD; }
+int staged_box_h() { return GSH; }
+
 int launch_warp_accumulate(const WarpAccArgs &a_in, const Tables &tab, cudaStream_t s) {
   WarpAccArgs a = a_in;
   SSK_REQUIRE(a.interp == SSK_INTER_NEAREST || a.interp == SSK_INTER_LINEAR || a.interp == SSK_INTER_CUBIC,
@@ -823,6 +889,12 @@ int launch_warp_accumulate(const WarpAccArgs &a_in, const Tables &tab, cudaStrea
     const int njobs = a.njobs;
     for (int j0 = 0; j0 < njobs; j0 += KPLAN) {     // the per-CTA plan table holds KPLAN frames
       a.jobs = jobs + j0; a.njobs = std::min(KPLAN, njobs - j0);
+      if (a_in.tmap_frames && a_in.tmap_weights) {
+        a.tmap_frames = static_cast<const char *>(a_in.tmap_frames) + (size_t)j0 * 128;
+        a.tmap_weights = static_cast<const char *>(a_in.tmap_weights) + (size_t)j0 * 128;
+      } else {
+        a.tmap_frames = a.tmap_weights = nullptr;
+      }
       if (a.depth == SSK_32F) launch_staged<SSK_32F>(a, tab, tl, nring, s);
       else if (a.depth == SSK_16U) launch_staged<SSK_16U>(a, tab, tl, nring, s);
       else launch_staged<SSK_8U>(a, tab, tl, nring, s);

@@ -1,5 +1,6 @@
 // Process-wide runtime state: error string, launch counter, remap tables.
 #include "ssk_common.cuh"
+#include <cuda.h>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -19,6 +20,35 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
   snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
   g_err = buf;
   return SSK_ERR_CUDA;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links cudart only).
+// A 2-D fp32 image (cols x rows, row pitch step_bytes) with a box of box_w x box_h elements, no swizzle, out-of-bounds
+// elements read as zero.  Returns false when the driver entry point is missing or the geometry is not encodable
+// (base not 16-byte aligned, pitch not a multiple of 16); the caller then stays on the cp.async staging path.
+bool encode_tmap_2d_f32(void *out128, const void *base, int cols, int rows, int64_t step_bytes, int box_w, int box_h) {
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(sym);
+    cudaGetLastError();
+  }
+  if (!fn) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (step_bytes & 15) || box_w > 256 || box_h > 256 || ((box_w * 4) & 15)) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)step_bytes};
+  const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(static_cast<CUtensorMap *>(out128), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }

@@ -55,6 +55,11 @@ struct ssk_stack {
   DevBuf d_slot_ptrs, d_weight_ptrs, d_half_ptrs, d_half2_ptrs, d_gmap_ptrs;
   DevBuf d_user_ptrs[kRing];
   PinnedBuf h_user_ptrs[kRing];
+  // TMA staging of the fused kernel (32F single-channel frames): 128-byte tensor maps per frame slot / weight slot,
+  // and per user frame of a device-frame chunk (same ring as the pointer tables)
+  DevBuf d_tmaps_slots, d_tmaps_weights, d_tmaps_user[kRing];
+  PinnedBuf h_tmaps_user[kRing];
+  bool tma_slots = false, tma_weights = false;
   cudaEvent_t ring_ev[kRing] = {};
   int ring_pos = 0;
   PinnedBuf h_counter;
@@ -103,6 +108,22 @@ static int stack_alloc_slots(ssk_stack *h) {
   for (int b = 0; b < B; ++b) p[b] = h->frame_slots.as<char>() + frame_bytes * b;
   if (int e = h->d_slot_ptrs.ensure(sizeof(void *) * B)) return e;
   SSK_CUDA(cudaMemcpy(h->d_slot_ptrs.p, p.data(), sizeof(void *) * B, cudaMemcpyHostToDevice));
+  h->tma_slots = false;
+  if (d == SSK_32F && cn == 1 && !getenv("SSK_NO_TMA")) {
+    std::vector<unsigned char> maps((size_t)B * 128);
+    bool ok = true;
+    for (int b = 0; b < B && ok; ++b)
+      ok = encode_tmap_2d_f32(maps.data() + (size_t)b * 128, p[b], h->cols, h->rows, (int64_t)h->cols * 4, staged_box_w(), staged_box_h());
+    if (ok) {
+      if (int e = h->d_tmaps_slots.ensure(maps.size())) return e;
+      SSK_CUDA(cudaMemcpy(h->d_tmaps_slots.p, maps.data(), maps.size(), cudaMemcpyHostToDevice));
+      for (int r = 0; r < kRing; ++r) {
+        if (int e = h->d_tmaps_user[r].ensure(maps.size())) return e;
+        if (int e = h->h_tmaps_user[r].ensure(maps.size())) return e;
+      }
+      h->tma_slots = true;
+    }
+  }
   if (int e = h->jobs.ensure(sizeof(FrameJob) * B)) return e;
   if (int e = h->counter.ensure(sizeof(int))) return e;
   if (int e = h->h_counter.ensure(sizeof(int))) return e;
@@ -150,6 +171,18 @@ static int stack_alloc_slots(ssk_stack *h) {
     if (int e = h->d_gmap_ptrs.ensure(sizeof(void *) * B)) return e;
     for (int b = 0; b < B; ++b) p[b] = h->weight_slots.as<float>() + npix * b;
     SSK_CUDA(cudaMemcpy(h->d_weight_ptrs.p, p.data(), sizeof(void *) * B, cudaMemcpyHostToDevice));
+    h->tma_weights = false;
+    if (!getenv("SSK_NO_TMA")) {
+      std::vector<unsigned char> maps((size_t)B * 128);
+      bool ok = true;
+      for (int b = 0; b < B && ok; ++b)
+        ok = encode_tmap_2d_f32(maps.data() + (size_t)b * 128, p[b], h->cols, h->rows, (int64_t)h->cols * 4, staged_box_w(), staged_box_h());
+      if (ok) {
+        if (int e = h->d_tmaps_weights.ensure(maps.size())) return e;
+        SSK_CUDA(cudaMemcpy(h->d_tmaps_weights.p, maps.data(), maps.size(), cudaMemcpyHostToDevice));
+        h->tma_weights = true;
+      }
+    }
     for (int b = 0; b < B; ++b) p[b] = h->half_slots.as<float>() + half_px * b;
     SSK_CUDA(cudaMemcpy(h->d_half_ptrs.p, p.data(), sizeof(void *) * B, cudaMemcpyHostToDevice));
     for (int b = 0; b < B; ++b) p[b] = h->half2_slots.as<float>() + half_px * b;
@@ -256,6 +289,7 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
   geom.rows = h->rows; geom.cols = h->cols; geom.depth = d; geom.cn = cn; geom.scale = bpp_scale(d, h->bpp);
   geom.data = nullptr;
   const void *const *d_frame_ptrs;
+  const void *d_tmaps = nullptr;          // tensor maps of this chunk's frames (TMA staging), if available
   h->frames_aligned = true;
   if (frames[0].mem == SSK_MEM_DEVICE) {
     // frames already resident: upload this chunk's pointer table through a small pinned ring
@@ -269,6 +303,16 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
       if (reinterpret_cast<uintptr_t>(frames[i].data) & 15) h->frames_aligned = false;
     }
     SSK_CUDA(cudaMemcpyAsync(h->d_user_ptrs[r].p, hp, sizeof(void *) * n, cudaMemcpyHostToDevice, s));
+    if (h->tma_slots && h->tma_weights && h->frames_aligned) {
+      unsigned char *hm = h->h_tmaps_user[r].as<unsigned char>();
+      bool ok = true;
+      for (int i = 0; i < n && ok; ++i)
+        ok = encode_tmap_2d_f32(hm + (size_t)i * 128, frames[i].data, h->cols, h->rows, (int64_t)frames[i].step, staged_box_w(), staged_box_h());
+      if (ok) {
+        SSK_CUDA(cudaMemcpyAsync(h->d_tmaps_user[r].p, hm, (size_t)n * 128, cudaMemcpyHostToDevice, s));
+        d_tmaps = h->d_tmaps_user[r].p;
+      }
+    }
     SSK_CUDA(cudaEventRecord(h->ring_ev[r], s));
     d_frame_ptrs = h->d_user_ptrs[r].as<const void *>();
     geom.step = frames[0].step;
@@ -276,6 +320,7 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
     SSK_REQUIRE(set >= 0, "internal: host frames without a slot set");
     SSK_CUDA(cudaStreamWaitEvent(s, h->set_full[set], 0));
     d_frame_ptrs = h->d_slot_ptrs.as<const void *>() + (size_t)set * h->host_chunk;
+    if (h->tma_slots && h->tma_weights) d_tmaps = h->d_tmaps_slots.as<char>() + (size_t)set * h->host_chunk * 128;
     geom.step = (int64_t)rowb;
   }
   SSK_CUDA(cudaEventRecord(h->ev[0], s));
@@ -359,6 +404,8 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
     make_transform(&t0, h->o.enable_registration ? ro.motion_type : SSK_MOTION_TRANSLATION);
     a.map_type = make_mapcoef(t0).type;
   }
+  a.tmap_frames = (weighted && d_tmaps) ? d_tmaps : nullptr;
+  a.tmap_weights = (weighted && d_tmaps) ? h->d_tmaps_weights.p : nullptr;
   a.acc = h->acc_h.a.acc.as<float>(); a.wacc = h->acc_h.a.wacc.as<float>();
   if (int e = launch_warp_accumulate(a, h->tab, s)) return e;
   SSK_CUDA(cudaEventRecord(h->ev[4], s));

@@ -30,11 +30,18 @@ struct WarpAccArgs {
   int stage_aligned;      // all frame / weight-map base pointers are 16-byte aligned (enables cp.async staging)
   int map_type;           // MAP_* common to all jobs of the batch (-1: mixed / unknown -> generic kernel)
   void *side_stream, *ev_fork, *ev_join;   // host only: optional side stream (+2 events) for the border-ring kernel
+  // optional TMA staging of the interior tiles (32F frames + weight maps): device arrays of 128-byte tensor maps, one per
+  // job, box = staged_box_w() x staged_box_h() elements; null -> cp.async staging
+  const void *tmap_frames, *tmap_weights;
   float *acc;             // running mean, rows x cols x cn (dense)
   float *wacc;            // running weight sum, rows x cols (dense)
 };
 
 int launch_warp_accumulate(const WarpAccArgs &a, const Tables &tab, cudaStream_t stream);
+// geometry of the staged source window of an interior tile (32F frames), for the tensor maps of the TMA path
+int staged_box_w();
+int staged_box_h();
+bool encode_tmap_2d_f32(void *out128, const void *base, int cols, int rows, int64_t step_bytes, int box_w, int box_h);
 
 // cv::remap of a CV_32F image (cn 1..4) by an analytic map or an explicit CV_32FC2 map.
 struct RemapArgs {
