@@ -278,3 +278,84 @@ def pyrup_f32(src, dsize):
     if dh > 2 * h:
         D = np.concatenate([D, D[-1:]], 0)
     return (D[:dh] * f32(1.0 / 64.0)).astype(f32)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# cv::resize(INTER_AREA), down-scaling, CV_32FC1 (modules/imgproc/src/resize.cpp: computeResizeAreaTab,
+# ResizeArea_Invoker, ResizeAreaFast_Invoker, ResizeAreaFastVec_SIMD_32f).  Used by scaleImage for ecc.scale other
+# than 0.5 (c_frame_registration.cc:242-247) and by compute_local_variance_map's uscale stage
+# (c_local_variance_sharpness_measure.cc:231-234).
+# ---------------------------------------------------------------------------------------------------------
+def _area_tab(ssize, dsize, scale):
+    import math
+    tab = []
+    for dx in range(dsize):
+        fsx1 = dx * scale
+        cell = min(scale, ssize - fsx1)
+        fsx2 = fsx1 + cell
+        sx1, sx2 = math.ceil(fsx1), math.floor(fsx2)
+        sx2 = min(sx2, ssize - 1)
+        sx1 = min(sx1, sx2)
+        if sx1 - fsx1 > 1e-3:
+            tab.append((dx, sx1 - 1, f32((sx1 - fsx1) / cell)))
+        for sx in range(sx1, sx2):
+            tab.append((dx, sx, f32(1.0 / cell)))
+        if fsx2 - sx2 > 1e-3:
+            tab.append((dx, sx2, f32(min(min(fsx2 - sx2, 1.0), cell) / cell)))
+    return tab
+
+
+def resize_area_f32(src, dsize, inv_scale=None, simd_lanes=8):
+    """cv2.resize(src, dsize, interpolation=INTER_AREA) for scale >= 1 (pure Python loops: small images only).
+    inv_scale = (fx, fy) when the call derived dsize from them (the scale is then 1/fx, not ssize/dsize).
+    simd_lanes: vector width of the 2x2 fast path of the OpenCV build (8 = AVX2)."""
+    s = np.asarray(src, dtype=f32)
+    sh, sw = s.shape
+    dw, dh = dsize
+    ix, iy = inv_scale if inv_scale is not None else (dw / sw, dh / sh)
+    scale_x, scale_y = 1.0 / ix, 1.0 / iy
+    isx, isy = int(round(scale_x)), int(round(scale_y))
+    dst = np.zeros((dh, dw), f32)
+    eps = np.finfo(np.float64).eps
+    if abs(scale_x - isx) < eps and abs(scale_y - isy) < eps:
+        wfull = min(dw, sw // isx)
+        sc = f32(1.0 / (isx * isy))
+        for dy in range(dh):
+            y0 = dy * isy
+            for dx in range(dw):
+                x0 = dx * isx
+                if x0 + isx > sw or y0 + isy > sh:      # cell clipped by the image edge: running sum / count
+                    vals = [s[y0 + ky, x0 + kx] for ky in range(isy) if y0 + ky < sh for kx in range(isx) if x0 + kx < sw]
+                    acc = f32(0)
+                    for v in vals:
+                        acc = f32(acc + v)
+                    dst[dy, dx] = f32(acc / f32(len(vals))) if vals else 0
+                    continue
+                vals = [s[y0 + ky, x0 + kx] for ky in range(isy) for kx in range(isx)]
+                if isx == 2 and isy == 2 and dx < wfull - wfull % simd_lanes:
+                    acc = f32(f32(vals[0] + vals[1]) + f32(vals[2] + vals[3]))
+                else:
+                    acc, k = f32(0), 0
+                    while k + 4 <= len(vals):
+                        acc = f32(acc + f32(f32(f32(vals[k] + vals[k + 1]) + vals[k + 2]) + vals[k + 3]))
+                        k += 4
+                    while k < len(vals):
+                        acc = f32(acc + vals[k])
+                        k += 1
+                dst[dy, dx] = f32(acc * sc)
+        return dst
+    xtab, ytab = _area_tab(sw, dw, scale_x), _area_tab(sh, dh, scale_y)
+    prev_dy = ytab[0][0]
+    summ = np.zeros(dw, f32)
+    for dy, sy, beta in ytab:
+        buf = np.zeros(dw, f32)
+        for dx, sx, alpha in xtab:
+            buf[dx] = f32(buf[dx] + f32(s[sy, sx] * alpha))
+        if dy != prev_dy:
+            dst[prev_dy] = summ
+            summ = (beta * buf).astype(f32)
+            prev_dy = dy
+        else:
+            summ = (summ + (beta * buf).astype(f32)).astype(f32)
+    dst[prev_dy] = summ
+    return dst

@@ -593,7 +593,7 @@ int ssk_acc_from_sum_form(ssk_acc *h, int accumulated_frames) {
 int ssk_local_variance_map(const ssk_mat *image, int bpp, int dscale, int kradius, int uscale, ssk_mat *map, double *Q) {
   if (int e = ensure_device()) return e;
   if (int e = check_mat(image, "compute_local_variance_map")) return e;
-  SSK_REQUIRE(uscale == 0, "compute_local_variance_map: uscale > 0 (INTER_AREA stage) is not implemented");
+  SSK_REQUIRE(uscale >= 0 && uscale <= 12, "compute_local_variance_map: uscale 0..12");
   SSK_REQUIRE(dscale >= 0 && dscale <= 6, "compute_local_variance_map: dscale 0..6");
   if (map) {
     if (int e = check_mat(map, "compute_local_variance_map map")) return e;
@@ -630,7 +630,7 @@ int ssk_local_variance_map(const ssk_mat *image, int bpp, int dscale, int kradiu
     M = bufA;
   }
   const int nb = w1_num_blocks(r, c);
-  if (int e = sc.c.ensure((size_t)r * c * 4)) return e;
+  if (int e = sc.c.ensure((size_t)r * c * 4 * 2)) return e;      // gmap + uscale scratch
   if (int e = sc.d.ensure((size_t)nb * 2 * 8 + 4 * 8 + (size_t)(im.rows + im.cols + 8) * sizeof(int2) + 16)) return e;
   if (int e = sc.e.ensure(n * 4)) return e;
   W1Args w = {};
@@ -638,6 +638,7 @@ int ssk_local_variance_map(const ssk_mat *image, int bpp, int dscale, int kradiu
   w.gmap = sc.c.as<float>(); w.partials = sc.d.as<double>(); w.stats = sc.d.as<double>() + (size_t)nb * 2;
   w.out = map ? sc.e.as<float>() : nullptr; w.full_rows = im.rows; w.full_cols = im.cols; w.batch = 1;
   w.axis_tab = reinterpret_cast<int2 *>(sc.d.as<double>() + (size_t)nb * 2 + 4);
+  w.uscale = uscale; w.gmap2 = sc.c.as<float>() + (size_t)r * c;
   if (int e = launch_w1(w, s)) return e;
   double stats[4];
   SSK_CUDA(cudaMemcpyAsync(stats, w.stats, sizeof(stats), cudaMemcpyDeviceToHost, s));

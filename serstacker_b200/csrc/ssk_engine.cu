@@ -435,14 +435,39 @@ int Reg::init(const ssk_registration_options &o, cudaStream_t s, bool own) {
   return SSK_OK;
 }
 
+// scaleImage (c_frame_registration.cc:230-250): 0.5 -> cv::pyrDown, 1 (or <= 0) -> as is, anything else -> cv::resize(fx = fy =
+// scale, INTER_AREA) whose dsize is (cvRound(cols * scale), cvRound(rows * scale))
+static bool ecc_scale_is_pyrdown(const ssk_registration_options &o) { return o.ecc.scale > 0 && std::fabs(o.ecc.scale - 0.5) < 1e-2; }
+static bool ecc_scale_is_area(const ssk_registration_options &o) { return o.ecc.scale > 0 && o.ecc.scale != 1 && !ecc_scale_is_pyrdown(o); }
+
 static int ecc_image_size(const ssk_registration_options &o, int rows, int cols, int *er, int *ec) {
-  if (o.ecc.scale > 0 && o.ecc.scale != 1) {
-    SSK_REQUIRE(std::fabs(o.ecc.scale - 0.5) < 1e-2, "ecc.scale must be 0.5 (cv::pyrDown branch of scaleImage) or 1");
+  if (ecc_scale_is_pyrdown(o)) {
     *er = (rows + 1) / 2; *ec = (cols + 1) / 2;   // cv::pyrDown default dstsize
+  } else if (ecc_scale_is_area(o)) {
+    SSK_REQUIRE(o.ecc.scale < 1, "ecc.scale > 1 (INTER_AREA up-scaling) is not implemented");
+    *er = (int)lrint(rows * o.ecc.scale); *ec = (int)lrint(cols * o.ecc.scale);
+    SSK_REQUIRE(*er >= 1 && *ec >= 1, "ecc.scale leaves an empty ECC image");
   } else {
     *er = rows; *ec = cols;
   }
   return SSK_OK;
+}
+
+static int scale_to_ecc_image(const ssk_registration_options &o, const Img &geom, const void *const *src_ptrs, float *dst,
+                              float *const *dst_ptrs, int er, int ec, int batch, cudaStream_t stream) {
+  if (ecc_scale_is_pyrdown(o)) {
+    PyrDownArgs pd = {};
+    pd.src = geom; pd.src_ptrs = src_ptrs; pd.dst = dst; pd.dst_ptrs = dst_ptrs; pd.dst_rows = er; pd.dst_cols = ec; pd.batch = batch;
+    pd.post_scale = 1.f;
+    return launch_pyrdown(pd, stream);
+  }
+  if (ecc_scale_is_area(o)) {
+    ResizeAreaArgs ra = {};
+    ra.src = geom; ra.src_ptrs = src_ptrs; ra.dst = dst; ra.dst_ptrs = dst_ptrs; ra.dst_rows = er; ra.dst_cols = ec; ra.batch = batch;
+    ra.inv_scale_x = ra.inv_scale_y = o.ecc.scale;
+    return launch_resize_area(ra, stream);
+  }
+  return launch_to_gray(geom, src_ptrs, dst, dst_ptrs, batch, stream);
 }
 
 int Reg::setup_reference(const Img &frame, const uint8_t *d_mask, int64_t mask_step) {
@@ -451,16 +476,11 @@ int Reg::setup_reference(const Img &frame, const uint8_t *d_mask, int64_t mask_s
   if (int e = ecc_image_size(opts, frame.rows, frame.cols, &ecc_rows, &ecc_cols)) return e;
   if (int e = staging.ensure((size_t)ecc_rows * ecc_cols * 4)) return e;
   float *d_ecc = staging.as<float>();
-  if (ecc_rows != frame.rows) {
-    PyrDownArgs pd = {};
-    pd.src = frame; pd.dst = d_ecc; pd.dst_rows = ecc_rows; pd.dst_cols = ecc_cols; pd.batch = 1; pd.post_scale = 1.f;
-    if (int e = launch_pyrdown(pd, stream)) return e;
-  } else {
-    if (int e = launch_to_gray(frame, nullptr, d_ecc, nullptr, 1, stream)) return e;
-  }
+  if (int e = scale_to_ecc_image(opts, frame, nullptr, d_ecc, nullptr, ecc_rows, ecc_cols, 1, stream)) return e;
   const uint8_t *d_ecc_mask = nullptr;
   if (d_mask) {
     if (int e = mask_tmp.ensure((size_t)ecc_rows * ecc_cols)) return e;
+    SSK_REQUIRE(!ecc_scale_is_area(opts), "reference masks with ecc.scale other than 0.5 / 1 (8-bit INTER_AREA) are not implemented");
     if (ecc_rows != frame.rows) {   // scaleImage: pyrDown(mask) >= 250 (c_frame_registration.cc:237-241)
       if (int e = launch_pyrdown_mask_u8(d_mask, mask_step, frame.rows, frame.cols, mask_tmp.as<uint8_t>(), ecc_rows, ecc_cols, 250, stream)) return e;
     } else {
@@ -483,14 +503,7 @@ int Reg::prepare(const Img &geom, const void *const *d_frame_ptrs, int batch) {
   SSK_REQUIRE(ecch.have_reference, "c_frame_registration: setup_reference_frame() must be called first");
   SSK_REQUIRE(geom.rows == ref_rows && geom.cols == ref_cols, "current frame size differs from the reference frame size");
   if (int e = ecch.reserve(batch)) return e;
-  if (ecc_rows != geom.rows) {
-    PyrDownArgs pd = {};
-    pd.src = geom; pd.src_ptrs = d_frame_ptrs;
-    pd.dst_ptrs = ecch.level0_scratch_ptrs(); pd.dst_rows = ecc_rows; pd.dst_cols = ecc_cols; pd.batch = batch; pd.post_scale = 1.f;
-    if (int e = launch_pyrdown(pd, stream)) return e;
-  } else {
-    if (int e = launch_to_gray(geom, d_frame_ptrs, nullptr, ecch.level0_scratch_ptrs(), batch, stream)) return e;
-  }
+  if (int e = scale_to_ecc_image(opts, geom, d_frame_ptrs, nullptr, ecch.level0_scratch_ptrs(), ecc_rows, ecc_cols, batch, stream)) return e;
   if (normalize_enabled()) {
     if (int e = normalize(ecch.level0_scratch_ptrs(), batch, nullptr)) return e;
   }

@@ -148,6 +148,8 @@ class Reg {
   DevBuf d_one_ptr;                    // 1-entry pointer tables for the single-frame path
   DevBuf norm_buf, norm_ptrs;          // ecc_normalize: per-frame pyrDown chain + per-level pointer tables
   int norm_capacity = 0;
+  // scaleImage took the cv::pyrDown branch (ecc.scale == 0.5): the ECC image is also the first level of W1's pdownscale chain
+  bool scaled_by_pyrdown() const { return opts.ecc.scale > 0 && opts.ecc.scale > 0.49 && opts.ecc.scale < 0.51; }
   bool normalize_enabled() const { return opts.ecc.normalization_scale > 0 && opts.ecc.normalization_noise > 0; }
   // ecc_normalize (ecc2.cc:385-397) in place on `batch` dense ecc_rows x ecc_cols images; d_mask: dense mask or null
   int normalize(float *const *d_img_ptrs, int batch, const uint8_t *d_mask);

@@ -8,6 +8,8 @@
 //   compute_local_variance_map                         core/proc/sharpness_measure/c_local_variance_sharpness_measure.cc:193-247
 // All kernels are batched over the frames of a batch through blockIdx.z.
 #include "ssk_prep.cuh"
+#include <cfloat>
+#include <cmath>
 
 namespace ssk {
 
@@ -97,6 +99,89 @@ __global__ void __launch_bounds__(256) k_pyrdown(const PyrDownArgs a) {
     if (a.post_scale != 1.f) v = __fmul_rn(v, a.post_scale);
     dst[(int64_t)(oy0 + j) * a.dst_cols + ox] = v;
   }
+}
+
+// ---- cv::resize INTER_AREA, down-scaling ------------------------------------------------------------------------
+// Arithmetic restated from OpenCV's resize.cpp and checked bit-exactly against cv2 4.13 on the CPU (numpy model) before
+// it was written here:
+//   integer scale (ResizeAreaFast): sum of the iscale_x * iscale_y cell in row-major order, four terms at a time
+//     (s += ((a + b) + c) + d), times 1/area; for 2 x 2 the columns covered by the 8-lane SIMD loop use
+//     ((s00 + s01) + (s10 + s11)) * 0.25 (the tail columns of a row use the scalar form; the lane count is the
+//     AVX2 one - a build with another vector width differs in the last ulp on those few columns)
+//   otherwise (ResizeArea): per destination pixel the source cells it overlaps, weights alpha / beta =
+//     overlap / cellWidth computed in double and narrowed to float (computeResizeAreaTab); a row's contribution is
+//     buf = sum_x S * alpha (in x order), the pixel is sum_y beta * buf (first row assigns, the others add).
+constexpr int kAreaSimdLanes = 8;
+
+struct AreaAxis { int s0, n; float a_first, a_mid, a_last; bool has_first, has_last; };
+
+__device__ __forceinline__ AreaAxis area_axis(int d, double scale, int ssize) {
+  AreaAxis r;
+  const double fsx1 = d * scale;
+  const double cell = fmin(scale, ssize - fsx1);
+  const double fsx2 = fsx1 + cell;
+  int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+  sx2 = min(sx2, ssize - 1);
+  sx1 = min(sx1, sx2);
+  r.has_first = sx1 - fsx1 > 1e-3;
+  r.has_last = fsx2 - sx2 > 1e-3;
+  r.a_first = (float)((sx1 - fsx1) / cell);
+  r.a_mid = (float)(1.0 / cell);
+  r.a_last = (float)(fmin(fmin(fsx2 - sx2, 1.), cell) / cell);
+  r.s0 = r.has_first ? sx1 - 1 : sx1;
+  r.n = (sx2 - sx1) + (r.has_first ? 1 : 0) + (r.has_last ? 1 : 0);
+  return r;
+}
+__device__ __forceinline__ float area_weight(const AreaAxis &r, int k) {
+  if (k == 0 && r.has_first) return r.a_first;
+  if (k == r.n - 1 && r.has_last) return r.a_last;
+  return r.a_mid;
+}
+
+template <int DEPTH>
+__global__ void __launch_bounds__(256) k_resize_area(const ResizeAreaArgs a, double scale_x, double scale_y, int iscale_x, int iscale_y) {
+  const int b = blockIdx.z;
+  Img src = a.src;
+  if (a.src_ptrs) src.data = a.src_ptrs[b];
+  float *dst = a.dst_ptrs ? a.dst_ptrs[b] : a.dst;
+  const int dx = blockIdx.x * 32 + (threadIdx.x & 31), dy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (dx >= a.dst_cols || dy >= a.dst_rows) return;
+  float out;
+  if (iscale_x > 0) {
+    const int x0 = dx * iscale_x, y0 = dy * iscale_y;
+    const bool full = x0 + iscale_x <= src.cols && y0 + iscale_y <= src.rows;
+    const int wfull = min(a.dst_cols, src.cols / iscale_x);      // columns whose cell is complete (ResizeAreaFast_Invoker's w)
+    if (!full) {
+      // cell clipped by the image edge: plain running sum over the part inside, divided by the number of samples
+      float sum = 0.f;
+      int count = 0;
+      for (int ky = 0; ky < iscale_y && y0 + ky < src.rows; ++ky)
+        for (int kx = 0; kx < iscale_x && x0 + kx < src.cols; ++kx) { sum = __fadd_rn(sum, load_gray<DEPTH>(src, y0 + ky, x0 + kx)); ++count; }
+      out = count ? __fdiv_rn(sum, (float)count) : 0.f;
+    } else if (iscale_x == 2 && iscale_y == 2 && dx < wfull - wfull % kAreaSimdLanes) {
+      const float s00 = load_gray<DEPTH>(src, y0, x0), s01 = load_gray<DEPTH>(src, y0, x0 + 1);
+      const float s10 = load_gray<DEPTH>(src, y0 + 1, x0), s11 = load_gray<DEPTH>(src, y0 + 1, x0 + 1);
+      out = __fmul_rn(__fadd_rn(__fadd_rn(s00, s01), __fadd_rn(s10, s11)), 0.25f);
+    } else {
+      const int area = iscale_x * iscale_y;
+      float sum = 0.f;
+      int k = 0;
+      auto at = [&](int kk) { const int ky = kk / iscale_x, kx = kk - ky * iscale_x; return load_gray<DEPTH>(src, y0 + ky, x0 + kx); };
+      for (; k + 4 <= area; k += 4) sum = __fadd_rn(sum, __fadd_rn(__fadd_rn(__fadd_rn(at(k), at(k + 1)), at(k + 2)), at(k + 3)));
+      for (; k < area; ++k) sum = __fadd_rn(sum, at(k));
+      out = __fmul_rn(sum, (float)(1.0 / area));
+    }
+  } else {
+    const AreaAxis ax = area_axis(dx, scale_x, src.cols), ay = area_axis(dy, scale_y, src.rows);
+    out = 0.f;
+    for (int ky = 0; ky < ay.n; ++ky) {
+      float buf = 0.f;
+      for (int kx = 0; kx < ax.n; ++kx) buf = __fadd_rn(buf, __fmul_rn(load_gray<DEPTH>(src, ay.s0 + ky, ax.s0 + kx), area_weight(ax, kx)));
+      const float t = __fmul_rn(area_weight(ay, ky), buf);
+      out = ky == 0 ? t : __fadd_rn(out, t);
+    }
+  }
+  dst[(int64_t)dy * a.dst_cols + dx] = out;
 }
 
 template <int DEPTH>
@@ -587,6 +672,23 @@ int launch_pyrdown(const PyrDownArgs &a, cudaStream_t s) {
   return SSK_OK;
 }
 
+int launch_resize_area(const ResizeAreaArgs &a, cudaStream_t s) {
+  SSK_REQUIRE(a.inv_scale_x > 0 && a.inv_scale_y > 0 && a.inv_scale_x <= 1.0 && a.inv_scale_y <= 1.0,
+              "resize INTER_AREA: only down-scaling is implemented");
+  SSK_REQUIRE(a.dst_cols >= 1 && a.dst_rows >= 1, "resize INTER_AREA: empty destination");
+  const double scale_x = 1.0 / a.inv_scale_x, scale_y = 1.0 / a.inv_scale_y;   // cv::hal::resize
+  int iscale_x = (int)lrint(scale_x), iscale_y = (int)lrint(scale_y);           // saturate_cast<int>(double)
+  const bool fast = std::fabs(scale_x - iscale_x) < DBL_EPSILON && std::fabs(scale_y - iscale_y) < DBL_EPSILON;
+  if (!fast) iscale_x = iscale_y = 0;
+  dim3 grid(div_up(a.dst_cols, 32), div_up(a.dst_rows, 8), a.batch);
+  if (a.src.depth == SSK_32F) k_resize_area<SSK_32F><<<grid, 256, 0, s>>>(a, scale_x, scale_y, iscale_x, iscale_y);
+  else if (a.src.depth == SSK_16U) k_resize_area<SSK_16U><<<grid, 256, 0, s>>>(a, scale_x, scale_y, iscale_x, iscale_y);
+  else if (a.src.depth == SSK_8U) k_resize_area<SSK_8U><<<grid, 256, 0, s>>>(a, scale_x, scale_y, iscale_x, iscale_y);
+  else { set_error("resize INTER_AREA: unsupported depth"); return SSK_ERR_INVALID; }
+  SSK_LAUNCH_CHECK();
+  return SSK_OK;
+}
+
 int launch_to_gray(const Img &src, const void *const *src_ptrs, float *dst, float *const *dst_ptrs, int batch, cudaStream_t s) {
   dim3 grid(div_up(src.cols, 32), div_up(src.rows, 8), batch);
   if (src.depth == SSK_32F) k_to_gray<SSK_32F><<<grid, 256, 0, s>>>(src, src_ptrs, dst, dst_ptrs);
@@ -620,29 +722,55 @@ int launch_w1(const W1Args &a, cudaStream_t s) {
   k_w1_final<<<a.batch, 256, 0, s>>>(a, nblocks);
   SSK_LAUNCH_CHECK();
   if (a.out || a.out_ptrs) {
-    if (a.full_cols != a.cols || a.full_rows != a.rows) {
-      SSK_REQUIRE(a.axis_tab, "local variance map: axis table scratch missing");
-      if (!(a.axis_tab_built && *a.axis_tab_built)) {   // the tables depend on the geometry only: built once per handle
-        const int xpad = (a.full_cols + 3) & ~3, ypad = (a.full_rows + 3) & ~3;
-        int *xi = reinterpret_cast<int *>(a.axis_tab), *yi = xi + 2 * xpad;
-        cudaMemsetAsync(a.axis_tab, 0, (size_t)(2 * xpad + 2 * ypad) * 4, s);
-        k_w1_axis<<<div_up(a.full_cols, 256), 256, 0, s>>>(a.full_cols, a.cols, (double)a.cols / a.full_cols, xi, reinterpret_cast<float *>(xi + xpad));
-        SSK_LAUNCH_CHECK();
-        k_w1_axis<<<div_up(a.full_rows, 256), 256, 0, s>>>(a.full_rows, a.rows, (double)a.rows / a.full_rows, yi, reinterpret_cast<float *>(yi + ypad));
-        SSK_LAUNCH_CHECK();
-        if (a.axis_tab_built) *a.axis_tab_built = 1;
+    W1Args u = a;     // geometry of the map that is up-sampled
+    if (a.uscale > 0) {
+      int ur, uc;
+      w1_uscale_size(a.rows, a.cols, a.uscale, &ur, &uc);
+      if (ur != a.rows || uc != a.cols) {
+        SSK_REQUIRE(a.gmap2 || a.gmap2_ptrs, "local variance map: uscale scratch missing");
+        ResizeAreaArgs ra = {};
+        ra.src.data = a.gmap; ra.src.step = (int64_t)a.cols * 4; ra.src.rows = a.rows; ra.src.cols = a.cols;
+        ra.src.depth = SSK_32F; ra.src.cn = 1; ra.src.scale = 1.f;
+        ra.src_ptrs = reinterpret_cast<const void *const *>(a.gmap_ptrs);
+        ra.dst = a.gmap2; ra.dst_ptrs = a.gmap2_ptrs; ra.dst_rows = ur; ra.dst_cols = uc; ra.batch = a.batch;
+        ra.inv_scale_x = (double)uc / a.cols; ra.inv_scale_y = (double)ur / a.rows;   // cv::resize with an explicit dsize
+        if (int e = launch_resize_area(ra, s)) return e;
+        u.gmap = a.gmap2; u.gmap_ptrs = a.gmap2_ptrs; u.rows = ur; u.cols = uc;
       }
     }
-    if (a.full_cols == 2 * a.cols && a.full_rows == 2 * a.rows) {
-      dim3 g2(div_up(a.full_cols, 128), div_up(a.full_rows, 16), a.batch);
-      k_w1_upsample2x<<<g2, 256, 0, s>>>(a);
+    if (u.full_cols != u.cols || u.full_rows != u.rows) {
+      SSK_REQUIRE(u.axis_tab, "local variance map: axis table scratch missing");
+      if (!(u.axis_tab_built && *u.axis_tab_built)) {   // the tables depend on the geometry only: built once per handle
+        const int xpad = (u.full_cols + 3) & ~3, ypad = (u.full_rows + 3) & ~3;
+        int *xi = reinterpret_cast<int *>(u.axis_tab), *yi = xi + 2 * xpad;
+        cudaMemsetAsync(u.axis_tab, 0, (size_t)(2 * xpad + 2 * ypad) * 4, s);
+        k_w1_axis<<<div_up(u.full_cols, 256), 256, 0, s>>>(u.full_cols, u.cols, (double)u.cols / u.full_cols, xi, reinterpret_cast<float *>(xi + xpad));
+        SSK_LAUNCH_CHECK();
+        k_w1_axis<<<div_up(u.full_rows, 256), 256, 0, s>>>(u.full_rows, u.rows, (double)u.rows / u.full_rows, yi, reinterpret_cast<float *>(yi + ypad));
+        SSK_LAUNCH_CHECK();
+        if (u.axis_tab_built) *u.axis_tab_built = 1;
+      }
+    }
+    if (u.full_cols == 2 * u.cols && u.full_rows == 2 * u.rows) {
+      dim3 g2(div_up(u.full_cols, 128), div_up(u.full_rows, 16), u.batch);
+      k_w1_upsample2x<<<g2, 256, 0, s>>>(u);
     } else {
-      dim3 g2(div_up(a.full_cols, 128), div_up(a.full_rows, 8), a.batch);
-      k_w1_upsample<<<g2, 256, 0, s>>>(a);
+      dim3 g2(div_up(u.full_cols, 128), div_up(u.full_rows, 8), u.batch);
+      k_w1_upsample<<<g2, 256, 0, s>>>(u);
     }
     SSK_LAUNCH_CHECK();
   }
   return SSK_OK;
+}
+
+void w1_uscale_size(int rows, int cols, int uscale, int *urows, int *ucols) {
+  // dscaleSize (c_local_variance_sharpness_measure.cc:15-25)
+  for (int l = 0; l < uscale; ++l) {
+    const int nc = (cols + 1) / 2, nr = (rows + 1) / 2;
+    if (std::min(nc, nr) < 4) break;
+    cols = nc; rows = nr;
+  }
+  *urows = rows; *ucols = cols;
 }
 
 int launch_lpg5x5(const float *src, int rows, int cols, float *dst, float alpha, float beta, float eps, cudaStream_t s) {

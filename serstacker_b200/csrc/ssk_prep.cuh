@@ -21,6 +21,18 @@ struct PyrDownArgs {
 };
 int launch_pyrdown(const PyrDownArgs &a, cudaStream_t s);
 
+// cv::resize(INTER_AREA) for down-scaling (scale >= 1 in both axes), single-channel fp32 result (colour / integer frames go
+// through the same gray load as pyrDown): scaleImage's branch for ecc.scale != 0.5 (c_frame_registration.cc:242-247).
+// inv_scale_x/y are cv::resize's inv_scale_* (fx, fy when dsize was derived from them, else dsize / ssize).
+struct ResizeAreaArgs {
+  Img src; const void *const *src_ptrs;
+  float *dst; float *const *dst_ptrs;
+  int dst_rows, dst_cols;
+  double inv_scale_x, inv_scale_y;
+  int batch;
+};
+int launch_resize_area(const ResizeAreaArgs &a, cudaStream_t s);
+
 // cv::pyrUp(src, dst, dstsize) on dense CV_32FC1 images (dst_cols in {2*cols - 1, 2*cols, 2*cols + 1}, same for rows),
 // optionally fused with ecc_normalize's subtraction: dst = minuend - pyrUp(src), zeroed where mask == 0.
 struct PyrUpArgs {
@@ -61,9 +73,13 @@ struct W1Args {
   int full_rows, full_cols;
   int batch;
   int2 *axis_tab;                                 // scratch [full_cols + full_rows]: per output column / row source index + fraction
+  // uscale > 0 (c_local_variance_sharpness_measure.cc:231-234): the map is reduced to dscaleSize(size, uscale) by
+  // cv::resize(INTER_AREA) before the 0.05 Q offset and the up-sampling; gmap2 is scratch of rows x cols floats per frame
+  int uscale; float *gmap2; float *const *gmap2_ptrs;
   int *axis_tab_built;                            // host flag (optional): the tables in axis_tab are already those of this geometry
 };
 int w1_num_blocks(int rows, int cols);
+void w1_uscale_size(int rows, int cols, int uscale, int *urows, int *ucols);   // dscaleSize()
 int launch_w1(const W1Args &a, cudaStream_t s);
 
 // W2 (lpg.cc): 5x5 Laplacian/gradient energy; in-place scale + integer power

@@ -53,6 +53,7 @@ struct ssk_stack {
   // per-slot device buffers
   DevBuf frame_slots, weight_slots, half_slots, half2_slots, gmap_slots, partials, stats, jobs, counter;
   DevBuf d_slot_ptrs, d_weight_ptrs, d_half_ptrs, d_half2_ptrs, d_gmap_ptrs;
+  DevBuf gmap2_slots, d_gmap2_ptrs;      // sharpness_measure.uscale > 0: INTER_AREA-reduced maps
   DevBuf d_user_ptrs[kRing];
   PinnedBuf h_user_ptrs[kRing];
   // TMA staging of the fused kernel (32F single-channel frames): 128-byte tensor maps per frame slot / weight slot,
@@ -189,6 +190,12 @@ static int stack_alloc_slots(ssk_stack *h) {
     SSK_CUDA(cudaMemcpy(h->d_half2_ptrs.p, p.data(), sizeof(void *) * B, cudaMemcpyHostToDevice));
     for (int b = 0; b < B; ++b) p[b] = h->gmap_slots.as<float>() + (size_t)r * c * b;
     SSK_CUDA(cudaMemcpy(h->d_gmap_ptrs.p, p.data(), sizeof(void *) * B, cudaMemcpyHostToDevice));
+    if (h->o.sm_uscale > 0) {
+      if (int e = h->gmap2_slots.ensure((size_t)r * c * 4 * B)) return e;
+      if (int e = h->d_gmap2_ptrs.ensure(sizeof(void *) * B)) return e;
+      for (int b = 0; b < B; ++b) p[b] = h->gmap2_slots.as<float>() + (size_t)r * c * b;
+      SSK_CUDA(cudaMemcpy(h->d_gmap2_ptrs.p, p.data(), sizeof(void *) * B, cudaMemcpyHostToDevice));
+    }
   }
   return SSK_OK;
 }
@@ -217,7 +224,7 @@ int ssk_stack_create(const ssk_stack_options *opts, ssk_stack **out) {
   SSK_REQUIRE(opts->max_batch >= 1 && opts->max_batch <= 4096, "max_batch 1..4096");
   SSK_REQUIRE(opts->accumulation_method == SSK_STACK_AVERAGE || opts->accumulation_method == SSK_STACK_WEIGHTED_AVERAGE,
               "ssk_stack: average and weighted_average are fused; bayer_average goes through ssk_reg_* + ssk_acc_*");
-  SSK_REQUIRE(opts->sm_uscale == 0, "sharpness_measure.uscale > 0 is not implemented");
+  SSK_REQUIRE(opts->sm_uscale >= 0 && opts->sm_uscale <= 12, "sharpness_measure.uscale 0..12");
   ssk_stack *h = new (std::nothrow) ssk_stack();
   SSK_REQUIRE(h, "out of memory");
   h->o = *opts;
@@ -340,7 +347,7 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
       const void *const *src_ptrs = d_frame_ptrs;
       float *const *dst_ptrs = h->d_half_ptrs.as<float *>();
       int l0 = 0;
-      if (h->o.enable_registration && h->reg_h.r.ecc_rows != h->rows && !h->reg_h.r.normalize_enabled()) {
+      if (h->o.enable_registration && h->reg_h.r.scaled_by_pyrdown() && !h->reg_h.r.normalize_enabled()) {
         // the first cv::pyrDown of the gray frame is exactly the ECC image scaleImage() just produced
         // (c_frame_registration.cc:236-237 vs c_local_variance_sharpness_measure.cc:36): reuse it
         const int nr = (cur.rows + 1) / 2, nc = (cur.cols + 1) / 2;
@@ -371,6 +378,7 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
     w.gmap_ptrs = h->d_gmap_ptrs.as<float *>(); w.partials = h->partials.as<double>(); w.stats = h->stats.as<double>();
     w.out_ptrs = h->d_weight_ptrs.as<float *>(); w.full_rows = h->rows; w.full_cols = h->cols; w.batch = n;
     w.axis_tab = h->axis_tab.as<int2>(); w.axis_tab_built = &h->axis_tab_built;
+    w.uscale = h->o.sm_uscale; w.gmap2_ptrs = h->o.sm_uscale > 0 ? h->d_gmap2_ptrs.as<float *>() : nullptr;
     if (int e = launch_w1(w, s)) return e;
   }
   SSK_CUDA(cudaEventRecord(h->ev[2], s));

@@ -115,3 +115,31 @@ def test_pyrdown_replicate_model_is_border_independent_inside():
     r = cv2.pyrDown(a, borderType=cv2.BORDER_REPLICATE)
     d = cv2.pyrDown(a)
     assert np.array_equal(r[1:-1, 1:-1], d[1:-1, 1:-1])
+
+
+@pytest.mark.parametrize("sw,sh,dw,dh", [(97, 61, 49, 31), (100, 60, 75, 45), (101, 77, 25, 19), (50, 40, 37, 29), (96, 64, 24, 16), (99, 63, 33, 21)])
+def test_resize_area_model_bit_exact(sw, sh, dw, dh):
+    """INTER_AREA down-scaling, fractional ratios (ResizeArea) and integer ratios 3 / 4 (ResizeAreaFast): bit-exact."""
+    rng = np.random.default_rng(sw * 1000 + dw)
+    src = rng.random((sh, sw)).astype(np.float32)
+    want = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_AREA)
+    assert np.array_equal(m.resize_area_f32(src, (dw, dh)), want)
+
+
+@pytest.mark.parametrize("sw,sh,f", [(402, 302, 0.25), (80, 60, 0.75), (101, 77, 0.4)])
+def test_resize_area_model_with_fx_fy(sw, sh, f):
+    """scaleImage's call form: dsize derived from fx = fy (cells clipped by the edge when cvRound rounds up)."""
+    rng = np.random.default_rng(sw)
+    src = rng.random((sh, sw)).astype(np.float32)
+    want = cv2.resize(src, (0, 0), fx=f, fy=f, interpolation=cv2.INTER_AREA)
+    got = m.resize_area_f32(src, (want.shape[1], want.shape[0]), inv_scale=(f, f))
+    assert np.array_equal(got, want)
+
+
+def test_resize_area_model_2x2_simd_form():
+    """2 x 2 cells: the SIMD columns use (s00 + s01) + (s10 + s11), the tail columns the scalar running form; which
+    columns are 'tail' depends on the vector width of the OpenCV build, so one of the common widths must match."""
+    rng = np.random.default_rng(5)
+    src = rng.random((50, 70)).astype(np.float32)
+    want = cv2.resize(src, (35, 25), interpolation=cv2.INTER_AREA)
+    assert any(np.array_equal(m.resize_area_f32(src, (35, 25), simd_lanes=l), want) for l in (4, 8, 16))

@@ -97,6 +97,34 @@ def test_register_frame_matches_oracle(gpu, method, motion, tfirst):
                 assert d <= max(1e-3, (10 if motion == 1 else 4) * env), (d, env)
 
 
+@pytest.mark.parametrize("scale,size", [(0.25, (400, 300)), (0.25, (402, 302)), (0.75, (400, 300)), (0.4, (401, 299)), (1.0, (200, 150))])
+def test_register_frame_with_ecc_scale(gpu, scale, size):
+    """scaleImage's cv::resize(INTER_AREA) branch (c_frame_registration.cc:242-247): integer scale (ResizeAreaFast, with and
+    without cells clipped by the image edge), fractional scale (ResizeArea), and scale 1 (no scaling)."""
+    from serstacker_b200 import api
+    w, h = size
+    frames, _ = _seq(w, h, 4, seed=57, rot=0.0, scale=0.0, sigma_t=3.0)
+    oo = oreg.ImageRegistrationOptions(motion_type=0)
+    oo.ecc.ecc_method = oecc.ECC_ALIGN_INVERSE_COMPOSITIONAL_LM
+    oo.ecc.ecch_max_level = -1
+    oo.ecc.scale = scale
+    o = oreg.FrameRegistration(oo)
+    o.setup_reference_frame(frames[0])
+    g = api.c_frame_registration(api.registration_options(motion_type=0, ecc=dict(ecc_method=3, ecch_max_level=-1, scale=scale)))
+    g.setup_reference_frame(frames[0])
+    for f in frames:
+        ok_o = o.register_frame(f)
+        ok_g = g.register_frame(f)
+        assert ok_o == ok_g
+        assert abs(g.status.rho - o.status.rho) <= 1e-4
+        if ok_o:
+            d = map_diff_px(0, g.image_transform_parameters(), o.image_transform.parameters().copy(), (w, h))
+            assert d <= 1e-3, (d, g.status.num_iterations, o.status.num_iterations)
+            # the scaled ECC images are bit-identical to cv::resize's, so the translation solver takes the same steps
+            assert g.status.num_iterations == o.status.num_iterations
+            assert np.array_equal(g.image_transform_parameters(), o.image_transform.parameters().ravel()[:2])
+
+
 def test_low_correlation_frame_is_dropped(gpu):
     from serstacker_b200 import api
     frames, _ = _seq(320, 240, 2, seed=5)

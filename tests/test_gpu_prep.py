@@ -60,6 +60,20 @@ def test_local_variance_map_matches_oracle(gpu, size, kradius, dscale):
     assert np.abs(Mg - Mo).max() <= 5e-6 * scale, np.abs(Mg - Mo).max() / scale
 
 
+@pytest.mark.parametrize("size", [(320, 240), (301, 203), (652, 490)])
+@pytest.mark.parametrize("dscale,uscale", [(1, 1), (1, 2), (0, 1), (2, 3)])
+def test_local_variance_map_uscale_matches_oracle(gpu, size, dscale, uscale):
+    """uscale > 0: cv::resize(INTER_AREA) of the map to dscaleSize(size, uscale) before the offset and the up-sampling
+    (c_local_variance_sharpness_measure.cc:231-234); integer and fractional area ratios."""
+    from serstacker_b200 import api
+    img, _ = _frame(size[0], size[1], 8)
+    Qo, Mo = ow.compute_local_variance_map(img, dscale=dscale, kradius=1, uscale=uscale)
+    Qg, Mg = api.compute_local_variance_map(img, dscale=dscale, kradius=1, uscale=uscale)
+    assert abs(Qg - Qo) <= 2e-5 * abs(Qo)
+    scale = np.abs(Mo).max()
+    assert np.abs(Mg - Mo).max() <= 5e-6 * scale, np.abs(Mg - Mo).max() / scale
+
+
 def test_level0_smoothing_bit_exact(gpu):
     """The 7-tap Gaussian sepFilter2D (and the 5/3-tap derivative filters) follow OpenCV's filter-engine
     arithmetic exactly, so the reference-side Hessian sees the same gradients as the oracle."""
