@@ -330,7 +330,7 @@ def main():
     achieved_resident = bytes_kernel / t_k / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of the two fused launches (border ring + interior) of one batch, from
     # profiles/r01_fused_warp_accumulate_ncu.txt (ncu --set full); measured for the batch sizes listed here only
-    traffic = {128: 2.1844e9 + 20.8e6 + 0.2362e9 + 4.4e6, 64: 1.0494e9 + 14.8e6 + 0.1192e9 + 0.4e6}.get(B)
+    traffic = {128: 2.4560e9 + 20.5e6 + 0.2362e9 + 4.2e6}.get(B)
 
     # ---------------- CPU baseline (rank 0, N=1 only) ---------------------------------------------------
     cpu = None

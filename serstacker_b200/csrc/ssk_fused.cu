@@ -581,6 +581,19 @@ __device__ __noinline__ StagePlan plan_stage_ring(const MapCoef &m, int bx0, int
   const int lo_x = min(p.sx0, p.sxw), hi_x = max(p.sx0 + wd, p.sxw + WWD), hi_y = p.sy0 + GSH;
   if (-lo_x >= a.src_cols || hi_x - a.src_cols >= a.src_cols || -p.sy0 >= a.src_rows || hi_y - a.src_rows >= a.src_rows) return p;
   p.staged = (x_hi - p.sx0 < wd) && (y_hi - p.sy0 < GSH) && (x_hi - p.sxw < WWD);
+  if (p.staged) {
+    // staged = 2: every pixel of the tile and of its 2-px erosion halo (clipped to the image) maps into the tap-safe
+    // interior of the frame, so the eroded validity mask is all ones for this frame and the flag pass is skipped
+    const int hx0 = max(bx0 - 2, 0), hy0 = max(by0 - 2, 0), hx1 = min(bx0 + TW + 1, a.cols - 1), hy1 = min(by0 + TH + 1, a.rows - 1);
+    float hu0 = 3.4e38f, hu1 = -3.4e38f, hv0 = 3.4e38f, hv1 = -3.4e38f;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+      float u, v;
+      map_xy(m, (float)((k & 1) ? hx1 : hx0), (float)((k & 2) ? hy1 : hy0), u, v);
+      hu0 = fminf(hu0, u); hu1 = fmaxf(hu1, u); hv0 = fminf(hv0, v); hv1 = fmaxf(hv1, v);
+    }
+    if (hu0 >= 3.f && hv0 >= 3.f && hu1 <= (float)(a.src_cols - 4) && hv1 <= (float)(a.src_rows - 4)) p.staged = 2;
+  }
   return p;
 }
 
@@ -690,7 +703,7 @@ __global__ void __launch_bounds__(TW * (RING ? RING_WARPS : SWARPS), RING ? SSK_
       }
     }
     cp_async_commit();
-    if (RING && plan.staged) {
+    if (RING && plan.staged == 1) {
       // pre-erosion validity of the tile and its 2-px halo (outside the image: erode border value 255), one warp
       // per row, packed by ballots
       // columns -2 .. 29 of a row go through one ballot; columns 30 .. 33 of all rows of this warp share one more
@@ -762,7 +775,7 @@ __global__ void __launch_bounds__(TW * (RING ? RING_WARPS : SWARPS), RING ? SSK_
 #pragma unroll
           for (int jj = 0; jj < N; ++jj) {
             const unsigned long long m4 = k + jj < GR ? hm[k + jj + 4] : 0ull;
-            const bool ok = ((m0 & m1 & m2 & m3 & m4) >> lane) & 1ull;
+            const bool ok = plan.staged == 2 || (((m0 & m1 & m2 & m3 & m4) >> lane) & 1ull);
             m0 = m1; m1 = m2; m2 = m3; m3 = m4;
             if (k + jj < nrow) {
               if (C2) {
