@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(256) k_sepfilter(const SepFilterArgs a) {
 }
 
 // ---- W1 ------------------------------------------------------------------------------------------
-constexpr int W1_W = 64, W1_H = 16, W1_RMAX = 4;
+constexpr int W1_W = 64, W1_H = 32, W1_RMAX = 4;
 
 __global__ void __launch_bounds__(256) k_w1_grad(const W1Args a, int nblocks) {
   __shared__ float s_in[W1_H + 2 * W1_RMAX][W1_W + 2 * W1_RMAX + 1];
