@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=128, help="frames per step per GPU")
+    ap.add_argument("--chunk", type=int, default=128, help="frames per launch (max_batch of the pipeline); a step is batch/chunk launches")
     ap.add_argument("--pool", type=int, default=256, help="distinct synthetic frames resident per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=24, help="frames of the CPU baseline sample")
@@ -227,6 +228,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     B = args.batch
+    CH = max(1, min(args.chunk, B))
     pool_n = max(args.pool, B + 1)
     pool = make_frames_gpu(pool_n, args.seed + 1000 * rank, dev)       # frame 0 = unjittered reference scene
     ref = make_frames_gpu(1, 2, dev)[0] if rank != 0 else pool[0]   # every rank uses the same reference frame
@@ -235,7 +237,8 @@ def main():
 
     ro = api.registration_options(motion_type=capi.MOTION_AFFINE, interpolation=capi.INTER_CUBIC,
                                   ecc=dict(ecc_method=capi.ECC_INVERSE_COMPOSITIONAL_LM, ecch_max_level=-1))
-    so = api.stack_options(registration=ro, accumulation_method=capi.STACK_WEIGHTED_AVERAGE, max_batch=B)
+    so = api.stack_options(registration=ro, accumulation_method=capi.STACK_WEIGHTED_AVERAGE, max_batch=CH)
+    so_e2e = api.stack_options(registration=ro, accumulation_method=capi.STACK_WEIGHTED_AVERAGE, max_batch=B)
     pipe = api.c_image_stacking_pipeline(so)
     pipe.set_reference(capi.device_mat(ref.data_ptr(), H, W, np.float32))
     stream = torch.cuda.ExternalStream(pipe.stream(), device=dev)
@@ -268,6 +271,7 @@ def main():
     keep = []
     for s in range(args.steps):
         keep.append(pipe.add_frames_async(dev_batch(args.warmup + s)))
+    pipe.flush()                                    # the last call's ring kernel (side stream) is part of the timed work
     e1.record(stream)
     pipe.sync()
     combined_frames = combine()
@@ -287,7 +291,7 @@ def main():
     host = torch.empty((n_host, H, W), dtype=torch.float32).pin_memory()
     host.copy_(pool[1:1 + n_host])
     host_np = host.numpy()
-    pipe2 = api.c_image_stacking_pipeline(so)
+    pipe2 = api.c_image_stacking_pipeline(so_e2e)
     pipe2.set_reference(ref.cpu().numpy())
     e2e_steps = max(4, min(args.steps, 16))
 
@@ -321,8 +325,8 @@ def main():
     # ---------------- roofline of the fused warp+accumulate kernel --------------------------------------
     peak, peak_src = peaks()
     t_k = stage[3] * 1e-3                            # device time of k_fill_jobs + k_warp_acc for one batch
-    bytes_kernel = NPIX * (4 + 4) * B + NPIX * 16    # frame + weight map read per frame; mean + weight RMW once per batch
-    bytes_survey = NPIX * 24 * B                     # N*(4 + 8 + 8 + 4) per frame (un-batched RMW)
+    bytes_kernel = NPIX * (4 + 4) * CH + NPIX * 16   # frame + weight map read per frame; mean + weight RMW once per launch
+    bytes_survey = NPIX * 24 * CH                    # N*(4 + 8 + 8 + 4) per frame (un-batched RMW)
     # roofline.achieved follows the contract: SURVEY section 8(d)'s per-frame figure x the frames of one launch / launch time.
     # The kernel keeps the accumulator tile on chip across the batch, so the bytes it really has to move are fewer
     # (frame + weight map once per frame, accumulators once per batch): reported beside it as *_resident_acc.
@@ -330,7 +334,7 @@ def main():
     achieved_resident = bytes_kernel / t_k / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of the two fused launches (border ring + interior) of one batch, from
     # profiles/r01_fused_warp_accumulate_ncu.txt (ncu --set full); measured for the batch sizes listed here only
-    traffic = {128: 2.4560e9 + 20.5e6 + 0.2362e9 + 4.2e6}.get(B)
+    traffic = {128: 2.4560e9 + 20.5e6 + 0.2362e9 + 4.2e6}.get(CH)
 
     # ---------------- CPU baseline (rank 0, N=1 only) ---------------------------------------------------
     cpu = None
@@ -348,7 +352,7 @@ def main():
             "metric": "frames/sec register+warp+stack 1080p", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "resident_pool_frames": pool_n,
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "frames_per_launch": CH, "resident_pool_frames": pool_n,
                        "l2_policy": "inputs larger than L2: %d distinct frames (%.1f GB) cycled, %.0f MB touched per step" % (
                            pool_n, pool_n * NPIX * 4 / 1e9, B * NPIX * 4 / 1e6),
                        "accumulated_frames": accumulated},
@@ -358,7 +362,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_fused_staged (fused bicubic warp + eroded mask + weight warp + running weighted mean; interior + border-ring launch per batch)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "launch_ms": stage[3], "frames_per_launch": B,
+                         "traffic": traffic, "peak_source": peak_src, "launch_ms": stage[3], "frames_per_launch": CH,
                          "algorithmic_bytes_per_launch": bytes_survey,
                          "algorithmic_bytes_per_frame": NPIX * 24,
                          "achieved_resident_acc": achieved_resident, "frac_resident_acc": achieved_resident / peak,

@@ -326,6 +326,11 @@ SSK_API int ssk_stack_submit(ssk_stack *h, const ssk_mat *frames, int n, int bpp
 SSK_API int ssk_stack_wait(ssk_stack *h, int64_t ticket, ssk_transform *transforms_out, ssk_ecc_status *status_out,
                            int capacity, int *n_out);
 SSK_API int ssk_stack_sync(ssk_stack *h);
+/* Device-frame calls leave the border-ring part of their warp+accumulate stage running on a side stream so that it
+ * overlaps the registration of the next call.  ssk_stack_flush makes the handle's stream wait for it (no host
+ * synchronisation): call it before recording a timing event on ssk_stack_stream().  ssk_stack_sync, _compute,
+ * _accumulated_frames and _accumulator include it. */
+SSK_API int ssk_stack_flush(ssk_stack *h);
 /* c_frame_accumulation::compute() of the pipeline's accumulator. */
 SSK_API int ssk_stack_compute(ssk_stack *h, ssk_mat *avg, ssk_mat *mask);
 SSK_API int ssk_stack_accumulated_frames(ssk_stack *h);

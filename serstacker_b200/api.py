@@ -407,6 +407,10 @@ class c_image_stacking_pipeline:
     def sync(self):
         check(capi.lib.ssk_stack_sync(self._h))
 
+    def flush(self):
+        """Stream-side join of the ring kernel left running by the last device-frame call (no host sync)."""
+        check(capi.lib.ssk_stack_flush(self._h))
+
     def accumulated_frames(self):
         return capi.lib.ssk_stack_accumulated_frames(self._h)
 

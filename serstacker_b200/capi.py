@@ -137,6 +137,7 @@ _sigs = {
     "ssk_stack_add_frames": (C.c_int, [C.c_void_p, _P(ssk_mat), C.c_int, C.c_int, _P(ssk_transform), _P(ssk_ecc_status)]),
     "ssk_stack_add_frames_async": (C.c_int, [C.c_void_p, _P(ssk_mat), C.c_int, C.c_int]),
     "ssk_stack_sync": (C.c_int, [C.c_void_p]),
+    "ssk_stack_flush": (C.c_int, [C.c_void_p]),
     "ssk_stack_submit": (C.c_int, [C.c_void_p, _P(ssk_mat), C.c_int, C.c_int, _P(C.c_int64)]),
     "ssk_stack_wait": (C.c_int, [C.c_void_p, C.c_int64, _P(ssk_transform), _P(ssk_ecc_status), C.c_int, _P(C.c_int)]),
     "ssk_stack_compute": (C.c_int, [C.c_void_p, _P(ssk_mat), _P(ssk_mat)]),

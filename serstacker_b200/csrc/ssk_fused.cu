@@ -855,7 +855,7 @@ void launch_staged_ring(const WarpAccArgs &a, const Tables &tab, const TileList 
   count_launch();
   if (a.side_stream) cudaEventRecord(static_cast<cudaEvent_t>(a.ev_join), ring_stream);
   k_fused_staged<DEPTH, INTERP, WEIGHTS, MT, false><<<dim3(tl.ntx - 2, tl.nty - 2), block, 0, s>>>(a, tab, tl);
-  if (a.side_stream) cudaStreamWaitEvent(s, static_cast<cudaEvent_t>(a.ev_join), 0);
+  if (a.side_stream && !a.defer_join) cudaStreamWaitEvent(s, static_cast<cudaEvent_t>(a.ev_join), 0);
 }
 
 template <int DEPTH, int INTERP, bool WEIGHTS>

@@ -69,6 +69,14 @@ struct ssk_stack {
   cudaEvent_t ev[5] = {};
   cudaStream_t side = nullptr;           // border-ring kernel of the fused warp+accumulate stage
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // Device-frame calls that span several chunks let the ring kernel of chunk k run behind the registration of chunk
+  // k + 1 (joined at the end of the call): what the ring kernel reads exists twice, chunks alternate between the copies.
+  DevBuf weight_slots_b, d_weight_ptrs_b, d_tmaps_weights_b, jobs_b;
+  cudaEvent_t ev_join_b = nullptr;
+  int parity = 0;
+  bool join_recorded[2] = {false, false};
+  int ring_pending = -1;                 // copy whose ring kernel the handle's stream has not been made to wait for yet
+  cudaEvent_t ev_ring_end = nullptr;     // (timing) end of the last chunk's ring kernel, on the side stream
   DevBuf ref_staging, axis_tab;
   int axis_tab_built = 0;                // W1 up-sampling tables of this geometry are in axis_tab
   // host frames: sub-chunks of `host_chunk` frames rotate through `nsets` sets of frame slots; a copy stream uploads
@@ -94,6 +102,8 @@ struct ssk_stack {
     for (auto &e : ev) if (e) cudaEventDestroy(e);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
+    if (ev_join_b) cudaEventDestroy(ev_join_b);
+    if (ev_ring_end) cudaEventDestroy(ev_ring_end);
     if (side) cudaStreamDestroy(side);
     if (stream) cudaStreamDestroy(stream);
   }
@@ -126,6 +136,7 @@ static int stack_alloc_slots(ssk_stack *h) {
     }
   }
   if (int e = h->jobs.ensure(sizeof(FrameJob) * B)) return e;
+  if (int e = h->jobs_b.ensure(sizeof(FrameJob) * B)) return e;
   if (int e = h->counter.ensure(sizeof(int))) return e;
   if (int e = h->h_counter.ensure(sizeof(int))) return e;
   SSK_CUDA(cudaMemset(h->counter.p, 0, sizeof(int)));
@@ -151,6 +162,8 @@ static int stack_alloc_slots(ssk_stack *h) {
     SSK_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
     SSK_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     SSK_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    SSK_CUDA(cudaEventCreateWithFlags(&h->ev_join_b, cudaEventDisableTiming));
+    SSK_CUDA(cudaEventCreate(&h->ev_ring_end));
   }
   if (h->o.accumulation_method == SSK_STACK_WEIGHTED_AVERAGE && h->o.sm_kradius > 0) {
     // pdownscale chain sizes (c_local_variance_sharpness_measure.cc:28-52)
@@ -172,15 +185,23 @@ static int stack_alloc_slots(ssk_stack *h) {
     if (int e = h->d_gmap_ptrs.ensure(sizeof(void *) * B)) return e;
     for (int b = 0; b < B; ++b) p[b] = h->weight_slots.as<float>() + npix * b;
     SSK_CUDA(cudaMemcpy(h->d_weight_ptrs.p, p.data(), sizeof(void *) * B, cudaMemcpyHostToDevice));
+    if (int e = h->weight_slots_b.ensure(npix * 4 * B)) return e;
+    if (int e = h->d_weight_ptrs_b.ensure(sizeof(void *) * B)) return e;
+    std::vector<void *> pb(B);
+    for (int b = 0; b < B; ++b) pb[b] = h->weight_slots_b.as<float>() + npix * b;
+    SSK_CUDA(cudaMemcpy(h->d_weight_ptrs_b.p, pb.data(), sizeof(void *) * B, cudaMemcpyHostToDevice));
     h->tma_weights = false;
     if (!getenv("SSK_NO_TMA")) {
-      std::vector<unsigned char> maps((size_t)B * 128);
+      std::vector<unsigned char> maps((size_t)B * 128), maps_b((size_t)B * 128);
       bool ok = true;
       for (int b = 0; b < B && ok; ++b)
-        ok = encode_tmap_2d_f32(maps.data() + (size_t)b * 128, p[b], h->cols, h->rows, (int64_t)h->cols * 4, staged_box_w(), staged_box_h());
+        ok = encode_tmap_2d_f32(maps.data() + (size_t)b * 128, p[b], h->cols, h->rows, (int64_t)h->cols * 4, staged_box_w(), staged_box_h()) &&
+             encode_tmap_2d_f32(maps_b.data() + (size_t)b * 128, pb[b], h->cols, h->rows, (int64_t)h->cols * 4, staged_box_w(), staged_box_h());
       if (ok) {
         if (int e = h->d_tmaps_weights.ensure(maps.size())) return e;
+        if (int e = h->d_tmaps_weights_b.ensure(maps.size())) return e;
         SSK_CUDA(cudaMemcpy(h->d_tmaps_weights.p, maps.data(), maps.size(), cudaMemcpyHostToDevice));
+        SSK_CUDA(cudaMemcpy(h->d_tmaps_weights_b.p, maps_b.data(), maps_b.size(), cudaMemcpyHostToDevice));
         h->tma_weights = true;
       }
     }
@@ -288,10 +309,19 @@ static int stack_upload(ssk_stack *h, const ssk_mat *frames, int n, int set) {
 
 // One chunk of frames through the per-frame loop.  set >= 0: host frames already being uploaded into slot set `set`;
 // set < 0: device frames.  The registration records land in rec_all[rec_off ...].
-static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int set, int rec_off) {
+static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int set, int rec_off, bool last_in_call) {
   const int d = type_depth(h->type), cn = type_cn(h->type);
   const size_t rowb = (size_t)h->cols * cn * depth_bytes(d);
   cudaStream_t s = h->stream;
+  // copy (0 / 1) of the buffers the ring kernel reads; host-frame chunks join their ring kernel at once and stay on copy 0
+  (void)last_in_call;
+  const bool defer = set < 0 && h->side && !getenv("SSK_NO_SIDE_STREAM") && !getenv("SSK_NO_DEFERRED_RING");
+  const int par = set < 0 ? h->parity : 0;
+  if (set < 0) h->parity ^= 1;
+  float *const *weight_ptrs = (par ? h->d_weight_ptrs_b : h->d_weight_ptrs).as<float *>();
+  FrameJob *jobs = (par ? h->jobs_b : h->jobs).as<FrameJob>();
+  cudaEvent_t ev_join = par ? h->ev_join_b : h->ev_join;
+  if (h->join_recorded[par]) SSK_CUDA(cudaStreamWaitEvent(s, ev_join, 0));   // ring kernel of the chunk that used this copy last
   Img geom;
   geom.rows = h->rows; geom.cols = h->cols; geom.depth = d; geom.cn = cn; geom.scale = bpp_scale(d, h->bpp);
   geom.data = nullptr;
@@ -376,7 +406,7 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
     w.M_ptrs = Mptrs; w.rows = h->w1_rows; w.cols = h->w1_cols; w.kradius = std::max(1, h->o.sm_kradius);
     w.depth_scale = 20.0;   // frames are CV_32F when they reach compute_weights
     w.gmap_ptrs = h->d_gmap_ptrs.as<float *>(); w.partials = h->partials.as<double>(); w.stats = h->stats.as<double>();
-    w.out_ptrs = h->d_weight_ptrs.as<float *>(); w.full_rows = h->rows; w.full_cols = h->cols; w.batch = n;
+    w.out_ptrs = weight_ptrs; w.full_rows = h->rows; w.full_cols = h->cols; w.batch = n;
     w.axis_tab = h->axis_tab.as<int2>(); w.axis_tab_built = &h->axis_tab_built;
     w.uscale = h->o.sm_uscale; w.gmap2_ptrs = h->o.sm_uscale > 0 ? h->d_gmap2_ptrs.as<float *>() : nullptr;
     if (int e = launch_w1(w, s)) return e;
@@ -390,12 +420,12 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
 
   // ---- fused warp + mask + weights + accumulate
   k_fill_jobs<<<div_up(n, 128), 128, 0, s>>>(h->o.enable_registration ? h->reg_h.r.ecch.device_frames() : nullptr, d_frame_ptrs,
-                                             weighted ? h->d_weight_ptrs.as<float *>() : nullptr,
-                                             weighted ? h->stats.as<double>() : nullptr, h->jobs.as<FrameJob>(), n,
+                                             weighted ? weight_ptrs : nullptr,
+                                             weighted ? h->stats.as<double>() : nullptr, jobs, n,
                                              h->counter.as<int>(), h->o.enable_registration ? 1 : 0);
   SSK_LAUNCH_CHECK();
   WarpAccArgs a = {};
-  a.jobs = h->jobs.as<FrameJob>(); a.njobs = n;
+  a.jobs = jobs; a.njobs = n;
   a.rows = h->rows; a.cols = h->cols; a.src_rows = h->rows; a.src_cols = h->cols;
   a.src_step = geom.step; a.w_step = (int64_t)h->cols * 4;
   a.depth = d; a.cn = cn; a.scale = geom.scale;
@@ -405,7 +435,7 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
   for (int i = 0; i < 4; ++i) a.bval[i] = (float)ro.border_value[i];
   a.use_weights = weighted ? 1 : 0;
   a.stage_aligned = h->frames_aligned ? 1 : 0;
-  a.side_stream = h->side; a.ev_fork = h->ev_fork; a.ev_join = h->ev_join;
+  a.side_stream = h->side; a.ev_fork = h->ev_fork; a.ev_join = ev_join; a.defer_join = defer ? 1 : 0;
   if (getenv("SSK_NO_SIDE_STREAM")) a.side_stream = nullptr;   // tuning knob: border-ring kernel in stream order
   {
     ssk_transform t0;
@@ -413,9 +443,14 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
     a.map_type = make_mapcoef(t0).type;
   }
   a.tmap_frames = (weighted && d_tmaps) ? d_tmaps : nullptr;
-  a.tmap_weights = (weighted && d_tmaps) ? h->d_tmaps_weights.p : nullptr;
+  a.tmap_weights = (weighted && d_tmaps) ? (par ? h->d_tmaps_weights_b.p : h->d_tmaps_weights.p) : nullptr;
   a.acc = h->acc_h.a.acc.as<float>(); a.wacc = h->acc_h.a.wacc.as<float>();
   if (int e = launch_warp_accumulate(a, h->tab, s)) return e;
+  if (a.side_stream) {
+    h->join_recorded[par] = true;
+    h->ring_pending = defer ? par : -1;
+    SSK_CUDA(cudaEventRecord(h->ev_ring_end, h->side));
+  }
   SSK_CUDA(cudaEventRecord(h->ev[4], s));
   if (set >= 0) SSK_CUDA(cudaEventRecord(h->set_free[set], s));
   if (h->o.enable_registration)
@@ -425,13 +460,13 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
 }
 
 // One chunk of <= max_batch frames: enqueue everything, snapshot the registration records into the chunk's ring slot.
-static int stack_submit_chunk(ssk_stack *h, const ssk_mat *frames, int m, int64_t *ticket) {
+static int stack_submit_chunk(ssk_stack *h, const ssk_mat *frames, int m, int64_t *ticket, bool last_in_call) {
   const int64_t t = h->next_ticket++;
   const int slot = (int)(t % ssk_stack::kRecRing);
   const int base = slot * h->max_batch;
   SSK_CUDA(cudaEventSynchronize(h->rec_ev[slot]));   // the slot's previous download has landed (no-op if never used)
   if (frames[0].mem == SSK_MEM_DEVICE) {
-    if (int e = stack_process_chunk(h, frames, m, -1, base)) return e;
+    if (int e = stack_process_chunk(h, frames, m, -1, base, last_in_call)) return e;
   } else {
     // host frames: upload sub-chunk k+1 on the copy stream while sub-chunk k is processed
     const int hc = h->host_chunk;
@@ -443,7 +478,7 @@ static int stack_submit_chunk(ssk_stack *h, const ssk_mat *frames, int m, int64_
       if (k0 + hc < m) {
         if (int e = stack_upload(h, frames + k0 + hc, std::min(hc, m - k0 - hc), next_set)) return e;
       }
-      if (int e = stack_process_chunk(h, frames + k0, mk, set, base + k0)) return e;
+      if (int e = stack_process_chunk(h, frames + k0, mk, set, base + k0, true)) return e;
       set = next_set;
     }
     h->set_pos = set;
@@ -471,7 +506,7 @@ static int stack_check_frames(ssk_stack *h, const ssk_mat *frames, int n, int bp
 int ssk_stack_submit(ssk_stack *h, const ssk_mat *frames, int n, int bpp, int64_t *ticket) {
   if (int e = stack_check_frames(h, frames, n, bpp)) return e;
   SSK_REQUIRE(n >= 1 && n <= h->max_batch, "ssk_stack_submit: 1..max_batch frames per call");
-  return stack_submit_chunk(h, frames, n, ticket);
+  return stack_submit_chunk(h, frames, n, ticket, true);
 }
 
 int ssk_stack_wait(ssk_stack *h, int64_t ticket, ssk_transform *transforms_out, ssk_ecc_status *status_out, int capacity,
@@ -501,15 +536,26 @@ int ssk_stack_wait(ssk_stack *h, int64_t ticket, ssk_transform *transforms_out, 
 int ssk_stack_add_frames_async(ssk_stack *h, const ssk_mat *frames, int n, int bpp) {
   if (int e = stack_check_frames(h, frames, n, bpp)) return e;
   for (int i0 = 0; i0 < n; i0 += h->max_batch) {
-    if (int e = stack_submit_chunk(h, frames + i0, std::min(h->max_batch, n - i0), nullptr)) return e;
+    if (int e = stack_submit_chunk(h, frames + i0, std::min(h->max_batch, n - i0), nullptr, i0 + h->max_batch >= n)) return e;
+  }
+  return SSK_OK;
+}
+
+int ssk_stack_flush(ssk_stack *h) {
+  SSK_REQUIRE(h, "null handle");
+  if (h->ring_pending >= 0) {
+    SSK_CUDA(cudaStreamWaitEvent(h->stream, h->ring_pending ? h->ev_join_b : h->ev_join, 0));
+    h->ring_pending = -1;
   }
   return SSK_OK;
 }
 
 int ssk_stack_sync(ssk_stack *h) {
   SSK_REQUIRE(h, "null handle");
+  if (int e = ssk_stack_flush(h)) return e;
   SSK_CUDA(cudaMemcpyAsync(h->h_counter.p, h->counter.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   SSK_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->side) SSK_CUDA(cudaStreamSynchronize(h->side));   // a ring kernel left behind by a call that failed half-way
   h->acc_h.a.frames = *h->h_counter.as<int>();
   return SSK_OK;
 }
@@ -520,7 +566,7 @@ int ssk_stack_add_frames(ssk_stack *h, const ssk_mat *frames, int n, int bpp, ss
   for (int i0 = 0; i0 < n; i0 += h->max_batch) {
     const int m = std::min(h->max_batch, n - i0);
     int64_t t = -1;
-    if (int e = stack_submit_chunk(h, frames + i0, m, &t)) return e;
+    if (int e = stack_submit_chunk(h, frames + i0, m, &t, i0 + h->max_batch >= n)) return e;
     if (int e = ssk_stack_wait(h, t, transforms_out ? transforms_out + i0 : nullptr, status_out ? status_out + i0 : nullptr, m, nullptr)) return e;
   }
   return ssk_stack_sync(h);
@@ -538,16 +584,26 @@ int ssk_stack_accumulated_frames(ssk_stack *h) {
   return h->acc_h.a.frames;
 }
 
-ssk_acc *ssk_stack_accumulator(ssk_stack *h) { return h ? &h->acc_h : nullptr; }
+ssk_acc *ssk_stack_accumulator(ssk_stack *h) {
+  if (!h) return nullptr;
+  ssk_stack_flush(h);     // accumulator calls are ordered on the handle's stream: the pending ring kernel first
+  return &h->acc_h;
+}
 ssk_reg *ssk_stack_registration(ssk_stack *h) { return h ? &h->reg_h : nullptr; }
 
 void *ssk_stack_stream(ssk_stack *h) { return h ? (void *)h->stream : nullptr; }
 
 int ssk_stack_stage_times(ssk_stack *h, float ms[4]) {
   SSK_REQUIRE(h && ms, "null argument");
-  SSK_CUDA(cudaStreamSynchronize(h->stream));
+  if (int e = ssk_stack_sync(h)) return e;
   float t[4];
   for (int i = 0; i < 4; ++i) SSK_CUDA(cudaEventElapsedTime(&t[i], h->ev[i], h->ev[i + 1]));
+  // the warp+accumulate stage ends when both of its kernels have: the ring kernel runs on the side stream
+  if (h->side && h->join_recorded[0]) {
+    float tr = 0.f;
+    if (cudaEventElapsedTime(&tr, h->ev[3], h->ev_ring_end) == cudaSuccess) t[3] = std::max(t[3], tr);
+    else cudaGetLastError();
+  }
   ms[0] = t[0]; ms[1] = t[1]; ms[2] = t[2]; ms[3] = t[3];
   return SSK_OK;
 }

@@ -30,6 +30,7 @@ struct WarpAccArgs {
   int stage_aligned;      // all frame / weight-map base pointers are 16-byte aligned (enables cp.async staging)
   int map_type;           // MAP_* common to all jobs of the batch (-1: mixed / unknown -> generic kernel)
   void *side_stream, *ev_fork, *ev_join;   // host only: optional side stream (+2 events) for the border-ring kernel
+  int defer_join;         // host only: do not make `stream` wait for the ring kernel (the caller joins ev_join later)
   // optional TMA staging of the interior tiles (32F frames + weight maps): device arrays of 128-byte tensor maps, one per
   // job, box = staged_box_w() x staged_box_h() elements; null -> cp.async staging
   const void *tmap_frames, *tmap_weights;
