@@ -351,6 +351,23 @@ class c_stacking_loop {
     return ssk_stack_compute(h_, &a, &m) == SSK_OK;
   }
   int accumulated_frames() const { return ssk_stack_accumulated_frames(h_); }
+  // streaming form: enqueue a chunk (<= max_batch frames) and collect its per-frame results one chunk late
+  bool submit(const std::vector<image_t> &frames, int64_t *ticket, int bpp = 0) {
+    std::vector<ssk_mat> v;
+    for (const image_t &f : frames) v.push_back(detail::view(f));
+    return ssk_stack_submit(h_, v.data(), (int)v.size(), bpp, ticket) == SSK_OK;
+  }
+  bool wait(int64_t ticket, std::vector<ssk_transform> *transforms, std::vector<ssk_ecc_status> *status, int capacity) {
+    if (transforms) transforms->resize(capacity);
+    if (status) status->resize(capacity);
+    int n = 0;
+    const bool ok = ssk_stack_wait(h_, ticket, transforms ? transforms->data() : nullptr, status ? status->data() : nullptr, capacity, &n) == SSK_OK;
+    if (transforms) transforms->resize(n);
+    if (status) status->resize(n);
+    return ok;
+  }
+  bool sync() { return ssk_stack_sync(h_) == SSK_OK; }
+  bool flush() { return ssk_stack_flush(h_) == SSK_OK; }   // stream-side join of the side-stream ring kernel (see ssk.h)
 
  private:
   ssk_stack *h_ = nullptr;
