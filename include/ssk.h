@@ -268,6 +268,17 @@ SSK_API int ssk_lpg(const ssk_mat *image, double k, double p, int dscale, int us
 SSK_API int ssk_gaussian_blur(const ssk_mat *src, double sigma_x, double sigma_y, ssk_mat *dst);
 
 /* ---------------------------------------------------------------------------------------------
+ * Finishing step of the stacking pass: average_pyramid_inpaint(src, mask, dst, dstmask, max_levels)
+ * (core/proc/inpaint/average_pyramid_inpaint.cc:97-127; call site c_image_stacking_pipeline.cc:763-767 with
+ * max_levels = 100).  src / dst: CV_32F, 1 to 4 channels, same size; mask / dstmask: CV_8UC1 (dstmask may be null).
+ * A null mask or a mask without holes returns copies of the inputs, like the reference.
+ * ------------------------------------------------------------------------------------------- */
+SSK_API int ssk_average_pyramid_inpaint(const ssk_mat *src, const ssk_mat *mask, ssk_mat *dst, ssk_mat *dstmask, int max_levels);
+/* c_frame_accumulation::compute(avg, mask, dscale) followed by average_pyramid_inpaint(avg, mask, avg, mask, max_levels)
+ * without leaving the device: what c_image_stacking_pipeline.cc:742-767 does with the accumulator at the end of a run. */
+SSK_API int ssk_acc_compute_inpainted(ssk_acc *h, ssk_mat *avg, ssk_mat *mask, double dscale, int max_levels);
+
+/* ---------------------------------------------------------------------------------------------
  * Jovian derotation map: compute_ellipsoid_zrotation_remap (core/proc/feature2d/ellipsoid.cc:206-277), called by
  * c_jovian_derotation_remap::compute_derotation_for_angle (c_jovian_derotation_remap.cc:47-60).
  * R1 = pose of the ellipsoid as imaged, R2 = target pose (row-major 3x3, XYZscreen = R * XYZplanet); ebox_angle_deg and
@@ -333,6 +344,8 @@ SSK_API int ssk_stack_sync(ssk_stack *h);
 SSK_API int ssk_stack_flush(ssk_stack *h);
 /* c_frame_accumulation::compute() of the pipeline's accumulator. */
 SSK_API int ssk_stack_compute(ssk_stack *h, ssk_mat *avg, ssk_mat *mask);
+/* ssk_stack_compute + average_pyramid_inpaint (c_image_stacking_pipeline.cc:742-767) */
+SSK_API int ssk_stack_compute_inpainted(ssk_stack *h, ssk_mat *avg, ssk_mat *mask, int max_levels);
 SSK_API int ssk_stack_accumulated_frames(ssk_stack *h);
 SSK_API ssk_acc *ssk_stack_accumulator(ssk_stack *h);
 SSK_API ssk_reg *ssk_stack_registration(ssk_stack *h);

@@ -7,7 +7,7 @@ Follows /root/reference/core/pipeline/c_image_stacking_pipeline/c_image_stacking
                                            remap(weights) -> weights*mask -> add)
   multiply_weights            :108-138, 1704-1714
   weights_required            :2004-2011, compute_weights :2013-2020
-  finalise (compute)          :731-769 (average_pyramid_inpaint is out of scope: compared on W>0 before it)
+  finalise (compute)          :731-769 (average_pyramid_inpaint: oracle/inpaint.py)
 and the input scaling of c_image_stacking_pipeline_base.cc:271-276 (convertTo(CV_32F, 1/(1<<bpp))).
 
 Test infrastructure only (see oracle/__init__.py).

@@ -239,6 +239,14 @@ class c_frame_accumulation:
         check(capi.lib.ssk_acc_compute(self._h, C.byref(mat(avg)), ref(mat(mask)), float(dscale)))
         return avg, mask
 
+    def compute_inpainted(self, dscale=1.0, max_levels=100):
+        """compute() + average_pyramid_inpaint on the device (c_image_stacking_pipeline.cc:742-767)."""
+        w, h, c = self.accumulator_size()
+        avg = np.empty((h, w) if c == 1 else (h, w, c), dtype=f32)
+        mask = np.empty((h, w), dtype=np.uint8)
+        check(capi.lib.ssk_acc_compute_inpainted(self._h, C.byref(mat(avg)), C.byref(mat(mask)), float(dscale), int(max_levels)))
+        return avg, mask
+
     def get_acc_counters(self):
         w, h, c = self.accumulator_size()
         wc = 3 if self.kind == capi.ACC_BAYER_AVERAGE else 1
@@ -288,6 +296,20 @@ def lpg(image, k=2.0, p=2.0, dscale=2, uscale=6):
     mo = mat(out)
     check(capi.lib.ssk_lpg(C.byref(mat(image)), float(k), float(p), int(dscale), int(uscale), C.byref(mo)))
     return out
+
+
+def average_pyramid_inpaint(src, mask, max_levels=100, want_mask=True):
+    """average_pyramid_inpaint (core/proc/inpaint/average_pyramid_inpaint.cc:97-127) -> (dst, dstmask)."""
+    src = np.ascontiguousarray(src, dtype=f32)
+    dst = np.empty_like(src)
+    if mask is None:
+        check(capi.lib.ssk_average_pyramid_inpaint(C.byref(mat(src)), None, C.byref(mat(dst)), None, int(max_levels)))
+        return dst, None
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    dmask = np.empty_like(mask) if want_mask else None
+    check(capi.lib.ssk_average_pyramid_inpaint(C.byref(mat(src)), C.byref(mat(mask)), C.byref(mat(dst)), ref(mat(dmask)),
+                                               int(max_levels)))
+    return dst, dmask
 
 
 def gaussian_blur(src, sigma_x, sigma_y=0.0):
@@ -414,11 +436,16 @@ class c_image_stacking_pipeline:
     def accumulated_frames(self):
         return capi.lib.ssk_stack_accumulated_frames(self._h)
 
-    def compute(self):
+    def compute(self, inpaint_max_levels=None):
+        """(avg, mask) of the accumulator; with inpaint_max_levels the holes are filled on the device by
+        average_pyramid_inpaint, as c_image_stacking_pipeline.cc:742-767 does at the end of a run."""
         h, w, c = self._shape
         avg = np.empty((h, w) if c == 1 else (h, w, c), dtype=f32)
         mask = np.empty((h, w), dtype=np.uint8)
-        check(capi.lib.ssk_stack_compute(self._h, C.byref(mat(avg)), C.byref(mat(mask))))
+        if inpaint_max_levels is None:
+            check(capi.lib.ssk_stack_compute(self._h, C.byref(mat(avg)), C.byref(mat(mask))))
+        else:   # c_image_stacking_pipeline.cc:763-767 passes 100
+            check(capi.lib.ssk_stack_compute_inpainted(self._h, C.byref(mat(avg)), C.byref(mat(mask)), int(inpaint_max_levels)))
         return avg, mask
 
     def accumulator(self):

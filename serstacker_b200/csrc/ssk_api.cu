@@ -486,6 +486,41 @@ int ssk_acc_compute(ssk_acc *h, ssk_mat *avg, ssk_mat *mask, double dscale) {
   return SSK_OK;
 }
 
+// c_image_stacking_pipeline.cc:742-767: compute() then average_pyramid_inpaint(avg, mask, avg, mask, max_levels)
+int ssk_acc_compute_inpainted(ssk_acc *h, ssk_mat *avg, ssk_mat *mask, double dscale, int max_levels) {
+  SSK_REQUIRE(h && avg, "null argument");
+  Acc &a = h->a;
+  if (a.frames < 1) { set_error("c_frame_accumulation::compute: no accumulated frames"); return SSK_ERR_STATE; }
+  const int ocn = a.kind == SSK_ACC_BAYER_AVERAGE ? 3 : a.cn;
+  const size_t rowb = (size_t)a.cols * ocn * 4, npx = (size_t)a.rows * a.cols;
+  if (int e = check_mat(avg, "compute avg")) return e;
+  SSK_REQUIRE(type_depth(avg->type) == SSK_32F && type_cn(avg->type) == ocn && avg->rows == a.rows && avg->cols == a.cols,
+              "compute: avg must be CV_32F with the accumulator's size and channels");
+  if (mask) {
+    if (int e = check_mat(mask, "compute mask")) return e;
+    SSK_REQUIRE(mask->type == SSK_8UC1 && mask->rows == a.rows && mask->cols == a.cols, "compute: mask must be CV_8UC1 of the accumulator size");
+  }
+  const size_t img_b = (rowb * a.rows + 15) & ~(size_t)15, msk_b = (npx + 15) & ~(size_t)15;
+  if (int e = a.out_staging.ensure(2 * (img_b + msk_b) + inpaint_work_bytes(a.rows, a.cols, ocn, max_levels))) return e;
+  char *base = a.out_staging.as<char>();
+  float *d_avg = reinterpret_cast<float *>(base), *d_out = reinterpret_cast<float *>(base + img_b);
+  uint8_t *d_mask = reinterpret_cast<uint8_t *>(base + 2 * img_b), *d_omask = d_mask + msk_b;
+  void *work = base + 2 * (img_b + msk_b);
+  if (a.kind == SSK_ACC_BAYER_AVERAGE) {
+    if (int e = launch_bayer_compute(a.acc.as<float>(), a.wacc.as<float>(), a.rows, a.cols, d_avg, (int64_t)rowb, d_mask, a.cols, a.stream)) return e;
+  } else {
+    if (int e = launch_acc_compute(a.acc.as<float>(), a.wacc.as<float>(), a.rows, a.cols, a.cn, (float)dscale, d_avg, (int64_t)rowb,
+                                   d_mask, a.cols, a.stream)) return e;
+  }
+  int full = 0;
+  if (int e = launch_average_pyramid_inpaint(d_avg, (int64_t)rowb, d_mask, a.cols, a.rows, a.cols, ocn, max_levels, work, d_out, d_omask,
+                                             &full, a.stream)) return e;
+  if (int e = from_device(d_out, rowb, a.rows, avg, a.stream)) return e;
+  if (mask) if (int e = from_device(d_omask, (size_t)a.cols, a.rows, mask, a.stream)) return e;
+  SSK_CUDA(cudaStreamSynchronize(a.stream));
+  return SSK_OK;
+}
+
 int ssk_acc_get_counters(ssk_acc *h, ssk_mat *accw) {
   SSK_REQUIRE(h, "null handle");
   Acc &a = h->a;
@@ -789,6 +824,53 @@ int ssk_ellipsoid_zrotation_remap(int rows, int cols, const double center[2], co
   if (int e = from_device(sc.a.p, (size_t)cols * 8, rows, rmap, s)) return e;
   if (int e = from_device(sc.d.p, (size_t)cols * 4, rows, wmap, s)) return e;
   if (int e = from_device(sc.c.p, (size_t)cols, rows, rmask, s)) return e;
+  SSK_CUDA(cudaStreamSynchronize(s));
+  return SSK_OK;
+}
+
+// average_pyramid_inpaint(src, mask, dst, dstmask, max_levels) (core/proc/inpaint/average_pyramid_inpaint.cc:97-127)
+int ssk_average_pyramid_inpaint(const ssk_mat *src, const ssk_mat *mask, ssk_mat *dst, ssk_mat *dstmask, int max_levels) {
+  if (int e = ensure_device()) return e;
+  if (int e = check_mat(src, "average_pyramid_inpaint src")) return e;
+  if (int e = check_mat(dst, "average_pyramid_inpaint dst")) return e;
+  SSK_REQUIRE(type_depth(src->type) == SSK_32F && dst->type == src->type && dst->rows == src->rows && dst->cols == src->cols,
+              "average_pyramid_inpaint: CV_32F source and destination of the same size and type");
+  if (mask) {
+    if (int e = check_mat(mask, "average_pyramid_inpaint mask")) return e;
+    SSK_REQUIRE(mask->type == SSK_8UC1 && mask->rows == src->rows && mask->cols == src->cols,
+                "average_pyramid_inpaint: the mask must be CV_8UC1 of the image size");
+  }
+  if (dstmask) {
+    SSK_REQUIRE(mask, "average_pyramid_inpaint: dstmask requested without a mask");
+    if (int e = check_mat(dstmask, "average_pyramid_inpaint dstmask")) return e;
+    SSK_REQUIRE(dstmask->type == SSK_8UC1 && dstmask->rows == src->rows && dstmask->cols == src->cols,
+                "average_pyramid_inpaint: dstmask must be CV_8UC1 of the image size");
+  }
+  Scratch &sc = scratch();
+  if (int e = sc.init()) return e;
+  cudaStream_t s = sc.stream;
+  Img im;
+  if (int e = to_device(src, sc.a, s, &im, 0)) return e;
+  const int cn = im.cn;
+  const size_t rowb = (size_t)im.cols * cn * 4;
+  if (!mask) {     // average_pyramid_inpaint.cc:104-110: nothing to fill
+    SSK_CUDA(cudaMemcpy2DAsync(dst->data, dst->step, im.data, im.step, rowb, im.rows,
+                               dst->mem == SSK_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    SSK_CUDA(cudaStreamSynchronize(s));
+    return SSK_OK;
+  }
+  Img mim;
+  if (int e = to_device(mask, sc.b, s, &mim, 0)) return e;
+  const size_t npx = (size_t)im.rows * im.cols;
+  if (int e = sc.c.ensure(rowb * im.rows + npx)) return e;
+  if (int e = sc.d.ensure(inpaint_work_bytes(im.rows, im.cols, cn, max_levels))) return e;
+  float *d_out = sc.c.as<float>();
+  uint8_t *d_omask = reinterpret_cast<uint8_t *>(sc.c.as<char>() + rowb * im.rows);
+  int full = 0;
+  if (int e = launch_average_pyramid_inpaint(static_cast<const float *>(im.data), im.step, static_cast<const uint8_t *>(mim.data), mim.step,
+                                             im.rows, im.cols, cn, max_levels, sc.d.p, d_out, d_omask, &full, s)) return e;
+  if (int e = from_device(d_out, rowb, im.rows, dst, s)) return e;
+  if (dstmask) if (int e = from_device(d_omask, (size_t)im.cols, im.rows, dstmask, s)) return e;
   SSK_CUDA(cudaStreamSynchronize(s));
   return SSK_OK;
 }

@@ -96,4 +96,11 @@ int launch_apply_refmask(const uint8_t *mask, int n, float *gx, float *gy, int *
 int launch_erode5_u8(const uint8_t *src, int64_t sstep, uint8_t *dst, int64_t dstep, int rows, int cols,
                      int border_replicate, cudaStream_t s);
 
+// average_pyramid_inpaint (core/proc/inpaint/average_pyramid_inpaint.cc:97-127; ssk_inpaint.cu).  src: CV_32F with `cn`
+// interleaved channels, mask: CV_8UC1 (both on the device, any step); dst / dstmask dense; `work` holds
+// inpaint_work_bytes() bytes.  *was_full = 1 when the mask had no holes (outputs are copies of the inputs).
+size_t inpaint_work_bytes(int rows, int cols, int cn, int max_levels);
+int launch_average_pyramid_inpaint(const float *src, int64_t sstep, const uint8_t *mask, int64_t mstep, int rows, int cols, int cn,
+                                   int max_levels, void *work, float *dst, uint8_t *dstmask, int *was_full, cudaStream_t s);
+
 }  // namespace ssk

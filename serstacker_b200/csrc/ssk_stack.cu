@@ -578,6 +578,12 @@ int ssk_stack_compute(ssk_stack *h, ssk_mat *avg, ssk_mat *mask) {
   return ssk_acc_compute(&h->acc_h, avg, mask, 1.0);
 }
 
+int ssk_stack_compute_inpainted(ssk_stack *h, ssk_mat *avg, ssk_mat *mask, int max_levels) {
+  SSK_REQUIRE(h, "null handle");
+  if (int e = ssk_stack_sync(h)) return e;
+  return ssk_acc_compute_inpainted(&h->acc_h, avg, mask, 1.0, max_levels);
+}
+
 int ssk_stack_accumulated_frames(ssk_stack *h) {
   if (!h) return 0;
   if (ssk_stack_sync(h)) return -1;

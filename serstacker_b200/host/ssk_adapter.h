@@ -258,6 +258,15 @@ class c_frame_accumulation {
     if (mask) { create_like(*mask, rows, cols, SSK_8UC1); m = detail::view(*mask); }
     return ssk_acc_compute(h_, &a, mask ? &m : nullptr, dscale) == SSK_OK;
   }
+  // compute() + average_pyramid_inpaint(avg, mask, avg, mask, max_levels) on the device (c_image_stacking_pipeline.cc:742-767)
+  bool compute_inpainted(image_t &avg, image_t *mask = nullptr, double dscale = 1.0, int max_levels = 100) const {
+    int cols = 0, rows = 0, cn = 0;
+    if (ssk_acc_size(h_, &cols, &rows, &cn) != SSK_OK || cols <= 0) return false;
+    create_like(avg, rows, cols, SSK_MAKETYPE(SSK_32F, cn));
+    ssk_mat a = detail::view(avg), m;
+    if (mask) { create_like(*mask, rows, cols, SSK_8UC1); m = detail::view(*mask); }
+    return ssk_acc_compute_inpainted(h_, &a, mask ? &m : nullptr, dscale, max_levels) == SSK_OK;
+  }
   bool reinitialize(const image_t &src, const image_t &accw) {
     ssk_mat s = detail::view(src), w = detail::view(accw);
     return ssk_acc_reinitialize(h_, &s, &w) == SSK_OK;
@@ -349,6 +358,12 @@ class c_stacking_loop {
     create_like(mask, rows, cols, SSK_8UC1);
     ssk_mat a = detail::view(avg), m = detail::view(mask);
     return ssk_stack_compute(h_, &a, &m) == SSK_OK;
+  }
+  bool compute_inpainted(image_t &avg, image_t &mask, int rows, int cols, int cn = 1, int max_levels = 100) {
+    create_like(avg, rows, cols, SSK_MAKETYPE(SSK_32F, cn));
+    create_like(mask, rows, cols, SSK_8UC1);
+    ssk_mat a = detail::view(avg), m = detail::view(mask);
+    return ssk_stack_compute_inpainted(h_, &a, &m, max_levels) == SSK_OK;
   }
   int accumulated_frames() const { return ssk_stack_accumulated_frames(h_); }
   // streaming form: enqueue a chunk (<= max_batch frames) and collect its per-frame results one chunk late
