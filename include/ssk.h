@@ -268,6 +268,13 @@ SSK_API int ssk_lpg(const ssk_mat *image, double k, double p, int dscale, int us
 SSK_API int ssk_gaussian_blur(const ssk_mat *src, double sigma_x, double sigma_y, ssk_mat *dst);
 
 /* ---------------------------------------------------------------------------------------------
+ * unsharp_mask(src, dst, sigma, alpha, outmin, outmax) (core/proc/unsharp_mask.cc:72-118): the sharpening applied to the
+ * master / reference frame before registration (c_image_stacking_pipeline.cc:1302-1306; defaults sigma 1, alpha 0.8).
+ * CV_32F, 1 to 4 channels.  sigma <= 2 (create_lpass_image's exact branch); outmax <= outmin: no clamp.
+ * ------------------------------------------------------------------------------------------- */
+SSK_API int ssk_unsharp_mask(const ssk_mat *src, ssk_mat *dst, double sigma, double alpha, double outmin, double outmax);
+
+/* ---------------------------------------------------------------------------------------------
  * Finishing step of the stacking pass: average_pyramid_inpaint(src, mask, dst, dstmask, max_levels)
  * (core/proc/inpaint/average_pyramid_inpaint.cc:97-127; call site c_image_stacking_pipeline.cc:763-767 with
  * max_levels = 100).  src / dst: CV_32F, 1 to 4 channels, same size; mask / dstmask: CV_8UC1 (dstmask may be null).

@@ -298,6 +298,14 @@ def lpg(image, k=2.0, p=2.0, dscale=2, uscale=6):
     return out
 
 
+def unsharp_mask(src, sigma, alpha, outmin=-1.0, outmax=-1.0):
+    """unsharp_mask (core/proc/unsharp_mask.cc:72-118) on CV_32F images; c_image_stacking_pipeline.cc:1302-1306."""
+    src = np.ascontiguousarray(src, dtype=f32)
+    dst = np.empty_like(src)
+    check(capi.lib.ssk_unsharp_mask(C.byref(mat(src)), C.byref(mat(dst)), float(sigma), float(alpha), float(outmin), float(outmax)))
+    return dst
+
+
 def average_pyramid_inpaint(src, mask, max_levels=100, want_mask=True):
     """average_pyramid_inpaint (core/proc/inpaint/average_pyramid_inpaint.cc:97-127) -> (dst, dstmask)."""
     src = np.ascontiguousarray(src, dtype=f32)

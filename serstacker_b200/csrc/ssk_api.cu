@@ -828,6 +828,65 @@ int ssk_ellipsoid_zrotation_remap(int rows, int cols, const double center[2], co
   return SSK_OK;
 }
 
+// unsharp_mask(src, dst, sigma, alpha, outmin, outmax) (core/proc/unsharp_mask.cc:72-118) on CV_32F images: the sharpening of
+// the master / reference frame (c_image_stacking_pipeline.cc:1302-1306).  create_lpass_image's single-pass branch
+// (unsharp_mask.cc:44-47: sigma <= 2, or an image too small for a pyramid level) runs on the device; its pyrDown / pyrUp
+// approximation for larger sigma is rejected.
+int ssk_unsharp_mask(const ssk_mat *src, ssk_mat *dst, double sigma, double alpha, double outmin, double outmax) {
+  if (int e = ensure_device()) return e;
+  if (int e = check_mat(src, "unsharp_mask src")) return e;
+  if (int e = check_mat(dst, "unsharp_mask dst")) return e;
+  SSK_REQUIRE(type_depth(src->type) == SSK_32F && dst->type == src->type && dst->rows == src->rows && dst->cols == src->cols,
+              "unsharp_mask: CV_32F source and destination of the same size and type");
+  SSK_REQUIRE(alpha < 1.0, "unsharp_mask: alpha < 1");
+  Scratch &sc = scratch();
+  if (int e = sc.init()) return e;
+  cudaStream_t s = sc.stream;
+  Img im;
+  if (int e = to_device(src, sc.a, s, &im, 0)) return e;
+  const int cn = im.cn;
+  const size_t rowb = (size_t)im.cols * cn * 4, n = (size_t)im.rows * im.cols * cn;
+  if (int e = sc.b.ensure(n * 4 * 2)) return e;
+  const float *d_src = static_cast<const float *>(im.data);
+  if (im.step != (int64_t)rowb) {
+    if (int e = sc.c.ensure(n * 4)) return e;
+    SSK_CUDA(cudaMemcpy2DAsync(sc.c.p, rowb, im.data, im.step, rowb, im.rows, cudaMemcpyDeviceToDevice, s));
+    d_src = sc.c.as<float>();
+  }
+  float *d_lp = sc.b.as<float>(), *d_out = sc.b.as<float>() + n;
+  const int clamp = outmax > outmin;
+  if (sigma <= 0 || alpha <= 0) {           // unsharp_mask.cc:76-78: copy (the clamp below still applies)
+    if (int e = launch_add_weighted(d_src, 1.0, d_src, 0.0, d_out, (int64_t)n, clamp, (float)outmin, (float)outmax, s)) return e;
+  } else {
+    int level = 0;                          // unsharp_mask.cc:25-42
+    if (sigma > 2) {
+      int m = im.rows < im.cols ? im.rows : im.cols, imax = 0, Ci = 0;
+      while (m >>= 1) ++imax;
+      const int Cc = (int)(sigma * sigma / 2);
+      while (level < imax && (1 + 4 * Ci) <= Cc) { Ci = 1 + 4 * Ci; ++level; }
+    }
+    SSK_REQUIRE(level < 1, "unsharp_mask: the pyramid approximation of create_lpass_image (sigma > 2) is not implemented");
+    SepFilterArgs f = {};
+    f.src = d_src; f.dst = d_lp; f.rows = im.rows; f.cols = im.cols; f.batch = 1; f.cn = cn; f.border = SSK_BORDER_REFLECT;
+    // cv::getGaussianKernel(2 * max(1, (int)(sigma * 5)) + 1, sigma, CV_32F)
+    const int taps = 2 * ((int)(sigma * 5) > 1 ? (int)(sigma * 5) : 1) + 1;
+    SSK_REQUIRE(taps <= kMaxTaps, "unsharp_mask: kernel too large");
+    {
+      double cf[kMaxTaps], sum = 0;
+      const double s2 = -0.5 / (sigma * sigma);
+      for (int i = 0; i < taps; ++i) { const double x = i - (taps - 1) * 0.5; cf[i] = std::exp(s2 * x * x); sum += cf[i]; }
+      for (int i = 0; i < taps; ++i) f.kx[i] = f.ky[i] = (float)(cf[i] / sum);
+    }
+    f.kxn = f.kyn = taps;
+    if (int e = launch_sepfilter(f, s)) return e;
+    if (int e = launch_add_weighted(d_src, 1.0 / (1.0 - alpha), d_lp, -alpha / (1.0 - alpha), d_out, (int64_t)n, clamp,
+                                    (float)outmin, (float)outmax, s)) return e;
+  }
+  if (int e = from_device(d_out, rowb, im.rows, dst, s)) return e;
+  SSK_CUDA(cudaStreamSynchronize(s));
+  return SSK_OK;
+}
+
 // average_pyramid_inpaint(src, mask, dst, dstmask, max_levels) (core/proc/inpaint/average_pyramid_inpaint.cc:97-127)
 int ssk_average_pyramid_inpaint(const ssk_mat *src, const ssk_mat *mask, ssk_mat *dst, ssk_mat *dstmask, int max_levels) {
   if (int e = ensure_device()) return e;

@@ -202,7 +202,9 @@ __global__ void __launch_bounds__(256) k_sepfilter(const SepFilterArgs a) {
   constexpr int RMAX = (KXN && KYN) ? ((KXN > KYN ? KXN : KYN) >> 1) : SF_R;
   __shared__ float s_in[SF_H + 2 * RMAX][SF_W + 2 * RMAX + 1];
   __shared__ float s_h[SF_H + 2 * RMAX][SF_W];
-  const int b = blockIdx.z;
+  // interleaved channels and borders other than REPLICATE go through the generic instantiation only
+  const int cn = (KXN || a.cn < 1) ? 1 : a.cn;
+  const int b = blockIdx.z / cn, ch = blockIdx.z - b * cn;
   const float *src = a.src_ptrs ? a.src_ptrs[b] : a.src;
   float *dst = a.dst_ptrs ? a.dst_ptrs[b] : a.dst;
   const int kxn = KXN ? KXN : a.kxn, kyn = KYN ? KYN : a.kyn;
@@ -211,8 +213,13 @@ __global__ void __launch_bounds__(256) k_sepfilter(const SepFilterArgs a) {
   const int ow = min(SF_W, a.cols - x0), oh = min(SF_H, a.rows - y0);
   const int iw = ow + 2 * rx, ih = oh + 2 * ry;
   for_tile(ih, iw, [&](int r, int c) {
-    const int yy = min(max(y0 - ry + r, 0), a.rows - 1), xx = min(max(x0 - rx + c, 0), a.cols - 1);
-    s_in[r][c] = __ldg(src + (int64_t)yy * a.cols + xx);
+    int yy, xx;
+    if (KXN == 0 && a.border) {
+      yy = border_idx(y0 - ry + r, a.rows, a.border); xx = border_idx(x0 - rx + c, a.cols, a.border);
+    } else {
+      yy = min(max(y0 - ry + r, 0), a.rows - 1); xx = min(max(x0 - rx + c, 0), a.cols - 1);
+    }
+    s_in[r][c] = __ldg(src + ((int64_t)yy * a.cols + xx) * cn + ch);
   });
   __syncthreads();
   // row / column arithmetic follows OpenCV's filter engine (found bit-exact against cv2 4.13 for the kernels of this
@@ -255,7 +262,7 @@ __global__ void __launch_bounds__(256) k_sepfilter(const SepFilterArgs a) {
 #pragma unroll
       for (int i = 2; i <= ry; ++i) acc = __fmaf_rn(__fsub_rn(s_h[r + i][tx], s_h[r - i][tx]), a.ky[ry + i], acc);
     }
-    dst[(int64_t)(y0 + ty) * a.cols + x0 + tx] = acc;
+    dst[((int64_t)(y0 + ty) * a.cols + x0 + tx) * cn + ch] = acc;
   });
 }
 
@@ -701,11 +708,33 @@ int launch_to_gray(const Img &src, const void *const *src_ptrs, float *dst, floa
 
 int launch_sepfilter(const SepFilterArgs &a, cudaStream_t s) {
   SSK_REQUIRE((a.kxn & 1) && (a.kyn & 1) && a.kxn <= kMaxTaps && a.kyn <= kMaxTaps, "sepFilter2D: odd kernels up to 31 taps");
-  dim3 grid(div_up(a.cols, SF_W), div_up(a.rows, SF_H), a.batch);
-  if (a.kxn == 7 && a.kyn == 7) k_sepfilter<7, 7><<<grid, 256, 0, s>>>(a);          // Gaussian, sigma = 1
+  const int cn = a.cn < 1 ? 1 : a.cn;
+  SSK_REQUIRE(a.border == 0 || a.border == SSK_BORDER_REPLICATE || a.border == SSK_BORDER_REFLECT || a.border == SSK_BORDER_REFLECT101,
+              "sepFilter2D: BORDER_REPLICATE, BORDER_REFLECT or BORDER_REFLECT101");
+  dim3 grid(div_up(a.cols, SF_W), div_up(a.rows, SF_H), a.batch * cn);
+  if (cn > 1 || (a.border && a.border != SSK_BORDER_REPLICATE)) k_sepfilter<0, 0><<<grid, 256, 0, s>>>(a);
+  else if (a.kxn == 7 && a.kyn == 7) k_sepfilter<7, 7><<<grid, 256, 0, s>>>(a);     // Gaussian, sigma = 1
   else if (a.kxn == 5 && a.kyn == 3) k_sepfilter<5, 3><<<grid, 256, 0, s>>>(a);     // ecc_differentiate, d/dx
   else if (a.kxn == 3 && a.kyn == 5) k_sepfilter<3, 5><<<grid, 256, 0, s>>>(a);     // ecc_differentiate, d/dy
   else k_sepfilter<0, 0><<<grid, 256, 0, s>>>(a);
+  SSK_LAUNCH_CHECK();
+  return SSK_OK;
+}
+
+__global__ void __launch_bounds__(256) k_add_weighted(const float *__restrict__ src, double alpha, const float *__restrict__ lpass,
+                                                      double beta, float *__restrict__ dst, int64_t n, int clamp, float outmin,
+                                                      float outmax) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    float v = __double2float_rn(__fma_rn((double)__ldg(src + i), alpha, __dmul_rn((double)__ldg(lpass + i), beta)));
+    if (clamp) v = fmaxf(fminf(v, outmax), outmin);
+    dst[i] = v;
+  }
+}
+
+int launch_add_weighted(const float *src, double alpha, const float *lpass, double beta, float *dst, int64_t n, int clamp,
+                        float outmin, float outmax, cudaStream_t s) {
+  const int64_t blocks = (n + 255) / 256;
+  k_add_weighted<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, s>>>(src, alpha, lpass, beta, dst, n, clamp, outmin, outmax);
   SSK_LAUNCH_CHECK();
   return SSK_OK;
 }

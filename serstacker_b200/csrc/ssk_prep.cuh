@@ -51,6 +51,8 @@ struct SepFilterArgs {
   int rows, cols, batch;
   int kxn, kyn;                  // odd tap counts
   float kx[kMaxTaps], ky[kMaxTaps];
+  int border;                    // 0 / SSK_BORDER_REPLICATE (default), SSK_BORDER_REFLECT, SSK_BORDER_REFLECT101
+  int cn;                        // interleaved channels filtered independently (0 or 1: single channel)
 };
 int launch_sepfilter(const SepFilterArgs &a, cudaStream_t s);
 
@@ -95,6 +97,11 @@ int launch_apply_refmask(const uint8_t *mask, int n, float *gx, float *gy, int *
 // erode 5x5 / 8U helpers for user masks
 int launch_erode5_u8(const uint8_t *src, int64_t sstep, uint8_t *dst, int64_t dstep, int rows, int cols,
                      int border_replicate, cudaStream_t s);
+
+// unsharp_mask's combine step (unsharp_mask.cc:106): dst = src * alpha + lpass * beta as cv::addWeighted computes it for
+// CV_32F (fp64 fma(src, alpha, lpass * beta) rounded to fp32), then the optional cv::min / cv::max clamp.  n = all samples.
+int launch_add_weighted(const float *src, double alpha, const float *lpass, double beta, float *dst, int64_t n, int clamp,
+                        float outmin, float outmax, cudaStream_t s);
 
 // average_pyramid_inpaint (core/proc/inpaint/average_pyramid_inpaint.cc:97-127; ssk_inpaint.cu).  src: CV_32F with `cn`
 // interleaved channels, mask: CV_8UC1 (both on the device, any step); dst / dstmask dense; `work` holds
