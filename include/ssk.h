@@ -270,7 +270,8 @@ SSK_API int ssk_gaussian_blur(const ssk_mat *src, double sigma_x, double sigma_y
 /* ---------------------------------------------------------------------------------------------
  * unsharp_mask(src, dst, sigma, alpha, outmin, outmax) (core/proc/unsharp_mask.cc:72-118): the sharpening applied to the
  * master / reference frame before registration (c_image_stacking_pipeline.cc:1302-1306; defaults sigma 1, alpha 0.8).
- * CV_32F, 1 to 4 channels.  sigma <= 2 (create_lpass_image's exact branch); outmax <= outmin: no clamp.
+ * CV_32F; 1 to 4 channels for sigma <= 2 (create_lpass_image's exact branch), single-channel for its pyramid
+ * approximation (sigma > 2).  outmax <= outmin: no clamp.
  * ------------------------------------------------------------------------------------------- */
 SSK_API int ssk_unsharp_mask(const ssk_mat *src, ssk_mat *dst, double sigma, double alpha, double outmin, double outmax);
 

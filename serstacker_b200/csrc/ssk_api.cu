@@ -830,8 +830,8 @@ int ssk_ellipsoid_zrotation_remap(int rows, int cols, const double center[2], co
 
 // unsharp_mask(src, dst, sigma, alpha, outmin, outmax) (core/proc/unsharp_mask.cc:72-118) on CV_32F images: the sharpening of
 // the master / reference frame (c_image_stacking_pipeline.cc:1302-1306).  create_lpass_image's single-pass branch
-// (unsharp_mask.cc:44-47: sigma <= 2, or an image too small for a pyramid level) runs on the device; its pyrDown / pyrUp
-// approximation for larger sigma is rejected.
+// (unsharp_mask.cc:44-47: sigma <= 2, or an image too small for a pyramid level) handles 1 to 4 channels; its pyrDown /
+// pyrUp approximation for larger sigma (unsharp_mask.cc:50-68) single-channel images.
 int ssk_unsharp_mask(const ssk_mat *src, ssk_mat *dst, double sigma, double alpha, double outmin, double outmax) {
   if (int e = ensure_device()) return e;
   if (int e = check_mat(src, "unsharp_mask src")) return e;
@@ -858,27 +858,60 @@ int ssk_unsharp_mask(const ssk_mat *src, ssk_mat *dst, double sigma, double alph
   if (sigma <= 0 || alpha <= 0) {           // unsharp_mask.cc:76-78: copy (the clamp below still applies)
     if (int e = launch_add_weighted(d_src, 1.0, d_src, 0.0, d_out, (int64_t)n, clamp, (float)outmin, (float)outmax, s)) return e;
   } else {
-    int level = 0;                          // unsharp_mask.cc:25-42
+    int level = 0, Ci = 0;                  // unsharp_mask.cc:25-42
     if (sigma > 2) {
-      int m = im.rows < im.cols ? im.rows : im.cols, imax = 0, Ci = 0;
+      int m = im.rows < im.cols ? im.rows : im.cols, imax = 0;
       while (m >>= 1) ++imax;
       const int Cc = (int)(sigma * sigma / 2);
       while (level < imax && (1 + 4 * Ci) <= Cc) { Ci = 1 + 4 * Ci; ++level; }
     }
-    SSK_REQUIRE(level < 1, "unsharp_mask: the pyramid approximation of create_lpass_image (sigma > 2) is not implemented");
-    SepFilterArgs f = {};
-    f.src = d_src; f.dst = d_lp; f.rows = im.rows; f.cols = im.cols; f.batch = 1; f.cn = cn; f.border = SSK_BORDER_REFLECT;
-    // cv::getGaussianKernel(2 * max(1, (int)(sigma * 5)) + 1, sigma, CV_32F)
-    const int taps = 2 * ((int)(sigma * 5) > 1 ? (int)(sigma * 5) : 1) + 1;
-    SSK_REQUIRE(taps <= kMaxTaps, "unsharp_mask: kernel too large");
-    {
+    auto gaussian = [&](const float *from, float *to, int rows, int cols, int ch, double sg) -> int {
+      // gaussian_blur of unsharp_mask.cc:19-23: getGaussianKernel(2 * max(1, (int)(5 sigma)) + 1, sigma, CV_32F), BORDER_REFLECT
+      SepFilterArgs f = {};
+      f.src = from; f.dst = to; f.rows = rows; f.cols = cols; f.batch = 1; f.cn = ch; f.border = SSK_BORDER_REFLECT;
+      const int taps = 2 * ((int)(sg * 5) > 1 ? (int)(sg * 5) : 1) + 1;
+      SSK_REQUIRE(taps <= kMaxTaps, "unsharp_mask: Gaussian kernel too large");
       double cf[kMaxTaps], sum = 0;
-      const double s2 = -0.5 / (sigma * sigma);
+      const double s2 = -0.5 / (sg * sg);
       for (int i = 0; i < taps; ++i) { const double x = i - (taps - 1) * 0.5; cf[i] = std::exp(s2 * x * x); sum += cf[i]; }
       for (int i = 0; i < taps; ++i) f.kx[i] = f.ky[i] = (float)(cf[i] / sum);
+      f.kxn = f.kyn = taps;
+      return launch_sepfilter(f, s);
+    };
+    if (level < 1) {
+      if (int e = gaussian(d_src, d_lp, im.rows, im.cols, cn, sigma)) return e;
+    } else {
+      // unsharp_mask.cc:50-68: pyrDown chain (BORDER_REFLECT), residual blur, pyrUp chain back through the size history
+      SSK_REQUIRE(cn == 1, "unsharp_mask: the pyramid approximation (sigma > 2) is implemented for single-channel images");
+      SSK_REQUIRE(level < 30, "unsharp_mask: too many pyramid levels");
+      int lr[32], lc[32];
+      lr[0] = im.rows; lc[0] = im.cols;
+      for (int j = 1; j <= level; ++j) { lr[j] = (lr[j - 1] + 1) / 2; lc[j] = (lc[j - 1] + 1) / 2; }
+      if (int e = sc.d.ensure(n * 4 * 2)) return e;
+      float *pp[2] = {sc.d.as<float>(), sc.d.as<float>() + n};
+      const float *cur = d_src;
+      int w = 0;
+      for (int j = 1; j <= level; ++j) {
+        PyrDownArgs pd = {};
+        pd.src.data = cur; pd.src.step = (int64_t)lc[j - 1] * 4; pd.src.rows = lr[j - 1]; pd.src.cols = lc[j - 1];
+        pd.src.depth = SSK_32F; pd.src.cn = 1; pd.src.scale = 1.f;
+        pd.dst = pp[w]; pd.dst_rows = lr[j]; pd.dst_cols = lc[j]; pd.batch = 1; pd.post_scale = 1.f; pd.border = SSK_BORDER_REFLECT;
+        if (int e = launch_pyrdown(pd, s)) return e;
+        cur = pp[w]; w ^= 1;
+      }
+      const double delta = std::sqrt(sigma * sigma - 2 * Ci) / (double)(1 << level);
+      if (delta > 0) {
+        if (int e = gaussian(cur, pp[w], lr[level], lc[level], 1, delta)) return e;
+        cur = pp[w]; w ^= 1;
+      }
+      for (int j = level - 1; j >= 0; --j) {
+        PyrUpArgs pu = {};
+        pu.src = cur; pu.rows = lr[j + 1]; pu.cols = lc[j + 1];
+        pu.dst = j == 0 ? d_lp : pp[w]; pu.dst_rows = lr[j]; pu.dst_cols = lc[j]; pu.batch = 1;
+        if (int e = launch_pyrup(pu, s)) return e;
+        cur = pu.dst; w ^= 1;
+      }
     }
-    f.kxn = f.kyn = taps;
-    if (int e = launch_sepfilter(f, s)) return e;
     if (int e = launch_add_weighted(d_src, 1.0 / (1.0 - alpha), d_lp, -alpha / (1.0 - alpha), d_out, (int64_t)n, clamp,
                                     (float)outmin, (float)outmax, s)) return e;
   }

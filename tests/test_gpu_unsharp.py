@@ -40,4 +40,27 @@ def test_unsharp_mask_clamp_copy_and_rejects(gpu):
     assert np.array_equal(api.unsharp_mask(src, 0.0, 0.8), src)       # sigma <= 0 or alpha <= 0: copy
     assert np.array_equal(api.unsharp_mask(src, 1.0, 0.0), src)
     with pytest.raises(Exception):
-        api.unsharp_mask(src, 3.0, 0.5)                                  # pyramid approximation: rejected loudly
+        api.unsharp_mask(src, 1.0, 1.0)                                  # alpha must stay below 1
+
+
+@pytest.mark.parametrize("shape", [(64, 96), (97, 131), (270, 480), (1080, 1920)])
+@pytest.mark.parametrize("sigma,alpha", [(2.5, 0.5), (3.0, 0.8), (4.0, 0.6), (6.0, 0.5), (10.0, 0.5)])
+def test_unsharp_mask_pyramid_branch_matches_oracle(gpu, shape, sigma, alpha):
+    """create_lpass_image's approximation for sigma > 2 (unsharp_mask.cc:50-68): pyrDown chain with BORDER_REFLECT, residual
+    Gaussian, pyrUp chain through the size history."""
+    from serstacker_b200 import api
+    level, _ = ou.lpass_pyramid_level(shape[0], shape[1], sigma)
+    assert level >= 1
+    rng = np.random.default_rng(shape[1] + int(sigma * 10))
+    src = rng.random(shape, dtype=f32)
+    want = ou.unsharp_mask(src, sigma, alpha)
+    got = api.unsharp_mask(src, sigma, alpha)
+    beta = alpha / (1.0 - alpha)
+    tol = (2.0 + beta) * 2.4e-7 * max(1.0, float(np.abs(want).max()))
+    assert np.abs(got - want).max() <= tol
+
+
+def test_unsharp_mask_pyramid_branch_rejects_colour(gpu):
+    from serstacker_b200 import api
+    with pytest.raises(Exception):
+        api.unsharp_mask(np.zeros((64, 64, 3), f32), 3.0, 0.5)
