@@ -92,3 +92,21 @@ def run_stacking(frames, o: StackingOptions, reference=None, collect=None):
                                 rho=reg.status.rho, eps=reg.status.eps, iterations=reg.status.num_iterations))
     avg, mask = acc.compute()
     return avg, mask, acc, reg
+
+
+def run_stacking_pass(frames, o: StackingOptions, reference, unsharp_sigma=1.0, unsharp_alpha=0.8, inpaint_max_levels=100,
+                      collect=None):
+    """The stacking pass with the steps either side of the per-frame loop:
+      * the master / reference frame is sharpened by unsharp_mask(sigma, alpha) when both are positive
+        (c_image_stacking_pipeline.cc:1302-1306, defaults c_image_stacking_pipeline.h:169-170),
+      * the accumulator read-out is finished by average_pyramid_inpaint(avg, mask, avg, mask, 100)
+        (c_image_stacking_pipeline.cc:742-767).
+    Returns (avg, mask, sharpened_reference)."""
+    from .unsharp import unsharp_mask
+    from .inpaint import average_pyramid_inpaint
+    ref = np.ascontiguousarray(reference, dtype=f32)
+    if unsharp_sigma > 0 and unsharp_alpha > 0:
+        ref = unsharp_mask(ref, unsharp_sigma, unsharp_alpha)
+    avg, mask, _, _ = run_stacking(frames, o, reference=ref, collect=collect)
+    avg, mask = average_pyramid_inpaint(avg, mask, inpaint_max_levels)
+    return avg, mask, ref

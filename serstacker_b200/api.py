@@ -411,6 +411,24 @@ class c_image_stacking_pipeline:
         return [dict(ok=bool(st[i].ok), params=ts[i].parameters(), rho=st[i].rho, eps=st[i].eps,
                      iterations=st[i].num_iterations) for i in range(n)]
 
+    def run_stacking_pass(self, frames, reference, bpp=0, unsharp_sigma=1.0, unsharp_alpha=0.8, inpaint_max_levels=100):
+        """One stacking pass with the steps either side of the per-frame loop, as run_pipeline does them:
+        unsharp_mask of the master / reference frame (c_image_stacking_pipeline.cc:1302-1306), set_reference, the
+        batched per-frame loop, compute() + average_pyramid_inpaint (c_image_stacking_pipeline.cc:742-767).
+        `reference` is CV_32F (a master frame is always float); returns (avg, mask, per-frame results)."""
+        ref_img = np.ascontiguousarray(reference, dtype=f32)
+        if unsharp_sigma > 0 and unsharp_alpha > 0:
+            ref_img = unsharp_mask(ref_img, unsharp_sigma, unsharp_alpha)
+        self.set_reference(ref_img, bpp=0)
+        self._bpp = bpp
+        res = []
+        mb = max(1, int(self.options.max_batch))
+        frames = list(frames)
+        for i in range(0, len(frames), mb):
+            res += self.add_frames(frames[i:i + mb])
+        avg, mask = self.compute(inpaint_max_levels=inpaint_max_levels)
+        return avg, mask, res
+
     def submit(self, frames):
         """Streaming form: enqueue up to max_batch frames, return a ticket at once (ssk_stack_submit)."""
         arr, keep = self._mats(frames)

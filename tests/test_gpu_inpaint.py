@@ -125,3 +125,31 @@ def test_accumulator_compute_inpainted_matches_oracle(gpu, cn):
     got, gmask = g.compute_inpainted(1.0, 100)
     assert np.array_equal(gmask, wmask)
     assert np.array_equal(got, want)
+
+
+def test_stacking_pass_with_sharpened_reference_and_inpaint_matches_oracle(gpu):
+    """Both neighbours of the per-frame loop in one run: unsharp_mask of the master frame (sigma 1, alpha 0.8:
+    c_image_stacking_pipeline.cc:1302-1306), registration + weighted stacking, average_pyramid_inpaint of the result."""
+    from serstacker_b200 import api
+    from oracle import ecc as oecc
+    from helpers import rel_l2
+    import cv2
+    frames, _, bpp = synth.make_planet_sequence(320, 240, 7, seed=9, radius=70, sigma_t=5.0, dtype="f32")
+    master = np.mean(np.stack(frames[:3]), axis=0).astype(f32)       # any float master frame
+    so = opl.StackingOptions(accumulation_method=opl.ACC_WEIGHTED_AVERAGE)
+    so.registration.motion_type = otf.IMAGE_MOTION_AFFINE
+    so.registration.interpolation = cv2.INTER_CUBIC
+    so.registration.ecc.ecc_method = oecc.ECC_ALIGN_INVERSE_COMPOSITIONAL_LM
+    so.registration.ecc.ecch_max_level = -1
+    rec = []
+    avg_o, mask_o, ref_o = opl.run_stacking_pass(frames[3:], so, master, 1.0, 0.8, 100, collect=rec)
+
+    ro = api.registration_options(motion_type=3, interpolation=2, ecc=dict(ecc_method=3, ecch_max_level=-1))
+    p = api.c_image_stacking_pipeline(api.stack_options(registration=ro, accumulation_method=1, max_batch=4))
+    avg_g, mask_g, res = p.run_stacking_pass(frames[3:], master, bpp=bpp, unsharp_sigma=1.0, unsharp_alpha=0.8)
+    assert p.accumulated_frames() == sum(r["ok"] for r in rec)
+    for rg, r in zip(res, rec):
+        assert rg["ok"] == r["ok"]
+        assert np.abs(rg["params"] - r["params"]).max() <= 1e-3
+    assert np.array_equal(mask_g, mask_o)
+    assert rel_l2(avg_g, avg_o, mask_o > 0) <= 1e-4
