@@ -316,6 +316,32 @@ inline bool lpg(const image_t &image, image_t &map, double k = 2.0, double p = 2
   return ssk_lpg(&s, k, p, dscale, uscale, &m) == SSK_OK;
 }
 
+// unsharp_mask (core/proc/unsharp_mask.cc:72-118): sharpening of the master / reference frame
+// (c_image_stacking_pipeline.cc:1302-1306).  CV_32F; outmax <= outmin: no clamp.
+inline bool unsharp_mask(const image_t &src, image_t &dst, double sigma, double alpha, double outmin = -1, double outmax = -1) {
+  ssk_mat s = detail::view(src);
+  image_t out;
+  create_like(out, s.rows, s.cols, s.type);
+  ssk_mat d = detail::view(out);
+  const bool ok = ssk_unsharp_mask(&s, &d, sigma, alpha, outmin, outmax) == SSK_OK;
+  if (ok) dst = out;      // src and dst may be the same image, as at the reference's call site
+  return ok;
+}
+
+// average_pyramid_inpaint (core/proc/inpaint/average_pyramid_inpaint.cc:97-127; call site
+// c_image_stacking_pipeline.cc:763-767 with max_levels = 100).  src CV_32F, mask CV_8UC1.
+inline bool average_pyramid_inpaint(const image_t &src, const image_t &mask, image_t &dst, image_t *dstmask = nullptr,
+                                    int max_levels = 100) {
+  ssk_mat s = detail::view(src), m = detail::view(mask);
+  image_t out, outmask;
+  create_like(out, s.rows, s.cols, s.type);
+  ssk_mat d = detail::view(out), dm;
+  if (dstmask) { create_like(outmask, s.rows, s.cols, SSK_8UC1); dm = detail::view(outmask); }
+  const bool ok = ssk_average_pyramid_inpaint(&s, &m, &d, dstmask ? &dm : nullptr, max_levels) == SSK_OK;
+  if (ok) { dst = out; if (dstmask) *dstmask = outmask; }
+  return ok;
+}
+
 // compute_ellipsoid_zrotation_remap (core/proc/feature2d/ellipsoid.cc:206-277).  R1 / R2: row-major 3x3 doubles;
 // ebox_angle_deg / crop_box {x, y, w, h}: ellipsoid_bbox(center, A, B, C, R2).angle and ellipse_crop_box(ebox, size).
 inline bool compute_ellipsoid_zrotation_remap(int rows, int cols, const double center[2], const double axes[3],

@@ -64,5 +64,19 @@ int main(int argc, char **argv) {
     for (int x = 8; x < W - 8; ++x)
       if (amask.ptr<uint8_t>(y)[x]) { err = std::fmax(err, std::fabs(avg.ptr<float>(y)[x] - ref.ptr<float>(y)[x])); ++cnt; }
   std::printf("adapter_smoke: worst |shift error| = %.4f px, stack max |avg - ref| = %.4g over %d px\n", worst, err, cnt);
+  // the steps either side of the loop: the inpainted read-out keeps every valid pixel and fills the mask; a sharpened
+  // copy of the reference keeps its size and type
+  ssk::Mat filled, fmask, sharp;
+  if (!acc.compute_inpainted(filled, &fmask)) { std::fprintf(stderr, "compute_inpainted: %s\n", ssk_last_error()); return 8; }
+  int holes = 0, kept_bad = 0, unfilled = 0;
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      if (!amask.ptr<uint8_t>(y)[x]) ++holes;
+      else if (filled.ptr<float>(y)[x] != avg.ptr<float>(y)[x]) ++kept_bad;
+      if (!fmask.ptr<uint8_t>(y)[x]) ++unfilled;
+    }
+  std::printf("adapter_smoke: inpaint filled %d holes, %d valid pixels changed, %d left empty\n", holes, kept_bad, unfilled);
+  if (kept_bad || unfilled) return 9;
+  if (!ssk::unsharp_mask(ref, sharp, 1.0, 0.8) || sharp.rows != H || sharp.cols != W) { std::fprintf(stderr, "unsharp_mask: %s\n", ssk_last_error()); return 10; }
   return (worst <= 0.1 && err <= 5e-3 && cnt > W * H / 2) ? 0 : 1;
 }
