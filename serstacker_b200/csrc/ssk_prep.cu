@@ -229,11 +229,17 @@ __global__ void __launch_bounds__(256) k_sepfilter(const SepFilterArgs a) {
     const float *p = &s_in[r][x + rx];
     float acc;
     if (kxn <= 5) {
-      // SymmRowSmallFilter: k0*x0 then fma over the (anti)symmetric pairs
+      // SymmRowSmallFilter (SymmRowSmallVec_32f): symmetric 3 taps fma(x0, k0, (x-1 + x1) * k1), 5 taps
+      // fma(x-2 + x2, k2, that) (found against cv2 4.13 with a general Gaussian, tests/test_unsharp_oracle.py; for the
+      // power-of-two smoothing kernel of ecc_differentiate every product is exact and the order is immaterial);
+      // antisymmetric: first pair product, then fma over the remaining pairs
       if (xsym) {
-        acc = __fmul_rn(a.kx[rx], p[0]);
-#pragma unroll
-        for (int i = 1; i <= rx; ++i) acc = __fmaf_rn(__fadd_rn(p[i], p[-i]), a.kx[rx + i], acc);
+        if (rx == 0) {
+          acc = __fmul_rn(a.kx[0], p[0]);
+        } else {
+          acc = __fmaf_rn(p[0], a.kx[rx], __fmul_rn(__fadd_rn(p[1], p[-1]), a.kx[rx + 1]));
+          if (rx == 2) acc = __fmaf_rn(__fadd_rn(p[2], p[-2]), a.kx[rx + 2], acc);
+        }
       } else {
         acc = rx >= 1 ? __fmul_rn(__fsub_rn(p[1], p[-1]), a.kx[rx + 1]) : 0.f;
 #pragma unroll

@@ -53,3 +53,30 @@ def test_unsharp_identity_cases_and_pyramid_levels():
     assert ou.lpass_pyramid_level(1080, 1920, 2.5) == (1, 1)
     assert ou.lpass_pyramid_level(1080, 1920, 4.0) == (2, 5)
     assert ou.unsharp_mask(src, 3.0, 0.5).shape == src.shape
+
+
+def test_small_symmetric_row_filter_model_matches_cv2():
+    """cv2's SymmRowSmallVec_32f for general symmetric kernels: 3 taps fma(x0, k0, (x-1 + x1) k1); 5 taps
+    fma(x-2 + x2, k2, fma(x0, k0, (x-1 + x1) k1)) - the form k_sepfilter uses for kernels up to 5 taps."""
+    rng = np.random.default_rng(0)
+    H, W = 64, 96
+    src = rng.random((H, W), dtype=f32)
+    one = np.array([[1.0]], dtype=f32)
+    D = np.float64
+
+    def fma(a, b, c):
+        return (a.astype(D) * D(b) + c.astype(D)).astype(f32)
+
+    for sigma in (0.3, 0.5):
+        k = 2 * max(1, int(sigma * 5)) + 1
+        G = cv2.getGaussianKernel(k, sigma, cv2.CV_32F)
+        g, r = G.reshape(-1), k // 2
+        want = cv2.sepFilter2D(src, -1, G, one, borderType=cv2.BORDER_REFLECT)
+        P = np.pad(src, ((0, 0), (r, r)), mode="symmetric")
+        x0 = P[:, r:r + W]
+        a1 = (P[:, r - 1:r - 1 + W] + P[:, r + 1:r + 1 + W]).astype(f32)
+        acc = fma(x0, g[r], (a1 * g[r + 1]).astype(f32))
+        if r == 2:
+            a2 = (P[:, 0:W] + P[:, 4:4 + W]).astype(f32)
+            acc = fma(a2, g[4], acc)
+        assert np.array_equal(acc, want), sigma
