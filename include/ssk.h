@@ -268,6 +268,13 @@ SSK_API int ssk_lpg(const ssk_mat *image, double k, double p, int dscale, int us
 SSK_API int ssk_gaussian_blur(const ssk_mat *src, double sigma_x, double sigma_y, ssk_mat *dst);
 
 /* ---------------------------------------------------------------------------------------------
+ * Input side: debayer_nn2(src, dst, colorid) (core/io/debayer.cc:827-1195), the bilinear demosaic of raw Bayer frames in
+ * read_input_frame (c_image_stacking_pipeline_base.cc:125-279).  src: CV_8UC1 / CV_16UC1 / CV_32FC1 with even size;
+ * dst: 3 channels (BGR) of the same depth; colorid: SSK_COLORID_BAYER_{RGGB,GRBG,GBRG,BGGR}.
+ * ------------------------------------------------------------------------------------------- */
+SSK_API int ssk_debayer_nn2(const ssk_mat *src, ssk_mat *dst, int colorid);
+
+/* ---------------------------------------------------------------------------------------------
  * unsharp_mask(src, dst, sigma, alpha, outmin, outmax) (core/proc/unsharp_mask.cc:72-118): the sharpening applied to the
  * master / reference frame before registration (c_image_stacking_pipeline.cc:1302-1306; defaults sigma 1, alpha 0.8).
  * CV_32F; 1 to 4 channels for sigma <= 2 (create_lpass_image's exact branch), single-channel for its pyramid

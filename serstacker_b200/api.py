@@ -298,6 +298,14 @@ def lpg(image, k=2.0, p=2.0, dscale=2, uscale=6):
     return out
 
 
+def debayer_nn2(raw, colorid):
+    """debayer_nn2 (core/io/debayer.cc:827-1195): raw Bayer HxW (uint8 / uint16 / float32) -> HxWx3 BGR of the same dtype."""
+    raw = np.ascontiguousarray(raw)
+    dst = np.empty(raw.shape + (3,), dtype=raw.dtype)
+    check(capi.lib.ssk_debayer_nn2(C.byref(mat(raw)), C.byref(mat(dst)), int(colorid)))
+    return dst
+
+
 def unsharp_mask(src, sigma, alpha, outmin=-1.0, outmax=-1.0):
     """unsharp_mask (core/proc/unsharp_mask.cc:72-118) on CV_32F images; c_image_stacking_pipeline.cc:1302-1306."""
     src = np.ascontiguousarray(src, dtype=f32)
@@ -419,8 +427,7 @@ class c_image_stacking_pipeline:
         ref_img = np.ascontiguousarray(reference, dtype=f32)
         if unsharp_sigma > 0 and unsharp_alpha > 0:
             ref_img = unsharp_mask(ref_img, unsharp_sigma, unsharp_alpha)
-        self.set_reference(ref_img, bpp=0)
-        self._bpp = bpp
+        self.set_reference(ref_img, bpp=bpp)      # a float reference is never rescaled; bpp applies to integer frames
         res = []
         mb = max(1, int(self.options.max_batch))
         frames = list(frames)

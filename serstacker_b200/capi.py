@@ -125,6 +125,7 @@ _sigs = {
     "ssk_local_variance_map": (C.c_int, [_P(ssk_mat), C.c_int, C.c_int, C.c_int, C.c_int, _P(ssk_mat), _P(C.c_double)]),
     "ssk_lpg": (C.c_int, [_P(ssk_mat), C.c_double, C.c_double, C.c_int, C.c_int, _P(ssk_mat)]),
     "ssk_gaussian_blur": (C.c_int, [_P(ssk_mat), C.c_double, C.c_double, _P(ssk_mat)]),
+    "ssk_debayer_nn2": (C.c_int, [_P(ssk_mat), _P(ssk_mat), C.c_int]),
     "ssk_unsharp_mask": (C.c_int, [_P(ssk_mat), _P(ssk_mat), C.c_double, C.c_double, C.c_double, C.c_double]),
     "ssk_average_pyramid_inpaint": (C.c_int, [_P(ssk_mat), _P(ssk_mat), _P(ssk_mat), _P(ssk_mat), C.c_int]),
     "ssk_acc_compute_inpainted": (C.c_int, [C.c_void_p, _P(ssk_mat), _P(ssk_mat), C.c_double, C.c_int]),

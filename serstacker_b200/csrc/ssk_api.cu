@@ -828,6 +828,33 @@ int ssk_ellipsoid_zrotation_remap(int rows, int cols, const double center[2], co
   return SSK_OK;
 }
 
+// debayer_nn2(src, dst, colorid) (core/io/debayer.cc:827-1195): raw Bayer frame -> BGR of the same depth
+int ssk_debayer_nn2(const ssk_mat *src, ssk_mat *dst, int colorid) {
+  if (int e = ensure_device()) return e;
+  if (int e = check_mat(src, "debayer_nn2 src")) return e;
+  if (int e = check_mat(dst, "debayer_nn2 dst")) return e;
+  const int d = type_depth(src->type);
+  SSK_REQUIRE(type_cn(src->type) == 1, "debayer_nn2: the Bayer image must have one channel");
+  SSK_REQUIRE(type_depth(dst->type) == d && type_cn(dst->type) == 3 && dst->rows == src->rows && dst->cols == src->cols,
+              "debayer_nn2: the destination must have 3 channels of the source depth and the source size");
+  Scratch &sc = scratch();
+  if (int e = sc.init()) return e;
+  cudaStream_t s = sc.stream;
+  Img im;
+  if (int e = to_device(src, sc.a, s, &im, 0)) return e;
+  const size_t rowb = (size_t)im.cols * 3 * depth_bytes(d);
+  void *d_out = dst->data;
+  int64_t ostep = dst->step;
+  if (dst->mem != SSK_MEM_DEVICE) {
+    if (int e = sc.b.ensure(rowb * im.rows)) return e;
+    d_out = sc.b.p; ostep = (int64_t)rowb;
+  }
+  if (int e = launch_debayer_nn2(im.data, im.step, d, im.rows, im.cols, colorid, d_out, ostep, s)) return e;
+  if (dst->mem != SSK_MEM_DEVICE) if (int e = from_device(d_out, rowb, im.rows, dst, s)) return e;
+  SSK_CUDA(cudaStreamSynchronize(s));
+  return SSK_OK;
+}
+
 // unsharp_mask(src, dst, sigma, alpha, outmin, outmax) (core/proc/unsharp_mask.cc:72-118) on CV_32F images: the sharpening of
 // the master / reference frame (c_image_stacking_pipeline.cc:1302-1306).  create_lpass_image's single-pass branch
 // (unsharp_mask.cc:44-47: sigma <= 2, or an image too small for a pyramid level) handles 1 to 4 channels; its pyrDown /

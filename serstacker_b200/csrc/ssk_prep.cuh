@@ -103,6 +103,11 @@ int launch_erode5_u8(const uint8_t *src, int64_t sstep, uint8_t *dst, int64_t ds
 int launch_add_weighted(const float *src, double alpha, const float *lpass, double beta, float *dst, int64_t n, int clamp,
                         float outmin, float outmax, cudaStream_t s);
 
+// debayer_nn2 (core/io/debayer.cc:827-1195; ssk_debayer.cu): raw Bayer CV_8U / CV_16U / CV_32F single channel -> BGR of the
+// same depth; both images on the device.
+int launch_debayer_nn2(const void *src, int64_t sstep, int depth, int rows, int cols, int colorid, void *dst, int64_t dstep,
+                       cudaStream_t s);
+
 // average_pyramid_inpaint (core/proc/inpaint/average_pyramid_inpaint.cc:97-127; ssk_inpaint.cu).  src: CV_32F with `cn`
 // interleaved channels, mask: CV_8UC1 (both on the device, any step); dst / dstmask dense; `work` holds
 // inpaint_work_bytes() bytes.  *was_full = 1 when the mask had no holes (outputs are copies of the inputs).
