@@ -316,6 +316,17 @@ inline bool lpg(const image_t &image, image_t &map, double k = 2.0, double p = 2
   return ssk_lpg(&s, k, p, dscale, uscale, &m) == SSK_OK;
 }
 
+// debayer_nn2 (core/io/debayer.cc:827-1195): raw Bayer frame -> BGR of the same depth; colorid = SSK_COLORID_BAYER_*
+inline bool debayer_nn2(const image_t &src, image_t &dst, int colorid) {
+  ssk_mat s = detail::view(src);
+  image_t out;
+  create_like(out, s.rows, s.cols, SSK_MAKETYPE(s.type & 7, 3));
+  ssk_mat d = detail::view(out);
+  const bool ok = ssk_debayer_nn2(&s, &d, colorid) == SSK_OK;
+  if (ok) dst = out;
+  return ok;
+}
+
 // unsharp_mask (core/proc/unsharp_mask.cc:72-118): sharpening of the master / reference frame
 // (c_image_stacking_pipeline.cc:1302-1306).  CV_32F; outmax <= outmin: no clamp.
 inline bool unsharp_mask(const image_t &src, image_t &dst, double sigma, double alpha, double outmin = -1, double outmax = -1) {
