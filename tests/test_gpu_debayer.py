@@ -38,3 +38,43 @@ def test_debayer_nn2_rejects_uneven_sizes_and_unknown_patterns(gpu):
         api.debayer_nn2(np.zeros((5, 6), np.uint16), 8)
     with pytest.raises(Exception):
         api.debayer_nn2(np.zeros((6, 6), np.uint16), 3)
+
+
+def test_config3_chain_debayer_register_bayer_average_matches_oracle(gpu):
+    """Config #3's per-frame chain with the demosaic on the device: raw RGGB16 -> debayer_nn2 -> gray ECC registration ->
+    remap validity mask -> Bayer accumulation of the raw samples through the frame's remap
+    (c_image_stacking_pipeline.cc:1358-1862 with accumulation_method = bayer_average)."""
+    from serstacker_b200 import api, synth
+    from oracle import pipeline as opl, transforms as otf, accumulation as oacc
+    from oracle.registration import FrameRegistration
+    frames, shifts, bpp = synth.make_bayer_sequence(192, 128, 5, seed=5)
+    so = opl.StackingOptions(accumulation_method=opl.ACC_BAYER_AVERAGE)
+    so.registration.motion_type = otf.IMAGE_MOTION_TRANSLATION
+    oreg = FrameRegistration(so.registration)
+    oreg.setup_reference_frame(opl.to_float_frame(od.debayer_nn2(frames[0], 8), bpp), None)
+    oa = oacc.BayerAverage()
+    oa.set_bayer_pattern(8)
+    oparams = []
+    for f in frames:
+        ok = opl.process_frame(oreg, oa, so, opl.to_float_frame(od.debayer_nn2(f, 8), bpp), None,
+                               raw_bayer=opl.to_float_frame(f, bpp))
+        assert ok
+        oparams.append(oreg.image_transform.clone_parameters())
+    avg_o, mask_o = oa.compute()
+
+    greg = api.c_frame_registration(api.registration_options(motion_type=0))
+    ga = api.c_bayer_average()
+    ga.set_bayer_pattern(8)
+    greg.setup_reference_frame(api.debayer_nn2(frames[0], 8), bpp=bpp)
+    for f, po in zip(frames, oparams):
+        assert greg.register_frame(api.debayer_nn2(f, 8), bpp=bpp)
+        assert np.abs(greg.image_transform_parameters() - po).max() <= 1e-3
+        rmap = greg.current_remap()
+        _, mask = greg.custom_remap(rmap, None, None, want_mask=True)
+        ga.set_remap(rmap=rmap)
+        ga.add(f, mask, bpp=bpp)
+    avg_g, mask_g = ga.compute()
+    assert ga.accumulated_frames() == len(frames)
+    assert np.mean(mask_g == mask_o) >= 0.999
+    m = (mask_g > 0) & (mask_o > 0)
+    assert np.abs(avg_g - avg_o)[m].max() <= 2e-4
