@@ -51,6 +51,75 @@ __global__ void __launch_bounds__(256) k_debayer_nn2(const T *__restrict__ src, 
   o[0] = b; o[1] = g; o[2] = r;
 }
 
+// N raw samples per thread (N = 4, or 16 bytes' worth): one vector load per source row (+ the two neighbours), three vector
+// stores of the 3N output samples.  Same arithmetic as k_debayer_nn2; needs cols % N == 0 and rows / pointers aligned to N
+// samples.
+template <class T, int N> struct alignas(N * sizeof(T)) Pack { T v[N]; };
+
+template <class T, int N>
+__global__ void __launch_bounds__(256) k_debayer_nn2_vec(const T *__restrict__ src, int64_t sstep, int rows, int cols, int ry, int rx,
+                                                        T *__restrict__ dst, int64_t dstep) {
+  typedef typename Wide<T>::type W;
+  const int x0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * N, y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x0 >= cols || y >= rows) return;
+  const int yr[3] = {y == 0 ? 1 : y - 1, y, y == rows - 1 ? rows - 2 : y + 1};
+  W w[3][N + 2];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const T *row = reinterpret_cast<const T *>(reinterpret_cast<const char *>(src) + (int64_t)yr[r] * sstep);
+    const Pack<T, N> p = *reinterpret_cast<const Pack<T, N> *>(row + x0);
+#pragma unroll
+    for (int i = 0; i < N; ++i) w[r][i + 1] = (W)p.v[i];
+    w[r][0] = x0 == 0 ? (W)p.v[1] : (W)__ldg(row + x0 - 1);                   // column -1 -> 1
+    w[r][N + 1] = x0 + N == cols ? (W)p.v[N - 2] : (W)__ldg(row + x0 + N);    // column W -> W - 2
+  }
+  Pack<T, N> o[3];
+  T *ov = &o[0].v[0];
+  const int py = y & 1;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int px = i & 1;                                                   // x0 is even
+    const bool is_r = py == ry && px == rx, is_b = py != ry && px != rx;
+    const W c = w[1][i + 1];
+    T r, g, b;
+    if (is_r || is_b) {
+      const T diag = avg4<T>(w[0][i], w[0][i + 2], w[2][i], w[2][i + 2]);
+      g = avg4<T>(w[0][i + 1], w[1][i], w[1][i + 2], w[2][i + 1]);
+      r = is_r ? (T)c : diag;
+      b = is_r ? diag : (T)c;
+    } else {
+      const T vert = avg2<T>(w[0][i + 1], w[2][i + 1]);
+      const T horz = avg2<T>(w[1][i], w[1][i + 2]);
+      g = (T)c;
+      const bool on_r_row = py == ry;
+      r = on_r_row ? horz : vert;
+      b = on_r_row ? vert : horz;
+    }
+    ov[3 * i] = b; ov[3 * i + 1] = g; ov[3 * i + 2] = r;
+  }
+  Pack<T, N> *out = reinterpret_cast<Pack<T, N> *>(reinterpret_cast<T *>(reinterpret_cast<char *>(dst) + (int64_t)y * dstep) + (int64_t)x0 * 3);
+  out[0] = o[0]; out[1] = o[1]; out[2] = o[2];
+}
+
+template <class T, int N>
+bool try_debayer_vec(const void *src, int64_t sstep, int rows, int cols, int ry, int rx, void *dst, int64_t dstep, cudaStream_t s) {
+  const size_t a = N * sizeof(T);
+  if (!(cols % N == 0 && reinterpret_cast<uintptr_t>(src) % a == 0 && reinterpret_cast<uintptr_t>(dst) % a == 0 &&
+        sstep % (int64_t)a == 0 && dstep % (int64_t)a == 0)) return false;
+  dim3 grid(div_up(cols / N, 32), div_up(rows, 8));
+  k_debayer_nn2_vec<T, N><<<grid, 256, 0, s>>>(static_cast<const T *>(src), sstep, rows, cols, ry, rx, static_cast<T *>(dst), dstep);
+  return true;
+}
+
+template <class T>
+void run_debayer(const void *src, int64_t sstep, int rows, int cols, int ry, int rx, void *dst, int64_t dstep, cudaStream_t s) {
+  constexpr int NW = 16 / (int)sizeof(T);        // 16-byte vectors
+  if (NW > 4 && try_debayer_vec<T, NW>(src, sstep, rows, cols, ry, rx, dst, dstep, s)) return;
+  if (try_debayer_vec<T, 4>(src, sstep, rows, cols, ry, rx, dst, dstep, s)) return;
+  dim3 grid(div_up(cols, 32), div_up(rows, 8));
+  k_debayer_nn2<T><<<grid, 256, 0, s>>>(static_cast<const T *>(src), sstep, rows, cols, ry, rx, static_cast<T *>(dst), dstep);
+}
+
 }  // namespace
 
 int launch_debayer_nn2(const void *src, int64_t sstep, int depth, int rows, int cols, int colorid, void *dst, int64_t dstep,
@@ -64,10 +133,9 @@ int launch_debayer_nn2(const void *src, int64_t sstep, int depth, int rows, int 
     case SSK_COLORID_BAYER_BGGR: ry = 1; rx = 1; break;
     default: set_error("debayer_nn2: unsupported colorid (RGGB, GRBG, GBRG, BGGR)"); return SSK_ERR_INVALID;
   }
-  dim3 grid(div_up(cols, 32), div_up(rows, 8));
-  if (depth == SSK_8U) k_debayer_nn2<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t *>(src), sstep, rows, cols, ry, rx, static_cast<uint8_t *>(dst), dstep);
-  else if (depth == SSK_16U) k_debayer_nn2<uint16_t><<<grid, 256, 0, s>>>(static_cast<const uint16_t *>(src), sstep, rows, cols, ry, rx, static_cast<uint16_t *>(dst), dstep);
-  else if (depth == SSK_32F) k_debayer_nn2<float><<<grid, 256, 0, s>>>(static_cast<const float *>(src), sstep, rows, cols, ry, rx, static_cast<float *>(dst), dstep);
+  if (depth == SSK_8U) run_debayer<uint8_t>(src, sstep, rows, cols, ry, rx, dst, dstep, s);
+  else if (depth == SSK_16U) run_debayer<uint16_t>(src, sstep, rows, cols, ry, rx, dst, dstep, s);
+  else if (depth == SSK_32F) run_debayer<float>(src, sstep, rows, cols, ry, rx, dst, dstep, s);
   else { set_error("debayer_nn2: CV_8U, CV_16U or CV_32F"); return SSK_ERR_INVALID; }
   SSK_LAUNCH_CHECK();
   return SSK_OK;

@@ -15,7 +15,7 @@ def _raw(rng, shape, dtype):
 
 @pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.float32])
 @pytest.mark.parametrize("colorid", [8, 9, 10, 11])
-@pytest.mark.parametrize("shape", [(2, 2), (2, 6), (6, 2), (10, 14), (250, 334), (480, 640)])
+@pytest.mark.parametrize("shape", [(2, 2), (2, 6), (6, 2), (10, 14), (250, 334), (480, 640), (2, 4), (6, 8), (252, 336), (4, 16), (6, 48)])
 def test_debayer_nn2_matches_oracle(gpu, dtype, colorid, shape):
     from serstacker_b200 import api
     rng = np.random.default_rng(shape[0] + colorid)
