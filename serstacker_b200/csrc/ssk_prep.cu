@@ -200,8 +200,10 @@ constexpr int SF_W = 64, SF_H = 16, SF_R = (kMaxTaps - 1) / 2;
 template <int KXN, int KYN>
 __global__ void __launch_bounds__(256) k_sepfilter(const SepFilterArgs a) {
   constexpr int RMAX = (KXN && KYN) ? ((KXN > KYN ? KXN : KYN) >> 1) : SF_R;
-  __shared__ float s_in[SF_H + 2 * RMAX][SF_W + 2 * RMAX + 1];
-  __shared__ float s_h[SF_H + 2 * RMAX][SF_W];
+  constexpr bool G7 = KXN == 7 && KYN == 7;                      // the per-frame Gaussian (sigma = 1): register-blocked passes
+  constexpr int PITCH = G7 ? SF_W + 2 * RMAX + 2 : SF_W + 2 * RMAX + 1;
+  __shared__ __align__(16) float s_in[SF_H + 2 * RMAX][PITCH];
+  __shared__ __align__(16) float s_h[SF_H + 2 * RMAX][SF_W];
   // interleaved channels and borders other than REPLICATE go through the generic instantiation only
   const int cn = (KXN || a.cn < 1) ? 1 : a.cn;
   const int b = blockIdx.z / cn, ch = blockIdx.z - b * cn;
@@ -224,6 +226,44 @@ __global__ void __launch_bounds__(256) k_sepfilter(const SepFilterArgs a) {
   __syncthreads();
   // row / column arithmetic follows OpenCV's filter engine (found bit-exact against cv2 4.13 for the kernels of this
   // path: 5-tap derivative, 3-tap smoothing, 7-tap Gaussian)
+  if constexpr (G7) {
+    if (a.ky[0] == a.ky[6]) {
+      // Same operations in the same order as the generic passes below, four outputs per thread: the row pass reads its
+      // 10-sample window with three 16-byte shared loads (instead of 28 scalar ones), the column pass keeps a 10-row
+      // window in registers (10 loads instead of 28).
+      for (int i = threadIdx.x; i < (SF_H + 6) * (SF_W / 4); i += 256) {
+        const int r = i / (SF_W / 4), cg = (i % (SF_W / 4)) * 4;
+        if (r >= ih) break;
+        const float4 v0 = *reinterpret_cast<const float4 *>(&s_in[r][cg]);
+        const float4 v1 = *reinterpret_cast<const float4 *>(&s_in[r][cg + 4]);
+        const float4 v2 = *reinterpret_cast<const float4 *>(&s_in[r][cg + 8]);
+        const float w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float acc = __fmul_rn(w[j], a.kx[0]);          // RowVec_32f: taps in order, fma chain
+#pragma unroll
+          for (int t = 1; t < 7; ++t) acc = __fmaf_rn(w[j + t], a.kx[t], acc);
+          o[j] = acc;
+        }
+        *reinterpret_cast<float4 *>(&s_h[r][cg]) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+      __syncthreads();
+      const int tx = threadIdx.x & (SF_W - 1), g4 = (threadIdx.x / SF_W) * 4;
+      float c[10];
+#pragma unroll
+      for (int q = 0; q < 10; ++q) c[q] = s_h[g4 + q][tx];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float acc = __fmul_rn(a.ky[3], c[j + 3]);        // SymmColumnVec_32f: centre tap, then fma over the pairs
+#pragma unroll
+        for (int t = 1; t <= 3; ++t) acc = __fmaf_rn(__fadd_rn(c[j + 3 + t], c[j + 3 - t]), a.ky[3 + t], acc);
+        const int ty = g4 + j;
+        if (ty < oh && tx < ow) dst[(int64_t)(y0 + ty) * a.cols + x0 + tx] = acc;
+      }
+      return;
+    }
+  }
   const bool xsym = a.kx[0] == a.kx[kxn - 1];
   for_tile(ih, ow, [&](int r, int x) {
     const float *p = &s_in[r][x + rx];
