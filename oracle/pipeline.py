@@ -94,6 +94,31 @@ def run_stacking(frames, o: StackingOptions, reference=None, collect=None):
     return avg, mask, acc, reg
 
 
+def run_bayer_stacking(raw_frames, bpp, o: StackingOptions, colorid, reference=None, collect=None):
+    """The bayer_average form of the loop on raw Bayer frames (config #3): read_input_frame keeps the raw samples as
+    _raw_bayer_image (CV_32F, 1/(1<<bpp)), demosaics the frame with debayer_nn2 at its own depth and converts the result
+    to CV_32F (c_image_stacking_pipeline_base.cc:221-236, 271-276); the registration sees the demosaiced frame, the
+    accumulator gathers the raw samples through current_remap under the remapped mask
+    (c_image_stacking_pipeline.cc:1644-1651, 1730-1752).  reference: raw Bayer frame (default raw_frames[0]).
+    Returns (avg HxWx3, mask, accumulator, registration)."""
+    from .debayer import debayer_nn2
+    assert o.accumulation_method == ACC_BAYER_AVERAGE
+    raw_frames = list(raw_frames)
+    reg = FrameRegistration(o.registration)
+    ref = raw_frames[0] if reference is None else reference
+    if o.enable_registration:
+        reg.setup_reference_frame(to_float_frame(debayer_nn2(ref, colorid), bpp), None)
+    acc = BayerAverage()
+    acc.set_bayer_pattern(colorid)
+    for f in raw_frames:
+        ok = process_frame(reg, acc, o, to_float_frame(debayer_nn2(f, colorid), bpp), None, raw_bayer=to_float_frame(f, bpp))
+        if collect is not None:
+            collect.append(dict(ok=ok, params=None if reg.image_transform is None else reg.image_transform.clone_parameters(),
+                                rho=reg.status.rho, eps=reg.status.eps, iterations=reg.status.num_iterations))
+    avg, mask = acc.compute()
+    return avg, mask, acc, reg
+
+
 def run_stacking_pass(frames, o: StackingOptions, reference, unsharp_sigma=1.0, unsharp_alpha=0.8, inpaint_max_levels=100,
                       collect=None):
     """The stacking pass with the steps either side of the per-frame loop:

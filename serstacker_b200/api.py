@@ -396,7 +396,8 @@ class c_image_stacking_pipeline:
         m = image if isinstance(image, ssk_mat) else mat(np.ascontiguousarray(image))
         mm = mask if (mask is None or isinstance(mask, ssk_mat)) else mat(np.ascontiguousarray(mask))
         check(capi.lib.ssk_stack_set_reference(self._h, C.byref(m), ref(mm), bpp))
-        self._shape = (m.rows, m.cols, (m.type >> 3) + 1)
+        bayer = self.options.accumulation_method == capi.STACK_BAYER_AVERAGE
+        self._shape = (m.rows, m.cols, 3 if bayer else (m.type >> 3) + 1)   # c_bayer_average computes a BGR image
         self._bpp = bpp
 
     def _mats(self, frames):
@@ -482,6 +483,8 @@ class c_image_stacking_pipeline:
         return avg, mask
 
     def accumulator(self):
+        if self.options.accumulation_method == capi.STACK_BAYER_AVERAGE:
+            return c_bayer_average(capi.lib.ssk_stack_accumulator(self._h))
         return c_weigthed_average(capi.lib.ssk_stack_accumulator(self._h))
 
     def stream(self):

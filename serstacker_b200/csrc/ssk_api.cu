@@ -437,7 +437,10 @@ int ssk_acc_add(ssk_acc *h, const ssk_mat *src, const ssk_mat *weights, int bpp)
     BayerAccArgs b = {};
     b.src = im; b.have_map = a.have_map ? 1 : 0;
     if (a.have_map) {
-      if (a.rmap_explicit) { b.rmap = a.rmap.as<float2>(); b.rmap_step = (int64_t)im.cols * 8; }
+      if (a.rmap_explicit) {
+        SSK_REQUIRE(a.rmap_rows == im.rows && a.rmap_cols == im.cols, "c_bayer_average: remap size differs from the frame size");
+        b.rmap = a.rmap.as<float2>(); b.rmap_step = (int64_t)im.cols * 8;
+      }
       else b.map = make_mapcoef(a.map_t);
     }
     b.weights = wim.data; b.w_step = wim.step; b.wtype = wtype; b.colorid = a.colorid;
@@ -585,6 +588,7 @@ int ssk_acc_set_remap(ssk_acc *h, const ssk_transform *t, const ssk_mat *rmap) {
                                rmap->mem == SSK_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, a.stream));
     SSK_CUDA(cudaStreamSynchronize(a.stream));
     a.rmap_explicit = true;
+    a.rmap_rows = rmap->rows; a.rmap_cols = rmap->cols;
   } else {
     a.map_t = *t;
     a.rmap_explicit = false;

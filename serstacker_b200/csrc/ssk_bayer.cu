@@ -1,0 +1,148 @@
+// K5b: the Bayer form of the fused per-frame loop.  For a batch of raw Bayer frames, one launch gathers, per pixel of
+// the accumulator and per frame, the four raw samples around the frame's remap position into the per-colour sums
+// and counters, under the eroded validity mask of the frame's remap.  acc / cntr are read and written once per batch.
+//
+// Reference semantics reproduced here:
+//   c_image_stacking_pipeline::process_input_sequence, bayer branch
+//        core/pipeline/c_image_stacking_pipeline/c_image_stacking_pipeline.cc:1644-1651 (custom_remap -> current_mask),
+//        :1730-1752 (set_bayer_pattern, set_remap(current_remap), add(_raw_bayer_image, current_mask))
+//   c_frame_registration::base_remap mask: erode5x5(remap(all-255, interp, CONSTANT 0) >= 255), border value 255
+//        core/proc/image_registration/c_frame_registration.cc:1315-1337
+//   _bayer_accumulate, rmap + CV_8UC1 mask branch   core/average/c_frame_accumulation.cc:1040-1075, 1097-1110
+//        src_x = (int)p[0]; ax = (src_x + 1 - p[0]) evaluated in float then widened; s = ax * ay * w in double;
+//        acc[c] += src * s and cntr[c] += s: float += double (sum formed in double, narrowed once), taps in the
+//        order 00, 01, 10, 11 (the two green taps of a 2x2 cell update the same channel one after the other).
+#include "ssk_warp.cuh"
+
+namespace ssk {
+namespace {
+
+constexpr int BTW = 32, BTH = 8;      // pixels per CTA (one pixel per thread)
+constexpr int BPLAN = 256;            // frames per launch (per-CTA table of tile flags)
+
+// pre-erosion flag of base_remap's mask at accumulator pixel (x, y)
+__device__ __forceinline__ bool flag_at(const MapCoef &m, int interp, int x, int y, int src_cols, int src_rows, const short *itab) {
+  float u, v;
+  map_xy(m, (float)x, (float)y, u, v);
+  return valid255(interp, u, v, src_cols, src_rows, itab);
+}
+
+// mask(x, y) of base_remap: 5x5 erosion (border value 255: positions outside the image do not erode)
+__device__ __noinline__ bool mask_at(const MapCoef &m, int interp, int x, int y, int cols, int rows, int src_cols, int src_rows,
+                                     const short *itab) {
+#pragma unroll 1
+  for (int dy = -2; dy <= 2; ++dy) {
+    const int yy = y + dy;
+    if ((unsigned)yy >= (unsigned)rows) continue;
+#pragma unroll 1
+    for (int dx = -2; dx <= 2; ++dx) {
+      const int xx = x + dx;
+      if ((unsigned)xx >= (unsigned)cols) continue;
+      if (!flag_at(m, interp, xx, yy, src_cols, src_rows, itab)) return false;
+    }
+  }
+  return true;
+}
+
+// 1: every pixel of the tile and of its 2-px erosion halo maps into the tap-safe interior of the frame (mask = 255 and
+// the four raw samples are in bounds); 0: decide per pixel.  Affine-like maps are monotone along both axes of the
+// tile, so the four corners bound the footprint; projective maps always take the per-pixel path.
+__device__ __noinline__ int tile_safe(const MapCoef &m, int bx0, int by0, const WarpAccArgs &a) {
+  if (m.type == MAP_HOMOGRAPHY) return 0;
+  const int cx0 = max(bx0 - 2, 0), cy0 = max(by0 - 2, 0);
+  const int cx1 = min(bx0 + BTW + 1, a.cols - 1), cy1 = min(by0 + BTH + 1, a.rows - 1);
+  float umin = 3.4e38f, umax = -3.4e38f, vmin = 3.4e38f, vmax = -3.4e38f;
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    float u, v;
+    map_xy(m, (float)((k & 1) ? cx1 : cx0), (float)((k & 2) ? cy1 : cy0), u, v);
+    umin = fminf(umin, u); umax = fmaxf(umax, u); vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+  }
+  return (umin >= 3.f && vmin >= 3.f && umax <= (float)(a.src_cols - 4) && vmax <= (float)(a.src_rows - 4)) ? 1 : 0;
+}
+
+// colour channel (B = 0, G = 1, R = 2; c_frame_accumulation.h:230-234) of the 2x2 cell position q = (y & 1) * 2 + (x & 1),
+// packed two bits per position (c_frame_accumulation.cc:1262-1334)
+__host__ __device__ inline unsigned pattern_code(int colorid) {
+  switch (colorid) {
+    case SSK_COLORID_BAYER_RGGB: return 2u | (1u << 2) | (1u << 4) | (0u << 6);
+    case SSK_COLORID_BAYER_GRBG: return 1u | (2u << 2) | (0u << 4) | (1u << 6);
+    case SSK_COLORID_BAYER_GBRG: return 1u | (0u << 2) | (2u << 4) | (1u << 6);
+    default: /* BGGR */          return 0u | (1u << 2) | (1u << 4) | (2u << 6);
+  }
+}
+
+template <int DEPTH>
+__global__ void __launch_bounds__(BTW * BTH) k_fused_bayer(const __grid_constant__ WarpAccArgs a, const __grid_constant__ Tables tab,
+                                                          const unsigned pcode) {
+  __shared__ signed char s_flag[BPLAN];
+  const int bx0 = blockIdx.x * BTW, by0 = blockIdx.y * BTH;
+  for (int jj = threadIdx.x; jj < a.njobs; jj += BTW * BTH)
+    s_flag[jj] = a.jobs[jj].ok ? (signed char)tile_safe(a.jobs[jj].map, bx0, by0, a) : (signed char)-1;
+  __syncthreads();
+  const int x = bx0 + (threadIdx.x & 31), y = by0 + (threadIdx.x >> 5);
+  if (x >= a.cols || y >= a.rows) return;
+  const int64_t p = ((int64_t)y * a.cols + x) * 3;
+  float A[3] = {a.acc[p], a.acc[p + 1], a.acc[p + 2]};
+  float N[3] = {a.wacc[p], a.wacc[p + 1], a.wacc[p + 2]};
+  // the pattern table only covers the even-sized part of the image; elsewhere it reads 0 (c_frame_accumulation.cc:1262-1334)
+  const int prow = a.src_rows & ~1, pcol = a.src_cols & ~1;
+  Img im;
+  im.data = nullptr; im.step = a.src_step; im.rows = a.src_rows; im.cols = a.src_cols; im.depth = DEPTH; im.cn = 1; im.scale = a.scale;
+#pragma unroll 1
+  for (int j = 0; j < a.njobs; ++j) {
+    const int flag = s_flag[j];
+    if (flag < 0) continue;                       // frame dropped by the registration
+    const MapCoef &m = a.jobs[j].map;
+    if (!flag && !mask_at(m, a.interp, x, y, a.cols, a.rows, a.src_cols, a.src_rows, tab.cubic_itab)) continue;
+    float u, v;
+    map_xy(m, (float)x, (float)y, u, v);
+    const int sx = (int)u, sy = (int)v;           // truncation toward zero, as the reference's (int) cast
+    if (!(sx >= 0 && sx < a.src_cols - 1 && sy >= 0 && sy < a.src_rows - 1)) continue;
+    const double ax = (double)((float)(sx + 1) - u), ay = (double)((float)(sy + 1) - v);
+    const double bx = (double)(u - (float)sx), by = (double)(v - (float)sy);
+    const double sw[4] = {ax * ay, bx * ay, ax * by, bx * by};
+    im.data = a.jobs[j].frame;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = sy + (k >> 1), xx = sx + (k & 1);
+      const int q = ((yy & 1) << 1) | (xx & 1);
+      const int cc = (yy < prow && xx < pcol) ? (int)((pcode >> (2 * q)) & 3u) : 0;
+      const double s = (double)load_px<DEPTH>(im, yy, xx, 0);
+      const double an = (double)(cc == 0 ? A[0] : cc == 1 ? A[1] : A[2]) + s * sw[k];
+      const double nn = (double)(cc == 0 ? N[0] : cc == 1 ? N[1] : N[2]) + sw[k];
+      const float af = (float)an, nf = (float)nn;
+      if (cc == 0) { A[0] = af; N[0] = nf; } else if (cc == 1) { A[1] = af; N[1] = nf; } else { A[2] = af; N[2] = nf; }
+    }
+  }
+  a.acc[p] = A[0]; a.acc[p + 1] = A[1]; a.acc[p + 2] = A[2];
+  a.wacc[p] = N[0]; a.wacc[p + 1] = N[1]; a.wacc[p + 2] = N[2];
+}
+
+}  // namespace
+
+// a.acc / a.wacc: rows x cols x 3 sums and counters (c_bayer_average::_accumulator / _counter); a.jobs[j].frame: raw Bayer
+// frames (one channel).  a.interp selects the interpolation of the validity mask (registration_options.interpolation).
+int launch_bayer_warp_accumulate(const WarpAccArgs &a_in, const Tables &tab, int colorid, cudaStream_t s) {
+  WarpAccArgs a = a_in;
+  SSK_REQUIRE(a.interp == SSK_INTER_NEAREST || a.interp == SSK_INTER_LINEAR || a.interp == SSK_INTER_CUBIC,
+              "bayer_warp_accumulate: interpolation must be NEAREST, LINEAR or CUBIC");
+  SSK_REQUIRE(a.cn == 1, "bayer_warp_accumulate: raw Bayer frames have one channel");
+  SSK_REQUIRE(a.rows == a.src_rows && a.cols == a.src_cols, "bayer_warp_accumulate: accumulator and frame sizes differ");
+  SSK_REQUIRE(colorid >= SSK_COLORID_BAYER_RGGB && colorid <= SSK_COLORID_BAYER_BGGR, "bayer_warp_accumulate: RGGB/GRBG/GBRG/BGGR");
+  const unsigned pcode = pattern_code(colorid);
+  const dim3 grid(div_up(a.cols, BTW), div_up(a.rows, BTH));
+  const FrameJob *jobs = a.jobs;
+  const int njobs = a.njobs;
+  for (int j0 = 0; j0 < njobs; j0 += BPLAN) {
+    a.jobs = jobs + j0; a.njobs = std::min(BPLAN, njobs - j0);
+    if (a.depth == SSK_32F) k_fused_bayer<SSK_32F><<<grid, BTW * BTH, 0, s>>>(a, tab, pcode);
+    else if (a.depth == SSK_16U) k_fused_bayer<SSK_16U><<<grid, BTW * BTH, 0, s>>>(a, tab, pcode);
+    else if (a.depth == SSK_8U) k_fused_bayer<SSK_8U><<<grid, BTW * BTH, 0, s>>>(a, tab, pcode);
+    else { set_error("bayer_warp_accumulate: unsupported frame depth"); return SSK_ERR_INVALID; }
+    SSK_LAUNCH_CHECK();
+  }
+  return SSK_OK;
+}
+
+}  // namespace ssk

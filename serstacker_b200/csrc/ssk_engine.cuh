@@ -123,6 +123,7 @@ class Acc {
   ssk_transform map_t;
   DevBuf rmap;       // explicit CV_32FC2 map (dense) when set_remap was given one
   bool rmap_explicit = false;
+  int rmap_rows = 0, rmap_cols = 0;
   DevBuf acc, wacc;  // mean (rows*cols*cn) + weights (rows*cols)   |  bayer: acc (x3) + counters (x3)
   DevBuf staging, wstaging, out_staging;
   ~Acc();

@@ -482,7 +482,9 @@ __device__ __forceinline__ void roll_pixel_c2(RollC2 &R, const ColMap<MT> &cm, f
   const float Wn = W0 + wk;
   float rW;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rW) : "f"(Wn));
-  const float factor = wk * rW;
+  // wk <= Wn, so the exact factor is <= 1: the clamp keeps a denormal weight sum (flushed: rcp = inf) from poisoning
+  // the pixel with inf / NaN; elsewhere the approximate reciprocal is within 2 ulp of wk / Wn
+  const float factor = fminf(wk * rW, 1.0f);
   if (ok && wk > 0.f) {              // eroded validity mask (ring tiles); c_frame_accumulation.cc:114
     sts_f32(w_a, Wn);
     sts_f32(acc_a, fmaf(I - A, factor, A));

@@ -78,6 +78,10 @@ struct ssk_stack {
   int ring_pending = -1;                 // copy whose ring kernel the handle's stream has not been made to wait for yet
   cudaEvent_t ev_ring_end = nullptr;     // (timing) end of the last chunk's ring kernel, on the side stream
   DevBuf ref_staging, axis_tab;
+  // bayer_average: demosaiced (BGR, frame depth) copies of the chunk's raw frames feed the registration; the raw frames
+  // feed the accumulator (c_image_stacking_pipeline_base.cc:221-236, c_image_stacking_pipeline.cc:1730-1752)
+  DevBuf bgr_slots, d_bgr_ptrs, ref_bgr;
+  int ref_cn = 0;                        // channels of the reference frame as given
   int axis_tab_built = 0;                // W1 up-sampling tables of this geometry are in axis_tab
   // host frames: sub-chunks of `host_chunk` frames rotate through `nsets` sets of frame slots; a copy stream uploads
   // sub-chunk k+1 while sub-chunk k is processed
@@ -90,11 +94,16 @@ struct ssk_stack {
   DevBuf rec_all;
   PinnedBuf h_rec_all;
   cudaEvent_t rec_ev[kRecRing] = {};
+  // device-frame chunks leave their border-ring kernel running on the side stream: it reads the caller's frames, so
+  // ssk_stack_wait(ticket) also waits for the chunk's ring kernel (recorded on the side stream)
+  cudaEvent_t rec_ring_ev[kRecRing] = {};
+  bool rec_ring_valid[kRecRing] = {};
   int rec_n[kRecRing] = {};
   int64_t rec_ticket[kRecRing] = {-1, -1, -1, -1};
   int64_t next_ticket = 0;
   ~ssk_stack() {
     for (auto &e : rec_ev) if (e) cudaEventDestroy(e);
+    for (auto &e : rec_ring_ev) if (e) cudaEventDestroy(e);
     for (auto &e : set_free) if (e) cudaEventDestroy(e);
     for (auto &e : set_full) if (e) cudaEventDestroy(e);
     if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -135,6 +144,13 @@ static int stack_alloc_slots(ssk_stack *h) {
       h->tma_slots = true;
     }
   }
+  if (h->o.accumulation_method == SSK_STACK_BAYER_AVERAGE && h->o.enable_registration) {
+    const size_t bgr_bytes = frame_bytes * 3;
+    if (int e = h->bgr_slots.ensure(bgr_bytes * B)) return e;
+    for (int b = 0; b < B; ++b) p[b] = h->bgr_slots.as<char>() + bgr_bytes * b;
+    if (int e = h->d_bgr_ptrs.ensure(sizeof(void *) * B)) return e;
+    SSK_CUDA(cudaMemcpy(h->d_bgr_ptrs.p, p.data(), sizeof(void *) * B, cudaMemcpyHostToDevice));
+  }
   if (int e = h->jobs.ensure(sizeof(FrameJob) * B)) return e;
   if (int e = h->jobs_b.ensure(sizeof(FrameJob) * B)) return e;
   if (int e = h->counter.ensure(sizeof(int))) return e;
@@ -149,10 +165,12 @@ static int stack_alloc_slots(ssk_stack *h) {
   if (int e = h->rec_all.ensure(sizeof(EccFrame) * B * ssk_stack::kRecRing)) return e;
   if (int e = h->h_rec_all.ensure(sizeof(EccFrame) * B * ssk_stack::kRecRing)) return e;
   for (auto &e : h->rec_ev) if (!e) SSK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto &e : h->rec_ring_ev) if (!e) SSK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   // sub-chunk of host frames: large enough to keep the kernels efficient, small enough for >= 2 sets in flight
   h->host_chunk = B >= 32 ? std::max(16, B / 4) : B;
   if (const char *e = getenv("SSK_HOST_CHUNK")) { const int c = atoi(e); if (c >= 1 && c <= B) h->host_chunk = c; }
   h->nsets = std::max(1, std::min<int>(ssk_stack::kMaxSets, B / h->host_chunk));
+  if (h->nsets < 2) h->host_chunk = B;   // a single slot set cannot take the next sub-chunk's upload while it is in use
   if (!h->copy_stream) {
     SSK_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     for (auto &e : h->set_free) SSK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -243,8 +261,11 @@ int ssk_stack_create(const ssk_stack_options *opts, ssk_stack **out) {
   }
   SSK_REQUIRE(opts && out, "ssk_stack_create: null argument");
   SSK_REQUIRE(opts->max_batch >= 1 && opts->max_batch <= 4096, "max_batch 1..4096");
-  SSK_REQUIRE(opts->accumulation_method == SSK_STACK_AVERAGE || opts->accumulation_method == SSK_STACK_WEIGHTED_AVERAGE,
-              "ssk_stack: average and weighted_average are fused; bayer_average goes through ssk_reg_* + ssk_acc_*");
+  SSK_REQUIRE(opts->accumulation_method == SSK_STACK_AVERAGE || opts->accumulation_method == SSK_STACK_WEIGHTED_AVERAGE ||
+              opts->accumulation_method == SSK_STACK_BAYER_AVERAGE, "ssk_stack: accumulation_method must be average, weighted_average or bayer_average");
+  if (opts->accumulation_method == SSK_STACK_BAYER_AVERAGE)
+    SSK_REQUIRE(opts->bayer_colorid >= SSK_COLORID_BAYER_RGGB && opts->bayer_colorid <= SSK_COLORID_BAYER_BGGR,
+                "ssk_stack: bayer_average needs bayer_colorid RGGB / GRBG / GBRG / BGGR");
   SSK_REQUIRE(opts->sm_uscale >= 0 && opts->sm_uscale <= 12, "sharpness_measure.uscale 0..12");
   ssk_stack *h = new (std::nothrow) ssk_stack();
   SSK_REQUIRE(h, "out of memory");
@@ -255,7 +276,8 @@ int ssk_stack_create(const ssk_stack_options *opts, ssk_stack **out) {
   if (opts->enable_registration) {
     if (int e = h->reg_h.r.init(opts->registration, h->stream, false)) { delete h; return e; }
   }
-  h->acc_h.a.kind = SSK_ACC_WEIGHTED_AVERAGE;
+  h->acc_h.a.kind = opts->accumulation_method == SSK_STACK_BAYER_AVERAGE ? SSK_ACC_BAYER_AVERAGE : SSK_ACC_WEIGHTED_AVERAGE;
+  h->acc_h.a.colorid = opts->bayer_colorid;
   h->acc_h.a.stream = h->stream;
   if (int e = get_tables(&h->tab)) { delete h; return e; }
   *out = h;
@@ -264,11 +286,25 @@ int ssk_stack_create(const ssk_stack_options *opts, ssk_stack **out) {
 
 int ssk_stack_destroy(ssk_stack *h) { delete h; return SSK_OK; }
 
+static int stack_check_mat(const ssk_mat *m, const char *what) {
+  if (!m || !m->data || m->rows <= 0 || m->cols <= 0) { set_error(std::string(what) + ": empty image"); return SSK_ERR_INVALID; }
+  const int d = type_depth(m->type), cn = type_cn(m->type);
+  if (!depth_bytes(d) || cn < 1 || cn > 4) { set_error(std::string(what) + ": unsupported type"); return SSK_ERR_INVALID; }
+  if (m->step < (int64_t)m->cols * cn * depth_bytes(d)) { set_error(std::string(what) + ": step smaller than a row"); return SSK_ERR_INVALID; }
+  return SSK_OK;
+}
+
 int ssk_stack_set_reference(ssk_stack *h, const ssk_mat *image, const ssk_mat *mask, int bpp) {
-  SSK_REQUIRE(h && image && image->data, "ssk_stack_set_reference: null argument");
+  SSK_REQUIRE(h && image, "ssk_stack_set_reference: null argument");
+  if (int e = stack_check_mat(image, "ssk_stack_set_reference: reference frame")) return e;
   const int d = type_depth(image->type), cn = type_cn(image->type);
-  SSK_REQUIRE(depth_bytes(d) && (cn == 1 || cn == 3), "frames must be 8U/16U/32F with 1 or 3 channels");
-  h->rows = image->rows; h->cols = image->cols; h->type = image->type; h->bpp = bpp;
+  const bool bayer = h->o.accumulation_method == SSK_STACK_BAYER_AVERAGE;
+  SSK_REQUIRE(cn == 1 || cn == 3, "frames must be 8U/16U/32F with 1 or 3 channels");
+  if (bayer) SSK_REQUIRE(!(image->rows & 1) && !(image->cols & 1), "bayer_average: frame size must be even");
+  h->rows = image->rows; h->cols = image->cols; h->bpp = bpp; h->ref_cn = cn;
+  // frames are expected in the reference frame's type (a raw Bayer frame per reference pixel for bayer_average); the first
+  // frames of another depth re-latch it (a CV_32F master frame over 16-bit input frames), see stack_check_frames
+  h->type = bayer ? SSK_MAKETYPE(d, 1) : image->type;
   if (h->o.enable_registration) {
     Img im;
     im.rows = image->rows; im.cols = image->cols; im.depth = d; im.cn = cn; im.scale = bpp_scale(d, bpp);
@@ -279,6 +315,13 @@ int ssk_stack_set_reference(ssk_stack *h, const ssk_mat *image, const ssk_mat *m
       SSK_CUDA(cudaMemcpy2DAsync(h->ref_staging.p, rowb, image->data, image->step, rowb, image->rows, cudaMemcpyHostToDevice, h->stream));
       im.data = h->ref_staging.p; im.step = (int64_t)rowb;
     }
+    if (bayer && cn == 1) {
+      // a raw Bayer reference is demosaiced as read_input_frame does (c_image_stacking_pipeline_base.cc:221-236)
+      const size_t bstep = (size_t)image->cols * 3 * depth_bytes(d);
+      if (int e = h->ref_bgr.ensure(bstep * image->rows)) return e;
+      if (int e = launch_debayer_nn2(im.data, im.step, d, image->rows, image->cols, h->o.bayer_colorid, h->ref_bgr.p, (int64_t)bstep, h->stream)) return e;
+      im.data = h->ref_bgr.p; im.step = (int64_t)bstep; im.cn = 3;
+    }
     const uint8_t *d_mask = nullptr;
     int64_t mstep = 0;
     if (mask) { if (int e = mask_to_device(mask, image->rows, image->cols, h->reg_h.st_mask, h->stream, &d_mask, &mstep)) return e; }
@@ -286,7 +329,7 @@ int ssk_stack_set_reference(ssk_stack *h, const ssk_mat *image, const ssk_mat *m
     if (int e = h->reg_h.r.ecch.reserve(h->max_batch)) return e;
   }
   if (int e = stack_alloc_slots(h)) return e;
-  if (int e = h->acc_h.a.ensure(h->rows, h->cols, cn)) return e;
+  if (int e = h->acc_h.a.ensure(h->rows, h->cols, bayer ? 3 : cn)) return e;
   SSK_CUDA(cudaStreamSynchronize(h->stream));
   h->have_reference = true;
   return SSK_OK;
@@ -364,7 +407,21 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
 
   // ---- registration prep + ECC
   const bool weighted = h->o.accumulation_method == SSK_STACK_WEIGHTED_AVERAGE && h->o.sm_kradius > 0;
-  if (h->o.enable_registration) {
+  const bool bayer = h->o.accumulation_method == SSK_STACK_BAYER_AVERAGE;
+  if (h->o.enable_registration && bayer) {
+    // read_input_frame: debayer(raw) keeps the depth, the registration sees the demosaiced frame
+    // (c_image_stacking_pipeline_base.cc:221-236, 271-276); the raw samples go to the accumulator below
+    const size_t bstep = rowb * 3, bgr_bytes = bstep * h->rows;
+    for (int i = 0; i < n; ++i) {
+      const void *src = set >= 0 ? (const void *)(h->frame_slots.as<char>() + rowb * h->rows * ((size_t)set * h->host_chunk + i)) : frames[i].data;
+      const int64_t sstep = set >= 0 ? (int64_t)rowb : frames[i].step;
+      if (int e = launch_debayer_nn2(src, sstep, d, h->rows, h->cols, h->o.bayer_colorid, h->bgr_slots.as<char>() + bgr_bytes * i,
+                                     (int64_t)bstep, s)) return e;
+    }
+    Img g3 = geom;
+    g3.cn = 3; g3.step = (int64_t)bstep;
+    if (int e = h->reg_h.r.prepare(g3, h->d_bgr_ptrs.as<const void *>(), n)) return e;
+  } else if (h->o.enable_registration) {
     if (int e = h->reg_h.r.prepare(geom, d_frame_ptrs, n)) return e;
   }
   SSK_CUDA(cudaEventRecord(h->ev[1], s));
@@ -445,7 +502,25 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
   a.tmap_frames = (weighted && d_tmaps) ? d_tmaps : nullptr;
   a.tmap_weights = (weighted && d_tmaps) ? (par ? h->d_tmaps_weights_b.p : h->d_tmaps_weights.p) : nullptr;
   a.acc = h->acc_h.a.acc.as<float>(); a.wacc = h->acc_h.a.wacc.as<float>();
-  if (int e = launch_warp_accumulate(a, h->tab, s)) return e;
+  if (bayer) {
+    // the mask of custom_remap(current_remap, frame, mask, registration_options.interpolation) gates the gather of the raw
+    // samples through current_remap (c_image_stacking_pipeline.cc:1644-1651, 1730-1752)
+    a.side_stream = nullptr;
+    if (h->o.enable_registration) {
+      if (int e = launch_bayer_warp_accumulate(a, h->tab, h->o.bayer_colorid, s)) return e;
+    } else {
+      // no registration: empty remap, no mask -> acc[cc] += src, cntr[cc] += 1 per pixel (c_frame_accumulation.cc:998-1010)
+      for (int i = 0; i < n; ++i) {
+        BayerAccArgs b = {};
+        b.src = geom;
+        b.src.data = set >= 0 ? (const void *)(h->frame_slots.as<char>() + rowb * h->rows * ((size_t)set * h->host_chunk + i)) : frames[i].data;
+        b.src.step = set >= 0 ? (int64_t)rowb : frames[i].step;
+        b.have_map = 0; b.weights = nullptr; b.wtype = -1; b.colorid = h->o.bayer_colorid;
+        b.acc = a.acc; b.cntr = a.wacc;
+        if (int e = launch_bayer_add(b, s)) return e;
+      }
+    }
+  } else if (int e = launch_warp_accumulate(a, h->tab, s)) return e;
   if (a.side_stream) {
     h->join_recorded[par] = true;
     h->ring_pending = defer ? par : -1;
@@ -465,8 +540,13 @@ static int stack_submit_chunk(ssk_stack *h, const ssk_mat *frames, int m, int64_
   const int slot = (int)(t % ssk_stack::kRecRing);
   const int base = slot * h->max_batch;
   SSK_CUDA(cudaEventSynchronize(h->rec_ev[slot]));   // the slot's previous download has landed (no-op if never used)
+  h->rec_ring_valid[slot] = false;
   if (frames[0].mem == SSK_MEM_DEVICE) {
     if (int e = stack_process_chunk(h, frames, m, -1, base, last_in_call)) return e;
+    if (h->ring_pending >= 0) {      // the chunk's ring kernel is still in flight on the side stream
+      SSK_CUDA(cudaEventRecord(h->rec_ring_ev[slot], h->side));
+      h->rec_ring_valid[slot] = true;
+    }
   } else {
     // host frames: upload sub-chunk k+1 on the copy stream while sub-chunk k is processed
     const int hc = h->host_chunk;
@@ -496,8 +576,18 @@ static int stack_check_frames(ssk_stack *h, const ssk_mat *frames, int n, int bp
   SSK_REQUIRE(h && frames && n >= 0, "ssk_stack_add_frames: bad argument");
   SSK_REQUIRE(h->have_reference, "ssk_stack: set_reference must be called first");
   SSK_REQUIRE(bpp == h->bpp, "ssk_stack: bpp differs from the reference frame's");
+  if (n > 0 && frames[0].type != h->type) {
+    // frames of another depth than the reference frame (e.g. a CV_32F master frame over 16-bit input frames): the
+    // per-frame buffers follow the frames; the channel count stays the reference's (one for raw Bayer frames)
+    SSK_REQUIRE(depth_bytes(type_depth(frames[0].type)) && type_cn(frames[0].type) == type_cn(h->type),
+                "ssk_stack: frame type differs from the reference frame's channel layout");
+    if (int e = ssk_stack_sync(h)) return e;
+    h->type = frames[0].type;
+    if (int e = stack_alloc_slots(h)) return e;
+  }
   for (int i = 0; i < n; ++i) {
-    SSK_REQUIRE(frames[i].data && frames[i].rows == h->rows && frames[i].cols == h->cols && frames[i].type == h->type,
+    if (int e = stack_check_mat(&frames[i], "ssk_stack: frame")) return e;
+    SSK_REQUIRE(frames[i].rows == h->rows && frames[i].cols == h->cols && frames[i].type == h->type,
                 "ssk_stack: frame geometry/type differs from the reference frame");
   }
   return SSK_OK;
@@ -515,6 +605,7 @@ int ssk_stack_wait(ssk_stack *h, int64_t ticket, ssk_transform *transforms_out, 
   const int slot = (int)(ticket % ssk_stack::kRecRing);
   SSK_REQUIRE(ticket >= 0 && h->rec_ticket[slot] == ticket, "ssk_stack_wait: unknown ticket (only the last 4 chunks are kept)");
   SSK_CUDA(cudaEventSynchronize(h->rec_ev[slot]));
+  if (h->rec_ring_valid[slot]) SSK_CUDA(cudaEventSynchronize(h->rec_ring_ev[slot]));   // caller's device frames are free again
   const int m = h->rec_n[slot];
   if (n_out) *n_out = m;
   if (h->o.enable_registration && (transforms_out || status_out)) {

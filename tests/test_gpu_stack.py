@@ -218,3 +218,89 @@ def test_streaming_submit_wait_equals_add_frames(gpu):
     assert a.accumulated_frames() == b.accumulated_frames()
     from serstacker_b200 import capi
     assert capi.lib.ssk_stack_wait(b._h, 0, None, None, 0, None) != 0      # ticket 0 left the 4-chunk ring long ago
+
+
+def _bayer_oracle(frames, bpp, colorid, interpolation=cv2.INTER_LINEAR, enable_registration=True):
+    so = opl.StackingOptions(accumulation_method=opl.ACC_BAYER_AVERAGE, enable_registration=enable_registration)
+    so.registration.motion_type = otf.IMAGE_MOTION_TRANSLATION
+    so.registration.interpolation = interpolation
+    rec = []
+    avg, mask, acc, _ = opl.run_bayer_stacking(frames, bpp, so, colorid, collect=rec)
+    return avg, mask, acc, rec
+
+
+@pytest.mark.parametrize("colorid", [8, 9, 10, 11])
+@pytest.mark.parametrize("interp", [cv2.INTER_LINEAR, cv2.INTER_CUBIC])
+def test_stack_bayer_average_matches_oracle(gpu, colorid, interp):
+    """The bayer_average form of the batched loop (c_image_stacking_pipeline.cc:1730-1752): raw Bayer frames in, the
+    device demosaics them for the registration and gathers the raw samples through each frame's remap under the eroded
+    remap mask.  Translation trajectories are bit-faithful; sums / counters are compared exactly."""
+    from serstacker_b200 import api
+    frames, shifts, bpp = synth.make_bayer_sequence(192, 128, 6, seed=5)
+    avg_o, mask_o, acc_o, rec = _bayer_oracle(frames, bpp, colorid, interp)
+    ro = api.registration_options(motion_type=0, interpolation=interp)
+    p = api.c_image_stacking_pipeline(api.stack_options(registration=ro, accumulation_method=2, bayer_colorid=colorid, max_batch=4))
+    p.set_reference(frames[0], bpp=bpp)
+    res = p.add_frames(frames)
+    avg_g, mask_g = p.compute()
+    assert p.accumulated_frames() == sum(r["ok"] for r in rec)
+    assert [rg["ok"] for rg in res] == [r["ok"] for r in rec]
+    dmax = max(map_diff_px(0, rg["params"], r["params"], (192, 128)) for rg, r in zip(res, rec))
+    print("bayer stack colorid=%d interp=%d: max|dparam| = %.3g px" % (colorid, interp, dmax))
+    assert dmax <= 1e-3
+    assert np.array_equal(mask_g, mask_o)
+    if dmax == 0:      # identical maps: identical double-precision gathers
+        assert np.array_equal(avg_g, avg_o)
+        assert np.array_equal(p.accumulator().get_acc_counters(), acc_o.get_acc_counters())
+    else:
+        assert rel_l2(avg_g, avg_o, mask_o > 0) <= 1e-4
+
+
+@pytest.mark.parametrize("dtype", ["u8", "f32"])
+def test_stack_bayer_average_other_depths(gpu, dtype):
+    from serstacker_b200 import api
+    frames, shifts, bpp = synth.make_bayer_sequence(160, 96, 4, seed=7)
+    if dtype == "u8":
+        frames, bpp = [(f >> 8).astype(np.uint8) for f in frames], 8
+    else:
+        frames, bpp = [(f.astype(np.float32) / np.float32(65536.0)) for f in frames], 32
+    avg_o, mask_o, acc_o, rec = _bayer_oracle(frames, bpp, 8)
+    p = api.c_image_stacking_pipeline(api.stack_options(registration=api.registration_options(motion_type=0), accumulation_method=2,
+                                                        bayer_colorid=8, max_batch=8))
+    p.set_reference(frames[0], bpp=bpp)
+    res = p.add_frames(frames)
+    avg_g, mask_g = p.compute()
+    assert all(rg["ok"] == r["ok"] for rg, r in zip(res, rec))
+    assert max(map_diff_px(0, rg["params"], r["params"], (160, 96)) for rg, r in zip(res, rec)) <= 1e-3
+    assert np.array_equal(mask_g, mask_o)
+    assert rel_l2(avg_g, avg_o, mask_o > 0) <= 1e-5
+
+
+def test_stack_bayer_average_without_registration(gpu):
+    """enable_registration = false: empty remap, every raw sample goes to its own colour plane (c_frame_accumulation.cc:998-1010)."""
+    from serstacker_b200 import api
+    frames, _, bpp = synth.make_bayer_sequence(64, 48, 3, seed=9)
+    avg_o, mask_o, acc_o, _ = _bayer_oracle(frames, bpp, 9, enable_registration=False)
+    p = api.c_image_stacking_pipeline(api.stack_options(accumulation_method=2, bayer_colorid=9, enable_registration=0, max_batch=2))
+    p.set_reference(frames[0], bpp=bpp)
+    p.add_frames(frames, want_results=False)
+    avg_g, mask_g = p.compute()
+    assert p.accumulated_frames() == 3
+    assert np.array_equal(mask_g, mask_o) and np.array_equal(avg_g, avg_o)
+
+
+def test_stack_bayer_average_float_master_over_u16_frames(gpu):
+    """A CV_32F BGR master frame (what the master-frame pass hands over) over 16-bit raw frames."""
+    from serstacker_b200 import api
+    from oracle import debayer as od
+    frames, _, bpp = synth.make_bayer_sequence(128, 96, 4, seed=11)
+    master = opl.to_float_frame(od.debayer_nn2(frames[0], 8), bpp)
+    avg_o, mask_o, _, rec = _bayer_oracle(frames, bpp, 8)
+    p = api.c_image_stacking_pipeline(api.stack_options(registration=api.registration_options(motion_type=0), accumulation_method=2,
+                                                        bayer_colorid=8, max_batch=4))
+    p.set_reference(master, bpp=bpp)
+    res = p.add_frames(frames)
+    avg_g, mask_g = p.compute()
+    assert max(map_diff_px(0, rg["params"], r["params"], (128, 96)) for rg, r in zip(res, rec)) <= 1e-3
+    assert np.array_equal(mask_g, mask_o)
+    assert rel_l2(avg_g, avg_o, mask_o > 0) <= 1e-5
