@@ -56,6 +56,12 @@ int from_device(const void *dsrc, size_t rowb, int rows, ssk_mat *dst, cudaStrea
   return SSK_OK;
 }
 
+// c_bayer_average::get_acc_counters: cv::multiply(_counter, cv::Scalar(1, 0.5, 1), accw) (c_frame_accumulation.cc:1239-1249)
+__global__ void k_bayer_counters(const float *cntr, float *out, int64_t n3) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n3) out[i] = (i % 3 == 1) ? cntr[i] * 0.5f : cntr[i];
+}
+
 __global__ void k_create_remap(MapCoef m, int rows, int cols, float2 *dst) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= cols || y >= rows) return;
@@ -532,8 +538,15 @@ int ssk_acc_get_counters(ssk_acc *h, ssk_mat *accw) {
   const int wcn = a.kind == SSK_ACC_BAYER_AVERAGE ? 3 : 1;
   SSK_REQUIRE(type_depth(accw->type) == SSK_32F && type_cn(accw->type) == wcn && accw->rows == a.rows && accw->cols == a.cols,
               "get_acc_counters: CV_32F buffer of the accumulator size (3 channels for bayer)");
-  // note: c_bayer_average::get_acc_counters scales G by 0.5 (c_frame_accumulation.cc:1240-1250); raw counters are returned here
-  if (int e = from_device(a.wacc.p, (size_t)a.cols * wcn * 4, a.rows, accw, a.stream)) return e;
+  const void *src = a.wacc.p;
+  if (a.kind == SSK_ACC_BAYER_AVERAGE) {
+    const int64_t n3 = (int64_t)a.rows * a.cols * 3;
+    if (int e = a.out_staging.ensure((size_t)n3 * 4)) return e;
+    k_bayer_counters<<<(unsigned)((n3 + 255) / 256), 256, 0, a.stream>>>(a.wacc.as<float>(), a.out_staging.as<float>(), n3);
+    SSK_LAUNCH_CHECK();
+    src = a.out_staging.p;
+  }
+  if (int e = from_device(src, (size_t)a.cols * wcn * 4, a.rows, accw, a.stream)) return e;
   SSK_CUDA(cudaStreamSynchronize(a.stream));
   return SSK_OK;
 }

@@ -383,7 +383,8 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
       if (reinterpret_cast<uintptr_t>(frames[i].data) & 15) h->frames_aligned = false;
     }
     SSK_CUDA(cudaMemcpyAsync(h->d_user_ptrs[r].p, hp, sizeof(void *) * n, cudaMemcpyHostToDevice, s));
-    if (h->tma_slots && h->tma_weights && h->frames_aligned) {
+    const bool need_wmaps = h->o.accumulation_method == SSK_STACK_WEIGHTED_AVERAGE && h->o.sm_kradius > 0;
+    if (h->tma_slots && (h->tma_weights || !need_wmaps) && h->frames_aligned && !getenv("SSK_NO_TMA")) {
       unsigned char *hm = h->h_tmaps_user[r].as<unsigned char>();
       bool ok = true;
       for (int i = 0; i < n && ok; ++i)
@@ -400,7 +401,8 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
     SSK_REQUIRE(set >= 0, "internal: host frames without a slot set");
     SSK_CUDA(cudaStreamWaitEvent(s, h->set_full[set], 0));
     d_frame_ptrs = h->d_slot_ptrs.as<const void *>() + (size_t)set * h->host_chunk;
-    if (h->tma_slots && h->tma_weights) d_tmaps = h->d_tmaps_slots.as<char>() + (size_t)set * h->host_chunk * 128;
+    const bool need_wmaps = h->o.accumulation_method == SSK_STACK_WEIGHTED_AVERAGE && h->o.sm_kradius > 0;
+    if (h->tma_slots && (h->tma_weights || !need_wmaps)) d_tmaps = h->d_tmaps_slots.as<char>() + (size_t)set * h->host_chunk * 128;
     geom.step = (int64_t)rowb;
   }
   SSK_CUDA(cudaEventRecord(h->ev[0], s));
@@ -499,9 +501,11 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
     make_transform(&t0, h->o.enable_registration ? ro.motion_type : SSK_MOTION_TRANSLATION);
     a.map_type = make_mapcoef(t0).type;
   }
-  a.tmap_frames = (weighted && d_tmaps) ? d_tmaps : nullptr;
+  a.tmap_frames = (d_tmaps && !bayer) ? d_tmaps : nullptr;
   a.tmap_weights = (weighted && d_tmaps) ? (par ? h->d_tmaps_weights_b.p : h->d_tmaps_weights.p) : nullptr;
   a.acc = h->acc_h.a.acc.as<float>(); a.wacc = h->acc_h.a.wacc.as<float>();
+  if (getenv("SSK_NO_TMA_KERNEL")) a.tmap_frames = a.tmap_weights = nullptr;   // tuning knob: cp.async kernel pair
+  if (fused_tma_applicable(a)) a.side_stream = nullptr;                        // one launch over all tiles: nothing to fork
   if (bayer) {
     // the mask of custom_remap(current_remap, frame, mask, registration_options.interpolation) gates the gather of the raw
     // samples through current_remap (c_image_stacking_pipeline.cc:1644-1651, 1730-1752)

@@ -39,6 +39,9 @@ struct WarpAccArgs {
 };
 
 int launch_warp_accumulate(const WarpAccArgs &a, const Tables &tab, cudaStream_t stream);
+// TMA form (ssk_fused_tma.cu): CV_32F single-channel frames with tensor maps, affine-like maps; one launch over all tiles.
+bool fused_tma_applicable(const WarpAccArgs &a);
+int launch_warp_accumulate_tma(const WarpAccArgs &a, const Tables &tab, cudaStream_t stream);
 // Bayer form of the fused loop (ssk_bayer.cu): a.jobs[j].frame are raw Bayer frames, a.acc / a.wacc the rows x cols x 3 sums
 // and counters of c_bayer_average; the mask is base_remap's eroded validity for a.interp.
 int launch_bayer_warp_accumulate(const WarpAccArgs &a, const Tables &tab, int colorid, cudaStream_t stream);
