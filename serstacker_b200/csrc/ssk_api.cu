@@ -704,12 +704,32 @@ int ssk_local_variance_map(const ssk_mat *image, int bpp, int dscale, int kradiu
 }  // extern "C"
 
 // lpg on a device image; the result (dense, image size) lives in sc.b until the next call that uses sc.b
+// reduce_color_channels(s, s, cv::REDUCE_AVG) (lpg.cc:246-248, reduce_channels.cc:11-29): cv::reduce along the channel
+// axis of the CV_32F image = float sum in channel order, times (float)(1 / cn)  (checked against cv2.reduce)
+template <int DEPTH>
+__global__ void __launch_bounds__(256) k_channel_avg(const Img im, float *dst) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= im.cols || y >= im.rows) return;
+  float sum = load_px<DEPTH>(im, y, x, 0);
+  for (int c = 1; c < im.cn; ++c) sum = __fadd_rn(sum, load_px<DEPTH>(im, y, x, c));
+  dst[(int64_t)y * im.cols + x] = __fmul_rn(sum, (float)(1.0 / im.cn));
+}
+
 static int lpg_device(Scratch &sc, Img im, double k, double p, int dscale, int uscale, float **out) {
   cudaStream_t s = sc.stream;
-  SSK_REQUIRE(im.cn == 1, "lpg: single-channel images (the callers pass the gray frame)");
+  SSK_REQUIRE(im.cn >= 1 && im.cn <= 4, "lpg: 1 to 4 channels");
   // lpg.cc:184-200: integer samples are scaled by 1 / max value of the depth
   im.scale = im.depth == SSK_8U ? (float)(1.0 / 255.0) : im.depth == SSK_16U ? (float)(1.0 / 65535.0) : 1.f;
   const size_t n = (size_t)im.rows * im.cols;
+  if (im.cn > 1) {
+    if (int e = sc.c.ensure(n * 4)) return e;
+    const dim3 grid(div_up(im.cols, 32), div_up(im.rows, 8));
+    if (im.depth == SSK_32F) k_channel_avg<SSK_32F><<<grid, 256, 0, s>>>(im, sc.c.as<float>());
+    else if (im.depth == SSK_16U) k_channel_avg<SSK_16U><<<grid, 256, 0, s>>>(im, sc.c.as<float>());
+    else k_channel_avg<SSK_8U><<<grid, 256, 0, s>>>(im, sc.c.as<float>());
+    SSK_LAUNCH_CHECK();
+    im.data = sc.c.p; im.step = (int64_t)im.cols * 4; im.depth = SSK_32F; im.cn = 1; im.scale = 1.f;
+  }
   if (int e = sc.b.ensure(n * 4 * 2)) return e;
   float *bufA = sc.b.as<float>(), *bufB = bufA + n;
   // pdownscale (lpg.cc:132-156): `level` pyrDowns, stopping once a side drops below 4

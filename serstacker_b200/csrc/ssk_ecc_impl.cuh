@@ -452,10 +452,55 @@ struct Walk {
   }
 };
 
+// Pixels of a level one CTA of the cluster visits in a pass.  SSK_ECC_BANDS (default): rank r owns the contiguous band
+// [r * chunk, (r + 1) * chunk) and walks it NT pixels at a time, so that the source row a bilinear tap pair touches for
+// output row y is still in L1 when row y + 1 needs it (the interleaved assignment sent consecutive rows to different
+// SMs).  The order of the per-thread partial sums changes with it, their fixed-order double reduction does not.
+#ifndef SSK_ECC_BANDS
+#define SSK_ECC_BANDS 1
+#endif
+struct Band { int start, stride, end; };
+__device__ __forceinline__ Band pass_band(int rank, int csize, int tid, int n) {
+  Band b;
+#if SSK_ECC_BANDS
+  const int chunk = (((n + csize - 1) / csize) + 31) & ~31;
+  b.start = rank * chunk + tid; b.stride = NT; b.end = min(n, (rank + 1) * chunk);
+#else
+  b.start = rank * NT + tid; b.stride = csize * NT; b.end = n;
+#endif
+  return b;
+}
+
 // keeps a base pointer as one 64-bit register value (stops the compiler from re-adding its parts per access)
 template <typename T> __device__ __forceinline__ const T *opaque_ptr(const T *p) { asm volatile("" : "+l"(p)); return p; }
 
-__device__ __forceinline__ int cvround32(float v) { return __float2int_rn(__fmul_rn(v, 32.0f)); }
+// cvRound(v * 32).  Round-to-nearest-even through the 1.5 * 2^23 addend (FADD + IADD on the FP32 / integer pipes instead
+// of F2I on the quarter-rate conversion unit): identical to __float2int_rn for |32 v| < 2^22; beyond that (131 072 px
+// outside the image) both forms give coordinates every validity test rejects and every sampler clamps.
+#ifndef SSK_ECC_FASTROUND
+#define SSK_ECC_FASTROUND 1
+#endif
+__device__ __forceinline__ int cvround32(float v) {
+#if SSK_ECC_FASTROUND
+  return __float_as_int(__fadd_rn(__fmul_rn(v, 32.0f), 12582912.0f)) - 0x4B400000;
+#else
+  return __float2int_rn(__fmul_rn(v, 32.0f));
+#endif
+}
+// (float)(s & 31) / 32 without an integer-to-float conversion: 1 + f / 32 assembled in the mantissa, minus one (exact)
+__device__ __forceinline__ float frac32(int s) {
+#if SSK_ECC_FASTROUND
+  return __fsub_rn(__int_as_float(0x3F800000 | ((s & 31) << 18)), 1.0f);
+#else
+  return (float)(s & 31) * 0.03125f;
+#endif
+}
+// cvRound(u) in [0, n) decided on the float itself (round half to even at both ends): u >= -0.5 and u <= hi with
+// hi = n - 0.5 when n - 1 is even, the float below it otherwise
+__device__ __forceinline__ float nearest_hi(int n) {
+  const float h = (float)n - 0.5f;
+  return (n & 1) ? h : __int_as_float(__float_as_int(h) - 1);
+}
 
 // map_xy with the map kind fixed at compile time (the passes are instantiated per transform type)
 template <int TYPE> struct MapKind { static constexpr int MT = MAP_EUCLIDEAN; };
@@ -489,7 +534,7 @@ __device__ __forceinline__ bool lin_valid(int sx, int sy, int cols, int rows) {
 // out-of-range taps carry zero weight, so the result also equals the BORDER_CONSTANT sample.
 __device__ __forceinline__ float lin_sample(const float *__restrict__ p, int cols, int rows, int sx, int sy) {
   const int ix = sx >> 5, iy = sy >> 5;
-  const float tx = (float)(sx & 31) * 0.03125f, ty = (float)(sy & 31) * 0.03125f;
+  const float tx = frac32(sx), ty = frac32(sy);
   const float wx0 = 1.0f - tx, wy0 = 1.0f - ty;
   const int x0 = min(max(ix, 0), cols - 1), x1 = min(max(ix + 1, 0), cols - 1);
   const int y0 = min(max(iy, 0), rows - 1), y1 = min(max(iy + 1, 0), rows - 1);
@@ -529,16 +574,22 @@ __device__ void pass_ic(Ctx &c, int lvl, bool lm_masks) {
   int nvalid = 0;
   const int n = cols * rows;
   // Branch-free body (invalid pixels contribute an exact 0.0), so that several pixels per thread are in flight.
-  Walk w(c.rank * NT + c.tid, c.csize * NT, cols);
+  const Band bd = pass_band(c.rank, c.csize, c.tid, n);
+  Walk w(bd.start, bd.stride, cols);
+  const float hx = nearest_hi(cols), hy = nearest_hi(rows);
   constexpr int kUnroll = 3;   // pixels in flight per thread (measured: 2 -> 3 is -4 % on the pass, 4 is slower)
 #pragma unroll kUnroll
-  for (; w.i < n; w.next()) {
+  for (; w.i < bd.end; w.next()) {
     const float x = (float)w.x, y = (float)w.y;
     float u, v;
     map_xy_t<MapKind<TYPE>::MT>(m, x, y, u, v);
     const int sx = cvround32(u), sy = cvround32(v);
     bool ok;
+#if SSK_ECC_FASTROUND
+    if (lm_masks) ok = u >= -0.5f && u <= hx && v >= -0.5f && v <= hy;   // cvRound(u), cvRound(v) inside the image
+#else
     if (lm_masks) ok = (unsigned)__float2int_rn(u) < (unsigned)cols && (unsigned)__float2int_rn(v) < (unsigned)rows;
+#endif
     else ok = lin_valid(sx, sy, cols, rows);
     if (rmask) ok = ok && rmask[w.i] != 0;
     const float g = lin_sample(cur, cols, rows, sx, sy);
@@ -576,7 +627,8 @@ __device__ void pass_hp(Ctx &c, int lvl) {
 #pragma unroll
   for (int k = 0; k < NS; ++k) acc[k] = 0.0;
   const int n = L.cols * L.rows;
-  for (Walk w(c.rank * NT + c.tid, c.csize * NT, L.cols); w.i < n; w.next()) {
+  const Band bd = pass_band(c.rank, c.csize, c.tid, n);
+  for (Walk w(bd.start, bd.stride, L.cols); w.i < bd.end; w.next()) {
     const int i = w.i;
     float J[M];
     eval_J<TYPE>(jc, (float)w.x, (float)w.y, __ldg(L.gx + i), __ldg(L.gy + i), J);
@@ -620,7 +672,8 @@ __device__ void pass_fa_stats(Ctx &c, int lvl) {
   const int interp = c.cfg->interp;
   double acc[5] = {0, 0, 0, 0, 0};
   const int n = L.cols * L.rows;
-  for (Walk w(c.rank * NT + c.tid, c.csize * NT, L.cols); w.i < n; w.next()) {
+  const Band bd = pass_band(c.rank, c.csize, c.tid, n);
+  for (Walk w(bd.start, bd.stride, L.cols); w.i < bd.end; w.next()) {
     const int i = w.i;
     float u, v;
     map_xy(m, (float)w.x, (float)w.y, u, v);
@@ -724,9 +777,10 @@ __device__ void pass_rho(Ctx &c) {
   double acc[6] = {0, 0, 0, 0, 0, 0};
   int nvalid = 0;
   const int n = cols * rows;
-  Walk w(c.rank * NT + c.tid, c.csize * NT, cols);
+  const Band bd = pass_band(c.rank, c.csize, c.tid, n);
+  Walk w(bd.start, bd.stride, cols);
 #pragma unroll 2
-  for (; w.i < n; w.next()) {
+  for (; w.i < bd.end; w.next()) {
     float u, v;
     map_xy_t<MT>(m, (float)w.x, (float)w.y, u, v);
     const int sx = cvround32(u), sy = cvround32(v);

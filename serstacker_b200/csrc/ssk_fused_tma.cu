@@ -45,8 +45,11 @@ __device__ __noinline__ StagePlan plan_tma(const MapCoef &m, int bx0, int by0, c
   if (!(umin > -30000.f && vmin > -30000.f && umax < 30000.f && vmax < 30000.f)) return p;   // plans are packed as shorts
   const int x_lo = (int)floorf(umin) - 1, x_hi = (int)floorf(umax) + 3;
   const int y_lo = (int)floorf(vmin) - 1, y_hi = (int)floorf(vmax) + 3;
-  if (!(x_hi - x_lo < WD && y_hi - y_lo < GSH)) return p;
-  p.sx0 = p.sxw = x_lo; p.sy0 = y_lo; p.staged = 1;
+  // the copy engine wants the box origin 16-byte aligned along the row (measured: tools/probes/tma_probe.cu traps on a
+  // start column that is not a multiple of 4 floats; negative and fully out-of-range origins are fine and zero-filled)
+  const int sx0 = x_lo & ~3;
+  if (!(x_hi - sx0 < WD && y_hi - y_lo < GSH)) return p;
+  p.sx0 = p.sxw = sx0; p.sy0 = y_lo; p.staged = 1;
   // staged = 2: every pixel of the tile and of its 2-px erosion halo (clipped to the image) maps into the tap-safe
   // interior of the frame: the eroded validity mask is all ones for this frame and no tap leaves the frame
   const int hx0 = max(bx0 - 2, 0), hy0 = max(by0 - 2, 0), hx1 = min(bx0 + TW + 1, a.cols - 1), hy1 = min(by0 + TH + 1, a.rows - 1);

@@ -113,6 +113,21 @@ def test_lpg_matches_oracle(gpu, size, k, p, dscale, uscale):
     assert np.abs(got - want).max() <= 2e-6 * scale, (np.abs(got - want).max(), scale)
 
 
+@pytest.mark.parametrize("cn,dtype", [(3, np.float32), (3, np.uint16), (2, np.float32), (4, np.uint8)])
+def test_lpg_colour_images_average_their_channels(gpu, cn, dtype):
+    """lpg of a multi-channel image: reduce_color_channels(REDUCE_AVG) first (lpg.cc:246-248)."""
+    from serstacker_b200 import api
+    rng = np.random.default_rng(8)
+    base, _ = _frame(200, 144, 9)
+    img = np.stack([np.clip(base * (0.6 + 0.2 * c) + rng.normal(0, 0.01, base.shape), 0, 1) for c in range(cn)], axis=2).astype(np.float32)
+    if dtype != np.float32:
+        img = np.rint(img * np.iinfo(dtype).max).astype(dtype)
+    want = ow.lpg(img, 6.0, 2.0, 0, 0)
+    got = api.lpg(img, 6.0, 2.0, 0, 0)
+    scale = float(np.abs(want).max())
+    assert np.abs(got - want).max() <= 2e-6 * scale, (np.abs(got - want).max(), scale)
+
+
 def test_lpg_rejects_fractional_power(gpu):
     from serstacker_b200 import api, capi
     img, _ = _frame(64, 48, 6)
