@@ -255,6 +255,18 @@ SSK_API int ssk_acc_device_state(ssk_acc *h, void **acc, void **weights, int64_t
 SSK_API int ssk_acc_to_sum_form(ssk_acc *h);
 SSK_API int ssk_acc_from_sum_form(ssk_acc *h, int accumulated_frames);
 
+/* Multi-GPU combine (frames sharded over ranks, one process per GPU; the reference is single-process and ends a run with
+ * ONE c_frame_accumulation, c_frame_accumulation.h:14-63).  nccl_comm is the caller's ncclComm_t.  On return the root's
+ * accumulator holds the stack of all ranks' frames (A = sum_g W_g A_g / sum_g W_g, W = sum_g W_g; Bayer sums and counters
+ * added) and accumulated_frames() the total; the other ranks keep their local state.  One ncclReduce group (values,
+ * weights, frame count) on the handle's stream; NCCL is loaded at run time (libnccl.so.2), SSK_ERR_NCCL if absent. */
+SSK_API int ssk_acc_reduce(ssk_acc *h, void *nccl_comm, int root);
+/* Conveniences for hosts that do not link NCCL themselves: ncclGetUniqueId (128 bytes), ncclCommInitRank on the current
+ * device, ncclCommDestroy. */
+SSK_API int ssk_nccl_get_unique_id(void *id128);
+SSK_API int ssk_nccl_comm_create(const void *id128, int nranks, int rank, void **nccl_comm);
+SSK_API int ssk_nccl_comm_destroy(void *nccl_comm);
+
 /* ---------------------------------------------------------------------------------------------
  * Weight maps (core/proc/sharpness_measure/c_local_variance_sharpness_measure.cc:193-247, core/proc/lpg.cc:223-290).
  * ------------------------------------------------------------------------------------------- */
@@ -357,11 +369,17 @@ SSK_API int ssk_stack_sync(ssk_stack *h);
  * synchronisation): call it before recording a timing event on ssk_stack_stream().  ssk_stack_sync, _compute,
  * _accumulated_frames and _accumulator include it. */
 SSK_API int ssk_stack_flush(ssk_stack *h);
+/* A new run over the same reference frame: empties the accumulator and the frame count, like the fresh c_frame_accumulation a
+ * pipeline run starts with (create_frame_accumulation, c_image_stacking_pipeline.cc:450-466).  Stream-ordered, no host sync. */
+SSK_API int ssk_stack_reset(ssk_stack *h);
 /* c_frame_accumulation::compute() of the pipeline's accumulator. */
 SSK_API int ssk_stack_compute(ssk_stack *h, ssk_mat *avg, ssk_mat *mask);
 /* ssk_stack_compute + average_pyramid_inpaint (c_image_stacking_pipeline.cc:742-767) */
 SSK_API int ssk_stack_compute_inpainted(ssk_stack *h, ssk_mat *avg, ssk_mat *mask, int max_levels);
 SSK_API int ssk_stack_accumulated_frames(ssk_stack *h);
+/* ssk_acc_reduce for the pipeline's accumulator, ordered after everything the handle has enqueued (the end of a sharded
+ * run: c_image_stacking_pipeline.cc:731-769 then reads the root's accumulator). */
+SSK_API int ssk_stack_reduce(ssk_stack *h, void *nccl_comm, int root);
 SSK_API ssk_acc *ssk_stack_accumulator(ssk_stack *h);
 SSK_API ssk_reg *ssk_stack_registration(ssk_stack *h);
 /* CUDA stream the handle launches on (cudaStream_t as void*), for event timing by the caller. */

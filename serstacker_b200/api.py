@@ -463,6 +463,10 @@ class c_image_stacking_pipeline:
     def sync(self):
         check(capi.lib.ssk_stack_sync(self._h))
 
+    def reset(self):
+        """Empty accumulator and frame count for a new run over the same reference (ssk_stack_reset)."""
+        check(capi.lib.ssk_stack_reset(self._h))
+
     def flush(self):
         """Stream-side join of the ring kernel left running by the last device-frame call (no host sync)."""
         check(capi.lib.ssk_stack_flush(self._h))

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libssk.so")
+LIB_PATH = os.environ.get("SSK_LIB") or os.path.join(_HERE, "libssk.so")   # SSK_LIB: an alternative build of the same ABI (A/B runs)
 
 if not os.path.exists(LIB_PATH):
     raise ImportError("serstacker_b200/libssk.so is missing: run `python -m serstacker_b200.build` "
@@ -18,7 +18,7 @@ if not os.path.exists(LIB_PATH):
 
 lib = C.CDLL(LIB_PATH)
 
-SSK_OK, SSK_ERR_INVALID, SSK_ERR_CUDA, SSK_ERR_STATE, SSK_ERR_NOT_REGISTERED = 0, -1, -2, -3, -4
+SSK_OK, SSK_ERR_INVALID, SSK_ERR_CUDA, SSK_ERR_STATE, SSK_ERR_NOT_REGISTERED, SSK_ERR_NCCL = 0, -1, -2, -3, -4, -5
 SSK_8U, SSK_16U, SSK_32F = 0, 2, 5
 MEM_HOST, MEM_DEVICE = 0, 1
 
@@ -147,6 +147,12 @@ _sigs = {
     "ssk_stack_wait": (C.c_int, [C.c_void_p, C.c_int64, _P(ssk_transform), _P(ssk_ecc_status), C.c_int, _P(C.c_int)]),
     "ssk_stack_compute": (C.c_int, [C.c_void_p, _P(ssk_mat), _P(ssk_mat)]),
     "ssk_stack_accumulated_frames": (C.c_int, [C.c_void_p]),
+    "ssk_stack_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "ssk_stack_reset": (C.c_int, [C.c_void_p]),
+    "ssk_acc_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "ssk_nccl_get_unique_id": (C.c_int, [C.c_void_p]),
+    "ssk_nccl_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _P(C.c_void_p)]),
+    "ssk_nccl_comm_destroy": (C.c_int, [C.c_void_p]),
     "ssk_stack_accumulator": (C.c_void_p, [C.c_void_p]),
     "ssk_stack_registration": (C.c_void_p, [C.c_void_p]),
     "ssk_stack_stream": (C.c_void_p, [C.c_void_p]),

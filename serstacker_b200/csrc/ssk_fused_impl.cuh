@@ -201,6 +201,8 @@ __device__ __forceinline__ void tmap_acquire(const void *tmap) {
   asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
 }
 
+__device__ __forceinline__ void tmap_prefetch(const void *tmap) { asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory"); }
+
 struct StagePlan { int staged, sx0, sy0, sxw; };   // staged: tile safe and footprint fits; sxw: weight-tile origin
 // Plans of all frames of a launch are computed once per CTA (one frame per thread) and kept in shared memory.
 constexpr int KPLAN = 256;                          // frames per launch (longer batches are split by the launcher)

@@ -68,7 +68,7 @@ __device__ __noinline__ StagePlan plan_tma(const MapCoef &m, int bx0, int by0, c
 // Pre-erosion flags of the rows y0 - 2 .. y0 + GR + 1 and the columns bx0 - 2 .. bx0 + TW + 1 are packed by ballots
 // (positions outside the image do not erode: border value 255), eroded along x by shifts and along y by a sliding AND.
 template <int INTERP, int MT>
-__device__ __noinline__ unsigned warp_okbits(const MapCoef &m, int bx0, int y0, int lane, const WarpAccArgs &a, const short *itab) {
+__device__ __forceinline__ unsigned warp_okbits(const MapCoef &m, int bx0, int y0, int lane, const WarpAccArgs &a, const short *itab) {
   auto flag = [&](int gx, int gy) -> bool {
     if (gx < 0 || gy < 0 || gx >= a.cols || gy >= a.rows) return true;
     float u, v;
@@ -82,7 +82,7 @@ __device__ __noinline__ unsigned warp_okbits(const MapCoef &m, int bx0, int y0, 
   const unsigned ex0 = __ballot_sync(0xffffffffu, flag(ex, y0 - 2 + er));
   const unsigned ex1 = __ballot_sync(0xffffffffu, er + 8 < GR + 4 ? flag(ex, y0 - 2 + er + 8) : true);
   unsigned h0 = 0, h1 = 0, h2 = 0, h3 = 0, ok = 0;
-#pragma unroll
+#pragma unroll 1      // kept rolled: the frame loop's instruction footprint has to stay inside the 32 KB L1.5 I-cache
   for (int r = 0; r < GR + 4; ++r) {
     const unsigned lo = __ballot_sync(0xffffffffu, flag(bx0 - 2 + lane, y0 - 2 + r));
     const unsigned hi = ((r < 8 ? ex0 >> (4 * r) : ex1 >> (4 * (r - 8))) & 0xFu);
@@ -206,6 +206,11 @@ __global__ void __launch_bounds__(TW * NW, 6) k_fused_tma(const __grid_constant_
       tmap_acquire(tg);
       tma_load_2d((unsigned)__cvta_generic_to_shared(s_g[b]), tg, pq.sx0, pq.sy0, mb);
     }
+    if (q + 1 < nstaged) {       // the next copy uses other tensor maps (one per frame): start fetching them now
+      const int jn = s_list[q + 1];
+      tmap_prefetch(static_cast<const char *>(a.tmap_frames) + (size_t)jn * 128);
+      if (WEIGHTS) tmap_prefetch(static_cast<const char *>(a.tmap_weights) + (size_t)jn * 128);
+    }
   };
   if (threadIdx.x == 0) {
     if (nstaged > 0) issue(0, 0);
@@ -218,6 +223,11 @@ __global__ void __launch_bounds__(TW * NW, 6) k_fused_tma(const __grid_constant_
   const float xf = (float)min(x, a.cols - 1);            // lanes right of the image follow the last column (never stored)
   const float y0f = (float)y0;
   const bool patch_border = INTERP == SSK_INTER_CUBIC && !(a.border == SSK_BORDER_CONSTANT && a.bval[0] == 0.f);
+  // Map coefficients of the staged frames travel lane-wise: lane l holds c[l] of the NEXT staged frame (loaded while the
+  // current one is interpolated) and hands it to the warp by shuffles, so no global-memory latency sits at the head of a frame.
+  constexpr int NC = MT == MAP_TRANSLATION ? 2 : MT == MAP_AFFINE ? 6 : 7;
+  auto map_lane = [&](int jj) -> float { return lane < NC ? __ldg(&a.jobs[jj].map.c[lane]) : 0.f; };
+  float mlane = nstaged > 0 ? map_lane(s_list[0]) : 0.f;
   int q = 0;                                             // ordinal of the next staged frame
 #pragma unroll 1
   for (int j = 0; j < a.njobs; ++j) {
@@ -231,7 +241,11 @@ __global__ void __launch_bounds__(TW * NW, 6) k_fused_tma(const __grid_constant_
     }
     const int buf = q & 1;
     StagePlan plan; plan.staged = pp.staged; plan.sx0 = pp.sx0; plan.sy0 = pp.sy0; plan.sxw = pp.sxw;
-    const MapCoef m = a.jobs[j].map;
+    MapCoef m;
+    m.type = MT;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) m.c[i] = i < NC ? __shfl_sync(0xffffffffu, mlane, i) : 0.f;
+    if (q + 1 < nstaged) mlane = map_lane(s_list[q + 1]);
     unsigned okbits = 0xFFu;
     if (nrw > 0 && pp.staged == 1) okbits = warp_okbits<INTERP, MT>(m, bx0, y0, lane, a, tab.cubic_itab);   // overlaps the copy
     okbits &= (1u << nrow) - 1u;
@@ -253,7 +267,7 @@ __global__ void __launch_bounds__(TW * NW, 6) k_fused_tma(const __grid_constant_
       if (C2) {
         RollC2 R2;
         R2.ix = INT_MIN; R2.iy = INT_MIN; R2.pf = sf; R2.pw = sg;
-#pragma unroll
+#pragma unroll 1      // two rounds of four rows: half the code of the unrolled strip (I-cache), same window rotation
         for (int k = 0; k < GR; k += 4) {
           if (k < nrw) roll_pixel_c2<SSK_32F, MT, 0>(R2, cm, y0f + (float)k, sf, sg, a.scale, plan, cub_a, acc_a + k * TW * 4, w_a + k * TW * 4, (okbits >> k) & 1u);
           if (k + 1 < nrw) roll_pixel_c2<SSK_32F, MT, 1>(R2, cm, y0f + (float)(k + 1), sf, sg, a.scale, plan, cub_a, acc_a + (k + 1) * TW * 4, w_a + (k + 1) * TW * 4, (okbits >> (k + 1)) & 1u);

@@ -239,6 +239,13 @@ static int stack_alloc_slots(ssk_stack *h) {
   return SSK_OK;
 }
 
+// parts of the handle the multi-GPU combine works on (ssk_multi.cu)
+int stack_reduce_parts(ssk_stack *h, cudaStream_t *stream, ssk_acc **acc, int **d_counter) {
+  SSK_REQUIRE(h && h->have_reference, "ssk_stack_reduce: set_reference must be called first");
+  *stream = h->stream; *acc = &h->acc_h; *d_counter = h->counter.as<int>();
+  return SSK_OK;
+}
+
 extern "C" {
 
 void ssk_stack_options_default(ssk_stack_options *o) {
@@ -665,6 +672,21 @@ int ssk_stack_add_frames(ssk_stack *h, const ssk_mat *frames, int n, int bpp, ss
     if (int e = ssk_stack_wait(h, t, transforms_out ? transforms_out + i0 : nullptr, status_out ? status_out + i0 : nullptr, m, nullptr)) return e;
   }
   return ssk_stack_sync(h);
+}
+
+// Start of a new run over the same reference: the pipeline creates a fresh accumulator (create_frame_accumulation,
+// c_image_stacking_pipeline.cc:450-466); here the device accumulator and the frame counter are zeroed in stream order.
+int ssk_stack_reset(ssk_stack *h) {
+  SSK_REQUIRE(h && h->have_reference, "ssk_stack_reset: set_reference must be called first");
+  if (int e = ssk_stack_flush(h)) return e;
+  Acc &a = h->acc_h.a;
+  const size_t npix = (size_t)a.rows * a.cols;
+  const bool bayer = a.kind == SSK_ACC_BAYER_AVERAGE;
+  SSK_CUDA(cudaMemsetAsync(a.acc.p, 0, npix * (bayer ? 3 : a.cn) * 4, h->stream));
+  SSK_CUDA(cudaMemsetAsync(a.wacc.p, 0, npix * (bayer ? 3 : 1) * 4, h->stream));
+  SSK_CUDA(cudaMemsetAsync(h->counter.p, 0, sizeof(int), h->stream));
+  a.frames = 0;
+  return SSK_OK;
 }
 
 int ssk_stack_compute(ssk_stack *h, ssk_mat *avg, ssk_mat *mask) {
