@@ -170,6 +170,12 @@ __global__ void __launch_bounds__(TW * NW, 6) k_fused_tma(const __grid_constant_
       pp.sx0 = (short)p.sx0; pp.sy0 = (short)p.sy0; pp.sxw = (short)p.sxw; pp.staged = (short)p.staged;
     }
     s_plan[jj] = pp;
+    // The tensor maps live in global memory and are rewritten by the host between launches: one acquire fence per CTA
+    // and map before its first use (the CTA barrier below orders it before the copies any thread issues later)
+    if (pp.staged > 0) {
+      tmap_acquire(static_cast<const char *>(a.tmap_frames) + (size_t)jj * 128);
+      if (WEIGHTS) tmap_acquire(static_cast<const char *>(a.tmap_weights) + (size_t)jj * 128);
+    }
   }
   const unsigned full0 = (unsigned)__cvta_generic_to_shared(&s_full[0]);
   if (threadIdx.x == 0) {
@@ -198,12 +204,10 @@ __global__ void __launch_bounds__(TW * NW, 6) k_fused_tma(const __grid_constant_
     const PackedPlan pq = s_plan[jq];
     const unsigned mb = full0 + 8 * b;
     const char *tf = static_cast<const char *>(a.tmap_frames) + (size_t)jq * 128;
-    tmap_acquire(tf);
     mbar_expect_tx(mb, WEIGHTS ? 2 * WIN_BYTES : WIN_BYTES);
     tma_load_2d((unsigned)__cvta_generic_to_shared(s_f[b]), tf, pq.sx0, pq.sy0, mb);
     if (WEIGHTS) {
       const char *tg = static_cast<const char *>(a.tmap_weights) + (size_t)jq * 128;
-      tmap_acquire(tg);
       tma_load_2d((unsigned)__cvta_generic_to_shared(s_g[b]), tg, pq.sx0, pq.sy0, mb);
     }
     if (q + 1 < nstaged) {       // the next copy uses other tensor maps (one per frame): start fetching them now
@@ -267,12 +271,22 @@ __global__ void __launch_bounds__(TW * NW, 6) k_fused_tma(const __grid_constant_
       if (C2) {
         RollC2 R2;
         R2.ix = INT_MIN; R2.iy = INT_MIN; R2.pf = sf; R2.pw = sg;
-#pragma unroll 1      // two rounds of four rows: half the code of the unrolled strip (I-cache), same window rotation
-        for (int k = 0; k < GR; k += 4) {
-          if (k < nrw) roll_pixel_c2<SSK_32F, MT, 0>(R2, cm, y0f + (float)k, sf, sg, a.scale, plan, cub_a, acc_a + k * TW * 4, w_a + k * TW * 4, (okbits >> k) & 1u);
-          if (k + 1 < nrw) roll_pixel_c2<SSK_32F, MT, 1>(R2, cm, y0f + (float)(k + 1), sf, sg, a.scale, plan, cub_a, acc_a + (k + 1) * TW * 4, w_a + (k + 1) * TW * 4, (okbits >> (k + 1)) & 1u);
-          if (k + 2 < nrw) roll_pixel_c2<SSK_32F, MT, 2>(R2, cm, y0f + (float)(k + 2), sf, sg, a.scale, plan, cub_a, acc_a + (k + 2) * TW * 4, w_a + (k + 2) * TW * 4, (okbits >> (k + 2)) & 1u);
-          if (k + 3 < nrw) roll_pixel_c2<SSK_32F, MT, 3>(R2, cm, y0f + (float)(k + 3), sf, sg, a.scale, plan, cub_a, acc_a + (k + 3) * TW * 4, w_a + (k + 3) * TW * 4, (okbits >> (k + 3)) & 1u);
+        if (nrw == GR) {
+          // complete strip: straight-line code, row offsets are immediates
+#pragma unroll
+          for (int k = 0; k < GR; k += 4) {
+            roll_pixel_c2<SSK_32F, MT, 0>(R2, cm, y0f + (float)k, sf, sg, a.scale, plan, cub_a, acc_a + k * TW * 4, w_a + k * TW * 4, (okbits >> k) & 1u);
+            roll_pixel_c2<SSK_32F, MT, 1>(R2, cm, y0f + (float)(k + 1), sf, sg, a.scale, plan, cub_a, acc_a + (k + 1) * TW * 4, w_a + (k + 1) * TW * 4, (okbits >> (k + 1)) & 1u);
+            roll_pixel_c2<SSK_32F, MT, 2>(R2, cm, y0f + (float)(k + 2), sf, sg, a.scale, plan, cub_a, acc_a + (k + 2) * TW * 4, w_a + (k + 2) * TW * 4, (okbits >> (k + 2)) & 1u);
+            roll_pixel_c2<SSK_32F, MT, 3>(R2, cm, y0f + (float)(k + 3), sf, sg, a.scale, plan, cub_a, acc_a + (k + 3) * TW * 4, w_a + (k + 3) * TW * 4, (okbits >> (k + 3)) & 1u);
+          }
+        } else {
+          // strip cut by the bottom edge of the image (last tile row only): one row at a time, window re-anchored per row
+#pragma unroll 1
+          for (int k = 0; k < nrw; ++k) {
+            R2.ix = INT_MIN;
+            roll_pixel_c2<SSK_32F, MT, 0>(R2, cm, y0f + (float)k, sf, sg, a.scale, plan, cub_a, acc_a + k * TW * 4, w_a + k * TW * 4, (okbits >> k) & 1u);
+          }
         }
       } else {
         RollS<INTERP> R;
