@@ -82,7 +82,7 @@ class c_ecch:
         self.status = ssk_ecc_status()
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and capi is not None:
             capi.lib.ssk_ecch_destroy(self._h)
             self._h = None
 
@@ -159,7 +159,7 @@ class c_frame_registration:
         self._ref_shape = None
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and capi is not None:
             capi.lib.ssk_reg_destroy(self._h)
             self._h = None
 
@@ -215,7 +215,7 @@ class c_frame_accumulation:
             self._h = C.c_void_p(handle)
 
     def __del__(self):
-        if getattr(self, "_own", False) and getattr(self, "_h", None):
+        if getattr(self, "_own", False) and getattr(self, "_h", None) and capi is not None:
             capi.lib.ssk_acc_destroy(self._h)
             self._h = None
 
@@ -388,7 +388,7 @@ class c_image_stacking_pipeline:
         self._shape = None
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and capi is not None:
             capi.lib.ssk_stack_destroy(self._h)
             self._h = None
 

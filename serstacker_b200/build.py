@@ -9,8 +9,10 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libssk.so")
+# SSK_BUILD_TAG=<tag> (with SSK_NVCC_EXTRA=-D...): a side build of the same ABI into libssk_<tag>.so for A/B runs (SSK_LIB selects it)
+TAG = os.environ.get("SSK_BUILD_TAG", "")
+OBJ = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
+LIB = os.path.join(HERE, "libssk" + ("_" + TAG if TAG else "") + ".so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17"] + os.environ.get("SSK_NVCC_EXTRA", "").split() + [
          "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden"]

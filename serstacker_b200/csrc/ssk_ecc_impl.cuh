@@ -40,6 +40,11 @@ constexpr int NW = NT / 32;
 constexpr int NSMAX = 72;
 constexpr int FT_W = 32, FT_H = NT / 32;     // stencil tile of the forward methods (one pixel per thread)
 constexpr int FT_IW = FT_W + 4, FT_IH = FT_H + 4;
+// tiled inverse-compositional pass: a CTA walks its band of the level in tiles of TL_W x TL_H pixels (NT threads, two
+// rows per thread); the bilinear taps of a tile come from a TL_WW x TL_WH window of the current image staged in smem
+constexpr int TL_W = 64, TL_H = 2 * (NT / TL_W);
+constexpr int TL_WW = TL_W + 8, TL_WH = TL_H + 4;
+constexpr int TL_LD = (TL_WW * TL_WH + NT - 1) / NT;     // window elements per thread
 
 template <int TYPE> struct NParams;
 template <> struct NParams<SSK_MOTION_TRANSLATION> { static constexpr int M = 2; };
@@ -66,6 +71,8 @@ struct Shared {
   double tot[NSMAX];          // cluster totals
   double wpart[NW][NSMAX];
   float gw[FT_IH][FT_IW + 1]; // warped-image tile of the forward methods
+  float win[2][TL_WH][TL_WW]; // staged windows of the current image (tiled inverse-compositional pass), double buffered
+  int4 tw[2];                 // their origins: {ox, oy, fits, -}
   // ---- solver state: identical in every CTA of the cluster ----
   ssk_transform t;            // transform being estimated (accepted parameters)
   ssk_transform tq;           // parameters of the next pass
@@ -82,6 +89,10 @@ struct Shared {
   int num_it, recompute, brk, converged, failed, level_ok, cont;
   int total_iterations;
   double rho;
+  // compute_correlation sums [n, Sf, Sg, Sf2, Sg2, Sfg] gathered by the level-0 passes of the IC-LM solver at the
+  // parameters of the last pass (rho_try) and at the accepted parameters (rho_acc); rho_have: rho_acc belongs to S.t
+  double rho_try[6], rho_acc[6];
+  int rho_have;
 };
 
 struct Ctx {
@@ -456,6 +467,10 @@ struct Walk {
 // [r * chunk, (r + 1) * chunk) and walks it NT pixels at a time, so that the source row a bilinear tap pair touches for
 // output row y is still in L1 when row y + 1 needs it (the interleaved assignment sent consecutive rows to different
 // SMs).  The order of the per-thread partial sums changes with it, their fixed-order double reduction does not.
+#ifndef SSK_ECC_RHO_FUSION
+#define SSK_ECC_RHO_FUSION 0
+#endif
+__device__ __forceinline__ bool getenv_no_rho_fusion() { return !SSK_ECC_RHO_FUSION; }
 #ifndef SSK_ECC_BANDS
 #define SSK_ECC_BANDS 1
 #endif
@@ -554,10 +569,15 @@ __device__ __forceinline__ float lin_sample(const float *__restrict__ p, int col
 //                     coordinate falls outside the current image (no user current mask)
 //   lm_masks = false: ecc_remap (ecc2.cc:178-219): bilinear remap of the all-255 mask >= 250
 // ------------------------------------------------------------------------------------------------
-template <int TYPE>
+//   RHO = true (level 0 of the IC-LM solver when the registration checks the correlation afterwards): the same pass also
+//   gathers compute_correlation's sums (ecc2.cc:65-137) for its map - the bilinear sample is the one the residual uses,
+//   only the validity rule differs (remap(255) >= 254, i.e. lin_valid) - so that the separate correlation pass over
+//   level 0 is not needed when the solver ends on parameters it has evaluated (it always does).
+template <int TYPE, bool RHO>
 __device__ void pass_ic(Ctx &c, int lvl, bool lm_masks) {
   constexpr int M = NParams<TYPE>::M;
-  constexpr int NS = 2 + M;
+  constexpr int NS = 2 + M + (RHO ? 6 : 0);
+  constexpr int OR = 2 + M;            // offset of the correlation sums
   Shared &S = *c.S;
   const EccLevel &L = c.cfg->lv[lvl];
   const float *__restrict__ cur = opaque_ptr(c.frame->pyr + L.cur_off);
@@ -571,13 +591,17 @@ __device__ void pass_ic(Ctx &c, int lvl, bool lm_masks) {
   double acc[NS];   // Mat::dot / norm accumulate in double
 #pragma unroll
   for (int k = 0; k < NS; ++k) acc[k] = 0.0;
-  int nvalid = 0;
+  int nvalid = 0, nrho = 0;
+  const uint8_t *__restrict__ rho_mask = RHO ? L.refmask : nullptr;
   const int n = cols * rows;
   // Branch-free body (invalid pixels contribute an exact 0.0), so that several pixels per thread are in flight.
   const Band bd = pass_band(c.rank, c.csize, c.tid, n);
   Walk w(bd.start, bd.stride, cols);
   const float hx = nearest_hi(cols), hy = nearest_hi(rows);
-  constexpr int kUnroll = 3;   // pixels in flight per thread (measured: 2 -> 3 is -4 % on the pass, 4 is slower)
+#ifndef SSK_ECC_UNROLL_RHO
+#define SSK_ECC_UNROLL_RHO 3
+#endif
+  constexpr int kUnroll = RHO ? SSK_ECC_UNROLL_RHO : 3;   // pixels in flight per thread (measured: 2 -> 3 is -4 % on the pass, 4 is slower)
 #pragma unroll kUnroll
   for (; w.i < bd.end; w.next()) {
     const float x = (float)w.x, y = (float)w.y;
@@ -593,7 +617,15 @@ __device__ void pass_ic(Ctx &c, int lvl, bool lm_masks) {
     else ok = lin_valid(sx, sy, cols, rows);
     if (rmask) ok = ok && rmask[w.i] != 0;
     const float g = lin_sample(cur, cols, rows, sx, sy);
-    const float rhs = g - __ldg(ref + w.i);
+    const float fref = __ldg(ref + w.i);
+    const float rhs = g - fref;
+    if (RHO) {
+      bool okr = lin_valid(sx, sy, cols, rows);
+      if (rho_mask) okr = okr && rho_mask[w.i] != 0;
+      const double gd = okr ? (double)g : 0.0, fd = okr ? (double)fref : 0.0;
+      nrho += okr ? 1 : 0;
+      acc[OR + 1] += fd; acc[OR + 2] += gd; acc[OR + 3] += fd * fd; acc[OR + 4] += gd * gd; acc[OR + 5] += fd * gd;
+    }
     float J[M];
     eval_J<TYPE>(jc, x, y, __ldg(gxp + w.i), __ldg(gyp + w.i), J);
     if (TYPE == SSK_MOTION_HOMOGRAPHY) {   // J may be non-finite at a vanishing denominator: keep the branch
@@ -612,7 +644,186 @@ __device__ void pass_ic(Ctx &c, int lvl, bool lm_masks) {
     }
   }
   acc[1] = (double)nvalid;
+  if (RHO) acc[OR] = (double)nrho;
   cluster_reduce<NS>(c, acc);
+  if (RHO) {
+    if (c.tid < 6) c.S->rho_try[c.tid] = c.S->tot[OR + c.tid];
+    __syncthreads();
+  }
+}
+
+// Tiled form of pass_ic (same sums, same per-pixel arithmetic): the level is cut into row bands, one per CTA of the
+// cluster, and each band into TL_W x TL_H tiles.  The four bilinear taps of a pixel are read from a window of the
+// current image staged in shared memory instead of four gathers that wait on L2: the window of tile t + 1 (loaded with
+// the tap coordinates clamped to the image = lin_sample's replicate rule) and the reference / gradient samples of the
+// thread's own two pixels travel in registers while tile t is evaluated, one CTA barrier per tile.  The window origin
+// follows the map at the tile corners (affine-like maps are monotone along both axes); a tile whose footprint does
+// not fit the window (large rotation or scale) falls back to the direct gathers.
+template <int TYPE, bool RHO>
+__device__ void pass_ic_tiled(Ctx &c, int lvl, bool lm_masks) {
+  constexpr int M = NParams<TYPE>::M;
+  constexpr int NS = 2 + M + (RHO ? 6 : 0);
+  constexpr int OR = 2 + M;
+  constexpr int MT = MapKind<TYPE>::MT;
+  Shared &S = *c.S;
+  const EccLevel &L = c.cfg->lv[lvl];
+  const float *__restrict__ cur = opaque_ptr(c.frame->pyr + L.cur_off);
+  const float *__restrict__ ref = L.ref, *__restrict__ gxp = L.gx, *__restrict__ gyp = L.gy;
+  const uint8_t *__restrict__ rmask = lm_masks ? L.refmask : nullptr;
+  const uint8_t *__restrict__ rho_mask = RHO ? L.refmask : nullptr;
+  const int cols = L.cols, rows = L.rows;
+  const MapCoef m = S.map;
+  const JCoef jc = S.jc;
+  double acc[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) acc[k] = 0.0;
+  int nvalid = 0, nrho = 0;
+  const float hx = nearest_hi(cols), hy = nearest_hi(rows);
+  // band of tile rows of this CTA
+  const int ntx = (cols + TL_W - 1) / TL_W, nty = (rows + TL_H - 1) / TL_H;
+  const int per = (nty + c.csize - 1) / c.csize;
+  const int ty0 = min(nty, c.rank * per), ty1 = min(nty, ty0 + per);
+  const int ntiles = (ty1 - ty0) * ntx;
+  const int tx = c.tid & (TL_W - 1), tq = c.tid / TL_W;
+  const int lane = c.tid & 31, warp = c.tid >> 5;
+
+  // window origin of tile t, by the first four lanes of warp 0 (one tile corner each)
+  auto plan_tile = [&](int t, int slot) {
+    if (warp != 0) return;
+    const int x0 = (t % ntx) * TL_W, y0 = (ty0 + t / ntx) * TL_H;
+    const int x1 = min(x0 + TL_W - 1, cols - 1), y1 = min(y0 + TL_H - 1, rows - 1);
+    float u, v;
+    map_xy_t<MT>(m, (float)((lane & 1) ? x1 : x0), (float)((lane & 2) ? y1 : y0), u, v);
+    float umin = u, umax = u, vmin = v, vmax = v;
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      umin = fminf(umin, __shfl_xor_sync(0xffffffffu, umin, o)); umax = fmaxf(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+      vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o)); vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    if (lane == 0) {
+      // taps of a pixel: columns ix, ix + 1 with floor(u) <= ix <= floor(u) + 1 (1/32-px rounding), likewise rows
+      const bool finite = umin > -1.0e8f && vmin > -1.0e8f && umax < 1.0e8f && vmax < 1.0e8f;
+      const int ox = finite ? (int)floorf(umin) : 0, oy = finite ? (int)floorf(vmin) : 0;
+      const bool fits = MT != MAP_HOMOGRAPHY && finite && (int)floorf(umax) + 2 - ox < TL_WW && (int)floorf(vmax) + 2 - oy < TL_WH;
+      S.tw[slot] = make_int4(ox, oy, fits ? 1 : 0, 0);
+    }
+  };
+  float wreg[TL_LD];                 // window elements of the next tile
+  float pf[2], pgx[2], pgy[2];       // reference / gradient samples of this thread's pixels of the next tile
+  auto prefetch_tile = [&](int t, const int4 w) {
+    const int x0 = (t % ntx) * TL_W, y0 = (ty0 + t / ntx) * TL_H;
+    if (w.z) {
+#pragma unroll
+      for (int i = 0; i < TL_LD; ++i) {
+        const int e = c.tid + i * NT;
+        const int r = e / TL_WW, q = e - r * TL_WW;
+        const int gy_ = min(max(w.y + r, 0), rows - 1), gx_ = min(max(w.x + q, 0), cols - 1);
+        wreg[i] = e < TL_WW * TL_WH ? __ldg(cur + ((unsigned)(gy_ * cols) + (unsigned)gx_)) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int x = min(x0 + tx, cols - 1), y = min(y0 + tq + k * (TL_H / 2), rows - 1);
+      const unsigned i = (unsigned)(y * cols) + (unsigned)x;
+      pf[k] = __ldg(ref + i); pgx[k] = __ldg(gxp + i); pgy[k] = __ldg(gyp + i);
+    }
+  };
+
+  if (ntiles > 0) plan_tile(0, 0);
+  __syncthreads();
+  int4 wnext = S.tw[0];
+  if (ntiles > 0) prefetch_tile(0, wnext);
+#pragma unroll 1
+  for (int t = 0; t < ntiles; ++t) {
+    const int b = t & 1;
+    const int4 w = wnext;
+    if (w.z) {
+#pragma unroll
+      for (int i = 0; i < TL_LD; ++i) {
+        const int e = c.tid + i * NT;
+        if (e < TL_WW * TL_WH) (&S.win[b][0][0])[e] = wreg[i];
+      }
+    }
+    const float f0 = pf[0], f1 = pf[1], gx0 = pgx[0], gx1 = pgx[1], gy0 = pgy[0], gy1 = pgy[1];
+    if (t + 1 < ntiles) plan_tile(t + 1, b ^ 1);
+    __syncthreads();                       // window of tile t and the origin of tile t + 1 are visible
+    if (t + 1 < ntiles) { wnext = S.tw[b ^ 1]; prefetch_tile(t + 1, wnext); }
+    const int x0 = (t % ntx) * TL_W, y0 = (ty0 + t / ntx) * TL_H;
+    const int xi = x0 + tx;
+    const float x = (float)min(xi, cols - 1);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int yi = y0 + tq + k * (TL_H / 2);
+      const bool inb = xi < cols && yi < rows;
+      const float y = (float)min(yi, rows - 1);
+      float u, v;
+      map_xy_t<MT>(m, x, y, u, v);
+      const int sx = cvround32(u), sy = cvround32(v);
+      bool ok;
+      if (lm_masks) ok = u >= -0.5f && u <= hx && v >= -0.5f && v <= hy;   // cvRound(u), cvRound(v) inside the image
+      else ok = lin_valid(sx, sy, cols, rows);
+      const unsigned pi = (unsigned)(min(yi, rows - 1) * cols) + (unsigned)min(xi, cols - 1);
+      if (rmask) ok = ok && rmask[pi] != 0;
+      ok = ok && inb;
+      float g;
+      if (w.z) {
+        const int wx = (sx >> 5) - w.x, wy = (sy >> 5) - w.y;
+        const float txf = frac32(sx), tyf = frac32(sy);
+        const float wx0 = 1.0f - txf, wy0 = 1.0f - tyf;
+        const float *p0 = &S.win[b][wy][wx];
+        const float s00 = p0[0], s01 = p0[1], s10 = p0[TL_WW], s11 = p0[TL_WW + 1];
+        g = __fadd_rn(__fmul_rn(s00, __fmul_rn(wy0, wx0)), __fmul_rn(s01, __fmul_rn(wy0, txf)));
+        g = __fadd_rn(g, __fmul_rn(s10, __fmul_rn(tyf, wx0)));
+        g = __fadd_rn(g, __fmul_rn(s11, __fmul_rn(tyf, txf)));
+      } else {
+        g = lin_sample(cur, cols, rows, sx, sy);
+      }
+      const float fref = k ? f1 : f0;
+      const float rhs = g - fref;
+      if (RHO) {
+        bool okr = lin_valid(sx, sy, cols, rows) && inb;
+        if (rho_mask) okr = okr && rho_mask[pi] != 0;
+        const double gd = okr ? (double)g : 0.0, fd = okr ? (double)fref : 0.0;
+        nrho += okr ? 1 : 0;
+        acc[OR + 1] += fd; acc[OR + 2] += gd; acc[OR + 3] += fd * fd; acc[OR + 4] += gd * gd; acc[OR + 5] += fd * gd;
+      }
+      float J[M];
+      eval_J<TYPE>(jc, x, y, k ? gx1 : gx0, k ? gy1 : gy0, J);
+      if (TYPE == SSK_MOTION_HOMOGRAPHY) {
+        if (ok) {
+          acc[0] += (double)rhs * (double)rhs;
+          ++nvalid;
+#pragma unroll
+          for (int q = 0; q < M; ++q) acc[2 + q] += (double)J[q] * (double)rhs;
+        }
+      } else {
+        const double r = ok ? (double)rhs : 0.0;
+        acc[0] += r * r;
+        nvalid += ok ? 1 : 0;
+#pragma unroll
+        for (int q = 0; q < M; ++q) acc[2 + q] += (double)J[q] * r;
+      }
+    }
+  }
+  acc[1] = (double)nvalid;
+  if (RHO) acc[OR] = (double)nrho;
+  cluster_reduce<NS>(c, acc);
+  if (RHO) {
+    if (c.tid < 6) c.S->rho_try[c.tid] = c.S->tot[OR + c.tid];
+    __syncthreads();
+  }
+}
+
+// Measured on B200 (config #2, 128 frames): 5.15 ms against 2.89 ms for the gather form - staging the window with
+// ordinary loads costs as many instructions per element (clamps, address arithmetic, STS) as the four gathers it
+// replaces, and adds a CTA barrier per 512 pixels.  Kept for reference / as the base of a TMA-staged form; off.
+#ifndef SSK_ECC_TILED
+#define SSK_ECC_TILED 0
+#endif
+template <int TYPE, bool RHO>
+__device__ __forceinline__ void pass_ic_any(Ctx &c, int lvl, bool lm_masks) {
+  if (SSK_ECC_TILED && TYPE != SSK_MOTION_HOMOGRAPHY) pass_ic_tiled<TYPE, RHO>(c, lvl, lm_masks);
+  else pass_ic<TYPE, RHO>(c, lvl, lm_masks);
 }
 
 // reference-side normal matrix Hp = J^T J (ecc_compute_hessian_matrix, ecc2.cc:295-322): sums = lower triangle
@@ -856,17 +1067,21 @@ __device__ bool align_iclm(Ctx &c, int lvl, double max_eps, bool main_pass) {
   const EccConfig &cfg = *c.cfg;
   const EccLevel &L = cfg.lv[lvl];
   prepare_ic_level<TYPE>(c, lvl, main_pass);
+  // the correlation gate that follows the alignment (c_frame_registration.cc:838, 861) reads level 0 at the final parameters
+  const bool with_rho = lvl == 0 && (main_pass ? cfg.check_rho != 0 : true) && !getenv_no_rho_fusion();
   T0_BEGIN
   S.lambda = 0.001; S.dp = 0; S.recompute = 1; S.num_it = 0; S.eps = FLT_MAX; S.err = 0; S.newerr = 0;
+  if (lvl == 0) S.rho_have = 0;
   T0_END
   while (S.num_it < cfg.max_iterations) {
     if (S.recompute) {
       T0_BEGIN set_pass_params(S, S.t); T0_END
-      pass_ic<TYPE>(c, lvl, true);
+      if (with_rho) pass_ic_any<TYPE, true>(c, lvl, true); else pass_ic_any<TYPE, false>(c, lvl, true);
       T0_BEGIN
       const double CMA = S.tot[1], RMA = L.RMA;
       S.err = S.tot[0] * (RMA * RMA) / (CMA * CMA);
       for (int i = 0; i < M; ++i) S.v[i] = __fmul_rn((float)S.tot[2 + i], (float)(RMA / CMA));
+      if (with_rho) { for (int i = 0; i < 6; ++i) S.rho_acc[i] = S.rho_try[i]; S.rho_have = 1; }
       T0_END
     }
     do {
@@ -883,7 +1098,7 @@ __device__ bool align_iclm(Ctx &c, int lvl, double max_eps, bool main_pass) {
       for (int i = 0; i < M; ++i) q.params[i] = np[i];
       set_pass_params(S, q);
       T0_END
-      pass_ic<TYPE>(c, lvl, true);
+      if (with_rho) pass_ic_any<TYPE, true>(c, lvl, true); else pass_ic_any<TYPE, false>(c, lvl, true);
       T0_BEGIN
       const double CMA = S.tot[1], RMA = L.RMA;
       S.newerr = S.tot[0] * (RMA * RMA) / (CMA * CMA);
@@ -917,6 +1132,7 @@ __device__ bool align_iclm(Ctx &c, int lvl, double max_eps, bool main_pass) {
       S.err = S.newerr;
       S.recompute = 0;
       for (int i = 0; i < M; ++i) { S.t.params[i] = S.tq.params[i]; S.v[i] = S.vtrial[i]; }
+      if (with_rho) { for (int i = 0; i < 6; ++i) S.rho_acc[i] = S.rho_try[i]; }   // sums of the pass that evaluated tq
     }
     T0_END
     if (S.dp < max_eps) break;
@@ -941,7 +1157,7 @@ __device__ bool align_ic(Ctx &c, int lvl, double max_eps, bool main_pass) {
     if (S.cont) set_pass_params(S, S.t);
     T0_END
     if (!S.cont) break;
-    pass_ic<TYPE>(c, lvl, false);
+    pass_ic_any<TYPE, false>(c, lvl, false);
     T0_BEGIN
     const double CMA = S.tot[1], RMA = L.RMA;
     const double rmsnew = S.tot[0] * (RMA * RMA) / (CMA * CMA);
@@ -1153,6 +1369,10 @@ __device__ void ecch_align(Ctx &c, bool main_pass) {
 template <int MT>
 __device__ double correlation(Ctx &c) {
   Shared &S = *c.S;
+  if (S.rho_have) {       // level 0 was last evaluated at S.t by a pass that gathered these sums (align_iclm)
+    T0_BEGIN S.rho = rho_from_sums(S.rho_acc); S.rho_have = 0; T0_END
+    return S.rho;
+  }
   T0_BEGIN set_pass_params(S, S.t); T0_END
   pass_rho<MT>(c);
   T0_BEGIN S.rho = rho_from_sums(S.tot); T0_END
@@ -1175,7 +1395,7 @@ __global__ void __launch_bounds__(NT, SSK_ECC_MINB) k_ecc(const __grid_constant_
 
   T0_BEGIN
   S.t = fr->t;
-  S.failed = 0; S.rho = -1; S.eps = FLT_MAX; S.total_iterations = 0;
+  S.failed = 0; S.rho = -1; S.eps = FLT_MAX; S.total_iterations = 0; S.rho_have = 0;
   for (int i = 0; i < 8; ++i) S.jc.c[i] = 0.f;
   T0_END
 
