@@ -286,6 +286,36 @@ SSK_API int ssk_gaussian_blur(const ssk_mat *src, double sigma_x, double sigma_y
  * ------------------------------------------------------------------------------------------- */
 SSK_API int ssk_debayer_nn2(const ssk_mat *src, ssk_mat *dst, int colorid);
 
+/* average_bayer_planes(src, dst) (core/io/debayer.cc:277-376), raw single-channel form: one sample per 2x2 Bayer cell,
+ * (2 + s00 + s01 + s10 + s11) / 4 in integer arithmetic (float: the plain mean).  The gray proxy select_master_frame ranks
+ * for raw Bayer sequences (c_image_stacking_pipeline_base.cc:370-378).  dst: half the size, same type. */
+SSK_API int ssk_average_bayer_planes(const ssk_mat *src, ssk_mat *dst);
+/* read_input_frame's dark / flat correction (c_image_stacking_pipeline_base.cc:143-184): dst = (float(frame) / (1 << bpp) - dark)
+ * / flat, either of dark / flat may be NULL; dark, flat and dst are CV_32F of the frame's size and channel count. */
+SSK_API int ssk_input_calibrate(const ssk_mat *frame, int bpp, const ssk_mat *dark, const ssk_mat *flat, ssk_mat *dst);
+/* cv::transform(image, image, color_matrix) of read_input_frame (c_image_stacking_pipeline_base.cc:263-266): CV_32FC3 image,
+ * row-major 3 x mcols float matrix (mcols 3 or 4). */
+SSK_API int ssk_color_transform(const ssk_mat *src, const float *m, int mcols, ssk_mat *dst);
+/* linear_interpolation_inpaint(src, mask, dst) (core/proc/inpaint/linear_interpolation_inpaint.cc:327-368): holes (mask == 0)
+ * are filled by the distance-weighted mix of the linear interpolations along their row and their column; applied to the
+ * generated master frame (c_image_stacking_pipeline.cc:1282-1284) and to input frames with a missing-pixel mask
+ * (c_image_stacking_pipeline_base.cc:258-261).  CV_32F, 1 to 4 channels; mask CV_8UC1 or NULL (plain copy). */
+SSK_API int ssk_linear_interpolation_inpaint(const ssk_mat *src, const ssk_mat *mask, ssk_mat *dst);
+
+/* ---------------------------------------------------------------------------------------------
+ * SER container (c_ser_reader, core/io/c_ser_file.cc:272-531; 178-byte header c_ser_file.h:42-56, frames back to back,
+ * optional trailer of uint64 time stamps; the stored endianness flag is inverted, c_ser_file.cc:305).  Host side.
+ * type: OpenCV type code of a frame (CV_8U / CV_16U / CV_32F for bits_per_plane 1..8 / 9..16 / -32; 3 channels for RGB / BGR).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ssk_ser ssk_ser;
+SSK_API int ssk_ser_open(const char *path, ssk_ser **out);
+SSK_API int ssk_ser_close(ssk_ser *s);
+SSK_API int ssk_ser_info(const ssk_ser *s, int *cols, int *rows, int *type, int *bits_per_plane, int *color_id, int *frames,
+                         int *has_timestamps);
+/* c_ser_reader::seek + read: frame `frame_index` into a host image of the file's size and type (pinned memory lets
+ * ssk_stack_submit upload it asynchronously); *timestamp: the frame's trailer entry (0 without a trailer), may be NULL. */
+SSK_API int ssk_ser_read(ssk_ser *s, int frame_index, ssk_mat *dst, uint64_t *timestamp);
+
 /* ---------------------------------------------------------------------------------------------
  * unsharp_mask(src, dst, sigma, alpha, outmin, outmax) (core/proc/unsharp_mask.cc:72-118): the sharpening applied to the
  * master / reference frame before registration (c_image_stacking_pipeline.cc:1302-1306; defaults sigma 1, alpha 0.8).
@@ -343,6 +373,8 @@ typedef struct ssk_stack_options {
   int32_t enable_registration;               /* c_image_stacking_options::enable_registration */
   int32_t bayer_colorid;                     /* for SSK_STACK_BAYER_AVERAGE */
   int32_t max_batch;                         /* frames in flight per call (device scratch is sized for it) */
+  int32_t generating_master_frame;           /* the master-frame pass (create_reference_frame): frames are remapped with
+                                                ECC_BORDER_REFLECT101 instead of registration.border_mode (c_image_stacking_pipeline.cc:1644-1651) */
 } ssk_stack_options;
 
 typedef struct ssk_stack ssk_stack;

@@ -103,3 +103,14 @@ def debayer_nn2_rggb_literal(raw):
                       s1[x + 1], d4(s0[x + 1], s1[x], s1[x], s2[x + 1]), d4(s0[x], s0[x], s2[x], s2[x])]
         dst[y1] = np.array(o, dtype=raw.dtype).reshape(W, 3)
     return dst
+
+
+def average_bayer_planes(raw):
+    """average_bayer_planes, raw single-channel form (core/io/debayer.cc:277-328): (c1 + s00 + s01 + s10 + s11) / 4 per 2x2 cell,
+    c1 = 2 with integer division for integer samples, float arithmetic in that order otherwise."""
+    a, b, c, d = raw[0::2, 0::2], raw[0::2, 1::2], raw[1::2, 0::2], raw[1::2, 1::2]
+    if raw.dtype == np.float32:
+        f = np.float32
+        return ((((f(0) + a) + b) + c) + d) / f(4)
+    s = (2 + a.astype(np.int64) + b + c + d) // 4
+    return s.astype(raw.dtype)

@@ -102,3 +102,73 @@ def box_sum_model(a):
         r = p[dy:dy + rows, 0:cols] + p[dy:dy + rows, 1:cols + 1] + p[dy:dy + rows, 2:cols + 2]
         s = s + r
     return s.astype(f32)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# linear_interpolation_inpaint (core/proc/inpaint/linear_interpolation_inpaint.cc:14-368): what create_reference_frame
+# applies to the generated master frame (c_image_stacking_pipeline.cc:1282-1284) and read_input_frame to frames with a
+# missing-pixel mask (c_image_stacking_pipeline_base.cc:258-261).
+# ---------------------------------------------------------------------------------------------------------
+def _interpolate_holes_1d(image, mask):
+    """_interpolate_holes_h2 (:14-117) along axis 1 of image (H x W x C float32) -> (inpaint, dists).
+    Every run of holes [start, end) of a row is filled from its neighbours s = start - 1, e = end:
+      both sides:   sv + (x - s) * kk with kk = (ev - sv) * (1 / (end - start)),  dist = max(x - s, e - x)
+      left only:    sv, dist = x - s;     right only:  ev, dist = e - x;     neither: untouched, dist = 0."""
+    h, w = mask.shape
+    valid = mask != 0
+    idx = np.arange(w, dtype=np.int64)[None, :]
+    left = np.maximum.accumulate(np.where(valid, idx, -1), axis=1)               # nearest valid column <= x
+    right = np.minimum.accumulate(np.where(valid, idx, w)[:, ::-1], axis=1)[:, ::-1]   # nearest valid column >= x
+    hole = ~valid
+    has_l, has_r = hole & (left >= 0), hole & (right < w)
+    ls, rs = np.clip(left, 0, w - 1), np.clip(right, 0, w - 1)
+    rows = np.arange(h)[:, None]
+    sv, ev = image[rows, ls], image[rows, rs]
+    x = np.broadcast_to(idx, (h, w))
+    scale = (f32(1.0) / (right - left - 1).clip(1).astype(f32)).astype(f32)       # 1.0f / (end - start)
+    kk = ((ev - sv) * scale[..., None]).astype(f32)
+    factor = (x - left).astype(f32)
+    both = has_l & has_r
+    out = image.copy()
+    val_both = (sv + (factor[..., None] * kk).astype(f32)).astype(f32)
+    out[both] = val_both[both]
+    only_l, only_r = has_l & ~has_r, has_r & ~has_l
+    out[only_l] = sv[only_l]
+    out[only_r] = ev[only_r]
+    dist = np.zeros((h, w), dtype=f32)
+    dist[both] = np.maximum(x - left, right - x)[both].astype(f32)
+    dist[only_l] = (x - left)[only_l].astype(f32)
+    dist[only_r] = (right - x)[only_r].astype(f32)
+    return out, dist
+
+
+def linear_interpolation_inpaint(image, mask):
+    """linear_interpolation_inpaint(src, mask, dst) (:327-368) on CV_32F images -> filled copy of `image`."""
+    img = np.ascontiguousarray(image, dtype=f32)
+    squeeze = img.ndim == 2
+    if squeeze:
+        img = img[..., None]
+    img = img.copy()
+    if mask is None:
+        return img[..., 0] if squeeze else img
+    m = np.ascontiguousarray(mask).copy()
+    holes = int(m.size - np.count_nonzero(m))
+    while holes > 0:
+        ih, dh = _interpolate_holes_1d(img, m)
+        iv, dv = _interpolate_holes_1d(np.ascontiguousarray(img.transpose(1, 0, 2)), np.ascontiguousarray(m.T))
+        iv, dv = iv.transpose(1, 0, 2), dv.T
+        hole = m == 0
+        both = hole & (dh > 0) & (dv > 0)
+        dd = (f32(1.0) / (dh + dv).clip(1e-30)).astype(f32)
+        # dd * (h * dv + v * dh)   (_fill_holes2, :230-309)
+        mix = (dd[..., None] * ((ih * dv[..., None]).astype(f32) + (iv * dh[..., None]).astype(f32)).astype(f32)).astype(f32)
+        only_v, only_h = hole & ~(dh > 0) & (dv > 0), hole & (dh > 0) & ~(dv > 0)
+        img[both] = mix[both]
+        img[only_v] = iv[only_v]
+        img[only_h] = ih[only_h]
+        filled = int(both.sum() + only_v.sum() + only_h.sum())
+        m[both | only_v | only_h] = 255
+        if filled < 1:
+            break
+        holes -= filled
+    return img[..., 0] if squeeze else img

@@ -135,3 +135,50 @@ def run_stacking_pass(frames, o: StackingOptions, reference, unsharp_sigma=1.0, 
     avg, mask, _, _ = run_stacking(frames, o, reference=ref, collect=collect)
     avg, mask = average_pyramid_inpaint(avg, mask, inpaint_max_levels)
     return avg, mask, ref
+
+
+def master_frame_range(num_frames, master_frame_pos, max_frames_to_stack, start_frame_index=0):
+    """[startpos, endpos) of create_reference_frame (c_image_stacking_pipeline.cc:1211-1229)."""
+    start_frame_index = max(0, start_frame_index)
+    if start_frame_index + max_frames_to_stack >= num_frames:
+        return start_frame_index, num_frames
+    startpos = max(start_frame_index, master_frame_pos - max_frames_to_stack // 2)
+    endpos = startpos + max_frames_to_stack
+    if endpos >= num_frames:
+        startpos = max(start_frame_index, num_frames - max_frames_to_stack)
+        endpos = num_frames
+    return startpos, endpos
+
+
+def create_reference_frame(frames, master_frame_pos, o: StackingOptions, max_frames_to_stack=3000, unsharp_sigma=1.0,
+                           unsharp_alpha=0.8):
+    """c_image_stacking_pipeline::create_reference_frame (c_image_stacking_pipeline.cc:1112-1312) for CV_32F frames: the master
+    pass stacks the frames around the selected one registered against it (remap border REFLECT101 while generating the master
+    frame, :1644-1651), then compute(), linear_interpolation_inpaint, unsharp_mask."""
+    import copy
+    from .inpaint import linear_interpolation_inpaint
+    from .unsharp import unsharp_mask
+    frames = list(frames)
+    reference, mask = frames[master_frame_pos].copy(), None
+    if max_frames_to_stack >= 2 and len(frames) >= 2:
+        om = copy.deepcopy(o)
+        om.registration.border_mode = cv2.BORDER_REFLECT101
+        lo, hi = master_frame_range(len(frames), master_frame_pos, max_frames_to_stack)
+        reference, mask, _, _ = run_stacking(frames[lo:hi], om, reference=reference)
+        reference = linear_interpolation_inpaint(reference, mask)
+    if unsharp_sigma > 0 and unsharp_alpha > 0:
+        reference = unsharp_mask(reference, unsharp_sigma, unsharp_alpha)
+    return reference, mask
+
+
+def select_master_frame(frames, bayer=False, dscale=1, kradius=1, uscale=0):
+    """master_frame_best_of_100_in_middle over the scanned frames (c_image_stacking_pipeline_base.cc:311-399) -> (best, metrics)."""
+    from .debayer import average_bayer_planes
+    best, best_metric, metrics = 0, 0.0, []
+    for i, f in enumerate(frames):
+        tmp = average_bayer_planes(f) if bayer else f
+        q, _ = compute_local_variance_map(tmp, dscale, kradius, uscale, full_resolution=False)
+        metrics.append(q)
+        if q > best_metric:
+            best_metric, best = q, i
+    return best, metrics

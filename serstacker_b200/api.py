@@ -5,6 +5,7 @@ written against the reference.  The product host layer is the C++ adapter (serst
 this module only marshals numpy arrays into ssk_mat and calls libssk.so.  No computation happens here.
 """
 import ctypes as C
+import os
 import numpy as np
 
 from . import capi
@@ -363,6 +364,130 @@ def jdr_derotate_and_add(acc, frame, mask, center, axes, R_current, R_target, eb
                                             float(wscale), int(is_master), int(enable_weighted_average), float(lpg_k),
                                             float(lpg_p), int(lpg_dscale), int(lpg_uscale)))
     return True
+
+
+def linear_interpolation_inpaint(src, mask):
+    """linear_interpolation_inpaint (core/proc/inpaint/linear_interpolation_inpaint.cc:327-368) on CV_32F images -> filled copy."""
+    src = np.ascontiguousarray(src, dtype=f32)
+    dst = np.empty_like(src)
+    mm = None if mask is None else mat(np.ascontiguousarray(mask, dtype=np.uint8))
+    check(capi.lib.ssk_linear_interpolation_inpaint(C.byref(mat(src)), ref(mm), C.byref(mat(dst))))
+    return dst
+
+
+def average_bayer_planes(raw):
+    """average_bayer_planes (core/io/debayer.cc:277-376) of a raw single-channel Bayer frame -> half-size image of the same dtype."""
+    raw = np.ascontiguousarray(raw)
+    dst = np.empty((raw.shape[0] // 2, raw.shape[1] // 2), dtype=raw.dtype)
+    check(capi.lib.ssk_average_bayer_planes(C.byref(mat(raw)), C.byref(mat(dst))))
+    return dst
+
+
+def input_calibrate(frame, bpp=0, dark=None, flat=None):
+    """read_input_frame's dark / flat correction (c_image_stacking_pipeline_base.cc:143-184) -> CV_32F frame."""
+    frame = np.ascontiguousarray(frame)
+    dst = np.empty(frame.shape, dtype=f32)
+    md = None if dark is None else mat(np.ascontiguousarray(dark, dtype=f32))
+    mf = None if flat is None else mat(np.ascontiguousarray(flat, dtype=f32))
+    check(capi.lib.ssk_input_calibrate(C.byref(mat(frame)), int(bpp), ref(md), ref(mf), C.byref(mat(dst))))
+    return dst
+
+
+def color_transform(image, matrix):
+    """cv::transform(image, image, color_matrix) (c_image_stacking_pipeline_base.cc:263-266) on CV_32FC3 images."""
+    image = np.ascontiguousarray(image, dtype=f32)
+    m = np.ascontiguousarray(matrix, dtype=f32)
+    assert m.shape in ((3, 3), (3, 4))
+    dst = np.empty_like(image)
+    check(capi.lib.ssk_color_transform(C.byref(mat(image)), m.ctypes.data_as(C.POINTER(C.c_float)), m.shape[1], C.byref(mat(dst))))
+    return dst
+
+
+class c_ser_reader:
+    """c_ser_reader (core/io/c_ser_file.h:136-190): open / seek / read of a SER sequence."""
+
+    def __init__(self, path):
+        self._h = C.c_void_p()
+        check(capi.lib.ssk_ser_open(os.fsencode(path), C.byref(self._h)))
+        v = [C.c_int() for _ in range(7)]
+        check(capi.lib.ssk_ser_info(self._h, *[C.byref(x) for x in v]))
+        self.cols, self.rows, self.type, self.bits_per_plane, self.color_id, self.num_frames, ts = [x.value for x in v]
+        self.has_timestamps = bool(ts)
+        depth, cn = self.type & 7, (self.type >> 3) + 1
+        self._dtype = {capi.SSK_8U: np.uint8, capi.SSK_16U: np.uint16, capi.SSK_32F: np.float32}[depth]
+        self._shape = (self.rows, self.cols) if cn == 1 else (self.rows, self.cols, cn)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and capi is not None:
+            capi.lib.ssk_ser_close(self._h)
+            self._h = None
+
+    def bpp(self):
+        """c_input_source::bpp(): bits per sample of integer frames (the 1 / (1 << bpp) scale of read_input_frame)."""
+        return self.bits_per_plane if self.bits_per_plane > 0 else 0
+
+    def read(self, index, out=None):
+        """-> (frame, timestamp).  `out`: an array to read into (e.g. a pinned buffer)."""
+        img = np.empty(self._shape, dtype=self._dtype) if out is None else out
+        ts = C.c_uint64(0)
+        check(capi.lib.ssk_ser_read(self._h, int(index), C.byref(mat(img)), C.byref(ts)))
+        return img, ts.value
+
+
+def select_master_frame(frames, colorid=capi.COLORID_MONO, bpp=0, dscale=1, kradius=1, uscale=0):
+    """The master_frame_best_of_100_in_middle branch of select_master_frame (c_image_stacking_pipeline_base.cc:311-399) over the
+    scanned frames: the sharpness metric of compute_local_variance_map on each frame (on average_bayer_planes of a raw Bayer
+    frame), first maximum wins.  -> (best_index, metrics)."""
+    best, best_metric, metrics = 0, 0.0, []
+    for i, f in enumerate(frames):
+        tmp = average_bayer_planes(f) if colorid in (capi.COLORID_BAYER_RGGB, capi.COLORID_BAYER_GRBG, capi.COLORID_BAYER_GBRG,
+                                                      capi.COLORID_BAYER_BGGR) else f
+        q = C.c_double()
+        check(capi.lib.ssk_local_variance_map(C.byref(mat(np.ascontiguousarray(tmp))), bpp, dscale, kradius, uscale, None, C.byref(q)))
+        metrics.append(q.value)
+        if q.value > best_metric:
+            best_metric, best = q.value, i
+    return best, metrics
+
+
+def master_frame_range(num_frames, master_frame_pos, max_frames_to_stack, start_frame_index=0):
+    """[startpos, endpos) of the frames create_reference_frame stacks into the master frame (c_image_stacking_pipeline.cc:1211-1229)."""
+    start_frame_index = max(0, start_frame_index)
+    if start_frame_index + max_frames_to_stack >= num_frames:
+        return start_frame_index, num_frames
+    startpos = max(start_frame_index, master_frame_pos - max_frames_to_stack // 2)
+    endpos = startpos + max_frames_to_stack
+    if endpos >= num_frames:
+        startpos = max(start_frame_index, num_frames - max_frames_to_stack)
+        endpos = num_frames
+    return startpos, endpos
+
+
+def create_reference_frame(frames, master_frame_pos, options, max_frames_to_stack=3000, unsharp_sigma=1.0, unsharp_alpha=0.8, bpp=0):
+    """c_image_stacking_pipeline::create_reference_frame (c_image_stacking_pipeline.cc:1112-1312) for an in-memory sequence:
+    the master frame alone (max_frames_to_stack < 2), or the stack of the frames around it registered against it with
+    BORDER_REFLECT101 (generating_master_frame), compute(), linear_interpolation_inpaint; then unsharp_mask(sigma, alpha).
+    `options`: ssk_stack_options of the master pass.  -> (reference_frame CV_32F, reference_mask or None)."""
+    frames = list(frames)
+    ref0 = frames[master_frame_pos]
+    scale = 1.0 if ref0.dtype == np.float32 else 1.0 / (1 << bpp)
+    reference, mask = (ref0.astype(np.float64) * scale).astype(f32) if ref0.dtype != np.float32 else ref0.copy(), None
+    if max_frames_to_stack >= 2 and len(frames) >= 2:
+        o = capi.ssk_stack_options.from_buffer_copy(options)
+        o.generating_master_frame = 1
+        p = c_image_stacking_pipeline(o)
+        p.set_reference(ref0, bpp=bpp)
+        lo, hi = master_frame_range(len(frames), master_frame_pos, max_frames_to_stack)
+        mb = max(1, int(o.max_batch))
+        for i in range(lo, hi, mb):
+            p.add_frames(frames[i:min(hi, i + mb)], want_results=False)
+        if p.accumulated_frames() < 1:
+            raise RuntimeError("No frames accumulated for reference frame")
+        reference, mask = p.compute()
+        reference = linear_interpolation_inpaint(reference, mask)
+    if unsharp_sigma > 0 and unsharp_alpha > 0:
+        reference = unsharp_mask(reference, unsharp_sigma, unsharp_alpha)
+    return reference, mask
 
 
 def stack_options(**kw):

@@ -28,6 +28,7 @@ INTER_NEAREST, INTER_LINEAR, INTER_CUBIC, INTER_AREA = 0, 1, 2, 3
 BORDER_CONSTANT, BORDER_REPLICATE, BORDER_REFLECT, BORDER_WRAP, BORDER_REFLECT101, BORDER_TRANSPARENT = 0, 1, 2, 3, 4, 5
 ACC_WEIGHTED_AVERAGE, ACC_BAYER_AVERAGE = 0, 1
 STACK_AVERAGE, STACK_WEIGHTED_AVERAGE, STACK_BAYER_AVERAGE = 0, 1, 2
+COLORID_MONO = 0
 COLORID_BAYER_RGGB, COLORID_BAYER_GRBG, COLORID_BAYER_GBRG, COLORID_BAYER_BGGR = 8, 9, 10, 11
 
 
@@ -76,7 +77,8 @@ class ssk_transform(C.Structure):
 class ssk_stack_options(C.Structure):
     _fields_ = [("registration", ssk_registration_options), ("accumulation_method", C.c_int32),
                 ("sm_dscale", C.c_int32), ("sm_kradius", C.c_int32), ("sm_uscale", C.c_int32),
-                ("enable_registration", C.c_int32), ("bayer_colorid", C.c_int32), ("max_batch", C.c_int32)]
+                ("enable_registration", C.c_int32), ("bayer_colorid", C.c_int32), ("max_batch", C.c_int32),
+                ("generating_master_frame", C.c_int32)]
 
 
 _P = C.POINTER
@@ -126,6 +128,14 @@ _sigs = {
     "ssk_lpg": (C.c_int, [_P(ssk_mat), C.c_double, C.c_double, C.c_int, C.c_int, _P(ssk_mat)]),
     "ssk_gaussian_blur": (C.c_int, [_P(ssk_mat), C.c_double, C.c_double, _P(ssk_mat)]),
     "ssk_debayer_nn2": (C.c_int, [_P(ssk_mat), _P(ssk_mat), C.c_int]),
+    "ssk_average_bayer_planes": (C.c_int, [_P(ssk_mat), _P(ssk_mat)]),
+    "ssk_input_calibrate": (C.c_int, [_P(ssk_mat), C.c_int, _P(ssk_mat), _P(ssk_mat), _P(ssk_mat)]),
+    "ssk_color_transform": (C.c_int, [_P(ssk_mat), _P(C.c_float), C.c_int, _P(ssk_mat)]),
+    "ssk_linear_interpolation_inpaint": (C.c_int, [_P(ssk_mat), _P(ssk_mat), _P(ssk_mat)]),
+    "ssk_ser_open": (C.c_int, [C.c_char_p, _P(C.c_void_p)]),
+    "ssk_ser_close": (C.c_int, [C.c_void_p]),
+    "ssk_ser_info": (C.c_int, [C.c_void_p, _P(C.c_int), _P(C.c_int), _P(C.c_int), _P(C.c_int), _P(C.c_int), _P(C.c_int), _P(C.c_int)]),
+    "ssk_ser_read": (C.c_int, [C.c_void_p, C.c_int, _P(ssk_mat), _P(C.c_uint64)]),
     "ssk_unsharp_mask": (C.c_int, [_P(ssk_mat), _P(ssk_mat), C.c_double, C.c_double, C.c_double, C.c_double]),
     "ssk_average_pyramid_inpaint": (C.c_int, [_P(ssk_mat), _P(ssk_mat), _P(ssk_mat), _P(ssk_mat), C.c_int]),
     "ssk_acc_compute_inpainted": (C.c_int, [C.c_void_p, _P(ssk_mat), _P(ssk_mat), C.c_double, C.c_int]),

@@ -112,6 +112,10 @@ int launch_debayer_nn2(const void *src, int64_t sstep, int depth, int rows, int 
 // interleaved channels, mask: CV_8UC1 (both on the device, any step); dst / dstmask dense; `work` holds
 // inpaint_work_bytes() bytes.  *was_full = 1 when the mask had no holes (outputs are copies of the inputs).
 size_t inpaint_work_bytes(int rows, int cols, int cn, int max_levels);
+// linear_interpolation_inpaint (core/proc/inpaint/linear_interpolation_inpaint.cc; ssk_lininpaint.cu), in place on dense device buffers
+size_t lin_inpaint_work_bytes(int rows, int cols);
+int launch_linear_interpolation_inpaint(float *img, int64_t istep, uint8_t *mask, int64_t mstep, int rows, int cols, int cn, void *work,
+                                        cudaStream_t s);
 int launch_average_pyramid_inpaint(const float *src, int64_t sstep, const uint8_t *mask, int64_t mstep, int rows, int cols, int cn,
                                    int max_levels, void *work, float *dst, uint8_t *dstmask, int *was_full, cudaStream_t s);
 

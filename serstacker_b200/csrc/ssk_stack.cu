@@ -497,7 +497,7 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
   a.depth = d; a.cn = cn; a.scale = geom.scale;
   const ssk_registration_options &ro = h->o.registration;
   a.interp = h->o.enable_registration ? remap_interp(ro.interpolation) : SSK_INTER_NEAREST;
-  a.border = ro.border_mode;
+  a.border = h->o.generating_master_frame ? SSK_BORDER_REFLECT101 : ro.border_mode;   // c_image_stacking_pipeline.cc:1647-1650
   for (int i = 0; i < 4; ++i) a.bval[i] = (float)ro.border_value[i];
   a.use_weights = weighted ? 1 : 0;
   a.stage_aligned = h->frames_aligned ? 1 : 0;
