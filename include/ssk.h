@@ -270,8 +270,11 @@ SSK_API int ssk_nccl_comm_destroy(void *nccl_comm);
 /* ---------------------------------------------------------------------------------------------
  * Weight maps (core/proc/sharpness_measure/c_local_variance_sharpness_measure.cc:193-247, core/proc/lpg.cc:223-290).
  * ------------------------------------------------------------------------------------------- */
+/* compute_local_variance_map(image, dscale, kradius, uscale) -> sharpness metric *Q and (map != NULL) the weight map.
+ * bpp >= 0: integer frames are normalised by 1 / (1 << bpp) first, as read_input_frame hands them to compute_weights;
+ * bpp < 0: by 1 / maxval(depth), the reference's own scaling of integer images (select_master_frame ranks raw frames). */
 SSK_API int ssk_local_variance_map(const ssk_mat *image, int bpp, int dscale, int kradius, int uscale,
-                                   ssk_mat *map /*CV_32FC1, full resolution*/, double *Q);
+                                   ssk_mat *map /*CV_32FC1, full resolution, or NULL*/, double *Q);
 /* lpg(image, k, p, dscale, uscale, map) (core/proc/lpg.cc:223-290; callers c_jdr_pipeline.cc:1211, c_sdr_pipeline.cc:1205):
  * Laplacian + gradient energy weight map, CV_32FC1 of the image size.  Integer powers p only. */
 SSK_API int ssk_lpg(const ssk_mat *image, double k, double p, int dscale, int uscale, ssk_mat *map /*CV_32FC1*/);

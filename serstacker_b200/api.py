@@ -434,7 +434,7 @@ class c_ser_reader:
         return img, ts.value
 
 
-def select_master_frame(frames, colorid=capi.COLORID_MONO, bpp=0, dscale=1, kradius=1, uscale=0):
+def select_master_frame(frames, colorid=capi.COLORID_MONO, dscale=1, kradius=1, uscale=0):
     """The master_frame_best_of_100_in_middle branch of select_master_frame (c_image_stacking_pipeline_base.cc:311-399) over the
     scanned frames: the sharpness metric of compute_local_variance_map on each frame (on average_bayer_planes of a raw Bayer
     frame), first maximum wins.  -> (best_index, metrics)."""
@@ -443,7 +443,7 @@ def select_master_frame(frames, colorid=capi.COLORID_MONO, bpp=0, dscale=1, krad
         tmp = average_bayer_planes(f) if colorid in (capi.COLORID_BAYER_RGGB, capi.COLORID_BAYER_GRBG, capi.COLORID_BAYER_GBRG,
                                                       capi.COLORID_BAYER_BGGR) else f
         q = C.c_double()
-        check(capi.lib.ssk_local_variance_map(C.byref(mat(np.ascontiguousarray(tmp))), bpp, dscale, kradius, uscale, None, C.byref(q)))
+        check(capi.lib.ssk_local_variance_map(C.byref(mat(np.ascontiguousarray(tmp))), -1, dscale, kradius, uscale, None, C.byref(q)))
         metrics.append(q.value)
         if q.value > best_metric:
             best_metric, best = q.value, i

@@ -655,7 +655,12 @@ int ssk_local_variance_map(const ssk_mat *image, int bpp, int dscale, int kradiu
   if (int e = sc.init()) return e;
   cudaStream_t s = sc.stream;
   Img im;
-  if (int e = to_device(image, sc.a, s, &im, bpp)) return e;
+  if (int e = to_device(image, sc.a, s, &im, bpp < 0 ? 0 : bpp)) return e;
+  // bpp < 0: the image is taken as the reference's own overload takes it (select_master_frame ranks raw integer frames,
+  // c_image_stacking_pipeline_base.cc:376): depth_scale = 20 / maxval(depth) (c_local_variance_sharpness_measure.cc:203-209),
+  // i.e. integer samples normalised by 1 / 255 or 1 / 65535.  The pdownscale chain runs in float here, where cv::pyrDown
+  // rounds an integer image at every level: the metric agrees to ~1e-4 relative on integer frames, exactly on CV_32F.
+  if (bpp < 0) im.scale = im.depth == SSK_8U ? (float)(1.0 / 255.0) : im.depth == SSK_16U ? (float)(1.0 / 65535.0) : 1.f;
   SSK_REQUIRE(im.cn == 1 || im.cn == 3, "compute_local_variance_map: 1 or 3 channels");
   // pdownscale (c_local_variance_sharpness_measure.cc:28-52)
   const size_t n = (size_t)im.rows * im.cols;
