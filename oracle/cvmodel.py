@@ -359,3 +359,20 @@ def resize_area_f32(src, dsize, inv_scale=None, simd_lanes=8):
             summ = (summ + (beta * buf).astype(f32)).astype(f32)
     dst[prev_dy] = summ
     return dst
+
+
+def remap_linear_u8(mask, mapx, mapy):
+    """cv::remap of a CV_8UC1 image with INTER_LINEAR and BORDER_CONSTANT 0 (the mask remaps of ecc2.cc:205-216, 1311, 117):
+    coordinates quantised to 1/32 px, 15-bit fixed-point bilinear weights - for 1/32 fractions exactly
+    32 (32 - fx | fx)(32 - fy | fy), sum 32768 - and FixedPtCast's (sum + 2^14) >> 15."""
+    h, w = mask.shape
+    sx = np.rint(mapx.astype(np.float32) * np.float32(32)).astype(np.int64)
+    sy = np.rint(mapy.astype(np.float32) * np.float32(32)).astype(np.int64)
+    ix, iy, fx, fy = sx >> 5, sy >> 5, sx & 31, sy & 31
+
+    def at(x, y):
+        ok = (x >= 0) & (x < w) & (y >= 0) & (y < h)
+        return np.where(ok, mask[np.clip(y, 0, h - 1), np.clip(x, 0, w - 1)], 0).astype(np.int64)
+
+    s = (32 - fx) * (32 - fy) * at(ix, iy) + fx * (32 - fy) * at(ix + 1, iy) + (32 - fx) * fy * at(ix, iy + 1) + fx * fy * at(ix + 1, iy + 1)
+    return ((32 * s + (1 << 14)) >> 15).astype(np.uint8)

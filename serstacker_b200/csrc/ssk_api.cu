@@ -275,11 +275,21 @@ int ssk_ecch_align(ssk_ecch *h, const ssk_mat *image, const ssk_mat *mask, ssk_t
   SSK_REQUIRE(h && t, "null argument");
   SSK_REQUIRE(h->e.have_reference, "c_ecch: no reference image was set");
   if (int e = check_mat(image, "c_ecch::align")) return e;
-  SSK_REQUIRE(!mask, "c_ecch: current masks are not implemented yet");
   SSK_REQUIRE(image->rows == h->e.lh[0] && image->cols == h->e.lw[0], "c_ecch: current image size differs from the reference image size");
   if (int e = h->e.reserve(1)) return e;
   if (int e = ecch_image_to_gray(h, image, h->e.level0_scratch(0))) return e;
   if (int e = h->e.prepare_current(h->e.level0_scratch_ptrs(), 1)) return e;
+  if (mask) {
+    const uint8_t *d_mask = nullptr;
+    int64_t mstep = 0;
+    if (int e = mask_to_device(mask, image->rows, image->cols, h->st_mask2, h->stream, &d_mask, &mstep)) return e;
+    if (mstep != image->cols) {     // a strided device mask: the pyramid builder wants it dense
+      if (int e = h->st_mask2.ensure((size_t)image->rows * image->cols)) return e;
+      SSK_CUDA(cudaMemcpy2DAsync(h->st_mask2.p, image->cols, d_mask, mstep, image->cols, image->rows, cudaMemcpyDeviceToDevice, h->stream));
+      d_mask = h->st_mask2.as<uint8_t>();
+    }
+    if (int e = h->e.prepare_current_mask(d_mask)) return e;
+  }
   h->e.translation_first = 0; h->e.check_rho = 0; h->e.final_scale = 1.0;
   if (int e = h->e.align(1, *t)) return e;
   if (int e = h->e.download_frames(1)) return e;
@@ -363,14 +373,16 @@ int ssk_reg_register_frame(ssk_reg *h, const ssk_mat *image, const ssk_mat *mask
                            ssk_ecc_status *status) {
   SSK_REQUIRE(h, "null handle");
   if (int e = check_mat(image, "register_frame")) return e;
-  SSK_REQUIRE(!mask, "c_frame_registration: current masks are not implemented yet");
   Img im;
   if (int e = to_device(image, h->staging, h->r.stream, &im, bpp)) return e;
   if (int e = h->d_ptr.ensure(sizeof(void *))) return e;
   const void *p = im.data;
   SSK_CUDA(cudaMemcpyAsync(h->d_ptr.p, &p, sizeof(p), cudaMemcpyHostToDevice, h->r.stream));
   SSK_CUDA(cudaStreamSynchronize(h->r.stream));   // &p is a stack variable
-  if (int e = h->r.prepare(im, h->d_ptr.as<const void *>(), 1)) return e;
+  const uint8_t *d_mask = nullptr;
+  int64_t mstep = 0;
+  if (mask) { if (int e = mask_to_device(mask, image->rows, image->cols, h->st_mask, h->r.stream, &d_mask, &mstep)) return e; }
+  if (int e = h->r.prepare(im, h->d_ptr.as<const void *>(), 1, d_mask, mstep)) return e;
   if (int e = h->r.register_batch(1)) return e;
   if (int e = h->r.ecch.download_frames(1)) return e;
   SSK_CUDA(cudaStreamSynchronize(h->r.stream));

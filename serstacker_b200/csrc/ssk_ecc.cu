@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(NT, 1) k_ecc_precompute(const __grid_constant_
   cluster.sync();
 }
 
-__global__ void k_ecc_init_frames(EccFrame *frames, int n, const ssk_transform t0, const float *pyr_base, int64_t pyr_floats) {
+__global__ void k_ecc_init_frames(EccFrame *frames, int n, const ssk_transform t0, const float *pyr_base, int64_t pyr_floats,
+                                  const uint8_t *mask_base) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   EccFrame &f = frames[i];
@@ -53,13 +54,14 @@ __global__ void k_ecc_init_frames(EccFrame *frames, int n, const ssk_transform t
   f.t = t0;
   f.rho = -1; f.eps = 0; f.num_iterations = 0; f.ok = 0; f.failed = 0; f.pad = 0;
   f.map = make_mapcoef(t0);
+  f.cmask = mask_base ? mask_base + (int64_t)i * pyr_floats : nullptr;
 }
 
 }  // namespace
 
 int launch_ecc_init_frames(EccFrame *frames, int n, const ssk_transform &t0, const float *pyr_base, int64_t pyr_floats,
-                           cudaStream_t s) {
-  k_ecc_init_frames<<<div_up(n, 128), 128, 0, s>>>(frames, n, t0, pyr_base, pyr_floats);
+                           const uint8_t *mask_base, cudaStream_t s) {
+  k_ecc_init_frames<<<div_up(n, 128), 128, 0, s>>>(frames, n, t0, pyr_base, pyr_floats, mask_base);
   SSK_LAUNCH_CHECK();
   return SSK_OK;
 }

@@ -57,6 +57,8 @@ struct EccFrame {
   int failed;                 // solver failure flag
   int pad;
   MapCoef map;                // out: full-resolution map coefficients of `t` (for the fused warp kernel)
+  const uint8_t *cmask;       // this frame's current-mask pyramid as its solver keeps it (level l at cmask + lv[l].cur_off
+                              // bytes), or null: no current mask (c_ecc_align::set_current_image, ecc2.cc:611-632, 1214-1234)
 };
 
 // Launches one thread-block cluster per frame; the cluster runs the whole coarse-to-fine alignment of its
@@ -65,7 +67,7 @@ int launch_ecc(const EccConfig &cfg, EccFrame *frames, int nframes, int cluster_
 
 // Initialises `n` frame records on the device: t = t0, pyr = pyr_base + i * pyr_floats, status cleared.
 int launch_ecc_init_frames(EccFrame *frames, int n, const ssk_transform &t0, const float *pyr_base, int64_t pyr_floats,
-                           cudaStream_t s);
+                           const uint8_t *mask_base, cudaStream_t s);
 
 // Reference-side precompute: Hp of every level for the translation transform and, when the steepest-descent
 // images do not depend on the parameters (translation / affine), for the main transform.

@@ -543,6 +543,20 @@ __device__ __forceinline__ bool lin_valid(int sx, int sy, int cols, int rows) {
          ((sx & 31) == 0 || ix + 1 < cols) && ((sy & 31) == 0 || iy + 1 < rows);
 }
 
+// cv::remap of a CV_8UC1 mask with INTER_LINEAR and BORDER_CONSTANT 0 at the pre-quantised coordinates (sx, sy): the 15-bit
+// fixed-point bilinear table of a 1/32-px fraction is exactly 32 (32 - fx | fx)(32 - fy | fy) (sum 32768, no correction),
+// the result (sum + 2^14) >> 15 (FixedPtCast).  The reference compares it with 255 (forward-additive, ecc2.cc:1311),
+// 250 (ecc_remap, ecc2.cc:205-216) or 254 (compute_correlation, ecc2.cc:117).
+__device__ __forceinline__ int mask_lin_value(const uint8_t *__restrict__ m, int cols, int rows, int sx, int sy) {
+  const int ix = sx >> 5, iy = sy >> 5, fx = sx & 31, fy = sy & 31;
+  const bool x0 = (unsigned)ix < (unsigned)cols, x1 = (unsigned)(ix + 1) < (unsigned)cols;
+  const bool y0 = (unsigned)iy < (unsigned)rows, y1 = (unsigned)(iy + 1) < (unsigned)rows;
+  const int m00 = x0 && y0 ? (int)m[iy * cols + ix] : 0, m01 = x1 && y0 ? (int)m[iy * cols + ix + 1] : 0;
+  const int m10 = x0 && y1 ? (int)m[(iy + 1) * cols + ix] : 0, m11 = x1 && y1 ? (int)m[(iy + 1) * cols + ix + 1] : 0;
+  const int sum = (32 - fx) * (32 - fy) * m00 + fx * (32 - fy) * m01 + (32 - fx) * fy * m10 + fx * fy * m11;
+  return (32 * sum + (1 << 14)) >> 15;
+}
+
 // cv::remap INTER_LINEAR of a dense CV_32FC1 level with BORDER_REPLICATE: clamped tap coordinates are the
 // replicate border, the arithmetic is sample_linear's (bit-exact against cv2).  Unconditionally safe to call
 // (every address is in bounds), which lets the passes run branch-free.  For pixels that passed lin_valid the
@@ -585,6 +599,7 @@ __device__ void pass_ic(Ctx &c, int lvl, bool lm_masks) {
   // c_ecc_inverse_compositional leaves the reference mask out of rhs / CMA (ecc2.cc:1752-1763: only the remapped
   // current mask); c_ecclm_inverse_compositional ORs it in (ecc2.cc:1901-1904)
   const uint8_t *__restrict__ rmask = lm_masks ? L.refmask : nullptr;
+  const uint8_t *__restrict__ cm = c.frame->cmask ? c.frame->cmask + L.cur_off : nullptr;   // current mask of this level
   const int cols = L.cols, rows = L.rows;
   const MapCoef m = S.map;
   const JCoef jc = S.jc;
@@ -615,12 +630,18 @@ __device__ void pass_ic(Ctx &c, int lvl, bool lm_masks) {
     if (lm_masks) ok = (unsigned)__float2int_rn(u) < (unsigned)cols && (unsigned)__float2int_rn(v) < (unsigned)rows;
 #endif
     else ok = lin_valid(sx, sy, cols, rows);
+    if (cm) {
+      // IC-LM: INTER_NEAREST remap of the inverted current mask, border 255 (ecc2.cc:1877-1884); IC: ecc_remap's
+      // bilinear mask remap >= 250 (ecc2.cc:205-216)
+      if (lm_masks) ok = ok && cm[min(max(__float2int_rn(v), 0), rows - 1) * cols + min(max(__float2int_rn(u), 0), cols - 1)] != 0;
+      else ok = mask_lin_value(cm, cols, rows, sx, sy) >= 250;
+    }
     if (rmask) ok = ok && rmask[w.i] != 0;
     const float g = lin_sample(cur, cols, rows, sx, sy);
     const float fref = __ldg(ref + w.i);
     const float rhs = g - fref;
     if (RHO) {
-      bool okr = lin_valid(sx, sy, cols, rows);
+      bool okr = cm ? mask_lin_value(cm, cols, rows, sx, sy) >= 254 : lin_valid(sx, sy, cols, rows);
       if (rho_mask) okr = okr && rho_mask[w.i] != 0;
       const double gd = okr ? (double)g : 0.0, fd = okr ? (double)fref : 0.0;
       nrho += okr ? 1 : 0;
@@ -671,6 +692,7 @@ __device__ void pass_ic_tiled(Ctx &c, int lvl, bool lm_masks) {
   const float *__restrict__ ref = L.ref, *__restrict__ gxp = L.gx, *__restrict__ gyp = L.gy;
   const uint8_t *__restrict__ rmask = lm_masks ? L.refmask : nullptr;
   const uint8_t *__restrict__ rho_mask = RHO ? L.refmask : nullptr;
+  const uint8_t *__restrict__ cm = c.frame->cmask ? c.frame->cmask + L.cur_off : nullptr;
   const int cols = L.cols, rows = L.rows;
   const MapCoef m = S.map;
   const JCoef jc = S.jc;
@@ -762,6 +784,10 @@ __device__ void pass_ic_tiled(Ctx &c, int lvl, bool lm_masks) {
       bool ok;
       if (lm_masks) ok = u >= -0.5f && u <= hx && v >= -0.5f && v <= hy;   // cvRound(u), cvRound(v) inside the image
       else ok = lin_valid(sx, sy, cols, rows);
+      if (cm) {
+        if (lm_masks) ok = ok && cm[min(max(__float2int_rn(v), 0), rows - 1) * cols + min(max(__float2int_rn(u), 0), cols - 1)] != 0;
+        else ok = mask_lin_value(cm, cols, rows, sx, sy) >= 250;
+      }
       const unsigned pi = (unsigned)(min(yi, rows - 1) * cols) + (unsigned)min(xi, cols - 1);
       if (rmask) ok = ok && rmask[pi] != 0;
       ok = ok && inb;
@@ -781,7 +807,7 @@ __device__ void pass_ic_tiled(Ctx &c, int lvl, bool lm_masks) {
       const float fref = k ? f1 : f0;
       const float rhs = g - fref;
       if (RHO) {
-        bool okr = lin_valid(sx, sy, cols, rows) && inb;
+        bool okr = (cm ? mask_lin_value(cm, cols, rows, sx, sy) >= 254 : lin_valid(sx, sy, cols, rows)) && inb;
         if (rho_mask) okr = okr && rho_mask[pi] != 0;
         const double gd = okr ? (double)g : 0.0, fd = okr ? (double)fref : 0.0;
         nrho += okr ? 1 : 0;
@@ -884,11 +910,13 @@ __device__ void pass_fa_stats(Ctx &c, int lvl) {
   double acc[5] = {0, 0, 0, 0, 0};
   const int n = L.cols * L.rows;
   const Band bd = pass_band(c.rank, c.csize, c.tid, n);
+  const uint8_t *__restrict__ cm = c.frame->cmask ? c.frame->cmask + L.cur_off : nullptr;
   for (Walk w(bd.start, bd.stride, L.cols); w.i < bd.end; w.next()) {
     const int i = w.i;
     float u, v;
     map_xy(m, (float)w.x, (float)w.y, u, v);
-    bool ok = valid255_linear(u, v, L.cols, L.rows);
+    // wmask = remap(current_mask, INTER_LINEAR, BORDER_CONSTANT 0) >= 255 (ecc2.cc:1311-1312)
+    bool ok = cm ? mask_lin_value(cm, L.cols, L.rows, cvround32(u), cvround32(v)) >= 255 : valid255_linear(u, v, L.cols, L.rows);
     if (ok && L.refmask) ok = L.refmask[i] != 0;
     if (!ok) continue;
     const double g = fa_sample<0>(cur, interp, u, v);
@@ -912,6 +940,9 @@ __device__ void pass_forward(Ctx &c, int lvl) {
   const JCoef jc = S.jc;
   const int interp = FA ? c.cfg->interp : SSK_INTER_LINEAR;
   const float fa_a = S.fa_a, fa_c = S.fa_c;
+  // forward-additive: remapped mask >= 255 (ecc2.cc:1311-1312); LM: ecc_remap's >= 250 (ecc2.cc:205-216, 1444-1474)
+  const uint8_t *__restrict__ cm = c.frame->cmask ? c.frame->cmask + L.cur_off : nullptr;
+  const int cm_thr = FA ? 255 : 250;
   double acc[NS];
 #pragma unroll
   for (int k = 0; k < NS; ++k) acc[k] = 0.0;
@@ -932,7 +963,7 @@ __device__ void pass_forward(Ctx &c, int lvl) {
       const int i = y * L.cols + x;
       float u, v;
       map_xy(m, (float)x, (float)y, u, v);
-      bool ok = valid255_linear(u, v, L.cols, L.rows);
+      bool ok = cm ? mask_lin_value(cm, L.cols, L.rows, cvround32(u), cvround32(v)) >= cm_thr : valid255_linear(u, v, L.cols, L.rows);
       if (ok && L.refmask) ok = L.refmask[i] != 0;
       if (ok) {
         const int r = ty + 2, cc = tx + 2;
@@ -983,6 +1014,7 @@ __device__ void pass_rho(Ctx &c) {
   const float *__restrict__ cur = opaque_ptr(c.frame->pyr + L.cur_off);
   const float *__restrict__ ref = L.ref;
   const uint8_t *__restrict__ rmask = L.refmask;
+  const uint8_t *__restrict__ cm = c.frame->cmask;     // level 0 of the solver's current mask (c_ecch::current_mask())
   const int cols = L.cols, rows = L.rows;
   const MapCoef m = S.map;
   double acc[6] = {0, 0, 0, 0, 0, 0};
@@ -995,7 +1027,7 @@ __device__ void pass_rho(Ctx &c) {
     float u, v;
     map_xy_t<MT>(m, (float)w.x, (float)w.y, u, v);
     const int sx = cvround32(u), sy = cvround32(v);
-    bool ok = lin_valid(sx, sy, cols, rows);
+    bool ok = cm ? mask_lin_value(cm, cols, rows, sx, sy) >= 254 : lin_valid(sx, sy, cols, rows);
     if (rmask) ok = ok && rmask[w.i] != 0;
     // valid pixels have every non-zero-weight tap in bounds: the clamped sample equals BORDER_CONSTANT 0
     const double g = ok ? (double)lin_sample(cur, cols, rows, sx, sy) : 0.0;

@@ -291,6 +291,27 @@ int Ecch::prepare_current(const float *const *d_src_ptrs, int batch) {
   return SSK_OK;
 }
 
+int Ecch::prepare_current_mask(const uint8_t *d_mask) {
+  SSK_REQUIRE(have_reference && capacity >= 1, "c_ecch: current mask before the current image");
+  if (int e = cur_mask.ensure((size_t)pyr_floats)) return e;
+  if (int e = cur_mask_tmp.ensure((size_t)lw[0] * lh[0])) return e;
+  uint8_t *mp = cur_mask.as<uint8_t>();
+  SSK_CUDA(cudaMemcpyAsync(mp, d_mask, (size_t)lw[0] * lh[0], cudaMemcpyDeviceToDevice, stream));
+  for (int l = 1; l < nlevels; ++l)
+    if (int e = launch_resize_nearest_u8(mp + loff[l - 1], lh[l - 1], lw[l - 1], mp + loff[l], lh[l], lw[l], stream)) return e;
+  if (opts.method == SSK_ECC_FORWARD_ADDITIVE) {
+    // c_ecc_forward_additive::set_current_image: cv::erode(mask, 5x5, BORDER_REPLICATE) unless the mask is all set
+    // (eroding an all-set mask leaves it all set, so the test is not needed)
+    for (int l = 0; l < nlevels; ++l) {
+      const int n = lw[l] * lh[l];
+      SSK_CUDA(cudaMemcpyAsync(cur_mask_tmp.p, mp + loff[l], n, cudaMemcpyDeviceToDevice, stream));
+      if (int e = launch_erode5_u8(cur_mask_tmp.as<uint8_t>(), lw[l], mp + loff[l], lw[l], lh[l], lw[l], 1, stream)) return e;
+    }
+  }
+  cur_mask_pending = true;
+  return SSK_OK;
+}
+
 int Ecch::hp_mode_for_next_align() const {
   const bool ic = opts.method == SSK_ECC_INVERSE_COMPOSITIONAL || opts.method == SSK_ECC_INVERSE_COMPOSITIONAL_LM;
   if (!ic) return 0;
@@ -319,7 +340,10 @@ int Ecch::align(int batch, const ssk_transform &t0) {
     hp_main_type = motion_type;
   }
   // frame records are initialised on the device: no host staging, the call stays fully asynchronous
-  if (int e = launch_ecc_init_frames(device_frames(), batch, t0, cur_pyr.as<float>(), pyr_floats, stream)) return e;
+  SSK_REQUIRE(!cur_mask_pending || batch == 1, "c_ecch: a current mask applies to single-frame alignment only");
+  const uint8_t *mask_base = cur_mask_pending ? cur_mask.as<uint8_t>() : nullptr;
+  cur_mask_pending = false;
+  if (int e = launch_ecc_init_frames(device_frames(), batch, t0, cur_pyr.as<float>(), pyr_floats, mask_base, stream)) return e;
   int done = 0;
   const int mode = hp_mode_for_next_align();
   if (mode == 2) {
@@ -499,15 +523,30 @@ int Reg::setup_reference(const Img &frame, const uint8_t *d_mask, int64_t mask_s
   return SSK_OK;
 }
 
-int Reg::prepare(const Img &geom, const void *const *d_frame_ptrs, int batch) {
+int Reg::prepare(const Img &geom, const void *const *d_frame_ptrs, int batch, const uint8_t *d_mask, int64_t mask_step) {
   SSK_REQUIRE(ecch.have_reference, "c_frame_registration: setup_reference_frame() must be called first");
   SSK_REQUIRE(geom.rows == ref_rows && geom.cols == ref_cols, "current frame size differs from the reference frame size");
   if (int e = ecch.reserve(batch)) return e;
   if (int e = scale_to_ecc_image(opts, geom, d_frame_ptrs, nullptr, ecch.level0_scratch_ptrs(), ecc_rows, ecc_cols, batch, stream)) return e;
-  if (normalize_enabled()) {
-    if (int e = normalize(ecch.level0_scratch_ptrs(), batch, nullptr)) return e;
+  const uint8_t *d_ecc_mask = nullptr;
+  if (d_mask) {
+    // scaleImage of the current mask (c_frame_registration.cc:230-250): pyrDown(mask) >= 250 for ecc.scale 0.5, as is for 1
+    SSK_REQUIRE(batch == 1, "c_frame_registration: a current mask applies to single-frame registration");
+    SSK_REQUIRE(!ecc_scale_is_area(opts), "current masks with ecc.scale other than 0.5 / 1 (8-bit INTER_AREA) are not implemented");
+    if (int e = mask_tmp.ensure((size_t)ecc_rows * ecc_cols)) return e;
+    if (ecc_rows != geom.rows) {
+      if (int e = launch_pyrdown_mask_u8(d_mask, mask_step, geom.rows, geom.cols, mask_tmp.as<uint8_t>(), ecc_rows, ecc_cols, 250, stream)) return e;
+    } else {
+      SSK_CUDA(cudaMemcpy2DAsync(mask_tmp.p, ecc_cols, d_mask, mask_step, ecc_cols, ecc_rows, cudaMemcpyDeviceToDevice, stream));
+    }
+    d_ecc_mask = mask_tmp.as<uint8_t>();
   }
-  return ecch.prepare_current(ecch.level0_scratch_ptrs(), batch);
+  if (normalize_enabled()) {
+    if (int e = normalize(ecch.level0_scratch_ptrs(), batch, d_ecc_mask)) return e;
+  }
+  if (int e = ecch.prepare_current(ecch.level0_scratch_ptrs(), batch)) return e;
+  if (d_ecc_mask) return ecch.prepare_current_mask(d_ecc_mask);
+  return SSK_OK;
 }
 
 // ecc_normalize (ecc2.cc:385-397): dst = src - ecc_upscale(ecc_downscale(src, level, BORDER_REPLICATE), src.size()),

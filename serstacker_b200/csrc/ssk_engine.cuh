@@ -78,6 +78,10 @@ class Ecch {
   int reserve(int batch);
   // level-0 source images (dense CV_32FC1, device) of the frames of a batch -> smoothed pyramids
   int prepare_current(const float *const *d_src_ptrs /*device array*/, int batch);
+  // current mask of the frame in slot 0 (dense CV_8UC1 of level-0 size on the device): pyramid by cv::resize(INTER_NEAREST)
+  // (c_ecch::set_current_image, ecc2.cc:1060-1120), eroded 5x5 per level for the forward-additive solver
+  // (ecc2.cc:1214-1234).  Applies to the next align() only, which must be a single-frame one.
+  int prepare_current_mask(const uint8_t *d_mask);
   // run the alignment for `batch` prepared frames, every frame starting from t0
   int align(int batch, const ssk_transform &t0);
   EccFrame *device_frames() { return d_frames.as<EccFrame>(); }
@@ -96,6 +100,8 @@ class Ecch {
   int build_config();
   int hp_mode_for_next_align() const;
   DevBuf ref_pyr, ref_gx, ref_gy, cur_pyr, src0, tmp;
+  DevBuf cur_mask, cur_mask_tmp;
+  bool cur_mask_pending = false;
   DevBuf ref_mask, ref_mask_tmp, d_count;          // reference-mask pyramid (bytes, level l at loff[l]), erode scratch, counters
   bool have_ref_mask = false;
   double rma[kMaxLevels];                          // reference mask area per level
@@ -159,7 +165,8 @@ class Reg {
   // d_mask / mask_step: full-resolution CV_8UC1 reference mask on the device, or null
   int setup_reference(const Img &frame, const uint8_t *d_mask = nullptr, int64_t mask_step = 0);
   // frames (device, common geometry) -> ECC images -> pyramids.  d_frame_ptrs: device array of frame pointers.
-  int prepare(const Img &geom, const void *const *d_frame_ptrs, int batch);
+  // d_mask / mask_step: full-resolution CV_8UC1 mask of the (single) current frame on the device, or null
+  int prepare(const Img &geom, const void *const *d_frame_ptrs, int batch, const uint8_t *d_mask = nullptr, int64_t mask_step = 0);
   int register_batch(int batch);       // launches the ECC kernel; results in ecch.device_frames()
 };
 

@@ -143,3 +143,19 @@ def test_resize_area_model_2x2_simd_form():
     src = rng.random((50, 70)).astype(np.float32)
     want = cv2.resize(src, (35, 25), interpolation=cv2.INTER_AREA)
     assert any(np.array_equal(m.resize_area_f32(src, (35, 25), simd_lanes=l), want) for l in (4, 8, 16))
+
+
+def test_remap_linear_u8_fixed_point_model_is_bit_exact():
+    """The 8-bit bilinear mask remap the ECC solvers threshold at 255 / 254 / 250 (binary and non-binary mask values)."""
+    import cv2
+    from oracle import cvmodel
+    rng = np.random.default_rng(0)
+    h, w = 40, 56
+    m = (rng.random((h, w)) > 0.3).astype(np.uint8) * 255
+    m[5:9, 10:20] = 128
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    for tx, ty in [(0.3, -0.7), (2.53, 1.01), (-3.2, 4.96), (0.03125, 0.03125), (0.0, 0.0)]:
+        mapx = (xx * 1.01 + tx).astype(np.float32)
+        mapy = (yy * 0.99 + ty + 0.002 * xx).astype(np.float32)
+        want = cv2.remap(m, np.dstack([mapx, mapy]), None, cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+        assert np.array_equal(cvmodel.remap_linear_u8(m, mapx, mapy), want)

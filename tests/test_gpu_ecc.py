@@ -249,3 +249,87 @@ def test_register_frame_with_ecc_normalize(gpu, method, nscale, size):
                     o.register_frame(f)
                 env = map_diff_px(3, o.image_transform.parameters(), p_o, size)
                 assert d <= max(1e-3, 4 * env), (d, env)
+
+
+def _current_mask(shape, kind):
+    h, w = shape
+    m = np.full((h, w), 255, np.uint8)
+    if kind == "blob":                   # bad-pixel islands and a saturated region, as read_input_frame's masks have them
+        m[40:70, 100:160] = 0
+        m[150:152, 30:200] = 0
+        m[::37, ::41] = 0
+    elif kind == "roi":
+        m[:, :25] = 0
+        m[-18:] = 0
+    return m
+
+
+@pytest.mark.parametrize("method", METHODS)
+@pytest.mark.parametrize("motion", [0, 3])
+@pytest.mark.parametrize("kind", ["blob", "roi"])
+def test_ecch_align_with_current_mask_matches_oracle(gpu, method, motion, kind):
+    """c_ecch::align(current_image, current_mask): the mask pyramid (resize NEAREST), the forward-additive erosion, and the
+    per-solver remap of the mask (LINEAR >= 255 / >= 250, NEAREST of the inverted mask for IC-LM; ecc2.cc:1307-1316,
+    205-216, 1877-1884)."""
+    from serstacker_b200 import api
+    frames, _ = _seq(320, 240, 4, seed=71 + motion, rot=0.2 if motion else 0.0, scale=0.002 if motion else 0.0)
+    kw = dict(maxlevel=-1, minimum_image_size=16, epsx=0.05, max_iterations=30, update_step_scale=1.0)
+    ot = otf.create_image_transform(motion)
+    o = oecc.EccH(ot, method=method, **kw)
+    o.set_reference_image(frames[0], None)
+    gt = api.create_image_transform(motion)
+    g = api.c_ecch(gt, method=method, **kw)
+    g.set_reference_image(frames[0])
+    mask = _current_mask(frames[0].shape, kind)
+    strict = strict_case(motion, method)
+    for f in frames[1:]:
+        ot.reset()
+        gt.set_parameters(ot.parameters())
+        o.align(f, mask)
+        g.align(f, mask)
+        p_o = ot.parameters().copy()
+        d = map_diff_px(motion, gt.parameters(), p_o, (320, 240))
+        # the mask must matter: without it the oracle lands elsewhere (or takes another number of iterations)
+        if strict:
+            assert g.num_iterations() == o.num_iterations, (g.num_iterations(), o.num_iterations, d)
+            assert d <= 1e-3, d
+        else:
+            ot.reset()
+            with dot_noise():
+                o.align(f, mask)
+            env = map_diff_px(motion, ot.parameters(), p_o, (320, 240))
+            assert d <= max(1e-3, 4 * env), (d, env)
+    # an unmasked align after a masked one is not affected by the previous mask
+    ot.reset()
+    gt.set_parameters(ot.parameters())
+    o.align(frames[1], None)
+    g.align(frames[1])
+    if strict:
+        assert map_diff_px(motion, gt.parameters(), ot.parameters(), (320, 240)) <= 1e-3
+
+
+@pytest.mark.parametrize("method", [oecc.ECC_ALIGN_INVERSE_COMPOSITIONAL_LM, oecc.ECC_ALIGN_FORWARD_ADDITIVE, oecc.ECC_ALIGN_LM])
+def test_register_frame_with_current_mask(gpu, method):
+    """c_frame_registration::register_frame(src, srcmask): scaleImage of the mask (pyrDown >= 250), masked alignment, and the
+    correlation gate under the remapped current mask (>= 254)."""
+    from serstacker_b200 import api
+    frames, _ = _seq(400, 300, 4, seed=83, rot=0.0, scale=0.0, sigma_t=3.0)
+    oo = oreg.ImageRegistrationOptions(motion_type=0)
+    oo.ecc.ecc_method = method
+    oo.ecc.ecch_max_level = -1
+    oo.ecc.update_step_scale = 1.0 if method == oecc.ECC_ALIGN_LM else 1.5
+    o = oreg.FrameRegistration(oo)
+    o.setup_reference_frame(frames[0])
+    g = api.c_frame_registration(api.registration_options(motion_type=0, ecc=dict(ecc_method=method, ecch_max_level=-1,
+                                                                                    update_step_scale=oo.ecc.update_step_scale)))
+    g.setup_reference_frame(frames[0])
+    mask = _current_mask(frames[0].shape, "blob")
+    mask[200:260, 250:330] = 0
+    for f in frames[1:]:
+        ok_o = o.register_frame(f, mask)
+        ok_g = g.register_frame(f, mask)
+        assert ok_o == ok_g
+        assert abs(g.status.rho - o.status.rho) <= 1e-4
+        if ok_o:
+            assert map_diff_px(0, g.image_transform_parameters(), o.image_transform.parameters(), (400, 300)) <= 1e-3
+            assert g.status.num_iterations == o.status.num_iterations
