@@ -376,3 +376,64 @@ def remap_linear_u8(mask, mapx, mapy):
 
     s = (32 - fx) * (32 - fy) * at(ix, iy) + fx * (32 - fy) * at(ix + 1, iy) + (32 - fx) * fy * at(ix, iy + 1) + fx * fy * at(ix + 1, iy + 1)
     return ((32 * s + (1 << 14)) >> 15).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# cv::Mat::dot on CV_32F data WITHOUT IPP (OpenCV modules/core/src/matmul.simd.hpp, dotProd_32f): what a distribution
+# build of OpenCV (the reference links the system library, CMakeLists.txt:47-59) computes for H = <J_i, J_j> and
+# v = <J_i, rhs> (ecc2.cc:295-338).  The opencv-python wheel in this image has IPP, whose ippsDotProd_32f64f accumulates in
+# double, and no Python entry point reaches Mat::dot (cv2.UMat exposes no dot; cv2.gemm / mulTransposed / norm take other
+# routines), so this model cannot be pinned to a cv2 call: it restates the published source.
+#   blocks of 2^13 elements; inside a block four vector accumulators of `lanes` floats updated by fused multiply-add
+#   (v_muladd), combined as v_sum + ((v_sum1 + v_sum2) + v_sum3), left-over vectors into v_sum, horizontal sum in float
+#   (halves folded, then adjacent pairs), block sums added in double; scalar tail in double.
+# ---------------------------------------------------------------------------------------------------------
+def _fma32(a, b, c):
+    """fp32 fused multiply-add: the product of two floats is exact in double; one rounding to double (negligibly often
+    inexact), one to float."""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
+def _reduce_sum_f32(v):
+    """v_reduce_sum of a float vector (..., lanes): fold the halves until 4 lanes remain, then adjacent pairs."""
+    f = np.float32
+    while v.shape[-1] > 4:
+        h = v.shape[-1] // 2
+        v = (v[..., :h] + v[..., h:]).astype(f)
+    v = (v[..., 0::2] + v[..., 1::2]).astype(f)
+    return (v[..., 0] + v[..., 1]).astype(f)
+
+
+def dot_f32_simd(a, b, lanes=16):
+    """dotProd_32f(a, b) of OpenCV's universal-intrinsics path (lanes = 4 SSE/NEON, 8 AVX2, 16 AVX-512) -> double."""
+    a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1)
+    b = np.ascontiguousarray(b, dtype=np.float32).reshape(-1)
+    n = a.size
+    len0 = n & -(lanes * 4)
+    bs0 = 1 << 13
+    r = 0.0
+    i = 0
+    nfull = len0 // bs0
+    blocks = []
+    if nfull:
+        blocks.append((a[:nfull * bs0].reshape(nfull, bs0), b[:nfull * bs0].reshape(nfull, bs0)))
+        i = nfull * bs0
+    if len0 > i:
+        blocks.append((a[i:len0].reshape(1, -1), b[i:len0].reshape(1, -1)))
+        i = len0
+    for A, B in blocks:
+        nb, bs = A.shape
+        w = lanes * 4
+        nun = bs // w
+        acc = np.zeros((nb, 4, lanes), np.float32)
+        Au = A[:, :nun * w].reshape(nb, nun, 4, lanes)
+        Bu = B[:, :nun * w].reshape(nb, nun, 4, lanes)
+        for j in range(nun):
+            acc = _fma32(Au[:, j], Bu[:, j], acc)
+        vsum = (acc[:, 0] + ((acc[:, 1] + acc[:, 2]).astype(np.float32) + acc[:, 3]).astype(np.float32)).astype(np.float32)
+        for j in range(nun * w, bs - lanes + 1, lanes):
+            vsum = _fma32(A[:, j:j + lanes], B[:, j:j + lanes], vsum)
+        r += float(_reduce_sum_f32(vsum).astype(np.float64).sum())
+    if i < n:
+        r += float(np.dot(a[i:].astype(np.float64), b[i:].astype(np.float64)))
+    return r
