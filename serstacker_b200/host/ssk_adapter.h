@@ -10,6 +10,7 @@
 // cv::Mat memory layout, so the adapter and its test build with g++ alone.
 #pragma once
 #include <cstdint>
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -99,6 +100,19 @@ class c_image_transform {
     return true;
   }
   void scale_transfrom(double factor) { ssk_transform_scale(&t_, factor); }   // (sic) reference spelling
+  void reset() { const int mt = t_.motion_type; ssk_transform_init(&t_, mt); }   // c_image_transform::reset(): identity
+  bool invertible() const { return true; }                                    // every transform of the path is (c_image_transform.h:100)
+  // translation() / set_translation() (c_image_transform.h:95-98): where the shift lives in each parameter layout
+  void translation(float *tx, float *ty) const {
+    if (t_.motion_type == SSK_MOTION_AFFINE) { *tx = t_.params[2]; *ty = t_.params[5]; }
+    else if (t_.motion_type == SSK_MOTION_HOMOGRAPHY) { *tx = t_.params[2] / t_.aux[2]; *ty = t_.params[5] / t_.aux[2]; }
+    else { *tx = t_.params[0]; *ty = t_.params[1]; }
+  }
+  void set_translation(float tx, float ty) {
+    if (t_.motion_type == SSK_MOTION_AFFINE) { t_.params[2] = tx; t_.params[5] = ty; }
+    else if (t_.motion_type == SSK_MOTION_HOMOGRAPHY) { t_.params[2] = tx * t_.aux[2]; t_.params[5] = ty * t_.aux[2]; }
+    else { t_.params[0] = tx; t_.params[1] = ty; }
+  }
   bool create_remap(int cols, int rows, image_t &rmap) const {
     create_like(rmap, rows, cols, SSK_32FC2);
     ssk_mat v = detail::view(rmap);
@@ -155,11 +169,42 @@ class c_ecch {
     detail::Opt<image_t> mk(current_mask);
     return ssk_ecch_align(h_, &im, mk.get(), &transform_->raw(), &status_) == SSK_OK && !status_.failed;
   }
+  // set_current_image(image, mask) + align(): the two-step form (ecc2.h:262-266); the image is kept until align()
+  bool set_current_image(const image_t &current_image, const image_t &current_mask = image_t()) {
+    cur_ = current_image; cur_mask_ = current_mask;
+    return !cur_.empty();
+  }
+  bool align() { return !cur_.empty() && align(cur_, cur_mask_); }
+  // align(current_image, current_mask, reference_image, reference_mask) (ecc2.h:270-271)
+  bool align(const image_t &current_image, const image_t &current_mask, const image_t &reference_image, const image_t &reference_mask) {
+    return set_reference_image(reference_image, reference_mask) && align(current_image, current_mask);
+  }
+  // create_remap(rmap) (ecc2.h:287): the dense CV_32FC2 map of the bound transform at the reference image size
+  bool create_remap(image_t &rmap) const {
+    int cols = 0, rows = 0;
+    if (!h_ || !transform_ || ssk_ecch_level_size(h_, 0, &cols, &rows) != SSK_OK) return false;
+    return transform_->create_remap(cols, rows, rmap);
+  }
+  // reference_image() / current_image() (ecc2.h:275-282): level 0 of the pyramids, as the solver sees them (smoothed)
+  bool reference_image(image_t &dst, int level = 0) const { return get_image(0, level, dst); }
+  bool current_image(image_t &dst, int level = 0) const { return get_image(1, level, dst); }
   double eps() const { return status_.eps; }
   int num_iterations() const { return status_.num_iterations; }
   bool failed() const { return status_.failed != 0; }
+  // static c_ecch::compute_next_pyramid_layer_size (ecc2.h:290-293)
+  static void compute_next_pyramid_layer_size(int cols, int rows, int *ncols, int *nrows) {
+    *ncols = ((cols + 1) >> 1) & ~1; *nrows = ((rows + 1) >> 1) & ~1;
+  }
 
  private:
+  bool get_image(int which, int level, image_t &dst) const {
+    int cols = 0, rows = 0;
+    if (!h_ || ssk_ecch_level_size(h_, level, &cols, &rows) != SSK_OK) return false;
+    create_like(dst, rows, cols, SSK_32FC1);
+    ssk_mat v = detail::view(dst);
+    return ssk_ecch_get_image(h_, which, level, &v) == SSK_OK;
+  }
+  image_t cur_, cur_mask_;
   void reset() { if (h_) { ssk_ecch_destroy(h_); h_ = nullptr; } }   // options are bound at creation
   ssk_ecch *h_ = nullptr;
   ssk_ecch_options opts_;
@@ -170,6 +215,57 @@ class c_ecch {
 // ---------------------------------------------------------------------------------------------------------
 // c_frame_registration, ECC branch  (core/proc/image_registration/c_frame_registration.h:210-354)
 // ---------------------------------------------------------------------------------------------------------
+// c_ecc_registration_options / c_image_registration_options (c_frame_registration.h:47-64, 119-136): the reference's field
+// names and defaults, so that option plumbing written against the reference compiles unchanged.  The sparse-feature and
+// eccflow stages are not part of this library: setup_reference_frame() fails when they are the only stage enabled.
+struct c_ecc_registration_options {
+  double scale = 0.5;
+  double eps = 0.2;
+  double min_rho = 0.8;
+  double input_smooth_sigma = 1.0;
+  double reference_smooth_sigma = 1.0;
+  double update_step_scale = 1.5;
+  int se_radius = 5;
+  int ecc_method = SSK_ECC_LM;
+  int max_iterations = 50;
+  int ecch_max_level = 0;
+  int ecch_minimum_image_size = 16;
+  double normalization_noise = 0.01;
+  int normalization_scale = 0;
+  bool ecch_estimate_translation_first = true;
+  bool replace_planetary_disk_with_mask = false;
+};
+
+struct c_image_registration_options {
+  int motion_type = SSK_MOTION_AFFINE;
+  int ecc_registration_channel = 0;          // color_channel_gray
+  int interpolation = SSK_INTER_LINEAR;
+  int border_mode = SSK_BORDER_REFLECT101;
+  double border_value[4] = {0, 0, 0, 0};
+  bool enable_feature_registration = true;
+  bool enable_ecc_registration = false;
+  bool enable_eccflow_registration = false;
+  bool accumulate_and_compensate_turbulent_flow = false;
+  c_ecc_registration_options ecc;
+};
+
+inline ssk_registration_options to_ssk_options(const c_image_registration_options &o) {
+  ssk_registration_options r;
+  ssk_registration_options_default(&r);
+  r.motion_type = o.motion_type; r.interpolation = o.interpolation; r.border_mode = o.border_mode;
+  for (int i = 0; i < 4; ++i) r.border_value[i] = o.border_value[i];
+  r.enable_ecc_registration = o.enable_ecc_registration ? 1 : 0;
+  r.ecc.scale = o.ecc.scale; r.ecc.eps = o.ecc.eps; r.ecc.min_rho = o.ecc.min_rho;
+  r.ecc.input_smooth_sigma = o.ecc.input_smooth_sigma; r.ecc.reference_smooth_sigma = o.ecc.reference_smooth_sigma;
+  r.ecc.update_step_scale = o.ecc.update_step_scale; r.ecc.se_radius = o.ecc.se_radius; r.ecc.ecc_method = o.ecc.ecc_method;
+  r.ecc.max_iterations = o.ecc.max_iterations; r.ecc.ecch_max_level = o.ecc.ecch_max_level;
+  r.ecc.ecch_minimum_image_size = o.ecc.ecch_minimum_image_size; r.ecc.normalization_noise = o.ecc.normalization_noise;
+  r.ecc.normalization_scale = o.ecc.normalization_scale;
+  r.ecc.ecch_estimate_translation_first = o.ecc.ecch_estimate_translation_first ? 1 : 0;
+  r.ecc.replace_planetary_disk_with_mask = o.ecc.replace_planetary_disk_with_mask ? 1 : 0;
+  return r;
+}
+
 struct c_image_registration_status { ssk_ecc_status ecc = {}; };
 
 class c_frame_registration {
@@ -177,6 +273,9 @@ class c_frame_registration {
   typedef std::shared_ptr<c_frame_registration> sptr;
   c_frame_registration() { ssk_registration_options_default(&opts_); }
   explicit c_frame_registration(const ssk_registration_options &o) : opts_(o) {}
+  // the reference's constructor (c_frame_registration.h:216): c_frame_registration(const c_image_registration_options &)
+  explicit c_frame_registration(const c_image_registration_options &o)
+      : opts_(to_ssk_options(o)), other_stage_only_((o.enable_feature_registration || o.enable_eccflow_registration) && !o.enable_ecc_registration) {}
   ~c_frame_registration() { if (h_) ssk_reg_destroy(h_); }
   c_frame_registration(const c_frame_registration &) = delete;
   c_frame_registration &operator=(const c_frame_registration &) = delete;
@@ -187,6 +286,7 @@ class c_frame_registration {
   void set_input_bpp(int bpp) { bpp_ = bpp; }   // 8U/16U frames: c_image_stacking_pipeline_base.cc:271-276 scaling
 
   bool setup_reference_frame(const image_t &image, const image_t &msk = image_t()) {
+    if (other_stage_only_) return false;   // sparse-feature / eccflow registration without the ECC stage: not in this library
     if (h_) { ssk_reg_destroy(h_); h_ = nullptr; }
     if (ssk_reg_create(&opts_, &h_) != SSK_OK) return false;
     ssk_mat im = detail::view(image);
@@ -236,6 +336,7 @@ class c_frame_registration {
   c_image_transform::sptr transform_;
   c_image_registration_status status_;
   int bpp_ = 0;
+  bool other_stage_only_ = false;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -250,14 +351,44 @@ class c_frame_accumulation {
     detail::Opt<image_t> w(mask_or_weights);
     return ssk_acc_add(h_, &s, w.get(), 0) == SSK_OK;
   }
-  bool compute(image_t &avg, image_t *mask = nullptr, double dscale = 1.0) const {
+  // compute(avg, mask, dscale, ddepth) (c_frame_accumulation.h:22): ddepth < 0 or CV_32F keeps the accumulator's float
+  // samples; CV_8U / CV_16U round and saturate like cv::Mat::convertTo
+  bool compute(image_t &avg, image_t *mask = nullptr, double dscale = 1.0, int ddepth = -1) const {
     int cols = 0, rows = 0, cn = 0;
     if (ssk_acc_size(h_, &cols, &rows, &cn) != SSK_OK || cols <= 0) return false;
-    create_like(avg, rows, cols, SSK_MAKETYPE(SSK_32F, cn));
-    ssk_mat a = detail::view(avg), m;
+    if (ddepth >= 0 && ddepth != SSK_32F && ddepth != SSK_8U && ddepth != SSK_16U) return false;
+    image_t favg;
+    image_t &out = (ddepth < 0 || ddepth == SSK_32F) ? avg : favg;
+    create_like(out, rows, cols, SSK_MAKETYPE(SSK_32F, cn));
+    ssk_mat a = detail::view(out), m;
     if (mask) { create_like(*mask, rows, cols, SSK_8UC1); m = detail::view(*mask); }
-    return ssk_acc_compute(h_, &a, mask ? &m : nullptr, dscale) == SSK_OK;
+    if (ssk_acc_compute(h_, &a, mask ? &m : nullptr, dscale) != SSK_OK) return false;
+    if (&out == &favg) {
+      create_like(avg, rows, cols, SSK_MAKETYPE(ddepth, cn));
+      const ssk_mat s = detail::view(favg), d = detail::view(avg);
+      const double hi = ddepth == SSK_8U ? 255.0 : 65535.0;
+      for (int y = 0; y < rows; ++y) {
+        const float *sp = reinterpret_cast<const float *>(static_cast<const char *>(s.data) + y * s.step);
+        for (int x = 0; x < cols * cn; ++x) {
+          const double v = std::nearbyint((double)sp[x]);
+          const double c = v < 0 ? 0 : v > hi ? hi : v;
+          if (ddepth == SSK_8U) reinterpret_cast<uint8_t *>(static_cast<char *>(d.data) + y * d.step)[x] = (uint8_t)c;
+          else reinterpret_cast<uint16_t *>(static_cast<char *>(d.data) + y * d.step)[x] = (uint16_t)c;
+        }
+      }
+    }
+    return true;
   }
+  // get_acc_counters(accw) (c_frame_accumulation.h:24): the weight sums (Bayer: per-colour counters, G halved)
+  bool get_acc_counters(image_t &accw) const {
+    int cols = 0, rows = 0, cn = 0;
+    if (ssk_acc_size(h_, &cols, &rows, &cn) != SSK_OK || cols <= 0) return false;
+    create_like(accw, rows, cols, SSK_MAKETYPE(SSK_32F, counter_channels()));
+    ssk_mat v = detail::view(accw);
+    return ssk_acc_get_counters(h_, &v) == SSK_OK;
+  }
+  // Multi-GPU: combine the accumulators of all ranks on `root` (ssk_acc_reduce; nccl_comm is the caller's ncclComm_t)
+  bool reduce(void *nccl_comm, int root = 0) { return ssk_acc_reduce(h_, nccl_comm, root) == SSK_OK; }
   // compute() + average_pyramid_inpaint(avg, mask, avg, mask, max_levels) on the device (c_image_stacking_pipeline.cc:742-767)
   bool compute_inpainted(image_t &avg, image_t *mask = nullptr, double dscale = 1.0, int max_levels = 100) const {
     int cols = 0, rows = 0, cn = 0;
@@ -278,12 +409,16 @@ class c_frame_accumulation {
 
  protected:
   explicit c_frame_accumulation(int kind) { ssk_acc_create(kind, &h_); }
+  virtual int counter_channels() const { return 1; }
   ssk_acc *h_ = nullptr;
 };
 
 class c_weigthed_average : public c_frame_accumulation {   // (sic) reference spelling
  public:
   c_weigthed_average() : c_frame_accumulation(SSK_ACC_WEIGHTED_AVERAGE) {}
+  // accumulator() / counter() (c_frame_accumulation.h:58-59): copies of the running mean and of the weight sums
+  bool accumulator(image_t &acc) const { return compute(acc, nullptr, 1.0, -1); }
+  bool counter(image_t &cntr) const { return get_acc_counters(cntr); }
 };
 
 class c_bayer_average : public c_frame_accumulation {
@@ -291,9 +426,18 @@ class c_bayer_average : public c_frame_accumulation {
   c_bayer_average() : c_frame_accumulation(SSK_ACC_BAYER_AVERAGE) {}
   void set_bayer_pattern(int colorid) { ssk_acc_set_bayer_pattern(h_, colorid); }
   bool set_remap(const image_t &rmap) {
+    rmap_ = rmap;
+    if (rmap.empty()) return ssk_acc_set_remap(h_, nullptr, nullptr) == SSK_OK;
     ssk_mat v = detail::view(rmap);
     return ssk_acc_set_remap(h_, nullptr, &v) == SSK_OK;
   }
+  const image_t &remap() const { return rmap_; }     // c_bayer_average::remap() (c_frame_accumulation.h:249)
+
+ protected:
+  int counter_channels() const override { return 3; }
+
+ private:
+  image_t rmap_;
 };
 
 // c_local_variance_sharpness_measure::compute (c_local_variance_sharpness_measure.cc:193-247)
@@ -419,10 +563,177 @@ class c_stacking_loop {
     return ok;
   }
   bool sync() { return ssk_stack_sync(h_) == SSK_OK; }
+  bool reset() { return ssk_stack_reset(h_) == SSK_OK; }
+  // end of a run sharded over ranks: the accumulators of all ranks combined on `root` (ncclComm_t of the caller)
+  bool reduce(void *nccl_comm, int root = 0) { return ssk_stack_reduce(h_, nccl_comm, root) == SSK_OK; }
   bool flush() { return ssk_stack_flush(h_) == SSK_OK; }   // stream-side join of the side-stream ring kernel (see ssk.h)
 
  private:
   ssk_stack *h_ = nullptr;
+};
+
+
+// linear_interpolation_inpaint (core/proc/inpaint/linear_interpolation_inpaint.cc:327-368)
+inline bool linear_interpolation_inpaint(const image_t &src, const image_t &mask, image_t &dst) {
+  ssk_mat s = detail::view(src);
+  image_t out;
+  create_like(out, s.rows, s.cols, s.type);
+  ssk_mat d = detail::view(out);
+  detail::Opt<image_t> m(mask);
+  const bool ok = ssk_linear_interpolation_inpaint(&s, m.get(), &d) == SSK_OK;
+  if (ok) dst = out;
+  return ok;
+}
+
+// average_bayer_planes (core/io/debayer.cc:277-376), raw single-channel form
+inline bool average_bayer_planes(const image_t &src, image_t &dst) {
+  ssk_mat s = detail::view(src);
+  image_t out;
+  create_like(out, s.rows / 2, s.cols / 2, s.type);
+  ssk_mat d = detail::view(out);
+  const bool ok = ssk_average_bayer_planes(&s, &d) == SSK_OK;
+  if (ok) dst = out;
+  return ok;
+}
+
+// c_ser_reader (core/io/c_ser_file.h:136-190)
+class c_ser_reader {
+ public:
+  c_ser_reader() = default;
+  explicit c_ser_reader(const std::string &filename) { open(filename); }
+  ~c_ser_reader() { close(); }
+  c_ser_reader(const c_ser_reader &) = delete;
+  c_ser_reader &operator=(const c_ser_reader &) = delete;
+  bool open(const std::string &filename) {
+    close();
+    if (ssk_ser_open(filename.c_str(), &h_) != SSK_OK) return false;
+    return ssk_ser_info(h_, &cols_, &rows_, &type_, &bpp_, &color_id_, &frames_, &has_ts_) == SSK_OK;
+  }
+  void close() { if (h_) { ssk_ser_close(h_); h_ = nullptr; } curpos_ = 0; }
+  bool is_open() const { return h_ != nullptr; }
+  int image_width() const { return cols_; }
+  int image_height() const { return rows_; }
+  int bits_per_plane() const { return bpp_; }
+  int color_id() const { return color_id_; }
+  int num_frames() const { return frames_; }
+  int curpos() const { return curpos_; }
+  bool seek(int frame_index) { if (frame_index < 0) frame_index = 0; if (frame_index >= frames_) return false; curpos_ = frame_index; return true; }
+  bool read(image_t &image, uint64_t *timestamp = nullptr) {
+    if (!h_ || curpos_ >= frames_) return false;
+    create_like(image, rows_, cols_, type_);
+    ssk_mat v = detail::view(image);
+    if (ssk_ser_read(h_, curpos_, &v, timestamp) != SSK_OK) return false;
+    ++curpos_;
+    return true;
+  }
+
+ private:
+  ssk_ser *h_ = nullptr;
+  int cols_ = 0, rows_ = 0, type_ = 0, bpp_ = 0, color_id_ = 0, frames_ = 0, has_ts_ = 0, curpos_ = 0;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// c_image_stacking_pipeline, the stacking part of run_pipeline (c_image_stacking_pipeline.cc:436-466, 731-769, 1112-1312,
+// 1358-1862) over an in-memory sequence: master frame (selected frame alone, or generated from the frames around it),
+// unsharp_mask of the master, the batched per-frame loop, compute() + average_pyramid_inpaint.  Option names follow
+// c_image_stacking_master_options / c_frame_accumulation_options / c_image_stacking_options (c_image_stacking_pipeline.h:88-182).
+// ---------------------------------------------------------------------------------------------------------
+struct c_frame_accumulation_options {
+  int accumulation_method = SSK_STACK_AVERAGE;
+  struct { int dscale = 1, kradius = 1, uscale = 0; } sharpness_measure;
+};
+
+struct c_image_stacking_master_options {
+  c_image_registration_options registration;
+  c_frame_accumulation_options accumulation;
+  int master_frame_index = 0;
+  int max_frames_to_generate_master_frame = 3000;
+  bool generate_master_frame = true;
+  double unsharp_sigma = 1.0, unsharp_alpha = 0.8;
+};
+
+class c_image_stacking_pipeline {
+ public:
+  c_image_stacking_master_options master_options;
+  c_image_registration_options registration_options;   // of the stacking pass
+  c_frame_accumulation_options accumulation_options;
+  int bayer_colorid = SSK_COLORID_BAYER_RGGB;
+  int max_batch = 32;
+
+  // frames: the whole input sequence (same size and type); bpp: bits per sample of integer frames
+  bool run(const std::vector<image_t> &frames, int bpp, image_t &stacked, image_t &stacked_mask, bool inpaint = true) {
+    if (frames.empty()) return false;
+    image_t reference, refmask;
+    if (!create_reference_frame(frames, bpp, reference, refmask)) return false;
+    ssk_stack_options so = stack_options(registration_options, accumulation_options, false);
+    c_stacking_loop loop(so);
+    if (!loop.valid() || !loop.set_reference(reference, bpp)) return false;
+    if (!add_all(loop, frames, 0, (int)frames.size(), bpp)) return false;
+    accumulated_frames_ = loop.accumulated_frames();
+    const ssk_mat r = detail::view(reference);
+    const int cn = accumulation_options.accumulation_method == SSK_STACK_BAYER_AVERAGE ? 3 : ((r.type >> 3) + 1);
+    return inpaint ? loop.compute_inpainted(stacked, stacked_mask, r.rows, r.cols, cn) : loop.compute(stacked, stacked_mask, r.rows, r.cols, cn);
+  }
+  // create_reference_frame (c_image_stacking_pipeline.cc:1112-1312)
+  bool create_reference_frame(const std::vector<image_t> &frames, int bpp, image_t &reference, image_t &refmask) {
+    const int n = (int)frames.size();
+    const int pos = master_options.master_frame_index < 0 ? 0 : master_options.master_frame_index >= n ? n - 1 : master_options.master_frame_index;
+    const int max_stack = master_options.generate_master_frame ? master_options.max_frames_to_generate_master_frame : 1;
+    const ssk_mat f0 = detail::view(frames[pos]);
+    if (max_stack < 2 || n < 2) {
+      // the selected frame alone, converted like read_input_frame does (CV_32F, 1 / (1 << bpp))
+      create_like(reference, f0.rows, f0.cols, SSK_MAKETYPE(SSK_32F, (f0.type >> 3) + 1));
+      ssk_mat d = detail::view(reference);
+      if (ssk_input_calibrate(&f0, bpp, nullptr, nullptr, &d) != SSK_OK) return false;
+    } else {
+      ssk_stack_options so = stack_options(master_options.registration, master_options.accumulation, true);
+      c_stacking_loop loop(so);
+      if (!loop.valid() || !loop.set_reference(frames[pos], bpp)) return false;
+      int lo, hi;
+      master_frame_range(n, pos, max_stack, &lo, &hi);
+      if (!add_all(loop, frames, lo, hi, bpp) || loop.accumulated_frames() < 1) return false;
+      const int cn = master_options.accumulation.accumulation_method == SSK_STACK_BAYER_AVERAGE ? 3 : ((f0.type >> 3) + 1);
+      image_t avg;
+      if (!loop.compute(avg, refmask, f0.rows, f0.cols, cn)) return false;
+      if (!linear_interpolation_inpaint(avg, refmask, reference)) return false;
+    }
+    if (master_options.unsharp_sigma > 0 && master_options.unsharp_alpha > 0)
+      return unsharp_mask(reference, reference, master_options.unsharp_sigma, master_options.unsharp_alpha);
+    return true;
+  }
+  // [startpos, endpos) of the frames stacked into the master frame (c_image_stacking_pipeline.cc:1211-1229)
+  static void master_frame_range(int num_frames, int master_frame_pos, int max_frames_to_stack, int *startpos, int *endpos) {
+    if (max_frames_to_stack >= num_frames) { *startpos = 0; *endpos = num_frames; return; }
+    int s = master_frame_pos - max_frames_to_stack / 2;
+    if (s < 0) s = 0;
+    int e = s + max_frames_to_stack;
+    if (e >= num_frames) { s = num_frames - max_frames_to_stack; if (s < 0) s = 0; e = num_frames; }
+    *startpos = s; *endpos = e;
+  }
+  int accumulated_frames() const { return accumulated_frames_; }
+
+ private:
+  ssk_stack_options stack_options(const c_image_registration_options &r, const c_frame_accumulation_options &a, bool master) const {
+    ssk_stack_options so;
+    ssk_stack_options_default(&so);
+    so.registration = to_ssk_options(r);
+    so.enable_registration = r.enable_ecc_registration ? 1 : 0;
+    so.registration.enable_ecc_registration = 1;
+    so.accumulation_method = a.accumulation_method;
+    so.sm_dscale = a.sharpness_measure.dscale; so.sm_kradius = a.sharpness_measure.kradius; so.sm_uscale = a.sharpness_measure.uscale;
+    so.bayer_colorid = bayer_colorid;
+    so.max_batch = max_batch;
+    so.generating_master_frame = master ? 1 : 0;
+    return so;
+  }
+  bool add_all(c_stacking_loop &loop, const std::vector<image_t> &frames, int lo, int hi, int bpp) {
+    for (int i = lo; i < hi; i += max_batch) {
+      std::vector<image_t> chunk(frames.begin() + i, frames.begin() + (i + max_batch < hi ? i + max_batch : hi));
+      if (!loop.add_frames(chunk, bpp)) return false;
+    }
+    return true;
+  }
+  int accumulated_frames_ = 0;
 };
 
 }  // namespace ssk

@@ -5,6 +5,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <vector>
 
 #include "ssk_adapter.h"
 
@@ -32,6 +34,26 @@ int main(int argc, char **argv) {
   if (argc > 1 && !std::strcmp(argv[1], "--no-gpu")) {
     ssk::c_image_transform t(SSK_MOTION_AFFINE);
     if (t.parameters().size() != 6) return 3;
+    t.set_translation(1.5f, -2.f);
+    float tx = 0, ty = 0;
+    t.translation(&tx, &ty);
+    if (tx != 1.5f || ty != -2.f || !t.invertible()) return 3;
+    t.reset();
+    t.translation(&tx, &ty);
+    if (tx != 0.f || ty != 0.f || t.parameters()[0] != 1.f) return 3;
+    // the reference's option structs: defaults of c_frame_registration.h:47-64, 119-136 survive the conversion
+    ssk::c_image_registration_options io;
+    const ssk_registration_options so = ssk::to_ssk_options(io);
+    if (so.motion_type != SSK_MOTION_AFFINE || so.ecc.ecc_method != SSK_ECC_LM || so.ecc.scale != 0.5 || so.enable_ecc_registration) return 3;
+    ssk::c_frame_registration feature_only(io);            // feature registration is the default stage: not in this library
+    ssk::Mat dummy(8, 8, SSK_32FC1);
+    if (feature_only.setup_reference_frame(dummy)) return 3;
+    int lo = 0, hi = 0;
+    ssk::c_image_stacking_pipeline::master_frame_range(100, 50, 30, &lo, &hi);
+    if (lo != 35 || hi != 65) return 3;
+    int nc = 0, nr = 0;
+    ssk::c_ecch::compute_next_pyramid_layer_size(1920, 1080, &nc, &nr);
+    if (nc != 960 || nr != 540) return 3;
     std::printf("adapter_smoke: no-gpu checks ok (version %d)\n", ssk_version());
     return 0;
   }
@@ -78,5 +100,52 @@ int main(int argc, char **argv) {
   std::printf("adapter_smoke: inpaint filled %d holes, %d valid pixels changed, %d left empty\n", holes, kept_bad, unfilled);
   if (kept_bad || unfilled) return 9;
   if (!ssk::unsharp_mask(ref, sharp, 1.0, 0.8) || sharp.rows != H || sharp.cols != W) { std::fprintf(stderr, "unsharp_mask: %s\n", ssk_last_error()); return 10; }
+  // accumulator surface: counters, accumulator(), compute(..., ddepth)
+  ssk::Mat cntr, accm, avg16;
+  if (!acc.get_acc_counters(cntr) || !acc.counter(cntr) || cntr.type != SSK_32FC1 || !acc.accumulator(accm) || accm.rows != H) return 11;
+  if (cntr.ptr<float>(H / 2)[W / 2] != (float)N) return 11;
+  if (!acc.compute(avg16, nullptr, 65535.0, SSK_16U) || avg16.type != SSK_16UC1) return 11;
+  if (std::abs((int)avg16.ptr<uint16_t>(H / 2)[W / 2] - (int)std::lround(avg.ptr<float>(H / 2)[W / 2] * 65535.0)) > 1) return 11;
+  // c_ecch surface: two-step align, create_remap, pyramid images
+  ssk::c_image_transform tr(SSK_MOTION_TRANSLATION);
+  ssk::c_ecch ecch(&tr);
+  ecch.set_maxlevel(-1);
+  ecch.set_epsx(0.01);
+  render(frame, W, H, 1.25f, -0.75f);
+  ssk::Mat rm, rimg, cimg;
+  if (!ecch.set_reference_image(ref) || !ecch.set_current_image(frame) || !ecch.align()) { std::fprintf(stderr, "c_ecch: %s\n", ssk_last_error()); return 12; }
+  if (!ecch.create_remap(rm) || rm.type != SSK_32FC2 || rm.rows != H || !ecch.reference_image(rimg) || !ecch.current_image(cimg) || cimg.cols != W) return 12;
+  std::printf("adapter_smoke: c_ecch two-step align -> (%.3f, %.3f), %d iterations\n", tr.parameters()[0], tr.parameters()[1], ecch.num_iterations());
+  if (std::fabs(tr.parameters()[0] - 1.25f) > 0.1 || std::fabs(tr.parameters()[1] + 0.75f) > 0.1) return 12;
+  // masked current frame through the adapter
+  ssk::Mat cmask(H, W, SSK_8UC1);
+  std::memset(cmask.buf.data(), 255, cmask.buf.size());
+  for (int y = 20; y < 40; ++y) std::memset(cmask.ptr<uint8_t>(y) + 30, 0, 40);
+  tr.reset();
+  if (!ecch.align(frame, cmask) || std::fabs(tr.parameters()[0] - 1.25f) > 0.1) return 12;
+  // the pipeline class: generated master frame + stacking pass + inpainted read-out
+  std::vector<ssk::Mat> seq(N);
+  for (int i = 0; i < N; ++i) render(seq[i], W, H, sx[i], sy[i]);
+  ssk::c_image_stacking_pipeline pipe;
+  for (ssk::c_image_registration_options *o : {&pipe.registration_options, &pipe.master_options.registration}) {
+    o->motion_type = SSK_MOTION_TRANSLATION; o->enable_feature_registration = false; o->enable_ecc_registration = true;
+    o->ecc.ecc_method = SSK_ECC_INVERSE_COMPOSITIONAL_LM; o->ecc.ecch_max_level = -1; o->ecc.eps = 0.01; o->ecc.update_step_scale = 1.0;
+  }
+  pipe.master_options.max_frames_to_generate_master_frame = 3;
+  pipe.max_batch = 4;
+  ssk::Mat stacked, smask;
+  if (!pipe.run(seq, 0, stacked, smask) || pipe.accumulated_frames() != N || stacked.rows != H) { std::fprintf(stderr, "pipeline: %s\n", ssk_last_error()); return 13; }
+  double perr = 0;
+  for (int y = 12; y < H - 12; ++y)
+    for (int x = 12; x < W - 12; ++x) perr = std::fmax(perr, std::fabs(stacked.ptr<float>(y)[x] - ref.ptr<float>(y)[x]));
+  std::printf("adapter_smoke: c_image_stacking_pipeline::run stacked %d frames, max |stack - scene| = %.4g (master sharpened)\n", pipe.accumulated_frames(), perr);
+  if (perr > 0.05) return 13;
+  // input side
+  ssk::Mat hmask(H, W, SSK_8UC1), lin, raw(H, W, SSK_16UC1), planes;
+  std::memset(hmask.buf.data(), 255, hmask.buf.size());
+  for (int y = 50; y < 60; ++y) std::memset(hmask.ptr<uint8_t>(y) + 70, 0, 25);
+  if (!ssk::linear_interpolation_inpaint(ref, hmask, lin) || lin.ptr<float>(10)[10] != ref.ptr<float>(10)[10]) return 14;
+  for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) raw.ptr<uint16_t>(y)[x] = (uint16_t)(100 * ((y & 1) * 2 + (x & 1)));
+  if (!ssk::average_bayer_planes(raw, planes) || planes.rows != H / 2 || planes.ptr<uint16_t>(3)[5] != 150) return 14;
   return (worst <= 0.1 && err <= 5e-3 && cnt > W * H / 2) ? 0 : 1;
 }
