@@ -66,6 +66,11 @@ int launch_ecc_init_frames(EccFrame *frames, int n, const ssk_transform &t0, con
   return SSK_OK;
 }
 
+int ecc_tma_tile_w() { return TL_W; }
+int ecc_tma_tile_h() { return TL_H; }
+int ecc_tma_win_w() { return TL_WW; }
+int ecc_tma_win_h() { return TL_WH; }
+
 int launch_ecc(const EccConfig &cfg, EccFrame *frames, int nframes, int cluster_size, cudaStream_t s) {
   SSK_REQUIRE(cluster_size >= 1 && cluster_size <= 8, "ECC: cluster size 1..8");
   SSK_REQUIRE(cfg.nlevels >= 1 && cfg.nlevels <= kMaxLevels, "ECC: pyramid depth");

@@ -5,6 +5,7 @@
 namespace ssk {
 
 constexpr int kMaxLevels = 12;
+constexpr int kTmaLevels = 2;   // finest levels that may take the TMA-staged inverse-compositional pass
 constexpr int kTraceRec = 40;   // level, pass, num_it, err, newerr, lambda, eps, n | t[8] | tq[8] | deltap[8] | v[8]
 
 // One pyramid level, reference side (shared by every frame of every batch).
@@ -24,7 +25,13 @@ struct EccHpCache {
   int valid[kMaxLevels];
 };
 
-struct EccConfig {
+struct alignas(64) EccConfig {
+  // TMA-staged passes (ssk_ecc_impl.cuh::pass_ic_tma): tensor maps of the tma_levels finest levels - [0] the current images of
+  // all frame slots (3-D: x, y, slot; slot i = pyr_base + i * pyr_floats), [1] reference, [2] gx, [3] gy (2-D).  0 = off.
+  alignas(64) unsigned char tm[kTmaLevels][4][128];
+  int tma_levels;
+  const float *pyr_base;
+  int64_t pyr_floats;
   int nlevels;
   EccLevel lv[kMaxLevels];
   int method;                 // SSK_ECC_*
@@ -60,6 +67,9 @@ struct EccFrame {
   const uint8_t *cmask;       // this frame's current-mask pyramid as its solver keeps it (level l at cmask + lv[l].cur_off
                               // bytes), or null: no current mask (c_ecc_align::set_current_image, ecc2.cc:611-632, 1214-1234)
 };
+
+// box geometry of the TMA-staged passes (defined next to the kernel, ssk_ecc.cu)
+int ecc_tma_tile_w(); int ecc_tma_tile_h(); int ecc_tma_win_w(); int ecc_tma_win_h();
 
 // Launches one thread-block cluster per frame; the cluster runs the whole coarse-to-fine alignment of its
 // frame (all levels, all iterations, the correlation gate) on the device.

@@ -40,11 +40,6 @@ constexpr int NW = NT / 32;
 constexpr int NSMAX = 72;
 constexpr int FT_W = 32, FT_H = NT / 32;     // stencil tile of the forward methods (one pixel per thread)
 constexpr int FT_IW = FT_W + 4, FT_IH = FT_H + 4;
-// tiled inverse-compositional pass: a CTA walks its band of the level in tiles of TL_W x TL_H pixels (NT threads, two
-// rows per thread); the bilinear taps of a tile come from a TL_WW x TL_WH window of the current image staged in smem
-constexpr int TL_W = 64, TL_H = 2 * (NT / TL_W);
-constexpr int TL_WW = TL_W + 8, TL_WH = TL_H + 4;
-constexpr int TL_LD = (TL_WW * TL_WH + NT - 1) / NT;     // window elements per thread
 
 template <int TYPE> struct NParams;
 template <> struct NParams<SSK_MOTION_TRANSLATION> { static constexpr int M = 2; };
@@ -71,8 +66,8 @@ struct Shared {
   double tot[NSMAX];          // cluster totals
   double wpart[NW][NSMAX];
   float gw[FT_IH][FT_IW + 1]; // warped-image tile of the forward methods
-  float win[2][TL_WH][TL_WW]; // staged windows of the current image (tiled inverse-compositional pass), double buffered
-  int4 tw[2];                 // their origins: {ox, oy, fits, -}
+  unsigned long long tl_full[4], tl_empty[4];   // TMA-staged pass: transaction barrier / consumer barrier per stage
+  int4 tl_meta[4][2];         // per stage: {window origin x, y, first tap-safe wx, count} {first tap-safe wy, count, -, -}
   // ---- solver state: identical in every CTA of the cluster ----
   ssk_transform t;            // transform being estimated (accepted parameters)
   ssk_transform tq;           // parameters of the next pass
@@ -101,6 +96,7 @@ struct Ctx {
   Shared *S;
   int rank, csize, tid;
   int buf;
+  unsigned tl_par, tl_used;   // TMA-staged pass: per stage, parity of the uses so far / stage used at all (uniform across the CTA)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -462,13 +458,35 @@ struct Walk {
     if (x >= cols) { x -= cols; ++y; }
   }
 };
+// The same walk with the coordinates also kept as floats (exact: they are integers below 2^24), so that the per-pixel
+// int-to-float conversions (XU pipe) become additions.
+#ifndef SSK_ECC_FWALK
+#define SSK_ECC_FWALK 1
+#endif
+struct WalkF : Walk {
+  float fx, fy, fdx, fdy, fcols;
+  __device__ __forceinline__ WalkF(int start, int stride_, int cols_) : Walk(start, stride_, cols_) {
+    fx = (float)x; fy = (float)y; fdx = (float)dx; fdy = (float)dy; fcols = (float)cols_;
+  }
+  __device__ __forceinline__ void next() {
+#if SSK_ECC_FWALK
+    i += stride; x += dx; y += dy; fx += fdx; fy += fdy;
+    if (x >= cols) { x -= cols; ++y; fx -= fcols; fy += 1.0f; }
+#else
+    Walk::next(); fx = (float)x; fy = (float)y;
+#endif
+  }
+};
 
 // Pixels of a level one CTA of the cluster visits in a pass.  SSK_ECC_BANDS (default): rank r owns the contiguous band
 // [r * chunk, (r + 1) * chunk) and walks it NT pixels at a time, so that the source row a bilinear tap pair touches for
 // output row y is still in L1 when row y + 1 needs it (the interleaved assignment sent consecutive rows to different
 // SMs).  The order of the per-thread partial sums changes with it, their fixed-order double reduction does not.
+// compute_correlation's sums gathered by the level-0 passes of the IC-LM solver: 0 = never (separate pass_rho), 1 = by every
+// level-0 pass, 2 = by the trial passes only (the accepted trial is the one the solver ends on; a level that accepts no trial
+// falls back to pass_rho)
 #ifndef SSK_ECC_RHO_FUSION
-#define SSK_ECC_RHO_FUSION 0
+#define SSK_ECC_RHO_FUSION 2
 #endif
 __device__ __forceinline__ bool getenv_no_rho_fusion() { return !SSK_ECC_RHO_FUSION; }
 #ifndef SSK_ECC_BANDS
@@ -611,7 +629,7 @@ __device__ void pass_ic(Ctx &c, int lvl, bool lm_masks) {
   const int n = cols * rows;
   // Branch-free body (invalid pixels contribute an exact 0.0), so that several pixels per thread are in flight.
   const Band bd = pass_band(c.rank, c.csize, c.tid, n);
-  Walk w(bd.start, bd.stride, cols);
+  WalkF w(bd.start, bd.stride, cols);
   const float hx = nearest_hi(cols), hy = nearest_hi(rows);
 #ifndef SSK_ECC_UNROLL_RHO
 #define SSK_ECC_UNROLL_RHO 3
@@ -619,7 +637,7 @@ __device__ void pass_ic(Ctx &c, int lvl, bool lm_masks) {
   constexpr int kUnroll = RHO ? SSK_ECC_UNROLL_RHO : 3;   // pixels in flight per thread (measured: 2 -> 3 is -4 % on the pass, 4 is slower)
 #pragma unroll kUnroll
   for (; w.i < bd.end; w.next()) {
-    const float x = (float)w.x, y = (float)w.y;
+    const float x = w.fx, y = w.fy;
     float u, v;
     map_xy_t<MapKind<TYPE>::MT>(m, x, y, u, v);
     const int sx = cvround32(u), sy = cvround32(v);
@@ -673,26 +691,77 @@ __device__ void pass_ic(Ctx &c, int lvl, bool lm_masks) {
   }
 }
 
-// Tiled form of pass_ic (same sums, same per-pixel arithmetic): the level is cut into row bands, one per CTA of the
-// cluster, and each band into TL_W x TL_H tiles.  The four bilinear taps of a pixel are read from a window of the
-// current image staged in shared memory instead of four gathers that wait on L2: the window of tile t + 1 (loaded with
-// the tap coordinates clamped to the image = lin_sample's replicate rule) and the reference / gradient samples of the
-// thread's own two pixels travel in registers while tile t is evaluated, one CTA barrier per tile.  The window origin
-// follows the map at the tile corners (affine-like maps are monotone along both axes); a tile whose footprint does
-// not fit the window (large rotation or scale) falls back to the direct gathers.
+// ------------------------------------------------------------------------------------------------
+// TMA-staged form of pass_ic (same sums, same per-pixel arithmetic) for the large levels of a pyramid.
+// The level is cut into TL_W x TL_H tiles, dealt to the CTAs of the cluster as contiguous ranges of the row-major tile
+// order.  Per tile the copy engine brings four boxes into one of NSTAGE shared-memory stages: the reference, gx and gy tiles
+// (2-D tensor maps of the level) and the window of the current image that holds every bilinear tap of the tile (3-D tensor
+// map over all frame slots of the level: x, y, slot).  The window origin follows the map at the tile corners (affine-like
+// maps are monotone along both axes).  One warp per tile (round robin) plans and issues the copies two tiles ahead; every
+// warp waits on the stage's transaction barrier, evaluates its 4 pixels of the tile from shared memory and arrives on
+// the stage's "empty" barrier - no CTA barrier inside a pass, no global load in the pixel loop.
+// A pixel whose 2 x 2 tap footprint leaves the window or the image (the copy engine fills zeros there, the reference
+// semantics want the replicated border) takes lin_sample's gather instead: same arithmetic, rare.
+// ------------------------------------------------------------------------------------------------
+#ifndef SSK_ECC_TMA
+#define SSK_ECC_TMA 1
+#endif
+constexpr int TL_W = 64, TL_H = 4 * (NT / TL_W);          // 4 pixels per thread: rows tq, tq + NT/TL_W, ...
+constexpr int TL_WW = 76, TL_WH = TL_H + 6;               // window: 2 taps + 3 columns of origin alignment + drift of the map over a tile
+constexpr int TL_NSTAGE = 4;
+constexpr unsigned TL_TILE_BYTES = TL_W * TL_H * 4;
+constexpr unsigned TL_WIN_BYTES = TL_WW * TL_WH * 4;
+constexpr unsigned TL_WIN_SLOT = (TL_WIN_BYTES + 127) & ~127u;
+constexpr unsigned TL_STAGE_BYTES = TL_WIN_SLOT + 3 * TL_TILE_BYTES;
+constexpr unsigned TL_DYN_SMEM = TL_NSTAGE * TL_STAGE_BYTES + 128;
+static_assert(TL_W == 64 && (TL_WW * 4) % 16 == 0, "tile geometry");
+
+__device__ __forceinline__ void ecc_mbar_init(unsigned mbar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count));
+}
+__device__ __forceinline__ void ecc_mbar_expect_tx(unsigned mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ecc_mbar_arrive(unsigned mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void ecc_mbar_wait(unsigned mbar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "SSK_ECC_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra SSK_ECC_MBAR_DONE;\n"
+      "bra SSK_ECC_MBAR_WAIT;\n"
+      "SSK_ECC_MBAR_DONE:\n"
+      "}\n" ::"r"(mbar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void ecc_tma_2d(unsigned dst, const void *tmap, int x, int y, unsigned mbar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(tmap), "r"(x), "r"(y), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void ecc_tma_3d(unsigned dst, const void *tmap, int x, int y, int z, unsigned mbar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+               "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(mbar) : "memory");
+}
+
+// true when level lvl of this launch can take the TMA-staged pass
+__device__ __forceinline__ bool level_uses_tma(const Ctx &c, int lvl) {
+  return SSK_ECC_TMA && lvl < c.cfg->tma_levels && c.frame->cmask == nullptr;
+}
+
 template <int TYPE, bool RHO>
-__device__ void pass_ic_tiled(Ctx &c, int lvl, bool lm_masks) {
+__device__ void pass_ic_tma(Ctx &c, int lvl, bool lm_masks) {
   constexpr int M = NParams<TYPE>::M;
   constexpr int NS = 2 + M + (RHO ? 6 : 0);
   constexpr int OR = 2 + M;
   constexpr int MT = MapKind<TYPE>::MT;
+  constexpr int RQ = NT / TL_W;        // row step between the pixels of a thread
   Shared &S = *c.S;
   const EccLevel &L = c.cfg->lv[lvl];
   const float *__restrict__ cur = opaque_ptr(c.frame->pyr + L.cur_off);
-  const float *__restrict__ ref = L.ref, *__restrict__ gxp = L.gx, *__restrict__ gyp = L.gy;
   const uint8_t *__restrict__ rmask = lm_masks ? L.refmask : nullptr;
   const uint8_t *__restrict__ rho_mask = RHO ? L.refmask : nullptr;
-  const uint8_t *__restrict__ cm = c.frame->cmask ? c.frame->cmask + L.cur_off : nullptr;
   const int cols = L.cols, rows = L.rows;
   const MapCoef m = S.map;
   const JCoef jc = S.jc;
@@ -701,18 +770,29 @@ __device__ void pass_ic_tiled(Ctx &c, int lvl, bool lm_masks) {
   for (int k = 0; k < NS; ++k) acc[k] = 0.0;
   int nvalid = 0, nrho = 0;
   const float hx = nearest_hi(cols), hy = nearest_hi(rows);
-  // band of tile rows of this CTA
   const int ntx = (cols + TL_W - 1) / TL_W, nty = (rows + TL_H - 1) / TL_H;
-  const int per = (nty + c.csize - 1) / c.csize;
-  const int ty0 = min(nty, c.rank * per), ty1 = min(nty, ty0 + per);
-  const int ntiles = (ty1 - ty0) * ntx;
+  const int per = (ntx * nty + c.csize - 1) / c.csize;
+  const int t0 = min(ntx * nty, c.rank * per), t1 = min(ntx * nty, t0 + per);
+  const int ntiles = t1 - t0;
   const int tx = c.tid & (TL_W - 1), tq = c.tid / TL_W;
   const int lane = c.tid & 31, warp = c.tid >> 5;
+  extern __shared__ unsigned char ecc_dyn_smem[];
+  const unsigned char *dynp = ecc_dyn_smem + ((128u - ((unsigned)__cvta_generic_to_shared(ecc_dyn_smem) & 127u)) & 127u);
+  const unsigned dyn0 = (unsigned)__cvta_generic_to_shared(dynp);
+  const unsigned full0 = (unsigned)__cvta_generic_to_shared(&S.tl_full[0]), empty0 = (unsigned)__cvta_generic_to_shared(&S.tl_empty[0]);
+  const int slot = (int)((c.frame->pyr - c.cfg->pyr_base) / c.cfg->pyr_floats);
+  const unsigned char *tm = c.cfg->tm[lvl][0];
 
-  // window origin of tile t, by the first four lanes of warp 0 (one tile corner each)
-  auto plan_tile = [&](int t, int slot) {
-    if (warp != 0) return;
-    const int x0 = (t % ntx) * TL_W, y0 = (ty0 + t / ntx) * TL_H;
+  // The stage barriers are initialised once per kernel (k_ecc) and keep their phase across passes: use u of stage s
+  // completes phase u of both barriers; tl_par / tl_used carry the parities into this pass.
+  const unsigned par0 = c.tl_par, used0 = c.tl_used;
+
+  // one warp: plan local tile j and ask the copy engine for its four boxes
+  auto issue = [&](int j) {
+    const int s = j % TL_NSTAGE;
+    const int t = t0 + j;
+    const int tyi = t / ntx, txi = t - tyi * ntx;
+    const int x0 = txi * TL_W, y0 = tyi * TL_H;
     const int x1 = min(x0 + TL_W - 1, cols - 1), y1 = min(y0 + TL_H - 1, rows - 1);
     float u, v;
     map_xy_t<MT>(m, (float)((lane & 1) ? x1 : x0), (float)((lane & 2) ? y1 : y0), u, v);
@@ -723,80 +803,70 @@ __device__ void pass_ic_tiled(Ctx &c, int lvl, bool lm_masks) {
       vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o)); vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
     }
     if (lane == 0) {
-      // taps of a pixel: columns ix, ix + 1 with floor(u) <= ix <= floor(u) + 1 (1/32-px rounding), likewise rows
+      // taps of a pixel: columns ix, ix + 1 with floor(u) - 1 <= ix <= floor(u) + 1 (1/32-px rounding, one ulp of slack
+      // for the corner bound), likewise rows
       const bool finite = umin > -1.0e8f && vmin > -1.0e8f && umax < 1.0e8f && vmax < 1.0e8f;
-      const int ox = finite ? (int)floorf(umin) : 0, oy = finite ? (int)floorf(vmin) : 0;
-      const bool fits = MT != MAP_HOMOGRAPHY && finite && (int)floorf(umax) + 2 - ox < TL_WW && (int)floorf(vmax) + 2 - oy < TL_WH;
-      S.tw[slot] = make_int4(ox, oy, fits ? 1 : 0, 0);
+      const int xl = finite ? (int)floorf(umin) - 1 : 0, yl = finite ? (int)floorf(vmin) - 1 : 0;
+      const int ox = xl & ~3;                  // the copy engine wants the box origin 16-byte aligned along the row
+      const bool fits = MT != MAP_HOMOGRAPHY && finite && (int)floorf(umax) + 2 - ox < TL_WW && (int)floorf(vmax) + 2 - yl < TL_WH;
+      // window coordinates (wx, wy) of a pixel's first tap for which all four taps are inside window and image
+      const int wx_lo = max(0, -ox), wx_hi = min(TL_WW - 1, cols - 1 - ox);
+      const int wy_lo = max(0, -yl), wy_hi = min(TL_WH - 1, rows - 1 - yl);
+      const unsigned up = ((par0 >> s) ^ (unsigned)(j / TL_NSTAGE)) & 1u;     // parity of this use of the stage
+      if (j >= TL_NSTAGE || ((used0 >> s) & 1u)) ecc_mbar_wait(empty0 + 8 * s, up ^ 1u);
+      S.tl_meta[s][0] = make_int4(ox, yl, wx_lo, fits ? max(0, wx_hi - wx_lo) : 0);
+      S.tl_meta[s][1] = make_int4(wy_lo, max(0, wy_hi - wy_lo), 0, 0);
+      const unsigned st = dyn0 + s * TL_STAGE_BYTES, mb = full0 + 8 * s;
+      ecc_mbar_expect_tx(mb, 3 * TL_TILE_BYTES + (fits ? TL_WIN_BYTES : 0u));
+      ecc_tma_2d(st + TL_WIN_SLOT, tm + 128, x0, y0, mb);
+      ecc_tma_2d(st + TL_WIN_SLOT + TL_TILE_BYTES, tm + 256, x0, y0, mb);
+      ecc_tma_2d(st + TL_WIN_SLOT + 2 * TL_TILE_BYTES, tm + 384, x0, y0, mb);
+      if (fits) ecc_tma_3d(st, tm, ox, yl, slot, mb);
     }
+    __syncwarp();
   };
-  float wreg[TL_LD];                 // window elements of the next tile
-  float pf[2], pgx[2], pgy[2];       // reference / gradient samples of this thread's pixels of the next tile
-  auto prefetch_tile = [&](int t, const int4 w) {
-    const int x0 = (t % ntx) * TL_W, y0 = (ty0 + t / ntx) * TL_H;
-    if (w.z) {
-#pragma unroll
-      for (int i = 0; i < TL_LD; ++i) {
-        const int e = c.tid + i * NT;
-        const int r = e / TL_WW, q = e - r * TL_WW;
-        const int gy_ = min(max(w.y + r, 0), rows - 1), gx_ = min(max(w.x + q, 0), cols - 1);
-        wreg[i] = e < TL_WW * TL_WH ? __ldg(cur + ((unsigned)(gy_ * cols) + (unsigned)gx_)) : 0.f;
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int x = min(x0 + tx, cols - 1), y = min(y0 + tq + k * (TL_H / 2), rows - 1);
-      const unsigned i = (unsigned)(y * cols) + (unsigned)x;
-      pf[k] = __ldg(ref + i); pgx[k] = __ldg(gxp + i); pgy[k] = __ldg(gyp + i);
-    }
-  };
+  constexpr int AHEAD = TL_NSTAGE - 2;    // tiles issued ahead of the one being evaluated
+  for (int j = 0; j < min(AHEAD, ntiles); ++j)
+    if (warp == j % NW) issue(j);
 
-  if (ntiles > 0) plan_tile(0, 0);
-  __syncthreads();
-  int4 wnext = S.tw[0];
-  if (ntiles > 0) prefetch_tile(0, wnext);
 #pragma unroll 1
-  for (int t = 0; t < ntiles; ++t) {
-    const int b = t & 1;
-    const int4 w = wnext;
-    if (w.z) {
-#pragma unroll
-      for (int i = 0; i < TL_LD; ++i) {
-        const int e = c.tid + i * NT;
-        if (e < TL_WW * TL_WH) (&S.win[b][0][0])[e] = wreg[i];
-      }
-    }
-    const float f0 = pf[0], f1 = pf[1], gx0 = pgx[0], gx1 = pgx[1], gy0 = pgy[0], gy1 = pgy[1];
-    if (t + 1 < ntiles) plan_tile(t + 1, b ^ 1);
-    __syncthreads();                       // window of tile t and the origin of tile t + 1 are visible
-    if (t + 1 < ntiles) { wnext = S.tw[b ^ 1]; prefetch_tile(t + 1, wnext); }
-    const int x0 = (t % ntx) * TL_W, y0 = (ty0 + t / ntx) * TL_H;
+  for (int j = 0; j < ntiles; ++j) {
+    if (j + AHEAD < ntiles && warp == (j + AHEAD) % NW) issue(j + AHEAD);
+    const int s = j % TL_NSTAGE;
+    const int t = t0 + j;
+    const int tyi = t / ntx, txi = t - tyi * ntx;
+    const int x0 = txi * TL_W, y0 = tyi * TL_H;
+    ecc_mbar_wait(full0 + 8 * s, ((par0 >> s) ^ (unsigned)(j / TL_NSTAGE)) & 1u);
+    const int4 ma = S.tl_meta[s][0], mb4 = S.tl_meta[s][1];
+    const unsigned char *stg = dynp + s * TL_STAGE_BYTES;
+    const float *win = reinterpret_cast<const float *>(stg);
+    const float *sref = reinterpret_cast<const float *>(stg + TL_WIN_SLOT) + tq * TL_W + tx;
     const int xi = x0 + tx;
     const float x = (float)min(xi, cols - 1);
+    const float ymax = (float)(rows - 1);
+    const float yb = (float)(y0 + tq);
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int yi = y0 + tq + k * (TL_H / 2);
+    for (int k = 0; k < 4; ++k) {
+      const int yi = y0 + tq + k * RQ;
       const bool inb = xi < cols && yi < rows;
-      const float y = (float)min(yi, rows - 1);
+      const float y = fminf(yb + (float)(k * RQ), ymax);
       float u, v;
       map_xy_t<MT>(m, x, y, u, v);
       const int sx = cvround32(u), sy = cvround32(v);
       bool ok;
       if (lm_masks) ok = u >= -0.5f && u <= hx && v >= -0.5f && v <= hy;   // cvRound(u), cvRound(v) inside the image
       else ok = lin_valid(sx, sy, cols, rows);
-      if (cm) {
-        if (lm_masks) ok = ok && cm[min(max(__float2int_rn(v), 0), rows - 1) * cols + min(max(__float2int_rn(u), 0), cols - 1)] != 0;
-        else ok = mask_lin_value(cm, cols, rows, sx, sy) >= 250;
+      if (rmask || rho_mask) {
+        const unsigned pi = (unsigned)(min(yi, rows - 1) * cols) + (unsigned)min(xi, cols - 1);
+        if (rmask) ok = ok && rmask[pi] != 0;
       }
-      const unsigned pi = (unsigned)(min(yi, rows - 1) * cols) + (unsigned)min(xi, cols - 1);
-      if (rmask) ok = ok && rmask[pi] != 0;
       ok = ok && inb;
+      const int wx = (sx >> 5) - ma.x, wy = (sy >> 5) - ma.y;
       float g;
-      if (w.z) {
-        const int wx = (sx >> 5) - w.x, wy = (sy >> 5) - w.y;
+      if ((unsigned)(wx - ma.z) < (unsigned)ma.w && (unsigned)(wy - mb4.x) < (unsigned)mb4.y) {
         const float txf = frac32(sx), tyf = frac32(sy);
         const float wx0 = 1.0f - txf, wy0 = 1.0f - tyf;
-        const float *p0 = &S.win[b][wy][wx];
+        const float *p0 = win + wy * TL_WW + wx;
         const float s00 = p0[0], s01 = p0[1], s10 = p0[TL_WW], s11 = p0[TL_WW + 1];
         g = __fadd_rn(__fmul_rn(s00, __fmul_rn(wy0, wx0)), __fmul_rn(s01, __fmul_rn(wy0, txf)));
         g = __fadd_rn(g, __fmul_rn(s10, __fmul_rn(tyf, wx0)));
@@ -804,32 +874,32 @@ __device__ void pass_ic_tiled(Ctx &c, int lvl, bool lm_masks) {
       } else {
         g = lin_sample(cur, cols, rows, sx, sy);
       }
-      const float fref = k ? f1 : f0;
+      const float fref = sref[k * RQ * TL_W];
+      const float gxv = sref[TL_W * TL_H + k * RQ * TL_W], gyv = sref[2 * TL_W * TL_H + k * RQ * TL_W];
       const float rhs = g - fref;
       if (RHO) {
-        bool okr = (cm ? mask_lin_value(cm, cols, rows, sx, sy) >= 254 : lin_valid(sx, sy, cols, rows)) && inb;
-        if (rho_mask) okr = okr && rho_mask[pi] != 0;
+        bool okr = lin_valid(sx, sy, cols, rows) && inb;
+        if (rho_mask) okr = okr && rho_mask[(unsigned)(min(yi, rows - 1) * cols) + (unsigned)min(xi, cols - 1)] != 0;
         const double gd = okr ? (double)g : 0.0, fd = okr ? (double)fref : 0.0;
         nrho += okr ? 1 : 0;
         acc[OR + 1] += fd; acc[OR + 2] += gd; acc[OR + 3] += fd * fd; acc[OR + 4] += gd * gd; acc[OR + 5] += fd * gd;
       }
       float J[M];
-      eval_J<TYPE>(jc, x, y, k ? gx1 : gx0, k ? gy1 : gy0, J);
-      if (TYPE == SSK_MOTION_HOMOGRAPHY) {
-        if (ok) {
-          acc[0] += (double)rhs * (double)rhs;
-          ++nvalid;
+      eval_J<TYPE>(jc, x, y, gxv, gyv, J);
+      const double r = ok ? (double)rhs : 0.0;
+      acc[0] += r * r;
+      nvalid += ok ? 1 : 0;
 #pragma unroll
-          for (int q = 0; q < M; ++q) acc[2 + q] += (double)J[q] * (double)rhs;
-        }
-      } else {
-        const double r = ok ? (double)rhs : 0.0;
-        acc[0] += r * r;
-        nvalid += ok ? 1 : 0;
-#pragma unroll
-        for (int q = 0; q < M; ++q) acc[2 + q] += (double)J[q] * r;
-      }
+      for (int q = 0; q < M; ++q) acc[2 + q] += (double)J[q] * r;
     }
+    __syncwarp();
+    if (lane == 0) ecc_mbar_arrive(empty0 + 8 * s);
+  }
+#pragma unroll
+  for (int s = 0; s < TL_NSTAGE; ++s) {
+    const int uses = ntiles > s ? (ntiles - s + TL_NSTAGE - 1) / TL_NSTAGE : 0;
+    c.tl_par ^= (unsigned)(uses & 1) << s;
+    c.tl_used |= (unsigned)(uses > 0) << s;
   }
   acc[1] = (double)nvalid;
   if (RHO) acc[OR] = (double)nrho;
@@ -840,16 +910,12 @@ __device__ void pass_ic_tiled(Ctx &c, int lvl, bool lm_masks) {
   }
 }
 
-// Measured on B200 (config #2, 128 frames): 5.15 ms against 2.89 ms for the gather form - staging the window with
-// ordinary loads costs as many instructions per element (clamps, address arithmetic, STS) as the four gathers it
-// replaces, and adds a CTA barrier per 512 pixels.  Kept for reference / as the base of a TMA-staged form; off.
-#ifndef SSK_ECC_TILED
-#define SSK_ECC_TILED 0
-#endif
 template <int TYPE, bool RHO>
 __device__ __forceinline__ void pass_ic_any(Ctx &c, int lvl, bool lm_masks) {
-  if (SSK_ECC_TILED && TYPE != SSK_MOTION_HOMOGRAPHY) pass_ic_tiled<TYPE, RHO>(c, lvl, lm_masks);
-  else pass_ic<TYPE, RHO>(c, lvl, lm_masks);
+  if constexpr (TYPE != SSK_MOTION_HOMOGRAPHY) {
+    if (level_uses_tma(c, lvl)) { pass_ic_tma<TYPE, RHO>(c, lvl, lm_masks); return; }
+  }
+  pass_ic<TYPE, RHO>(c, lvl, lm_masks);
 }
 
 // reference-side normal matrix Hp = J^T J (ecc_compute_hessian_matrix, ecc2.cc:295-322): sums = lower triangle
@@ -1021,11 +1087,11 @@ __device__ void pass_rho(Ctx &c) {
   int nvalid = 0;
   const int n = cols * rows;
   const Band bd = pass_band(c.rank, c.csize, c.tid, n);
-  Walk w(bd.start, bd.stride, cols);
+  WalkF w(bd.start, bd.stride, cols);
 #pragma unroll 2
   for (; w.i < bd.end; w.next()) {
     float u, v;
-    map_xy_t<MT>(m, (float)w.x, (float)w.y, u, v);
+    map_xy_t<MT>(m, w.fx, w.fy, u, v);
     const int sx = cvround32(u), sy = cvround32(v);
     bool ok = cm ? mask_lin_value(cm, cols, rows, sx, sy) >= 254 : lin_valid(sx, sy, cols, rows);
     if (rmask) ok = ok && rmask[w.i] != 0;
@@ -1108,12 +1174,13 @@ __device__ bool align_iclm(Ctx &c, int lvl, double max_eps, bool main_pass) {
   while (S.num_it < cfg.max_iterations) {
     if (S.recompute) {
       T0_BEGIN set_pass_params(S, S.t); T0_END
-      if (with_rho) pass_ic_any<TYPE, true>(c, lvl, true); else pass_ic_any<TYPE, false>(c, lvl, true);
+      const bool rho_init = with_rho && SSK_ECC_RHO_FUSION == 1;
+      if (rho_init) pass_ic_any<TYPE, true>(c, lvl, true); else pass_ic_any<TYPE, false>(c, lvl, true);
       T0_BEGIN
       const double CMA = S.tot[1], RMA = L.RMA;
       S.err = S.tot[0] * (RMA * RMA) / (CMA * CMA);
       for (int i = 0; i < M; ++i) S.v[i] = __fmul_rn((float)S.tot[2 + i], (float)(RMA / CMA));
-      if (with_rho) { for (int i = 0; i < 6; ++i) S.rho_acc[i] = S.rho_try[i]; S.rho_have = 1; }
+      if (rho_init) { for (int i = 0; i < 6; ++i) S.rho_acc[i] = S.rho_try[i]; S.rho_have = 1; }
       T0_END
     }
     do {
@@ -1164,7 +1231,7 @@ __device__ bool align_iclm(Ctx &c, int lvl, double max_eps, bool main_pass) {
       S.err = S.newerr;
       S.recompute = 0;
       for (int i = 0; i < M; ++i) { S.t.params[i] = S.tq.params[i]; S.v[i] = S.vtrial[i]; }
-      if (with_rho) { for (int i = 0; i < 6; ++i) S.rho_acc[i] = S.rho_try[i]; }   // sums of the pass that evaluated tq
+      if (with_rho) { for (int i = 0; i < 6; ++i) S.rho_acc[i] = S.rho_try[i]; S.rho_have = 1; }   // sums of the pass that evaluated tq
     }
     T0_END
     if (S.dp < max_eps) break;
@@ -1421,9 +1488,17 @@ __global__ void __launch_bounds__(NT, SSK_ECC_MINB) k_ecc(const __grid_constant_
   c.rank = (int)cluster.block_rank();
   c.tid = threadIdx.x;
   c.buf = 0;
+  c.tl_par = 0; c.tl_used = 0;
   c.S = &S;
   EccFrame *fr = frames + blockIdx.x / c.csize;
   c.frame = fr;
+  if (c.tid == 0) {     // stage barriers of the TMA-staged passes (the T0 section below orders this before any use)
+    for (int s = 0; s < TL_NSTAGE; ++s) {
+      ecc_mbar_init((unsigned)__cvta_generic_to_shared(&S.tl_full[s]), 1);
+      ecc_mbar_init((unsigned)__cvta_generic_to_shared(&S.tl_empty[s]), NW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
 
   T0_BEGIN
   S.t = fr->t;
@@ -1475,11 +1550,12 @@ __global__ void __launch_bounds__(NT, SSK_ECC_MINB) k_ecc(const __grid_constant_
   cluster.sync();   // no CTA may exit while a peer can still read its shared memory
 }
 
-inline int launch_clustered(const void *kernel, void **args, int nclusters, int cluster_size, cudaStream_t s) {
+inline int launch_clustered(const void *kernel, void **args, int nclusters, int cluster_size, cudaStream_t s, unsigned dyn_smem = 0) {
+  if (dyn_smem) SSK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3(nclusters * cluster_size);
   lc.blockDim = dim3(NT);
-  lc.dynamicSmemBytes = 0;
+  lc.dynamicSmemBytes = dyn_smem;
   lc.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1505,7 +1581,9 @@ int launch_ecc_method(const EccConfig &cfg, EccFrame *frames, int nframes, int c
     case SSK_MOTION_HOMOGRAPHY: k = (const void *)k_ecc<METHOD, SSK_MOTION_HOMOGRAPHY>; break;
     default: set_error("ECC: unsupported motion type"); return SSK_ERR_INVALID;
   }
-  return launch_clustered(k, args, nframes, cluster_size, s);
+  const bool ic = METHOD == SSK_ECC_INVERSE_COMPOSITIONAL || METHOD == SSK_ECC_INVERSE_COMPOSITIONAL_LM;
+  const unsigned dyn = ic && cfg.tma_levels > 0 && cfg.motion_type != SSK_MOTION_HOMOGRAPHY ? TL_DYN_SMEM : 0u;
+  return launch_clustered(k, args, nframes, cluster_size, s, dyn);
 }
 
 }  // namespace

@@ -226,6 +226,25 @@ int Ecch::build_config() {
     L.cur_off = loff[l];
     L.RMA = rma[l];
   }
+  // TMA-staged passes of the inverse-compositional solvers on the large levels (ssk_ecc_impl.cuh::pass_ic_tma): rows must
+  // be 16-byte multiples for the copy engine; small levels stay on the gather pass (latency-bound either way)
+  cfg.tma_levels = 0;
+  cfg.pyr_base = cur_pyr.as<float>();
+  cfg.pyr_floats = pyr_floats;
+  const bool ic_method = opts.method == SSK_ECC_INVERSE_COMPOSITIONAL || opts.method == SSK_ECC_INVERSE_COMPOSITIONAL_LM;
+  static const bool no_tma = getenv("SSK_ECC_NO_TMA") != nullptr;
+  if (ic_method && !no_tma && cur_pyr.p && capacity > 0 && ref_gx.p && ref_gy.p) {
+    for (int l = 0; l < std::min(nlevels, kTmaLevels); ++l) {
+      if ((lw[l] & 3) || (int64_t)lw[l] * lh[l] < 32768) break;
+      const int64_t step = (int64_t)lw[l] * 4;
+      if (!encode_tmap_3d_f32(cfg.tm[l][0], cur_pyr.as<float>() + loff[l], lw[l], lh[l], capacity, step, pyr_floats * 4, ecc_tma_win_w(), ecc_tma_win_h()) ||
+          !encode_tmap_2d_f32(cfg.tm[l][1], ref_pyr.as<float>() + loff[l], lw[l], lh[l], step, ecc_tma_tile_w(), ecc_tma_tile_h()) ||
+          !encode_tmap_2d_f32(cfg.tm[l][2], ref_gx.as<float>() + loff[l], lw[l], lh[l], step, ecc_tma_tile_w(), ecc_tma_tile_h()) ||
+          !encode_tmap_2d_f32(cfg.tm[l][3], ref_gy.as<float>() + loff[l], lw[l], lh[l], step, ecc_tma_tile_w(), ecc_tma_tile_h()))
+        break;
+      cfg.tma_levels = l + 1;
+    }
+  }
   cfg.method = opts.method;
   cfg.interp = remap_interp(opts.interpolation);
   cfg.max_iterations = opts.max_iterations;

@@ -49,6 +49,8 @@ int launch_bayer_warp_accumulate(const WarpAccArgs &a, const Tables &tab, int co
 int staged_box_w();
 int staged_box_h();
 bool encode_tmap_2d_f32(void *out128, const void *base, int cols, int rows, int64_t step_bytes, int box_w, int box_h);
+bool encode_tmap_3d_f32(void *out128, const void *base, int cols, int rows, int depth, int64_t step_bytes, int64_t slice_bytes, int box_w,
+                        int box_h);
 
 // cv::remap of a CV_32F image (cn 1..4) by an analytic map or an explicit CV_32FC2 map.
 struct RemapArgs {
