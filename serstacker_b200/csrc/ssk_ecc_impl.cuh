@@ -66,8 +66,8 @@ struct Shared {
   double tot[NSMAX];          // cluster totals
   double wpart[NW][NSMAX];
   float gw[FT_IH][FT_IW + 1]; // warped-image tile of the forward methods
-  unsigned long long tl_full[4], tl_empty[4];   // TMA-staged pass: transaction barrier / consumer barrier per stage
-  int4 tl_meta[4][2];         // per stage: {window origin x, y, first tap-safe wx, count} {first tap-safe wy, count, -, -}
+  unsigned long long tl_full[8], tl_empty[8];   // TMA-staged pass: transaction barrier / consumer barrier per stage
+  int4 tl_meta[8][2];         // per stage: {window origin x, y, first tap-safe wx, count} {first tap-safe wy, count, -, -}
   // ---- solver state: identical in every CTA of the cluster ----
   ssk_transform t;            // transform being estimated (accepted parameters)
   ssk_transform tq;           // parameters of the next pass
@@ -523,7 +523,11 @@ __device__ __forceinline__ int cvround32(float v) {
 // (float)(s & 31) / 32 without an integer-to-float conversion: 1 + f / 32 assembled in the mantissa, minus one (exact)
 __device__ __forceinline__ float frac32(int s) {
 #if SSK_ECC_FASTROUND
-  return __fsub_rn(__int_as_float(0x3F800000 | ((s & 31) << 18)), 1.0f);
+  // ((s << 18) & 0x7c0000) | 0x3f800000 as one LOP3 (the constant 1.0f comes from a register the compiler cannot fold)
+  unsigned one = 0x3F800000u, r;
+  asm("" : "+r"(one));
+  asm("lop3.b32 %0, %1, 0x7c0000, %2, 0xEA;" : "=r"(r) : "r"((unsigned)s << 18), "r"(one));
+  return __fsub_rn(__uint_as_float(r), 1.0f);
 #else
   return (float)(s & 31) * 0.03125f;
 #endif
@@ -708,7 +712,10 @@ __device__ void pass_ic(Ctx &c, int lvl, bool lm_masks) {
 #endif
 constexpr int TL_W = 64, TL_H = 4 * (NT / TL_W);          // 4 pixels per thread: rows tq, tq + NT/TL_W, ...
 constexpr int TL_WW = 76, TL_WH = TL_H + 6;               // window: 2 taps + 3 columns of origin alignment + drift of the map over a tile
-constexpr int TL_NSTAGE = 4;
+#ifndef SSK_ECC_NSTAGE
+#define SSK_ECC_NSTAGE 4
+#endif
+constexpr int TL_NSTAGE = SSK_ECC_NSTAGE;
 constexpr unsigned TL_TILE_BYTES = TL_W * TL_H * 4;
 constexpr unsigned TL_WIN_BYTES = TL_WW * TL_WH * 4;
 constexpr unsigned TL_WIN_SLOT = (TL_WIN_BYTES + 127) & ~127u;

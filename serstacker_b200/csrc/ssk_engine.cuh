@@ -54,6 +54,7 @@ class Ecch {
  public:
   ssk_ecch_options opts;
   cudaStream_t stream = nullptr;
+  bool cluster_fixed = false;   // SSK_ECC_CLUSTER given
   int cluster_size = 8;   // CTAs per frame (SSK_ECC_CLUSTER overrides); 8 x 256 threads, >= 2 CTAs per SM: a 64-frame batch is resident at once
 
   int nlevels = 0;
