@@ -45,6 +45,7 @@ enum { SSK_8U = 0, SSK_16U = 2, SSK_32F = 5 };
 #define SSK_32FC1 SSK_MAKETYPE(SSK_32F, 1)
 #define SSK_32FC2 SSK_MAKETYPE(SSK_32F, 2)
 #define SSK_32FC3 SSK_MAKETYPE(SSK_32F, 3)
+#define SSK_32FC4 SSK_MAKETYPE(SSK_32F, 4)
 
 enum { SSK_MEM_HOST = 0, SSK_MEM_DEVICE = 1 };
 
@@ -121,8 +122,28 @@ typedef struct ssk_ecc_registration_options {
   int32_t replace_planetary_disk_with_mask;
 } ssk_ecc_registration_options;
 
-/* c_image_registration_options, c_frame_registration.h:119-136 (ECC members; the sparse-feature and
- * eccflow stages are out of scope and must stay disabled). */
+/* ECCFlowDownscaleMethod, ecc2.h:503-507 (same order). */
+enum { SSK_ECCFLOW_DOWNSCALE_RECURSIVE_RESIZE = 0, SSK_ECCFLOW_DOWNSCALE_FULL_RESIZE = 1, SSK_ECCFLOW_DOWNSCALE_PYRAMID = 2 };
+
+/* c_eccflow_options, ecc2.h:515-527 (defaults via ssk_eccflow_options_default), which is also the layout of
+ * c_eccflow_registration_options, c_frame_registration.h:88-100 (defaults via ssk_eccflow_registration_options_default).
+ * input_smooth_sigma / reference_smooth_sigma are carried but, as in the reference, not used by the computation. */
+typedef struct ssk_eccflow_options {
+  double input_smooth_sigma;
+  double reference_smooth_sigma;
+  double update_multiplier;
+  double scale_factor;
+  double noise_level;
+  int32_t max_iterations;
+  int32_t support_scale;
+  int32_t min_image_size;
+  int32_t max_pyramid_level;
+  int32_t downscale_method;
+  int32_t reserved;
+} ssk_eccflow_options;
+
+/* c_image_registration_options, c_frame_registration.h:119-136 (ECC and eccflow members; the sparse-feature stage is out of
+ * scope and must stay disabled). */
 typedef struct ssk_registration_options {
   int32_t motion_type;
   int32_t interpolation;
@@ -130,6 +151,8 @@ typedef struct ssk_registration_options {
   double border_value[4];
   ssk_ecc_registration_options ecc;
   int32_t enable_ecc_registration;
+  int32_t enable_eccflow_registration;   /* c_frame_registration.cc:900-917: refine _current_remap per pixel after ECC */
+  ssk_eccflow_options eccflow;
 } ssk_registration_options;
 
 /* c_image_registration_status::ecc, c_frame_registration.h:198-207. */
@@ -227,6 +250,28 @@ SSK_API int ssk_reg_remap(ssk_reg *h, const ssk_mat *rmap, const ssk_mat *src, s
                           const ssk_mat *src_mask, ssk_mat *dst_mask,
                           int interpolation /*<0: options*/, int border_mode /*<0: options*/,
                           const double border_value[4]);
+
+/* ---------------------------------------------------------------------------------------------
+ * c_eccflow (ecc2.h:548-662, ecc2.cc:2220-2865): dense smooth optical flow on a coarse-to-fine pyramid.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ssk_eccflow ssk_eccflow;
+SSK_API void ssk_eccflow_options_default(ssk_eccflow_options *o);                /* ecc2.h:515-527 */
+SSK_API void ssk_eccflow_registration_options_default(ssk_eccflow_options *o);   /* c_frame_registration.h:88-100 */
+SSK_API int ssk_eccflow_create(const ssk_eccflow_options *opts, ssk_eccflow **out);
+SSK_API int ssk_eccflow_destroy(ssk_eccflow *h);
+/* c_eccflow::set_reference_image(reference_image, reference_mask): single-channel image (any depth, converted to CV_32F
+ * without scaling as convertTo does), optional CV_8UC1 mask. */
+SSK_API int ssk_eccflow_set_reference_image(ssk_eccflow *h, const ssk_mat *image, const ssk_mat *mask);
+/* c_eccflow::compute(input_image, rmap, input_mask): rmap is CV_32FC2 of the reference size, read as the initial map when
+ * use_initial_map != 0 (an "empty rmap" otherwise) and overwritten with the refined map. */
+SSK_API int ssk_eccflow_compute(ssk_eccflow *h, const ssk_mat *image, const ssk_mat *mask, ssk_mat *rmap, int use_initial_map);
+/* c_eccflow::current_uv(): the flow of the last compute (CV_32FC2 of the reference size). */
+SSK_API int ssk_eccflow_get_uv(ssk_eccflow *h, ssk_mat *uv);
+/* c_eccflow::current_pyramid() (debug / tests): number of levels, level geometry (size of the level and of its avgdown grid),
+ * level images: which = 0 reference_image, 1 current_image, 2 Ix, 3 Iy (CV_32FC1 of the level size), 4 D (CV_32FC4, grid size). */
+SSK_API int ssk_eccflow_num_levels(const ssk_eccflow *h);
+SSK_API int ssk_eccflow_level_size(const ssk_eccflow *h, int level, int *cols, int *rows, int *grid_cols, int *grid_rows);
+SSK_API int ssk_eccflow_get_image(ssk_eccflow *h, int which, int level, ssk_mat *dst);
 
 /* ---------------------------------------------------------------------------------------------
  * c_frame_accumulation (core/average/c_frame_accumulation.h:14-63, 222-262).

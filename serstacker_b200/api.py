@@ -130,11 +130,14 @@ class c_ecch:
 
 def registration_options(**kw):
     """c_image_registration_options with the reference defaults (c_frame_registration.h:47-64, 119-136);
-    keyword `ecc` is a dict of c_ecc_registration_options fields."""
+    keyword `ecc` is a dict of c_ecc_registration_options fields, `eccflow` one of c_eccflow_registration_options fields."""
     o = capi.ssk_registration_options()
     capi.lib.ssk_registration_options_default(C.byref(o))
     o.enable_ecc_registration = 1
     ecc = kw.pop("ecc", {})
+    for k, v in kw.pop("eccflow", {}).items():
+        assert hasattr(o.eccflow, k), k
+        setattr(o.eccflow, k, v)
     for k, v in kw.items():
         if k == "border_value":
             for i in range(4):
@@ -146,6 +149,67 @@ def registration_options(**kw):
         assert hasattr(o.ecc, k), k
         setattr(o.ecc, k, v)
     return o
+
+
+def eccflow_options(registration_defaults=False, **kw):
+    """c_eccflow_options (ecc2.h:515-527) or, with registration_defaults, the values c_frame_registration hands to c_eccflow
+    (c_eccflow_registration_options, c_frame_registration.h:88-100)."""
+    o = capi.ssk_eccflow_options()
+    (capi.lib.ssk_eccflow_registration_options_default if registration_defaults else capi.lib.ssk_eccflow_options_default)(C.byref(o))
+    for k, v in kw.items():
+        assert hasattr(o, k), k
+        setattr(o, k, v)
+    return o
+
+
+class c_eccflow:
+    """c_eccflow (ecc2.h:548-662)."""
+
+    def __init__(self, options=None):
+        self.options = options if options is not None else eccflow_options()
+        self._h = C.c_void_p()
+        check(capi.lib.ssk_eccflow_create(C.byref(self.options), C.byref(self._h)))
+        self._shape = None
+
+    def __del__(self):
+        if getattr(self, "_h", None) and capi is not None:
+            capi.lib.ssk_eccflow_destroy(self._h)
+            self._h = None
+
+    def set_reference_image(self, reference_image, reference_mask=None):
+        m = mat(np.ascontiguousarray(reference_image))
+        check(capi.lib.ssk_eccflow_set_reference_image(self._h, C.byref(m), ref(mat(reference_mask))))
+        self._shape = reference_image.shape[:2]
+        return True
+
+    def compute(self, input_image, rmap=None, input_mask=None):
+        """c_eccflow::compute(input_image, rmap, input_mask): returns the refined map (rmap = None: empty initial map)."""
+        out = np.zeros(self._shape + (2,), dtype=f32) if rmap is None else np.ascontiguousarray(rmap, dtype=f32).copy()
+        m, mo = mat(np.ascontiguousarray(input_image)), mat(out)
+        check(capi.lib.ssk_eccflow_compute(self._h, C.byref(m), ref(mat(input_mask)), C.byref(mo), 0 if rmap is None else 1))
+        return out
+
+    def current_uv(self):
+        out = np.empty(self._shape + (2,), dtype=f32)
+        mo = mat(out)
+        check(capi.lib.ssk_eccflow_get_uv(self._h, C.byref(mo)))
+        return out
+
+    def num_levels(self):
+        return capi.lib.ssk_eccflow_num_levels(self._h)
+
+    def level_size(self, level):
+        v = [C.c_int() for _ in range(4)]
+        check(capi.lib.ssk_eccflow_level_size(self._h, level, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    def pyramid_image(self, which, level):
+        """which: 0 reference_image, 1 current_image, 2 Ix, 3 Iy, 4 D (current_pyramid(), ecc2.h:555-560)."""
+        w, h, gw, gh = self.level_size(level)
+        out = np.empty((gh, gw, 4), dtype=f32) if which == 4 else np.empty((h, w), dtype=f32)
+        mo = mat(out)
+        check(capi.lib.ssk_eccflow_get_image(self._h, which, level, C.byref(mo)))
+        return out
 
 
 class c_frame_registration:

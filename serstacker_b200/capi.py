@@ -24,6 +24,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 
 MOTION_TRANSLATION, MOTION_EUCLIDEAN, MOTION_SCALED_EUCLIDEAN, MOTION_AFFINE, MOTION_HOMOGRAPHY = 0, 1, 2, 3, 4
 ECC_FORWARD_ADDITIVE, ECC_INVERSE_COMPOSITIONAL, ECC_LM, ECC_INVERSE_COMPOSITIONAL_LM = 0, 1, 2, 3
+ECCFLOW_DOWNSCALE_RECURSIVE_RESIZE, ECCFLOW_DOWNSCALE_FULL_RESIZE, ECCFLOW_DOWNSCALE_PYRAMID = 0, 1, 2
 INTER_NEAREST, INTER_LINEAR, INTER_CUBIC, INTER_AREA = 0, 1, 2, 3
 BORDER_CONSTANT, BORDER_REPLICATE, BORDER_REFLECT, BORDER_WRAP, BORDER_REFLECT101, BORDER_TRANSPARENT = 0, 1, 2, 3, 4, 5
 ACC_WEIGHTED_AVERAGE, ACC_BAYER_AVERAGE = 0, 1
@@ -56,10 +57,18 @@ class ssk_ecc_registration_options(C.Structure):
                 ("ecch_estimate_translation_first", C.c_int32), ("replace_planetary_disk_with_mask", C.c_int32)]
 
 
+class ssk_eccflow_options(C.Structure):
+    _fields_ = [("input_smooth_sigma", C.c_double), ("reference_smooth_sigma", C.c_double), ("update_multiplier", C.c_double),
+                ("scale_factor", C.c_double), ("noise_level", C.c_double), ("max_iterations", C.c_int32),
+                ("support_scale", C.c_int32), ("min_image_size", C.c_int32), ("max_pyramid_level", C.c_int32),
+                ("downscale_method", C.c_int32), ("reserved", C.c_int32)]
+
+
 class ssk_registration_options(C.Structure):
     _fields_ = [("motion_type", C.c_int32), ("interpolation", C.c_int32), ("border_mode", C.c_int32),
                 ("border_value", C.c_double * 4), ("ecc", ssk_ecc_registration_options),
-                ("enable_ecc_registration", C.c_int32)]
+                ("enable_ecc_registration", C.c_int32), ("enable_eccflow_registration", C.c_int32),
+                ("eccflow", ssk_eccflow_options)]
 
 
 class ssk_ecc_status(C.Structure):
@@ -167,6 +176,16 @@ _sigs = {
     "ssk_stack_registration": (C.c_void_p, [C.c_void_p]),
     "ssk_stack_stream": (C.c_void_p, [C.c_void_p]),
     "ssk_stack_stage_times": (C.c_int, [C.c_void_p, _P(C.c_float)]),
+    "ssk_eccflow_options_default": (None, [_P(ssk_eccflow_options)]),
+    "ssk_eccflow_registration_options_default": (None, [_P(ssk_eccflow_options)]),
+    "ssk_eccflow_create": (C.c_int, [_P(ssk_eccflow_options), _P(C.c_void_p)]),
+    "ssk_eccflow_destroy": (C.c_int, [C.c_void_p]),
+    "ssk_eccflow_set_reference_image": (C.c_int, [C.c_void_p, _P(ssk_mat), _P(ssk_mat)]),
+    "ssk_eccflow_compute": (C.c_int, [C.c_void_p, _P(ssk_mat), _P(ssk_mat), _P(ssk_mat), C.c_int]),
+    "ssk_eccflow_get_uv": (C.c_int, [C.c_void_p, _P(ssk_mat)]),
+    "ssk_eccflow_num_levels": (C.c_int, [C.c_void_p]),
+    "ssk_eccflow_level_size": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_int), _P(C.c_int), _P(C.c_int), _P(C.c_int)]),
+    "ssk_eccflow_get_image": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _P(ssk_mat)]),
 }
 for _name, (_res, _args) in _sigs.items():
     _f = getattr(lib, _name)

@@ -198,6 +198,8 @@ void ssk_registration_options_default(ssk_registration_options *o) {
   o->ecc.normalization_noise = 0.01; o->ecc.normalization_scale = 0;
   o->ecc.ecch_estimate_translation_first = 1; o->ecc.replace_planetary_disk_with_mask = 0;
   o->enable_ecc_registration = 0;   // reference default (c_frame_registration.h:133); callers of this path set it
+  o->enable_eccflow_registration = 0;
+  ssk_eccflow_registration_options_default(&o->eccflow);   // c_frame_registration.h:88-100
 }
 
 int ssk_transform_init(ssk_transform *t, int motion_type) { return make_transform(t, motion_type); }
