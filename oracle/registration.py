@@ -17,6 +17,7 @@ import numpy as np
 import cv2
 
 from . import ecc as _ecc
+from . import eccflow as _flow
 from . import transforms as _tf
 
 f32 = np.float32
@@ -53,6 +54,7 @@ class ImageRegistrationOptions:
     enable_feature_registration: bool = False   # reference default is True; out of scope here
     enable_ecc_registration: bool = True        # reference default is False
     enable_eccflow_registration: bool = False
+    eccflow: object = None                      # c_eccflow_registration_options (oracle.eccflow.registration_options())
 
 
 @dataclass
@@ -139,7 +141,13 @@ class FrameRegistration:
             ecc_image, ecc_mask = ref_ecc_image, ref_ecc_mask
         if o.ecc.normalization_scale > 0 and o.ecc.normalization_noise > 0:
             ecc_image = _ecc.ecc_normalize(ecc_image, ecc_mask, o.ecc.normalization_scale)
-        return e.set_reference_image(ecc_image, ecc_mask)
+        if not e.set_reference_image(ecc_image, ecc_mask):
+            return False
+        if o.enable_eccflow_registration:
+            # c_frame_registration.cc:637-660: the flow works on the full-size ECC image and mask
+            self.eccflow = _flow.EccFlow(o.eccflow if o.eccflow is not None else _flow.registration_options())
+            return self.eccflow.set_reference_image(ref_ecc_image, ref_ecc_mask)
+        return True
 
     def register_frame(self, current_image, current_mask=None):
         # c_frame_registration.cc:721-964 (dst/dstmask not requested, as in the stacking pipeline)
@@ -183,6 +191,9 @@ class FrameRegistration:
         if o.ecc.scale > 0 and o.ecc.scale != 1:
             t.scale_transfrom(1.0 / o.ecc.scale)
         self.current_remap = t.create_remap(self.reference_frame_size)
+        if o.enable_eccflow_registration:
+            # c_frame_registration.cc:900-917
+            self.current_remap = self.eccflow.compute(ecc_image, self.current_remap, ecc_mask)
         self.status.ok = True
         return True
 

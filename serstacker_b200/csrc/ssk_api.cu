@@ -4,6 +4,7 @@
 #include <memory>
 #include <new>
 #include "ssk_engine.cuh"
+#include "ssk_eccflow.cuh"
 
 using namespace ssk;
 
@@ -402,8 +403,26 @@ int ssk_reg_register_frame(ssk_reg *h, const ssk_mat *image, const ssk_mat *mask
   return SSK_OK;
 }
 
+// _current_remap after the c_eccflow stage (c_frame_registration.cc:900-917) as a dense device CV_32FC2 image
+static int reg_flow_remap(ssk_reg *h, ssk_mat *m) {
+  const int rows = h->r.ref_rows, cols = h->r.ref_cols;
+  if (int e = h->st_flowmap.ensure((size_t)rows * cols * 8)) return e;
+  if (int e = h->r.flowh->write_remap(0, h->st_flowmap.as<float2>())) return e;
+  m->data = h->st_flowmap.p; m->step = (int64_t)cols * 8; m->rows = rows; m->cols = cols; m->type = SSK_32FC2; m->mem = SSK_MEM_DEVICE;
+  return SSK_OK;
+}
+
 int ssk_reg_get_current_remap(ssk_reg *h, ssk_mat *rmap) {
   SSK_REQUIRE(h && h->r.have_current, "c_frame_registration: no registered frame");
+  if (h->r.flow_enabled()) {
+    if (int e = check_mat(rmap, "current_remap")) return e;
+    SSK_REQUIRE(rmap->type == SSK_32FC2 && rmap->rows == h->r.ref_rows && rmap->cols == h->r.ref_cols, "current_remap: rmap must be CV_32FC2 of the reference size");
+    ssk_mat m;
+    if (int e = reg_flow_remap(h, &m)) return e;
+    if (int e = from_device(m.data, (size_t)m.cols * 8, m.rows, rmap, h->r.stream)) return e;
+    SSK_CUDA(cudaStreamSynchronize(h->r.stream));
+    return SSK_OK;
+  }
   return ssk_transform_create_remap(&h->r.current, h->r.ref_rows, h->r.ref_cols, rmap);
 }
 
@@ -415,6 +434,12 @@ int ssk_reg_remap(ssk_reg *h, const ssk_mat *rmap, const ssk_mat *src, ssk_mat *
   if (interpolation < 0) interpolation = h->r.opts.interpolation;
   const double *bv = border_value;
   if (border_mode < 0) { border_mode = h->r.opts.border_mode; bv = h->r.opts.border_value; }
+  if (!rmap && h->r.flow_enabled()) {
+    ssk_mat m;
+    if (int e = reg_flow_remap(h, &m)) return e;
+    return do_remap(h->r.stream, h->staging, h->st_map, h->st_mask, h->st_out, h->st_tmp, nullptr, &m, src, dst, src_mask, dst_mask,
+                    interpolation, border_mode, bv);
+  }
   return do_remap(h->r.stream, h->staging, h->st_map, h->st_mask, h->st_out, h->st_tmp, rmap ? nullptr : &h->r.current, rmap,
                   src, dst, src_mask, dst_mask, interpolation, border_mode, bv);
 }

@@ -290,6 +290,8 @@ struct Blob {
 // ---------------------------------------------------------------------------------------------------------------------
 // EccFlow
 // ---------------------------------------------------------------------------------------------------------------------
+EccFlowHolder::~EccFlowHolder() { delete p; }
+
 int EccFlow::init(const ssk_eccflow_options &o, cudaStream_t s) {
   opts = o; stream = s; have_reference = false;
   SSK_REQUIRE(o.support_scale >= 0 && o.support_scale <= 12, "eccflow: support_scale 0..12");

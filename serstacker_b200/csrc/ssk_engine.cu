@@ -1,5 +1,6 @@
 // Engine classes: device-resident c_ecch / c_frame_registration / accumulator state and batching.
 #include "ssk_engine.cuh"
+#include "ssk_eccflow.cuh"
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -478,6 +479,11 @@ int Reg::init(const ssk_registration_options &o, cudaStream_t s, bool own) {
   ecch.check_rho = 1;
   ecch.min_rho = o.ecc.min_rho;
   ecch.final_scale = (o.ecc.scale > 0 && o.ecc.scale != 1) ? 1.0 / o.ecc.scale : 1.0;
+  if (o.enable_eccflow_registration) {   // c_frame_registration.cc:637-660
+    if (!flowh.p) flowh.p = new (std::nothrow) EccFlow();
+    SSK_REQUIRE(flowh.p, "out of memory");
+    if (int e = flowh->init(o.eccflow, s)) return e;
+  }
   return SSK_OK;
 }
 
@@ -541,6 +547,18 @@ int Reg::setup_reference(const Img &frame, const uint8_t *d_mask, int64_t mask_s
     if (int e = normalize(d_one_ptr.as<float *>(), 1, d_ecc_mask)) return e;
   }
   if (int e = ecch.set_reference(d_ecc, ecc_rows, ecc_cols, d_ecc_mask)) return e;
+  if (flow_enabled()) {
+    // c_frame_registration.cc:637-660: c_eccflow sees the full-size ECC image (create_ecc_image) and the full-size mask
+    if (int e = flow_img.ensure((size_t)frame.rows * frame.cols * 4)) return e;
+    if (int e = launch_to_gray(frame, nullptr, flow_img.as<float>(), nullptr, 1, stream)) return e;
+    const uint8_t *dm = nullptr;
+    if (d_mask) {
+      if (int e = flow_mask.ensure((size_t)frame.rows * frame.cols)) return e;
+      SSK_CUDA(cudaMemcpy2DAsync(flow_mask.p, frame.cols, d_mask, mask_step, frame.cols, frame.rows, cudaMemcpyDeviceToDevice, stream));
+      dm = flow_mask.as<uint8_t>();
+    }
+    if (int e = flowh->set_reference(flow_img.as<float>(), frame.rows, frame.cols, dm)) return e;
+  }
   have_current = false;
   return SSK_OK;
 }
@@ -567,7 +585,20 @@ int Reg::prepare(const Img &geom, const void *const *d_frame_ptrs, int batch, co
     if (int e = normalize(ecch.level0_scratch_ptrs(), batch, d_ecc_mask)) return e;
   }
   if (int e = ecch.prepare_current(ecch.level0_scratch_ptrs(), batch)) return e;
-  if (d_ecc_mask) return ecch.prepare_current_mask(d_ecc_mask);
+  if (d_ecc_mask)
+    if (int e = ecch.prepare_current_mask(d_ecc_mask)) return e;
+  if (flow_enabled()) {
+    // c_frame_registration.cc:773-785, 900-917: the full-size ECC image and mask of the current frame
+    if (int e = flowh->reserve(batch)) return e;
+    if (int e = launch_to_gray(geom, d_frame_ptrs, nullptr, flowh->level0_ptrs(), batch, stream)) return e;
+    const uint8_t *dm = nullptr;
+    if (d_mask) {
+      if (int e = flow_mask.ensure((size_t)geom.rows * geom.cols)) return e;
+      SSK_CUDA(cudaMemcpy2DAsync(flow_mask.p, geom.cols, d_mask, mask_step, geom.cols, geom.rows, cudaMemcpyDeviceToDevice, stream));
+      dm = flow_mask.as<uint8_t>();
+    }
+    if (int e = flowh->build_current(batch, dm)) return e;
+  }
   return SSK_OK;
 }
 
@@ -620,7 +651,10 @@ int Reg::normalize(float *const *d_img_ptrs, int batch, const uint8_t *d_mask) {
 
 int Reg::register_batch(int batch) {
   // c_frame_registration.cc:744: every frame restarts from the default parameters
-  return ecch.align(batch, default_transform);
+  if (int e = ecch.align(batch, default_transform)) return e;
+  // c_frame_registration.cc:900-917: _eccflow.compute(ecc_image, _current_remap, eccflow_mask) for the registered frames
+  if (flow_enabled()) return flowh->compute(batch, ecch.device_frames(), nullptr);
+  return SSK_OK;
 }
 
 }  // namespace ssk

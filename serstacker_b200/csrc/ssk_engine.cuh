@@ -141,18 +141,30 @@ class Acc {
 // ------------------------------------------------------------------------------------------------
 // c_frame_registration (ECC branch)
 // ------------------------------------------------------------------------------------------------
+class EccFlow;                         // ssk_eccflow.cuh
+struct EccFlowHolder {                 // owning pointer with the deleter out of line (EccFlow is incomplete here)
+  EccFlow *p = nullptr;
+  EccFlowHolder() = default;
+  EccFlowHolder(const EccFlowHolder &) = delete;
+  EccFlowHolder &operator=(const EccFlowHolder &) = delete;
+  ~EccFlowHolder();
+  EccFlow *operator->() const { return p; }
+};
+
 class Reg {
  public:
   ssk_registration_options opts;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   Ecch ecch;
+  EccFlowHolder flowh;                 // c_eccflow stage (enable_eccflow_registration), null when disabled
+  bool flow_enabled() const { return opts.enable_eccflow_registration != 0; }
   int ref_rows = 0, ref_cols = 0;      // _reference_frame_size
   int ecc_rows = 0, ecc_cols = 0;      // size of the ECC image (after scaleImage)
   bool have_current = false;
   ssk_transform current;               // result of the last register_frame
   ssk_transform default_transform;     // _image_transform_defaut_parameters
-  DevBuf staging, mask_tmp, out_staging;
+  DevBuf staging, mask_tmp, out_staging, flow_img, flow_mask;
   DevBuf d_one_ptr;                    // 1-entry pointer tables for the single-frame path
   DevBuf norm_buf, norm_ptrs;          // ecc_normalize: per-frame pyrDown chain + per-level pointer tables
   int norm_capacity = 0;
@@ -188,7 +200,7 @@ struct ssk_ecch {
 
 struct ssk_reg {
   ssk::Reg r;
-  ssk::DevBuf staging, st_map, st_mask, st_out, st_tmp, d_ptr;
+  ssk::DevBuf staging, st_map, st_mask, st_out, st_tmp, d_ptr, st_flowmap;
 };
 
 struct ssk_acc {

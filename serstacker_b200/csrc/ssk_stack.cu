@@ -8,6 +8,7 @@
 #include <new>
 #include <cstdlib>
 #include "ssk_engine.cuh"
+#include "ssk_eccflow.cuh"
 
 using namespace ssk;
 
@@ -274,6 +275,8 @@ int ssk_stack_create(const ssk_stack_options *opts, ssk_stack **out) {
     SSK_REQUIRE(opts->bayer_colorid >= SSK_COLORID_BAYER_RGGB && opts->bayer_colorid <= SSK_COLORID_BAYER_BGGR,
                 "ssk_stack: bayer_average needs bayer_colorid RGGB / GRBG / GBRG / BGGR");
   SSK_REQUIRE(opts->sm_uscale >= 0 && opts->sm_uscale <= 12, "sharpness_measure.uscale 0..12");
+  SSK_REQUIRE(!(opts->enable_registration && opts->registration.enable_eccflow_registration && opts->accumulation_method == SSK_STACK_BAYER_AVERAGE),
+              "ssk_stack: eccflow registration with bayer_average is not implemented");
   ssk_stack *h = new (std::nothrow) ssk_stack();
   SSK_REQUIRE(h, "out of memory");
   h->o = *opts;
@@ -334,6 +337,8 @@ int ssk_stack_set_reference(ssk_stack *h, const ssk_mat *image, const ssk_mat *m
     if (mask) { if (int e = mask_to_device(mask, image->rows, image->cols, h->reg_h.st_mask, h->stream, &d_mask, &mstep)) return e; }
     if (int e = h->reg_h.r.setup_reference(im, d_mask, mstep)) return e;
     if (int e = h->reg_h.r.ecch.reserve(h->max_batch)) return e;
+    if (h->reg_h.r.flow_enabled())
+      if (int e = h->reg_h.r.flowh->reserve(h->max_batch)) return e;
   }
   if (int e = stack_alloc_slots(h)) return e;
   if (int e = h->acc_h.a.ensure(h->rows, h->cols, bayer ? 3 : cn)) return e;
@@ -513,7 +518,12 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
   a.acc = h->acc_h.a.acc.as<float>(); a.wacc = h->acc_h.a.wacc.as<float>();
   if (getenv("SSK_NO_TMA_KERNEL")) a.tmap_frames = a.tmap_weights = nullptr;   // tuning knob: cp.async kernel pair
   if (fused_tma_applicable(a)) a.side_stream = nullptr;                        // one launch over all tiles: nothing to fork
-  if (bayer) {
+  if (h->o.enable_registration && h->reg_h.r.flow_enabled()) {
+    // per-pixel maps: _current_remap = c_eccflow's refinement of the ECC map (c_frame_registration.cc:900-917)
+    a.flow = h->reg_h.r.flowh->uv(0); a.flow_stride = (int64_t)h->rows * h->cols;
+    a.side_stream = nullptr;
+    if (int e = launch_warp_accumulate_flow(a, h->tab, s)) return e;
+  } else if (bayer) {
     // the mask of custom_remap(current_remap, frame, mask, registration_options.interpolation) gates the gather of the raw
     // samples through current_remap (c_image_stacking_pipeline.cc:1644-1651, 1730-1752)
     a.side_stream = nullptr;

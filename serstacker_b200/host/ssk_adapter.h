@@ -213,11 +213,101 @@ class c_ecch {
 };
 
 // ---------------------------------------------------------------------------------------------------------
+// c_eccflow  (core/proc/image_registration/ecc2.h:515-662): dense smooth optical flow
+// ---------------------------------------------------------------------------------------------------------
+struct c_eccflow_options {   // ecc2.h:515-527
+  double input_smooth_sigma = 0;
+  double reference_smooth_sigma = 0;
+  double update_multiplier = 1.5;
+  double scale_factor = 0.5;
+  double noise_level = -1;
+  int max_iterations = 1;
+  int support_scale = 5;
+  int min_image_size = 4;
+  int max_pyramid_level = -1;
+  int downscale = SSK_ECCFLOW_DOWNSCALE_RECURSIVE_RESIZE;
+};
+
+class c_eccflow {
+ public:
+  c_eccflow() = default;
+  ~c_eccflow() { if (h_) ssk_eccflow_destroy(h_); }
+  c_eccflow(const c_eccflow &) = delete;
+  c_eccflow &operator=(const c_eccflow &) = delete;
+  c_eccflow_options &options() { return opts_; }
+  const c_eccflow_options &options() const { return opts_; }
+  void set_options(const c_eccflow_options &o) { opts_ = o; }
+  void set_support_scale(int v) { opts_.support_scale = v; }
+  int support_scale() const { return opts_.support_scale; }
+  void set_max_iterations(int v) { opts_.max_iterations = v; }
+  int max_iterations() const { return opts_.max_iterations; }
+  void set_update_multiplier(double v) { opts_.update_multiplier = v; }
+  double update_multiplier() const { return opts_.update_multiplier; }
+  void set_input_smooth_sigma(double v) { opts_.input_smooth_sigma = v; }
+  void set_reference_smooth_sigma(double v) { opts_.reference_smooth_sigma = v; }
+  void set_downscale_method(int v) { opts_.downscale = v; }
+  int downscale_method() const { return opts_.downscale; }
+  void set_scale_factor(double v) { opts_.scale_factor = v; }
+  double scale_factor() const { return opts_.scale_factor; }
+  void set_min_image_size(int v) { opts_.min_image_size = v; }
+  int min_image_size() const { return opts_.min_image_size; }
+  void set_max_pyramid_level(int v) { opts_.max_pyramid_level = v; }
+  int max_pyramid_level() const { return opts_.max_pyramid_level; }
+  void set_noise_level(double v) { opts_.noise_level = v; }
+  double noise_level() const { return opts_.noise_level; }
+  void copy_parameters(const c_eccflow &rhs) { opts_ = rhs.opts_; }
+
+  // the options are latched here, as the reference builds its pyramid here (ecc2.cc:2494-2672)
+  bool set_reference_image(const image_t &reference_image, const image_t &reference_mask = image_t()) {
+    if (h_) { ssk_eccflow_destroy(h_); h_ = nullptr; }
+    ssk_eccflow_options o;
+    ssk_eccflow_options_default(&o);
+    o.input_smooth_sigma = opts_.input_smooth_sigma; o.reference_smooth_sigma = opts_.reference_smooth_sigma;
+    o.update_multiplier = opts_.update_multiplier; o.scale_factor = opts_.scale_factor; o.noise_level = opts_.noise_level;
+    o.max_iterations = opts_.max_iterations; o.support_scale = opts_.support_scale; o.min_image_size = opts_.min_image_size;
+    o.max_pyramid_level = opts_.max_pyramid_level; o.downscale_method = opts_.downscale;
+    if (ssk_eccflow_create(&o, &h_) != SSK_OK) return false;
+    ssk_mat im = detail::view(reference_image);
+    detail::Opt<image_t> mk(reference_mask);
+    rows_ = im.rows; cols_ = im.cols;
+    return ssk_eccflow_set_reference_image(h_, &im, mk.get()) == SSK_OK;
+  }
+  // compute(input_image, rmap, input_mask): an empty rmap starts from a zero flow (ecc2.cc:2783-2786)
+  bool compute(const image_t &input_image, image_t &rmap, const image_t &input_mask = image_t()) {
+    if (!h_) return false;
+    const int have = rmap.empty() ? 0 : 1;
+    if (!have) create_like(rmap, rows_, cols_, SSK_32FC2);
+    ssk_mat im = detail::view(input_image), rm = detail::view(rmap);
+    detail::Opt<image_t> mk(input_mask);
+    return ssk_eccflow_compute(h_, &im, mk.get(), &rm, have) == SSK_OK;
+  }
+  // the reference tells this overload from the one above by the map's type (cv::Mat2f &); with one image type the input mask
+  // is spelled out here (an empty image = cv::noArray())
+  bool compute(const image_t &input_image, const image_t &reference_image, image_t &rmap, const image_t &input_mask,
+               const image_t &reference_mask = image_t()) {
+    return set_reference_image(reference_image, reference_mask) && compute(input_image, rmap, input_mask);
+  }
+  bool current_uv(image_t &uv) const {
+    if (!h_) return false;
+    create_like(uv, rows_, cols_, SSK_32FC2);
+    ssk_mat v = detail::view(uv);
+    return ssk_eccflow_get_uv(h_, &v) == SSK_OK;
+  }
+  int num_levels() const { return h_ ? ssk_eccflow_num_levels(h_) : 0; }
+
+ private:
+  ssk_eccflow *h_ = nullptr;
+  c_eccflow_options opts_;
+  int rows_ = 0, cols_ = 0;
+};
+
+// ---------------------------------------------------------------------------------------------------------
 // c_frame_registration, ECC branch  (core/proc/image_registration/c_frame_registration.h:210-354)
 // ---------------------------------------------------------------------------------------------------------
 // c_ecc_registration_options / c_image_registration_options (c_frame_registration.h:47-64, 119-136): the reference's field
-// names and defaults, so that option plumbing written against the reference compiles unchanged.  The sparse-feature and
-// eccflow stages are not part of this library: setup_reference_frame() fails when they are the only stage enabled.
+// names and defaults, so that option plumbing written against the reference compiles unchanged.  The sparse-feature stage is
+// not part of this library, and the eccflow stage runs after the ECC stage only: setup_reference_frame() fails when
+// enable_ecc_registration is off.
 struct c_ecc_registration_options {
   double scale = 0.5;
   double eps = 0.2;
@@ -236,6 +326,20 @@ struct c_ecc_registration_options {
   bool replace_planetary_disk_with_mask = false;
 };
 
+// c_eccflow_registration_options (c_frame_registration.h:88-100)
+struct c_eccflow_registration_options {
+  double update_multiplier = 1.5;
+  double input_smooth_sigma = 0;
+  double reference_smooth_sigma = 0;
+  double noise_level = -1;
+  double scale_factor = 0.75;
+  int max_iterations = 3;
+  int support_scale = 4;
+  int min_image_size = -1;
+  int max_pyramid_level = -1;
+  int downscale_method = SSK_ECCFLOW_DOWNSCALE_RECURSIVE_RESIZE;
+};
+
 struct c_image_registration_options {
   int motion_type = SSK_MOTION_AFFINE;
   int ecc_registration_channel = 0;          // color_channel_gray
@@ -247,6 +351,7 @@ struct c_image_registration_options {
   bool enable_eccflow_registration = false;
   bool accumulate_and_compensate_turbulent_flow = false;
   c_ecc_registration_options ecc;
+  c_eccflow_registration_options eccflow;
 };
 
 inline ssk_registration_options to_ssk_options(const c_image_registration_options &o) {
@@ -263,6 +368,13 @@ inline ssk_registration_options to_ssk_options(const c_image_registration_option
   r.ecc.normalization_scale = o.ecc.normalization_scale;
   r.ecc.ecch_estimate_translation_first = o.ecc.ecch_estimate_translation_first ? 1 : 0;
   r.ecc.replace_planetary_disk_with_mask = o.ecc.replace_planetary_disk_with_mask ? 1 : 0;
+  // c_frame_registration.cc:637-660
+  r.enable_eccflow_registration = o.enable_eccflow_registration ? 1 : 0;
+  r.eccflow.update_multiplier = o.eccflow.update_multiplier; r.eccflow.input_smooth_sigma = o.eccflow.input_smooth_sigma;
+  r.eccflow.reference_smooth_sigma = o.eccflow.reference_smooth_sigma; r.eccflow.noise_level = o.eccflow.noise_level;
+  r.eccflow.scale_factor = o.eccflow.scale_factor; r.eccflow.max_iterations = o.eccflow.max_iterations;
+  r.eccflow.support_scale = o.eccflow.support_scale; r.eccflow.min_image_size = o.eccflow.min_image_size;
+  r.eccflow.max_pyramid_level = o.eccflow.max_pyramid_level; r.eccflow.downscale_method = o.eccflow.downscale_method;
   return r;
 }
 

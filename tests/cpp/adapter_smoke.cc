@@ -45,6 +45,14 @@ int main(int argc, char **argv) {
     ssk::c_image_registration_options io;
     const ssk_registration_options so = ssk::to_ssk_options(io);
     if (so.motion_type != SSK_MOTION_AFFINE || so.ecc.ecc_method != SSK_ECC_LM || so.ecc.scale != 0.5 || so.enable_ecc_registration) return 3;
+    // c_eccflow_registration_options (c_frame_registration.h:88-100) and c_eccflow_options (ecc2.h:515-527)
+    if (so.enable_eccflow_registration || so.eccflow.scale_factor != 0.75 || so.eccflow.max_iterations != 3 || so.eccflow.support_scale != 4 ||
+        so.eccflow.min_image_size != -1 || so.eccflow.update_multiplier != 1.5) return 3;
+    ssk_eccflow_options fo;
+    ssk_eccflow_options_default(&fo);
+    ssk::c_eccflow_options fa;
+    if (fo.scale_factor != fa.scale_factor || fo.support_scale != fa.support_scale || fo.max_iterations != fa.max_iterations ||
+        fo.min_image_size != fa.min_image_size || fo.noise_level != fa.noise_level) return 3;
     ssk::c_frame_registration feature_only(io);            // feature registration is the default stage: not in this library
     ssk::Mat dummy(8, 8, SSK_32FC1);
     if (feature_only.setup_reference_frame(dummy)) return 3;
@@ -140,6 +148,38 @@ int main(int argc, char **argv) {
     for (int x = 12; x < W - 12; ++x) perr = std::fmax(perr, std::fabs(stacked.ptr<float>(y)[x] - ref.ptr<float>(y)[x]));
   std::printf("adapter_smoke: c_image_stacking_pipeline::run stacked %d frames, max |stack - scene| = %.4g (master sharpened)\n", pipe.accumulated_frames(), perr);
   if (perr > 0.05) return 13;
+  // c_eccflow: the flow between the reference and a shifted copy is the shift (the disk's textured interior)
+  {
+    ssk::c_eccflow flow;
+    flow.set_support_scale(3);
+    flow.set_max_iterations(3);
+    flow.set_scale_factor(0.75);
+    render(frame, W, H, 1.25f, -0.75f);
+    ssk::Mat fmap, uv;
+    if (!flow.compute(frame, ref, fmap, ssk::Mat()) || fmap.type != SSK_32FC2 || fmap.rows != H || !flow.current_uv(uv) || flow.num_levels() < 3) {
+      std::fprintf(stderr, "c_eccflow: %s\n", ssk_last_error());
+      return 15;
+    }
+    const float *c = uv.ptr<float>(H / 2) + 2 * (W / 2);
+    std::printf("adapter_smoke: c_eccflow flow at the centre (%.3f, %.3f), true shift (1.25, -0.75), %d levels\n", c[0], c[1], flow.num_levels());
+    if (std::fabs(c[0] - 1.25f) > 0.25 || std::fabs(c[1] + 0.75f) > 0.25) return 15;
+    // and as the second stage of c_frame_registration
+    ssk::c_image_registration_options fo;
+    fo.motion_type = SSK_MOTION_TRANSLATION; fo.enable_feature_registration = false; fo.enable_ecc_registration = true;
+    fo.enable_eccflow_registration = true;
+    fo.ecc.ecc_method = SSK_ECC_INVERSE_COMPOSITIONAL_LM; fo.ecc.ecch_max_level = -1;
+    ssk::c_frame_registration freg(fo);
+    ssk::Mat fw, fm, cr;
+    if (!freg.setup_reference_frame(ref) || !freg.register_frame(frame, ssk::Mat(), &fw, &fm) || !freg.current_remap(cr, W, H)) {
+      std::fprintf(stderr, "c_frame_registration + eccflow: %s\n", ssk_last_error());
+      return 15;
+    }
+    double ferr = 0;
+    for (int y = 24; y < H - 24; ++y)
+      for (int x = 24; x < W - 24; ++x) ferr = std::fmax(ferr, std::fabs(fw.ptr<float>(y)[x] - ref.ptr<float>(y)[x]));
+    std::printf("adapter_smoke: register_frame with eccflow: max |warped - reference| = %.4g\n", ferr);
+    if (ferr > 0.05) return 15;
+  }
   // input side
   ssk::Mat hmask(H, W, SSK_8UC1), lin, raw(H, W, SSK_16UC1), planes;
   std::memset(hmask.buf.data(), 255, hmask.buf.size());

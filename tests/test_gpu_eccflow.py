@@ -195,3 +195,95 @@ def test_eccflow_rejects_bad_arguments(gpu):
     with pytest.raises(api.SskError):
         g._shape = (64, 96)
         g.compute(cur, ident)                                        # ecc2.cc:2678: reference first
+
+
+# ---------------------------------------------------------------------------------------------------------
+# c_frame_registration with enable_eccflow_registration, and the stacking loop over per-pixel maps
+# ---------------------------------------------------------------------------------------------------------
+def _turbulent_sequence(w, h, n, seed, amp=30.0, smooth=18.0):
+    """Planet frames (jittered, defocused) with a smooth per-frame turbulence warp on top."""
+    from serstacker_b200 import synth
+    frames, _, _ = synth.make_planet_sequence(w, h, n, seed=seed, radius=min(w, h) * 0.37, sigma_t=3.0, sigma_rot_deg=0.1,
+                                              sigma_scale=0.001, blur_range=(0.8, 1.6), dtype="f32")
+    rng = np.random.default_rng(seed + 100)
+    yy, xx = np.mgrid[0:h, 0:w].astype(f32)
+    out = [frames[0]]
+    for f in frames[1:]:
+        du = cv2.GaussianBlur(rng.standard_normal((h, w)).astype(f32), (0, 0), smooth) * amp
+        dv = cv2.GaussianBlur(rng.standard_normal((h, w)).astype(f32), (0, 0), smooth) * amp
+        out.append(cv2.remap(f, xx + du, yy + dv, cv2.INTER_CUBIC, borderMode=cv2.BORDER_REFLECT101))
+    return out
+
+
+def _flow_registration_options(motion, method, interpolation):
+    from oracle import registration as oreg
+    o = oreg.ImageRegistrationOptions(motion_type=motion, interpolation=interpolation)
+    o.ecc.ecc_method = method
+    o.ecc.ecch_max_level = -1
+    o.enable_eccflow_registration = True
+    o.eccflow = oef.registration_options()
+    return o
+
+
+@pytest.mark.parametrize("motion", [0, 3])
+def test_register_frame_with_eccflow_matches_oracle(gpu, motion):
+    """c_frame_registration.cc:900-917: _current_remap = eccflow.compute(ecc_image, create_remap(transform), ecc_mask)."""
+    from serstacker_b200 import api
+    from oracle import registration as oreg
+    frames = _turbulent_sequence(480, 270, 3, seed=21)
+    oo = _flow_registration_options(motion, 3, cv2.INTER_LINEAR)
+    ro = oreg.FrameRegistration(oo)
+    ro.setup_reference_frame(frames[0])
+    rg = api.c_frame_registration(api.registration_options(motion_type=motion, interpolation=1, enable_eccflow_registration=1,
+                                                          ecc=dict(ecc_method=3, ecch_max_level=-1)))
+    rg.setup_reference_frame(frames[0])
+    rng = np.random.default_rng(5)
+    for f in frames[1:]:
+        assert ro.register_frame(f) and rg.register_frame(f)
+        want, got = ro.current_remap, rg.current_remap()
+        wimg, wmask = ro.remap(f, None)
+        f2 = (f * (1 + rng.standard_normal(f.shape).astype(f32) * f32(1e-7))).astype(f32)
+        assert ro.register_frame(f2)
+        env = np.abs(ro.current_remap - want).max(axis=-1)
+        d = np.abs(got - want).max(axis=-1)
+        print("  register_frame + eccflow (motion %d): max |d map| = %.3g px, 99.9%% = %.3g, mean = %.3g  (oracle one-ulp envelope: max %.3g, 99.9%% %.3g, mean %.3g)"
+              % (motion, d.max(), np.quantile(d, .999), d.mean(), env.max(), np.quantile(env, .999), env.mean()))
+        assert np.quantile(d, .999) <= max(1e-3, 3 * np.quantile(env, .999))
+        assert d.max() <= max(2e-3, 4 * env.max())
+        # remap() through the refined map = the oracle's base_remap through its map (image where both masks agree)
+        gimg, gmask = rg.remap(f)
+        both = (wmask > 0) & (gmask > 0)
+        assert (wmask != gmask).mean() < 1e-3
+        gy_, gx_ = np.gradient(f)
+        # cv::remap quantises the map to 1/32 px: a map difference can move a sample by one quantisation step
+        assert np.abs(gimg - wimg)[both].max() <= (2 * d.max() + 1.0 / 32) * max(np.abs(gx_).max(), np.abs(gy_).max()) + 1e-5
+        assert np.abs(gimg - wimg)[both].mean() <= 1e-4
+
+
+@pytest.mark.parametrize("acc,interp", [(0, cv2.INTER_LINEAR), (1, cv2.INTER_CUBIC)])
+def test_stack_with_eccflow_matches_oracle(gpu, acc, interp):
+    """The per-frame loop with per-pixel maps (k_fused_flow): ECC -> eccflow -> warp through the flow map -> (weighted) average."""
+    from serstacker_b200 import api
+    from oracle import pipeline as opl
+    frames = _turbulent_sequence(480, 270, 6, seed=31)
+    so = opl.StackingOptions(accumulation_method=opl.ACC_WEIGHTED_AVERAGE if acc else opl.ACC_AVERAGE)
+    so.registration = _flow_registration_options(3, 3, interp)
+    avg_o, mask_o, _, _ = opl.run_stacking(frames, so)
+    ro = api.registration_options(motion_type=3, interpolation=interp, enable_eccflow_registration=1, ecc=dict(ecc_method=3, ecch_max_level=-1))
+    p = api.c_image_stacking_pipeline(api.stack_options(registration=ro, accumulation_method=acc, max_batch=4))
+    p.set_reference(frames[0])
+    res = p.add_frames(frames)
+    avg_g, mask_g = p.compute()
+    assert p.accumulated_frames() == len(frames)
+    m = (mask_o > 0) & (mask_g > 0)
+    rel = float(np.sqrt(((avg_g[m] - avg_o[m]) ** 2).sum()) / np.sqrt((avg_o[m] ** 2).sum()))
+    print("  stack with eccflow (acc %d, interp %d): rel-L2 = %.3g, mask mismatch %.3g" % (acc, interp, rel, (mask_o != mask_g).mean()))
+    assert rel <= 1e-4
+    assert (mask_o != mask_g).mean() < 1e-3
+    # and the flow did its job: the stack is sharper than the one registered without it
+    so2 = opl.StackingOptions(accumulation_method=so.accumulation_method)
+    so2.registration = _flow_registration_options(3, 3, interp)
+    so2.registration.enable_eccflow_registration = False
+    avg_n, _, _, _ = opl.run_stacking(frames, so2)
+    lap = lambda im: float(np.abs(cv2.Laplacian(im, cv2.CV_32F))[40:-40, 40:-40].mean())
+    assert lap(avg_g) > lap(avg_n)
