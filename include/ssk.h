@@ -252,6 +252,37 @@ SSK_API int ssk_reg_remap(ssk_reg *h, const ssk_mat *rmap, const ssk_mat *src, s
                           const double border_value[4]);
 
 /* ---------------------------------------------------------------------------------------------
+ * c_image_stacking_pipeline::upscale_image / upscale_remap / upscale_optflow (c_image_stacking_pipeline.cc:1869-2002):
+ * option = SSK_UPSCALE_* (x2.0 = cv::pyrUp, x1.5 = cv::resize INTER_LINEAR, x3.0 = cv::resize INTER_LINEAR_EXACT).
+ * ------------------------------------------------------------------------------------------- */
+SSK_API int ssk_upscale_size(int option, int cols, int rows, int *ucols, int *urows);
+/* src / dst CV_32F (1-4 channels), srcmask / dstmask CV_8UC1 (result compared >= 255 as the reference does); either pair may be NULL. */
+SSK_API int ssk_upscale_image(int option, const ssk_mat *src, const ssk_mat *srcmask, ssk_mat *dst, ssk_mat *dstmask);
+SSK_API int ssk_upscale_remap(int option, const ssk_mat *srcmap, ssk_mat *dstmap);      /* CV_32FC2 */
+SSK_API int ssk_upscale_optflow(int option, const ssk_mat *srcmap, ssk_mat *dstmap);    /* CV_32FC2, values scaled by the factor */
+
+/* ---------------------------------------------------------------------------------------------
+ * c_canvas_average (core/average/c_frame_accumulation.h:65-137, c_frame_accumulation.cc:264-445): weighted average on a
+ * canvas larger than the frames; used by c_canvas_average_pipeline.  Frames are CV_32F (1-4 channels).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ssk_canvas ssk_canvas;
+/* interpolation = c_canvas_average::options::interpolation (cv::InterpolationFlags, default INTER_LINEAR). */
+SSK_API int ssk_canvas_create(int interpolation, ssk_canvas **out);
+SSK_API int ssk_canvas_destroy(ssk_canvas *h);
+SSK_API int ssk_canvas_set_canvas_size(ssk_canvas *h, int cols, int rows);   /* setCanvasSize(): clears */
+/* add(current_image, current_weights_or_mask, rmap, new_canvas_bbox): weights NULL / CV_8UC1 mask / CV_32FC1 weights of the image
+ * size; rmap NULL or CV_32FC2 of the box size; bbox = {x, y, width, height} or NULL.  The first frame is centred on a new canvas
+ * of max(setCanvasSize, 3/2 frame size). */
+SSK_API int ssk_canvas_add(ssk_canvas *h, const ssk_mat *image, const ssk_mat *weights_or_mask, const ssk_mat *rmap, const int bbox[4]);
+/* compute(avg, mask, dscale, ddepth = CV_32F, rbbox): the box (NULL: whole canvas) clipped to the canvas; avg / mask must have
+ * that size (ssk_canvas_size gives the canvas size). */
+SSK_API int ssk_canvas_compute(ssk_canvas *h, ssk_mat *avg, ssk_mat *mask, double dscale, const int rbbox[4]);
+SSK_API int ssk_canvas_clear(ssk_canvas *h);
+SSK_API int ssk_canvas_accumulated_frames(const ssk_canvas *h);
+SSK_API int ssk_canvas_size(const ssk_canvas *h, int *cols, int *rows, int *channels);   /* accumulator_size() */
+SSK_API int ssk_canvas_last_bbox(const ssk_canvas *h, int bbox[4]);                       /* last_bbox() */
+
+/* ---------------------------------------------------------------------------------------------
  * c_eccflow (ecc2.h:548-662, ecc2.cc:2220-2865): dense smooth optical flow on a coarse-to-fine pyramid.
  * ------------------------------------------------------------------------------------------- */
 typedef struct ssk_eccflow ssk_eccflow;
@@ -414,6 +445,9 @@ SSK_API int ssk_jdr_derotate_and_add(ssk_acc *acc, const ssk_mat *frame, const s
  * ssk_local_variance_map / ssk_reg_register_frame / ssk_reg_remap / ssk_acc_add frame by frame.
  * ------------------------------------------------------------------------------------------- */
 enum { SSK_STACK_AVERAGE = 0, SSK_STACK_WEIGHTED_AVERAGE = 1, SSK_STACK_BAYER_AVERAGE = 2 };
+/* frame_upscale_option / frame_upscale_stage, c_image_stacking_pipeline.h:33-49 (same values). */
+enum { SSK_UPSCALE_NONE = 0, SSK_UPSCALE_PYRUP = 1, SSK_UPSCALE_X15 = 2, SSK_UPSCALE_X30 = 3 };
+enum { SSK_UPSCALE_AFTER_ALIGN = 1, SSK_UPSCALE_BEFORE_ALIGN = 2 };
 typedef struct ssk_stack_options {
   ssk_registration_options registration;
   int32_t accumulation_method;
@@ -423,6 +457,11 @@ typedef struct ssk_stack_options {
   int32_t max_batch;                         /* frames in flight per call (device scratch is sized for it) */
   int32_t generating_master_frame;           /* the master-frame pass (create_reference_frame): frames are remapped with
                                                 ECC_BORDER_REFLECT101 instead of registration.border_mode (c_image_stacking_pipeline.cc:1644-1651) */
+  int32_t upscale_option;                    /* c_frame_upscale_options::upscale_option (SSK_UPSCALE_*), c_image_stacking_pipeline.h:57-86 */
+  int32_t upscale_stage;                     /* SSK_UPSCALE_AFTER_ALIGN: the registration map is up-scaled and the frames are stacked at
+                                                the up-scaled size (c_image_stacking_pipeline.cc:1633-1660; never during the master-frame
+                                                pass, :2093-2101).  SSK_UPSCALE_BEFORE_ALIGN is not fused: up-scale the frames with
+                                                ssk_upscale_image before the call, as INTEGRATION.md shows */
 } ssk_stack_options;
 
 typedef struct ssk_stack ssk_stack;

@@ -36,6 +36,9 @@ class StackingOptions:
     sm_kradius: int = 1
     sm_uscale: int = 0
     enable_registration: bool = True
+    # c_frame_upscale_options (c_image_stacking_pipeline.h:33-86); only frame_upscale_after_align is restated
+    upscale_option: int = 0      # 0 none, 1 x2.0 (pyrUp), 2 x1.5, 3 x3.0
+    generating_master_frame: bool = False
 
 
 def to_float_frame(raw, bpp):
@@ -43,6 +46,57 @@ def to_float_frame(raw, bpp):
     if raw.dtype == np.float32:
         return raw
     return (raw.astype(np.float64) * (1.0 / (1 << bpp))).astype(f32)
+
+
+UPSCALE_NONE, UPSCALE_PYRUP, UPSCALE_X15, UPSCALE_X30 = 0, 1, 2, 3
+
+
+def _resize_no_ipp(src, dsize, interpolation):
+    """cv::resize as a distribution build of OpenCV computes it (the reference links the system library, CMakeLists.txt:47-59):
+    the IPP code path of the cv2 wheel uses another arithmetic for INTER_LINEAR."""
+    was = cv2.ipp.useIPP()
+    cv2.ipp.setUseIPP(False)
+    try:
+        return cv2.resize(src, dsize, interpolation=interpolation)
+    finally:
+        cv2.ipp.setUseIPP(was)
+
+
+def upscale_remap(option, srcmap):
+    """c_image_stacking_pipeline::upscale_remap (c_image_stacking_pipeline.cc:1869-1905)."""
+    h, w = srcmap.shape[:2]
+    if option == UPSCALE_X15:
+        return _resize_no_ipp(srcmap, (w * 3 // 2, h * 3 // 2), cv2.INTER_LINEAR)
+    if option == UPSCALE_PYRUP:
+        return cv2.pyrUp(srcmap)
+    if option == UPSCALE_X30:
+        return _resize_no_ipp(srcmap, (w * 3, h * 3), cv2.INTER_LINEAR_EXACT)
+    return srcmap.copy()
+
+
+def upscale_optflow(option, srcmap):
+    """c_image_stacking_pipeline::upscale_optflow (c_image_stacking_pipeline.cc:1907-1946)."""
+    f = {UPSCALE_X15: 1.5, UPSCALE_PYRUP: 2.0, UPSCALE_X30: 3.0}.get(option)
+    dst = upscale_remap(option, srcmap)
+    return dst if f is None else cv2.multiply(dst, f)
+
+
+def upscale_image(option, src, srcmask=None):
+    """c_image_stacking_pipeline::upscale_image (c_image_stacking_pipeline.cc:1949-2000) -> (dst, dstmask)."""
+    if option == UPSCALE_NONE:
+        return (None if src is None else src.copy()), (None if srcmask is None else srcmask.copy())
+    def up(img):
+        h, w = img.shape[:2]
+        if option == UPSCALE_X15:
+            return _resize_no_ipp(img, (w * 3 // 2, h * 3 // 2), cv2.INTER_LINEAR)
+        if option == UPSCALE_PYRUP:
+            return cv2.pyrUp(img)
+        return _resize_no_ipp(img, (w * 3, h * 3), cv2.INTER_LINEAR_EXACT)
+    dst = None if src is None else up(src)
+    dmask = None
+    if srcmask is not None:
+        dmask = cv2.compare(up(srcmask), 255, cv2.CMP_GE)
+    return dst, dmask
 
 
 def weights_required(o: StackingOptions):
@@ -61,6 +115,8 @@ def process_frame(reg: FrameRegistration, acc, o: StackingOptions, frame, mask=N
         if not reg.register_frame(frame, mask):
             return False            # c_image_stacking_pipeline.cc:1578-1581: frame dropped
         rmap = reg.current_remap
+        if o.upscale_option != UPSCALE_NONE and not o.generating_master_frame:
+            rmap = upscale_remap(o.upscale_option, rmap)      # c_image_stacking_pipeline.cc:1633-1642
         frame, mask = reg.custom_remap(rmap, frame, mask, ro.interpolation, ro.border_mode, ro.border_value)
         if weights is not None:
             weights, _ = reg.custom_remap(rmap, weights, None, ro.interpolation, cv2.BORDER_CONSTANT, None,

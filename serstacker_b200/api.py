@@ -151,6 +151,90 @@ def registration_options(**kw):
     return o
 
 
+def _upscaled_shape(option, shape):
+    uc, ur = C.c_int(), C.c_int()
+    check(capi.lib.ssk_upscale_size(option, shape[1], shape[0], C.byref(uc), C.byref(ur)))
+    return (ur.value, uc.value) + tuple(shape[2:])
+
+
+def upscale_image(option, src, srcmask=None):
+    """c_image_stacking_pipeline::upscale_image (c_image_stacking_pipeline.cc:1949-2000) -> (dst, dstmask)."""
+    dst = None if src is None else np.empty(_upscaled_shape(option, src.shape), dtype=f32)
+    dmask = None if srcmask is None else np.empty(_upscaled_shape(option, srcmask.shape), dtype=np.uint8)
+    check(capi.lib.ssk_upscale_image(option, ref(mat(None if src is None else np.ascontiguousarray(src))), ref(mat(srcmask)), ref(mat(dst)), ref(mat(dmask))))
+    return dst, dmask
+
+
+def upscale_remap(option, srcmap):
+    """c_image_stacking_pipeline::upscale_remap (c_image_stacking_pipeline.cc:1869-1905)."""
+    dst = np.empty(_upscaled_shape(option, srcmap.shape), dtype=f32)
+    check(capi.lib.ssk_upscale_remap(option, ref(mat(np.ascontiguousarray(srcmap))), ref(mat(dst))))
+    return dst
+
+
+def upscale_optflow(option, srcmap):
+    """c_image_stacking_pipeline::upscale_optflow (c_image_stacking_pipeline.cc:1907-1946)."""
+    dst = np.empty(_upscaled_shape(option, srcmap.shape), dtype=f32)
+    check(capi.lib.ssk_upscale_optflow(option, ref(mat(np.ascontiguousarray(srcmap))), ref(mat(dst))))
+    return dst
+
+
+class c_canvas_average:
+    """c_canvas_average (core/average/c_frame_accumulation.h:65-137)."""
+
+    def __init__(self, interpolation=capi.INTER_LINEAR, canvas_size=None):
+        self._h = C.c_void_p()
+        check(capi.lib.ssk_canvas_create(interpolation, C.byref(self._h)))
+        if canvas_size is not None:
+            self.setCanvasSize(canvas_size)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and capi is not None:
+            capi.lib.ssk_canvas_destroy(self._h)
+            self._h = None
+
+    def setCanvasSize(self, size):
+        check(capi.lib.ssk_canvas_set_canvas_size(self._h, int(size[0]), int(size[1])))
+
+    def add(self, current_image, current_weights_or_mask=None, rmap=None, new_canvas_bbox=None):
+        bb = None if new_canvas_bbox is None else (C.c_int * 4)(*[int(v) for v in new_canvas_bbox])
+        rc = capi.lib.ssk_canvas_add(self._h, ref(mat(np.ascontiguousarray(current_image))), ref(mat(current_weights_or_mask)),
+                                     ref(mat(rmap)), bb)
+        if rc == capi.SSK_ERR_INVALID and "ROI is empty" in capi.last_error():
+            return False                    # c_frame_accumulation.cc:378-381
+        check(rc)
+        return True
+
+    def accumulator_size(self):
+        v = [C.c_int() for _ in range(3)]
+        check(capi.lib.ssk_canvas_size(self._h, *[C.byref(x) for x in v]))
+        return v[0].value, v[1].value, v[2].value
+
+    def last_bbox(self):
+        bb = (C.c_int * 4)()
+        check(capi.lib.ssk_canvas_last_bbox(self._h, bb))
+        return tuple(bb)
+
+    def accumulated_frames(self):
+        return capi.lib.ssk_canvas_accumulated_frames(self._h)
+
+    def compute(self, dscale=1.0, rbbox=None):
+        w, h, cn = self.accumulator_size()
+        if rbbox is not None and rbbox[2] > 0 and rbbox[3] > 0:
+            x0, y0 = max(rbbox[0], 0), max(rbbox[1], 0)
+            x1, y1 = min(rbbox[0] + rbbox[2], w), min(rbbox[1] + rbbox[3], h)
+            w, h = x1 - x0, y1 - y0
+        avg = np.empty((h, w) if cn == 1 else (h, w, cn), dtype=f32)
+        mask = np.empty((h, w), dtype=np.uint8)
+        bb = None if rbbox is None else (C.c_int * 4)(*[int(v) for v in rbbox])
+        ma, mm = mat(avg), mat(mask)
+        check(capi.lib.ssk_canvas_compute(self._h, C.byref(ma), C.byref(mm), float(dscale), bb))
+        return avg, mask
+
+    def clear(self):
+        check(capi.lib.ssk_canvas_clear(self._h))
+
+
 def eccflow_options(registration_defaults=False, **kw):
     """c_eccflow_options (ecc2.h:515-527) or, with registration_defaults, the values c_frame_registration hands to c_eccflow
     (c_eccflow_registration_options, c_frame_registration.h:88-100)."""
@@ -586,7 +670,13 @@ class c_image_stacking_pipeline:
         mm = mask if (mask is None or isinstance(mask, ssk_mat)) else mat(np.ascontiguousarray(mask))
         check(capi.lib.ssk_stack_set_reference(self._h, C.byref(m), ref(mm), bpp))
         bayer = self.options.accumulation_method == capi.STACK_BAYER_AVERAGE
-        self._shape = (m.rows, m.cols, 3 if bayer else (m.type >> 3) + 1)   # c_bayer_average computes a BGR image
+        rows, cols = m.rows, m.cols
+        o = self.options
+        if o.upscale_option and o.enable_registration and not o.generating_master_frame:   # frame_upscale_after_align
+            uc, ur = C.c_int(), C.c_int()
+            check(capi.lib.ssk_upscale_size(o.upscale_option, cols, rows, C.byref(uc), C.byref(ur)))
+            rows, cols = ur.value, uc.value
+        self._shape = (rows, cols, 3 if bayer else (m.type >> 3) + 1)   # c_bayer_average computes a BGR image
         self._bpp = bpp
 
     def _mats(self, frames):

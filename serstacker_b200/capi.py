@@ -29,6 +29,8 @@ INTER_NEAREST, INTER_LINEAR, INTER_CUBIC, INTER_AREA = 0, 1, 2, 3
 BORDER_CONSTANT, BORDER_REPLICATE, BORDER_REFLECT, BORDER_WRAP, BORDER_REFLECT101, BORDER_TRANSPARENT = 0, 1, 2, 3, 4, 5
 ACC_WEIGHTED_AVERAGE, ACC_BAYER_AVERAGE = 0, 1
 STACK_AVERAGE, STACK_WEIGHTED_AVERAGE, STACK_BAYER_AVERAGE = 0, 1, 2
+UPSCALE_NONE, UPSCALE_PYRUP, UPSCALE_X15, UPSCALE_X30 = 0, 1, 2, 3
+UPSCALE_AFTER_ALIGN, UPSCALE_BEFORE_ALIGN = 1, 2
 COLORID_MONO = 0
 COLORID_BAYER_RGGB, COLORID_BAYER_GRBG, COLORID_BAYER_GBRG, COLORID_BAYER_BGGR = 8, 9, 10, 11
 
@@ -87,7 +89,7 @@ class ssk_stack_options(C.Structure):
     _fields_ = [("registration", ssk_registration_options), ("accumulation_method", C.c_int32),
                 ("sm_dscale", C.c_int32), ("sm_kradius", C.c_int32), ("sm_uscale", C.c_int32),
                 ("enable_registration", C.c_int32), ("bayer_colorid", C.c_int32), ("max_batch", C.c_int32),
-                ("generating_master_frame", C.c_int32)]
+                ("generating_master_frame", C.c_int32), ("upscale_option", C.c_int32), ("upscale_stage", C.c_int32)]
 
 
 _P = C.POINTER
@@ -176,6 +178,19 @@ _sigs = {
     "ssk_stack_registration": (C.c_void_p, [C.c_void_p]),
     "ssk_stack_stream": (C.c_void_p, [C.c_void_p]),
     "ssk_stack_stage_times": (C.c_int, [C.c_void_p, _P(C.c_float)]),
+    "ssk_upscale_size": (C.c_int, [C.c_int, C.c_int, C.c_int, _P(C.c_int), _P(C.c_int)]),
+    "ssk_upscale_image": (C.c_int, [C.c_int, _P(ssk_mat), _P(ssk_mat), _P(ssk_mat), _P(ssk_mat)]),
+    "ssk_upscale_remap": (C.c_int, [C.c_int, _P(ssk_mat), _P(ssk_mat)]),
+    "ssk_upscale_optflow": (C.c_int, [C.c_int, _P(ssk_mat), _P(ssk_mat)]),
+    "ssk_canvas_create": (C.c_int, [C.c_int, _P(C.c_void_p)]),
+    "ssk_canvas_destroy": (C.c_int, [C.c_void_p]),
+    "ssk_canvas_set_canvas_size": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "ssk_canvas_add": (C.c_int, [C.c_void_p, _P(ssk_mat), _P(ssk_mat), _P(ssk_mat), _P(C.c_int)]),
+    "ssk_canvas_compute": (C.c_int, [C.c_void_p, _P(ssk_mat), _P(ssk_mat), C.c_double, _P(C.c_int)]),
+    "ssk_canvas_clear": (C.c_int, [C.c_void_p]),
+    "ssk_canvas_accumulated_frames": (C.c_int, [C.c_void_p]),
+    "ssk_canvas_size": (C.c_int, [C.c_void_p, _P(C.c_int), _P(C.c_int), _P(C.c_int)]),
+    "ssk_canvas_last_bbox": (C.c_int, [C.c_void_p, _P(C.c_int)]),
     "ssk_eccflow_options_default": (None, [_P(ssk_eccflow_options)]),
     "ssk_eccflow_registration_options_default": (None, [_P(ssk_eccflow_options)]),
     "ssk_eccflow_create": (C.c_int, [_P(ssk_eccflow_options), _P(C.c_void_p)]),

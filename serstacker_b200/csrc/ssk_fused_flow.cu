@@ -6,6 +6,11 @@
 // with the map c_eccflow::compute left in _current_remap (c_frame_registration.cc:900-917), then compute_weights /
 // multiply_weights / c_weigthed_average::add as on the analytic path (c_image_stacking_pipeline.cc:1644-1779).
 //
+// The same kernel serves frame_upscale_after_align (c_image_stacking_pipeline.cc:1633-1660): the accumulator is 1.5 / 2 / 3 times
+// the frame size and the map of an output pixel is upscale_remap(current_remap) - cv::resize(INTER_LINEAR) or cv::pyrUp of the
+// map - evaluated on the fly from the flow field or from the analytic transform (ssk_upscale.cuh); the up-scaled map is
+// never written to memory.
+//
 // Structure: one CTA per 32 x 32 accumulator tile, 256 threads, 4 pixels per thread; mean and weight sum stay in registers
 // for all frames of the batch (read and written once per batch).  Per frame the CTA
 //   1. reads the flow of the tile plus its 2-px erosion halo (36 x 36 float2, the only per-pixel map traffic), forms the map
@@ -14,6 +19,7 @@
 //   2. erodes the flags 5 x 5 (positions outside the image do not erode: border value 255) and, for valid pixels, gathers the
 //      weight map and the frame at the map coordinate with cv::remap's arithmetic (sample_any) and updates the running mean.
 #include "ssk_fused_impl.cuh"
+#include "ssk_upscale.cuh"
 
 namespace ssk {
 
@@ -21,7 +27,24 @@ namespace {
 
 constexpr int HW = TW + 4, HH = TH + 4;      // tile + 2-px halo
 
-__global__ void __launch_bounds__(256) k_fused_flow(const __grid_constant__ WarpAccArgs a, const __grid_constant__ Tables tab, int ntx) {
+// map coordinate of output pixel (gx, gy): current_remap, or its up-scaling
+__device__ __forceinline__ float2 map_at(const WarpAccArgs &a, const UpscaleGeom &up, const MapCoef &m, const float2 *flow, int gx, int gy) {
+  auto src_uv = [&](int x, int y) -> float2 {
+    if (flow) {
+      const float2 d = __ldg(flow + (int64_t)y * a.src_cols + x);
+      return make_float2(__fadd_rn(d.x, (float)x), __fadd_rn(d.y, (float)y));      // ecc_flow_to_remap
+    }
+    float u, v;
+    map_xy(m, (float)x, (float)y, u, v);
+    return make_float2(u, v);
+  };
+  if (up.option == SSK_UPSCALE_NONE) return src_uv(gx, gy);
+  return make_float2(upscale_sample(up, [&](int x, int y) { return src_uv(x, y).x; }, gx, gy),
+                     upscale_sample(up, [&](int x, int y) { return src_uv(x, y).y; }, gx, gy));
+}
+
+__global__ void __launch_bounds__(256) k_fused_flow(const __grid_constant__ WarpAccArgs a, const __grid_constant__ Tables tab, int ntx,
+                                                    const __grid_constant__ UpscaleGeom up) {
   __shared__ unsigned char s_flag[2][HH][HW + 4];
   __shared__ float2 s_uv[TH][TW];            // map coordinates of the tile's own pixels
   const int bx0 = (blockIdx.x % ntx) * TW, by0 = (blockIdx.x / ntx) * TH;
@@ -44,15 +67,16 @@ __global__ void __launch_bounds__(256) k_fused_flow(const __grid_constant__ Warp
   for (int j = 0; j < a.njobs; ++j) {
     const FrameJob &job = a.jobs[j];
     if (!job.ok) continue;                                       // block-uniform
-    const float2 *flow = a.flow + (int64_t)j * a.flow_stride;
+    const float2 *flow = a.flow ? a.flow + (int64_t)j * a.flow_stride : nullptr;
+    const MapCoef m = job.map;
     // ---- 1. flags of tile + halo
     for (int i = threadIdx.x; i < HH * HW; i += 256) {
       const int hy = i / HW, hx = i - hy * HW;
       const int gx = bx0 - 2 + hx, gy = by0 - 2 + hy;
       unsigned char f = 1;                                       // outside the image: does not erode
       if ((unsigned)gx < (unsigned)a.cols && (unsigned)gy < (unsigned)a.rows) {
-        const float2 d = __ldg(flow + (int64_t)gy * a.cols + gx);
-        const float u = __fadd_rn(d.x, (float)gx), v = __fadd_rn(d.y, (float)gy);   // ecc_flow_to_remap
+        const float2 uvh = map_at(a, up, m, flow, gx, gy);
+        const float u = uvh.x, v = uvh.y;
         f = valid255(a.interp, u, v, a.src_cols, a.src_rows, tab.cubic_itab) ? 1 : 0;
         if (hx >= 2 && hx < 2 + TW && hy >= 2 && hy < 2 + TH) s_uv[hy - 2][hx - 2] = make_float2(u, v);
       }
@@ -106,11 +130,12 @@ __global__ void __launch_bounds__(256) k_fused_flow(const __grid_constant__ Warp
 
 }  // namespace
 
-int launch_warp_accumulate_flow(const WarpAccArgs &a, const Tables &tab, cudaStream_t s) {
-  SSK_REQUIRE(a.flow, "internal: flow form without a flow field");
-  SSK_REQUIRE(a.rows == a.src_rows && a.cols == a.src_cols, "eccflow maps have the reference frame size");
+int launch_warp_accumulate_flow(const WarpAccArgs &a, const Tables &tab, int upscale_option, cudaStream_t s) {
+  SSK_REQUIRE(a.flow || upscale_option != SSK_UPSCALE_NONE, "internal: per-pixel-map form without a flow field or an up-scaling");
+  const UpscaleGeom up = make_upscale_geom(upscale_option, a.src_cols, a.src_rows);
+  SSK_REQUIRE(a.rows == up.dh && a.cols == up.dw, "internal: accumulator size differs from the (up-scaled) map size");
   const int ntx = div_up(a.cols, TW), nty = div_up(a.rows, TH);
-  k_fused_flow<<<ntx * nty, 256, 0, s>>>(a, tab, ntx);
+  k_fused_flow<<<ntx * nty, 256, 0, s>>>(a, tab, ntx, up);
   SSK_LAUNCH_CHECK();
   return SSK_OK;
 }

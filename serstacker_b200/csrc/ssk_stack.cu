@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include "ssk_engine.cuh"
 #include "ssk_eccflow.cuh"
+#include "ssk_upscale.cuh"
 
 using namespace ssk;
 
@@ -50,6 +51,7 @@ struct ssk_stack {
   int max_batch = 0;
   // geometry of the sequence (fixed by set_reference)
   int rows = 0, cols = 0, type = -1, bpp = 0;
+  int upscale = 0, out_rows = 0, out_cols = 0;   // frame_upscale_after_align: option in force and the accumulator size
   bool have_reference = false;
   // per-slot device buffers
   DevBuf frame_slots, weight_slots, half_slots, half2_slots, gmap_slots, partials, stats, jobs, counter;
@@ -277,6 +279,12 @@ int ssk_stack_create(const ssk_stack_options *opts, ssk_stack **out) {
   SSK_REQUIRE(opts->sm_uscale >= 0 && opts->sm_uscale <= 12, "sharpness_measure.uscale 0..12");
   SSK_REQUIRE(!(opts->enable_registration && opts->registration.enable_eccflow_registration && opts->accumulation_method == SSK_STACK_BAYER_AVERAGE),
               "ssk_stack: eccflow registration with bayer_average is not implemented");
+  SSK_REQUIRE(opts->upscale_option >= SSK_UPSCALE_NONE && opts->upscale_option <= SSK_UPSCALE_X30, "ssk_stack: upscale_option must be none / x2.0 / x1.5 / x3.0");
+  if (opts->upscale_option != SSK_UPSCALE_NONE) {
+    SSK_REQUIRE(opts->upscale_stage == SSK_UPSCALE_AFTER_ALIGN || opts->upscale_stage == 0,
+                "ssk_stack: only frame_upscale_after_align is fused into the loop (up-scale the frames with ssk_upscale_image for before_align)");
+    SSK_REQUIRE(opts->accumulation_method != SSK_STACK_BAYER_AVERAGE, "ssk_stack: up-scaling with bayer_average is not implemented");
+  }
   ssk_stack *h = new (std::nothrow) ssk_stack();
   SSK_REQUIRE(h, "out of memory");
   h->o = *opts;
@@ -341,7 +349,11 @@ int ssk_stack_set_reference(ssk_stack *h, const ssk_mat *image, const ssk_mat *m
       if (int e = h->reg_h.r.flowh->reserve(h->max_batch)) return e;
   }
   if (int e = stack_alloc_slots(h)) return e;
-  if (int e = h->acc_h.a.ensure(h->rows, h->cols, bayer ? 3 : cn)) return e;
+  // frame_upscale_after_align: the frames are stacked at the up-scaled size (never during the master-frame pass,
+  // c_image_stacking_pipeline.cc:2093-2101; only behind a registration, :1633-1642)
+  h->upscale = (h->o.enable_registration && !h->o.generating_master_frame) ? h->o.upscale_option : SSK_UPSCALE_NONE;
+  upscale_size(h->upscale, h->cols, h->rows, &h->out_cols, &h->out_rows);
+  if (int e = h->acc_h.a.ensure(h->out_rows, h->out_cols, bayer ? 3 : cn)) return e;
   SSK_CUDA(cudaStreamSynchronize(h->stream));
   h->have_reference = true;
   return SSK_OK;
@@ -497,7 +509,7 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
   SSK_LAUNCH_CHECK();
   WarpAccArgs a = {};
   a.jobs = jobs; a.njobs = n;
-  a.rows = h->rows; a.cols = h->cols; a.src_rows = h->rows; a.src_cols = h->cols;
+  a.rows = h->out_rows; a.cols = h->out_cols; a.src_rows = h->rows; a.src_cols = h->cols;
   a.src_step = geom.step; a.w_step = (int64_t)h->cols * 4;
   a.depth = d; a.cn = cn; a.scale = geom.scale;
   const ssk_registration_options &ro = h->o.registration;
@@ -518,11 +530,12 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
   a.acc = h->acc_h.a.acc.as<float>(); a.wacc = h->acc_h.a.wacc.as<float>();
   if (getenv("SSK_NO_TMA_KERNEL")) a.tmap_frames = a.tmap_weights = nullptr;   // tuning knob: cp.async kernel pair
   if (fused_tma_applicable(a)) a.side_stream = nullptr;                        // one launch over all tiles: nothing to fork
-  if (h->o.enable_registration && h->reg_h.r.flow_enabled()) {
-    // per-pixel maps: _current_remap = c_eccflow's refinement of the ECC map (c_frame_registration.cc:900-917)
-    a.flow = h->reg_h.r.flowh->uv(0); a.flow_stride = (int64_t)h->rows * h->cols;
+  if (h->o.enable_registration && (h->reg_h.r.flow_enabled() || h->upscale != SSK_UPSCALE_NONE)) {
+    // per-pixel maps: _current_remap = c_eccflow's refinement of the ECC map (c_frame_registration.cc:900-917) and / or its
+    // up-scaling (upscale_remap, c_image_stacking_pipeline.cc:1633-1642)
+    if (h->reg_h.r.flow_enabled()) { a.flow = h->reg_h.r.flowh->uv(0); a.flow_stride = (int64_t)h->rows * h->cols; }
     a.side_stream = nullptr;
-    if (int e = launch_warp_accumulate_flow(a, h->tab, s)) return e;
+    if (int e = launch_warp_accumulate_flow(a, h->tab, h->upscale, s)) return e;
   } else if (bayer) {
     // the mask of custom_remap(current_remap, frame, mask, registration_options.interpolation) gates the gather of the raw
     // samples through current_remap (c_image_stacking_pipeline.cc:1644-1651, 1730-1752)

@@ -44,8 +44,9 @@ int launch_warp_accumulate(const WarpAccArgs &a, const Tables &tab, cudaStream_t
 // TMA form (ssk_fused_tma.cu): CV_32F single-channel frames with tensor maps, affine-like maps; one launch over all tiles.
 bool fused_tma_applicable(const WarpAccArgs &a);
 int launch_warp_accumulate_tma(const WarpAccArgs &a, const Tables &tab, cudaStream_t stream);
-// per-pixel-map form (ssk_fused_flow.cu): a.flow holds the c_eccflow result of every job
-int launch_warp_accumulate_flow(const WarpAccArgs &a, const Tables &tab, cudaStream_t stream);
+// per-pixel-map form (ssk_fused_flow.cu): a.flow holds the c_eccflow result of every job (or null: analytic maps) and / or the
+// map is up-scaled (frame_upscale_option, c_image_stacking_pipeline.cc:1633-1660: a.rows x a.cols is the up-scaled size)
+int launch_warp_accumulate_flow(const WarpAccArgs &a, const Tables &tab, int upscale_option, cudaStream_t stream);
 // Bayer form of the fused loop (ssk_bayer.cu): a.jobs[j].frame are raw Bayer frames, a.acc / a.wacc the rows x cols x 3 sums
 // and counters of c_bayer_average; the mask is base_remap's eroded validity for a.interp.
 int launch_bayer_warp_accumulate(const WarpAccArgs &a, const Tables &tab, int colorid, cudaStream_t stream);
