@@ -4,7 +4,7 @@ bench.py - frames/s of the stacking hot path (register + warp + stack) on BASELI
 synthetic 1920x1080 mono 32F frames, ECCH pyramid registration (AFFINE, INVERSE_COMPOSITIONAL_LM, translation first),
 bicubic remap, sharpness-weighted average.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--chunk C] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--chunk C] [--impl ours|reference] [--config 1|2|3|4|5]
 
 The job is the one BASELINE.json names: ONE sequence of K x B frames (B = 1024 by default) stacked into ONE image, the
 frames of every step sharded over the N ranks (one process per GPU, multi.shard_frames), i.e. STRONG scaling.  A "step" is
@@ -209,6 +209,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=48, help="frames of the CPU baseline sample")
     ap.add_argument("--verify", type=int, default=8, help="frames per rank of the N-rank vs single-GPU stack check (N > 1)")
     ap.add_argument("--seed", type=int, default=2, help="seed of the synthetic frame pool (rank r uses seed + 1000 r)")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
+                    help="BASELINE.json config: 2 = the headline line (default); 1, 3, 4, 5 = the secondary rows (one GPU, bench_secondary.py)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -246,6 +248,12 @@ def main():
                                  per_step, args.steps, __import__("cv2").__version__, ncores)},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
+
+    if args.config != 2:
+        if rank != 0:
+            return 0
+        import bench_secondary
+        return bench_secondary.run(args, peaks, ClockSampler)
 
     import torch
     import torch.distributed as dist

@@ -1,0 +1,287 @@
+"""Secondary rows of the measurement plan: `python bench.py --config 1|3|4|5`.
+
+One GPU, frames resident in HBM, the same JSON shape as the headline line of bench.py: frames/s of the config's per-frame
+path, the HBM-roofline fraction of its accumulate stage against section 8(d)'s algorithmic bytes per frame, and the oracle
+(CPU restatement) timed on a bounded sample of the same workload.  Config #2 is the headline line of bench.py itself.
+
+  #1  640x480 mono16, translation ECC (forward-additive, single level) + LINEAR/REFLECT101 warp + average      ssk_stack
+  #3  4096x3000 RGGB16, debayer_nn2 -> translation ECC -> Bayer-average accumulation of the raw samples          ssk_stack
+  #4  2048x2048 mono32F Jupiter: derotation remap + lpg weights + blend accumulation (pose given)               ssk_jdr_derotate_and_add
+  #5  2448x2048 RGB32F focus stack: lpg(k=6, p=2, 0, 0) -> GaussianBlur(1) -> weighted add, no registration     ssk_lpg / ssk_gaussian_blur / ssk_acc_add
+"""
+import ctypes as C
+import json
+import math
+import os
+import time
+
+import numpy as np
+
+
+def _planet_u16(n, w, h, seed):
+    from serstacker_b200 import synth
+    frames, _, bpp = synth.make_planet_sequence(w, h, n, seed=seed, radius=150, sigma_t=3.0, dtype="u16")
+    return frames, bpp
+
+
+def _jovian(size, center, axes, lon, lat, pa, seed):
+    """Synthetic textured oblate planet at a pose (longitude, tilt, position angle) - data generation only."""
+    import cv2
+    w, h = size
+    cl, sl, ct, st, cp, sp = math.cos(lon), math.sin(lon), math.cos(lat), math.sin(lat), math.cos(pa), math.sin(pa)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    xs, ys = xx - center[0], yy - center[1]
+    xr, yr = cp * xs + sp * ys, -sp * xs + cp * ys
+    A, B = axes[0], axes[1]
+    r2 = (xr / A) ** 2 + (yr / B) ** 2
+    z = np.sqrt(np.clip(1 - r2, 0, 1))
+    latp = np.arcsin(np.clip(yr / B * ct + z * st, -1, 1))
+    lonp = np.arctan2(xr / A, z) + lon
+    tex = 0.5 + 0.2 * np.sin(7 * latp) + 0.15 * np.sin(9 * lonp + 3 * latp) + 0.1 * np.cos(23 * lonp) * np.cos(11 * latp)
+    rng = np.random.default_rng(seed)
+    img = np.where(r2 < 1, tex * (0.4 + 0.6 * z), 0.02) + rng.normal(0, 0.003, (h, w))
+    return cv2.GaussianBlur(img.astype(np.float32), (0, 0), 1.0)
+
+
+def _rot(lon, lat, pa):
+    """XYZscreen = R XYZplanet for a pose (rotation about the polar axis, tilt towards the viewer, position angle)."""
+    cl, sl, ct, st, cp, sp = math.cos(lon), math.sin(lon), math.cos(lat), math.sin(lat), math.cos(pa), math.sin(pa)
+    Ry = np.array([[cl, 0, sl], [0, 1, 0], [-sl, 0, cl]])
+    Rx = np.array([[1, 0, 0], [0, ct, -st], [0, st, ct]])
+    Rz = np.array([[cp, -sp, 0], [sp, cp, 0], [0, 0, 1]])
+    return Rz @ Rx @ Ry
+
+
+def _focus_frames(n, w, h, seed):
+    import cv2
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    scene = np.zeros((h, w, 3), np.float32)
+    for c in range(3):
+        tex = cv2.resize(rng.random((h // 8, w // 8)).astype(np.float32), (w, h), interpolation=cv2.INTER_CUBIC)
+        fine = rng.random((h, w)).astype(np.float32)
+        scene[..., c] = np.clip(0.35 + 0.4 * (tex - 0.5) + (cv2.GaussianBlur(fine, (0, 0), 1.0) - 0.5), 0, 1)
+    depth = (xx / w + 0.5 * yy / h) / 1.5
+    b1, b2 = cv2.GaussianBlur(scene, (0, 0), 1.5), cv2.GaussianBlur(scene, (0, 0), 4.0)
+    out = []
+    for i in range(n):
+        d = np.clip(np.abs(depth - (i + 0.5) / n) * 3.0, 0, 1)[..., None]
+        f = np.where(d < 0.5, scene * (1 - 2 * d) + b1 * (2 * d), b1 * (2 - 2 * d) + b2 * (2 * d - 1)).astype(np.float32)
+        out.append(np.clip(f + rng.normal(0, 0.002, f.shape).astype(np.float32), 0, 1))
+    return out
+
+
+def run(args, peaks, ClockSampler):
+    import torch
+    from serstacker_b200 import api, capi
+    cfg = args.config
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    peak, peak_src = peaks()
+    sampler = ClockSampler(0)
+    launches0 = None
+    cpu = None
+    ncores = os.cpu_count() or 1
+
+    if cfg in (1, 3):
+        if cfg == 1:
+            W, H, B, POOL = 640, 480, 500, 64
+            frames, bpp = _planet_u16(POOL, W, H, seed=1)
+            workload = "config#1: 640x480 mono16, ECC(forward-additive, translation, single level) + LINEAR/REFLECT101 remap + average"
+            ro = api.registration_options(motion_type=capi.MOTION_TRANSLATION, interpolation=capi.INTER_LINEAR,
+                                          ecc=dict(ecc_method=capi.ECC_FORWARD_ADDITIVE, ecch_max_level=0))
+            so = api.stack_options(registration=ro, accumulation_method=capi.STACK_AVERAGE, max_batch=min(args.chunk, 250))
+            bytes_frame = W * H * (2 + 8 + 8)                    # N (s_in + 8C + 8)
+            kname = "fused LINEAR warp + eroded mask + running mean of 16-bit frames (k_fused_staged / k_fused_generic)"
+        else:
+            from serstacker_b200 import synth
+            W, H, B, POOL = 4096, 3000, 64, 8
+            frames, _, bpp = synth.make_bayer_sequence(W, H, POOL, seed=3)
+            workload = "config#3: 4096x3000 RGGB16, debayer_nn2 -> ECC(IC-LM, translation, full pyramid) at scale 0.5 -> Bayer-average accumulation"
+            ro = api.registration_options(motion_type=capi.MOTION_TRANSLATION, interpolation=capi.INTER_LINEAR,
+                                          ecc=dict(ecc_method=capi.ECC_INVERSE_COMPOSITIONAL_LM, ecch_max_level=-1))
+            so = api.stack_options(registration=ro, accumulation_method=capi.STACK_BAYER_AVERAGE, bayer_colorid=capi.COLORID_BAYER_RGGB,
+                                   max_batch=min(args.chunk, 32))
+            bytes_frame = W * H * (2 + 24 + 24)                  # N (s_in + 2*12 + 2*12)
+            kname = "Bayer gather of the raw samples through the analytic map into acc / cntr (k_bayer_warp_accumulate)"
+        CH = so.max_batch
+        pool = [torch.from_numpy(f.view(np.int16)).to(dev) for f in frames]     # 16-bit samples (torch has no uint16 arithmetic: raw bytes only)
+        pipe = api.c_image_stacking_pipeline(so)
+        pipe.set_reference(frames[0], bpp=bpp)
+        stream = torch.cuda.ExternalStream(pipe.stream(), device=dev)
+
+        def step_mats(s):
+            return [capi.device_mat(pool[1 + ((s * B + i) % (POOL - 1))].data_ptr(), H, W, np.uint16) for i in range(B)]
+
+        for s in range(args.warmup):
+            pipe.add_frames_async(step_mats(s))
+        pipe.sync()
+        pipe.reset()
+        torch.cuda.synchronize()
+        sampler.start()
+        launches0 = capi.lib.ssk_kernel_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        keep = [pipe.add_frames_async(step_mats(args.warmup + s)) for s in range(args.steps)]
+        out = pipe.compute()
+        e1.record(stream)
+        pipe.sync()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        stage = pipe.stage_times()
+        FL = B - ((B - 1) // CH) * CH
+        t_k = stage[3] * 1e-3
+        accumulated = pipe.accumulated_frames()
+        # e2e: the same job from pinned host frames through the public call
+        host = torch.empty((min(B, POOL - 1), H, W), dtype=torch.int16).pin_memory()
+        for i in range(host.shape[0]):
+            host[i].copy_(torch.from_numpy(frames[1 + i].view(np.int16)))
+        hnp = host.numpy().view(np.uint16)
+        pipe2 = api.c_image_stacking_pipeline(so)
+        pipe2.set_reference(frames[0], bpp=bpp)
+        hf = [hnp[i % hnp.shape[0]] for i in range(B)]
+        pipe2.add_frames(hf[:CH])
+        pipe2.reset()
+        t0 = time.perf_counter()
+        for i in range(0, B, CH):
+            pipe2.add_frames(hf[i:i + CH])
+        pipe2.compute()
+        e2e_s = time.perf_counter() - t0
+        e2e = {"value": B / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": B * W * H * 2,
+               "d2h_bytes_per_step": B * (C.sizeof(capi.ssk_transform) + C.sizeof(capi.ssk_ecc_status)) + W * H * (13 if cfg == 3 else 5)}
+        stage_ms = {"prep": stage[0], "weights": stage[1], "ecc": stage[2], "warp_accumulate": stage[3], "frames": FL}
+        # CPU baseline
+        from oracle import pipeline as opl, transforms as otf, ecc as oecc
+        import cv2
+        cv2.setNumThreads(ncores)
+        so_o = opl.StackingOptions(accumulation_method=opl.ACC_BAYER_AVERAGE if cfg == 3 else opl.ACC_AVERAGE)
+        so_o.registration.motion_type = otf.IMAGE_MOTION_TRANSLATION
+        so_o.registration.ecc.ecc_method = oecc.ECC_ALIGN_INVERSE_COMPOSITIONAL_LM if cfg == 3 else oecc.ECC_ALIGN_FORWARD_ADDITIVE
+        so_o.registration.ecc.ecch_max_level = -1 if cfg == 3 else 0
+        ns = 3 if cfg == 3 else min(48, POOL - 1)
+        t0 = time.perf_counter()
+        if cfg == 3:
+            opl.run_bayer_stacking(frames[1:1 + ns], bpp, so_o, 8, reference=frames[0])
+        else:
+            opl.run_stacking([opl.to_float_frame(f, bpp) for f in frames[1:1 + ns]], so_o, reference=opl.to_float_frame(frames[0], bpp))
+        dt_cpu = time.perf_counter() - t0
+        cpu = {"value": ns / dt_cpu, "unit": "frames/s", "cores": ncores, "kind": "port",
+               "sample": "%d frames of the same workload in %.1f s incl. the reference set-up (oracle/ over cv2 %s, cv2 threads = %d)" % (ns, dt_cpu, cv2.__version__, ncores)}
+        value = args.steps * B / (ms * 1e-3)
+        frames_total = args.steps * B
+    else:
+        import cv2
+        if cfg == 4:
+            W = H = 2048
+            POOL, B = 6, 24
+            center, A = (1021.4, 1030.8), 700.0
+            axes = (A, A * 0.93512560845968779724, A)
+            target = (0.3, math.radians(3.0), math.radians(15.0))
+            period, wts = 35740.632, 190.0
+            times = [(-150.0 + 60.0 * i) for i in range(POOL)]
+            poses = [(target[0] - 2 * math.pi * t / period, target[1], target[2]) for t in times]
+            frames = [_jovian((W, H), center, axes, p[0], p[1], p[2], seed=i) for i, p in enumerate(poses)]
+            workload = "config#4: 2048x2048 mono32F Jupiter sequence, per-frame derotation remap + lpg(k=2,p=2,dscale=2,uscale=6) weights + GaussianBlur + blend accumulation (pose given)"
+            bytes_frame = W * H * (4 + 8 + 8 + 4)
+            kname = "whole per-frame chain of ssk_jdr_derotate_and_add (derotation map, lpg, weight rules, GaussianBlur, TRANSPARENT remap, weighted add): time of the chain, not of one kernel"
+            Rt = _rot(*target)
+            half = int(A) + 24
+            cbox = (max(0, int(center[0]) - half), max(0, int(center[1]) - half), min(W, 2 * half), min(H, 2 * half))
+            acc = api.c_weigthed_average()
+            dfr = [torch.from_numpy(f).to(dev) for f in frames]
+            d = lambda v, n: (C.c_double * n)(*[float(x) for x in np.asarray(v, dtype=np.float64).reshape(-1)])
+
+            def one(i):
+                k = i % POOL
+                m = capi.device_mat(dfr[k].data_ptr(), H, W, np.float32)
+                capi.check(capi.lib.ssk_jdr_derotate_and_add(acc._h, C.byref(m), None, d(center, 2), d(axes, 3), d(_rot(*poses[k]), 9), d(Rt, 9),
+                                                             math.degrees(target[2]), (C.c_int * 4)(*cbox), 1.0 / (1.0 + abs(times[k]) / wts),
+                                                             int(times[k] == 0), 1, 2.0, 2.0, 2, 6))
+            hostone = lambda i: api.jdr_derotate_and_add(acc, frames[i % POOL], None, center, axes, _rot(*poses[i % POOL]), Rt, math.degrees(target[2]), cbox,
+                                                         1.0 / (1.0 + abs(times[i % POOL]) / wts), times[i % POOL] == 0)
+            h2d = W * H * 4
+        else:
+            W, H, POOL, B = 2448, 2048, 4, 24
+            frames = _focus_frames(POOL, W, H, seed=5)
+            workload = "config#5: 2448x2048 RGB32F focus stack, lpg(k=6,p=2,dscale=0,uscale=0) -> GaussianBlur(1) -> weighted average, no registration"
+            bytes_frame = W * H * (12 + 24 + 8 + 4)
+            kname = "whole per-frame chain ssk_lpg -> ssk_gaussian_blur -> ssk_acc_add: time of the chain, not of one kernel"
+            acc = api.c_weigthed_average()
+            dfr = [torch.from_numpy(f).to(dev) for f in frames]
+            wmap = torch.empty((H, W), dtype=torch.float32, device=dev)
+            wblur = torch.empty((H, W), dtype=torch.float32, device=dev)
+
+            def one(i):
+                m = capi.device_mat(dfr[i % POOL].data_ptr(), H, W, np.float32, cn=3)
+                mw, mb = capi.device_mat(wmap.data_ptr(), H, W, np.float32), capi.device_mat(wblur.data_ptr(), H, W, np.float32)
+                capi.check(capi.lib.ssk_lpg(C.byref(m), 6.0, 2.0, 0, 0, C.byref(mw)))
+                capi.check(capi.lib.ssk_gaussian_blur(C.byref(mw), 1.0, 1.0, C.byref(mb)))
+                capi.check(capi.lib.ssk_acc_add(acc._h, C.byref(m), C.byref(mb), 0))
+
+            def hostone(i):
+                f = frames[i % POOL]
+                acc.add(f, api.gaussian_blur(api.lpg(f, k=6.0, p=2.0, dscale=0, uscale=0), 1.0))
+            h2d = W * H * 12
+        for i in range(args.warmup * 2):
+            one(i)
+        acc.clear()
+        torch.cuda.synchronize()
+        sampler.start()
+        launches0 = capi.lib.ssk_kernel_launch_count()
+        t0 = time.perf_counter()                                 # every call of these stateless entry points ends with a stream sync
+        for s in range(args.steps):
+            for i in range(B):
+                one(s * B + i)
+        avg, _ = acc.compute()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        accumulated = acc.accumulated_frames()
+        value = args.steps * B / (ms * 1e-3)
+        frames_total = args.steps * B
+        t_k = ms * 1e-3 / frames_total
+        FL = 1
+        stage_ms = None
+        acc.clear()
+        t0 = time.perf_counter()
+        for i in range(B):
+            hostone(i)
+        acc.compute()
+        e2e_s = time.perf_counter() - t0
+        e2e = {"value": B / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": B * h2d, "d2h_bytes_per_step": W * H * (4 * (1 if cfg == 4 else 3) + 1)}
+        # CPU baseline
+        cv2.setNumThreads(ncores)
+        from oracle import accumulation as oacc
+        o = oacc.WeightedAverage()
+        ns = 3
+        t0 = time.perf_counter()
+        if cfg == 4:
+            from oracle import derotation as od
+            for i in range(ns):
+                od.jdr_derotate_and_add(o, frames[i], None, (W, H), center, axes, target, poses[i][0] - target[0], 1.0 / (1.0 + abs(times[i]) / wts),
+                                        is_master=(times[i] == 0), lpg_opts=dict(k=2.0, p=2.0, dscale=2, uscale=6))
+        else:
+            from oracle import weights as ow
+            for i in range(ns):
+                o.add(frames[i], cv2.GaussianBlur(ow.lpg(frames[i], k=6.0, p=2.0, dscale=0, uscale=0), (0, 0), 1, None, 1, cv2.BORDER_REPLICATE))
+        dt_cpu = time.perf_counter() - t0
+        cpu = {"value": ns / dt_cpu, "unit": "frames/s", "cores": ncores, "kind": "port",
+               "sample": "%d frames of the same workload in %.1f s (oracle/ over cv2 %s, cv2 threads = %d)" % (ns, dt_cpu, cv2.__version__, ncores)}
+
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    launches = capi.lib.ssk_kernel_launch_count() - launches0
+    achieved = bytes_frame * FL / t_k / 1e9
+    line = {
+        "metric": "frames/sec register+warp+stack (config #%d)" % cfg, "value": value, "unit": "frames/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "frames_per_step": B, "resident_pool_frames": POOL, "accumulated_frames": accumulated,
+                   "l2_policy": "inputs larger than L2: %d distinct frames (%.0f MB) cycled" % (POOL, POOL * bytes_frame / 1e6) if POOL * W * H * 2 > 126e6 else
+                                "pool of %d distinct frames (%.0f MB of input); the accumulate stage streams %.1f MB per frame" % (POOL, POOL * W * H * 2 / 1e6, bytes_frame / 1e6)},
+        "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "launch_ms": t_k * 1e3, "frames_per_launch": FL, "algorithmic_bytes_per_frame": bytes_frame},
+        "stage_ms_per_launch": stage_ms, "cpu_baseline": cpu, "clocks": sampler.summary(),
+    }
+    print(json.dumps(line))
+    return 0

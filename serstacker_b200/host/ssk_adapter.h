@@ -553,6 +553,51 @@ class c_bayer_average : public c_frame_accumulation {
 };
 
 // c_local_variance_sharpness_measure::compute (c_local_variance_sharpness_measure.cc:193-247)
+// c_canvas_average (core/average/c_frame_accumulation.h:65-137): boxes are {x, y, width, height}
+class c_canvas_average {
+ public:
+  struct options { int interpolation = SSK_INTER_LINEAR; } opts;
+  c_canvas_average() = default;
+  ~c_canvas_average() { if (h_) ssk_canvas_destroy(h_); }
+  c_canvas_average(const c_canvas_average &) = delete;
+  c_canvas_average &operator=(const c_canvas_average &) = delete;
+  void setCanvasSize(int cols, int rows) { want_cols_ = cols; want_rows_ = rows; clear(); }
+  int accumulated_frames() const { return h_ ? ssk_canvas_accumulated_frames(h_) : 0; }
+  void accumulator_size(int *cols, int *rows) const { *cols = *rows = 0; if (h_) ssk_canvas_size(h_, cols, rows, nullptr); }
+  void last_bbox(int bbox[4]) const { bbox[0] = bbox[1] = bbox[2] = bbox[3] = 0; if (h_) ssk_canvas_last_bbox(h_, bbox); }
+  bool add(const image_t &current_image, const image_t &current_weights_or_mask = image_t(), const image_t &rmap = image_t(),
+           const int *new_canvas_bbox = nullptr) {
+    if (!h_) {   // opts.interpolation is latched with the first frame
+      if (ssk_canvas_create(opts.interpolation, &h_) != SSK_OK) return false;
+      ssk_canvas_set_canvas_size(h_, want_cols_, want_rows_);
+    }
+    ssk_mat im = detail::view(current_image);
+    detail::Opt<image_t> w(current_weights_or_mask), m(rmap);
+    return ssk_canvas_add(h_, &im, w.get(), m.get(), new_canvas_bbox) == SSK_OK;
+  }
+  bool compute(image_t &avg, image_t *mask = nullptr, double dscale = 1.0, int ddepth = -1, const int *rbbox = nullptr) const {
+    if (!h_ || (ddepth >= 0 && ddepth != SSK_32F)) return false;
+    int cols = 0, rows = 0, cn = 0;
+    ssk_canvas_size(h_, &cols, &rows, &cn);
+    int x0 = 0, y0 = 0, x1 = cols, y1 = rows;
+    if (rbbox && rbbox[2] > 0 && rbbox[3] > 0) {
+      x0 = rbbox[0] > 0 ? rbbox[0] : 0; y0 = rbbox[1] > 0 ? rbbox[1] : 0;
+      x1 = rbbox[0] + rbbox[2] < cols ? rbbox[0] + rbbox[2] : cols; y1 = rbbox[1] + rbbox[3] < rows ? rbbox[1] + rbbox[3] : rows;
+    }
+    if (x1 <= x0 || y1 <= y0) return false;
+    create_like(avg, y1 - y0, x1 - x0, SSK_MAKETYPE(SSK_32F, cn));
+    ssk_mat a = detail::view(avg), mk;
+    if (mask) { create_like(*mask, y1 - y0, x1 - x0, SSK_8UC1); mk = detail::view(*mask); }
+    return ssk_canvas_compute(h_, &a, mask ? &mk : nullptr, dscale, rbbox) == SSK_OK;
+  }
+  void clear() { if (h_) { ssk_canvas_destroy(h_); h_ = nullptr; } }
+  static void computeCanvasSize(int frame_cols, int frame_rows, int *cols, int *rows) { *cols = 3 * frame_cols / 2; *rows = 3 * frame_rows / 2; }
+
+ private:
+  ssk_canvas *h_ = nullptr;
+  int want_cols_ = 0, want_rows_ = 0;
+};
+
 inline bool compute_local_variance_map(const image_t &image, image_t &map, int dscale = 1, int kradius = 1,
                                        int uscale = 0, double *Q = nullptr) {
   ssk_mat s = detail::view(image);
@@ -755,6 +800,55 @@ struct c_frame_accumulation_options {
   struct { int dscale = 1, kradius = 1, uscale = 0; } sharpness_measure;
 };
 
+// c_frame_upscale_options (c_image_stacking_pipeline.h:33-86)
+enum frame_upscale_stage { frame_upscale_stage_unknown = -1, frame_upscale_after_align = 1, frame_upscale_before_align = 2 };
+enum frame_upscale_option { frame_upscale_none = 0, frame_upscale_pyrUp = 1, frame_upscale_x15 = 2, frame_upscale_x30 = 3 };
+struct c_frame_upscale_options {
+  frame_upscale_option upscale_option = frame_upscale_none;
+  frame_upscale_stage upscale_stage = frame_upscale_after_align;
+  bool need_upscale_before_align() const { return upscale_option != frame_upscale_none && upscale_stage == frame_upscale_before_align; }
+  bool need_upscale_after_align() const { return upscale_option != frame_upscale_none && upscale_stage == frame_upscale_after_align; }
+  double image_scale() const { return upscale_option == frame_upscale_x15 ? 1.5 : upscale_option == frame_upscale_pyrUp ? 2 : upscale_option == frame_upscale_x30 ? 3 : 1.0; }
+};
+
+// c_image_stacking_pipeline::upscale_image / upscale_remap / upscale_optflow (c_image_stacking_pipeline.cc:1869-2002)
+inline bool upscale_image(frame_upscale_option scale, const image_t &src, const image_t &srcmask, image_t &dst, image_t *dstmask = nullptr) {
+  ssk_mat s = detail::view(src);
+  int uc = 0, ur = 0;
+  if (ssk_upscale_size(scale, s.cols, s.rows, &uc, &ur) != SSK_OK) return false;
+  image_t out, outm;                      // the reference up-scales in place: src and dst may be the same image
+  create_like(out, ur, uc, s.type);
+  ssk_mat d = detail::view(out), sm, dm;
+  const bool with_mask = dstmask && !srcmask.empty();
+  if (with_mask) { create_like(outm, ur, uc, SSK_8UC1); sm = detail::view(srcmask); dm = detail::view(outm); }
+  if (ssk_upscale_image(scale, &s, with_mask ? &sm : nullptr, &d, with_mask ? &dm : nullptr) != SSK_OK) return false;
+  dst = out;
+  if (with_mask) *dstmask = outm;
+  return true;
+}
+inline bool upscale_remap(frame_upscale_option scale, const image_t &srcmap, image_t &dstmap) {
+  ssk_mat s = detail::view(srcmap);
+  int uc = 0, ur = 0;
+  if (ssk_upscale_size(scale, s.cols, s.rows, &uc, &ur) != SSK_OK) return false;
+  image_t out;
+  create_like(out, ur, uc, SSK_32FC2);
+  ssk_mat d = detail::view(out);
+  if (ssk_upscale_remap(scale, &s, &d) != SSK_OK) return false;
+  dstmap = out;
+  return true;
+}
+inline bool upscale_optflow(frame_upscale_option scale, const image_t &srcmap, image_t &dstmap) {
+  ssk_mat s = detail::view(srcmap);
+  int uc = 0, ur = 0;
+  if (ssk_upscale_size(scale, s.cols, s.rows, &uc, &ur) != SSK_OK) return false;
+  image_t out;
+  create_like(out, ur, uc, SSK_32FC2);
+  ssk_mat d = detail::view(out);
+  if (ssk_upscale_optflow(scale, &s, &d) != SSK_OK) return false;
+  dstmap = out;
+  return true;
+}
+
 struct c_image_stacking_master_options {
   c_image_registration_options registration;
   c_frame_accumulation_options accumulation;
@@ -769,6 +863,9 @@ class c_image_stacking_pipeline {
   c_image_stacking_master_options master_options;
   c_image_registration_options registration_options;   // of the stacking pass
   c_frame_accumulation_options accumulation_options;
+  c_frame_upscale_options upscale_options;              // frame_upscale_after_align is fused into the loop; before_align up-scales
+                                                        // the frames first (weights are then computed on the up-scaled frames: the
+                                                        // reference computes them before up-scaling, c_image_stacking_pipeline.cc:1465-1496)
   int bayer_colorid = SSK_COLORID_BAYER_RGGB;
   int max_batch = 32;
 
@@ -778,13 +875,17 @@ class c_image_stacking_pipeline {
     image_t reference, refmask;
     if (!create_reference_frame(frames, bpp, reference, refmask)) return false;
     ssk_stack_options so = stack_options(registration_options, accumulation_options, false);
+    if (upscale_options.need_upscale_after_align()) { so.upscale_option = upscale_options.upscale_option; so.upscale_stage = SSK_UPSCALE_AFTER_ALIGN; }
+    if (upscale_options.need_upscale_before_align()) return false;   // see upscale_options above: up-scale the frames with upscale_image() first
     c_stacking_loop loop(so);
     if (!loop.valid() || !loop.set_reference(reference, bpp)) return false;
     if (!add_all(loop, frames, 0, (int)frames.size(), bpp)) return false;
     accumulated_frames_ = loop.accumulated_frames();
     const ssk_mat r = detail::view(reference);
     const int cn = accumulation_options.accumulation_method == SSK_STACK_BAYER_AVERAGE ? 3 : ((r.type >> 3) + 1);
-    return inpaint ? loop.compute_inpainted(stacked, stacked_mask, r.rows, r.cols, cn) : loop.compute(stacked, stacked_mask, r.rows, r.cols, cn);
+    int orows = r.rows, ocols = r.cols;
+    if (so.upscale_option != SSK_UPSCALE_NONE && so.enable_registration) ssk_upscale_size(so.upscale_option, r.cols, r.rows, &ocols, &orows);
+    return inpaint ? loop.compute_inpainted(stacked, stacked_mask, orows, ocols, cn) : loop.compute(stacked, stacked_mask, orows, ocols, cn);
   }
   // create_reference_frame (c_image_stacking_pipeline.cc:1112-1312)
   bool create_reference_frame(const std::vector<image_t> &frames, int bpp, image_t &reference, image_t &refmask) {

@@ -180,6 +180,35 @@ int main(int argc, char **argv) {
     std::printf("adapter_smoke: register_frame with eccflow: max |warped - reference| = %.4g\n", ferr);
     if (ferr > 0.05) return 15;
   }
+  // c_canvas_average and the up-scaling helpers
+  {
+    ssk::c_canvas_average canvas;
+    canvas.setCanvasSize(2 * W, 2 * H);
+    ssk::Mat ident(H, W, SSK_32FC2), cavg, cmsk;
+    for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) { ident.ptr<float>(y)[2 * x] = (float)x; ident.ptr<float>(y)[2 * x + 1] = (float)y; }
+    int bb[4];
+    if (!canvas.add(ref)) { std::fprintf(stderr, "c_canvas_average: %s\n", ssk_last_error()); return 16; }
+    canvas.last_bbox(bb);
+    const int moved[4] = {bb[0] + 40, bb[1] + 10, W, H};
+    if (!canvas.add(ref, ssk::Mat(), ident, moved) || canvas.accumulated_frames() != 2 || !canvas.compute(cavg, &cmsk)) return 16;
+    int cc = 0, cr = 0;
+    canvas.accumulator_size(&cc, &cr);
+    if (cc != 2 * W || cr != 2 * H || cavg.cols != cc || cmsk.ptr<uint8_t>(bb[1] + 20)[bb[0] + W + 20] != 255 || cmsk.ptr<uint8_t>(2)[2] != 0) return 16;
+    ssk::Mat up, upm, upmap;
+    if (!ssk::upscale_image(ssk::frame_upscale_x15, ref, amask, up, &upm) || up.cols != W * 3 / 2 || upm.rows != H * 3 / 2) return 16;
+    if (!ssk::upscale_remap(ssk::frame_upscale_pyrUp, ident, upmap) || upmap.cols != 2 * W) return 16;
+    if (std::fabs(upmap.ptr<float>(50)[2 * 100] - 49.75f) > 0.26f) return 16;   // pyrUp of the identity map: x / 2 up to the half-pixel phase
+    ssk::c_image_stacking_pipeline up_pipe;
+    up_pipe.registration_options.motion_type = SSK_MOTION_TRANSLATION; up_pipe.registration_options.enable_feature_registration = false;
+    up_pipe.registration_options.enable_ecc_registration = true; up_pipe.registration_options.ecc.ecc_method = SSK_ECC_INVERSE_COMPOSITIONAL_LM;
+    up_pipe.registration_options.ecc.ecch_max_level = -1;
+    up_pipe.master_options.generate_master_frame = false; up_pipe.master_options.unsharp_alpha = 0;
+    up_pipe.upscale_options.upscale_option = ssk::frame_upscale_x15;
+    up_pipe.max_batch = 4;
+    ssk::Mat ustack, umask;
+    if (!up_pipe.run(seq, 0, ustack, umask) || ustack.cols != W * 3 / 2 || ustack.rows != H * 3 / 2) { std::fprintf(stderr, "pipeline x1.5: %s\n", ssk_last_error()); return 16; }
+    std::printf("adapter_smoke: c_canvas_average %dx%d canvas, upscale helpers, x1.5 stack %dx%d ok\n", cc, cr, ustack.cols, ustack.rows);
+  }
   // input side
   ssk::Mat hmask(H, W, SSK_8UC1), lin, raw(H, W, SSK_16UC1), planes;
   std::memset(hmask.buf.data(), 255, hmask.buf.size());
