@@ -78,7 +78,7 @@ enum {
 /* ECC_INTERPOLATION_METHOD / ECC_BORDER_MODE, ecc2.h:27-52 (cv::InterpolationFlags / cv::BorderTypes values). */
 /* cv::InterpolationFlags values.  cv::remap itself replaces INTER_AREA by INTER_LINEAR, so SSK_INTER_AREA is accepted
    wherever a remap interpolation is expected and behaves as SSK_INTER_LINEAR (ECC_INTER_AREA, ecc2.h:37). */
-enum { SSK_INTER_NEAREST = 0, SSK_INTER_LINEAR = 1, SSK_INTER_CUBIC = 2, SSK_INTER_AREA = 3 };
+enum { SSK_INTER_NEAREST = 0, SSK_INTER_LINEAR = 1, SSK_INTER_CUBIC = 2, SSK_INTER_AREA = 3, SSK_INTER_LANCZOS4 = 4 };
 enum {
   SSK_BORDER_CONSTANT = 0, SSK_BORDER_REPLICATE = 1, SSK_BORDER_REFLECT = 2, SSK_BORDER_WRAP = 3,
   SSK_BORDER_REFLECT101 = 4, SSK_BORDER_TRANSPARENT = 5

@@ -7,6 +7,7 @@ tests/test_cvmodel.py.  The model is the specification the kernels are written t
 
 Test infrastructure only (see oracle/__init__.py).
 """
+import math
 import numpy as np
 
 f32 = np.float32
@@ -437,3 +438,93 @@ def dot_f32_simd(a, b, lanes=16):
     if i < n:
         r += float(np.dot(a[i:].astype(np.float64), b[i:].astype(np.float64)))
     return r
+
+
+# ---------------------------------------------------------------------------------------------------------
+# cv::remap(INTER_LANCZOS4) (OpenCV imgproc/imgwarp.cpp: interpolateLanczos4, initInterTab1D / initInterTab2D, remapLanczos4)
+# ---------------------------------------------------------------------------------------------------------
+def lanczos4_tab():
+    """[32][8] float coefficients of interpolateLanczos4 at f / 32: sin / cos in double, coefficients and their sum in float."""
+    s45 = 0.70710678118654752440084436210485
+    cs = [[1, 0], [-s45, -s45], [0, 1], [s45, -s45], [-1, 0], [s45, s45], [0, -1], [-s45, s45]]
+    tab = np.zeros((32, 8), f32)
+    for i in range(32):
+        x = f32(f32(i) * f32(1.0 / 32))
+        c = np.zeros(8, f32)
+        ssum = f32(0)
+        y0 = -(float(x) + 3) * math.pi * 0.25
+        s0, c0 = math.sin(y0), math.cos(y0)
+        for k in range(8):
+            y0_ = f32(x + f32(3) - f32(k))
+            if abs(float(y0_)) >= 1e-6:
+                y = -float(y0_) * math.pi * 0.25
+                c[k] = f32((cs[k][0] * s0 + cs[k][1] * c0) / (y * y))
+            else:
+                c[k] = f32(1e30)
+            ssum = f32(ssum + c[k])
+        tab[i] = (c * f32(f32(1) / ssum)).astype(f32)
+    return tab
+
+
+def lanczos4_itab():
+    """[32][32][8][8] fixed-point 2-D weights (initInterTab2D, fixpt): cvRound(w * 32768) with the sum forced to 32768 on the
+    largest / smallest of the four central entries."""
+    tab = lanczos4_tab()
+    out = np.zeros((32, 32, 8, 8), np.int32)
+    for i in range(32):
+        for j in range(32):
+            w = (tab[i][:, None] * tab[j][None, :]).astype(f32)
+            it = np.clip(np.rint((w * f32(32768)).astype(f32)), -32768, 32767).astype(np.int32)
+            diff = int(it.sum()) - 32768
+            if diff != 0:
+                Mk, mk = (4, 4), (4, 4)
+                for k1 in (4, 5):
+                    for k2 in (4, 5):
+                        if it[k1, k2] < it[mk]:
+                            mk = (k1, k2)
+                        elif it[k1, k2] > it[Mk]:
+                            Mk = (k1, k2)
+                if diff < 0:
+                    it[Mk] -= diff
+                else:
+                    it[mk] -= diff
+            out[i, j] = it
+    return out
+
+
+def remap_lanczos4_f32(src, mapx, mapy):
+    """cv::remap(src CV_32FC1, INTER_LANCZOS4) where the 8 x 8 footprint lies inside the image (NaN elsewhere): the float weight
+    of tap (ky, kx) is tab[fy][ky] * tab[fx][kx]; a row's eight products are added left to right, the rows top to bottom."""
+    tab = lanczos4_tab()
+    h, w = src.shape
+    sx = np.rint(mapx.astype(f32) * f32(32)).astype(np.int64)
+    sy = np.rint(mapy.astype(f32) * f32(32)).astype(np.int64)
+    ix, iy, fx, fy = (sx >> 5) - 3, (sy >> 5) - 3, sx & 31, sy & 31
+    inside = (ix >= 0) & (ix + 8 <= w) & (iy >= 0) & (iy + 8 <= h)
+    ixc, iyc = np.clip(ix, 0, w - 8), np.clip(iy, 0, h - 8)
+    out = np.zeros(mapx.shape, f32)
+    for r in range(8):
+        wy = tab[fy, r]
+        row = None
+        for k in range(8):
+            term = (src[iyc + r, ixc + k] * (wy * tab[fx, k]).astype(f32)).astype(f32)
+            row = term if row is None else (row + term).astype(f32)
+        out = (out + row).astype(f32)
+    out[~inside] = np.nan
+    return out
+
+
+def remap_lanczos4_all255_valid(size, mapx, mapy):
+    """(cv::remap(Mat1b(size, 255), INTER_LANCZOS4, BORDER_CONSTANT 0) >= 255) through the fixed-point table."""
+    h, w = size
+    itab = lanczos4_itab()
+    sx = np.rint(mapx.astype(f32) * f32(32)).astype(np.int64)
+    sy = np.rint(mapy.astype(f32) * f32(32)).astype(np.int64)
+    ix, iy, fx, fy = (sx >> 5) - 3, (sy >> 5) - 3, sx & 31, sy & 31
+    S = np.zeros(mapx.shape, np.int64)
+    for r in range(8):
+        oky = (iy + r >= 0) & (iy + r < h)
+        for k in range(8):
+            ok = oky & (ix + k >= 0) & (ix + k < w)
+            S += np.where(ok, itab[fy, fx, r, k], 0)
+    return np.clip((255 * S + (1 << 14)) >> 15, 0, 255) >= 255

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) k_canvas_add(const CanvasAddArgs a, const
   const float factor = weighted ? __fdiv_rn(wk, Wn) : __fdiv_rn(1.0f, Wn);
   *W = Wn;
   for (int c = 0; c < a.src.cn; ++c) {
-    const float I = a.rmap ? sample_any(a.src, c, u, v, a.interp, SSK_BORDER_REPLICATE, 0.f, tab.cubic)
+    const float I = a.rmap ? sample_any(a.src, c, u, v, a.interp, SSK_BORDER_REPLICATE, 0.f, tab.cubic, tab.lanczos)
                            : *reinterpret_cast<const float *>(static_cast<const char *>(a.src.data) + (int64_t)y * a.src.step + ((int64_t)x * a.src.cn + c) * 4);
     A[c] = fmaf(I - A[c], factor, A[c]);
   }
@@ -153,8 +153,8 @@ int ssk_canvas_create(int interpolation, ssk_canvas **out) {
     return SSK_ERR_CUDA;
   }
   SSK_REQUIRE(out, "null argument");
-  SSK_REQUIRE(interpolation == SSK_INTER_NEAREST || interpolation == SSK_INTER_LINEAR || interpolation == SSK_INTER_CUBIC || interpolation == SSK_INTER_AREA,
-              "c_canvas_average: interpolation must be NEAREST, LINEAR, CUBIC or AREA");
+  SSK_REQUIRE(interpolation == SSK_INTER_NEAREST || interpolation == SSK_INTER_LINEAR || interpolation == SSK_INTER_CUBIC || interpolation == SSK_INTER_AREA ||
+              interpolation == SSK_INTER_LANCZOS4, "c_canvas_average: interpolation must be NEAREST, LINEAR, CUBIC, AREA or LANCZOS4");
   ssk_canvas *h = new (std::nothrow) ssk_canvas();
   SSK_REQUIRE(h, "out of memory");
   h->interpolation = remap_interp(interpolation);

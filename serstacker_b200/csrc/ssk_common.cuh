@@ -49,6 +49,8 @@ constexpr int kCoefScale = 1 << kCoefBits;
 struct Tables {
   const float4 *cubic;      // [32] Keys coefficients at f/32 (float, A=-0.75)
   const short *cubic_itab;  // [32*32][16] fixed-point 2-D cubic weights, sum forced to 32768
+  const float *lanczos;     // [32][8] interpolateLanczos4 coefficients at f/32 (float)
+  const short *lanczos_itab;  // [32*32][64] fixed-point 2-D Lanczos weights, sum forced to 32768
 };
 int get_tables(Tables *t);   // lazily initialises for the current device
 
@@ -227,6 +229,50 @@ __device__ __forceinline__ float sample_cubic(const Img &im, int c, float u, flo
   return out;
 }
 
+// Lanczos4 (8 x 8 taps, first tap at ix - 3), one channel: the float weight of tap (ky, kx) is the product of the two 1-D
+// table entries (initInterTab2D); remapLanczos4 adds the eight products of a row left to right and the rows top to bottom
+// (bit-exact against cv2 4.13 where the 8 x 8 footprint is inside the image, oracle/cvmodel.py::remap_lanczos4_f32).
+template <int DEPTH>
+__device__ __forceinline__ float sample_lanczos4(const Img &im, int c, float u, float v, int border, float bval,
+                                                 const float *__restrict__ lz) {
+  int ix, fx, iy, fy;
+  quant32(u, ix, fx);
+  quant32(v, iy, fy);
+  const float *wx = lz + fx * 8, *wy = lz + fy * 8;
+  const bool inside = ix >= 3 && iy >= 3 && ix + 4 < im.cols && iy + 4 < im.rows;
+  if (inside) {
+    float out = 0.f;
+#pragma unroll 1
+    for (int ky = 0; ky < 8; ++ky) {
+      const float wyk = __ldg(wy + ky);
+      float row = 0.f;
+#pragma unroll
+      for (int kx = 0; kx < 8; ++kx) {
+        const float term = __fmul_rn(load_px<DEPTH>(im, iy - 3 + ky, ix - 3 + kx, c), __fmul_rn(wyk, __ldg(wx + kx)));
+        row = kx == 0 ? term : __fadd_rn(row, term);
+      }
+      out = __fadd_rn(out, row);
+    }
+    return out;
+  }
+  // footprint crossing the image edge: sum = cval + sum over the taps of (S - cval) w, tap by tap (remapLanczos4's border branch;
+  // BORDER_TRANSPARENT positions its taps like BORDER_REFLECT_101, BORDER_CONSTANT skips the outside taps)
+  const int tb = border == SSK_BORDER_TRANSPARENT ? SSK_BORDER_REFLECT101 : border;
+  float sum = bval;
+#pragma unroll 1
+  for (int ky = 0; ky < 8; ++ky) {
+    const int yy = border_idx(iy - 3 + ky, im.rows, tb);
+    if (yy < 0) continue;
+    const float wyk = __ldg(wy + ky);
+#pragma unroll 1
+    for (int kx = 0; kx < 8; ++kx) {
+      const int xx = border_idx(ix - 3 + kx, im.cols, tb);
+      if (xx >= 0) sum = __fadd_rn(sum, __fmul_rn(__fsub_rn(load_px<DEPTH>(im, yy, xx, c), bval), __fmul_rn(wyk, __ldg(wx + kx))));
+    }
+  }
+  return sum;
+}
+
 // Nearest: cvRound of the coordinate.
 template <int DEPTH>
 __device__ __forceinline__ float sample_nearest(const Img &im, int c, float u, float v, int border, float bval) {
@@ -278,6 +324,23 @@ __device__ __forceinline__ bool valid255_cubic(float u, float v, int cols, int r
   return val >= 255;
 }
 
+// Lanczos4: as the bicubic rule with the 8 x 8 fixed-point table
+static __device__ __noinline__ bool valid255_lanczos4(float u, float v, int cols, int rows, const short *__restrict__ itab) {
+  int ix, fx, iy, fy;
+  quant32(u, ix, fx);
+  quant32(v, iy, fy);
+  if (ix >= 3 && iy >= 3 && ix + 4 < cols && iy + 4 < rows) return true;
+  const short *w = itab + ((fy << kInterBits) + fx) * 64;
+  int S = 0;
+  for (int ky = 0; ky < 8; ++ky) {
+    if ((unsigned)(iy - 3 + ky) >= (unsigned)rows) continue;
+    for (int kx = 0; kx < 8; ++kx)
+      if ((unsigned)(ix - 3 + kx) < (unsigned)cols) S += __ldg(w + ky * 8 + kx);
+  }
+  return ((255 * S + (1 << (kCoefBits - 1))) >> kCoefBits) >= 255;
+}
+
+// itab: Tables::cubic_itab; Lanczos4 needs the whole Tables (valid255_t below)
 __device__ __forceinline__ bool valid255(int interp, float u, float v, int cols, int rows, const short *itab) {
   if (interp == SSK_INTER_CUBIC) return valid255_cubic(u, v, cols, rows, itab);
   if (interp == SSK_INTER_NEAREST) {
@@ -285,6 +348,11 @@ __device__ __forceinline__ bool valid255(int interp, float u, float v, int cols,
     return (unsigned)ix < (unsigned)cols && (unsigned)iy < (unsigned)rows;
   }
   return valid255_linear(u, v, cols, rows);
+}
+
+__device__ __forceinline__ bool valid255_t(int interp, float u, float v, int cols, int rows, const Tables &tab) {
+  if (interp == SSK_INTER_LANCZOS4) return valid255_lanczos4(u, v, cols, rows, tab.lanczos_itab);
+  return valid255(interp, u, v, cols, rows, tab.cubic_itab);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -102,6 +102,10 @@ int Ecch::init(const ssk_ecch_options &o, cudaStream_t s) {
   opts = o;
   stream = s;
   have_reference = false;
+  // c_ecc_align::_interpolation (ecc2.h:137) is the warp the forward-additive solver samples the current image with; the
+  // other solvers always sample bilinearly.  c_frame_registration never changes the default (INTER_LINEAR)
+  SSK_REQUIRE(o.interpolation == SSK_INTER_NEAREST || o.interpolation == SSK_INTER_LINEAR || o.interpolation == SSK_INTER_AREA,
+              "c_ecch: interpolation must be NEAREST, LINEAR or AREA (the solvers' image warp)");
   if (const char *e = getenv("SSK_ECC_CLUSTER")) {   // tuning knob: CTAs per frame (thread-block cluster size)
     const int c = atoi(e);
     if (c == 1 || c == 2 || c == 4 || c == 8) { cluster_size = c; cluster_fixed = true; }

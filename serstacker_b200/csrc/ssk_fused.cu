@@ -492,15 +492,16 @@ int staged_box_h() { return GSH; }
 
 int launch_warp_accumulate(const WarpAccArgs &a_in, const Tables &tab, cudaStream_t s) {
   WarpAccArgs a = a_in;
-  SSK_REQUIRE(a.interp == SSK_INTER_NEAREST || a.interp == SSK_INTER_LINEAR || a.interp == SSK_INTER_CUBIC,
-              "warp_accumulate: interpolation must be NEAREST, LINEAR or CUBIC");
+  SSK_REQUIRE(a.interp == SSK_INTER_NEAREST || a.interp == SSK_INTER_LINEAR || a.interp == SSK_INTER_CUBIC || a.interp == SSK_INTER_LANCZOS4,
+              "warp_accumulate: interpolation must be NEAREST, LINEAR, CUBIC or LANCZOS4");
   SSK_REQUIRE(a.border != SSK_BORDER_TRANSPARENT, "warp_accumulate: BORDER_TRANSPARENT is not meaningful here");
   SSK_REQUIRE(a.cn >= 1 && a.cn <= 4, "warp_accumulate: 1..4 channels");
   SSK_REQUIRE(a.depth == SSK_32F || a.depth == SSK_16U || a.depth == SSK_8U, "warp_accumulate: unsupported frame depth");
   a.stage_aligned = a.stage_aligned && (a.src_step % 16 == 0) && (a.w_step % 16 == 0);
-  if (fused_tma_applicable(a)) return launch_warp_accumulate_tma(a, tab, s);
+  const bool lanczos = a.interp == SSK_INTER_LANCZOS4;     // 8 x 8 taps: the one-thread-per-pixel form only
+  if (!lanczos && fused_tma_applicable(a)) return launch_warp_accumulate_tma(a, tab, s);
   const int ntx = div_up(a.cols, TW), nty = div_up(a.rows, TH);
-  const bool staged = a.cn == 1 && ntx >= 3 && nty >= 3 && a.src_cols < 32000 && a.src_rows < 32000 &&
+  const bool staged = !lanczos && a.cn == 1 && ntx >= 3 && nty >= 3 && a.src_cols < 32000 && a.src_rows < 32000 &&
                       (a.map_type == MAP_AFFINE || a.map_type == MAP_TRANSLATION || a.map_type == MAP_EUCLIDEAN);
   TileList tl;
   tl.ntx = ntx; tl.nty = nty; tl.ring = staged ? 1 : 0;

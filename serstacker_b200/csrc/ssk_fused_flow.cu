@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) k_fused_flow(const __grid_constant__ Warp
       if ((unsigned)gx < (unsigned)a.cols && (unsigned)gy < (unsigned)a.rows) {
         const float2 uvh = map_at(a, up, m, flow, gx, gy);
         const float u = uvh.x, v = uvh.y;
-        f = valid255(a.interp, u, v, a.src_cols, a.src_rows, tab.cubic_itab) ? 1 : 0;
+        f = valid255_t(a.interp, u, v, a.src_cols, a.src_rows, tab) ? 1 : 0;
         if (hx >= 2 && hx < 2 + TW && hy >= 2 && hy < 2 + TH) s_uv[hy - 2][hx - 2] = make_float2(u, v);
       }
       s_flag[buf][hy][hx] = f;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) k_fused_flow(const __grid_constant__ Warp
       float wk = 1.f;
       if (weighted) {
         im.data = job.weights; im.step = a.w_step; im.depth = SSK_32F; im.cn = 1; im.scale = 1.f;
-        wk = sample_any(im, 0, uv.x, uv.y, a.interp, SSK_BORDER_CONSTANT, 0.f, tab.cubic);
+        wk = sample_any(im, 0, uv.x, uv.y, a.interp, SSK_BORDER_CONSTANT, 0.f, tab.cubic, tab.lanczos);
         if (!(wk > 0.f)) continue;                               // c_frame_accumulation.cc:114
       }
       im.data = job.frame; im.step = a.src_step; im.depth = a.depth; im.cn = a.cn; im.scale = a.scale;
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) k_fused_flow(const __grid_constant__ Warp
       const float factor = weighted ? __fdiv_rn(wk, Wn) : __fdiv_rn(1.0f, Wn);
       W[k] = Wn;
       for (int c = 0; c < a.cn; ++c) {
-        const float I = sample_any(im, c, uv.x, uv.y, a.interp, a.border, a.bval[c], tab.cubic);
+        const float I = sample_any(im, c, uv.x, uv.y, a.interp, a.border, a.bval[c], tab.cubic, tab.lanczos);
         A[k][c] = fmaf(I - A[k][c], factor, A[k][c]);
       }
     }

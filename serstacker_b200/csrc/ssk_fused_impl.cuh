@@ -33,7 +33,12 @@ __device__ __noinline__ int border_idx_call(int p, int n, int border) { return b
 
 // cv::remap sample with run-time depth / interpolation / border, cv::remap's operation order (see ssk_common.cuh)
 __device__ __noinline__ float sample_any(const Img &im, int c, float u, float v, int interp, int border, float bval,
-                                         const float4 *cubic) {
+                                         const float4 *cubic, const float *lanczos = nullptr) {
+  if (interp == SSK_INTER_LANCZOS4) {
+    if (im.depth == SSK_32F) return sample_lanczos4<SSK_32F>(im, c, u, v, border, bval, lanczos);
+    if (im.depth == SSK_16U) return sample_lanczos4<SSK_16U>(im, c, u, v, border, bval, lanczos);
+    return sample_lanczos4<SSK_8U>(im, c, u, v, border, bval, lanczos);
+  }
   int ix, iy, fx = 0, fy = 0, n, off;
   float wx[4], wy[4];
   if (interp == SSK_INTER_NEAREST) {
@@ -80,7 +85,7 @@ __device__ __noinline__ float sample_any(const Img &im, int c, float u, float v,
 
 // mask(x, y) of base_remap: erode5x5(remap(all-255, interp, CONSTANT 0) >= 255) with border value 255
 __device__ __noinline__ bool valid_eroded(const MapCoef &m, int interp, int x, int y, int cols, int rows, int src_cols,
-                                          int src_rows, const short *itab) {
+                                          int src_rows, const Tables &tab) {
   float u, v;
   map_xy(m, (float)x, (float)y, u, v);
   if (is_affine_like(m.type)) {
@@ -89,7 +94,8 @@ __device__ __noinline__ bool valid_eroded(const MapCoef &m, int interp, int x, i
     float u1, v1, u2, v2;
     map_xy(m, (float)(x + 2), (float)y, u1, v1);
     map_xy(m, (float)x, (float)(y + 2), u2, v2);
-    const float ru = fabsf(u1 - u) + fabsf(u2 - u) + 3.f, rv = fabsf(v1 - v) + fabsf(v2 - v) + 3.f;
+    const float mg = interp == SSK_INTER_LANCZOS4 ? 5.f : 3.f;     // reach of the taps (Lanczos4: ix - 3 .. ix + 4)
+    const float ru = fabsf(u1 - u) + fabsf(u2 - u) + mg, rv = fabsf(v1 - v) + fabsf(v2 - v) + mg;
     if (u - ru >= 0.f && v - rv >= 0.f && u + ru <= (float)(src_cols - 1) && v + rv <= (float)(src_rows - 1)) return true;
   }
 #pragma unroll 1
@@ -101,7 +107,7 @@ __device__ __noinline__ bool valid_eroded(const MapCoef &m, int interp, int x, i
       const int xx = x + dx;
       if ((unsigned)xx >= (unsigned)cols) continue;
       map_xy(m, (float)xx, (float)yy, u, v);
-      if (!valid255(interp, u, v, src_cols, src_rows, itab)) return false;
+      if (!valid255_t(interp, u, v, src_cols, src_rows, tab)) return false;
     }
   }
   return true;
@@ -111,7 +117,7 @@ __device__ __noinline__ bool valid_eroded(const MapCoef &m, int interp, int x, i
 __device__ __noinline__ void generic_pixel(const WarpAccArgs &a, const Tables &tab, const FrameJob &job, int x, int y,
                                            float *A, float *W) {
   const MapCoef m = job.map;
-  if (!valid_eroded(m, a.interp, x, y, a.cols, a.rows, a.src_cols, a.src_rows, tab.cubic_itab)) return;
+  if (!valid_eroded(m, a.interp, x, y, a.cols, a.rows, a.src_cols, a.src_rows, tab)) return;
   float u, v;
   map_xy(m, (float)x, (float)y, u, v);
   Img im;
@@ -120,7 +126,7 @@ __device__ __noinline__ void generic_pixel(const WarpAccArgs &a, const Tables &t
   float wk = 1.f;
   if (weighted) {
     im.data = job.weights; im.step = a.w_step; im.depth = SSK_32F; im.cn = 1; im.scale = 1.f;
-    wk = sample_any(im, 0, u, v, a.interp, SSK_BORDER_CONSTANT, 0.f, tab.cubic);
+    wk = sample_any(im, 0, u, v, a.interp, SSK_BORDER_CONSTANT, 0.f, tab.cubic, tab.lanczos);
     if (!(wk > 0.f)) return;                      // c_frame_accumulation.cc:114
   }
   im.data = job.frame; im.step = a.src_step; im.depth = a.depth; im.cn = a.cn; im.scale = a.scale;
@@ -128,7 +134,7 @@ __device__ __noinline__ void generic_pixel(const WarpAccArgs &a, const Tables &t
   const float factor = weighted ? __fdiv_rn(wk, Wn) : __fdiv_rn(1.0f, Wn);
   *W = Wn;
   for (int c = 0; c < a.cn; ++c) {
-    const float I = sample_any(im, c, u, v, a.interp, a.border, a.bval[c], tab.cubic);
+    const float I = sample_any(im, c, u, v, a.interp, a.border, a.bval[c], tab.cubic, tab.lanczos);
     A[c] = fmaf(I - A[c], factor, A[c]);
   }
 }

@@ -92,10 +92,33 @@ static int sat_short(float v) {
   return (int)(r < -32768 ? -32768 : r > 32767 ? 32767 : r);
 }
 
+// interpolateLanczos4 (OpenCV imgproc, imgwarp.cpp) evaluated as OpenCV does: sin / cos in double, coefficients in float
+static void lanczos4_coeffs_host(float x, float *coeffs) {
+  static const double s45 = 0.70710678118654752440084436210485;
+  static const double cs[][2] = {{1, 0}, {-s45, -s45}, {0, 1}, {s45, -s45}, {-1, 0}, {s45, s45}, {0, -1}, {-s45, s45}};
+  const double kPi = 3.1415926535897932384626433832795;
+  float sum = 0;
+  const double y0 = -(x + 3) * kPi * 0.25, s0 = std::sin(y0), c0 = std::cos(y0);
+  for (int i = 0; i < 8; i++) {
+    const float y0_ = (x + 3 - i);
+    if (std::fabs(y0_) >= 1e-6f) {
+      const double y = -y0_ * kPi * 0.25;
+      coeffs[i] = (float)((cs[i][0] * s0 + cs[i][1] * c0) / (y * y));
+    } else {
+      coeffs[i] = 1e30f;
+    }
+    sum += coeffs[i];
+  }
+  sum = 1.f / sum;
+  for (int i = 0; i < 8; i++) coeffs[i] *= sum;
+}
+
 struct TableStore {
   int device = -1;
   float4 *cubic = nullptr;
   short *itab = nullptr;
+  float *lanczos = nullptr;
+  short *lanczos_itab = nullptr;
 };
 static std::mutex g_tab_mutex;
 static std::vector<TableStore> g_tabs;
@@ -105,7 +128,7 @@ int get_tables(Tables *t) {
   SSK_CUDA(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lock(g_tab_mutex);
   for (auto &s : g_tabs) {
-    if (s.device == dev) { t->cubic = s.cubic; t->cubic_itab = s.itab; return SSK_OK; }
+    if (s.device == dev) { t->cubic = s.cubic; t->cubic_itab = s.itab; t->lanczos = s.lanczos; t->lanczos_itab = s.lanczos_itab; return SSK_OK; }
   }
   float coef[kInterTab][4];
   for (int i = 0; i < kInterTab; ++i) cubic_coeffs_host((float)i * (1.0f / kInterTab), coef[i]);
@@ -134,8 +157,40 @@ int get_tables(Tables *t) {
       for (int k = 0; k < 16; ++k) dst[k] = (short)it[k / 4][k % 4];
     }
   }
+  // initInterTab1D / initInterTab2D(INTER_LANCZOS4): 8 coefficients per 1/32 fraction, 8 x 8 fixed-point products with the sum
+  // forced to 32768 on the largest (smallest) of the four central entries
+  static float lz[kInterTab][8];
+  for (int i = 0; i < kInterTab; ++i) lanczos4_coeffs_host((float)i * (1.0f / kInterTab), lz[i]);
+  std::vector<short> lz_itab((size_t)kInterTab * kInterTab * 64);
+  for (int i = 0; i < kInterTab; ++i) {
+    for (int j = 0; j < kInterTab; ++j) {
+      int it[8][8], isum = 0;
+      for (int k1 = 0; k1 < 8; ++k1)
+        for (int k2 = 0; k2 < 8; ++k2) {
+          const float v = lz[i][k1] * lz[j][k2];
+          isum += it[k1][k2] = sat_short(v * (float)kCoefScale);
+        }
+      if (isum != kCoefScale) {
+        const int diff = isum - kCoefScale;
+        int Mk1 = 4, Mk2 = 4, mk1 = 4, mk2 = 4;
+        for (int k1 = 4; k1 < 6; ++k1)
+          for (int k2 = 4; k2 < 6; ++k2) {
+            if (it[k1][k2] < it[mk1][mk2]) mk1 = k1, mk2 = k2;
+            else if (it[k1][k2] > it[Mk1][Mk2]) Mk1 = k1, Mk2 = k2;
+          }
+        if (diff < 0) it[Mk1][Mk2] -= diff;
+        else it[mk1][mk2] -= diff;
+      }
+      short *dst = &lz_itab[(size_t)(i * kInterTab + j) * 64];
+      for (int k = 0; k < 64; ++k) dst[k] = (short)it[k / 8][k % 8];
+    }
+  }
   TableStore s;
   s.device = dev;
+  SSK_CUDA(cudaMalloc(&s.lanczos, sizeof(lz)));
+  SSK_CUDA(cudaMalloc(&s.lanczos_itab, lz_itab.size() * sizeof(short)));
+  SSK_CUDA(cudaMemcpy(s.lanczos, lz, sizeof(lz), cudaMemcpyHostToDevice));
+  SSK_CUDA(cudaMemcpy(s.lanczos_itab, lz_itab.data(), lz_itab.size() * sizeof(short), cudaMemcpyHostToDevice));
   SSK_CUDA(cudaMalloc(&s.cubic, sizeof(coef)));
   SSK_CUDA(cudaMalloc(&s.itab, itab.size() * sizeof(short)));
   SSK_CUDA(cudaMemcpy(s.cubic, coef, sizeof(coef), cudaMemcpyHostToDevice));
@@ -143,6 +198,8 @@ int get_tables(Tables *t) {
   g_tabs.push_back(s);
   t->cubic = s.cubic;
   t->cubic_itab = s.itab;
+  t->lanczos = s.lanczos;
+  t->lanczos_itab = s.lanczos_itab;
   return SSK_OK;
 }
 

@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(256) k_remap(const RemapArgs a, const Tables t
   for (int c = 0; c < a.src.cn; ++c) {
     float r;
     if (a.interp == SSK_INTER_CUBIC) r = sample_cubic<SSK_32F>(a.src, c, u, v, a.border, a.bval[c], tab.cubic);
+    else if (a.interp == SSK_INTER_LANCZOS4) r = sample_lanczos4<SSK_32F>(a.src, c, u, v, a.border, a.bval[c], tab.lanczos);
     else if (a.interp == SSK_INTER_NEAREST) r = sample_nearest<SSK_32F>(a.src, c, u, v, a.border, a.bval[c]);
     else r = sample_linear<SSK_32F>(a.src, c, u, v, a.border, a.bval[c]);
     d[c] = r;
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(256) k_mask_pre(const RemapMaskArgs a, const T
   job_coords(a.map, a.rmap, a.rmap_step, x, y, u, v);
   bool ok;
   if (!a.src_mask) {
-    ok = valid255(a.interp, u, v, a.src_cols, a.src_rows, tab.cubic_itab);
+    ok = valid255_t(a.interp, u, v, a.src_cols, a.src_rows, tab);
   } else if (a.interp == SSK_INTER_NEAREST) {
     const int ix = __float2int_rn(u), iy = __float2int_rn(v);
     ok = (unsigned)ix < (unsigned)a.src_cols && (unsigned)iy < (unsigned)a.src_rows &&
@@ -67,7 +68,15 @@ __global__ void __launch_bounds__(256) k_mask_pre(const RemapMaskArgs a, const T
     quant32(u, ix, fx);
     quant32(v, iy, fy);
     int S = 0;
-    if (a.interp == SSK_INTER_CUBIC) {
+    if (a.interp == SSK_INTER_LANCZOS4) {
+      const short *w = tab.lanczos_itab + ((fy << kInterBits) + fx) * 64;
+      for (int ky = 0; ky < 8; ++ky)
+        for (int kx = 0; kx < 8; ++kx) {
+          const int xx = ix - 3 + kx, yy = iy - 3 + ky;
+          if ((unsigned)xx < (unsigned)a.src_cols && (unsigned)yy < (unsigned)a.src_rows)
+            S += w[ky * 8 + kx] * (int)a.src_mask[(int64_t)yy * a.src_mask_step + xx];
+        }
+    } else if (a.interp == SSK_INTER_CUBIC) {
       const short *w = tab.cubic_itab + ((fy << kInterBits) + fx) * 16;
       for (int ky = 0; ky < 4; ++ky)
         for (int kx = 0; kx < 4; ++kx) {
@@ -110,6 +119,8 @@ __global__ void __launch_bounds__(256) k_erode5(const uint8_t *src, int rows, in
 
 int launch_remap(const RemapArgs &a, const Tables &tab, cudaStream_t s) {
   SSK_REQUIRE(a.src.depth == SSK_32F && a.src.cn >= 1 && a.src.cn <= 4, "remap: CV_32F source with 1..4 channels");
+  SSK_REQUIRE(a.interp == SSK_INTER_NEAREST || a.interp == SSK_INTER_LINEAR || a.interp == SSK_INTER_CUBIC || a.interp == SSK_INTER_LANCZOS4,
+              "remap: interpolation must be NEAREST, LINEAR, CUBIC, AREA or LANCZOS4");
   dim3 grid(div_up(a.cols, 32), div_up(a.rows, 8));
   k_remap<<<grid, 256, 0, s>>>(a, tab);
   SSK_LAUNCH_CHECK();
@@ -117,6 +128,8 @@ int launch_remap(const RemapArgs &a, const Tables &tab, cudaStream_t s) {
 }
 
 int launch_remap_mask(const RemapMaskArgs &a, const Tables &tab, cudaStream_t s) {
+  SSK_REQUIRE(a.interp == SSK_INTER_NEAREST || a.interp == SSK_INTER_LINEAR || a.interp == SSK_INTER_CUBIC || a.interp == SSK_INTER_LANCZOS4,
+              "remap: interpolation must be NEAREST, LINEAR, CUBIC, AREA or LANCZOS4");
   dim3 grid(div_up(a.cols, 32), div_up(a.rows, 8));
   k_mask_pre<<<grid, 256, 0, s>>>(a, tab);
   SSK_LAUNCH_CHECK();

@@ -159,3 +159,20 @@ def test_remap_linear_u8_fixed_point_model_is_bit_exact():
         mapy = (yy * 0.99 + ty + 0.002 * xx).astype(np.float32)
         want = cv2.remap(m, np.dstack([mapx, mapy]), None, cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=0)
         assert np.array_equal(cvmodel.remap_linear_u8(m, mapx, mapy), want)
+
+
+def test_lanczos4_models_match_cv2():
+    """cv::remap(INTER_LANCZOS4): the float sampler (footprint inside the image) and the fixed-point all-255 validity rule."""
+    rng = np.random.default_rng(12)
+    src = rng.random((60, 70)).astype(np.float32)
+    yy, xx = np.mgrid[0:60, 0:70].astype(np.float32)
+    for k in range(3):
+        mx = (xx * np.float32(1.01 - 0.01 * k) - np.float32(3.3 + k) + yy * np.float32(0.02)).astype(np.float32)
+        my = (yy * np.float32(0.99) + np.float32(2.7 - 2 * k) - xx * np.float32(0.01)).astype(np.float32)
+        want = cv2.remap(src, mx, my, cv2.INTER_LANCZOS4)
+        got = m.remap_lanczos4_f32(src, mx, my)
+        ok = ~np.isnan(got)
+        assert ok.sum() > 1000 and np.array_equal(got[ok], want[ok])
+        msk = np.full((60, 70), 255, np.uint8)
+        wv = cv2.remap(msk, mx, my, cv2.INTER_LANCZOS4, borderMode=cv2.BORDER_CONSTANT, borderValue=0) >= 255
+        assert np.array_equal(m.remap_lanczos4_all255_valid((60, 70), mx, my), wv)

@@ -9,7 +9,7 @@ from oracle import registration as oreg
 pytestmark = pytest.mark.gpu
 
 BORDERS = [cv2.BORDER_REFLECT101, cv2.BORDER_REPLICATE, cv2.BORDER_CONSTANT, cv2.BORDER_REFLECT, cv2.BORDER_WRAP]
-INTERPS = [cv2.INTER_LINEAR, cv2.INTER_CUBIC, cv2.INTER_NEAREST]
+INTERPS = [cv2.INTER_LINEAR, cv2.INTER_CUBIC, cv2.INTER_NEAREST, cv2.INTER_LANCZOS4]
 
 
 def _rand_transform(rng, motion):
@@ -64,6 +64,27 @@ def test_remap_matches_cv2(gpu, interp, border):
         assert nbad <= (0 if motion in (0, 3) else 8), (motion, nbad, d.max())
         got2, _ = api.remap(None, rmap, src, interpolation=interp, border_mode=border, border_value=(0.25, 0, 0, 0))
         assert np.abs(got2 - want).max() <= 2e-6
+
+
+def test_remap_lanczos4_bit_exact_and_transparent(gpu):
+    """ECC_INTER_LANCZOS4 (ecc2.h:38): bit-exact against cv::remap, also at the border and with BORDER_TRANSPARENT."""
+    from serstacker_b200 import api
+    rng = np.random.default_rng(44)
+    src = rng.random((83, 131)).astype(np.float32)
+    t, o = _rand_transform(rng, 3)
+    rmap = o.create_remap((131, 83))
+    for border in BORDERS:
+        want = cv2.remap(src, rmap, None, cv2.INTER_LANCZOS4, borderMode=border, borderValue=0.25)
+        got, _ = api.remap(t, None, src, interpolation=cv2.INTER_LANCZOS4, border_mode=border, border_value=(0.25, 0, 0, 0))
+        assert np.array_equal(got, want), (border, np.abs(got - want).max())
+    dst0 = rng.random((83, 131)).astype(np.float32)
+    want = cv2.remap(src, rmap, None, cv2.INTER_LANCZOS4, dst=dst0.copy(), borderMode=cv2.BORDER_TRANSPARENT)
+    got, _ = api.remap(None, rmap, src, interpolation=cv2.INTER_LANCZOS4, border_mode=cv2.BORDER_TRANSPARENT, dst=dst0.copy())
+    assert np.array_equal(got, want)
+    src3 = rng.random((50, 70, 3)).astype(np.float32)
+    rmap3 = o.create_remap((70, 50))
+    assert np.array_equal(api.remap(None, rmap3, src3, interpolation=cv2.INTER_LANCZOS4, border_mode=cv2.BORDER_REFLECT101)[0],
+                          cv2.remap(src3, rmap3, None, cv2.INTER_LANCZOS4, borderMode=cv2.BORDER_REFLECT101))
 
 
 def test_remap_inter_area_is_linear(gpu):

@@ -158,6 +158,30 @@ def test_stack_weighted_affine_cubic_matches_oracle(gpu, method):
     assert rel_l2(p.accumulator().get_acc_counters(), acc_o.weights, m) <= 1e-4
 
 
+@pytest.mark.parametrize("acc", [0, 1])
+def test_stack_lanczos4_matches_oracle(gpu, acc):
+    """ECC_INTER_LANCZOS4 as registration_options.interpolation (ecc2.h:38; base_remap, c_frame_registration.cc:1265-1386):
+    frame, weight map and validity mask (8-bit fixed-point Lanczos table) through the one-thread-per-pixel fused kernel."""
+    from serstacker_b200 import api
+    frames, mats, _ = synth.make_planet_sequence(320, 240, 5, seed=6, radius=80, sigma_t=3.0, sigma_rot_deg=0.2,
+                                                 sigma_scale=0.002, blur_range=(0.8, 2.0), dtype="f32")
+    so = opl.StackingOptions(accumulation_method=opl.ACC_WEIGHTED_AVERAGE if acc else opl.ACC_AVERAGE)
+    so.registration.motion_type = otf.IMAGE_MOTION_AFFINE
+    so.registration.interpolation = cv2.INTER_LANCZOS4
+    so.registration.ecc.ecc_method = oecc.ECC_ALIGN_INVERSE_COMPOSITIONAL_LM
+    so.registration.ecc.ecch_max_level = -1
+    avg_o, mask_o, acc_o, _ = opl.run_stacking(frames, so)
+    ro = api.registration_options(motion_type=3, interpolation=cv2.INTER_LANCZOS4, ecc=dict(ecc_method=3, ecch_max_level=-1))
+    p = api.c_image_stacking_pipeline(api.stack_options(registration=ro, accumulation_method=acc, max_batch=5))
+    p.set_reference(frames[0])
+    p.add_frames(frames)
+    avg_g, mask_g = p.compute()
+    assert np.array_equal(mask_g, mask_o)
+    m = mask_o > 0
+    print("  stack LANCZOS4 (acc %d): rel-L2 = %.3g" % (acc, rel_l2(avg_g, avg_o, m)))
+    assert rel_l2(avg_g, avg_o, m) <= 1e-4
+
+
 def test_batched_equals_frame_by_frame(gpu):
     """Batching must not change the result: the accumulation order inside a batch is the frame order."""
     from serstacker_b200 import api
