@@ -191,12 +191,15 @@ def run(args, peaks, ClockSampler):
             dfr = [torch.from_numpy(f).to(dev) for f in frames]
             d = lambda v, n: (C.c_double * n)(*[float(x) for x in np.asarray(v, dtype=np.float64).reshape(-1)])
 
+            # per-frame arguments marshalled once (the measured loop is the library, not ctypes object construction)
+            jargs = []
+            for k in range(POOL):
+                jargs.append((C.byref(capi.device_mat(dfr[k].data_ptr(), H, W, np.float32)), d(center, 2), d(axes, 3), d(_rot(*poses[k]), 9), d(Rt, 9),
+                              math.degrees(target[2]), (C.c_int * 4)(*cbox), 1.0 / (1.0 + abs(times[k]) / wts), int(times[k] == 0)))
+
             def one(i):
-                k = i % POOL
-                m = capi.device_mat(dfr[k].data_ptr(), H, W, np.float32)
-                capi.check(capi.lib.ssk_jdr_derotate_and_add(acc._h, C.byref(m), None, d(center, 2), d(axes, 3), d(_rot(*poses[k]), 9), d(Rt, 9),
-                                                             math.degrees(target[2]), (C.c_int * 4)(*cbox), 1.0 / (1.0 + abs(times[k]) / wts),
-                                                             int(times[k] == 0), 1, 2.0, 2.0, 2, 6))
+                m, c2, a3, rc, rt, ang, cb, ws, ism = jargs[i % POOL]
+                capi.check(capi.lib.ssk_jdr_derotate_and_add(acc._h, m, None, c2, a3, rc, rt, ang, cb, ws, ism, 1, 2.0, 2.0, 2, 6))
             hostone = lambda i: api.jdr_derotate_and_add(acc, frames[i % POOL], None, center, axes, _rot(*poses[i % POOL]), Rt, math.degrees(target[2]), cbox,
                                                          1.0 / (1.0 + abs(times[i % POOL]) / wts), times[i % POOL] == 0)
             h2d = W * H * 4
@@ -211,12 +214,14 @@ def run(args, peaks, ClockSampler):
             wmap = torch.empty((H, W), dtype=torch.float32, device=dev)
             wblur = torch.empty((H, W), dtype=torch.float32, device=dev)
 
+            fm = [capi.device_mat(t.data_ptr(), H, W, np.float32, cn=3) for t in dfr]
+            mw, mb = capi.device_mat(wmap.data_ptr(), H, W, np.float32), capi.device_mat(wblur.data_ptr(), H, W, np.float32)
+            rf, rw, rb = [C.byref(m) for m in fm], C.byref(mw), C.byref(mb)
+
             def one(i):
-                m = capi.device_mat(dfr[i % POOL].data_ptr(), H, W, np.float32, cn=3)
-                mw, mb = capi.device_mat(wmap.data_ptr(), H, W, np.float32), capi.device_mat(wblur.data_ptr(), H, W, np.float32)
-                capi.check(capi.lib.ssk_lpg(C.byref(m), 6.0, 2.0, 0, 0, C.byref(mw)))
-                capi.check(capi.lib.ssk_gaussian_blur(C.byref(mw), 1.0, 1.0, C.byref(mb)))
-                capi.check(capi.lib.ssk_acc_add(acc._h, C.byref(m), C.byref(mb), 0))
+                capi.check(capi.lib.ssk_lpg(rf[i % POOL], 6.0, 2.0, 0, 0, rw))
+                capi.check(capi.lib.ssk_gaussian_blur(rw, 1.0, 1.0, rb))
+                capi.check(capi.lib.ssk_acc_add(acc._h, rf[i % POOL], rb, 0))
 
             def hostone(i):
                 f = frames[i % POOL]

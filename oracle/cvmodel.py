@@ -528,3 +528,132 @@ def remap_lanczos4_all255_valid(size, mapx, mapy):
             ok = oky & (ix + k >= 0) & (ix + k < w)
             S += np.where(ok, itab[fy, fx, r, k], 0)
     return np.clip((255 * S + (1 << 14)) >> 15, 0, 255) >= 255
+
+
+# ---------------------------------------------------------------------------------------------------------
+# cv::resize on CV_32F data as a non-IPP OpenCV build computes it (imgproc/resize.cpp): the per-axis tables the device code of
+# c_eccflow (ssk_eccflow.cu) and of the frame up-scaling (ssk_upscale.cuh) is written from
+# ---------------------------------------------------------------------------------------------------------
+def resize_cubic_tab(ssize, dsize):
+    """INTER_CUBIC: fx = (float)((d + 0.5) * scale - 0.5), s = floor(fx), interpolateCubic(fx - s) (A = -0.75) in float.
+    -> (s [dsize], coeffs [dsize][4]); the taps are s - 1 .. s + 2, clamped into the image."""
+    scale = 1.0 / (dsize / ssize)
+    s = np.zeros(dsize, np.int64)
+    c = np.zeros((dsize, 4), f32)
+    A = f32(-0.75)
+    for d in range(dsize):
+        fx = f32((d + 0.5) * scale - 0.5)
+        sx = int(np.floor(fx))
+        fx = f32(fx - f32(sx))
+        c0 = f32(f32(f32(f32(f32(f32(A * f32(fx + 1)) - f32(5 * A)) * f32(fx + 1)) + f32(8 * A)) * f32(fx + 1)) - f32(4 * A))
+        c1 = f32(f32(f32(f32(f32(f32(A + 2) * fx) - f32(A + 3)) * fx) * fx) + f32(1))
+        g = f32(1 - fx)
+        c2 = f32(f32(f32(f32(f32(f32(A + 2) * g) - f32(A + 3)) * g) * g) + f32(1))
+        c3 = f32(f32(f32(f32(1) - c0) - c1) - c2)
+        s[d] = sx
+        c[d] = [c0, c1, c2, c3]
+    return s, c
+
+
+def resize_cubic_f32(src, dsize):
+    """cv2.resize(src, dsize, interpolation=INTER_CUBIC) on CV_32F (1 or more channels): horizontal pass, then vertical."""
+    sh, sw = src.shape[:2]
+    dw, dh = dsize
+    xs, xc = resize_cubic_tab(sw, dw)
+    ys, yc = resize_cubic_tab(sh, dh)
+    H = np.zeros((sh, dw) + src.shape[2:], f32)
+    for dx in range(dw):
+        idx = np.clip(xs[dx] - 1 + np.arange(4), 0, sw - 1)
+        v = (src[:, idx[0]] * xc[dx, 0]).astype(f32)
+        for k in range(1, 4):
+            v = (v + (src[:, idx[k]] * xc[dx, k]).astype(f32)).astype(f32)
+        H[:, dx] = v
+    out = np.zeros((dh, dw) + src.shape[2:], f32)
+    for dy in range(dh):
+        idx = np.clip(ys[dy] - 1 + np.arange(4), 0, sh - 1)
+        v = (H[idx[0]] * yc[dy, 0]).astype(f32)
+        for k in range(1, 4):
+            v = (v + (H[idx[k]] * yc[dy, k]).astype(f32)).astype(f32)
+        out[dy] = v
+    return out
+
+
+def resize_area_tab(ssize, dsize):
+    """computeResizeAreaTab for one axis -> per destination index the list of (source index, float weight)."""
+    scale = 1.0 / (dsize / ssize)
+    out = []
+    for dx in range(dsize):
+        f1 = dx * scale
+        f2 = f1 + scale
+        cell = min(scale, ssize - f1)
+        s1, s2 = math.ceil(f1), math.floor(f2)
+        s2 = min(s2, ssize - 1)
+        s1 = min(s1, s2)
+        e = []
+        if s1 - f1 > 1e-3:
+            e.append((s1 - 1, f32((s1 - f1) / cell)))
+        for sx in range(s1, s2):
+            e.append((sx, f32(1.0 / cell)))
+        if f2 - s2 > 1e-3:
+            e.append((s2, f32(min(min(f2 - s2, 1.0), cell) / cell)))
+        out.append(e)
+    return out
+
+
+def resize_area_tables_f32(src, dsize):
+    """INTER_AREA through the per-axis tables, columns first (the order ssk_eccflow.cu::k_flow_reduce sums in); equals
+    cv2.resize(INTER_AREA) to float rounding for any scale >= 1 (cv2 sums rows first and takes a 1 / area path for integer scales)."""
+    sh, sw = src.shape[:2]
+    dw, dh = dsize
+    xt, yt = resize_area_tab(sw, dw), resize_area_tab(sh, dh)
+    col = np.zeros((dh, sw) + src.shape[2:], np.float64)
+    for dy, e in enumerate(yt):
+        for sy, b in e:
+            col[dy] += float(b) * src[sy]
+    out = np.zeros((dh, dw) + src.shape[2:], np.float64)
+    for dx, e in enumerate(xt):
+        for sx, a in e:
+            out[:, dx] += float(a) * col[:, sx]
+    return out.astype(f32)
+
+
+def resize_linear_axis(ssize, dsize):
+    """INTER_LINEAR: (s0, s1, a0, a1) per destination index; the fraction is zeroed where the taps would leave the image."""
+    scale = 1.0 / (dsize / ssize)
+    s0, s1 = np.zeros(dsize, np.int64), np.zeros(dsize, np.int64)
+    a0, a1 = np.zeros(dsize, f32), np.zeros(dsize, f32)
+    for d in range(dsize):
+        fx = f32((d + 0.5) * scale - 0.5)
+        s = int(np.floor(fx))
+        fx = f32(fx - f32(s))
+        if s < 0:
+            fx, s = f32(0), 0
+        if s >= ssize - 1:
+            fx, s = f32(0), ssize - 1
+        s0[d], s1[d], a0[d], a1[d] = s, min(s + 1, ssize - 1), f32(1) - fx, fx
+    return s0, s1, a0, a1
+
+
+def resize_linear_f32(src, dsize):
+    """cv2.resize(src, dsize, interpolation=INTER_LINEAR) on CV_32FC1 without IPP: S0 a0 + S1 a1 per axis, no fused multiply-add."""
+    sh, sw = src.shape
+    dw, dh = dsize
+    x0, x1, ax0, ax1 = resize_linear_axis(sw, dw)
+    y0, y1, ay0, ay1 = resize_linear_axis(sh, dh)
+    H = ((src[:, x0] * ax0).astype(f32) + (src[:, x1] * ax1).astype(f32)).astype(f32)
+    return ((H[y0] * ay0[:, None]).astype(f32) + (H[y1] * ay1[:, None]).astype(f32)).astype(f32)
+
+
+def resize_linear_u8_ge255(mask, dsize):
+    """(cv2.resize(mask CV_8UC1, dsize, INTER_LINEAR) >= 255) without IPP: 11-bit fixed-point coefficients cvRound(f * 2048),
+    horizontal pass in int, vertical ((b0 (S0 >> 4)) >> 16) + ((b1 (S1 >> 4)) >> 16) + 2) >> 2."""
+    sh, sw = mask.shape
+    dw, dh = dsize
+    x0, x1, ax0, ax1 = resize_linear_axis(sw, dw)
+    y0, y1, ay0, ay1 = resize_linear_axis(sh, dh)
+    ia0, ia1 = np.rint(ax0 * f32(2048)).astype(np.int64), np.rint(ax1 * f32(2048)).astype(np.int64)
+    ib0, ib1 = np.rint(ay0 * f32(2048)).astype(np.int64), np.rint(ay1 * f32(2048)).astype(np.int64)
+    m = mask.astype(np.int64)
+    H = m[:, x0] * ia0 + m[:, x1] * ia1
+    v = (((ib0[:, None] * (H[y0] >> 4)) >> 16) + ((ib1[:, None] * (H[y1] >> 4)) >> 16) + 2) >> 2
+    return v >= 255

@@ -759,67 +759,42 @@ __global__ void __launch_bounds__(256) k_channel_avg(const Img im, float *dst) {
   dst[(int64_t)y * im.cols + x] = __fmul_rn(sum, (float)(1.0 / im.cn));
 }
 
-static int lpg_device(Scratch &sc, Img im, double k, double p, int dscale, int uscale, float **out) {
-  cudaStream_t s = sc.stream;
-  SSK_REQUIRE(im.cn >= 1 && im.cn <= 4, "lpg: 1 to 4 channels");
-  // lpg.cc:184-200: integer samples are scaled by 1 / max value of the depth
-  im.scale = im.depth == SSK_8U ? (float)(1.0 / 255.0) : im.depth == SSK_16U ? (float)(1.0 / 65535.0) : 1.f;
-  const size_t n = (size_t)im.rows * im.cols;
-  if (im.cn > 1) {
-    if (int e = sc.c.ensure(n * 4)) return e;
-    const dim3 grid(div_up(im.cols, 32), div_up(im.rows, 8));
-    if (im.depth == SSK_32F) k_channel_avg<SSK_32F><<<grid, 256, 0, s>>>(im, sc.c.as<float>());
-    else if (im.depth == SSK_16U) k_channel_avg<SSK_16U><<<grid, 256, 0, s>>>(im, sc.c.as<float>());
-    else k_channel_avg<SSK_8U><<<grid, 256, 0, s>>>(im, sc.c.as<float>());
-    SSK_LAUNCH_CHECK();
-    im.data = sc.c.p; im.step = (int64_t)im.cols * 4; im.depth = SSK_32F; im.cn = 1; im.scale = 1.f;
+// pdownscale (lpg.cc:132-156): `level` pyrDowns between the two scratch buffers, stopping once a side drops below 4
+static int lpg_pdown(cudaStream_t s, float *bufA, float *bufB, Img cur, int level, float post, float **out, int *orows, int *ocols) {
+  float *dst = static_cast<const void *>(cur.data) == bufA ? bufB : bufA;
+  if (std::min(cur.rows, cur.cols) < 4) { *out = nullptr; return SSK_OK; }
+  for (int l = 0; l < level; ++l) {
+    const int nr = (cur.rows + 1) / 2, nc = (cur.cols + 1) / 2;
+    PyrDownArgs pd = {};
+    pd.src = cur; pd.dst = dst; pd.dst_rows = nr; pd.dst_cols = nc; pd.batch = 1; pd.post_scale = 1.f;
+    if (int e = launch_pyrdown(pd, s)) return e;
+    cur.data = dst; cur.step = (int64_t)nc * 4; cur.rows = nr; cur.cols = nc; cur.depth = SSK_32F; cur.cn = 1; cur.scale = 1.f;
+    *out = dst;
+    dst = dst == bufA ? bufB : bufA;
+    if (std::min(nr, nc) < 4) break;
   }
-  if (int e = sc.b.ensure(n * 4 * 2)) return e;
-  float *bufA = sc.b.as<float>(), *bufB = bufA + n;
-  // pdownscale (lpg.cc:132-156): `level` pyrDowns, stopping once a side drops below 4
-  auto pdown = [&](Img cur, int level, float post, float **out, int *orows, int *ocols) -> int {
-    float *dst = static_cast<const void *>(cur.data) == bufA ? bufB : bufA;
-    if (std::min(cur.rows, cur.cols) < 4) { *out = nullptr; return SSK_OK; }
-    for (int l = 0; l < level; ++l) {
-      const int nr = (cur.rows + 1) / 2, nc = (cur.cols + 1) / 2;
-      PyrDownArgs pd = {};
-      pd.src = cur; pd.dst = dst; pd.dst_rows = nr; pd.dst_cols = nc; pd.batch = 1; pd.post_scale = 1.f;
-      if (int e = launch_pyrdown(pd, s)) return e;
-      cur.data = dst; cur.step = (int64_t)nc * 4; cur.rows = nr; cur.cols = nc; cur.depth = SSK_32F; cur.cn = 1; cur.scale = 1.f;
-      *out = dst;
-      dst = dst == bufA ? bufB : bufA;
-      if (std::min(nr, nc) < 4) break;
-    }
-    *orows = cur.rows; *ocols = cur.cols;
-    if (post != 1.f) return launch_scale_ipow(*out, (int64_t)cur.rows * cur.cols, post, true, 1, s);
-    return SSK_OK;
-  };
-  float *S = nullptr;
-  int r = im.rows, c = im.cols;
-  if (dscale > 0) {
-    if (int e = pdown(im, dscale, (float)(1.0 / (1 + dscale)), &S, &r, &c)) return e;
-  }
-  if (!S) {   // no down-scaling: plain float copy of the image
-    if (int e = launch_to_gray(im, nullptr, bufA, nullptr, 1, s)) return e;
-    S = bufA; r = im.rows; c = im.cols;
-    if (dscale > 0) { if (int e = launch_scale_ipow(S, (int64_t)r * c, (float)(1.0 / (1 + dscale)), true, 1, s)) return e; }
-  }
-  float *M = S == bufA ? bufB : bufA;
-  if (int e = launch_lpg5x5(S, r, c, M, (float)((float)(k / (k + 1)) * (25.f * 25.f)), (float)((float)(1.0 / (k + 1)) * ((float)(100.0 / 36.0) * (float)(100.0 / 36.0))), 1e-9f, s)) return e;
+  *orows = cur.rows; *ocols = cur.cols;
+  if (post != 1.f) return launch_scale_ipow(*out, (int64_t)cur.rows * cur.cols, post, true, 1, s);
+  return SSK_OK;
+}
+
+// lpg.cc:262-290 after the 5 x 5 operator: pdownscale by uscale - dscale (times that factor), cv::pow(p), pupscale back
+static int lpg_finish(cudaStream_t s, float *M, float *bufA, float *bufB, int r, int c, int im_rows, int im_cols, double p, int dscale,
+                      int uscale, bool pow_done, float **out) {
   if (uscale > 0 && uscale > dscale) {
     Img cur = {};
     cur.data = M; cur.step = (int64_t)c * 4; cur.rows = r; cur.cols = c; cur.depth = SSK_32F; cur.cn = 1; cur.scale = 1.f;
     float *D = nullptr;
-    if (int e = pdown(cur, uscale - dscale, (float)(uscale - dscale), &D, &r, &c)) return e;
+    if (int e = lpg_pdown(s, bufA, bufB, cur, uscale - dscale, (float)(uscale - dscale), &D, &r, &c)) return e;
     if (D) M = D;
     else { if (int e = launch_scale_ipow(M, (int64_t)r * c, (float)(uscale - dscale), true, 1, s)) return e; }
   }
   const int ip = (int)p;
-  if (ip != 0 && ip != 1) { if (int e = launch_scale_ipow(M, (int64_t)r * c, 1.f, false, ip, s)) return e; }
+  if (!pow_done && ip != 0 && ip != 1) { if (int e = launch_scale_ipow(M, (int64_t)r * c, 1.f, false, ip, s)) return e; }
   // pupscale (lpg.cc:158-182): the (w+1)/2 size chain from the image size down to the map size, walked back by cv::pyrUp
-  if (r != im.rows || c != im.cols) {
+  if (r != im_rows || c != im_cols) {
     int cw[32], chh[32], nl = 0;
-    cw[0] = im.cols; chh[0] = im.rows;
+    cw[0] = im_cols; chh[0] = im_rows;
     while (true) {
       const int nw = (cw[nl] + 1) / 2, nh = (chh[nl] + 1) / 2;
       if (nw == c && nh == r) break;
@@ -836,6 +811,47 @@ static int lpg_device(Scratch &sc, Img im, double k, double p, int dscale, int u
   }
   *out = M;
   return SSK_OK;
+}
+
+static int lpg_device(Scratch &sc, Img im, double k, double p, int dscale, int uscale, float **out) {
+  cudaStream_t s = sc.stream;
+  SSK_REQUIRE(im.cn >= 1 && im.cn <= 4, "lpg: 1 to 4 channels");
+  // lpg.cc:184-200: integer samples are scaled by 1 / max value of the depth
+  im.scale = im.depth == SSK_8U ? (float)(1.0 / 255.0) : im.depth == SSK_16U ? (float)(1.0 / 65535.0) : 1.f;
+  const size_t n = (size_t)im.rows * im.cols;
+  const float alpha = (float)((float)(k / (k + 1)) * (25.f * 25.f));
+  const float beta = (float)((float)(1.0 / (k + 1)) * ((float)(100.0 / 36.0) * (float)(100.0 / 36.0)));
+  if (int e = sc.b.ensure(n * 4 * 2)) return e;
+  float *bufA = sc.b.as<float>(), *bufB = bufA + n;
+  if (dscale <= 0 && std::min(im.rows, im.cols) >= 5) {
+    // nothing is scaled before the 5 x 5 operator: channel average, operator and (when no scaling follows either) the power in
+    // one pass over the frame
+    const bool pow_fused = !(uscale > 0 && uscale > dscale);
+    if (int e = launch_lpg_fused(im, bufA, alpha, beta, 1e-9f, pow_fused ? (int)p : 1, s)) return e;
+    return lpg_finish(s, bufA, bufA, bufB, im.rows, im.cols, im.rows, im.cols, p, dscale, uscale, pow_fused, out);
+  }
+  if (im.cn > 1) {
+    if (int e = sc.c.ensure(n * 4)) return e;
+    const dim3 grid(div_up(im.cols, 32), div_up(im.rows, 8));
+    if (im.depth == SSK_32F) k_channel_avg<SSK_32F><<<grid, 256, 0, s>>>(im, sc.c.as<float>());
+    else if (im.depth == SSK_16U) k_channel_avg<SSK_16U><<<grid, 256, 0, s>>>(im, sc.c.as<float>());
+    else k_channel_avg<SSK_8U><<<grid, 256, 0, s>>>(im, sc.c.as<float>());
+    SSK_LAUNCH_CHECK();
+    im.data = sc.c.p; im.step = (int64_t)im.cols * 4; im.depth = SSK_32F; im.cn = 1; im.scale = 1.f;
+  }
+  float *S = nullptr;
+  int r = im.rows, c = im.cols;
+  if (dscale > 0) {
+    if (int e = lpg_pdown(s, bufA, bufB, im, dscale, (float)(1.0 / (1 + dscale)), &S, &r, &c)) return e;
+  }
+  if (!S) {   // no down-scaling: plain float copy of the image
+    if (int e = launch_to_gray(im, nullptr, bufA, nullptr, 1, s)) return e;
+    S = bufA; r = im.rows; c = im.cols;
+    if (dscale > 0) { if (int e = launch_scale_ipow(S, (int64_t)r * c, (float)(1.0 / (1 + dscale)), true, 1, s)) return e; }
+  }
+  float *M = S == bufA ? bufB : bufA;
+  if (int e = launch_lpg5x5(S, r, c, M, alpha, beta, 1e-9f, s)) return e;
+  return lpg_finish(s, M, bufA, bufB, r, c, im.rows, im.cols, p, dscale, uscale, false, out);
 }
 
 extern "C" {
@@ -1131,19 +1147,24 @@ int ssk_jdr_derotate_and_add(ssk_acc *acc, const ssk_mat *frame, const ssk_mat *
   Scratch &sc = scratch();
   if (int e = sc.init()) return e;
   cudaStream_t s = sc.stream;
-  static thread_local DevBuf d_frame, d_mask, d_rmap, d_wpre, d_w, d_rmask, d_lpg, d_wblur, d_out;
+  static thread_local DevBuf d_frame, d_mask, d_rmap, d_wpre, d_w, d_rmask, d_wblur;
   Tables tab;
   if (int e = get_tables(&tab)) return e;
   const size_t n = (size_t)rows * cols;
-  if (int e = d_frame.ensure(n * 4)) return e;
   if (int e = d_rmap.ensure(n * 8)) return e;
   if (int e = d_wpre.ensure(n * 4)) return e;
   if (int e = d_w.ensure(n * 4)) return e;
   if (int e = d_rmask.ensure(n)) return e;
   if (int e = d_wblur.ensure(n * 4)) return e;
-  if (int e = d_out.ensure(n * 4)) return e;
-  SSK_CUDA(cudaMemcpy2DAsync(d_frame.p, (size_t)cols * 4, frame->data, frame->step, (size_t)cols * 4, rows,
-                             frame->mem == SSK_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  // the frame as a dense device image (a dense device frame is used where it lies)
+  const float *d_f;
+  if (frame->mem == SSK_MEM_DEVICE && frame->step == (int64_t)cols * 4) d_f = static_cast<const float *>(frame->data);
+  else {
+    if (int e = d_frame.ensure(n * 4)) return e;
+    SSK_CUDA(cudaMemcpy2DAsync(d_frame.p, (size_t)cols * 4, frame->data, frame->step, (size_t)cols * 4, rows,
+                               frame->mem == SSK_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    d_f = d_frame.as<float>();
+  }
   const uint8_t *dm = nullptr;
   int64_t mstep = 0;
   if (mask) { if (int e = mask_to_device(mask, rows, cols, d_mask, s, &dm, &mstep)) return e; }
@@ -1156,26 +1177,15 @@ int ssk_jdr_derotate_and_add(ssk_acc *acc, const ssk_mat *frame, const ssk_mat *
   a.ca = std::cos(ang); a.sa = std::sin(ang); a.wscale = wscale;
   a.rmap = d_rmap.as<float2>(); a.wmap = d_wpre.as<float>(); a.rmask = d_rmask.as<uint8_t>();
   if (int e = launch_ellipsoid_remap(a, s)) return e;
-  RemapArgs ra = {};
-  ra.src.data = d_wpre.p; ra.src.step = (int64_t)cols * 4; ra.src.rows = rows; ra.src.cols = cols; ra.src.depth = SSK_32F; ra.src.cn = 1; ra.src.scale = 1.f;
-  ra.dst = d_w.as<float>(); ra.dst_step = (int64_t)cols * 4; ra.rows = rows; ra.cols = cols;
-  ra.rmap = d_rmap.as<float2>(); ra.rmap_step = (int64_t)cols * 8;
-  ra.interp = SSK_INTER_LINEAR; ra.border = SSK_BORDER_CONSTANT;
-  if (int e = launch_remap(ra, tab, s)) return e;
-  // lpg(frame) remapped in place with BORDER_TRANSPARENT (outliers keep the unmapped value)
-  const float *d_l = nullptr;
+  // lpg(frame); its TRANSPARENT remap, the remap of the limb weight and the weight rules are one pass (k_jdr_weights_fused)
+  float *L = nullptr;
   if (enable_weighted_average) {
     Img im;
-    im.data = d_frame.p; im.step = (int64_t)cols * 4; im.rows = rows; im.cols = cols; im.depth = SSK_32F; im.cn = 1; im.scale = 1.f;
-    float *L = nullptr;
+    im.data = d_f; im.step = (int64_t)cols * 4; im.rows = rows; im.cols = cols; im.depth = SSK_32F; im.cn = 1; im.scale = 1.f;
     if (int e = lpg_device(sc, im, lpg_k, lpg_p, lpg_dscale, lpg_uscale, &L)) return e;
-    if (int e = d_lpg.ensure(n * 4)) return e;
-    SSK_CUDA(cudaMemcpyAsync(d_lpg.p, L, n * 4, cudaMemcpyDeviceToDevice, s));
-    ra.src.data = L; ra.dst = d_lpg.as<float>(); ra.border = SSK_BORDER_TRANSPARENT;
-    if (int e = launch_remap(ra, tab, s)) return e;
-    d_l = d_lpg.as<float>();
   }
-  if (int e = launch_jdr_weights(d_w.as<float>(), d_l, d_rmask.as<uint8_t>(), dm, mstep, rows, cols, is_master, s)) return e;
+  if (int e = launch_jdr_weights_fused(d_wpre.as<float>(), L, d_rmap.as<float2>(), d_rmask.as<uint8_t>(), dm, mstep, rows, cols, is_master,
+                                       d_w.as<float>(), s)) return e;
   // cv::GaussianBlur(weights, Size(), 1, 1, BORDER_REPLICATE): 9 taps
   SepFilterArgs f = {};
   f.src = d_w.as<float>(); f.dst = d_wblur.as<float>(); f.rows = rows; f.cols = cols; f.batch = 1;
@@ -1186,15 +1196,17 @@ int ssk_jdr_derotate_and_add(ssk_acc *acc, const ssk_mat *frame, const ssk_mat *
     f.kxn = f.kyn = 9;
   }
   if (int e = launch_sepfilter(f, s)) return e;
-  // derotate the frame in place (INTER_LINEAR, BORDER_TRANSPARENT)
-  SSK_CUDA(cudaMemcpyAsync(d_out.p, d_frame.p, n * 4, cudaMemcpyDeviceToDevice, s));
-  ra.src.data = d_frame.p; ra.dst = d_out.as<float>(); ra.border = SSK_BORDER_TRANSPARENT;
-  if (int e = launch_remap(ra, tab, s)) return e;
-  SSK_CUDA(cudaStreamSynchronize(s));    // the accumulator works on its own stream
-  ssk_mat fm, wm;
-  fm.data = d_out.p; fm.step = (int64_t)cols * 4; fm.rows = rows; fm.cols = cols; fm.type = SSK_32FC1; fm.mem = SSK_MEM_DEVICE;
-  wm = fm; wm.data = d_wblur.p;
-  return ssk_acc_add(acc, &fm, &wm, 0);
+  // derotation of the frame (INTER_LINEAR, BORDER_TRANSPARENT in place) fused with c_weigthed_average::add(frame, weights)
+  Acc &A = acc->a;
+  SSK_REQUIRE(A.kind == SSK_ACC_WEIGHTED_AVERAGE, "jdr: a c_weigthed_average accumulator is expected");
+  if (A.rows) SSK_REQUIRE(A.rows == rows && A.cols == cols && A.cn == 1, "c_weigthed_average::add: frame size / channels differ from the accumulator");
+  SSK_CUDA(cudaStreamSynchronize(A.stream));      // work the accumulator still has in flight on its own stream
+  if (int e = A.ensure(rows, cols, 1)) return e;
+  SSK_CUDA(cudaStreamSynchronize(A.stream));      // first use: the zero-fill
+  if (int e = launch_jdr_remap_add(d_f, d_rmap.as<float2>(), d_wblur.as<float>(), rows, cols, A.acc.as<float>(), A.wacc.as<float>(), s)) return e;
+  ++A.frames;
+  SSK_CUDA(cudaStreamSynchronize(s));
+  return SSK_OK;
 }
 
 }  // extern "C"

@@ -655,6 +655,59 @@ __global__ void __launch_bounds__(256) k_lpg5x5(const float *__restrict__ src, i
   dst[(int64_t)oy * cols + ox] = add(add(mul(alpha, lapl), mul(beta, grad)), eps);
 }
 
+// The same operator with its neighbours fused for the un-scaled case (dscale = 0): the channel average of a colour frame
+// (reduce_color_channels, lpg.cc:246-248) is formed on load, the 36 x 20 source tile of a 32 x 16 output tile is staged once in
+// shared memory (the plain kernel reads 25 + 12 global values per pixel) and the integer power (lpg.cc:270) is applied in
+// registers: one read of the frame, one write of the map.  Every arithmetic step is the one of k_channel_avg / k_lpg5x5 /
+// k_scale_ipow, in the same order.
+constexpr int LF_W = 32, LF_H = 16;
+template <int DEPTH>
+__global__ void __launch_bounds__(256) k_lpg_fused(const Img im, float *__restrict__ dst, float alpha, float beta, float eps, int ipow) {
+  __shared__ float s_t[LF_H + 4][LF_W + 4 + 1];
+  const int bx = blockIdx.x * LF_W, by = blockIdx.y * LF_H;
+  const float inv_cn = (float)(1.0 / im.cn);
+  for (int i = threadIdx.x; i < (LF_H + 4) * (LF_W + 4); i += 256) {
+    const int r = i / (LF_W + 4), c = i - r * (LF_W + 4);
+    const int gy = min(max(by - 2 + r, 0), im.rows - 1), gx = min(max(bx - 2 + c, 0), im.cols - 1);
+    float v = load_px<DEPTH>(im, gy, gx, 0);
+    if (im.cn > 1) {
+      for (int k = 1; k < im.cn; ++k) v = __fadd_rn(v, load_px<DEPTH>(im, gy, gx, k));
+      v = __fmul_rn(v, inv_cn);
+    }
+    s_t[r][c] = v;
+  }
+  __syncthreads();
+  auto add = [](float a, float b) { return __fadd_rn(a, b); };
+  auto sub = [](float a, float b) { return __fsub_rn(a, b); };
+  auto mul = [](float a, float b) { return __fmul_rn(a, b); };
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int ox = bx + (threadIdx.x & 31), oy = by + (threadIdx.x >> 5) + 8 * k;
+    if (ox >= im.cols || oy >= im.rows) continue;
+    const int x = min(max(ox, 2), im.cols - 3) - (bx - 2), y = min(max(oy, 2), im.rows - 3) - (by - 2);   // tile coordinates of the stencil centre
+    auto r = [&](int dy, int dx) { return s_t[y + dy][x + dx]; };
+    auto col5 = [&](int dx) { return add(add(add(add(r(-2, dx), mul(2.f, r(-1, dx))), mul(4.f, r(0, dx))), mul(2.f, r(1, dx))), r(2, dx)); };
+    auto col3 = [&](int dx) { return add(add(r(-1, dx), mul(2.f, r(0, dx))), r(1, dx)); };
+    auto row5 = [&](int dy) { return add(add(add(add(r(dy, -2), mul(2.f, r(dy, -1))), mul(4.f, r(dy, 0))), mul(2.f, r(dy, 1))), r(dy, 2)); };
+    auto row3 = [&](int dy) { return add(add(r(dy, -1), mul(2.f, r(dy, 0))), r(dy, 1)); };
+    const float gx = add(sub(col5(2), col5(-2)), mul(2.f, sub(col3(1), col3(-1))));
+    const float gy = add(sub(row5(2), row5(-2)), mul(2.f, sub(row3(1), row3(-1))));
+    const float grad = add(mul(gx, gx), mul(gy, gy));
+    const float s4 = add(add(add(r(-1, 0), r(1, 0)), r(0, -1)), r(0, 1));
+    const float d4 = add(add(add(r(-1, -1), r(-1, 1)), r(1, -1)), r(1, 1));
+    const float f4 = add(add(add(r(-2, 0), r(2, 0)), r(0, -2)), r(0, 2));
+    const float lap = sub(sub(sub(mul(16.f, r(0, 0)), mul(2.f, s4)), d4), f4);
+    float v = add(add(mul(alpha, mul(lap, lap)), mul(beta, grad)), eps);
+    if (ipow > 1) {
+      float a = 1.f, b = v;
+      int p = ipow;
+      while (p > 1) { if (p & 1) a = __fmul_rn(a, b); b = __fmul_rn(b, b); p >>= 1; }
+      v = __fmul_rn(a, b);
+    }
+    dst[(int64_t)oy * im.cols + ox] = v;
+  }
+}
+
 // v = cv::pow(v * scale, ipow) for integer ipow >= 1 (cv::multiply by a scalar, then iPow32f's square-and-multiply)
 __global__ void __launch_bounds__(256) k_scale_ipow(float *buf, int64_t n, float scale, int apply_scale, int ipow) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -760,6 +813,7 @@ int launch_sepfilter(const SepFilterArgs &a, cudaStream_t s) {
   dim3 grid(div_up(a.cols, SF_W), div_up(a.rows, SF_H), a.batch * cn);
   if (cn > 1 || (a.border && a.border != SSK_BORDER_REPLICATE)) k_sepfilter<0, 0><<<grid, 256, 0, s>>>(a);
   else if (a.kxn == 7 && a.kyn == 7) k_sepfilter<7, 7><<<grid, 256, 0, s>>>(a);     // Gaussian, sigma = 1
+  else if (a.kxn == 9 && a.kyn == 9) k_sepfilter<9, 9><<<grid, 256, 0, s>>>(a);     // cv::GaussianBlur(sigma = 1) of CV_32F weights
   else if (a.kxn == 5 && a.kyn == 3) k_sepfilter<5, 3><<<grid, 256, 0, s>>>(a);     // ecc_differentiate, d/dx
   else if (a.kxn == 3 && a.kyn == 5) k_sepfilter<3, 5><<<grid, 256, 0, s>>>(a);     // ecc_differentiate, d/dy
   else k_sepfilter<0, 0><<<grid, 256, 0, s>>>(a);
@@ -852,6 +906,17 @@ int launch_lpg5x5(const float *src, int rows, int cols, float *dst, float alpha,
   SSK_REQUIRE(rows >= 5 && cols >= 5, "lpg: image smaller than 5x5 at the working scale");
   dim3 grid(div_up(cols, 32), div_up(rows, 8));
   k_lpg5x5<<<grid, 256, 0, s>>>(src, rows, cols, dst, alpha, beta, eps);
+  SSK_LAUNCH_CHECK();
+  return SSK_OK;
+}
+
+int launch_lpg_fused(const Img &im, float *dst, float alpha, float beta, float eps, int ipow, cudaStream_t s) {
+  SSK_REQUIRE(im.rows >= 5 && im.cols >= 5, "lpg: image smaller than 5x5 at the working scale");
+  dim3 grid(div_up(im.cols, LF_W), div_up(im.rows, LF_H));
+  if (im.depth == SSK_32F) k_lpg_fused<SSK_32F><<<grid, 256, 0, s>>>(im, dst, alpha, beta, eps, ipow);
+  else if (im.depth == SSK_16U) k_lpg_fused<SSK_16U><<<grid, 256, 0, s>>>(im, dst, alpha, beta, eps, ipow);
+  else if (im.depth == SSK_8U) k_lpg_fused<SSK_8U><<<grid, 256, 0, s>>>(im, dst, alpha, beta, eps, ipow);
+  else { set_error("lpg: unsupported depth"); return SSK_ERR_INVALID; }
   SSK_LAUNCH_CHECK();
   return SSK_OK;
 }

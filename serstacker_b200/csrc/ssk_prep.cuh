@@ -86,6 +86,8 @@ int launch_w1(const W1Args &a, cudaStream_t s);
 
 // W2 (lpg.cc): 5x5 Laplacian/gradient energy; in-place scale + integer power
 int launch_lpg5x5(const float *src, int rows, int cols, float *dst, float alpha, float beta, float eps, cudaStream_t s);
+// channel average + 5x5 operator + integer power in one pass (the dscale = 0 form of lpg: no scaling before the operator)
+int launch_lpg_fused(const Img &im, float *dst, float alpha, float beta, float eps, int ipow, cudaStream_t s);
 int launch_scale_ipow(float *buf, int64_t n, float scale, bool apply_scale, int ipow, cudaStream_t s);
 
 // reference-mask helpers: 8U pyrDown + threshold, INTER_NEAREST resize, gradient masking + non-zero count

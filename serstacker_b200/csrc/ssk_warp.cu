@@ -215,6 +215,75 @@ __global__ void __launch_bounds__(256) k_jdr_weights(float *w, const float *lpg_
 }
 }  // namespace
 
+namespace {
+// cv::remap(src, dst, rmap, INTER_LINEAR, BORDER_TRANSPARENT) of a dense CV_32FC1 image applied in place, one sample: the
+// destination keeps its own value where the anchor tap of the map lies outside the source (k_remap's rule)
+__device__ __forceinline__ float remap_transparent_inplace(const Img &im, float2 m, int x, int y) {
+  int ix, iy, f;
+  quant32(m.x, ix, f);
+  quant32(m.y, iy, f);
+  if ((unsigned)ix >= (unsigned)im.cols || (unsigned)iy >= (unsigned)im.rows) return load_px<SSK_32F>(im, y, x, 0);
+  return sample_linear<SSK_32F>(im, 0, m.x, m.y, SSK_BORDER_TRANSPARENT, 0.f);
+}
+
+// c_jdr_pipeline.cc:1207-1227 in one pass: w = remap(wmap, rmap, LINEAR, CONSTANT 0); w < 1e-5 -> 0; w *= remap(lpg, rmap,
+// LINEAR, TRANSPARENT in place); master frame: 1 outside the disk; 0 under the frame mask.  Same per-sample arithmetic as the
+// k_remap / k_jdr_weights chain it replaces.
+__global__ void __launch_bounds__(256) k_jdr_weights_fused(const float *wpre, const float *lpg_map, const float2 *rmap, const uint8_t *rmask,
+                                                           const uint8_t *mask, int64_t mask_step, int rows, int cols, int is_master, float *w) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= cols || y >= rows) return;
+  const int64_t o = (int64_t)y * cols + x;
+  const float2 m = rmap[o];
+  Img im;
+  im.data = wpre; im.step = (int64_t)cols * 4; im.rows = rows; im.cols = cols; im.depth = SSK_32F; im.cn = 1; im.scale = 1.f;
+  float v = sample_linear<SSK_32F>(im, 0, m.x, m.y, SSK_BORDER_CONSTANT, 0.f);
+  if (v < 1e-5f) v = 0.f;
+  if (lpg_map) {
+    im.data = lpg_map;
+    v = __fmul_rn(v, remap_transparent_inplace(im, m, x, y));
+  }
+  if (is_master && !rmask[o]) v = 1.f;
+  if (mask && !mask[(int64_t)y * mask_step + x]) v = 0.f;
+  w[o] = v;
+}
+
+// derotation of the frame (cv::remap LINEAR / TRANSPARENT in place, c_jdr_pipeline.cc:1231-1234) fused with
+// c_weigthed_average::add(frame, weights) (c_frame_accumulation.cc:20-129, CV_32FC1 weights)
+__global__ void __launch_bounds__(256) k_jdr_remap_add(const float *frame, const float2 *rmap, const float *weights, int rows, int cols,
+                                                       float *acc, float *wacc) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= cols || y >= rows) return;
+  const int64_t o = (int64_t)y * cols + x;
+  const float wnew = weights[o];
+  if (!(wnew > 0.f)) return;
+  Img im;
+  im.data = frame; im.step = (int64_t)cols * 4; im.rows = rows; im.cols = cols; im.depth = SSK_32F; im.cn = 1; im.scale = 1.f;
+  const float I = remap_transparent_inplace(im, rmap[o], x, y);
+  const float Wn = wacc[o] + wnew;
+  const float factor = __fdiv_rn(wnew, Wn);
+  wacc[o] = Wn;
+  const float A = acc[o];
+  acc[o] = fmaf(I - A, factor, A);
+}
+}  // namespace
+
+int launch_jdr_weights_fused(const float *wpre, const float *lpg_map, const float2 *rmap, const uint8_t *rmask, const uint8_t *mask,
+                             int64_t mask_step, int rows, int cols, int is_master, float *w, cudaStream_t s) {
+  dim3 grid(div_up(cols, 32), div_up(rows, 8));
+  k_jdr_weights_fused<<<grid, 256, 0, s>>>(wpre, lpg_map, rmap, rmask, mask, mask_step, rows, cols, is_master, w);
+  SSK_LAUNCH_CHECK();
+  return SSK_OK;
+}
+
+int launch_jdr_remap_add(const float *frame, const float2 *rmap, const float *weights, int rows, int cols, float *acc, float *wacc,
+                         cudaStream_t s) {
+  dim3 grid(div_up(cols, 32), div_up(rows, 8));
+  k_jdr_remap_add<<<grid, 256, 0, s>>>(frame, rmap, weights, rows, cols, acc, wacc);
+  SSK_LAUNCH_CHECK();
+  return SSK_OK;
+}
+
 int launch_jdr_weights(float *w, const float *lpg_map, const uint8_t *rmask, const uint8_t *mask, int64_t mask_step, int rows,
                        int cols, int is_master, cudaStream_t s) {
   dim3 grid(div_up(cols, 32), div_up(rows, 8));

@@ -97,6 +97,13 @@ int launch_ellipsoid_remap(const EllipsoidArgs &a, cudaStream_t s);
 int launch_jdr_weights(float *w, const float *lpg_map, const uint8_t *rmask, const uint8_t *mask, int64_t mask_step,
                        int rows, int cols, int is_master, cudaStream_t s);
 
+// the same weight with its two remaps fused (w = remap(wpre, rmap, LINEAR, CONSTANT) [* remap(lpg, rmap, LINEAR, TRANSPARENT)]),
+// and the frame's TRANSPARENT derotation fused with the weighted add (dense CV_32FC1 images of rows x cols)
+int launch_jdr_weights_fused(const float *wpre, const float *lpg_map, const float2 *rmap, const uint8_t *rmask, const uint8_t *mask,
+                             int64_t mask_step, int rows, int cols, int is_master, float *w, cudaStream_t s);
+int launch_jdr_remap_add(const float *frame, const float2 *rmap, const float *weights, int rows, int cols, float *acc, float *wacc,
+                         cudaStream_t s);
+
 // c_weigthed_average::add without warp (c_frame_accumulation.cc:20-129)
 struct AccAddArgs {
   Img src;
