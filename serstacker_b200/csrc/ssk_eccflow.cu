@@ -36,9 +36,61 @@ constexpr float kS3[3] = {0.25f, 0.5f, 0.25f};
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
+// cv::resize(INTER_CUBIC) of a 2-channel float image at one destination pixel: horizontal pass of the four source rows, then
+// the vertical combination (HResizeCubic / VResizeCubic), taps clamped into the image
+template <class LD>
+__device__ __forceinline__ float2 cubic_at(LD ld, int sw, int sh, int sx, const float4 cx, int sy, const float4 cy) {
+  const int x0 = clampi(sx - 1, 0, sw - 1), x1 = clampi(sx, 0, sw - 1), x2 = clampi(sx + 1, 0, sw - 1), x3 = clampi(sx + 2, 0, sw - 1);
+  float2 r[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int yy = clampi(sy - 1 + k, 0, sh - 1);
+    const float2 a0 = ld(x0, yy), a1 = ld(x1, yy), a2 = ld(x2, yy), a3 = ld(x3, yy);
+    r[k].x = a0.x * cx.x + a1.x * cx.y + a2.x * cx.z + a3.x * cx.w;
+    r[k].y = a0.y * cx.x + a1.y * cx.y + a2.y * cx.z + a3.y * cx.w;
+  }
+  float2 o;
+  o.x = r[0].x * cy.x + r[1].x * cy.y + r[2].x * cy.z + r[3].x * cy.w;
+  o.y = r[0].y * cy.x + r[1].y * cy.y + r[2].y * cy.z + r[3].y * cy.w;
+  return o;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // k_flow_reduce
 // ---------------------------------------------------------------------------------------------------------------------
+// cv::remap's bilinear sample (sample_linear of ssk_common.cuh with BORDER_REPLICATE) split in two steps, so that a thread can
+// have the taps of several pixels in flight: offsets + weights first, the arithmetic after the loads
+struct LinTaps { int o00, o01, o10, o11; float w00, w01, w10, w11; };
+// read-only loads the compiler keeps in program order relative to each other (asm volatile): the batched loop below wants all
+// loads of a step issued before the first use, ptxas otherwise re-serialises them to save registers
+__device__ __forceinline__ float ldg_ord(const float *p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float2 ldg_ord2(const float2 *p) {
+  float2 v;
+  asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ LinTaps lin_taps(float u, float v, int w, int h) {
+  int ix, fx, iy, fy;
+  quant32(u, ix, fx);
+  quant32(v, iy, fy);
+  const float tx = (float)fx * 0.03125f, ty = (float)fy * 0.03125f;
+  const float wx0 = 1.0f - tx, wy0 = 1.0f - ty;
+  const int x0 = clampi(ix, 0, w - 1), x1 = clampi(ix + 1, 0, w - 1), y0 = clampi(iy, 0, h - 1), y1 = clampi(iy + 1, 0, h - 1);
+  LinTaps t;
+  t.o00 = y0 * w + x0; t.o01 = y0 * w + x1; t.o10 = y1 * w + x0; t.o11 = y1 * w + x1;
+  t.w00 = __fmul_rn(wy0, wx0); t.w01 = __fmul_rn(wy0, tx); t.w10 = __fmul_rn(ty, wx0); t.w11 = __fmul_rn(ty, tx);
+  return t;
+}
+__device__ __forceinline__ float lin_combine(const LinTaps &t, float s00, float s01, float s10, float s11) {
+  float out = __fadd_rn(__fmul_rn(s00, t.w00), __fmul_rn(s01, t.w01));
+  out = __fadd_rn(out, __fmul_rn(s10, t.w10));
+  return __fadd_rn(out, __fmul_rn(s11, t.w11));
+}
+
 struct FlowReduceArgs {
   int w, h, cw, ch;
   const float *ref, *ix, *iy;            // level images (dense)
@@ -46,13 +98,20 @@ struct FlowReduceArgs {
   const float *cur; int64_t cur_stride;  // frame b: cur + b * cur_stride (floats)
   const uint8_t *curmask;                // level mask of frame 0 (batch == 1) or null
   const float2 *uv; int64_t uv_stride;   // frame b: uv + b * uv_stride (float2)
+  // the update of the previous iteration of this level applied on the way instead of by a k_flow_update pass of its own:
+  // f = uv + resize(cuv_prev, INTER_CUBIC) is used and written to uv_out (another buffer: a source row shared by two coarse
+  // rows is read by both CTAs and written by the first one only).  null: uv is used as it is
+  const float2 *cuv_prev; int64_t cuv_stride;
+  float2 *uv_out;
+  FlowCubicAxis ux, uy;
   float *out; int64_t out_stride;        // frame b: raw coarse sums [ch][cw][NOUT]
   FlowAreaAxis ax, ay;
   const EccFrame *frames;                // ok flags of the batch or null
 };
 
 // MODE 0: (It Ix, It Iy) of the flow iteration; MODE 1: (Ix Ix, Ix Iy, Iy Iy) of the reference side (avgp)
-template <int MODE>
+// FUSE (MODE 0 only): apply the previous iteration's update on the way (a.cuv_prev, a.uv_out)
+template <int MODE, int FUSE>
 __global__ void __launch_bounds__(256) k_flow_reduce(const FlowReduceArgs a) {
   constexpr int NOUT = MODE == 0 ? 2 : 3;
   extern __shared__ float s_col[];       // [NOUT][w]
@@ -63,16 +122,60 @@ __global__ void __launch_bounds__(256) k_flow_reduce(const FlowReduceArgs a) {
   Img im;
   im.data = a.cur + (int64_t)b * a.cur_stride; im.step = (int64_t)a.w * 4; im.rows = a.h; im.cols = a.w;
   im.depth = SSK_32F; im.cn = 1; im.scale = 1.f;
-  const float2 *uv = a.uv + (int64_t)b * a.uv_stride;
+  const float2 *__restrict__ uv = a.uv + (int64_t)b * a.uv_stride;
+  const float2 *__restrict__ cprev = FUSE ? a.cuv_prev + (int64_t)b * a.cuv_stride : nullptr;
+  float2 *__restrict__ uv_out = FUSE ? a.uv_out + (int64_t)b * a.uv_stride : nullptr;
+  const int own_from = (FUSE && cy > 0) ? a.ay.start[cy - 1] + a.ay.count[cy - 1] : 0;   // rows below belong to the coarse row above
   for (int x = threadIdx.x; x < a.w; x += 256) {
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
-    for (int k = 0; k < ny; ++k) {
+    int uxs = 0; float4 uxc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (FUSE) { uxs = __ldg(a.ux.s + x); uxc = __ldg(a.ux.c + x); }
+    int kbeg = 0;
+    if (MODE == 0 && !FUSE && !a.refmask && !a.curmask) {
+      // four rows per step: all coalesced loads, then all 16 gathers, then the arithmetic (the loop below is latency-bound
+      // with one pixel in flight per thread)
+      const float *__restrict__ cur = static_cast<const float *>(im.data);
+      for (; kbeg + 4 <= ny; kbeg += 4) {
+        float2 f[4]; float gxs[4], gys[4], rf[4], bk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int64_t p = (int64_t)(y0 + kbeg + j) * a.w + x;
+          f[j] = ldg_ord2(uv + p);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int64_t p = (int64_t)(y0 + kbeg + j) * a.w + x;
+          gxs[j] = ldg_ord(a.ix + p); gys[j] = ldg_ord(a.iy + p); rf[j] = ldg_ord(a.ref + p); bk[j] = __ldg(beta + kbeg + j);
+        }
+        LinTaps t[4]; float s[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] = lin_taps(__fadd_rn(f[j].x, (float)x), __fadd_rn(f[j].y, (float)(y0 + kbeg + j)), a.w, a.h);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          s[j][0] = ldg_ord(cur + t[j].o00); s[j][1] = ldg_ord(cur + t[j].o01); s[j][2] = ldg_ord(cur + t[j].o10); s[j][3] = ldg_ord(cur + t[j].o11);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float It = __fsub_rn(rf[j], lin_combine(t[j], s[j][0], s[j][1], s[j][2], s[j][3]));
+          acc0 = fmaf(bk[j], __fmul_rn(It, gxs[j]), acc0);
+          acc1 = fmaf(bk[j], __fmul_rn(It, gys[j]), acc1);
+        }
+      }
+    }
+#pragma unroll 1
+    for (int k = kbeg; k < ny; ++k) {
       const int y = y0 + k;
       const int64_t p = (int64_t)y * a.w + x;
       const float gx = __ldg(a.ix + p), gy = __ldg(a.iy + p);
       const float bk = __ldg(beta + k);
       if (MODE == 0) {
-        const float2 f = __ldg(uv + p);
+        float2 f = __ldg(uv + p);
+        if (FUSE) {
+          const float2 d = cubic_at([&](int sx, int sy) { return __ldg(cprev + (int64_t)sy * a.cw + sx); }, a.cw, a.ch, uxs, uxc, __ldg(a.uy.s + y),
+                                    __ldg(a.uy.c + y));
+          f = make_float2(__fadd_rn(f.x, d.x), __fadd_rn(f.y, d.y));
+          if (y >= own_from) uv_out[p] = f;
+        }
         const float u = __fadd_rn(f.x, (float)x), v = __fadd_rn(f.y, (float)y);      // ecc_flow_to_remap
         bool ok = true;
         if (a.refmask) ok = __ldg(a.refmask + p) != 0;
@@ -154,25 +257,6 @@ __global__ void __launch_bounds__(256) k_flow_solve(const float *raw, int64_t ra
   const float u = __fmul_rn(d.w, __fsub_rn(__fmul_rn(d.z, t[0]), __fmul_rn(d.y, t[1])));
   const float v = __fmul_rn(d.w, __fsub_rn(__fmul_rn(d.x, t[1]), __fmul_rn(d.y, t[0])));
   cuv[(int64_t)b * cuv_stride + i] = make_float2(u, v);
-}
-
-// cv::resize(INTER_CUBIC) of a 2-channel float image at one destination pixel: horizontal pass of the four source rows, then
-// the vertical combination (HResizeCubic / VResizeCubic), taps clamped into the image
-template <class LD>
-__device__ __forceinline__ float2 cubic_at(LD ld, int sw, int sh, int sx, const float4 cx, int sy, const float4 cy) {
-  const int x0 = clampi(sx - 1, 0, sw - 1), x1 = clampi(sx, 0, sw - 1), x2 = clampi(sx + 1, 0, sw - 1), x3 = clampi(sx + 2, 0, sw - 1);
-  float2 r[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int yy = clampi(sy - 1 + k, 0, sh - 1);
-    const float2 a0 = ld(x0, yy), a1 = ld(x1, yy), a2 = ld(x2, yy), a3 = ld(x3, yy);
-    r[k].x = a0.x * cx.x + a1.x * cx.y + a2.x * cx.z + a3.x * cx.w;
-    r[k].y = a0.y * cx.x + a1.y * cx.y + a2.y * cx.z + a3.y * cx.w;
-  }
-  float2 o;
-  o.x = r[0].x * cy.x + r[1].x * cy.y + r[2].x * cy.z + r[3].x * cy.w;
-  o.y = r[0].y * cy.x + r[1].y * cy.y + r[2].y * cy.z + r[3].y * cy.w;
-  return o;
 }
 
 // uv += resize(cuv, level size, INTER_CUBIC)   (ecc2.cc:2392-2395, 2827-2831)
@@ -402,8 +486,9 @@ int EccFlow::set_reference(const float *d_img, int rows, int cols, const uint8_t
   }
   SSK_REQUIRE((size_t)lw[0] * 3 * 4 <= 96 * 1024, "eccflow: image wider than 8192 pixels");
   if ((size_t)lw[0] * 3 * 4 > 48 * 1024 && !reduce_smem_optin) {
-    SSK_CUDA(cudaFuncSetAttribute(k_flow_reduce<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    SSK_CUDA(cudaFuncSetAttribute(k_flow_reduce<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    SSK_CUDA(cudaFuncSetAttribute(k_flow_reduce<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    SSK_CUDA(cudaFuncSetAttribute(k_flow_reduce<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    SSK_CUDA(cudaFuncSetAttribute(k_flow_reduce<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     reduce_smem_optin = 1;
   }
   if (int e = build_tables()) return e;
@@ -441,7 +526,7 @@ int EccFlow::set_reference(const float *d_img, int rows, int cols, const uint8_t
     a.w = lw[l]; a.h = lh[l]; a.cw = cw[l]; a.ch = ch[l];
     a.ix = ref_ix.as<float>() + loff[l]; a.iy = ref_iy.as<float>() + loff[l];
     a.out = raw.as<float>(); a.out_stride = 0; a.ax = lt[l].ax; a.ay = lt[l].ay;
-    k_flow_reduce<1><<<dim3(ch[l], 1), 256, (size_t)lw[l] * 3 * 4, stream>>>(a);
+    k_flow_reduce<1, 0><<<dim3(ch[l], 1), 256, (size_t)lw[l] * 3 * 4, stream>>>(a);
     SSK_LAUNCH_CHECK();
     // "this regularization term estimation looks crazy" (ecc2.cc:2613): float(pow(1e-5 * noise / 2^level, 4))
     const float reg = noise_level > 0 ? (float)std::pow(1e-5 * noise_level / (double)(1ll << std::min(l, 62)), 4) : 0.f;
@@ -519,6 +604,8 @@ int EccFlow::compute(int batch, const EccFrame *d_frames, const float2 *d_rmap0)
       SSK_LAUNCH_CHECK();
       std::swap(cur_uv, other);
     }
+    // iterations after the first apply the previous update inside k_flow_reduce (read uv, write the other buffer)
+    static const bool fuse_update = !getenv("SSK_FLOW_NO_FUSED_UPDATE");
     for (int j = 0; j < opts.max_iterations; ++j) {
       FlowReduceArgs a = {};
       a.w = lw[l]; a.h = lh[l]; a.cw = cw[l]; a.ch = ch[l];
@@ -529,15 +616,22 @@ int EccFlow::compute(int batch, const EccFrame *d_frames, const float2 *d_rmap0)
       a.uv = cur_uv; a.uv_stride = n0;
       a.out = raw.as<float>(); a.out_stride = (int64_t)cw[l] * ch[l] * 2;
       a.ax = lt[l].ax; a.ay = lt[l].ay; a.frames = okf;
-      k_flow_reduce<0><<<dim3(ch[l], batch), 256, (size_t)lw[l] * 2 * 4, stream>>>(a);
+      if (fuse_update && j > 0) {
+        a.cuv_prev = cuv.as<float2>(); a.cuv_stride = (int64_t)cw[l] * ch[l]; a.ux = lt[l].ux; a.uy = lt[l].uy; a.uv_out = other;
+      }
+      if (a.cuv_prev) k_flow_reduce<0, 1><<<dim3(ch[l], batch), 256, (size_t)lw[l] * 2 * 4, stream>>>(a);
+      else k_flow_reduce<0, 0><<<dim3(ch[l], batch), 256, (size_t)lw[l] * 2 * 4, stream>>>(a);
       SSK_LAUNCH_CHECK();
+      if (a.cuv_prev) std::swap(cur_uv, other);
       k_flow_solve<<<dim3(div_up(cw[l] * ch[l], 256), batch), 256, 0, stream>>>(raw.as<float>(), a.out_stride, ref_D.as<float4>() + coff[l], cw[l],
                                                                               ch[l], cuv.as<float2>(), (int64_t)cw[l] * ch[l], okf);
       SSK_LAUNCH_CHECK();
-      dim3 grid(div_up(lw[l], 32), div_up(lh[l], 8), batch);
-      k_flow_update<<<grid, 256, 0, stream>>>(cur_uv, n0, lw[l], lh[l], cuv.as<float2>(), (int64_t)cw[l] * ch[l], cw[l], ch[l], lt[l].ux, lt[l].uy,
-                                              okf);
-      SSK_LAUNCH_CHECK();
+      if (!fuse_update || j == opts.max_iterations - 1) {
+        dim3 grid(div_up(lw[l], 32), div_up(lh[l], 8), batch);
+        k_flow_update<<<grid, 256, 0, stream>>>(cur_uv, n0, lw[l], lh[l], cuv.as<float2>(), (int64_t)cw[l] * ch[l], cw[l], ch[l], lt[l].ux, lt[l].uy,
+                                                okf);
+        SSK_LAUNCH_CHECK();
+      }
     }
   }
   if (cur_uv != uv_a.as<float2>())

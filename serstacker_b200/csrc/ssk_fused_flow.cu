@@ -43,6 +43,9 @@ __device__ __forceinline__ float2 map_at(const WarpAccArgs &a, const UpscaleGeom
                      upscale_sample(up, [&](int x, int y) { return src_uv(x, y).y; }, gx, gy));
 }
 
+// FAST: 0 = any depth / channel count / interpolation through sample_any (real calls); 1 / 2 = CV_32FC1 frames with INTER_LINEAR /
+// INTER_CUBIC: the samplers of ssk_common.cuh inlined (same arithmetic, the interior 4 x 4 footprint without border logic)
+template <int FAST>
 __global__ void __launch_bounds__(256) k_fused_flow(const __grid_constant__ WarpAccArgs a, const __grid_constant__ Tables tab, int ntx,
                                                     const __grid_constant__ UpscaleGeom up) {
   __shared__ unsigned char s_flag[2][HH][HW + 4];
@@ -101,16 +104,24 @@ __global__ void __launch_bounds__(256) k_fused_flow(const __grid_constant__ Warp
       float wk = 1.f;
       if (weighted) {
         im.data = job.weights; im.step = a.w_step; im.depth = SSK_32F; im.cn = 1; im.scale = 1.f;
-        wk = sample_any(im, 0, uv.x, uv.y, a.interp, SSK_BORDER_CONSTANT, 0.f, tab.cubic, tab.lanczos);
+        if (FAST == 2) wk = sample_cubic<SSK_32F>(im, 0, uv.x, uv.y, SSK_BORDER_CONSTANT, 0.f, tab.cubic);
+        else if (FAST == 1) wk = sample_linear<SSK_32F>(im, 0, uv.x, uv.y, SSK_BORDER_CONSTANT, 0.f);
+        else wk = sample_any(im, 0, uv.x, uv.y, a.interp, SSK_BORDER_CONSTANT, 0.f, tab.cubic, tab.lanczos);
         if (!(wk > 0.f)) continue;                               // c_frame_accumulation.cc:114
       }
       im.data = job.frame; im.step = a.src_step; im.depth = a.depth; im.cn = a.cn; im.scale = a.scale;
       const float Wn = W[k] + wk;
       const float factor = weighted ? __fdiv_rn(wk, Wn) : __fdiv_rn(1.0f, Wn);
       W[k] = Wn;
-      for (int c = 0; c < a.cn; ++c) {
-        const float I = sample_any(im, c, uv.x, uv.y, a.interp, a.border, a.bval[c], tab.cubic, tab.lanczos);
-        A[k][c] = fmaf(I - A[k][c], factor, A[k][c]);
+      if (FAST) {
+        const float I = FAST == 2 ? sample_cubic<SSK_32F>(im, 0, uv.x, uv.y, a.border, a.bval[0], tab.cubic)
+                                  : sample_linear<SSK_32F>(im, 0, uv.x, uv.y, a.border, a.bval[0]);
+        A[k][0] = fmaf(I - A[k][0], factor, A[k][0]);
+      } else {
+        for (int c = 0; c < a.cn; ++c) {
+          const float I = sample_any(im, c, uv.x, uv.y, a.interp, a.border, a.bval[c], tab.cubic, tab.lanczos);
+          A[k][c] = fmaf(I - A[k][c], factor, A[k][c]);
+        }
       }
     }
     buf ^= 1;
@@ -135,7 +146,10 @@ int launch_warp_accumulate_flow(const WarpAccArgs &a, const Tables &tab, int ups
   const UpscaleGeom up = make_upscale_geom(upscale_option, a.src_cols, a.src_rows);
   SSK_REQUIRE(a.rows == up.dh && a.cols == up.dw, "internal: accumulator size differs from the (up-scaled) map size");
   const int ntx = div_up(a.cols, TW), nty = div_up(a.rows, TH);
-  k_fused_flow<<<ntx * nty, 256, 0, s>>>(a, tab, ntx, up);
+  const bool f32c1 = a.depth == SSK_32F && a.cn == 1;
+  if (f32c1 && a.interp == SSK_INTER_CUBIC) k_fused_flow<2><<<ntx * nty, 256, 0, s>>>(a, tab, ntx, up);
+  else if (f32c1 && a.interp == SSK_INTER_LINEAR) k_fused_flow<1><<<ntx * nty, 256, 0, s>>>(a, tab, ntx, up);
+  else k_fused_flow<0><<<ntx * nty, 256, 0, s>>>(a, tab, ntx, up);
   SSK_LAUNCH_CHECK();
   return SSK_OK;
 }
