@@ -380,6 +380,14 @@ SSK_API int ssk_color_transform(const ssk_mat *src, const float *m, int mcols, s
  * generated master frame (c_image_stacking_pipeline.cc:1282-1284) and to input frames with a missing-pixel mask
  * (c_image_stacking_pipeline_base.cc:258-261).  CV_32F, 1 to 4 channels; mask CV_8UC1 or NULL (plain copy). */
 SSK_API int ssk_linear_interpolation_inpaint(const ssk_mat *src, const ssk_mat *mask, ssk_mat *dst);
+/* median_filter_bad_pixels(image, variation_threshold, COLORID_MONO / a colour image) (core/proc/bad_pixels.cc:14-70; read_input_frame's
+ * filter_bad_pixels option, c_image_stacking_pipeline_base.cc:192-212): in place; 8U / 16U / 32F, 1-4 interleaved channels.
+ * A raw Bayer frame goes through ssk_bayer_denoise, as median_filter_bad_pixels does for a Bayer COLORID (bad_pixels.cc:62-64). */
+SSK_API int ssk_median_filter_bad_pixels(ssk_mat *image, double variation_threshold);
+/* bayer_denoise(image, variation_threshold, colorid, returnBayerPlanes = false) (core/io/debayer.cc:1471-1611; the Bayer branch of
+ * filter_bad_pixels, c_image_stacking_pipeline_base.cc:204-209): 3 x 3 median / mean-absolute-deviation test on each of the four
+ * colour planes of the raw mosaic, in place; single channel 8U / 16U / 32F, even size.  The CFA order does not enter the arithmetic. */
+SSK_API int ssk_bayer_denoise(ssk_mat *image, double variation_threshold);
 
 /* ---------------------------------------------------------------------------------------------
  * SER container (c_ser_reader, core/io/c_ser_file.cc:272-531; 178-byte header c_ser_file.h:42-56, frames back to back,
@@ -422,12 +430,21 @@ SSK_API int ssk_acc_compute_inpainted(ssk_acc *h, ssk_mat *avg, ssk_mat *mask, d
  * the caller computes (scalar geometry, ellipsoid.cc:16-84, 299-328).  Outputs: rmap CV_32FC2 (identity outside the
  * disk, (-1,-1) on the hidden side), wmap CV_32FC1 (limb weight wscale*sqrt(1-r^2), remapped by rmap), rmask CV_8UC1.
  * ------------------------------------------------------------------------------------------- */
+/* Scalar geometry of the same classes, on the host: build_ellipsoid_rotation(pose = {longitude_rotation, tilt_to_earth,
+ * position_angle}) = Rz * Rx * Ry (ellipsoid.h:47-71, pose.h:18-58), and ellipsoid_bbox(center, A, B, C, R) +
+ * ellipse_crop_box(ebox, image_size) (ellipsoid.cc:16-84, 279-328): ebox = {center.x, center.y, width, height, angle_deg}
+ * as the float members of the cv::RotatedRect, crop_box = {x, y, width, height}. */
+SSK_API int ssk_build_ellipsoid_rotation(const double pose[3], double R[9]);
+SSK_API int ssk_ellipsoid_bbox(int rows, int cols, const double center[2], const double axes[3], const double R[9],
+                               float ebox[5], int crop_box[4]);
 SSK_API int ssk_ellipsoid_zrotation_remap(int rows, int cols, const double center[2], const double axes[3],
                                           const double R1[9], const double R2[9], double ebox_angle_deg,
                                           const int crop_box[4], double wscale,
                                           ssk_mat *rmap, ssk_mat *wmap, ssk_mat *rmask);
 
-/* One frame of c_jdr_pipeline::derotate_and_average_frames (core/pipeline/c_jdr_pipeline/c_jdr_pipeline.cc:1184-1236),
+/* One frame of c_jdr_pipeline::derotate_and_average_frames (core/pipeline/c_jdr_pipeline/c_jdr_pipeline.cc:1184-1236) and of
+ * c_sdr_pipeline::derotate_and_average_frames (core/pipeline/c_sdr_pipeline/c_sdr_pipeline.cc:1192-1246: the same statements
+ * over c_saturn_derotation_remap, which differs from the Jovian class by its rotation period only),
  * after preproc_align_and_remap: derotation map for R_current -> R_target (ssk_ellipsoid_zrotation_remap arguments),
  * weight = limb weight * wscale, 0 below 1e-5 [, * lpg(frame) remapped with BORDER_TRANSPARENT when
  * enable_weighted_average], 1 outside the disk for the master frame, 0 under the frame mask, GaussianBlur(1, REPLICATE);

@@ -514,6 +514,68 @@ def jdr_derotate_and_add(acc, frame, mask, center, axes, R_current, R_target, eb
     return True
 
 
+def build_ellipsoid_rotation(pose):
+    """build_ellipsoid_rotation(pose = (longitude_rotation, tilt_to_earth, position_angle)) (ellipsoid.h:47-71) -> 3x3 float64."""
+    R = (C.c_double * 9)()
+    check(capi.lib.ssk_build_ellipsoid_rotation((C.c_double * 3)(*[float(v) for v in pose]), R))
+    return np.array(R, np.float64).reshape(3, 3)
+
+
+def ellipsoid_bbox(size, center, axes, R):
+    """ellipsoid_bbox + ellipse_crop_box (ellipsoid.cc:16-84, 279-328); size = (w, h)
+    -> (((cx, cy), (width, height), angle_deg) as float32, [x, y, w, h])."""
+    d = lambda v, n: (C.c_double * n)(*[float(x) for x in np.asarray(v, dtype=np.float64).reshape(-1)])
+    e, cb = (C.c_float * 5)(), (C.c_int * 4)()
+    check(capi.lib.ssk_ellipsoid_bbox(int(size[1]), int(size[0]), d(center, 2), d(axes, 3), d(R, 9), e, cb))
+    e = np.array(e, f32)
+    return ((e[0], e[1]), (e[2], e[3]), e[4]), [int(v) for v in cb]
+
+
+class c_jovian_derotation_remap:
+    """c_jovian_derotation_remap (core/proc/feature2d/c_jovian_derotation_remap.{h,cc}): pose bookkeeping on the host,
+    compute_ellipsoid_zrotation_remap on the device."""
+    default_rotation_period_sec = 9. * 3600 + 55. * 60 + 40.632       # c_jovian_derotation_remap.cc:39
+
+    def __init__(self, rotation_period_sec=None):
+        self.rotation_period_sec = self.default_rotation_period_sec if rotation_period_sec is None else rotation_period_sec
+        self.rmap = self.wmap = self.rmask = None
+
+    def set_reference_pose(self, image_size, center, axes, pose):
+        self.image_size, self.center, self.axes = tuple(image_size), tuple(center), tuple(axes)
+        self.target_pose = self.current_pose = tuple(float(v) for v in pose)
+        self.Rtarget = self.Rcurrent = build_ellipsoid_rotation(self.target_pose)
+        self.ebox, self.crop_box = ellipsoid_bbox(self.image_size, self.center, self.axes, self.Rtarget)
+
+    def compute_derotation_for_angle(self, longitude_rotation_radians, wscale=1.0):
+        self.current_pose = (self.target_pose[0] + longitude_rotation_radians, self.target_pose[1], self.target_pose[2])
+        self.Rcurrent = build_ellipsoid_rotation(self.current_pose)
+        self.wscale = wscale
+        self.rmap, self.wmap, self.rmask = compute_ellipsoid_zrotation_remap(self.image_size, self.center, self.axes, self.Rcurrent,
+                                                                            self.Rtarget, self.ebox[2], self.crop_box, wscale)
+
+    def rotation_angle_for_time(self, deltat_sec):
+        period = self.rotation_period_sec if self.rotation_period_sec > 0 else self.default_rotation_period_sec
+        return 2 * np.pi * deltat_sec / period
+
+    def compute_derotation_for_time(self, deltat_sec, wscale=1.0):
+        self.compute_derotation_for_angle(self.rotation_angle_for_time(deltat_sec), wscale)
+
+    def derotate_and_add(self, acc, frame, mask, deltat_sec, wscale, is_master, enable_weighted_average=True, **lpg):
+        """One frame of derotate_and_average_frames (c_jdr_pipeline.cc:1184-1236 / c_sdr_pipeline.cc:1192-1246): the caller's
+        compute_derotation_for_time(-dt, w) and everything after it, fused on the device."""
+        angle = self.rotation_angle_for_time(deltat_sec)
+        self.current_pose = (self.target_pose[0] + angle, self.target_pose[1], self.target_pose[2])
+        self.Rcurrent = build_ellipsoid_rotation(self.current_pose)
+        return jdr_derotate_and_add(acc, frame, mask, self.center, self.axes, self.Rcurrent, self.Rtarget, self.ebox[2], self.crop_box,
+                                    wscale, is_master, enable_weighted_average, **lpg)
+
+
+class c_saturn_derotation_remap(c_jovian_derotation_remap):
+    """c_saturn_derotation_remap (core/proc/feature2d/c_saturn_derotation_remap.{h,cc}): the Jovian class with Saturn's
+    System III period, as in the reference."""
+    default_rotation_period_sec = 10 * 3600. + 33 * 60. + 38          # c_saturn_derotation_remap.cc:34
+
+
 def linear_interpolation_inpaint(src, mask):
     """linear_interpolation_inpaint (core/proc/inpaint/linear_interpolation_inpaint.cc:327-368) on CV_32F images -> filled copy."""
     src = np.ascontiguousarray(src, dtype=f32)
@@ -521,6 +583,22 @@ def linear_interpolation_inpaint(src, mask):
     mm = None if mask is None else mat(np.ascontiguousarray(mask, dtype=np.uint8))
     check(capi.lib.ssk_linear_interpolation_inpaint(C.byref(mat(src)), ref(mm), C.byref(mat(dst))))
     return dst
+
+
+def median_filter_bad_pixels(image, variation_threshold):
+    """median_filter_bad_pixels (core/proc/bad_pixels.cc:58-70) of a mono / colour frame -> filtered copy."""
+    out = np.ascontiguousarray(image).copy()
+    m = mat(out)
+    check(capi.lib.ssk_median_filter_bad_pixels(C.byref(m), float(variation_threshold)))
+    return out
+
+
+def bayer_denoise(raw, variation_threshold):
+    """bayer_denoise (core/io/debayer.cc:1471-1611, returnBayerPlanes = false) of a raw single-channel Bayer frame -> filtered copy."""
+    out = np.ascontiguousarray(raw).copy()
+    m = mat(out)
+    check(capi.lib.ssk_bayer_denoise(C.byref(m), float(variation_threshold)))
+    return out
 
 
 def average_bayer_planes(raw):

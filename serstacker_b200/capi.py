@@ -178,6 +178,10 @@ _sigs = {
     "ssk_stack_registration": (C.c_void_p, [C.c_void_p]),
     "ssk_stack_stream": (C.c_void_p, [C.c_void_p]),
     "ssk_stack_stage_times": (C.c_int, [C.c_void_p, _P(C.c_float)]),
+    "ssk_median_filter_bad_pixels": (C.c_int, [_P(ssk_mat), C.c_double]),
+    "ssk_bayer_denoise": (C.c_int, [_P(ssk_mat), C.c_double]),
+    "ssk_build_ellipsoid_rotation": (C.c_int, [_P(C.c_double), _P(C.c_double)]),
+    "ssk_ellipsoid_bbox": (C.c_int, [C.c_int, C.c_int, _P(C.c_double), _P(C.c_double), _P(C.c_double), _P(C.c_float), _P(C.c_int)]),
     "ssk_upscale_size": (C.c_int, [C.c_int, C.c_int, C.c_int, _P(C.c_int), _P(C.c_int)]),
     "ssk_upscale_image": (C.c_int, [C.c_int, _P(ssk_mat), _P(ssk_mat), _P(ssk_mat), _P(ssk_mat)]),
     "ssk_upscale_remap": (C.c_int, [C.c_int, _P(ssk_mat), _P(ssk_mat)]),

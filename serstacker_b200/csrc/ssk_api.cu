@@ -6,7 +6,11 @@
 #include "ssk_engine.cuh"
 #include "ssk_eccflow.cuh"
 
+#include <cfloat>
+
 using namespace ssk;
+
+static constexpr double CV_PI_D = 3.1415926535897932384626433832795;
 
 // ------------------------------------------------------------------------------------------------
 // helpers
@@ -875,6 +879,93 @@ int ssk_lpg(const ssk_mat *image, double k, double p, int dscale, int uscale, ss
   if (int e = lpg_device(sc, im, k, p, dscale, uscale, &M)) return e;
   if (int e = from_device(M, (size_t)im.cols * 4, im.rows, map, s)) return e;
   SSK_CUDA(cudaStreamSynchronize(s));
+  return SSK_OK;
+}
+
+// Host side of c_jovian_derotation_remap / c_saturn_derotation_remap: build_ellipsoid_rotation (ellipsoid.h:47-63,
+// build_rotation pose.h:18-58), ellipsoid_bbox (ellipsoid.cc:16-84) and ellipse_crop_box (ellipsoid.cc:279-328), scalar
+// double / float arithmetic, no device work.
+namespace {
+// cv::hypot of lapack.cpp and one Jacobi rotation = cv::eigen of a symmetric 2 x 2 (eigenvalues descending, eigenvectors in rows)
+inline double cv_hypot(double a, double b) {
+  a = std::fabs(a); b = std::fabs(b);
+  if (a > b) { b /= a; return a * std::sqrt(1 + b * b); }
+  if (b > 0) { a /= b; return b * std::sqrt(1 + a * a); }
+  return 0;
+}
+void eigen_sym2(double a00, double a01, double a11, double W[2], double V[2][2]) {
+  W[0] = a00; W[1] = a11;
+  V[0][0] = 1; V[0][1] = 0; V[1][0] = 0; V[1][1] = 1;
+  const double p = a01;
+  if (std::fabs(p) > DBL_EPSILON) {
+    const double y = (W[1] - W[0]) * 0.5;
+    double t = std::fabs(y) + cv_hypot(p, y);
+    double sn = cv_hypot(p, t);
+    const double c = t / sn;
+    sn = p / sn; t = (p / t) * p;
+    if (y < 0) { sn = -sn; t = -t; }
+    W[0] -= t; W[1] += t;
+    for (int i = 0; i < 2; ++i) {
+      const double v0 = V[0][i], v1 = V[1][i];
+      V[0][i] = v0 * c - v1 * sn;
+      V[1][i] = v0 * sn + v1 * c;
+    }
+  }
+  if (W[0] < W[1]) { std::swap(W[0], W[1]); std::swap(V[0][0], V[1][0]); std::swap(V[0][1], V[1][1]); }
+}
+void mat3_mul(const double a[9], const double b[9], double c[9]) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) c[i * 3 + j] = a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j] + a[i * 3 + 2] * b[6 + j];
+}
+}  // namespace
+
+int ssk_build_ellipsoid_rotation(const double pose[3], double R[9]) {
+  SSK_REQUIRE(pose && R, "build_ellipsoid_rotation: null argument");
+  const double ax = pose[1], ay = pose[0], az = pose[2];   // build_rotation(tilt_to_earth, longitude_rotation, position_angle)
+  const double cx = std::cos(ax), sx = std::sin(ax), cy = std::cos(ay), sy = std::sin(ay), cz = std::cos(az), sz = std::sin(az);
+  const double Rx[9] = {1, 0, 0, 0, cx, -sx, 0, sx, cx}, Ry[9] = {cy, 0, sy, 0, 1, 0, -sy, 0, cy}, Rz[9] = {cz, -sz, 0, sz, cz, 0, 0, 0, 1};
+  double t[9];
+  mat3_mul(Rz, Rx, t);
+  mat3_mul(t, Ry, R);
+  return SSK_OK;
+}
+
+int ssk_ellipsoid_bbox(int rows, int cols, const double center[2], const double axes[3], const double R[9], float ebox[5], int crop_box[4]) {
+  SSK_REQUIRE(center && axes && R && ebox && crop_box, "ellipsoid_bbox: null argument");
+  SSK_REQUIRE(rows > 0 && cols > 0 && axes[0] > 0 && axes[1] > 0 && axes[2] > 0, "ellipsoid_bbox: bad geometry");
+  // Q = RR diag(1/A^2, 1/B^2, 1/C^2, -1) RR^T is block diagonal, so (P Q^-1 P^T)^-1 restricted to x, y is the inverse of the
+  // upper-left 2 x 2 of (R diag(1/A^2, 1/B^2, 1/C^2) R^T)^-1
+  const double d[3] = {1 / (axes[0] * axes[0]), 1 / (axes[1] * axes[1]), 1 / (axes[2] * axes[2])};
+  double M[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) M[i * 3 + j] = R[i * 3] * d[0] * R[j * 3] + R[i * 3 + 1] * d[1] * R[j * 3 + 1] + R[i * 3 + 2] * d[2] * R[j * 3 + 2];
+  const double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[2] * M[7] - M[1] * M[8], c11 = M[0] * M[8] - M[2] * M[6];
+  const double det = M[0] * c00 + M[1] * (M[5] * M[6] - M[3] * M[8]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+  SSK_REQUIRE(det != 0, "ellipsoid_bbox: singular pose");
+  const double s00 = c00 / det, s01 = c01 / det, s11 = c11 / det;   // upper-left 2 x 2 of M^-1
+  const double sd = s00 * s11 - s01 * s01;
+  SSK_REQUIRE(sd != 0, "ellipsoid_bbox: degenerate outline");
+  double W[2], V[2][2];
+  eigen_sym2(s11 / sd, -s01 / sd, s00 / sd, W, V);
+  const double axis_x = 2 / std::sqrt(W[1]), axis_y = 2 / std::sqrt(W[0]);
+  double t0 = std::atan2(V[1][1], V[1][0]);
+  if (t0 > CV_PI_D) t0 -= 2 * CV_PI_D;
+  if (t0 < -CV_PI_D) t0 += CV_PI_D;
+  ebox[0] = (float)center[0]; ebox[1] = (float)center[1]; ebox[2] = (float)axis_x; ebox[3] = (float)axis_y; ebox[4] = (float)(t0 * 180 / CV_PI_D);
+  // ellipse_bounding_box: float arithmetic on the RotatedRect members (the angle conversion goes through double)
+  const float a = (float)(ebox[4] * CV_PI_D / 180);
+  const float ca = std::cos(a), sa = std::sin(a);
+  const float ux = ebox[2] * ca / 2, uy = -ebox[2] * sa / 2, vx = ebox[3] * sa / 2, vy = ebox[3] * ca / 2;
+  const float hw = std::sqrt(ux * ux + vx * vx), hh = std::sqrt(uy * uy + vy * vy);
+  const float left = ebox[0] - hw, top = ebox[1] - hh;
+  int x = (int)left, y = (int)top, w = (int)(2 * hw), h = (int)(2 * hh);
+  const int margin = 1;                                       // ellipse_crop_box's default, what compute_ellipsoid_zrotation_remap uses
+  x -= margin; y -= margin; w += 2 * margin; h += 2 * margin;
+  if (x < 0) x = 0;
+  if (y < 0) y = 0;
+  if (x + w >= cols) w = cols - x;
+  if (y + h >= rows) h = rows - y;
+  crop_box[0] = x; crop_box[1] = y; crop_box[2] = w; crop_box[3] = h;
   return SSK_OK;
 }
 

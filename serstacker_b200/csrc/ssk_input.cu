@@ -5,6 +5,8 @@
 //                                      select_master_frame ranks (c_image_stacking_pipeline_base.cc:370-378)
 //   ssk_color_transform                cv::transform(image, image, color_matrix) (c_image_stacking_pipeline_base.cc:263-266)
 //   ssk_linear_interpolation_inpaint   linear_interpolation_inpaint (core/proc/inpaint/linear_interpolation_inpaint.cc)
+//   ssk_median_filter_bad_pixels       median_filter_bad_pixels (core/proc/bad_pixels.cc:14-70) and bayer_denoise
+//   ssk_bayer_denoise                  (core/io/debayer.cc:1471-1611): both branches of read_input_frame's filter_bad_pixels
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -134,6 +136,142 @@ struct ssk_ser {
   ~ssk_ser() { if (f) fclose(f); }
   int64_t frame_size() const { return (int64_t)h.image_width * h.image_height * cn * bytes_per_sample; }
 };
+
+// ---- median_filter_bad_pixels (bad_pixels.cc:14-56) and bayer_denoise (debayer.cc:1471-1611) ---------------------------
+// median = cv::medianBlur(image, K) (BORDER_REPLICATE), mad = cv::boxFilter(|image - median|, K x K, normalised,
+// BORDER_REFLECT_101), then image = median where |median - image| > k * mad + mv (mv = 1 for integer depths, 1 / 256 for float).
+// K = 5 over the interleaved channels of a mono / colour frame; K = 3 over the four half-size colour planes of a raw Bayer
+// mosaic, which are addressed in place (plane c = rows 2y + (c >> 1), columns 2x + (c & 1)): the reference's
+// _extract_bayer_planes copy and the write-back loop disappear.  Samples are handled as float: exact for 8 / 16-bit integers.
+namespace {
+
+// a view of `cn` planes of rows x cols samples inside one frame buffer
+struct BpView {
+  int64_t row_step;      // bytes between plane rows
+  int64_t chan_step[4];  // byte offset of plane c
+  int pix_step;          // elements between plane columns
+  int rows, cols, cn;
+};
+
+template <class T> __device__ __forceinline__ T *bp_ptr(T *img, const BpView &v, int y, int x, int c) {
+  return reinterpret_cast<T *>((char *)(img) + (int64_t)y * v.row_step + v.chan_step[c]) + (int64_t)x * v.pix_step;
+}
+
+// median of N (9 or 25) by forgetful selection: keep N / 2 + 2 candidates, drop the extremes, take in the next sample
+template <int N> __device__ __forceinline__ float median_of(const float (&in)[N]) {
+  constexpr int M = N / 2 + 2;
+  float v[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) v[i] = in[i];
+#pragma unroll
+  for (int n = M; n >= 3; --n) {
+#pragma unroll
+    for (int i = 1; i < n; ++i) { const float lo = fminf(v[0], v[i]), hi = fmaxf(v[0], v[i]); v[0] = lo; v[i] = hi; }
+#pragma unroll
+    for (int i = 1; i < n - 1; ++i) { const float lo = fminf(v[i], v[n - 1]), hi = fmaxf(v[i], v[n - 1]); v[i] = lo; v[n - 1] = hi; }
+    // v[0] is the minimum, v[n - 1] the maximum of the n candidates: both leave, the next sample takes slot 0
+    if (n > 3) v[0] = in[N - (n - 3)];
+  }
+  return v[1];
+}
+
+template <class T, int K>
+__global__ void __launch_bounds__(256) k_bp_median(const T *img, const BpView v, float *med, float *adiff) {
+  const int xc = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (xc >= v.cols * v.cn || y >= v.rows) return;
+  const int x = xc / v.cn, c = xc - x * v.cn;
+  float w[K * K];
+#pragma unroll
+  for (int dy = 0; dy < K; ++dy) {
+    const int yy = min(max(y + dy - K / 2, 0), v.rows - 1);
+#pragma unroll
+    for (int dx = 0; dx < K; ++dx) w[dy * K + dx] = (float)*bp_ptr(img, v, yy, min(max(x + dx - K / 2, 0), v.cols - 1), c);
+  }
+  const float m = median_of<K * K>(w), p = w[(K * K) / 2];
+  const int64_t o = (int64_t)y * v.cols * v.cn + xc;
+  med[o] = m;
+  adiff[o] = fabsf(p - m);                 // cv::absdiff (exact for the integer depths, no saturation can occur)
+}
+
+__device__ __forceinline__ int reflect101(int p, int n) {
+  if (n == 1) return 0;
+  while ((unsigned)p >= (unsigned)n) p = p < 0 ? -p : 2 * (n - 1) - p;
+  return p;
+}
+
+template <class T, int K>
+__global__ void __launch_bounds__(256) k_bp_replace(T *img, const BpView v, const float *med, const float *adiff, float k, float mv, int integer_depth) {
+  const int xc = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (xc >= v.cols * v.cn || y >= v.rows) return;
+  const int x = xc / v.cn, c = xc - x * v.cn;
+  // cv::boxFilter: integer depths sum in int and round sum / K^2 to the depth (no ties: K^2 is odd); CV_32F sums in double
+  double sum = 0;
+  for (int dy = -(K / 2); dy <= K / 2; ++dy) {
+    const int yy = reflect101(y + dy, v.rows);
+    for (int dx = -(K / 2); dx <= K / 2; ++dx) sum += (double)adiff[((int64_t)yy * v.cols + reflect101(x + dx, v.cols)) * v.cn + c];
+  }
+  float mad;
+  if (integer_depth) mad = (float)__double2int_rn(sum * (1.0 / (K * K)));
+  else mad = (float)(sum * (1.0 / (K * K)));
+  const int64_t o = (int64_t)y * v.cols * v.cn + xc;
+  T *p = bp_ptr(img, v, y, x, c);
+  const float pv = (float)*p, m = med[o];
+  if (fabsf(m - pv) > __fadd_rn(__fmul_rn(k, mad), mv)) *p = (T)m;
+}
+
+template <class T, int K>
+int bp_run(void *dimg, const BpView &v, float *med, float *adiff, float k, float mv, int integer_depth, cudaStream_t s) {
+  const dim3 grid(div_up(v.cols * v.cn, 32), div_up(v.rows, 8));
+  k_bp_median<T, K><<<grid, 256, 0, s>>>(static_cast<const T *>(dimg), v, med, adiff);
+  SSK_LAUNCH_CHECK();
+  k_bp_replace<T, K><<<grid, 256, 0, s>>>(static_cast<T *>(dimg), v, med, adiff, k, mv, integer_depth);
+  SSK_LAUNCH_CHECK();
+  return SSK_OK;
+}
+
+int bp_filter(ssk_mat *image, double variation_threshold, bool bayer, const char *what) {
+  if (int e = need_device()) return e;
+  if (int e = check_mat_in(image, what)) return e;
+  const int d = type_depth(image->type), cn = type_cn(image->type);
+  if (bayer) {
+    SSK_REQUIRE(cn == 1, "bayer_denoise: a raw Bayer frame has one channel");
+    SSK_REQUIRE(!(image->rows & 1) && !(image->cols & 1) && image->rows >= 4 && image->cols >= 4, "bayer_denoise: uneven or too small image size");
+  } else SSK_REQUIRE(image->rows >= 2 && image->cols >= 2, "median_filter_bad_pixels: image smaller than 2 x 2");
+  InScratch &sc = in_scratch();
+  if (int e = sc.init()) return e;
+  cudaStream_t s = sc.stream;
+  const size_t es = depth_bytes(d), rowb = (size_t)image->cols * cn * es, n = (size_t)image->rows * image->cols * cn;
+  void *dimg; int64_t dstep;
+  if (image->mem == SSK_MEM_DEVICE) { dimg = image->data; dstep = image->step; }
+  else {
+    if (int e = sc.a.ensure(rowb * image->rows)) return e;
+    SSK_CUDA(cudaMemcpy2DAsync(sc.a.p, rowb, image->data, image->step, rowb, image->rows, cudaMemcpyHostToDevice, s));
+    dimg = sc.a.p; dstep = (int64_t)rowb;
+  }
+  if (int e = sc.b.ensure(n * 4)) return e;
+  if (int e = sc.c.ensure(n * 4)) return e;
+  BpView v{};
+  if (bayer) {
+    v.row_step = 2 * dstep; v.pix_step = 2; v.rows = image->rows / 2; v.cols = image->cols / 2; v.cn = 4;
+    for (int c = 0; c < 4; ++c) v.chan_step[c] = (c >> 1) * dstep + (c & 1) * (int64_t)es;
+  } else {
+    v.row_step = dstep; v.pix_step = cn; v.rows = image->rows; v.cols = image->cols; v.cn = cn;
+    for (int c = 0; c < 4; ++c) v.chan_step[c] = c * (int64_t)es;
+  }
+  const float k = (float)variation_threshold, mv = d == SSK_32F ? 1.f / 256.f : 1.f;
+  float *med = sc.b.as<float>(), *adiff = sc.c.as<float>();
+  int e;
+  if (d == SSK_8U) e = bayer ? bp_run<uint8_t, 3>(dimg, v, med, adiff, k, mv, 1, s) : bp_run<uint8_t, 5>(dimg, v, med, adiff, k, mv, 1, s);
+  else if (d == SSK_16U) e = bayer ? bp_run<uint16_t, 3>(dimg, v, med, adiff, k, mv, 1, s) : bp_run<uint16_t, 5>(dimg, v, med, adiff, k, mv, 1, s);
+  else if (d == SSK_32F) e = bayer ? bp_run<float, 3>(dimg, v, med, adiff, k, mv, 0, s) : bp_run<float, 5>(dimg, v, med, adiff, k, mv, 0, s);
+  else { set_error(std::string(what) + ": unsupported depth"); return SSK_ERR_INVALID; }
+  if (e) return e;
+  if (image->mem != SSK_MEM_DEVICE) SSK_CUDA(cudaMemcpy2DAsync(image->data, image->step, dimg, rowb, rowb, image->rows, cudaMemcpyDeviceToHost, s));
+  SSK_CUDA(cudaStreamSynchronize(s));
+  return SSK_OK;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -334,6 +472,14 @@ int ssk_linear_interpolation_inpaint(const ssk_mat *src, const ssk_mat *mask, ss
                              dst->mem == SSK_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
   SSK_CUDA(cudaStreamSynchronize(s));
   return SSK_OK;
+}
+
+int ssk_median_filter_bad_pixels(ssk_mat *image, double variation_threshold) {
+  return bp_filter(image, variation_threshold, false, "median_filter_bad_pixels");
+}
+
+int ssk_bayer_denoise(ssk_mat *image, double variation_threshold) {
+  return bp_filter(image, variation_threshold, true, "bayer_denoise");
 }
 
 }  // extern "C"

@@ -138,8 +138,17 @@ __device__ __forceinline__ float area_weight(const AreaAxis &r, int k) {
   return r.a_mid;
 }
 
+// the per-axis tables of the fractional path, one entry per destination column / row (the double-precision divisions of
+// area_axis once per axis instead of twice per pixel)
+__global__ void __launch_bounds__(256) k_area_axis_tab(int dcols, int drows, double scale_x, double scale_y, int scols, int srows, AreaAxis *tab) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < dcols) tab[i] = area_axis(i, scale_x, scols);
+  else if (i < dcols + drows) tab[i] = area_axis(i - dcols, scale_y, srows);
+}
+
 template <int DEPTH>
-__global__ void __launch_bounds__(256) k_resize_area(const ResizeAreaArgs a, double scale_x, double scale_y, int iscale_x, int iscale_y) {
+__global__ void __launch_bounds__(256) k_resize_area(const ResizeAreaArgs a, double scale_x, double scale_y, int iscale_x, int iscale_y,
+                                                     const AreaAxis *__restrict__ axis_tab) {
   const int b = blockIdx.z;
   Img src = a.src;
   if (a.src_ptrs) src.data = a.src_ptrs[b];
@@ -172,7 +181,8 @@ __global__ void __launch_bounds__(256) k_resize_area(const ResizeAreaArgs a, dou
       out = __fmul_rn(sum, (float)(1.0 / area));
     }
   } else {
-    const AreaAxis ax = area_axis(dx, scale_x, src.cols), ay = area_axis(dy, scale_y, src.rows);
+    const AreaAxis ax = axis_tab ? axis_tab[dx] : area_axis(dx, scale_x, src.cols);
+    const AreaAxis ay = axis_tab ? axis_tab[a.dst_cols + dy] : area_axis(dy, scale_y, src.rows);
     out = 0.f;
     for (int ky = 0; ky < ay.n; ++ky) {
       float buf = 0.f;
@@ -787,10 +797,20 @@ int launch_resize_area(const ResizeAreaArgs &a, cudaStream_t s) {
   const bool fast = std::fabs(scale_x - iscale_x) < DBL_EPSILON && std::fabs(scale_y - iscale_y) < DBL_EPSILON;
   if (!fast) iscale_x = iscale_y = 0;
   dim3 grid(div_up(a.dst_cols, 32), div_up(a.dst_rows, 8), a.batch);
-  if (a.src.depth == SSK_32F) k_resize_area<SSK_32F><<<grid, 256, 0, s>>>(a, scale_x, scale_y, iscale_x, iscale_y);
-  else if (a.src.depth == SSK_16U) k_resize_area<SSK_16U><<<grid, 256, 0, s>>>(a, scale_x, scale_y, iscale_x, iscale_y);
-  else if (a.src.depth == SSK_8U) k_resize_area<SSK_8U><<<grid, 256, 0, s>>>(a, scale_x, scale_y, iscale_x, iscale_y);
-  else { set_error("resize INTER_AREA: unsupported depth"); return SSK_ERR_INVALID; }
+  // fractional scale on images large enough to matter: per-axis tables in stream-ordered scratch
+  AreaAxis *tab = nullptr;
+  if (!fast && (int64_t)a.dst_cols * a.dst_rows * a.batch >= 65536) {
+    if (cudaMallocAsync(reinterpret_cast<void **>(&tab), sizeof(AreaAxis) * (size_t)(a.dst_cols + a.dst_rows), s) != cudaSuccess) { tab = nullptr; cudaGetLastError(); }
+    else {
+      k_area_axis_tab<<<div_up(a.dst_cols + a.dst_rows, 256), 256, 0, s>>>(a.dst_cols, a.dst_rows, scale_x, scale_y, a.src.cols, a.src.rows, tab);
+      SSK_LAUNCH_CHECK();
+    }
+  }
+  if (a.src.depth == SSK_32F) k_resize_area<SSK_32F><<<grid, 256, 0, s>>>(a, scale_x, scale_y, iscale_x, iscale_y, tab);
+  else if (a.src.depth == SSK_16U) k_resize_area<SSK_16U><<<grid, 256, 0, s>>>(a, scale_x, scale_y, iscale_x, iscale_y, tab);
+  else if (a.src.depth == SSK_8U) k_resize_area<SSK_8U><<<grid, 256, 0, s>>>(a, scale_x, scale_y, iscale_x, iscale_y, tab);
+  else { if (tab) cudaFreeAsync(tab, s); set_error("resize INTER_AREA: unsupported depth"); return SSK_ERR_INVALID; }
+  if (tab) cudaFreeAsync(tab, s);
   SSK_LAUNCH_CHECK();
   return SSK_OK;
 }

@@ -667,6 +667,71 @@ inline bool compute_ellipsoid_zrotation_remap(int rows, int cols, const double c
   return ssk_ellipsoid_zrotation_remap(rows, cols, center, axes, R1, R2, ebox_angle_deg, crop_box, wscale, &a, &b, &c) == SSK_OK;
 }
 
+// c_jovian_derotation_remap / c_saturn_derotation_remap (core/proc/feature2d/c_jovian_derotation_remap.{h,cc},
+// c_saturn_derotation_remap.{h,cc}): the two classes are the same code in the reference apart from the default rotation
+// period; pose bookkeeping on the host (ssk_build_ellipsoid_rotation / ssk_ellipsoid_bbox), the map on the device.
+struct c_lpg_options { double k = 2.0, p = 2.0; int dscale = 2, uscale = 6; };   // core/proc/lpg.h
+
+template <int PERIOD_MS>
+class c_ellipsoid_derotation_remap {
+ public:
+  static constexpr double default_rotation_period_sec = PERIOD_MS * 1e-3;
+  void set_rotation_period_sec(double v) { period_ = v; }
+  double rotation_period_sec() const { return period_; }
+  bool set_reference_pose(int image_cols, int image_rows, const double center[2], const double axes[3], const double pose[3]) {
+    cols_ = image_cols; rows_ = image_rows;
+    for (int i = 0; i < 2; ++i) center_[i] = center[i];
+    for (int i = 0; i < 3; ++i) { axes_[i] = axes[i]; current_pose_[i] = target_pose_[i] = pose[i]; }
+    if (ssk_build_ellipsoid_rotation(target_pose_, Rtarget_) != SSK_OK) return false;
+    for (int i = 0; i < 9; ++i) Rcurrent_[i] = Rtarget_[i];
+    return ssk_ellipsoid_bbox(rows_, cols_, center_, axes_, Rtarget_, ebox_, crop_box_) == SSK_OK;
+  }
+  bool compute_derotation_for_angle(double longitude_rotation_radians, double wscale = 1) {
+    set_current(longitude_rotation_radians);
+    return compute_ellipsoid_zrotation_remap(rows_, cols_, center_, axes_, Rcurrent_, Rtarget_, ebox_[4], crop_box_, wscale, rmap_, wmap_, rmask_);
+  }
+  bool compute_derotation_for_time(double deltat_sec, double wscale = 1) { return compute_derotation_for_angle(angle_for_time(deltat_sec), wscale); }
+  // one frame of derotate_and_average_frames after preproc_align_and_remap (c_jdr_pipeline.cc:1184-1236,
+  // c_sdr_pipeline.cc:1192-1246): compute_derotation_for_time(deltat_sec, wscale) and every statement up to
+  // _frame_average.add(current_frame, current_weights) as one device chain
+  bool derotate_and_add(c_frame_accumulation &acc, const image_t &frame, const image_t &mask, double deltat_sec, double wscale, bool is_master,
+                        bool enable_weighted_average = true, const c_lpg_options &lpg = c_lpg_options()) {
+    set_current(angle_for_time(deltat_sec));
+    ssk_mat f = detail::view(frame);
+    detail::Opt<image_t> m(mask);
+    return ssk_jdr_derotate_and_add(acc.handle(), &f, m.get(), center_, axes_, Rcurrent_, Rtarget_, ebox_[4], crop_box_, wscale, is_master,
+                                    enable_weighted_average, lpg.k, lpg.p, lpg.dscale, lpg.uscale) == SSK_OK;
+  }
+  const image_t &rmap() const { return rmap_; }
+  const image_t &wmap() const { return wmap_; }
+  const image_t &rmask() const { return rmask_; }
+  const double *center() const { return center_; }
+  const double *axes() const { return axes_; }
+  const double *current_pose() const { return current_pose_; }
+  const double *target_pose() const { return target_pose_; }
+  const double *Rcurrent() const { return Rcurrent_; }
+  const double *Rtarget() const { return Rtarget_; }
+  const float *ebox() const { return ebox_; }          // {center.x, center.y, width, height, angle_deg}
+  const int *crop_box() const { return crop_box_; }
+
+ private:
+  double angle_for_time(double deltat_sec) const {
+    const double period = period_ > 0 ? period_ : default_rotation_period_sec;
+    return 2 * 3.1415926535897932384626433832795 * deltat_sec / period;
+  }
+  void set_current(double angle) {
+    current_pose_[0] = target_pose_[0] + angle; current_pose_[1] = target_pose_[1]; current_pose_[2] = target_pose_[2];
+    ssk_build_ellipsoid_rotation(current_pose_, Rcurrent_);
+  }
+  double period_ = default_rotation_period_sec;
+  int rows_ = 0, cols_ = 0, crop_box_[4] = {0, 0, 0, 0};
+  double center_[2] = {0, 0}, axes_[3] = {1, 1, 1}, current_pose_[3] = {0, 0, 0}, target_pose_[3] = {0, 0, 0}, Rcurrent_[9] = {}, Rtarget_[9] = {};
+  float ebox_[5] = {};
+  image_t rmap_, wmap_, rmask_;
+};
+using c_jovian_derotation_remap = c_ellipsoid_derotation_remap<35740632>;   // 9h 55m 40.632s (c_jovian_derotation_remap.cc:39)
+using c_saturn_derotation_remap = c_ellipsoid_derotation_remap<38018000>;   // 10h 33m 38s (c_saturn_derotation_remap.cc:34)
+
 // ---------------------------------------------------------------------------------------------------------
 // The batched per-frame loop of c_image_stacking_pipeline::process_input_sequence
 // (c_image_stacking_pipeline.cc:1358-1862): one call registers, warps and accumulates a batch of frames.
@@ -740,6 +805,17 @@ inline bool linear_interpolation_inpaint(const image_t &src, const image_t &mask
   const bool ok = ssk_linear_interpolation_inpaint(&s, m.get(), &d) == SSK_OK;
   if (ok) dst = out;
   return ok;
+}
+
+// median_filter_bad_pixels (core/proc/bad_pixels.cc:58-70): in place; a Bayer colorid dispatches to bayer_denoise like the reference
+inline bool bayer_denoise(image_t &image, double variation_threshold) {   // core/io/debayer.cc:1599-1611, returnBayerPlanes = false
+  ssk_mat m = detail::view(image);
+  return ssk_bayer_denoise(&m, variation_threshold) == SSK_OK;
+}
+inline bool median_filter_bad_pixels(image_t &image, double variation_threshold, bool is_bayer_pattern = false) {
+  if (is_bayer_pattern) return bayer_denoise(image, variation_threshold);
+  ssk_mat m = detail::view(image);
+  return ssk_median_filter_bad_pixels(&m, variation_threshold) == SSK_OK;
 }
 
 // average_bayer_planes (core/io/debayer.cc:277-376), raw single-channel form

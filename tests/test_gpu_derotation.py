@@ -90,3 +90,42 @@ def test_jdr_derotate_and_average_matches_oracle(gpu, weighted):
     assert rel_l2(ag, ao, m) <= 1e-4
     wg, wo = g.get_acc_counters(), o.weights
     assert rel_l2(wg, wo, m) <= 1e-4
+
+
+def test_sdr_derotate_and_average_matches_oracle(gpu):
+    """c_sdr_pipeline::derotate_and_average_frames (c_sdr_pipeline.cc:1192-1246) through c_saturn_derotation_remap with frame
+    time stamps: dt -> compute_derotation_for_time(-dt, w), w = 1 / (1 + |dt| / wts); the host geometry (pose matrices, bounding
+    ellipse, crop box) comes from libssk, the oracle's from its own restatement over cv2.eigen."""
+    from serstacker_b200 import api
+    from oracle import accumulation as oacc
+    size, center, axes = (520, 360), (262.4, 181.2), (160.0, 143.0, 160.0)
+    target = (-0.7, math.radians(-9.0), math.radians(6.0))
+    period = 10 * 3600. + 33 * 60. + 38
+    master_ts, wts = 1000.0, 120.0
+    tss = [700.0, 910.0, 1000.0, 1130.0, 1290.0]
+    lpg_opts = dict(k=2.0, p=2.0, dscale=1, uscale=3)
+    sat = api.c_saturn_derotation_remap()
+    assert sat.rotation_period_sec == period
+    sat.set_reference_pose(size, center, axes, target)
+    o, g = oacc.WeightedAverage(), api.c_weigthed_average()
+    for i, ts in enumerate(tss):
+        dt = ts - master_ts
+        w = 1.0 / (1.0 + abs(dt) / wts)
+        dl = 2 * math.pi * (-dt) / period
+        frame = _jovian_frame(size, center, axes, (target[0] + dl, target[1], target[2]), seed=10 + i)
+        od.jdr_derotate_and_add(o, frame, None, size, center, axes, target, dl, w, is_master=(i == 2),
+                                enable_weighted_average=True, lpg_opts=lpg_opts)
+        sat.derotate_and_add(g, frame, None, -dt, w, i == 2, True, lpg_k=2.0, lpg_p=2.0, lpg_dscale=1, lpg_uscale=3)
+    # the stand-alone map of the class for the last frame equals the oracle's
+    sat.compute_derotation_for_time(-(tss[-1] - master_ts), 0.5)
+    rmap_o, wmap_o, mask_o, _, _ = od.compute_derotation_for_angle(size, center, axes, target, 2 * math.pi * -(tss[-1] - master_ts) / period, 0.5)
+    assert np.array_equal(sat.rmask, mask_o)
+    assert np.abs(sat.rmap - rmap_o).max() <= 2e-4
+    ao, mo = o.compute()
+    ag, mg = g.compute()
+    assert g.accumulated_frames() == len(tss)
+    assert np.mean(mo != mg) < 1e-4
+    m = (mo > 0) & (mg > 0)
+    r = rel_l2(ag, ao, m)
+    print("sdr stack rel-L2 = %.3g" % r)
+    assert r <= 1e-4
