@@ -216,5 +216,30 @@ int main(int argc, char **argv) {
   if (!ssk::linear_interpolation_inpaint(ref, hmask, lin) || lin.ptr<float>(10)[10] != ref.ptr<float>(10)[10]) return 14;
   for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) raw.ptr<uint16_t>(y)[x] = (uint16_t)(100 * ((y & 1) * 2 + (x & 1)));
   if (!ssk::average_bayer_planes(raw, planes) || planes.rows != H / 2 || planes.ptr<uint16_t>(3)[5] != 150) return 14;
+  // filter_bad_pixels (bad_pixels.cc:58-70, debayer.cc:1599-1611): a planted hot pixel goes, its neighbours stay
+  raw.ptr<uint16_t>(40)[60] = 60000;
+  const uint16_t keep = raw.ptr<uint16_t>(40)[62];
+  if (!ssk::median_filter_bad_pixels(raw, 5.0, true) || raw.ptr<uint16_t>(40)[60] != 0 || raw.ptr<uint16_t>(40)[62] != keep) return 14;
+  ssk::Mat hot(H, W, SSK_32FC1);
+  std::memcpy(hot.buf.data(), ref.buf.data(), hot.buf.size());
+  const float before = hot.ptr<float>(70)[90];
+  hot.ptr<float>(70)[90] = before + 0.7f;
+  if (!ssk::median_filter_bad_pixels(hot, 5.0) || std::fabs(hot.ptr<float>(70)[90] - before) > 0.2f) return 14;
+  // c_saturn_derotation_remap (c_saturn_derotation_remap.cc:21-55) and one frame of c_sdr_pipeline's loop
+  {
+    ssk::c_saturn_derotation_remap sat;
+    const double center[2] = {W / 2.0, H / 2.0}, axes[3] = {50, 45, 50}, pose[3] = {0.3, 0.05, -0.1};
+    if (sat.rotation_period_sec() != 10 * 3600. + 33 * 60. + 38 || !sat.set_reference_pose(W, H, center, axes, pose)) return 17;
+    if (!sat.compute_derotation_for_time(300.0, 0.8)) { std::fprintf(stderr, "saturn remap: %s\n", ssk_last_error()); return 17; }
+    const int cy = H / 2, cx = W / 2;
+    if (sat.rmask().ptr<uint8_t>(cy)[cx] != 255 || sat.rmask().ptr<uint8_t>(2)[2] != 0 || sat.rmap().ptr<float>(2)[2 * 2] != 2.f) return 17;
+    if (sat.wmap().ptr<float>(cy)[cx] < 0.7f || sat.crop_box()[2] < 100 || std::fabs(sat.ebox()[2] - 100.f) > 1.f) return 17;
+    ssk::c_weigthed_average dacc;
+    ssk::Mat nomask;
+    if (!sat.derotate_and_add(dacc, ref, nomask, 300.0, 0.8, false) || !sat.derotate_and_add(dacc, ref, nomask, 0.0, 1.0, true) ||
+        dacc.accumulated_frames() != 2) { std::fprintf(stderr, "saturn derotate_and_add: %s\n", ssk_last_error()); return 17; }
+    std::printf("adapter_smoke: c_saturn_derotation_remap ebox %.1f x %.1f @ %.2f deg, crop %d x %d ok\n", sat.ebox()[2], sat.ebox()[3], sat.ebox()[4],
+                sat.crop_box()[2], sat.crop_box()[3]);
+  }
   return (worst <= 0.1 && err <= 5e-3 && cnt > W * H / 2) ? 0 : 1;
 }
