@@ -6,9 +6,10 @@ bicubic remap, sharpness-weighted average.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--chunk C] [--impl ours|reference] [--config 1|2|3|4|5]
 
-The job is the one BASELINE.json names: ONE sequence of K x B frames (B = 1024 by default) stacked into ONE image, the
+The job is the one BASELINE.json names: ONE sequence of K x B frames (B = 8192 by default) stacked into ONE image, the
 frames of every step sharded over the N ranks (one process per GPU, multi.shard_frames), i.e. STRONG scaling.  A "step" is
-one pass of the hot path over B frames (B / N per rank, in launches of C frames).  The timed region runs from the first
+one pass of the hot path over B frames (B / N per rank, in chunks of C = 1024 frames: one ECC launch, four launches of the
+fused warp+accumulate kernel).  The timed region runs from the first
 frame of the first step to the finished stack on rank 0: per-frame loop on every rank, ssk_stack_reduce (one ncclReduce
 group over NVLink through the C ABI) and compute() of the stack into host memory are inside it.
 
@@ -202,8 +203,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=1024, help="frames per step, whole job (sharded over the ranks)")
-    ap.add_argument("--chunk", type=int, default=128, help="frames per launch (max_batch of the pipeline)")
+    ap.add_argument("--batch", type=int, default=8192, help="frames per step, whole job (sharded over the ranks)")
+    ap.add_argument("--chunk", type=int, default=1024, help="frames per launch (max_batch of the pipeline)")
     ap.add_argument("--pool", type=int, default=256, help="distinct synthetic frames resident per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=48, help="frames of the CPU baseline sample")
@@ -269,7 +270,7 @@ def main():
     CH = max(1, args.chunk)
     lo, hi = multi.shard_frames(B, rank, world)      # this rank's frames of every step
     mine = hi - lo
-    pool_n = max(args.pool, min(mine, 512) + 1)
+    pool_n = max(args.pool, min(mine, CH, 1024) + 1)     # a launch never sees a frame twice
     pool = make_frames_gpu(pool_n, args.seed + 1000 * rank, dev)       # frame 0 = unjittered reference scene
     ref = make_frames_gpu(1, 2, dev)[0] if rank != 0 else pool[0]      # every rank registers against the same reference frame
     if rank != 0:
@@ -426,8 +427,13 @@ def main():
 
     # ---------------- roofline of the fused warp+accumulate kernel --------------------------------------
     peak, peak_src = peaks()
-    FL = frames_last_launch
-    t_k = fused_ms * 1e-3                            # device time of one launch of the fused kernel (k_fill_jobs + k_fused_tma)
+    # The fused stage of a chunk of frames_last_launch frames is ceil(frames / 256) launches of k_fused_tma (KPLAN = 256 frames per
+    # launch, csrc/ssk_fused_impl.cuh) plus k_fill_jobs; the stage time of the LAST chunk of the timed region (CUDA events on the
+    # pipeline's stream) divided by that count is the kernel's average launch duration
+    n_kl = (frames_last_launch + 255) // 256
+    FL = frames_last_launch / n_kl
+    fused_ms = stage[3] / n_kl
+    t_k = fused_ms * 1e-3
     bytes_kernel = NPIX * (4 + 4) * FL + NPIX * 16   # frame + weight map read per frame; mean + weight RMW once per launch
     bytes_survey = NPIX * 24 * FL                    # N*(4 + 8 + 8 + 4) per frame (un-batched RMW)
     # roofline.achieved follows the contract: SURVEY section 8(d)'s per-frame figure x the frames of one launch / launch time.
@@ -467,14 +473,14 @@ def main():
                     "limiter": "host-to-device copy of the frames: the job moves %.1f GB/s per GPU against %.1f GB/s of bare cudaMemcpyAsync from the same pinned buffer with all %d rank(s) copying at once" % (
                         h2d_e2e, h2d_bare, world)},
             "gpu_launches": int(n_l.item()),
-            "roofline": {"kernel": "k_fused_tma (fused bicubic warp + eroded mask + weight warp + running weighted mean; one launch per batch over all tiles)",
+            "roofline": {"kernel": "k_fused_tma (fused bicubic warp + eroded mask + weight warp + running weighted mean; one launch per 256 frames over all tiles)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launch_ms": fused_ms, "frames_per_launch": FL,
                          "algorithmic_bytes_per_launch": bytes_survey,
                          "algorithmic_bytes_per_frame": NPIX * 24,
                          "achieved_resident_acc": achieved_resident, "frac_resident_acc": achieved_resident / peak,
                          "bytes_per_launch_resident_acc": bytes_kernel},
-            "stage_ms_per_launch": {"prep": stage[0], "weights": stage[1], "ecc": stage[2], "warp_accumulate": stage[3], "frames": FL},
+            "stage_ms_per_launch": {"prep": stage[0], "weights": stage[1], "ecc": stage[2], "warp_accumulate": stage[3], "frames": frames_last_launch},
             "combine_rel_l2": combine_rel_l2,
             "cpu_baseline": cpu,
             "clocks": sampler.summary(),

@@ -380,8 +380,11 @@ int Ecch::align(int batch, const ssk_transform &t0) {
     cfg.hp_main_mode = mode;
   }
   // CTAs per frame: 8 for short batches (latency of one frame), 4 once the batch outnumbers the 33 clusters of 8 a B200
-  // holds (measured, 128 frames of config #2: 2.47 ms with 8, 2.29 ms with 4, 2.76 ms with 2)
-  const int cs = cluster_fixed ? cluster_size : (batch - done >= 48 ? 4 : 8);
+  // holds, 2 for batches of several hundred frames (fewer cluster barriers per frame; the tail of the last wave no longer
+  // matters).  Measured on config #2, ECC stage per 128 frames (gpurun_out/s5_sweep.log): batch 128: 2.47 / 2.28 / 2.79 ms
+  // with 8 / 4 / 2; batch 296: 2.12 (4) / 2.16 (2); batch 512: 2.04 (4) / 1.97 (2); batch 1024: 1.98 (4) / 1.84 (2) / 2.08 (1)
+  const int left = batch - done;
+  const int cs = cluster_fixed ? cluster_size : (left >= 400 ? 2 : left >= 48 ? 4 : 8);
   if (batch > done)
     if (int e = launch_ecc(cfg, device_frames() + done, batch - done, cs, stream)) return e;
   return SSK_OK;
