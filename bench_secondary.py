@@ -173,7 +173,7 @@ def run(args, peaks, ClockSampler):
         import cv2
         if cfg == 4:
             W = H = 2048
-            POOL, B = 6, 24
+            POOL, B = 6, 100
             center, A = (1021.4, 1030.8), 700.0
             axes = (A, A * 0.93512560845968779724, A)
             target = (0.3, math.radians(3.0), math.radians(15.0))
@@ -197,14 +197,15 @@ def run(args, peaks, ClockSampler):
                 jargs.append((C.byref(capi.device_mat(dfr[k].data_ptr(), H, W, np.float32)), d(center, 2), d(axes, 3), d(_rot(*poses[k]), 9), d(Rt, 9),
                               math.degrees(target[2]), (C.c_int * 4)(*cbox), 1.0 / (1.0 + abs(times[k]) / wts), int(times[k] == 0)))
 
-            def one(i):
-                m, c2, a3, rc, rt, ang, cb, ws, ism = jargs[i % POOL]
+            def one_on(i, m):
+                _, c2, a3, rc, rt, ang, cb, ws, ism = jargs[i % POOL]
                 capi.check(capi.lib.ssk_jdr_derotate_and_add(acc._h, m, None, c2, a3, rc, rt, ang, cb, ws, ism, 1, 2.0, 2.0, 2, 6))
-            hostone = lambda i: api.jdr_derotate_and_add(acc, frames[i % POOL], None, center, axes, _rot(*poses[i % POOL]), Rt, math.degrees(target[2]), cbox,
-                                                         1.0 / (1.0 + abs(times[i % POOL]) / wts), times[i % POOL] == 0)
+
+            def one(i):
+                one_on(i, jargs[i % POOL][0])
             h2d = W * H * 4
         else:
-            W, H, POOL, B = 2448, 2048, 4, 24
+            W, H, POOL, B = 2448, 2048, 4, 100
             frames = _focus_frames(POOL, W, H, seed=5)
             workload = "config#5: 2448x2048 RGB32F focus stack, lpg(k=6,p=2,dscale=0,uscale=0) -> GaussianBlur(1) -> weighted average, no registration"
             bytes_frame = W * H * (12 + 24 + 8 + 4)
@@ -218,26 +219,32 @@ def run(args, peaks, ClockSampler):
             mw, mb = capi.device_mat(wmap.data_ptr(), H, W, np.float32), capi.device_mat(wblur.data_ptr(), H, W, np.float32)
             rf, rw, rb = [C.byref(m) for m in fm], C.byref(mw), C.byref(mb)
 
-            def one(i):
-                capi.check(capi.lib.ssk_lpg(rf[i % POOL], 6.0, 2.0, 0, 0, rw))
+            def one_on(i, m):
+                capi.check(capi.lib.ssk_lpg(m, 6.0, 2.0, 0, 0, rw))
                 capi.check(capi.lib.ssk_gaussian_blur(rw, 1.0, 1.0, rb))
-                capi.check(capi.lib.ssk_acc_add(acc._h, rf[i % POOL], rb, 0))
+                capi.check(capi.lib.ssk_acc_add(acc._h, m, rb, 0))
 
-            def hostone(i):
-                f = frames[i % POOL]
-                acc.add(f, api.gaussian_blur(api.lpg(f, k=6.0, p=2.0, dscale=0, uscale=0), 1.0))
+            def one(i):
+                one_on(i, rf[i % POOL])
+
             h2d = W * H * 12
+        # the frames are device-resident: the calls are stream-ordered (ssk_set_stream_ordered), the host enqueues ahead and
+        # compute() at the end of the step waits for the chain
+        api.set_stream_ordered(True)
+        ocn = 1 if cfg == 4 else 3
+        avg_host = torch.empty((H, W) if ocn == 1 else (H, W, ocn), dtype=torch.float32).pin_memory().numpy()     # the stack is read into pinned memory
+        mask_host = torch.empty((H, W), dtype=torch.uint8).pin_memory().numpy()
         for i in range(args.warmup * 2):
             one(i)
         acc.clear()
         torch.cuda.synchronize()
         sampler.start()
         launches0 = capi.lib.ssk_kernel_launch_count()
-        t0 = time.perf_counter()                                 # every call of these stateless entry points ends with a stream sync
+        t0 = time.perf_counter()
         for s in range(args.steps):
             for i in range(B):
                 one(s * B + i)
-        avg, _ = acc.compute()
+        capi.check(capi.lib.ssk_acc_compute(acc._h, C.byref(capi.mat(avg_host)), C.byref(capi.mat(mask_host)), 1.0))   # waits for the chain
         torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) * 1e3
         accumulated = acc.accumulated_frames()
@@ -246,12 +253,22 @@ def run(args, peaks, ClockSampler):
         t_k = ms * 1e-3 / frames_total
         FL = 1
         stage_ms = None
+        # e2e: pinned host frames -> device (H2D inside the timed region, double-buffered against the previous frame's chain)
+        # -> the same stream-ordered calls -> compute() of the stack into host memory
         acc.clear()
+        pinned = [torch.from_numpy(f).pin_memory() for f in frames]
+        dbuf = [torch.empty_like(dfr[0]) for _ in range(2)]
+        dmat = [C.byref(capi.device_mat(t.data_ptr(), H, W, np.float32, cn=(1 if cfg == 4 else 3))) for t in dbuf]
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(B):
-            hostone(i)
-        acc.compute()
+            dbuf[i & 1].copy_(pinned[i % POOL], non_blocking=True)    # overlaps the chain of frame i - 1
+            torch.cuda.current_stream().synchronize()
+            api.device_synchronize()                                  # frame i - 1 done: its buffer is free for frame i + 1
+            one_on(i, dmat[i & 1])
+        capi.check(capi.lib.ssk_acc_compute(acc._h, C.byref(capi.mat(avg_host)), C.byref(capi.mat(mask_host)), 1.0))
         e2e_s = time.perf_counter() - t0
+        api.set_stream_ordered(False)
         e2e = {"value": B / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": B * h2d, "d2h_bytes_per_step": W * H * (4 * (1 if cfg == 4 else 3) + 1)}
         # CPU baseline
         cv2.setNumThreads(ncores)

@@ -423,6 +423,20 @@ SSK_API int ssk_average_pyramid_inpaint(const ssk_mat *src, const ssk_mat *mask,
 SSK_API int ssk_acc_compute_inpainted(ssk_acc *h, ssk_mat *avg, ssk_mat *mask, double dscale, int max_levels);
 
 /* ---------------------------------------------------------------------------------------------
+ * Stream-ordered call chains for device-resident data.  The reference's operators are blocking calls on cv::Mat
+ * (lpg -> cv::GaussianBlur -> c_frame_accumulation::add in the focus-stack loop, c_jdr_pipeline.cc:1184-1236 per frame);
+ * every libssk call therefore returns with its work finished.  With ssk_set_stream_ordered(1), ssk_lpg, ssk_gaussian_blur,
+ * ssk_acc_add and ssk_jdr_derotate_and_add return as soon as the work is enqueued WHEN all their matrices are
+ * SSK_MEM_DEVICE: the library orders these calls on the device (each waits for the previous one, whatever stream it runs
+ * on), the host runs ahead, and nothing is lost to per-call launch and wait latency.  Calls with host matrices, and
+ * ssk_acc_compute / _compute_inpainted / _get_counters / _clear and the other stateless operators, wait for the chain as
+ * before.  Before reading a device result yourself, or handing it to another handle (ssk_stack_*, ssk_reg_*, ssk_ecch_*),
+ * call ssk_device_synchronize().  The mode is process-wide, the chain is per host thread; returns the previous mode.
+ * ------------------------------------------------------------------------------------------- */
+SSK_API int ssk_set_stream_ordered(int enable);
+SSK_API int ssk_device_synchronize(void);
+
+/* ---------------------------------------------------------------------------------------------
  * Jovian derotation map: compute_ellipsoid_zrotation_remap (core/proc/feature2d/ellipsoid.cc:206-277), called by
  * c_jovian_derotation_remap::compute_derotation_for_angle (c_jovian_derotation_remap.cc:47-60).
  * R1 = pose of the ellipsoid as imaged, R2 = target pose (row-major 3x3, XYZscreen = R * XYZplanet); ebox_angle_deg and

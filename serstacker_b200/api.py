@@ -514,6 +514,17 @@ def jdr_derotate_and_add(acc, frame, mask, center, axes, R_current, R_target, eb
     return True
 
 
+def set_stream_ordered(enable):
+    """ssk_set_stream_ordered: device-resident lpg / gaussian_blur / acc.add / jdr_derotate_and_add calls return once enqueued
+    (ordered on the device by the library).  Returns the previous mode."""
+    return bool(capi.lib.ssk_set_stream_ordered(1 if enable else 0))
+
+
+def device_synchronize():
+    """ssk_device_synchronize: waits for everything the library has in flight."""
+    check(capi.lib.ssk_device_synchronize())
+
+
 def build_ellipsoid_rotation(pose):
     """build_ellipsoid_rotation(pose = (longitude_rotation, tilt_to_earth, position_angle)) (ellipsoid.h:47-71) -> 3x3 float64."""
     R = (C.c_double * 9)()

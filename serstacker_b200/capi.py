@@ -180,6 +180,8 @@ _sigs = {
     "ssk_stack_stage_times": (C.c_int, [C.c_void_p, _P(C.c_float)]),
     "ssk_median_filter_bad_pixels": (C.c_int, [_P(ssk_mat), C.c_double]),
     "ssk_bayer_denoise": (C.c_int, [_P(ssk_mat), C.c_double]),
+    "ssk_set_stream_ordered": (C.c_int, [C.c_int]),
+    "ssk_device_synchronize": (C.c_int, []),
     "ssk_build_ellipsoid_rotation": (C.c_int, [_P(C.c_double), _P(C.c_double)]),
     "ssk_ellipsoid_bbox": (C.c_int, [C.c_int, C.c_int, _P(C.c_double), _P(C.c_double), _P(C.c_double), _P(C.c_float), _P(C.c_int)]),
     "ssk_upscale_size": (C.c_int, [C.c_int, C.c_int, C.c_int, _P(C.c_int), _P(C.c_int)]),

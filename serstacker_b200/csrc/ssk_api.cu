@@ -25,7 +25,15 @@ int check_mat(const ssk_mat *m, const char *what) {
   return SSK_OK;
 }
 
+inline bool on_device(const ssk_mat *m) { return !m || m->mem == SSK_MEM_DEVICE; }
+
+// entry check of the calls that end with a host wait: a pending stream-ordered chain is waited for first
+int ensure_device_ordered();
 int ensure_device() {
+  if (int e = ensure_device_ordered()) return e;
+  return chain_drain();
+}
+int ensure_device_ordered() {
   static thread_local bool checked = false;
   if (checked) return SSK_OK;
   int n = 0;
@@ -463,12 +471,13 @@ int ssk_acc_create(int kind, ssk_acc **out) {
 }
 
 int ssk_acc_destroy(ssk_acc *h) { delete h; return SSK_OK; }
-int ssk_acc_clear(ssk_acc *h) { SSK_REQUIRE(h, "null handle"); return h->a.clear(); }
+int ssk_acc_clear(ssk_acc *h) { SSK_REQUIRE(h, "null handle"); if (int e = chain_drain()) return e; return h->a.clear(); }
 
 int ssk_acc_add(ssk_acc *h, const ssk_mat *src, const ssk_mat *weights, int bpp) {
   SSK_REQUIRE(h, "null handle");
   Acc &a = h->a;
   if (int e = check_mat(src, "c_frame_accumulation::add")) return e;
+  if (int e = chain_wait(a.stream)) return e;
   Img im;
   if (int e = to_device(src, a.staging, a.stream, &im, bpp)) return e;
   int wtype = -1;
@@ -503,12 +512,12 @@ int ssk_acc_add(ssk_acc *h, const ssk_mat *src, const ssk_mat *weights, int bpp)
     if (int e = launch_acc_add(x, a.stream)) return e;
   }
   ++a.frames;
-  SSK_CUDA(cudaStreamSynchronize(a.stream));   // the caller's host buffers are free again
-  return SSK_OK;
+  return chain_finish(a.stream, on_device(src) && on_device(weights));   // host buffers of the caller are free again on return
 }
 
 int ssk_acc_compute(ssk_acc *h, ssk_mat *avg, ssk_mat *mask, double dscale) {
   SSK_REQUIRE(h, "null handle");
+  if (int e = chain_drain()) return e;
   Acc &a = h->a;
   if (a.frames < 1) { set_error("c_frame_accumulation::compute: no accumulated frames"); return SSK_ERR_STATE; }
   const int ocn = a.kind == SSK_ACC_BAYER_AVERAGE ? 3 : a.cn;
@@ -575,6 +584,7 @@ int ssk_acc_compute_inpainted(ssk_acc *h, ssk_mat *avg, ssk_mat *mask, double ds
 
 int ssk_acc_get_counters(ssk_acc *h, ssk_mat *accw) {
   SSK_REQUIRE(h, "null handle");
+  if (int e = chain_drain()) return e;
   Acc &a = h->a;
   SSK_REQUIRE(a.wacc.p, "get_acc_counters: empty accumulator");
   if (int e = check_mat(accw, "get_acc_counters")) return e;
@@ -817,7 +827,9 @@ static int lpg_finish(cudaStream_t s, float *M, float *bufA, float *bufB, int r,
   return SSK_OK;
 }
 
-static int lpg_device(Scratch &sc, Img im, double k, double p, int dscale, int uscale, float **out) {
+// `direct`: a dense device buffer of the image size the caller wants the map in (or null); used when the map comes out of a
+// single pass, *out then equals it and no copy follows
+static int lpg_device(Scratch &sc, Img im, double k, double p, int dscale, int uscale, float **out, float *direct = nullptr) {
   cudaStream_t s = sc.stream;
   SSK_REQUIRE(im.cn >= 1 && im.cn <= 4, "lpg: 1 to 4 channels");
   // lpg.cc:184-200: integer samples are scaled by 1 / max value of the depth
@@ -831,6 +843,11 @@ static int lpg_device(Scratch &sc, Img im, double k, double p, int dscale, int u
     // nothing is scaled before the 5 x 5 operator: channel average, operator and (when no scaling follows either) the power in
     // one pass over the frame
     const bool pow_fused = !(uscale > 0 && uscale > dscale);
+    if (pow_fused && direct) {
+      if (int e = launch_lpg_fused(im, direct, alpha, beta, 1e-9f, (int)p, s)) return e;
+      *out = direct;
+      return SSK_OK;
+    }
     if (int e = launch_lpg_fused(im, bufA, alpha, beta, 1e-9f, pow_fused ? (int)p : 1, s)) return e;
     return lpg_finish(s, bufA, bufA, bufB, im.rows, im.cols, im.rows, im.cols, p, dscale, uscale, pow_fused, out);
   }
@@ -864,7 +881,7 @@ extern "C" {
 // compute_lpg_5x5(k/(k+1), 1/(k+1), 1e-9), pdownscale(uscale - dscale) * (uscale - dscale), pow(p), pyrUp chain back
 // to the image size.
 int ssk_lpg(const ssk_mat *image, double k, double p, int dscale, int uscale, ssk_mat *map) {
-  if (int e = ensure_device()) return e;
+  if (int e = ensure_device_ordered()) return e;
   if (int e = check_mat(image, "lpg")) return e;
   if (int e = check_mat(map, "lpg map")) return e;
   SSK_REQUIRE(map->type == SSK_32FC1 && map->rows == image->rows && map->cols == image->cols, "lpg: map must be CV_32FC1 of the image size");
@@ -873,13 +890,14 @@ int ssk_lpg(const ssk_mat *image, double k, double p, int dscale, int uscale, ss
   Scratch &sc = scratch();
   if (int e = sc.init()) return e;
   cudaStream_t s = sc.stream;
+  if (int e = chain_wait(s)) return e;
   Img im;
   if (int e = to_device(image, sc.a, s, &im, 0)) return e;
   float *M = nullptr;
-  if (int e = lpg_device(sc, im, k, p, dscale, uscale, &M)) return e;
-  if (int e = from_device(M, (size_t)im.cols * 4, im.rows, map, s)) return e;
-  SSK_CUDA(cudaStreamSynchronize(s));
-  return SSK_OK;
+  float *direct = (map->mem == SSK_MEM_DEVICE && map->step == (int64_t)map->cols * 4 && map->data != image->data) ? static_cast<float *>(map->data) : nullptr;
+  if (int e = lpg_device(sc, im, k, p, dscale, uscale, &M, direct)) return e;
+  if (M != direct) { if (int e = from_device(M, (size_t)im.cols * 4, im.rows, map, s)) return e; }
+  return chain_finish(s, on_device(image) && on_device(map));
 }
 
 // Host side of c_jovian_derotation_remap / c_saturn_derotation_remap: build_ellipsoid_rotation (ellipsoid.h:47-63,
@@ -918,6 +936,14 @@ void mat3_mul(const double a[9], const double b[9], double c[9]) {
     for (int j = 0; j < 3; ++j) c[i * 3 + j] = a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j] + a[i * 3 + 2] * b[6 + j];
 }
 }  // namespace
+
+int ssk_set_stream_ordered(int enable) { return set_stream_ordered(enable); }
+
+int ssk_device_synchronize(void) {
+  if (int e = chain_drain()) return e;
+  SSK_CUDA(cudaDeviceSynchronize());
+  return SSK_OK;
+}
 
 int ssk_build_ellipsoid_rotation(const double pose[3], double R[9]) {
   SSK_REQUIRE(pose && R, "build_ellipsoid_rotation: null argument");
@@ -1185,7 +1211,7 @@ int ssk_average_pyramid_inpaint(const ssk_mat *src, const ssk_mat *mask, ssk_mat
 // cv::GaussianBlur(src, dst, Size(), sigma_x, sigma_y, BORDER_REPLICATE) on CV_32FC1 (the weight post-processing of
 // c_jdr_pipeline.cc:1228): equals cv::sepFilter2D with getGaussianKernel(cvRound(8 sigma + 1) | 1, sigma, CV_32F).
 int ssk_gaussian_blur(const ssk_mat *src, double sigma_x, double sigma_y, ssk_mat *dst) {
-  if (int e = ensure_device()) return e;
+  if (int e = ensure_device_ordered()) return e;
   if (int e = check_mat(src, "GaussianBlur src")) return e;
   if (int e = check_mat(dst, "GaussianBlur dst")) return e;
   SSK_REQUIRE(src->type == SSK_32FC1 && dst->type == SSK_32FC1 && dst->rows == src->rows && dst->cols == src->cols,
@@ -1195,6 +1221,7 @@ int ssk_gaussian_blur(const ssk_mat *src, double sigma_x, double sigma_y, ssk_ma
   Scratch &sc = scratch();
   if (int e = sc.init()) return e;
   cudaStream_t s = sc.stream;
+  if (int e = chain_wait(s)) return e;
   Img im;
   if (int e = to_device(src, sc.a, s, &im, 0)) return e;
   const size_t n = (size_t)im.rows * im.cols;
@@ -1213,12 +1240,13 @@ int ssk_gaussian_blur(const ssk_mat *src, double sigma_x, double sigma_y, ssk_ma
     return n;
   };
   SepFilterArgs f = {};
-  f.src = d_src; f.dst = sc.b.as<float>() + n; f.rows = im.rows; f.cols = im.cols; f.batch = 1;
+  // a dense device destination other than the source is written in place of the scratch image
+  const bool direct = dst->mem == SSK_MEM_DEVICE && dst->step == (int64_t)dst->cols * 4 && dst->data != src->data;
+  f.src = d_src; f.dst = direct ? static_cast<float *>(dst->data) : sc.b.as<float>() + n; f.rows = im.rows; f.cols = im.cols; f.batch = 1;
   f.kxn = taps(sigma_x, f.kx); f.kyn = taps(sigma_y, f.ky);
   if (int e = launch_sepfilter(f, s)) return e;
-  if (int e = from_device(f.dst, (size_t)im.cols * 4, im.rows, dst, s)) return e;
-  SSK_CUDA(cudaStreamSynchronize(s));
-  return SSK_OK;
+  if (!direct) { if (int e = from_device(f.dst, (size_t)im.cols * 4, im.rows, dst, s)) return e; }
+  return chain_finish(s, on_device(src) && on_device(dst));
 }
 
 // One frame of c_jdr_pipeline::derotate_and_average_frames (c_jdr_pipeline.cc:1184-1236): derotation map for the frame's
@@ -1229,7 +1257,7 @@ int ssk_jdr_derotate_and_add(ssk_acc *acc, const ssk_mat *frame, const ssk_mat *
                              const double axes[3], const double R_current[9], const double R_target[9],
                              double ebox_angle_deg, const int crop_box[4], double wscale, int is_master,
                              int enable_weighted_average, double lpg_k, double lpg_p, int lpg_dscale, int lpg_uscale) {
-  if (int e = ensure_device()) return e;
+  if (int e = ensure_device_ordered()) return e;
   SSK_REQUIRE(acc && center && axes && R_current && R_target && crop_box, "jdr: null argument");
   if (int e = check_mat(frame, "jdr frame")) return e;
   SSK_REQUIRE(frame->type == SSK_32FC1, "jdr: CV_32FC1 frames (the pipeline's aligned gray frame)");
@@ -1238,6 +1266,7 @@ int ssk_jdr_derotate_and_add(ssk_acc *acc, const ssk_mat *frame, const ssk_mat *
   Scratch &sc = scratch();
   if (int e = sc.init()) return e;
   cudaStream_t s = sc.stream;
+  if (int e = chain_wait(s)) return e;
   static thread_local DevBuf d_frame, d_mask, d_rmap, d_wpre, d_w, d_rmask, d_wblur;
   Tables tab;
   if (int e = get_tables(&tab)) return e;
@@ -1291,13 +1320,12 @@ int ssk_jdr_derotate_and_add(ssk_acc *acc, const ssk_mat *frame, const ssk_mat *
   Acc &A = acc->a;
   SSK_REQUIRE(A.kind == SSK_ACC_WEIGHTED_AVERAGE, "jdr: a c_weigthed_average accumulator is expected");
   if (A.rows) SSK_REQUIRE(A.rows == rows && A.cols == cols && A.cn == 1, "c_weigthed_average::add: frame size / channels differ from the accumulator");
-  SSK_CUDA(cudaStreamSynchronize(A.stream));      // work the accumulator still has in flight on its own stream
   if (int e = A.ensure(rows, cols, 1)) return e;
-  SSK_CUDA(cudaStreamSynchronize(A.stream));      // first use: the zero-fill
+  if (int e = stream_after(s, A.stream)) return e;     // work the accumulator has in flight on its own stream, the zero-fill of a first use
   if (int e = launch_jdr_remap_add(d_f, d_rmap.as<float2>(), d_wblur.as<float>(), rows, cols, A.acc.as<float>(), A.wacc.as<float>(), s)) return e;
   ++A.frames;
-  SSK_CUDA(cudaStreamSynchronize(s));
-  return SSK_OK;
+  if (int e = stream_after(A.stream, s)) return e;     // later calls on the accumulator's stream see this frame
+  return chain_finish(s, on_device(frame) && on_device(mask));
 }
 
 }  // extern "C"

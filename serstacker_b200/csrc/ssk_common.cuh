@@ -18,6 +18,13 @@ namespace ssk {
 void set_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 void count_launch(int n = 1);
+// stream-ordered call chains (ssk_runtime.cu)
+int stream_ordered();
+int set_stream_ordered(int enable);
+int chain_wait(cudaStream_t s);
+int chain_finish(cudaStream_t s, bool all_device);
+int chain_drain();
+int stream_after(cudaStream_t waiter, cudaStream_t producer);
 
 #define SSK_CUDA(expr)                                                        \
   do {                                                                        \

@@ -26,6 +26,7 @@ int check_mat_in(const ssk_mat *m, const char *what) {
 }
 
 int need_device() {
+  if (int e = chain_drain()) return e;
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) {
     cudaGetLastError();

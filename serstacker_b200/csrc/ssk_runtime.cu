@@ -75,6 +75,52 @@ bool encode_tmap_3d_f32(void *out128, const void *base, int cols, int rows, int 
                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// ---- stream-ordered call chains (ssk_set_stream_ordered, include/ssk.h) ----------------------------------------------
+// Handles and the stateless operators own different streams.  In stream-ordered mode a call whose matrices all live on the
+// device ends with an event record instead of a host wait; the next such call makes its stream wait for that event, so
+// the library's calls stay totally ordered on the device while the host runs ahead.
+namespace {
+std::atomic<int> g_ordered{0};
+struct Chain { cudaEvent_t ev = nullptr, hop = nullptr; bool pending = false; };
+thread_local Chain g_chain;
+}  // namespace
+
+int stream_ordered() { return g_ordered.load(std::memory_order_relaxed); }
+int set_stream_ordered(int enable) { return g_ordered.exchange(enable ? 1 : 0); }
+
+int chain_wait(cudaStream_t s) {
+  if (g_chain.pending) SSK_CUDA(cudaStreamWaitEvent(s, g_chain.ev, 0));
+  return SSK_OK;
+}
+
+int chain_finish(cudaStream_t s, bool all_device) {
+  if (stream_ordered() && all_device) {
+    if (!g_chain.ev) SSK_CUDA(cudaEventCreateWithFlags(&g_chain.ev, cudaEventDisableTiming));
+    SSK_CUDA(cudaEventRecord(g_chain.ev, s));
+    g_chain.pending = true;
+    return SSK_OK;
+  }
+  SSK_CUDA(cudaStreamSynchronize(s));
+  return SSK_OK;
+}
+
+int chain_drain() {
+  if (g_chain.pending) {
+    SSK_CUDA(cudaEventSynchronize(g_chain.ev));
+    g_chain.pending = false;
+  }
+  return SSK_OK;
+}
+
+// `waiter` continues after everything `producer` has been given so far (no host wait)
+int stream_after(cudaStream_t waiter, cudaStream_t producer) {
+  if (waiter == producer) return SSK_OK;
+  if (!g_chain.hop) SSK_CUDA(cudaEventCreateWithFlags(&g_chain.hop, cudaEventDisableTiming));
+  SSK_CUDA(cudaEventRecord(g_chain.hop, producer));
+  SSK_CUDA(cudaStreamWaitEvent(waiter, g_chain.hop, 0));
+  return SSK_OK;
+}
+
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int64_t launch_count() { return g_launches.load(); }
 

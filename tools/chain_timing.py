@@ -20,3 +20,15 @@ print("ssk_lpg           %.1f us" % t(lambda: capi.check(capi.lib.ssk_lpg(C.byre
 print("ssk_gaussian_blur %.1f us" % t(lambda: capi.check(capi.lib.ssk_gaussian_blur(C.byref(mw), 1.0, 1.0, C.byref(mb)))))
 print("ssk_acc_add       %.1f us" % t(lambda: capi.check(capi.lib.ssk_acc_add(acc._h, C.byref(m), C.byref(mb), 0))))
 print("empty sync        %.1f us" % t(lambda: torch.cuda.synchronize()))
+api.set_stream_ordered(True)
+print("stream-ordered:")
+print("ssk_lpg           %.1f us" % t(lambda: capi.check(capi.lib.ssk_lpg(C.byref(m), 6.0, 2.0, 0, 0, C.byref(mw)))))
+print("ssk_gaussian_blur %.1f us" % t(lambda: capi.check(capi.lib.ssk_gaussian_blur(C.byref(mw), 1.0, 1.0, C.byref(mb)))))
+print("ssk_acc_add       %.1f us" % t(lambda: capi.check(capi.lib.ssk_acc_add(acc._h, C.byref(m), C.byref(mb), 0))))
+def chain():
+    capi.check(capi.lib.ssk_lpg(C.byref(m), 6.0, 2.0, 0, 0, C.byref(mw)))
+    capi.check(capi.lib.ssk_gaussian_blur(C.byref(mw), 1.0, 1.0, C.byref(mb)))
+    capi.check(capi.lib.ssk_acc_add(acc._h, C.byref(m), C.byref(mb), 0))
+print("chain             %.1f us" % t(chain, 50))
+api.device_synchronize()
+api.set_stream_ordered(False)
