@@ -582,6 +582,90 @@ __global__ void __launch_bounds__(256) k_w1_upsample2x(const W1Args a) {
   }
 }
 
+// The same up-sampling, eight outputs x two rows per thread (the form the stacking loop runs: 1080p from a 960 x 540 map).
+// For full = 2 x small the table of k_w1_axis is s = k - 1, f = 0.75 for dx = 2k and s = k, f = 0.25 for dx = 2k + 1
+// ((dx + 0.5) * 0.5 - 0.5 is exact), clamped only at the first and the last sample of an axis: away from the edges a thread
+// needs no table.  It reads one aligned 16-byte group of three map rows, takes the two neighbouring samples from the lanes
+// beside it, forms the horizontal interpolations of the three rows once (cv::resize's order: v0 * (1 - f) + v1 * f, each
+// product rounded) and combines them vertically.  Edge threads take the table-driven path element by element.
+__global__ void __launch_bounds__(256) k_w1_upsample2x_v8(const W1Args a) {
+  const int b = blockIdx.z;
+  const float *__restrict__ g = a.gmap_ptrs ? a.gmap_ptrs[b] : a.gmap;
+  float *__restrict__ out = a.out_ptrs ? a.out_ptrs[b] : a.out;
+  const int lane = threadIdx.x & 31;
+  const int j4 = (blockIdx.x * 32 + lane) * 4;                   // first map column of this thread's group
+  const int i = blockIdx.y * 8 + (threadIdx.x >> 5);             // map row: output rows 2i and 2i + 1
+  const int x8 = 2 * j4, y0 = 2 * i;
+  const bool inside = j4 < a.cols && i < a.rows;
+  const float add = (float)a.stats[b * 4 + 3];
+  // rows i - 1, i, i + 1 (clamped: the clamped copies are only used by the edge path's own loads, never by the fast one)
+  float w[3][6];
+  const bool aligned = ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;   // 16-byte loads and stores
+  const bool fast = inside && aligned && j4 >= 4 && j4 + 4 <= a.cols - 1 && i >= 1 && i + 1 <= a.rows - 1;
+  const unsigned fast_mask = __ballot_sync(0xffffffffu, fast);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *__restrict__ row = g + (int64_t)min(max(i - 1 + r, 0), a.rows - 1) * a.cols;
+    if (fast) v = __ldg(reinterpret_cast<const float4 *>(row + j4));
+    float left = __shfl_up_sync(0xffffffffu, v.w, 1), right = __shfl_down_sync(0xffffffffu, v.x, 1);
+    if (fast) {
+      // a neighbour that is not on the fast path (or belongs to another warp) did not load: fetch the sample directly
+      if (lane == 0 || !((fast_mask >> (lane - 1)) & 1u)) left = __ldg(row + j4 - 1);
+      if (lane == 31 || !((fast_mask >> (lane + 1)) & 1u)) right = __ldg(row + j4 + 4);
+    }
+    w[r][0] = __fadd_rn(left, add); w[r][1] = __fadd_rn(v.x, add); w[r][2] = __fadd_rn(v.y, add);
+    w[r][3] = __fadd_rn(v.z, add); w[r][4] = __fadd_rn(v.w, add); w[r][5] = __fadd_rn(right, add);
+  }
+  if (!inside) return;
+  if (fast) {
+    float h[3][8];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        // t even: samples (t / 2, t / 2 + 1) of the window with f = 0.75; t odd: ((t + 1) / 2, (t + 1) / 2 + 1) with f = 0.25
+        const int k = (t + 1) >> 1;
+        const float a1 = (t & 1) ? 0.25f : 0.75f, a0 = 1.f - a1;
+        h[r][t] = __fadd_rn(__fmul_rn(w[r][k], a0), __fmul_rn(w[r][k + 1], a1));
+      }
+    }
+    float o0[8], o1[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      o0[t] = __fadd_rn(__fmul_rn(h[0][t], 0.25f), __fmul_rn(h[1][t], 0.75f));      // output row 2i: s = i - 1, f = 0.75
+      o1[t] = __fadd_rn(__fmul_rn(h[1][t], 0.75f), __fmul_rn(h[2][t], 0.25f));      // output row 2i + 1: s = i, f = 0.25
+    }
+    float4 *p0 = reinterpret_cast<float4 *>(out + (int64_t)y0 * a.full_cols + x8);
+    float4 *p1 = reinterpret_cast<float4 *>(out + (int64_t)(y0 + 1) * a.full_cols + x8);
+    p0[0] = make_float4(o0[0], o0[1], o0[2], o0[3]); p0[1] = make_float4(o0[4], o0[5], o0[6], o0[7]);
+    p1[0] = make_float4(o1[0], o1[1], o1[2], o1[3]); p1[1] = make_float4(o1[4], o1[5], o1[6], o1[7]);
+    return;
+  }
+  // edge threads: the tables, one element at a time
+  const int xpad = (a.full_cols + 3) & ~3, ypad = (a.full_rows + 3) & ~3;
+  const int *__restrict__ xi = reinterpret_cast<const int *>(a.axis_tab);
+  const float *__restrict__ xf = reinterpret_cast<const float *>(xi + xpad);
+  const int *__restrict__ yi = xi + 2 * xpad;
+  const float *__restrict__ yf = reinterpret_cast<const float *>(yi + ypad);
+#pragma unroll 1
+  for (int jj = 0; jj < 2; ++jj) {
+    const int y = y0 + jj;
+    if (y >= a.full_rows) break;
+    const int sy = __ldg(yi + y), sy1 = min(sy + 1, a.rows - 1);
+    const float b1 = __ldg(yf + y);
+    const float *__restrict__ g0 = g + (int64_t)sy * a.cols, *__restrict__ g1 = g + (int64_t)sy1 * a.cols;
+#pragma unroll 1
+    for (int t = 0; t < 8; ++t) {
+      const int x = x8 + t;
+      if (x >= a.full_cols) break;
+      const int sx = min(max(__ldg(xi + x), 0), a.cols - 1), sx1 = min(sx + 1, a.cols - 1);
+      out[(int64_t)y * a.full_cols + x] = w1_bilin(__fadd_rn(__ldg(g0 + sx), add), __fadd_rn(__ldg(g0 + sx1), add), __fadd_rn(__ldg(g1 + sx), add),
+                                                  __fadd_rn(__ldg(g1 + sx1), add), __ldg(xf + x), b1);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) k_erode5_u8(const uint8_t *src, int64_t sstep, uint8_t *dst, int64_t dstep, int rows,
                                                    int cols, int border_replicate) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
@@ -900,7 +984,10 @@ int launch_w1(const W1Args &a, cudaStream_t s) {
         if (u.axis_tab_built) *u.axis_tab_built = 1;
       }
     }
-    if (u.full_cols == 2 * u.cols && u.full_rows == 2 * u.rows) {
+    if (u.full_cols == 2 * u.cols && u.full_rows == 2 * u.rows && (u.cols & 3) == 0 && !getenv("SSK_W1_UP_V4")) {
+      dim3 g2(div_up(u.cols, 128), div_up(u.rows, 8), u.batch);
+      k_w1_upsample2x_v8<<<g2, 256, 0, s>>>(u);
+    } else if (u.full_cols == 2 * u.cols && u.full_rows == 2 * u.rows) {
       dim3 g2(div_up(u.full_cols, 128), div_up(u.full_rows, 16), u.batch);
       k_w1_upsample2x<<<g2, 256, 0, s>>>(u);
     } else {

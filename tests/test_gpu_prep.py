@@ -144,3 +144,19 @@ def test_gaussian_blur_matches_opencv(gpu, size, sigma):
     want = cv2.GaussianBlur(img, (0, 0), sigma, None, sigma, cv2.BORDER_REPLICATE)
     got = api.gaussian_blur(img, sigma, sigma)
     assert np.abs(got - want).max() <= 2e-7 * max(1.0, float(np.abs(want).max()))
+
+
+@pytest.mark.parametrize("size", [(320, 240), (1920, 1080), (648, 486), (328, 250), (264, 34)])
+def test_w1_upsample2x_wide_kernel_is_bit_identical(gpu, size):
+    """The eight-outputs-per-thread 2x up-sampling (analytic fractions + neighbour shuffles away from the edges) against the
+    table-driven four-wide kernel it replaces in the stacking loop (SSK_W1_UP_V4 selects the latter)."""
+    import os
+    from serstacker_b200 import api
+    img, _ = _frame(size[0], size[1], 11)
+    Qa, Ma = api.compute_local_variance_map(img, dscale=1, kradius=1, uscale=0)
+    os.environ["SSK_W1_UP_V4"] = "1"
+    try:
+        Qb, Mb = api.compute_local_variance_map(img, dscale=1, kradius=1, uscale=0)
+    finally:
+        del os.environ["SSK_W1_UP_V4"]
+    assert Qa == Qb and np.array_equal(Ma, Mb)
