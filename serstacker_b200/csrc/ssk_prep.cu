@@ -77,14 +77,13 @@ __global__ void __launch_bounds__(256) k_pyrdown(const PyrDownArgs a) {
     int xx[5];
 #pragma unroll
     for (int c = 0; c < 5; ++c) xx[c] = border_idx(ix + c, src.cols, border);
-#pragma unroll 1
+    // unrolled: the loads of all rows are in flight together (a rolled loop walks the rows one memory latency at a time,
+    // which is the whole run time of the small pyramid levels)
+#pragma unroll
     for (int r = 0; r < NR; ++r) {
       const int yy = border_idx(iy + r, src.rows, border);
-      const float v = pd_hform(load_gray<DEPTH>(src, yy, xx[0]), load_gray<DEPTH>(src, yy, xx[1]), load_gray<DEPTH>(src, yy, xx[2]),
-                               load_gray<DEPTH>(src, yy, xx[3]), load_gray<DEPTH>(src, yy, xx[4]), hsimd);
-      // h[] must stay in registers: write through a fully unrolled select instead of a dynamic index
-#pragma unroll
-      for (int k = 0; k < NR; ++k) if (k == r) h[k] = v;
+      h[r] = pd_hform(load_gray<DEPTH>(src, yy, xx[0]), load_gray<DEPTH>(src, yy, xx[1]), load_gray<DEPTH>(src, yy, xx[2]),
+                      load_gray<DEPTH>(src, yy, xx[3]), load_gray<DEPTH>(src, yy, xx[4]), hsimd);
     }
   }
 #pragma unroll
@@ -210,8 +209,10 @@ constexpr int SF_W = 64, SF_H = 16, SF_R = (kMaxTaps - 1) / 2;
 template <int KXN, int KYN>
 __global__ void __launch_bounds__(256) k_sepfilter(const SepFilterArgs a) {
   constexpr int RMAX = (KXN && KYN) ? ((KXN > KYN ? KXN : KYN) >> 1) : SF_R;
-  constexpr bool G7 = KXN == 7 && KYN == 7;                      // the per-frame Gaussian (sigma = 1): register-blocked passes
-  constexpr int PITCH = G7 ? SF_W + 2 * RMAX + 2 : SF_W + 2 * RMAX + 1;
+  // the per-frame Gaussians (7 taps: the ECC image smoothing, 9 taps: cv::GaussianBlur(sigma = 1) of the weight maps):
+  // register-blocked passes
+  constexpr bool G7 = KXN == KYN && (KXN == 7 || KXN == 9);
+  constexpr int PITCH = G7 ? SF_W + 8 : SF_W + 2 * RMAX + 1;     // G7: a multiple of 4 floats (16-byte shared loads)
   __shared__ __align__(16) float s_in[SF_H + 2 * RMAX][PITCH];
   __shared__ __align__(16) float s_h[SF_H + 2 * RMAX][SF_W];
   // interleaved channels and borders other than REPLICATE go through the generic instantiation only
@@ -237,11 +238,12 @@ __global__ void __launch_bounds__(256) k_sepfilter(const SepFilterArgs a) {
   // row / column arithmetic follows OpenCV's filter engine (found bit-exact against cv2 4.13 for the kernels of this
   // path: 5-tap derivative, 3-tap smoothing, 7-tap Gaussian)
   if constexpr (G7) {
-    if (a.ky[0] == a.ky[6]) {
+    if (a.ky[0] == a.ky[KYN - 1]) {
       // Same operations in the same order as the generic passes below, four outputs per thread: the row pass reads its
-      // 10-sample window with three 16-byte shared loads (instead of 28 scalar ones), the column pass keeps a 10-row
-      // window in registers (10 loads instead of 28).
-      for (int i = threadIdx.x; i < (SF_H + 6) * (SF_W / 4); i += 256) {
+      // (3 + taps)-sample window with three 16-byte shared loads (instead of 4 x taps scalar ones), the column pass keeps a
+      // (3 + taps)-row window in registers.
+      constexpr int R = KXN >> 1;
+      for (int i = threadIdx.x; i < (SF_H + 2 * R) * (SF_W / 4); i += 256) {
         const int r = i / (SF_W / 4), cg = (i % (SF_W / 4)) * 4;
         if (r >= ih) break;
         const float4 v0 = *reinterpret_cast<const float4 *>(&s_in[r][cg]);
@@ -253,21 +255,21 @@ __global__ void __launch_bounds__(256) k_sepfilter(const SepFilterArgs a) {
         for (int j = 0; j < 4; ++j) {
           float acc = __fmul_rn(w[j], a.kx[0]);          // RowVec_32f: taps in order, fma chain
 #pragma unroll
-          for (int t = 1; t < 7; ++t) acc = __fmaf_rn(w[j + t], a.kx[t], acc);
+          for (int t = 1; t < KXN; ++t) acc = __fmaf_rn(w[j + t], a.kx[t], acc);
           o[j] = acc;
         }
         *reinterpret_cast<float4 *>(&s_h[r][cg]) = make_float4(o[0], o[1], o[2], o[3]);
       }
       __syncthreads();
       const int tx = threadIdx.x & (SF_W - 1), g4 = (threadIdx.x / SF_W) * 4;
-      float c[10];
+      float c[4 + 2 * R];
 #pragma unroll
-      for (int q = 0; q < 10; ++q) c[q] = s_h[g4 + q][tx];
+      for (int q = 0; q < 4 + 2 * R; ++q) c[q] = s_h[g4 + q][tx];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float acc = __fmul_rn(a.ky[3], c[j + 3]);        // SymmColumnVec_32f: centre tap, then fma over the pairs
+        float acc = __fmul_rn(a.ky[R], c[j + R]);        // SymmColumnVec_32f: centre tap, then fma over the pairs
 #pragma unroll
-        for (int t = 1; t <= 3; ++t) acc = __fmaf_rn(__fadd_rn(c[j + 3 + t], c[j + 3 - t]), a.ky[3 + t], acc);
+        for (int t = 1; t <= R; ++t) acc = __fmaf_rn(__fadd_rn(c[j + R + t], c[j + R - t]), a.ky[R + t], acc);
         const int ty = g4 + j;
         if (ty < oh && tx < ow) dst[(int64_t)(y0 + ty) * a.cols + x0 + tx] = acc;
       }
@@ -697,13 +699,8 @@ __device__ __forceinline__ float pu_row(const float *__restrict__ p, int w, int 
   return __fadd_rn(__fadd_rn(p[x - 1], __fmul_rn(p[x], 6.f)), p[x + 1]);
 }
 
-__global__ void __launch_bounds__(256) k_pyrup(const PyrUpArgs a) {
-  const int b = blockIdx.z;
-  const float *__restrict__ src = a.src_ptrs ? a.src_ptrs[b] : a.src;
-  float *__restrict__ dst = a.dst_ptrs ? a.dst_ptrs[b] : a.dst;
-  const int ox = blockIdx.x * 32 + (threadIdx.x & 31), oy = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (ox >= a.dst_cols || oy >= a.dst_rows) return;
-  const int w = a.cols, h = a.rows;
+// one output of cv::pyrUp (any position, all border rules) and the optional `minuend - pyrUp` epilogue of ecc_normalize
+__device__ __forceinline__ float pu_px(const float *__restrict__ src, int w, int h, int ox, int oy) {
   const int y = min(oy >> 1, h - 1);
   const bool odd = (oy & 1) || (oy >> 1) >= h;
   const int yd = min(y + 1, h - 1), yu = y == 0 ? 1 : y - 1;
@@ -711,14 +708,85 @@ __global__ void __launch_bounds__(256) k_pyrup(const PyrUpArgs a) {
   float v;
   if (odd) v = __fmul_rn(__fadd_rn(r1, r2), 4.f);
   else v = __fadd_rn(__fadd_rn(__fmul_rn(r1, 6.f), pu_row(src + (int64_t)yu * w, w, ox)), r2);
-  v = __fmul_rn(v, 1.0f / 64.0f);
-  const int64_t o = (int64_t)oy * a.dst_cols + ox;
+  return __fmul_rn(v, 1.0f / 64.0f);
+}
+
+__device__ __forceinline__ float pu_epilogue(const PyrUpArgs &a, int b, int64_t o, float v) {
   if (a.minuend_ptrs || a.minuend) {
     const float *m = a.minuend_ptrs ? a.minuend_ptrs[b] : a.minuend;
     v = __fsub_rn(m[o], v);
     if (a.mask && a.mask[o] == 0) v = 0.f;
   }
-  dst[o] = v;
+  return v;
+}
+
+__global__ void __launch_bounds__(256) k_pyrup(const PyrUpArgs a) {
+  const int b = blockIdx.z;
+  const float *__restrict__ src = a.src_ptrs ? a.src_ptrs[b] : a.src;
+  float *__restrict__ dst = a.dst_ptrs ? a.dst_ptrs[b] : a.dst;
+  const int ox = blockIdx.x * 32 + (threadIdx.x & 31), oy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (ox >= a.dst_cols || oy >= a.dst_rows) return;
+  const int64_t o = (int64_t)oy * a.dst_cols + ox;
+  dst[o] = pu_epilogue(a, b, o, pu_px(src, a.cols, a.rows, ox, oy));
+}
+
+// The same operator, one thread per SOURCE pixel (x, y) -> the 2 x 2 outputs (2x .. 2x + 1, 2y .. 2y + 1).  Away from the
+// borders the thread loads its own column of the rows y - 1, y, y + 1, takes the columns x - 1 and x + 1 from the lanes
+// beside it, forms the even / odd row-pass values of the three rows once and combines them into the four outputs (the
+// operations and their order are those of pu_row / pu_px); the two outputs of a row leave as one 8-byte store.  Border
+// threads evaluate pu_px per output.  9 loads + ~70 instructions per output become 3 loads + 6 shuffles per four outputs.
+__global__ void __launch_bounds__(256) k_pyrup_2x2(const PyrUpArgs a) {
+  const int b = blockIdx.z;
+  const float *__restrict__ src = a.src_ptrs ? a.src_ptrs[b] : a.src;
+  float *__restrict__ dst = a.dst_ptrs ? a.dst_ptrs[b] : a.dst;
+  const int lane = threadIdx.x & 31;
+  const int x = blockIdx.x * 32 + lane, y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int w = a.cols, h = a.rows;
+  const bool inside = 2 * x < a.dst_cols && 2 * y < a.dst_rows;
+  const bool fast = inside && x >= 1 && x <= w - 2 && y >= 1 && y <= h - 2 && 2 * x + 1 < a.dst_cols && 2 * y + 1 < a.dst_rows &&
+                    !(a.dst_cols & 1) && (reinterpret_cast<uintptr_t>(dst) & 7) == 0;
+  const unsigned fast_mask = __ballot_sync(0xffffffffu, fast);
+  float c[3], l[3], r[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float *__restrict__ row = src + (int64_t)min(max(y - 1 + k, 0), h - 1) * w;
+    c[k] = fast ? __ldg(row + x) : 0.f;
+    l[k] = __shfl_up_sync(0xffffffffu, c[k], 1);
+    r[k] = __shfl_down_sync(0xffffffffu, c[k], 1);
+    if (fast) {
+      if (lane == 0 || !((fast_mask >> (lane - 1)) & 1u)) l[k] = __ldg(row + x - 1);
+      if (lane == 31 || !((fast_mask >> (lane + 1)) & 1u)) r[k] = __ldg(row + x + 1);
+    }
+  }
+  if (!inside) return;
+  if (fast) {
+    float E[3], O[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      E[k] = __fadd_rn(__fadd_rn(l[k], __fmul_rn(c[k], 6.f)), r[k]);      // pu_row, even column, interior
+      O[k] = __fmul_rn(__fadd_rn(c[k], r[k]), 4.f);                       // pu_row, odd column, interior
+    }
+    // even output row 2y: (6 r[y] + r[y-1]) + r[y+1]; odd output row 2y + 1: 4 (r[y] + r[y+1])
+    float v00 = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(E[1], 6.f), E[0]), E[2]), 1.0f / 64.0f);
+    float v01 = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(O[1], 6.f), O[0]), O[2]), 1.0f / 64.0f);
+    float v10 = __fmul_rn(__fmul_rn(__fadd_rn(E[1], E[2]), 4.f), 1.0f / 64.0f);
+    float v11 = __fmul_rn(__fmul_rn(__fadd_rn(O[1], O[2]), 4.f), 1.0f / 64.0f);
+    const int64_t o0 = (int64_t)(2 * y) * a.dst_cols + 2 * x, o1 = o0 + a.dst_cols;
+    if (a.minuend_ptrs || a.minuend) {
+      v00 = pu_epilogue(a, b, o0, v00); v01 = pu_epilogue(a, b, o0 + 1, v01);
+      v10 = pu_epilogue(a, b, o1, v10); v11 = pu_epilogue(a, b, o1 + 1, v11);
+    }
+    *reinterpret_cast<float2 *>(dst + o0) = make_float2(v00, v01);
+    *reinterpret_cast<float2 *>(dst + o1) = make_float2(v10, v11);
+    return;
+  }
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    const int ox = 2 * x + (k & 1), oy = 2 * y + (k >> 1);
+    if (ox >= a.dst_cols || oy >= a.dst_rows) continue;
+    const int64_t o = (int64_t)oy * a.dst_cols + ox;
+    dst[o] = pu_epilogue(a, b, o, pu_px(src, w, h, ox, oy));
+  }
 }
 
 // ---- W2: lpg --------------------------------------------------------------------------------------
@@ -759,10 +827,13 @@ template <int DEPTH>
 __global__ void __launch_bounds__(256) k_lpg_fused(const Img im, float *__restrict__ dst, float alpha, float beta, float eps, int ipow) {
   __shared__ float s_t[LF_H + 4][LF_W + 4 + 1];
   const int bx = blockIdx.x * LF_W, by = blockIdx.y * LF_H;
+  // origin of the staged tile = the first stencil centre of the tile minus 2.  Centres are clamped to [2, size - 3], so a last
+  // tile narrower than 3 columns (or rows) has its centres left of (above) the tile: the origin follows them
+  const int sx0 = min(max(bx, 2), im.cols - 3) - 2, sy0 = min(max(by, 2), im.rows - 3) - 2;
   const float inv_cn = (float)(1.0 / im.cn);
   for (int i = threadIdx.x; i < (LF_H + 4) * (LF_W + 4); i += 256) {
     const int r = i / (LF_W + 4), c = i - r * (LF_W + 4);
-    const int gy = min(max(by - 2 + r, 0), im.rows - 1), gx = min(max(bx - 2 + c, 0), im.cols - 1);
+    const int gy = min(max(sy0 + r, 0), im.rows - 1), gx = min(max(sx0 + c, 0), im.cols - 1);
     float v = load_px<DEPTH>(im, gy, gx, 0);
     if (im.cn > 1) {
       for (int k = 1; k < im.cn; ++k) v = __fadd_rn(v, load_px<DEPTH>(im, gy, gx, k));
@@ -778,7 +849,7 @@ __global__ void __launch_bounds__(256) k_lpg_fused(const Img im, float *__restri
   for (int k = 0; k < 2; ++k) {
     const int ox = bx + (threadIdx.x & 31), oy = by + (threadIdx.x >> 5) + 8 * k;
     if (ox >= im.cols || oy >= im.rows) continue;
-    const int x = min(max(ox, 2), im.cols - 3) - (bx - 2), y = min(max(oy, 2), im.rows - 3) - (by - 2);   // tile coordinates of the stencil centre
+    const int x = min(max(ox, 2), im.cols - 3) - sx0, y = min(max(oy, 2), im.rows - 3) - sy0;   // tile coordinates of the stencil centre
     auto r = [&](int dy, int dx) { return s_t[y + dy][x + dx]; };
     auto col5 = [&](int dx) { return add(add(add(add(r(-2, dx), mul(2.f, r(-1, dx))), mul(4.f, r(0, dx))), mul(2.f, r(1, dx))), r(2, dx)); };
     auto col3 = [&](int dx) { return add(add(r(-1, dx), mul(2.f, r(0, dx))), r(1, dx)); };
@@ -1037,8 +1108,13 @@ int launch_scale_ipow(float *buf, int64_t n, float scale, bool apply_scale, int 
 int launch_pyrup(const PyrUpArgs &a, cudaStream_t s) {
   SSK_REQUIRE(a.cols >= 2 && a.rows >= 2, "pyrUp: source smaller than 2x2");
   SSK_REQUIRE(abs(a.dst_cols - 2 * a.cols) <= 1 && abs(a.dst_rows - 2 * a.rows) <= 1, "pyrUp: bad dstsize");
-  dim3 grid(div_up(a.dst_cols, 32), div_up(a.dst_rows, 8), a.batch);
-  k_pyrup<<<grid, 256, 0, s>>>(a);
+  if (getenv("SSK_PYRUP_V1")) {       // A/B knob: one thread per output
+    dim3 grid(div_up(a.dst_cols, 32), div_up(a.dst_rows, 8), a.batch);
+    k_pyrup<<<grid, 256, 0, s>>>(a);
+  } else {
+    dim3 grid(div_up(div_up(a.dst_cols, 2), 32), div_up(div_up(a.dst_rows, 2), 8), a.batch);
+    k_pyrup_2x2<<<grid, 256, 0, s>>>(a);
+  }
   SSK_LAUNCH_CHECK();
   return SSK_OK;
 }

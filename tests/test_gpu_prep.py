@@ -100,10 +100,12 @@ def test_pyramid_bit_exact(gpu, size):
         assert np.array_equal(g.reference_image(l), e.reference_image), l
 
 
-@pytest.mark.parametrize("size", [(320, 240), (333, 251)])
+@pytest.mark.parametrize("size", [(320, 240), (333, 251), (130, 97), (161, 82)])
 @pytest.mark.parametrize("k,p,dscale,uscale", [(2.0, 2.0, 2, 6), (2.0, 1.0, 0, 0), (1.0, 3.0, 1, 3), (3.0, 2.0, 2, 2)])
 def test_lpg_matches_oracle(gpu, size, k, p, dscale, uscale):
-    """W2: lpg (lpg.cc:223-290) = pdownscale, 5x5 Laplacian/gradient energy, pdownscale, pow, pyrUp chain."""
+    """W2: lpg (lpg.cc:223-290) = pdownscale, 5x5 Laplacian/gradient energy, pdownscale, pow, pyrUp chain.
+    (130, 97) and (161, 82): last tile of the fused dscale = 0 kernel one or two pixels wide / high (its stencil centres are
+    clamped into the neighbouring tile)."""
     from serstacker_b200 import api
     img, _ = _frame(size[0], size[1], 5)
     want = ow.lpg(img, k, p, dscale, uscale)
@@ -160,3 +162,22 @@ def test_w1_upsample2x_wide_kernel_is_bit_identical(gpu, size):
     finally:
         del os.environ["SSK_W1_UP_V4"]
     assert Qa == Qb and np.array_equal(Ma, Mb)
+
+
+@pytest.mark.parametrize("size", [(480, 400), (301, 203), (1024, 1024), (130, 95)])
+@pytest.mark.parametrize("k,p,dscale,uscale", [(2.0, 2.0, 2, 6), (1.0, 3.0, 1, 3), (2.0, 2.0, 0, 5), (2.0, 1.0, 1, 8)])
+def test_lpg_pyrup_2x2_is_bit_identical(gpu, size, k, p, dscale, uscale):
+    """lpg's pyrUp chain through the four-outputs-per-thread kernel (k_pyrup_2x2) against the one-thread-per-output form
+    (SSK_PYRUP_V1): same bits on even, odd and tiny levels, and within the oracle's tolerance."""
+    import os
+    from serstacker_b200 import api
+    img, _ = _frame(size[0], size[1], 13)
+    a = api.lpg(img, k, p, dscale, uscale)
+    os.environ["SSK_PYRUP_V1"] = "1"
+    try:
+        b = api.lpg(img, k, p, dscale, uscale)
+    finally:
+        del os.environ["SSK_PYRUP_V1"]
+    assert np.array_equal(a, b)
+    want = ow.lpg(img, k, p, dscale, uscale)
+    assert np.abs(a - want).max() <= 2e-6 * np.abs(want).max()
