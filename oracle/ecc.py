@@ -42,6 +42,13 @@ def _dot(a, b):
     return float(np.dot(a.reshape(-1).astype(np.float64), b.reshape(-1).astype(np.float64)))
 
 
+def _ddiv(a, b):
+    """a / b as C++ computes it on doubles: x / 0 is +-inf, 0 / 0 is NaN (the reference divides by CMA == 0 when a diverging trial
+    maps every pixel outside the image, ecc2.cc:1915, 1923)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return float(np.float64(a) / np.float64(b))
+
+
 def _norm_l2sqr(a):
     return float(np.dot(a.reshape(-1).astype(np.float64), a.reshape(-1).astype(np.float64)))
 
@@ -430,9 +437,9 @@ class EccInverseCompositional(EccAlign):
             rhs = cv2.subtract(remapped_image, f)
             rhs[remapped_mask == 0] = 0
             CMA = cv2.countNonZero(remapped_mask)
-            rmsnew = _norm_l2sqr(rhs) * (RMA * RMA) / (CMA * CMA)
+            rmsnew = _ddiv(_norm_l2sqr(rhs) * (RMA * RMA), CMA * CMA)
             v = ecc_project_error_image(self._jac, rhs)
-            ok, deltap = cv2.solve(self._H, (v * f32(RMA / CMA)).astype(f32), flags=cv2.DECOMP_CHOLESKY)
+            ok, deltap = cv2.solve(self._H, (v * f32(_ddiv(RMA, CMA))).astype(f32), flags=cv2.DECOMP_CHOLESKY)
             if not ok:
                 deltap = np.zeros((M, 1), dtype=f32)
             if rmsnew >= rmsold:
@@ -480,13 +487,14 @@ class EccLMInverseCompositional(EccAlign):
         self._CMA = f.size - bad
         rhs[inv_mask != 0] = 0
         self._rhs = rhs
-        self._last_rms = _norm_l2sqr(rhs) * (self._RMA * self._RMA) / (self._CMA * self._CMA)
+        self._last_rms = _ddiv(_norm_l2sqr(rhs) * (self._RMA * self._RMA), self._CMA * self._CMA)
         return self._last_rms
 
     def _compute_v(self):
         # ecc2.cc:1919-1924
         v = ecc_project_error_image(self._jac, self._rhs)
-        return (v * f32(self._RMA / self._CMA)).astype(f32)
+        with np.errstate(invalid="ignore", over="ignore"):
+            return (v * f32(_ddiv(self._RMA, self._CMA))).astype(f32)
 
     def align(self):
         # ecc2.cc:1926-2086

@@ -74,14 +74,12 @@ def test_register_frame_matches_oracle(gpu, method, motion, tfirst):
     g.setup_reference_frame(frames[0])
     strict = strict_case(motion, method)
     for f in frames:
-        try:
-            ok_o = o.register_frame(f)
-        except ZeroDivisionError:
-            # the reference divides by CMA == 0 when a diverging trial maps every pixel outside (inf in C++)
-            pytest.skip("oracle trial left the image (CMA == 0)")
+        # a diverging trial that maps every pixel outside the image divides by CMA == 0: inf / NaN in the reference's double
+        # arithmetic (ecc2.cc:1915, 1923), in the oracle (_ddiv) and on the device alike
+        ok_o = o.register_frame(f)
         ok_g = g.register_frame(f)
         assert ok_o == ok_g
-        assert abs(g.status.rho - o.status.rho) <= 1e-4
+        assert (np.isnan(g.status.rho) and np.isnan(o.status.rho)) or abs(g.status.rho - o.status.rho) <= 1e-4
         if ok_o:
             p_o = o.image_transform.parameters().copy()
             d = map_diff_px(motion, g.image_transform_parameters(), p_o, (400, 300))
