@@ -328,3 +328,38 @@ def test_stack_bayer_average_float_master_over_u16_frames(gpu):
     assert max(map_diff_px(0, rg["params"], r["params"], (128, 96)) for rg, r in zip(res, rec)) <= 1e-3
     assert np.array_equal(mask_g, mask_o)
     assert rel_l2(avg_g, avg_o, mask_o > 0) <= 1e-5
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
+def test_stack_is_independent_of_the_ecc_cluster_size(gpu, cluster):
+    """The ECC kernel runs 8 / 4 / 2 CTAs per frame depending on the batch length (ssk_engine.cu: 2 from 400 frames on, what
+    bench.py's 1024-frame chunks use).  Every cluster size must give the oracle's registration and stack (config #2 shape)."""
+    import os
+    from serstacker_b200 import api
+    frames, mats, _ = synth.make_planet_sequence(480, 270, 6, seed=4, radius=100, sigma_t=4.0, sigma_rot_deg=0.2,
+                                                 sigma_scale=0.002, blur_range=(0.8, 2.5), dtype="f32")
+    so = opl.StackingOptions(accumulation_method=opl.ACC_WEIGHTED_AVERAGE)
+    so.registration.motion_type = otf.IMAGE_MOTION_AFFINE
+    so.registration.interpolation = cv2.INTER_CUBIC
+    so.registration.ecc.ecc_method = oecc.ECC_ALIGN_INVERSE_COMPOSITIONAL_LM
+    so.registration.ecc.ecch_max_level = -1
+    rec = []
+    avg_o, mask_o, acc_o, _ = opl.run_stacking(frames, so, collect=rec)
+    os.environ["SSK_ECC_CLUSTER"] = str(cluster)          # read when the handle is created
+    try:
+        ro = api.registration_options(motion_type=3, interpolation=2, ecc=dict(ecc_method=3, ecch_max_level=-1))
+        p = api.c_image_stacking_pipeline(api.stack_options(registration=ro, accumulation_method=1, max_batch=8))
+    finally:
+        del os.environ["SSK_ECC_CLUSTER"]
+    p.set_reference(frames[0])
+    res = p.add_frames(frames)
+    avg_g, mask_g = p.compute()
+    worst = 0.0
+    for rg, r in zip(res, rec):
+        assert rg["ok"] == r["ok"]
+        worst = max(worst, map_diff_px(3, rg["params"], r["params"], (480, 270)))
+    m = mask_o > 0
+    print("cluster %d: max |d map| = %.3g px, stack rel-L2 = %.3g" % (cluster, worst, rel_l2(avg_g, avg_o, m)))
+    assert worst <= 1e-3
+    assert np.array_equal(mask_g, mask_o)
+    assert rel_l2(avg_g, avg_o, m) <= 1e-4
