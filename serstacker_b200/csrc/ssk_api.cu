@@ -795,16 +795,46 @@ static int lpg_pdown(cudaStream_t s, float *bufA, float *bufB, Img cur, int leve
 // lpg.cc:262-290 after the 5 x 5 operator: pdownscale by uscale - dscale (times that factor), cv::pow(p), pupscale back
 static int lpg_finish(cudaStream_t s, float *M, float *bufA, float *bufB, int r, int c, int im_rows, int im_cols, double p, int dscale,
                       int uscale, bool pow_done, float **out) {
+  const int ip = (int)p;
+  bool tail_done = false;
   if (uscale > 0 && uscale > dscale) {
+    // the pyrDown levels lpg_pdown would run from (r, c): `uscale - dscale` levels, or fewer once a level is smaller than 4
+    int nd = 0;
+    if (std::min(r, c) >= 4) {
+      int rr = r, cc = c;
+      while (nd < uscale - dscale) {
+        rr = (rr + 1) / 2; cc = (cc + 1) / 2; ++nd;
+        if (std::min(rr, cc) < 4) break;
+      }
+    }
+    // levels above `tail_px` pixels are launches of their own; the rest (down, scale, power, up again) is one cluster launch
+    // (a larger cut loses: eight CTAs walk a 128-pixel level slower than 148 SMs run its own launch)
+    static const int tail_px = getenv("SSK_LPG_TAIL_PX") ? atoi(getenv("SSK_LPG_TAIL_PX")) : 64;   // measured on config #4 (frames/s): no tail 4 900, 64: 5 115, 128: 4 630, 256: 4 480
+    int lead = 0;
+    {
+      int rr = r, cc = c;
+      while (lead < nd && std::max(rr, cc) > tail_px) { rr = (rr + 1) / 2; cc = (cc + 1) / 2; ++lead; }
+    }
+    const bool use_tail = nd - lead >= 1 && nd - lead <= 7 && !pow_done && !getenv("SSK_LPG_NO_TAIL");
     Img cur = {};
     cur.data = M; cur.step = (int64_t)c * 4; cur.rows = r; cur.cols = c; cur.depth = SSK_32F; cur.cn = 1; cur.scale = 1.f;
-    float *D = nullptr;
-    if (int e = lpg_pdown(s, bufA, bufB, cur, uscale - dscale, (float)(uscale - dscale), &D, &r, &c)) return e;
-    if (D) M = D;
-    else { if (int e = launch_scale_ipow(M, (int64_t)r * c, (float)(uscale - dscale), true, 1, s)) return e; }
+    if (use_tail) {
+      if (lead > 0) {
+        float *D = nullptr;
+        if (int e = lpg_pdown(s, bufA, bufB, cur, lead, 1.f, &D, &r, &c)) return e;
+        M = D;
+      }
+      float *Q = M == bufA ? bufB : bufA;
+      if (int e = launch_lpg_tail(M, Q, r, c, nd - lead, (float)(uscale - dscale), ip >= 2 ? ip : 1, s)) return e;
+      tail_done = true;
+    } else {
+      float *D = nullptr;
+      if (int e = lpg_pdown(s, bufA, bufB, cur, uscale - dscale, (float)(uscale - dscale), &D, &r, &c)) return e;
+      if (D) M = D;
+      else { if (int e = launch_scale_ipow(M, (int64_t)r * c, (float)(uscale - dscale), true, 1, s)) return e; }
+    }
   }
-  const int ip = (int)p;
-  if (!pow_done && ip != 0 && ip != 1) { if (int e = launch_scale_ipow(M, (int64_t)r * c, 1.f, false, ip, s)) return e; }
+  if (!tail_done && !pow_done && ip != 0 && ip != 1) { if (int e = launch_scale_ipow(M, (int64_t)r * c, 1.f, false, ip, s)) return e; }
   // pupscale (lpg.cc:158-182): the (w+1)/2 size chain from the image size down to the map size, walked back by cv::pyrUp
   if (r != im_rows || c != im_cols) {
     int cw[32], chh[32], nl = 0;

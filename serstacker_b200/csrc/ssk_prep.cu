@@ -8,6 +8,7 @@
 //   compute_local_variance_map                         core/proc/sharpness_measure/c_local_variance_sharpness_measure.cc:193-247
 // All kernels are batched over the frames of a batch through blockIdx.z.
 #include "ssk_prep.cuh"
+#include <cooperative_groups.h>
 #include <cfloat>
 #include <cmath>
 
@@ -789,6 +790,93 @@ __global__ void __launch_bounds__(256) k_pyrup_2x2(const PyrUpArgs a) {
   }
 }
 
+// ---- the small end of lpg's pyramid in one launch -------------------------------------------------
+// lpg.cc:262-290 walks cv::pyrDown to a map of a few dozen pixels, scales it, raises it to the power p and walks cv::pyrUp
+// back.  A level of a few thousand pixels is a few microseconds of launch latency and nothing else, so one 8-CTA cluster
+// runs the levels from a small image down, the scalar steps, and back up to that size, with a cluster barrier between
+// levels.  The levels are written inside this kernel by other CTAs: they are read with ld.global.cg (no L1).
+// Per-output arithmetic = k_pyrdown's general path / pu_px.
+__device__ __forceinline__ float pd_px_cg(const float *src, int w, int h, int dst_cols, int ox, int oy) {
+  const int width0 = min((w - 3) / 2 + 1, dst_cols);
+  const bool hsimd = ox >= 1 && ox < 1 + 4 * ((width0 - 1) / 4);
+  const bool vsimd = ox < (dst_cols & ~3);
+  int xx[5];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) xx[c] = border_idx(2 * ox - 2 + c, w, SSK_BORDER_REFLECT101);
+  float r[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const float *row = src + (int64_t)border_idx(2 * oy - 2 + k, h, SSK_BORDER_REFLECT101) * w;
+    r[k] = pd_hform(__ldcg(row + xx[0]), __ldcg(row + xx[1]), __ldcg(row + xx[2]), __ldcg(row + xx[3]), __ldcg(row + xx[4]), hsimd);
+  }
+  const float a13 = __fadd_rn(r[1], r[3]);
+  float v;
+  if (vsimd) v = __fadd_rn(__fmul_rn(__fadd_rn(a13, r[2]), 4.f), __fadd_rn(__fadd_rn(r[0], r[4]), __fadd_rn(r[2], r[2])));
+  else v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r[2], 6.f), __fmul_rn(a13, 4.f)), r[0]), r[4]);
+  return __fmul_rn(v, 1.0f / 256.0f);
+}
+
+// pu_row / pu_px with ld.global.cg
+__device__ __forceinline__ float pu_row_cg(const float *p, int w, int ox) {
+  const int x = min(ox >> 1, w - 1);
+  const bool odd = (ox & 1) || (ox >> 1) >= w;
+  if (odd) return x == w - 1 ? __fmul_rn(__ldcg(p + x), 8.f) : __fmul_rn(__fadd_rn(__ldcg(p + x), __ldcg(p + x + 1)), 4.f);
+  if (x == 0) return __fadd_rn(__fmul_rn(__ldcg(p), 6.f), __fmul_rn(__ldcg(p + 1), 2.f));
+  if (x == w - 1) return __fadd_rn(__ldcg(p + x - 1), __fmul_rn(__ldcg(p + x), 7.f));
+  return __fadd_rn(__fadd_rn(__ldcg(p + x - 1), __fmul_rn(__ldcg(p + x), 6.f)), __ldcg(p + x + 1));
+}
+__device__ __forceinline__ float pu_px_cg(const float *src, int w, int h, int ox, int oy) {
+  const int y = min(oy >> 1, h - 1);
+  const bool odd = (oy & 1) || (oy >> 1) >= h;
+  const int yd = min(y + 1, h - 1), yu = y == 0 ? 1 : y - 1;
+  const float r1 = pu_row_cg(src + (int64_t)y * w, w, ox), r2 = pu_row_cg(src + (int64_t)yd * w, w, ox);
+  float v;
+  if (odd) v = __fmul_rn(__fadd_rn(r1, r2), 4.f);
+  else v = __fadd_rn(__fadd_rn(__fmul_rn(r1, 6.f), pu_row_cg(src + (int64_t)yu * w, w, ox)), r2);
+  return __fmul_rn(v, 1.0f / 64.0f);
+}
+
+constexpr int LT_CTAS = 8, LT_THREADS = 512;
+
+__global__ void __launch_bounds__(LT_THREADS) k_lpg_tail(float *P, float *Q, int rows, int cols, int ndown, float scale, int ipow) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = (int)cluster.block_rank() * LT_THREADS + threadIdx.x, nthr = (int)cluster.num_blocks() * LT_THREADS;
+  int hs[8], ws[8];
+  hs[0] = rows; ws[0] = cols;
+  for (int l = 0; l < ndown; ++l) { hs[l + 1] = (hs[l] + 1) / 2; ws[l + 1] = (ws[l] + 1) / 2; }
+  float *cur = P, *oth = Q;
+  for (int l = 0; l < ndown; ++l) {
+    const int n = hs[l + 1] * ws[l + 1];
+    const bool last = l == ndown - 1;
+    for (int i = tid; i < n; i += nthr) {
+      const int oy = i / ws[l + 1], ox = i - oy * ws[l + 1];
+      float v = pd_px_cg(cur, ws[l], hs[l], ws[l + 1], ox, oy);
+      if (last) {                                      // the smallest level: cv::multiply by (uscale - dscale), cv::pow (k_scale_ipow)
+        v = __fmul_rn(v, scale);
+        if (ipow > 1) {
+          float a = 1.f, b = v;
+          int p = ipow;
+          while (p > 1) { if (p & 1) a = __fmul_rn(a, b); b = __fmul_rn(b, b); p >>= 1; }
+          v = __fmul_rn(a, b);
+        }
+      }
+      oth[i] = v;
+    }
+    cluster.sync();
+    float *t = cur; cur = oth; oth = t;
+  }
+  for (int l = ndown - 1; l >= 0; --l) {
+    const int n = hs[l] * ws[l];
+    for (int i = tid; i < n; i += nthr) {
+      const int oy = i / ws[l], ox = i - oy * ws[l];
+      oth[i] = pu_px_cg(cur, ws[l + 1], hs[l + 1], ox, oy);
+    }
+    cluster.sync();
+    float *t = cur; cur = oth; oth = t;
+  }
+}
+
 // ---- W2: lpg --------------------------------------------------------------------------------------
 // compute_lpg_5x5 (lpg.cc:60-129): alpha * laplacian^2 + beta * |gradient|^2 + eps with the 5x5 operators of the
 // reference, single-rounded float operations in its evaluation order; the two border rows / columns repeat the
@@ -1102,6 +1190,25 @@ int launch_lpg_fused(const Img &im, float *dst, float alpha, float beta, float e
 int launch_scale_ipow(float *buf, int64_t n, float scale, bool apply_scale, int ipow, cudaStream_t s) {
   k_scale_ipow<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(buf, n, scale, apply_scale ? 1 : 0, ipow);
   SSK_LAUNCH_CHECK();
+  return SSK_OK;
+}
+
+// P holds a rows x cols image; on return P holds pyrUp^ndown(pow(scale * pyrDown^ndown(P), ipow)) (ipow = 1: no power); Q is
+// scratch of the same size.  One cluster of 8 CTAs.
+int launch_lpg_tail(float *P, float *Q, int rows, int cols, int ndown, float scale, int ipow, cudaStream_t s) {
+  SSK_REQUIRE(ndown >= 1 && ndown <= 7 && ipow >= 1, "lpg tail: bad geometry");
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(LT_CTAS);
+  lc.blockDim = dim3(LT_THREADS);
+  lc.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = LT_CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  lc.attrs = attr;
+  lc.numAttrs = 1;
+  void *args[7] = {(void *)&P, (void *)&Q, (void *)&rows, (void *)&cols, (void *)&ndown, (void *)&scale, (void *)&ipow};
+  SSK_CUDA(cudaLaunchKernelExC(&lc, (const void *)k_lpg_tail, args));
+  count_launch();
   return SSK_OK;
 }
 

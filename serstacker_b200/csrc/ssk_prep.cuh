@@ -89,6 +89,8 @@ int launch_lpg5x5(const float *src, int rows, int cols, float *dst, float alpha,
 // channel average + 5x5 operator + integer power in one pass (the dscale = 0 form of lpg: no scaling before the operator)
 int launch_lpg_fused(const Img &im, float *dst, float alpha, float beta, float eps, int ipow, cudaStream_t s);
 int launch_scale_ipow(float *buf, int64_t n, float scale, bool apply_scale, int ipow, cudaStream_t s);
+// the small levels of lpg's pyramid (down, scale, power, up) in one 8-CTA cluster launch; P in place, Q scratch
+int launch_lpg_tail(float *P, float *Q, int rows, int cols, int ndown, float scale, int ipow, cudaStream_t s);
 
 // reference-mask helpers: 8U pyrDown + threshold, INTER_NEAREST resize, gradient masking + non-zero count
 int launch_pyrdown_mask_u8(const uint8_t *src, int64_t sstep, int rows, int cols, uint8_t *dst, int drows, int dcols, int thresh,

@@ -166,18 +166,21 @@ def test_w1_upsample2x_wide_kernel_is_bit_identical(gpu, size):
 
 @pytest.mark.parametrize("size", [(480, 400), (301, 203), (1024, 1024), (130, 95)])
 @pytest.mark.parametrize("k,p,dscale,uscale", [(2.0, 2.0, 2, 6), (1.0, 3.0, 1, 3), (2.0, 2.0, 0, 5), (2.0, 1.0, 1, 8)])
-def test_lpg_pyrup_2x2_is_bit_identical(gpu, size, k, p, dscale, uscale):
-    """lpg's pyrUp chain through the four-outputs-per-thread kernel (k_pyrup_2x2) against the one-thread-per-output form
-    (SSK_PYRUP_V1): same bits on even, odd and tiny levels, and within the oracle's tolerance."""
+def test_lpg_pyramid_kernels_are_bit_identical(gpu, size, k, p, dscale, uscale):
+    """lpg's pyramid through the four-outputs-per-thread pyrUp (k_pyrup_2x2) and the single cluster launch for the small levels
+    (k_lpg_tail) against the per-level, one-thread-per-output launches (SSK_PYRUP_V1, SSK_LPG_NO_TAIL): same bits on even, odd
+    and tiny levels, and within the oracle's tolerance."""
     import os
     from serstacker_b200 import api
     img, _ = _frame(size[0], size[1], 13)
     a = api.lpg(img, k, p, dscale, uscale)
     os.environ["SSK_PYRUP_V1"] = "1"
+    os.environ["SSK_LPG_NO_TAIL"] = "1"
     try:
         b = api.lpg(img, k, p, dscale, uscale)
     finally:
         del os.environ["SSK_PYRUP_V1"]
+        del os.environ["SSK_LPG_NO_TAIL"]
     assert np.array_equal(a, b)
     want = ow.lpg(img, k, p, dscale, uscale)
     assert np.abs(a - want).max() <= 2e-6 * np.abs(want).max()
