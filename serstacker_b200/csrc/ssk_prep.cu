@@ -587,10 +587,13 @@ __global__ void __launch_bounds__(256) k_w1_upsample2x(const W1Args a) {
 
 // The same up-sampling, eight outputs x two rows per thread (the form the stacking loop runs: 1080p from a 960 x 540 map).
 // For full = 2 x small the table of k_w1_axis is s = k - 1, f = 0.75 for dx = 2k and s = k, f = 0.25 for dx = 2k + 1
-// ((dx + 0.5) * 0.5 - 0.5 is exact), clamped only at the first and the last sample of an axis: away from the edges a thread
-// needs no table.  It reads one aligned 16-byte group of three map rows, takes the two neighbouring samples from the lanes
-// beside it, forms the horizontal interpolations of the three rows once (cv::resize's order: v0 * (1 - f) + v1 * f, each
-// product rounded) and combines them vertically.  Edge threads take the table-driven path element by element.
+// ((dx + 0.5) * 0.5 - 0.5 is exact); only the first and the last sample of an axis are clamped (s = 0 resp. n - 1 with
+// f = 0, the second tap being s + 1 clamped to n - 1).  So a thread needs no table: it reads one aligned 16-byte group of
+// three map rows, takes the two neighbouring samples from the lanes beside it, forms the horizontal interpolations of the
+// three rows once (cv::resize's order: v0 * (1 - f) + v1 * f, each product rounded) and combines them vertically; the
+// threads on the image border substitute the clamped taps with f = 0 (evaluated literally: v0 * 1 + v1 * 0).  Only frames
+// whose buffers are not 16-byte aligned take the table-driven path element by element.  (First version: border threads
+// walked the tables; one such lane per warp on the left / right border made a quarter of the warps 10 x slower.)
 __global__ void __launch_bounds__(256) k_w1_upsample2x_v8(const W1Args a) {
   const int b = blockIdx.z;
   const float *__restrict__ g = a.gmap_ptrs ? a.gmap_ptrs[b] : a.gmap;
@@ -599,13 +602,13 @@ __global__ void __launch_bounds__(256) k_w1_upsample2x_v8(const W1Args a) {
   const int j4 = (blockIdx.x * 32 + lane) * 4;                   // first map column of this thread's group
   const int i = blockIdx.y * 8 + (threadIdx.x >> 5);             // map row: output rows 2i and 2i + 1
   const int x8 = 2 * j4, y0 = 2 * i;
-  const bool inside = j4 < a.cols && i < a.rows;
+  const bool inside = j4 < a.cols && i < a.rows;                 // cols is a multiple of 4: a group is inside as a whole
   const float add = (float)a.stats[b * 4 + 3];
-  // rows i - 1, i, i + 1 (clamped: the clamped copies are only used by the edge path's own loads, never by the fast one)
-  float w[3][6];
   const bool aligned = ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;   // 16-byte loads and stores
-  const bool fast = inside && aligned && j4 >= 4 && j4 + 4 <= a.cols - 1 && i >= 1 && i + 1 <= a.rows - 1;
+  const bool fast = inside && aligned;
+  const bool first = j4 == 0, last = j4 + 4 == a.cols, top = i == 0, bottom = i == a.rows - 1;
   const unsigned fast_mask = __ballot_sync(0xffffffffu, fast);
+  float w[3][6];
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -613,9 +616,11 @@ __global__ void __launch_bounds__(256) k_w1_upsample2x_v8(const W1Args a) {
     if (fast) v = __ldg(reinterpret_cast<const float4 *>(row + j4));
     float left = __shfl_up_sync(0xffffffffu, v.w, 1), right = __shfl_down_sync(0xffffffffu, v.x, 1);
     if (fast) {
-      // a neighbour that is not on the fast path (or belongs to another warp) did not load: fetch the sample directly
-      if (lane == 0 || !((fast_mask >> (lane - 1)) & 1u)) left = __ldg(row + j4 - 1);
-      if (lane == 31 || !((fast_mask >> (lane + 1)) & 1u)) right = __ldg(row + j4 + 4);
+      // a neighbour that did not load (another warp, or outside the map): fetch the sample directly; none beyond the border
+      if (first) left = 0.f;
+      else if (lane == 0 || !((fast_mask >> (lane - 1)) & 1u)) left = __ldg(row + j4 - 1);
+      if (last) right = 0.f;
+      else if (lane == 31 || !((fast_mask >> (lane + 1)) & 1u)) right = __ldg(row + j4 + 4);
     }
     w[r][0] = __fadd_rn(left, add); w[r][1] = __fadd_rn(v.x, add); w[r][2] = __fadd_rn(v.y, add);
     w[r][3] = __fadd_rn(v.z, add); w[r][4] = __fadd_rn(v.w, add); w[r][5] = __fadd_rn(right, add);
@@ -632,12 +637,17 @@ __global__ void __launch_bounds__(256) k_w1_upsample2x_v8(const W1Args a) {
         const float a1 = (t & 1) ? 0.25f : 0.75f, a0 = 1.f - a1;
         h[r][t] = __fadd_rn(__fmul_rn(w[r][k], a0), __fmul_rn(w[r][k + 1], a1));
       }
+      // dx = 0: s = 0, f = 0 (taps 0 and 1 of the map); dx = 2 cols - 1: s = cols - 1, f = 0 (second tap clamped onto the first)
+      if (first) h[r][0] = __fadd_rn(__fmul_rn(w[r][1], 1.f), __fmul_rn(w[r][2], 0.f));
+      if (last) h[r][7] = __fadd_rn(__fmul_rn(w[r][4], 1.f), __fmul_rn(w[r][4], 0.f));
     }
     float o0[8], o1[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-      o0[t] = __fadd_rn(__fmul_rn(h[0][t], 0.25f), __fmul_rn(h[1][t], 0.75f));      // output row 2i: s = i - 1, f = 0.75
-      o1[t] = __fadd_rn(__fmul_rn(h[1][t], 0.75f), __fmul_rn(h[2][t], 0.25f));      // output row 2i + 1: s = i, f = 0.25
+      // output row 2i: s = i - 1, f = 0.75 (top row: s = 0, f = 0, taps rows 0 and 1); row 2i + 1: s = i, f = 0.25 (bottom row:
+      // s = rows - 1, f = 0, second tap clamped onto the first)
+      o0[t] = top ? __fadd_rn(__fmul_rn(h[1][t], 1.f), __fmul_rn(h[2][t], 0.f)) : __fadd_rn(__fmul_rn(h[0][t], 0.25f), __fmul_rn(h[1][t], 0.75f));
+      o1[t] = bottom ? __fadd_rn(__fmul_rn(h[1][t], 1.f), __fmul_rn(h[1][t], 0.f)) : __fadd_rn(__fmul_rn(h[1][t], 0.75f), __fmul_rn(h[2][t], 0.25f));
     }
     float4 *p0 = reinterpret_cast<float4 *>(out + (int64_t)y0 * a.full_cols + x8);
     float4 *p1 = reinterpret_cast<float4 *>(out + (int64_t)(y0 + 1) * a.full_cols + x8);
@@ -645,7 +655,7 @@ __global__ void __launch_bounds__(256) k_w1_upsample2x_v8(const W1Args a) {
     p1[0] = make_float4(o1[0], o1[1], o1[2], o1[3]); p1[1] = make_float4(o1[4], o1[5], o1[6], o1[7]);
     return;
   }
-  // edge threads: the tables, one element at a time
+  // buffers that are not 16-byte aligned: the tables, one element at a time
   const int xpad = (a.full_cols + 3) & ~3, ypad = (a.full_rows + 3) & ~3;
   const int *__restrict__ xi = reinterpret_cast<const int *>(a.axis_tab);
   const float *__restrict__ xf = reinterpret_cast<const float *>(xi + xpad);
@@ -1143,7 +1153,7 @@ int launch_w1(const W1Args &a, cudaStream_t s) {
         if (u.axis_tab_built) *u.axis_tab_built = 1;
       }
     }
-    if (u.full_cols == 2 * u.cols && u.full_rows == 2 * u.rows && (u.cols & 3) == 0 && !getenv("SSK_W1_UP_V4")) {
+    if (u.full_cols == 2 * u.cols && u.full_rows == 2 * u.rows && (u.cols & 3) == 0 && u.cols >= 8 && u.rows >= 2 && !getenv("SSK_W1_UP_V4")) {
       dim3 g2(div_up(u.cols, 128), div_up(u.rows, 8), u.batch);
       k_w1_upsample2x_v8<<<g2, 256, 0, s>>>(u);
     } else if (u.full_cols == 2 * u.cols && u.full_rows == 2 * u.rows) {
