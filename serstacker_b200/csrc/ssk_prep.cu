@@ -226,20 +226,33 @@ __global__ void __launch_bounds__(256) k_sepfilter(const SepFilterArgs a) {
   const int x0 = blockIdx.x * SF_W, y0 = blockIdx.y * SF_H;
   const int ow = min(SF_W, a.cols - x0), oh = min(SF_H, a.rows - y0);
   const int iw = ow + 2 * rx, ih = oh + 2 * ry;
-  for_tile(ih, iw, [&](int r, int c) {
-    int yy, xx;
-    if (KXN == 0 && a.border) {
-      yy = border_idx(y0 - ry + r, a.rows, a.border); xx = border_idx(x0 - rx + c, a.cols, a.border);
-    } else {
-      yy = min(max(y0 - ry + r, 0), a.rows - 1); xx = min(max(x0 - rx + c, 0), a.cols - 1);
+  // register-blocked Gaussian passes (below): the staged tile starts at column x0 - 4 (16-byte groups of the source row), so
+  // the sample of column x0 - rx sits at index 4 - rx
+  const bool g7 = G7 && a.ky[0] == a.ky[(KYN ? KYN : 1) - 1];
+  const int off = g7 ? 4 - rx : 0;
+  if (g7 && x0 >= 4 && x0 + SF_W + 4 <= a.cols && (a.cols & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    // tile away from the left / right border: 18 aligned 16-byte loads per row instead of 70 scalar ones
+    for (int i = threadIdx.x; i < ih * (PITCH / 4); i += 256) {
+      const int r = i / (PITCH / 4), q = i - r * (PITCH / 4);
+      const int yy = min(max(y0 - ry + r, 0), a.rows - 1);
+      *reinterpret_cast<float4 *>(&s_in[r][4 * q]) = __ldg(reinterpret_cast<const float4 *>(src + (int64_t)yy * a.cols + x0 - 4) + q);
     }
-    s_in[r][c] = __ldg(src + ((int64_t)yy * a.cols + xx) * cn + ch);
-  });
+  } else {
+    for_tile(ih, iw, [&](int r, int c) {
+      int yy, xx;
+      if (KXN == 0 && a.border) {
+        yy = border_idx(y0 - ry + r, a.rows, a.border); xx = border_idx(x0 - rx + c, a.cols, a.border);
+      } else {
+        yy = min(max(y0 - ry + r, 0), a.rows - 1); xx = min(max(x0 - rx + c, 0), a.cols - 1);
+      }
+      s_in[r][c + off] = __ldg(src + ((int64_t)yy * a.cols + xx) * cn + ch);
+    });
+  }
   __syncthreads();
   // row / column arithmetic follows OpenCV's filter engine (found bit-exact against cv2 4.13 for the kernels of this
   // path: 5-tap derivative, 3-tap smoothing, 7-tap Gaussian)
   if constexpr (G7) {
-    if (a.ky[0] == a.ky[KYN - 1]) {
+    if (g7) {
       // Same operations in the same order as the generic passes below, four outputs per thread: the row pass reads its
       // (3 + taps)-sample window with three 16-byte shared loads (instead of 4 x taps scalar ones), the column pass keeps a
       // (3 + taps)-row window in registers.
@@ -254,9 +267,10 @@ __global__ void __launch_bounds__(256) k_sepfilter(const SepFilterArgs a) {
         float o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float acc = __fmul_rn(w[j], a.kx[0]);          // RowVec_32f: taps in order, fma chain
+          constexpr int OFF = 4 - R;                      // index of column x0 - R in the staged row
+          float acc = __fmul_rn(w[j + OFF], a.kx[0]);    // RowVec_32f: taps in order, fma chain
 #pragma unroll
-          for (int t = 1; t < KXN; ++t) acc = __fmaf_rn(w[j + t], a.kx[t], acc);
+          for (int t = 1; t < KXN; ++t) acc = __fmaf_rn(w[j + t + OFF], a.kx[t], acc);
           o[j] = acc;
         }
         *reinterpret_cast<float4 *>(&s_h[r][cg]) = make_float4(o[0], o[1], o[2], o[3]);
