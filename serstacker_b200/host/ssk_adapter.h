@@ -807,6 +807,11 @@ inline bool linear_interpolation_inpaint(const image_t &src, const image_t &mask
   return ok;
 }
 
+// Stream-ordered call chains for device-resident matrices (include/ssk.h): lpg / GaussianBlur / c_frame_accumulation::add /
+// derotate_and_add return once enqueued and are ordered on the device by the library; compute() waits for the chain.
+inline bool set_stream_ordered(bool enable) { return ssk_set_stream_ordered(enable ? 1 : 0) != 0; }   // returns the previous mode
+inline bool device_synchronize() { return ssk_device_synchronize() == SSK_OK; }
+
 // median_filter_bad_pixels (core/proc/bad_pixels.cc:58-70): in place; a Bayer colorid dispatches to bayer_denoise like the reference
 inline bool bayer_denoise(image_t &image, double variation_threshold) {   // core/io/debayer.cc:1599-1611, returnBayerPlanes = false
   ssk_mat m = detail::view(image);

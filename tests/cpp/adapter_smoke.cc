@@ -238,6 +238,7 @@ int main(int argc, char **argv) {
     ssk::Mat nomask;
     if (!sat.derotate_and_add(dacc, ref, nomask, 300.0, 0.8, false) || !sat.derotate_and_add(dacc, ref, nomask, 0.0, 1.0, true) ||
         dacc.accumulated_frames() != 2) { std::fprintf(stderr, "saturn derotate_and_add: %s\n", ssk_last_error()); return 17; }
+    if (ssk::set_stream_ordered(true) || !ssk::set_stream_ordered(false) || !ssk::device_synchronize()) return 17;   // mode toggles, host frames: blocking as before
     std::printf("adapter_smoke: c_saturn_derotation_remap ebox %.1f x %.1f @ %.2f deg, crop %d x %d ok\n", sat.ebox()[2], sat.ebox()[3], sat.ebox()[4],
                 sat.crop_box()[2], sat.crop_box()[3]);
   }
