@@ -113,6 +113,80 @@ __device__ __noinline__ bool valid_eroded(const MapCoef &m, int interp, int x, i
   return true;
 }
 
+// Interior pixels of LINEAR / CUBIC warps (every tap inside the frame): the weight map and all channels of the frame are
+// sampled with one set of tap coefficients and unrolled loads.  Operations and their order are sample_any's (the products
+// wy * wx are formed once instead of once per channel and image).  N = taps per axis.
+template <int N, int DEPTH>
+__device__ __forceinline__ void interior_pixel(const WarpAccArgs &a, const FrameJob &job, const float (&cw)[N * N], int ix, int iy,
+                                               bool weighted, float *A, float *W) {
+  constexpr int OFF = N == 4 ? -1 : 0;
+  typedef typename PixT<DEPTH>::type T;
+  float wk = 1.f;
+  if (weighted) {
+    const float *wp = reinterpret_cast<const float *>(reinterpret_cast<const char *>(job.weights) + (int64_t)(iy + OFF) * a.w_step) + (ix + OFF);
+    float out = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < N; ++ky) {
+      const float *row = reinterpret_cast<const float *>(reinterpret_cast<const char *>(wp) + (int64_t)ky * a.w_step);
+      float r = 0.f;
+#pragma unroll
+      for (int kx = 0; kx < N; ++kx) {
+        const float term = __fmul_rn(__ldg(row + kx), cw[ky * N + kx]);
+        if (N == 2) out = (ky == 0 && kx == 0) ? term : __fadd_rn(out, term);
+        else r = __fadd_rn(r, term);
+      }
+      if (N == 4) out = __fadd_rn(out, r);
+    }
+    wk = out;
+    if (!(wk > 0.f)) return;                      // c_frame_accumulation.cc:114
+  }
+  const float Wn = *W + wk;
+  const float factor = weighted ? __fdiv_rn(wk, Wn) : __fdiv_rn(1.0f, Wn);
+  *W = Wn;
+  const T *fp = reinterpret_cast<const T *>(static_cast<const char *>(job.frame) + (int64_t)(iy + OFF) * a.src_step) + (int64_t)(ix + OFF) * a.cn;
+#pragma unroll 1
+  for (int c = 0; c < a.cn; ++c) {
+    float out = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < N; ++ky) {
+      const T *row = reinterpret_cast<const T *>(reinterpret_cast<const char *>(fp) + (int64_t)ky * a.src_step) + c;
+      float r = 0.f;
+#pragma unroll
+      for (int kx = 0; kx < N; ++kx) {
+        float sv;
+        if (DEPTH == SSK_32F) sv = (float)__ldg(row + kx * a.cn);
+        else sv = __fmul_rn((float)__ldg(row + kx * a.cn), a.scale);
+        const float term = __fmul_rn(sv, cw[ky * N + kx]);
+        if (N == 2) out = (ky == 0 && kx == 0) ? term : __fadd_rn(out, term);
+        else r = __fadd_rn(r, term);
+      }
+      if (N == 4) out = __fadd_rn(out, r);
+    }
+    A[c] = fmaf(out - A[c], factor, A[c]);
+  }
+}
+
+template <int N>
+__device__ __noinline__ void interior_pixel_n(const WarpAccArgs &a, const Tables &tab, const FrameJob &job, int ix, int fx, int iy, int fy,
+                                              bool weighted, float *A, float *W) {
+  float wx[N], wy[N], cw[N * N];
+  if (N == 2) {
+    const float tx = (float)fx * 0.03125f, ty = (float)fy * 0.03125f;
+    wx[0] = 1.0f - tx; wx[1] = tx; wy[0] = 1.0f - ty; wy[1] = ty;
+  } else {
+    const float4 cx = __ldg(tab.cubic + fx), cy = __ldg(tab.cubic + fy);
+    wx[0] = cx.x; wx[1] = cx.y; wx[2 % N] = cx.z; wx[3 % N] = cx.w;
+    wy[0] = cy.x; wy[1] = cy.y; wy[2 % N] = cy.z; wy[3 % N] = cy.w;
+  }
+#pragma unroll
+  for (int ky = 0; ky < N; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < N; ++kx) cw[ky * N + kx] = __fmul_rn(wy[ky], wx[kx]);
+  if (a.depth == SSK_32F) interior_pixel<N, SSK_32F>(a, job, cw, ix, iy, weighted, A, W);
+  else if (a.depth == SSK_16U) interior_pixel<N, SSK_16U>(a, job, cw, ix, iy, weighted, A, W);
+  else interior_pixel<N, SSK_8U>(a, job, cw, ix, iy, weighted, A, W);
+}
+
 // one pixel of one frame through the generic path: A (cn values) and W are updated in place
 __device__ __noinline__ void generic_pixel(const WarpAccArgs &a, const Tables &tab, const FrameJob &job, int x, int y,
                                            float *A, float *W) {
@@ -120,6 +194,18 @@ __device__ __noinline__ void generic_pixel(const WarpAccArgs &a, const Tables &t
   if (!valid_eroded(m, a.interp, x, y, a.cols, a.rows, a.src_cols, a.src_rows, tab)) return;
   float u, v;
   map_xy(m, (float)x, (float)y, u, v);
+  if (a.interp == SSK_INTER_LINEAR || a.interp == SSK_INTER_CUBIC) {
+    int ix, fx, iy, fy;
+    quant32(u, ix, fx);
+    quant32(v, iy, fy);
+    const int off = a.interp == SSK_INTER_CUBIC ? -1 : 0, n = a.interp == SSK_INTER_CUBIC ? 4 : 2;
+    if (ix + off >= 0 && iy + off >= 0 && ix + off + n <= a.src_cols && iy + off + n <= a.src_rows) {
+      const bool wtd = a.use_weights && job.weights != nullptr;
+      if (n == 4) interior_pixel_n<4>(a, tab, job, ix, fx, iy, fy, wtd, A, W);
+      else interior_pixel_n<2>(a, tab, job, ix, fx, iy, fy, wtd, A, W);
+      return;
+    }
+  }
   Img im;
   im.rows = a.src_rows; im.cols = a.src_cols;
   const bool weighted = a.use_weights && job.weights != nullptr;
