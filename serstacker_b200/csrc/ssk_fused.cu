@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) k_fused_generic(const __grid_constant__ W
 #pragma unroll 1
   for (int j = 0; j < a.njobs; ++j) {
     if (!a.jobs[j].ok) continue;
-    generic_pixel(a, tab, a.jobs[j], x, y, A, &W);
+    generic_pixel_fast(a, tab, a.jobs[j], x, y, A, &W);
   }
   a.wacc[p] = W;
   for (int c = 0; c < a.cn; ++c) a.acc[p * a.cn + c] = A[c];

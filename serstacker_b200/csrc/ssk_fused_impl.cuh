@@ -194,18 +194,6 @@ __device__ __noinline__ void generic_pixel(const WarpAccArgs &a, const Tables &t
   if (!valid_eroded(m, a.interp, x, y, a.cols, a.rows, a.src_cols, a.src_rows, tab)) return;
   float u, v;
   map_xy(m, (float)x, (float)y, u, v);
-  if (a.interp == SSK_INTER_LINEAR || a.interp == SSK_INTER_CUBIC) {
-    int ix, fx, iy, fy;
-    quant32(u, ix, fx);
-    quant32(v, iy, fy);
-    const int off = a.interp == SSK_INTER_CUBIC ? -1 : 0, n = a.interp == SSK_INTER_CUBIC ? 4 : 2;
-    if (ix + off >= 0 && iy + off >= 0 && ix + off + n <= a.src_cols && iy + off + n <= a.src_rows) {
-      const bool wtd = a.use_weights && job.weights != nullptr;
-      if (n == 4) interior_pixel_n<4>(a, tab, job, ix, fx, iy, fy, wtd, A, W);
-      else interior_pixel_n<2>(a, tab, job, ix, fx, iy, fy, wtd, A, W);
-      return;
-    }
-  }
   Img im;
   im.rows = a.src_rows; im.cols = a.src_cols;
   const bool weighted = a.use_weights && job.weights != nullptr;
@@ -223,6 +211,30 @@ __device__ __noinline__ void generic_pixel(const WarpAccArgs &a, const Tables &t
     const float I = sample_any(im, c, u, v, a.interp, a.border, a.bval[c], tab.cubic, tab.lanczos);
     A[c] = fmaf(I - A[c], factor, A[c]);
   }
+}
+
+// generic_pixel with the interior fast path in front: used by k_fused_generic only (multi-channel frames, projective maps).
+// The staged kernels keep calling generic_pixel itself for their rare fall-backs: their code and its layout stay as tuned
+// (routing them through this function cost the TMA kernel 5 %, measured).
+__device__ __forceinline__ void generic_pixel_fast(const WarpAccArgs &a, const Tables &tab, const FrameJob &job, int x, int y,
+                                                   float *A, float *W) {
+  if (a.interp == SSK_INTER_LINEAR || a.interp == SSK_INTER_CUBIC) {
+    const MapCoef m = job.map;
+    float u, v;
+    map_xy(m, (float)x, (float)y, u, v);
+    int ix, fx, iy, fy;
+    quant32(u, ix, fx);
+    quant32(v, iy, fy);
+    const int off = a.interp == SSK_INTER_CUBIC ? -1 : 0, n = a.interp == SSK_INTER_CUBIC ? 4 : 2;
+    if (ix + off >= 0 && iy + off >= 0 && ix + off + n <= a.src_cols && iy + off + n <= a.src_rows) {
+      if (!valid_eroded(m, a.interp, x, y, a.cols, a.rows, a.src_cols, a.src_rows, tab)) return;
+      const bool wtd = a.use_weights && job.weights != nullptr;
+      if (n == 4) interior_pixel_n<4>(a, tab, job, ix, fx, iy, fy, wtd, A, W);
+      else interior_pixel_n<2>(a, tab, job, ix, fx, iy, fy, wtd, A, W);
+      return;
+    }
+  }
+  generic_pixel(a, tab, job, x, y, A, W);
 }
 
 // ------------------------------------------------------------------------------------------------
