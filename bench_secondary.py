@@ -85,7 +85,7 @@ def run(args, peaks, ClockSampler):
 
     if cfg in (1, 3):
         if cfg == 1:
-            W, H, B, POOL = 640, 480, 500, 64
+            W, H, B, POOL = 640, 480, 2000, 64        # 20 steps = 40 000 frames: long enough for steady clocks
             frames, bpp = _planet_u16(POOL, W, H, seed=1)
             workload = "config#1: 640x480 mono16, ECC(forward-additive, translation, single level) + LINEAR/REFLECT101 remap + average"
             ro = api.registration_options(motion_type=capi.MOTION_TRANSLATION, interpolation=capi.INTER_LINEAR,
