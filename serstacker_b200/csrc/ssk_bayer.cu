@@ -20,16 +20,28 @@ namespace {
 constexpr int BTW = 32, BTH = 8;      // pixels per CTA (one pixel per thread)
 constexpr int BPLAN = 256;            // frames per launch (per-CTA table of tile flags)
 
+// current_remap at accumulator pixel (x, y): the analytic map, or flow + grid when c_eccflow refined it
+// (ecc_flow_to_remap, c_frame_registration.cc:900-917; same form as k_fused_flow's map_at)
+__device__ __forceinline__ void remap_at(const MapCoef &m, const float2 *flow, int x, int y, int src_cols, float &u, float &v) {
+  if (flow) {
+    const float2 d = __ldg(flow + (int64_t)y * src_cols + x);
+    u = __fadd_rn(d.x, (float)x); v = __fadd_rn(d.y, (float)y);
+  } else {
+    map_xy(m, (float)x, (float)y, u, v);
+  }
+}
+
 // pre-erosion flag of base_remap's mask at accumulator pixel (x, y)
-__device__ __forceinline__ bool flag_at(const MapCoef &m, int interp, int x, int y, int src_cols, int src_rows, const short *itab) {
+__device__ __forceinline__ bool flag_at(const MapCoef &m, const float2 *flow, int interp, int x, int y, int src_cols, int src_rows,
+                                        const short *itab) {
   float u, v;
-  map_xy(m, (float)x, (float)y, u, v);
+  remap_at(m, flow, x, y, src_cols, u, v);
   return valid255(interp, u, v, src_cols, src_rows, itab);
 }
 
 // mask(x, y) of base_remap: 5x5 erosion (border value 255: positions outside the image do not erode)
-__device__ __noinline__ bool mask_at(const MapCoef &m, int interp, int x, int y, int cols, int rows, int src_cols, int src_rows,
-                                     const short *itab) {
+__device__ __noinline__ bool mask_at(const MapCoef &m, const float2 *flow, int interp, int x, int y, int cols, int rows, int src_cols,
+                                     int src_rows, const short *itab) {
 #pragma unroll 1
   for (int dy = -2; dy <= 2; ++dy) {
     const int yy = y + dy;
@@ -38,7 +50,7 @@ __device__ __noinline__ bool mask_at(const MapCoef &m, int interp, int x, int y,
     for (int dx = -2; dx <= 2; ++dx) {
       const int xx = x + dx;
       if ((unsigned)xx >= (unsigned)cols) continue;
-      if (!flag_at(m, interp, xx, yy, src_cols, src_rows, itab)) return false;
+      if (!flag_at(m, flow, interp, xx, yy, src_cols, src_rows, itab)) return false;
     }
   }
   return true;
@@ -78,7 +90,7 @@ __global__ void __launch_bounds__(BTW * BTH) k_fused_bayer(const __grid_constant
   __shared__ signed char s_flag[BPLAN];
   const int bx0 = blockIdx.x * BTW, by0 = blockIdx.y * BTH;
   for (int jj = threadIdx.x; jj < a.njobs; jj += BTW * BTH)
-    s_flag[jj] = a.jobs[jj].ok ? (signed char)tile_safe(a.jobs[jj].map, bx0, by0, a) : (signed char)-1;
+    s_flag[jj] = a.jobs[jj].ok ? (signed char)(a.flow ? 0 : tile_safe(a.jobs[jj].map, bx0, by0, a)) : (signed char)-1;   // per-pixel maps: decide per pixel
   __syncthreads();
   const int x = bx0 + (threadIdx.x & 31), y = by0 + (threadIdx.x >> 5);
   if (x >= a.cols || y >= a.rows) return;
@@ -94,9 +106,10 @@ __global__ void __launch_bounds__(BTW * BTH) k_fused_bayer(const __grid_constant
     const int flag = s_flag[j];
     if (flag < 0) continue;                       // frame dropped by the registration
     const MapCoef &m = a.jobs[j].map;
-    if (!flag && !mask_at(m, a.interp, x, y, a.cols, a.rows, a.src_cols, a.src_rows, tab.cubic_itab)) continue;
+    const float2 *flow = a.flow ? a.flow + (int64_t)j * a.flow_stride : nullptr;
+    if (!flag && !mask_at(m, flow, a.interp, x, y, a.cols, a.rows, a.src_cols, a.src_rows, tab.cubic_itab)) continue;
     float u, v;
-    map_xy(m, (float)x, (float)y, u, v);
+    remap_at(m, flow, x, y, a.src_cols, u, v);
     const int sx = (int)u, sy = (int)v;           // truncation toward zero, as the reference's (int) cast
     if (!(sx >= 0 && sx < a.src_cols - 1 && sy >= 0 && sy < a.src_rows - 1)) continue;
     const double ax = (double)((float)(sx + 1) - u), ay = (double)((float)(sy + 1) - v);
@@ -136,6 +149,7 @@ int launch_bayer_warp_accumulate(const WarpAccArgs &a_in, const Tables &tab, int
   const int njobs = a.njobs;
   for (int j0 = 0; j0 < njobs; j0 += BPLAN) {
     a.jobs = jobs + j0; a.njobs = std::min(BPLAN, njobs - j0);
+    if (a_in.flow) a.flow = a_in.flow + (int64_t)j0 * a.flow_stride;
     if (a.depth == SSK_32F) k_fused_bayer<SSK_32F><<<grid, BTW * BTH, 0, s>>>(a, tab, pcode);
     else if (a.depth == SSK_16U) k_fused_bayer<SSK_16U><<<grid, BTW * BTH, 0, s>>>(a, tab, pcode);
     else if (a.depth == SSK_8U) k_fused_bayer<SSK_8U><<<grid, BTW * BTH, 0, s>>>(a, tab, pcode);

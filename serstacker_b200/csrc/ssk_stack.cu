@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include "ssk_engine.cuh"
 #include "ssk_eccflow.cuh"
+#include "ssk_nvtx.h"
 #include "ssk_upscale.cuh"
 
 using namespace ssk;
@@ -277,13 +278,11 @@ int ssk_stack_create(const ssk_stack_options *opts, ssk_stack **out) {
     SSK_REQUIRE(opts->bayer_colorid >= SSK_COLORID_BAYER_RGGB && opts->bayer_colorid <= SSK_COLORID_BAYER_BGGR,
                 "ssk_stack: bayer_average needs bayer_colorid RGGB / GRBG / GBRG / BGGR");
   SSK_REQUIRE(opts->sm_uscale >= 0 && opts->sm_uscale <= 12, "sharpness_measure.uscale 0..12");
-  SSK_REQUIRE(!(opts->enable_registration && opts->registration.enable_eccflow_registration && opts->accumulation_method == SSK_STACK_BAYER_AVERAGE),
-              "ssk_stack: eccflow registration with bayer_average is not implemented");
   SSK_REQUIRE(opts->upscale_option >= SSK_UPSCALE_NONE && opts->upscale_option <= SSK_UPSCALE_X30, "ssk_stack: upscale_option must be none / x2.0 / x1.5 / x3.0");
   if (opts->upscale_option != SSK_UPSCALE_NONE) {
     SSK_REQUIRE(opts->upscale_stage == SSK_UPSCALE_AFTER_ALIGN || opts->upscale_stage == 0,
                 "ssk_stack: only frame_upscale_after_align is fused into the loop (up-scale the frames with ssk_upscale_image for before_align)");
-    SSK_REQUIRE(opts->accumulation_method != SSK_STACK_BAYER_AVERAGE, "ssk_stack: up-scaling with bayer_average is not implemented");
+    SSK_REQUIRE(opts->accumulation_method != SSK_STACK_BAYER_AVERAGE, "ssk_stack: up-scaling with bayer_average: the reference hands the un-scaled current_remap and the up-scaled mask to c_bayer_average::add, which rejects the size mismatch (c_image_stacking_pipeline.cc:1633-1642, 1750-1751)");
   }
   ssk_stack *h = new (std::nothrow) ssk_stack();
   SSK_REQUIRE(h, "out of memory");
@@ -380,6 +379,8 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
   const int d = type_depth(h->type), cn = type_cn(h->type);
   const size_t rowb = (size_t)h->cols * cn * depth_bytes(d);
   cudaStream_t s = h->stream;
+  NvtxStage nvtx;
+  nvtx.next("ssk_stack: frame pointers");
   // copy (0 / 1) of the buffers the ring kernel reads; host-frame chunks join their ring kernel at once and stay on copy 0
   (void)last_in_call;
   const bool defer = set < 0 && h->side && !getenv("SSK_NO_SIDE_STREAM") && !getenv("SSK_NO_DEFERRED_RING");
@@ -432,6 +433,7 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
   SSK_CUDA(cudaEventRecord(h->ev[0], s));
 
   // ---- registration prep + ECC
+  nvtx.next("ssk_stack: registration prep");
   const bool weighted = h->o.accumulation_method == SSK_STACK_WEIGHTED_AVERAGE && h->o.sm_kradius > 0;
   const bool bayer = h->o.accumulation_method == SSK_STACK_BAYER_AVERAGE;
   if (h->o.enable_registration && bayer) {
@@ -453,6 +455,7 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
   SSK_CUDA(cudaEventRecord(h->ev[1], s));
 
   // ---- W1 weights on the unaligned frame
+  nvtx.next("ssk_stack: sharpness weights");
   if (weighted) {
     const float *const *Mptrs = nullptr;
     if (h->o.sm_dscale > 0 && std::min(h->rows, h->cols) >= 4) {
@@ -496,12 +499,14 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
   }
   SSK_CUDA(cudaEventRecord(h->ev[2], s));
 
+  nvtx.next("ssk_stack: register_frame (ECC)");
   if (h->o.enable_registration) {
     if (int e = h->reg_h.r.register_batch(n)) return e;
   }
   SSK_CUDA(cudaEventRecord(h->ev[3], s));
 
   // ---- fused warp + mask + weights + accumulate
+  nvtx.next("ssk_stack: warp + accumulate");
   k_fill_jobs<<<div_up(n, 128), 128, 0, s>>>(h->o.enable_registration ? h->reg_h.r.ecch.device_frames() : nullptr, d_frame_ptrs,
                                              weighted ? weight_ptrs : nullptr,
                                              weighted ? h->stats.as<double>() : nullptr, jobs, n,
@@ -530,7 +535,7 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
   a.acc = h->acc_h.a.acc.as<float>(); a.wacc = h->acc_h.a.wacc.as<float>();
   if (getenv("SSK_NO_TMA_KERNEL")) a.tmap_frames = a.tmap_weights = nullptr;   // tuning knob: cp.async kernel pair
   if (fused_tma_applicable(a)) a.side_stream = nullptr;                        // one launch over all tiles: nothing to fork
-  if (h->o.enable_registration && (h->reg_h.r.flow_enabled() || h->upscale != SSK_UPSCALE_NONE)) {
+  if (h->o.enable_registration && !bayer && (h->reg_h.r.flow_enabled() || h->upscale != SSK_UPSCALE_NONE)) {
     // per-pixel maps: _current_remap = c_eccflow's refinement of the ECC map (c_frame_registration.cc:900-917) and / or its
     // up-scaling (upscale_remap, c_image_stacking_pipeline.cc:1633-1642)
     if (h->reg_h.r.flow_enabled()) { a.flow = h->reg_h.r.flowh->uv(0); a.flow_stride = (int64_t)h->rows * h->cols; }
@@ -541,6 +546,8 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
     // samples through current_remap (c_image_stacking_pipeline.cc:1644-1651, 1730-1752)
     a.side_stream = nullptr;
     if (h->o.enable_registration) {
+      // with enable_eccflow_registration current_remap is the refined per-pixel map (c_frame_registration.cc:900-917)
+      if (h->reg_h.r.flow_enabled()) { a.flow = h->reg_h.r.flowh->uv(0); a.flow_stride = (int64_t)h->rows * h->cols; }
       if (int e = launch_bayer_warp_accumulate(a, h->tab, h->o.bayer_colorid, s)) return e;
     } else {
       // no registration: empty remap, no mask -> acc[cc] += src, cntr[cc] += 1 per pixel (c_frame_accumulation.cc:998-1010)

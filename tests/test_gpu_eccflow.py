@@ -287,3 +287,78 @@ def test_stack_with_eccflow_matches_oracle(gpu, acc, interp):
     avg_n, _, _, _ = opl.run_stacking(frames, so2)
     lap = lambda im: float(np.abs(cv2.Laplacian(im, cv2.CV_32F))[40:-40, 40:-40].mean())
     assert lap(avg_g) > lap(avg_n)
+
+
+
+def _bayer_turbulent_sequence(w, h, n, seed, amp=20.0, smooth=16.0):
+    """Raw RGGB frames (uint16) of a textured colour scene: per frame a small shift plus a smooth turbulence warp."""
+    rng = np.random.default_rng(seed)
+    base = cv2.GaussianBlur(rng.random((h + 40, w + 40)).astype(f32), (0, 0), 2.5)
+    base = (base - base.min()) / (base.max() - base.min())
+    yy, xx = np.mgrid[0:h, 0:w].astype(f32)
+    frames = []
+    for i in range(n):
+        tx, ty = (0.0, 0.0) if i == 0 else rng.normal(0.0, 1.5, 2)
+        du = dv = 0
+        if i:
+            du = cv2.GaussianBlur(rng.standard_normal((h, w)).astype(f32), (0, 0), smooth) * amp
+            dv = cv2.GaussianBlur(rng.standard_normal((h, w)).astype(f32), (0, 0), smooth) * amp
+        lum = cv2.remap(base, xx + 20 + f32(tx) + du, yy + 20 + f32(ty) + dv, cv2.INTER_CUBIC)
+        rgb = [0.15 + 0.70 * lum, 0.10 + 0.60 * lum, 0.20 + 0.45 * lum]
+        mosaic = np.empty((h, w), f32)
+        mosaic[0::2, 0::2] = rgb[0][0::2, 0::2]
+        mosaic[0::2, 1::2] = rgb[1][0::2, 1::2]
+        mosaic[1::2, 0::2] = rgb[1][1::2, 0::2]
+        mosaic[1::2, 1::2] = rgb[2][1::2, 1::2]
+        mosaic += rng.standard_normal(mosaic.shape).astype(f32) * f32(0.001)
+        frames.append(np.clip(np.rint(mosaic * 65535.0), 0, 65535).astype(np.uint16))
+    return frames, 16
+
+
+def test_stack_bayer_average_with_eccflow_matches_oracle(gpu):
+    """bayer_average with enable_eccflow_registration: the raw Bayer samples are gathered through the refined per-pixel
+    map c_eccflow left in current_remap (c_frame_registration.cc:900-917, c_image_stacking_pipeline.cc:1750-1751) under the
+    eroded mask of that map (k_fused_bayer with a flow field).  Two checks: (1) the gather itself is exact - the oracle's
+    accumulator fed with the DEVICE maps reproduces the device stack bit for bit; (2) against the oracle's own maps the
+    stack agrees to the eccflow envelope of the scene (printed)."""
+    from serstacker_b200 import api
+    from oracle import pipeline as opl, registration as oreg, accumulation as oacc
+    from oracle.debayer import debayer_nn2
+    frames, bpp = _bayer_turbulent_sequence(320, 224, 5, seed=41)
+    oo = _flow_registration_options(0, 3, cv2.INTER_LINEAR)
+    so = opl.StackingOptions(accumulation_method=opl.ACC_BAYER_AVERAGE)
+    so.registration = oo
+    avg_o, mask_o, _, _ = opl.run_bayer_stacking(frames, bpp, so, 8)
+    rkw = dict(motion_type=0, interpolation=cv2.INTER_LINEAR, enable_eccflow_registration=1, ecc=dict(ecc_method=3, ecch_max_level=-1))
+    p = api.c_image_stacking_pipeline(api.stack_options(registration=api.registration_options(**rkw), accumulation_method=2,
+                                                        bayer_colorid=8, max_batch=4))
+    p.set_reference(frames[0], bpp=bpp)
+    p.add_frames(frames)
+    avg_g, mask_g = p.compute()
+    assert p.accumulated_frames() == len(frames)
+    # (1) device maps through the oracle's accumulator
+    ro = oreg.FrameRegistration(oo)
+    rg = api.c_frame_registration(api.registration_options(**rkw))
+    bgr = [opl.to_float_frame(debayer_nn2(f, 8), bpp) for f in frames]
+    ro.setup_reference_frame(bgr[0], None)
+    rg.setup_reference_frame(bgr[0])
+    acc = oacc.BayerAverage()
+    acc.set_bayer_pattern(8)
+    dmap = 0.0
+    for f, raw in zip(bgr, frames):
+        assert rg.register_frame(f) and ro.register_frame(f, None)
+        mg = rg.current_remap()
+        dmap = max(dmap, float(np.abs(mg - ro.current_remap).max()))
+        _, mk = ro.custom_remap(mg, f, None, oo.interpolation, oo.border_mode, oo.border_value)
+        acc.set_remap(mg)
+        acc.add(opl.to_float_frame(raw, bpp), mk)
+    avg_x, mask_x = acc.compute()
+    assert np.array_equal(mask_g, mask_x) and np.array_equal(avg_g, avg_x)
+    # (2) against the oracle's own maps
+    m = (mask_o > 0) & (mask_g > 0)
+    rel = float(np.sqrt(((avg_g[m] - avg_o[m]) ** 2).sum()) / np.sqrt((avg_o[m] ** 2).sum()))
+    mism = float((mask_o != mask_g).mean())
+    print("  bayer stack with eccflow: gather exact; max |d map| = %.3g px, rel-L2 vs the oracle's own maps = %.3g, mask mismatch %.3g"
+          % (dmap, rel, mism))
+    assert rel <= 1e-4
+    assert mism < 1e-3
