@@ -97,8 +97,16 @@ __global__ void __launch_bounds__(BTW * BTH) k_fused_bayer(const __grid_constant
   const int64_t p = ((int64_t)y * a.cols + x) * 3;
   float A[3] = {a.acc[p], a.acc[p + 1], a.acc[p + 2]};
   float N[3] = {a.wacc[p], a.wacc[p + 1], a.wacc[p + 2]};
-  // the pattern table only covers the even-sized part of the image; elsewhere it reads 0 (c_frame_accumulation.cc:1262-1334)
-  const int prow = a.src_rows & ~1, pcol = a.src_cols & ~1;
+  // positions (row parity, column parity) of R and B in the 2x2 cell, column parity of G on even rows (frame sizes are even,
+  // so the pattern table of c_frame_accumulation.cc:1262-1334 covers every sample)
+  int rR = 0, cR = 0, rB = 0, cB = 0, cg0 = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int cc = (int)((pcode >> (2 * q)) & 3u);
+    if (cc == 2) { rR = q >> 1; cR = q & 1; }
+    if (cc == 0) { rB = q >> 1; cB = q & 1; }
+    if (cc == 1 && (q >> 1) == 0) cg0 = q & 1;
+  }
   Img im;
   im.data = nullptr; im.step = a.src_step; im.rows = a.src_rows; im.cols = a.src_cols; im.depth = DEPTH; im.cn = 1; im.scale = a.scale;
 #pragma unroll 1
@@ -114,19 +122,23 @@ __global__ void __launch_bounds__(BTW * BTH) k_fused_bayer(const __grid_constant
     if (!(sx >= 0 && sx < a.src_cols - 1 && sy >= 0 && sy < a.src_rows - 1)) continue;
     const double ax = (double)((float)(sx + 1) - u), ay = (double)((float)(sy + 1) - v);
     const double bx = (double)(u - (float)sx), by = (double)(v - (float)sy);
-    const double sw[4] = {ax * ay, bx * ay, ax * by, bx * by};
     im.data = a.jobs[j].frame;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int yy = sy + (k >> 1), xx = sx + (k & 1);
-      const int q = ((yy & 1) << 1) | (xx & 1);
-      const int cc = (yy < prow && xx < pcol) ? (int)((pcode >> (2 * q)) & 3u) : 0;
-      const double s = (double)load_px<DEPTH>(im, yy, xx, 0);
-      const double an = (double)(cc == 0 ? A[0] : cc == 1 ? A[1] : A[2]) + s * sw[k];
-      const double nn = (double)(cc == 0 ? N[0] : cc == 1 ? N[1] : N[2]) + sw[k];
-      const float af = (float)an, nf = (float)nn;
-      if (cc == 0) { A[0] = af; N[0] = nf; } else if (cc == 1) { A[1] = af; N[1] = nf; } else { A[2] = af; N[2] = nf; }
-    }
+    // The 2x2 footprint holds one R, one B and two G samples whatever the parity of (sx, sy).  The reference walks the taps
+    // in the order 00, 01, 10, 11 and updates the channel of each; channels do not interact, so only the order of the two G
+    // updates matters: the G of the top row first.  Walking by channel instead of by tap keeps the updates free of per-lane
+    // channel selects (the tap-order form compiled to three predicated copies of every conversion).
+    auto update = [&](float &Ac, float &Nc, int dy, int dx) {
+      const double w = (dx ? bx : ax) * (dy ? by : ay);
+      const double sv = (double)load_px<DEPTH>(im, sy + dy, sx + dx, 0);
+      const double an = (double)Ac + sv * w;
+      const double nn = (double)Nc + w;
+      Ac = (float)an; Nc = (float)nn;
+    };
+    const int gdx = (sx ^ cg0 ^ sy) & 1;                      // column offset of the G sample in row sy
+    update(A[1], N[1], 0, gdx);
+    update(A[1], N[1], 1, gdx ^ 1);
+    update(A[2], N[2], (sy ^ rR) & 1, (sx ^ cR) & 1);
+    update(A[0], N[0], (sy ^ rB) & 1, (sx ^ cB) & 1);
   }
   a.acc[p] = A[0]; a.acc[p + 1] = A[1]; a.acc[p + 2] = A[2];
   a.wacc[p] = N[0]; a.wacc[p + 1] = N[1]; a.wacc[p + 2] = N[2];
@@ -142,6 +154,7 @@ int launch_bayer_warp_accumulate(const WarpAccArgs &a_in, const Tables &tab, int
               "bayer_warp_accumulate: interpolation must be NEAREST, LINEAR or CUBIC");
   SSK_REQUIRE(a.cn == 1, "bayer_warp_accumulate: raw Bayer frames have one channel");
   SSK_REQUIRE(a.rows == a.src_rows && a.cols == a.src_cols, "bayer_warp_accumulate: accumulator and frame sizes differ");
+  SSK_REQUIRE(!(a.src_rows & 1) && !(a.src_cols & 1), "bayer_warp_accumulate: frame size must be even");
   SSK_REQUIRE(colorid >= SSK_COLORID_BAYER_RGGB && colorid <= SSK_COLORID_BAYER_BGGR, "bayer_warp_accumulate: RGGB/GRBG/GBRG/BGGR");
   const unsigned pcode = pattern_code(colorid);
   const dim3 grid(div_up(a.cols, BTW), div_up(a.rows, BTH));
