@@ -120,6 +120,115 @@ void run_debayer(const void *src, int64_t sstep, int rows, int cols, int ry, int
   k_debayer_nn2<T><<<grid, 256, 0, s>>>(static_cast<const T *>(src), sstep, rows, cols, ry, rx, static_cast<T *>(dst), dstep);
 }
 
+
+// ---- debayer_nn2 -> BGR2GRAY -> cv::pyrDown in one pass ------------------------------------------------------------
+// The registration side of the bayer_average loop (read_input_frame's debayer, extract_channel gray, scaleImage's pyrDown at
+// ecc.scale 0.5: c_image_stacking_pipeline_base.cc:221-236, c_frame_registration.cc:203-250) only needs the half-size gray
+// ECC image, so the demosaiced BGR frame (3 samples written and read back per raw sample) is never formed: a CTA demosaics the
+// gray window of its 64 x 16 output tile into shared memory - one thread per 2 x 2 Bayer cell, the cell's 4 x 4 raw neighbourhood
+// in registers - and applies pyrDown's 5 x 5 from there.  Same arithmetic as k_debayer_nn2 -> load_gray -> k_pyrdown (integer
+// rounding of the demosaic, sample * 1/(1 << bpp), the gray FMAs, pyrDown's operand orders), so the result is bit-identical.
+constexpr int BP_OW = 64, BP_OH = 16, BP_RPT = 4;
+constexpr int BP_GH = 2 * BP_OH + 4, BP_GW = 2 * BP_OW + 4;     // gray window, cell-aligned: rows 2 oy0 - 2 ... 2 oy0 + 33
+
+template <class T> __device__ __forceinline__ float sample_f(T v, float scale) { return __fmul_rn((float)v, scale); }
+template <> __device__ __forceinline__ float sample_f<float>(float v, float) { return v; }
+
+// BGR of the pixel at the centre of the 3 x 3 window w (rows / columns already border-mapped), parities (py, px)
+template <class T>
+__device__ __forceinline__ float debayer_gray(const typename Wide<T>::type (&w)[3][3], int py, int px, int ry, int rx, float scale) {
+  const bool is_r = py == ry && px == rx, is_b = py != ry && px != rx;
+  T r, g, b;
+  if (is_r || is_b) {
+    const T diag = avg4<T>(w[0][0], w[0][2], w[2][0], w[2][2]);
+    g = avg4<T>(w[0][1], w[1][0], w[1][2], w[2][1]);
+    r = is_r ? (T)w[1][1] : diag;
+    b = is_r ? diag : (T)w[1][1];
+  } else {
+    const T vert = avg2<T>(w[0][1], w[2][1]);
+    const T horz = avg2<T>(w[1][0], w[1][2]);
+    g = (T)w[1][1];
+    const bool on_r_row = py == ry;
+    r = on_r_row ? horz : vert;
+    b = on_r_row ? vert : horz;
+  }
+  return bgr2gray(sample_f<T>(b, scale), sample_f<T>(g, scale), sample_f<T>(r, scale));
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) k_bayer_gray_pyrdown(const void *const *__restrict__ src_ptrs, int64_t sstep, int rows, int cols,
+                                                            int ry, int rx, float scale, float *const *__restrict__ dst_ptrs,
+                                                            int dst_rows, int dst_cols) {
+  typedef typename Wide<T>::type W;
+  __shared__ float sg[BP_GH][BP_GW + 1];
+  const char *src = static_cast<const char *>(src_ptrs[blockIdx.z]);
+  float *dst = dst_ptrs[blockIdx.z];
+  const int gx0 = 2 * (int)blockIdx.x * BP_OW - 2, gy0 = 2 * (int)blockIdx.y * BP_OH - 2;   // even
+  auto row_ptr = [&](int y) { return reinterpret_cast<const T *>(src + (int64_t)y * sstep); };
+  // ---- gray window, one 2 x 2 cell per thread and pass
+  for (int c = threadIdx.x; c < (BP_GH / 2) * (BP_GW / 2); c += 256) {
+    const int cy = c / (BP_GW / 2), cx = c - cy * (BP_GW / 2);
+    const int y0 = gy0 + 2 * cy, x0 = gx0 + 2 * cx;
+    if (y0 >= 0 && y0 + 1 < rows && x0 >= 0 && x0 + 1 < cols) {
+      // debayer_nn2's own border rule for the neighbourhood: row / column -1 -> 1, N -> N - 2
+      const int yy[4] = {y0 == 0 ? 1 : y0 - 1, y0, y0 + 1, y0 + 2 == rows ? rows - 2 : y0 + 2};
+      const int xx[4] = {x0 == 0 ? 1 : x0 - 1, x0, x0 + 1, x0 + 2 == cols ? cols - 2 : x0 + 2};
+      W q[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const T *rp = row_ptr(yy[i]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) q[i][k] = (W)__ldg(rp + xx[k]);
+      }
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          W w[3][3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) w[i][k] = q[dy + i][dx + k];
+          sg[2 * cy + dy][2 * cx + dx] = debayer_gray<T>(w, dy, dx, ry, rx, scale);      // y0, x0 are even
+        }
+    } else {
+      // positions outside the frame: cv::pyrDown's BORDER_REFLECT101 of the gray image, pixel by pixel
+#pragma unroll 1
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const int y = border_idx(y0 + (k4 >> 1), rows, SSK_BORDER_REFLECT101), x = border_idx(x0 + (k4 & 1), cols, SSK_BORDER_REFLECT101);
+        const int yy[3] = {y == 0 ? 1 : y - 1, y, y == rows - 1 ? rows - 2 : y + 1};
+        const int xx[3] = {x == 0 ? 1 : x - 1, x, x == cols - 1 ? cols - 2 : x + 1};
+        W w[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) w[i][k] = (W)__ldg(row_ptr(yy[i]) + xx[k]);
+        sg[2 * cy + (k4 >> 1)][2 * cx + (k4 & 1)] = debayer_gray<T>(w, y & 1, x & 1, ry, rx, scale);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- pyrDown from the window (k_pyrdown's forms: ssk_prep.cu)
+  const int lx = threadIdx.x & (BP_OW - 1), ly0 = (threadIdx.x / BP_OW) * BP_RPT;
+  const int ox = blockIdx.x * BP_OW + lx, oy0 = blockIdx.y * BP_OH + ly0;
+  if (ox >= dst_cols || oy0 >= dst_rows) return;
+  const int width0 = min((cols - 3) / 2 + 1, dst_cols);
+  const bool hsimd = ox >= 1 && ox < 1 + 4 * ((width0 - 1) / 4);
+  const bool vsimd = ox < (dst_cols & ~3);
+  constexpr int NR = 2 * BP_RPT + 3;
+  float h[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const float *g = &sg[2 * ly0 + r][2 * lx];
+    h[r] = pd_hform(g[0], g[1], g[2], g[3], g[4], hsimd);
+  }
+#pragma unroll
+  for (int j = 0; j < BP_RPT; ++j) {
+    if (oy0 + j >= dst_rows) break;
+    dst[(int64_t)(oy0 + j) * dst_cols + ox] = pd_vform(h[2 * j], h[2 * j + 1], h[2 * j + 2], h[2 * j + 3], h[2 * j + 4], vsimd);
+  }
+}
+
 }  // namespace
 
 int launch_debayer_nn2(const void *src, int64_t sstep, int depth, int rows, int cols, int colorid, void *dst, int64_t dstep,
@@ -137,6 +246,30 @@ int launch_debayer_nn2(const void *src, int64_t sstep, int depth, int rows, int 
   else if (depth == SSK_16U) run_debayer<uint16_t>(src, sstep, rows, cols, ry, rx, dst, dstep, s);
   else if (depth == SSK_32F) run_debayer<float>(src, sstep, rows, cols, ry, rx, dst, dstep, s);
   else { set_error("debayer_nn2: CV_8U, CV_16U or CV_32F"); return SSK_ERR_INVALID; }
+  SSK_LAUNCH_CHECK();
+  return SSK_OK;
+}
+
+// batched: src_ptrs[b] raw Bayer frames (rows x cols, one channel, `depth`), dst_ptrs[b] dense CV_32FC1 images of
+// ((rows + 1) / 2) x ((cols + 1) / 2): pyrDown(gray(debayer_nn2(raw) * scale))
+int launch_bayer_gray_pyrdown(const void *const *src_ptrs, int64_t sstep, int depth, int rows, int cols, int colorid, float scale,
+                              float *const *dst_ptrs, int batch, cudaStream_t s) {
+  SSK_REQUIRE(!(rows & 1) && !(cols & 1), "debayer_nn2: Can not make debayer for uneven image size");
+  SSK_REQUIRE(rows >= 4 && cols >= 4, "bayer_gray_pyrdown: frame too small");
+  int ry, rx;
+  switch (colorid) {
+    case SSK_COLORID_BAYER_RGGB: ry = 0; rx = 0; break;
+    case SSK_COLORID_BAYER_GRBG: ry = 0; rx = 1; break;
+    case SSK_COLORID_BAYER_GBRG: ry = 1; rx = 0; break;
+    case SSK_COLORID_BAYER_BGGR: ry = 1; rx = 1; break;
+    default: set_error("debayer_nn2: unsupported colorid (RGGB, GRBG, GBRG, BGGR)"); return SSK_ERR_INVALID;
+  }
+  const int dr = (rows + 1) / 2, dc = (cols + 1) / 2;
+  const dim3 grid(div_up(dc, BP_OW), div_up(dr, BP_OH), batch);
+  if (depth == SSK_8U) k_bayer_gray_pyrdown<uint8_t><<<grid, 256, 0, s>>>(src_ptrs, sstep, rows, cols, ry, rx, scale, dst_ptrs, dr, dc);
+  else if (depth == SSK_16U) k_bayer_gray_pyrdown<uint16_t><<<grid, 256, 0, s>>>(src_ptrs, sstep, rows, cols, ry, rx, scale, dst_ptrs, dr, dc);
+  else if (depth == SSK_32F) k_bayer_gray_pyrdown<float><<<grid, 256, 0, s>>>(src_ptrs, sstep, rows, cols, ry, rx, scale, dst_ptrs, dr, dc);
+  else { set_error("bayer_gray_pyrdown: CV_8U, CV_16U or CV_32F"); return SSK_ERR_INVALID; }
   SSK_LAUNCH_CHECK();
   return SSK_OK;
 }

@@ -570,11 +570,19 @@ int Reg::setup_reference(const Img &frame, const uint8_t *d_mask, int64_t mask_s
   return SSK_OK;
 }
 
+int Reg::reserve_batch(int batch) {
+  SSK_REQUIRE(ecch.have_reference, "c_frame_registration: setup_reference_frame() must be called first");
+  return ecch.reserve(batch);
+}
+
 int Reg::prepare(const Img &geom, const void *const *d_frame_ptrs, int batch, const uint8_t *d_mask, int64_t mask_step) {
   SSK_REQUIRE(ecch.have_reference, "c_frame_registration: setup_reference_frame() must be called first");
   SSK_REQUIRE(geom.rows == ref_rows && geom.cols == ref_cols, "current frame size differs from the reference frame size");
   if (int e = ecch.reserve(batch)) return e;
-  if (int e = scale_to_ecc_image(opts, geom, d_frame_ptrs, nullptr, ecch.level0_scratch_ptrs(), ecc_rows, ecc_cols, batch, stream)) return e;
+  const bool scaled = ecc_images_ready;
+  ecc_images_ready = false;
+  if (scaled) SSK_REQUIRE(!flow_enabled(), "internal: pre-scaled ECC images with eccflow (needs the full-size frame)");
+  else if (int e = scale_to_ecc_image(opts, geom, d_frame_ptrs, nullptr, ecch.level0_scratch_ptrs(), ecc_rows, ecc_cols, batch, stream)) return e;
   const uint8_t *d_ecc_mask = nullptr;
   if (d_mask) {
     // scaleImage of the current mask (c_frame_registration.cc:230-250): pyrDown(mask) >= 250 for ecc.scale 0.5, as is for 1

@@ -180,6 +180,11 @@ class Reg {
   // frames (device, common geometry) -> ECC images -> pyramids.  d_frame_ptrs: device array of frame pointers.
   // d_mask / mask_step: full-resolution CV_8UC1 mask of the (single) current frame on the device, or null
   int prepare(const Img &geom, const void *const *d_frame_ptrs, int batch, const uint8_t *d_mask = nullptr, int64_t mask_step = 0);
+  // bayer_average loop: reserve the batch's slots so that the caller can write the scaled ECC images of raw Bayer frames
+  // straight into ecch.level0_scratch_ptrs() (launch_bayer_gray_pyrdown), then prepare(geom, nullptr, batch) with
+  // ecc_images_ready set skips scaleImage
+  int reserve_batch(int batch);
+  bool ecc_images_ready = false;
   int register_batch(int batch);       // launches the ECC kernel; results in ecch.device_frames()
 };
 

@@ -21,7 +21,7 @@ __device__ __forceinline__ float load_gray(const Img &im, int y, int x) {
   if (im.cn == 1) return load_px<DEPTH>(im, y, x, 0);
   // cv::cvtColor(COLOR_BGR2GRAY) on float data: 0.114 B + 0.587 G + 0.299 R
   const float b = load_px<DEPTH>(im, y, x, 0), g = load_px<DEPTH>(im, y, x, 1), r = load_px<DEPTH>(im, y, x, 2);
-  return fmaf(r, 0.299f, fmaf(g, 0.587f, b * 0.114f));
+  return bgr2gray(b, g, r);
 }
 
 // Visits the (ih x iw) elements of a CTA tile with one warp per row and lanes along x (coalesced, no div/mod).
@@ -42,10 +42,7 @@ constexpr int PD_OW = 64, PD_OH = 16, PD_RPT = 4;   // CTA tile (outputs) and ou
 // One thread owns one output column and PD_RPT consecutive output rows: it forms the 2*PD_RPT+3 horizontally
 // filtered input rows in registers (interior: three 8-byte loads per row, coalesced across the warp) and then the
 // vertical taps.  No shared memory, no barrier.
-__device__ __forceinline__ float pd_hform(float p0, float p1, float p2, float p3, float p4, bool simd) {
-  const float a1 = __fmul_rn(__fadd_rn(p1, p3), 4.f), c6 = __fmul_rn(p2, 6.f);
-  return simd ? __fadd_rn(c6, __fadd_rn(a1, __fadd_rn(p0, p4))) : __fadd_rn(__fadd_rn(__fadd_rn(c6, a1), p0), p4);
-}
+// (pd_hform / pd_vform: ssk_prep.cuh)
 
 template <int DEPTH>
 __global__ void __launch_bounds__(256) k_pyrdown(const PyrDownArgs a) {
@@ -91,11 +88,7 @@ __global__ void __launch_bounds__(256) k_pyrdown(const PyrDownArgs a) {
   for (int j = 0; j < PD_RPT; ++j) {
     if (oy0 + j >= a.dst_rows) break;
     const float r0 = h[2 * j], r1 = h[2 * j + 1], r2 = h[2 * j + 2], r3 = h[2 * j + 3], r4 = h[2 * j + 4];
-    const float a13 = __fadd_rn(r1, r3);
-    float v;
-    if (vsimd) v = __fadd_rn(__fmul_rn(__fadd_rn(a13, r2), 4.f), __fadd_rn(__fadd_rn(r0, r4), __fadd_rn(r2, r2)));
-    else v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2, 6.f), __fmul_rn(a13, 4.f)), r0), r4);
-    v = __fmul_rn(v, 1.0f / 256.0f);
+    float v = pd_vform(r0, r1, r2, r3, r4, vsimd);
     if (a.post_scale != 1.f) v = __fmul_rn(v, a.post_scale);
     dst[(int64_t)(oy0 + j) * a.dst_cols + ox] = v;
   }

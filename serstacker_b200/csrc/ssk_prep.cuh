@@ -21,6 +21,24 @@ struct PyrDownArgs {
 };
 int launch_pyrdown(const PyrDownArgs &a, cudaStream_t s);
 
+#ifdef __CUDACC__
+// cv::cvtColor(COLOR_BGR2GRAY) on float data: 0.114 B + 0.587 G + 0.299 R (the gray load of the prep kernels)
+__device__ __forceinline__ float bgr2gray(float b, float g, float r) { return fmaf(r, 0.299f, fmaf(g, 0.587f, b * 0.114f)); }
+// cv::pyrDown's 1-4-6-4-1 forms as cv2 4.13 evaluates them (see k_pyrdown, ssk_prep.cu): `simd` selects the operand order of
+// the vectorised loop, otherwise the scalar tail's.  pd_vform includes the final 1/256.
+__device__ __forceinline__ float pd_hform(float p0, float p1, float p2, float p3, float p4, bool simd) {
+  const float a1 = __fmul_rn(__fadd_rn(p1, p3), 4.f), c6 = __fmul_rn(p2, 6.f);
+  return simd ? __fadd_rn(c6, __fadd_rn(a1, __fadd_rn(p0, p4))) : __fadd_rn(__fadd_rn(__fadd_rn(c6, a1), p0), p4);
+}
+__device__ __forceinline__ float pd_vform(float r0, float r1, float r2, float r3, float r4, bool simd) {
+  const float a13 = __fadd_rn(r1, r3);
+  float v;
+  if (simd) v = __fadd_rn(__fmul_rn(__fadd_rn(a13, r2), 4.f), __fadd_rn(__fadd_rn(r0, r4), __fadd_rn(r2, r2)));
+  else v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2, 6.f), __fmul_rn(a13, 4.f)), r0), r4);
+  return __fmul_rn(v, 1.0f / 256.0f);
+}
+#endif
+
 // cv::resize(INTER_AREA) for down-scaling (scale >= 1 in both axes), single-channel fp32 result (colour / integer frames go
 // through the same gray load as pyrDown): scaleImage's branch for ecc.scale != 0.5 (c_frame_registration.cc:242-247).
 // inv_scale_x/y are cv::resize's inv_scale_* (fx, fy when dsize was derived from them, else dsize / ssize).
@@ -111,6 +129,9 @@ int launch_add_weighted(const float *src, double alpha, const float *lpass, doub
 // same depth; both images on the device.
 int launch_debayer_nn2(const void *src, int64_t sstep, int depth, int rows, int cols, int colorid, void *dst, int64_t dstep,
                        cudaStream_t s);
+// debayer_nn2 -> BGR2GRAY -> cv::pyrDown fused (the ECC image of a raw Bayer frame at ecc.scale 0.5), bit-identical to the chain
+int launch_bayer_gray_pyrdown(const void *const *src_ptrs, int64_t sstep, int depth, int rows, int cols, int colorid, float scale,
+                              float *const *dst_ptrs, int batch, cudaStream_t s);
 
 // average_pyramid_inpaint (core/proc/inpaint/average_pyramid_inpaint.cc:97-127; ssk_inpaint.cu).  src: CV_32F with `cn`
 // interleaved channels, mask: CV_8UC1 (both on the device, any step); dst / dstmask dense; `work` holds

@@ -440,15 +440,25 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
     // read_input_frame: debayer(raw) keeps the depth, the registration sees the demosaiced frame
     // (c_image_stacking_pipeline_base.cc:221-236, 271-276); the raw samples go to the accumulator below
     const size_t bstep = rowb * 3, bgr_bytes = bstep * h->rows;
-    for (int i = 0; i < n; ++i) {
-      const void *src = set >= 0 ? (const void *)(h->frame_slots.as<char>() + rowb * h->rows * ((size_t)set * h->host_chunk + i)) : frames[i].data;
-      const int64_t sstep = set >= 0 ? (int64_t)rowb : frames[i].step;
-      if (int e = launch_debayer_nn2(src, sstep, d, h->rows, h->cols, h->o.bayer_colorid, h->bgr_slots.as<char>() + bgr_bytes * i,
-                                     (int64_t)bstep, s)) return e;
-    }
     Img g3 = geom;
     g3.cn = 3; g3.step = (int64_t)bstep;
-    if (int e = h->reg_h.r.prepare(g3, h->d_bgr_ptrs.as<const void *>(), n)) return e;
+    if (h->reg_h.r.scaled_by_pyrdown() && !h->reg_h.r.flow_enabled() && h->rows >= 4 && h->cols >= 4 && !getenv("SSK_NO_BAYER_PYRDOWN")) {
+      // ecc.scale 0.5: the registration only needs pyrDown(gray(debayer(raw))): one pass from the raw samples, the BGR frame
+      // is never formed (bit-identical to the chain below)
+      if (int e = h->reg_h.r.reserve_batch(n)) return e;
+      if (int e = launch_bayer_gray_pyrdown(d_frame_ptrs, geom.step, d, h->rows, h->cols, h->o.bayer_colorid, geom.scale,
+                                            h->reg_h.r.ecch.level0_scratch_ptrs(), n, s)) return e;
+      h->reg_h.r.ecc_images_ready = true;
+      if (int e = h->reg_h.r.prepare(g3, nullptr, n)) return e;
+    } else {
+      for (int i = 0; i < n; ++i) {
+        const void *src = set >= 0 ? (const void *)(h->frame_slots.as<char>() + rowb * h->rows * ((size_t)set * h->host_chunk + i)) : frames[i].data;
+        const int64_t sstep = set >= 0 ? (int64_t)rowb : frames[i].step;
+        if (int e = launch_debayer_nn2(src, sstep, d, h->rows, h->cols, h->o.bayer_colorid, h->bgr_slots.as<char>() + bgr_bytes * i,
+                                       (int64_t)bstep, s)) return e;
+      }
+      if (int e = h->reg_h.r.prepare(g3, h->d_bgr_ptrs.as<const void *>(), n)) return e;
+    }
   } else if (h->o.enable_registration) {
     if (int e = h->reg_h.r.prepare(geom, d_frame_ptrs, n)) return e;
   }
