@@ -129,7 +129,9 @@ void run_debayer(const void *src, int64_t sstep, int rows, int cols, int ry, int
 // in registers - and applies pyrDown's 5 x 5 from there.  Same arithmetic as k_debayer_nn2 -> load_gray -> k_pyrdown (integer
 // rounding of the demosaic, sample * 1/(1 << bpp), the gray FMAs, pyrDown's operand orders), so the result is bit-identical.
 constexpr int BP_OW = 64, BP_OH = 16, BP_RPT = 4;
-constexpr int BP_GH = 2 * BP_OH + 4, BP_GW = 2 * BP_OW + 4;     // gray window, cell-aligned: rows 2 oy0 - 2 ... 2 oy0 + 33
+constexpr int BP_UH = BP_OH + 2, BP_UW = BP_OW / 2 + 2;        // units of 2 rows x 4 columns covering the gray window
+constexpr int BP_GH = 2 * BP_UH, BP_GW = 4 * BP_UW;            // rows 2 oy0 - 2 ..., columns 2 ox0 - 4 ... (4-sample aligned)
+constexpr int BP_NIT = (BP_UH * BP_UW + 255) / 256;
 
 template <class T> __device__ __forceinline__ float sample_f(T v, float scale) { return __fmul_rn((float)v, scale); }
 template <> __device__ __forceinline__ float sample_f<float>(float v, float) { return v; }
@@ -155,7 +157,7 @@ __device__ __forceinline__ float debayer_gray(const typename Wide<T>::type (&w)[
   return bgr2gray(sample_f<T>(b, scale), sample_f<T>(g, scale), sample_f<T>(r, scale));
 }
 
-template <class T>
+template <class T, bool VEC>
 __global__ void __launch_bounds__(256) k_bayer_gray_pyrdown(const void *const *__restrict__ src_ptrs, int64_t sstep, int rows, int cols,
                                                             int ry, int rx, float scale, float *const *__restrict__ dst_ptrs,
                                                             int dst_rows, int dst_cols) {
@@ -163,39 +165,52 @@ __global__ void __launch_bounds__(256) k_bayer_gray_pyrdown(const void *const *_
   __shared__ float sg[BP_GH][BP_GW + 1];
   const char *src = static_cast<const char *>(src_ptrs[blockIdx.z]);
   float *dst = dst_ptrs[blockIdx.z];
-  const int gx0 = 2 * (int)blockIdx.x * BP_OW - 2, gy0 = 2 * (int)blockIdx.y * BP_OH - 2;   // even
+  const int gx0 = 2 * (int)blockIdx.x * BP_OW - 4, gy0 = 2 * (int)blockIdx.y * BP_OH - 2;   // multiples of 4 / 2
   auto row_ptr = [&](int y) { return reinterpret_cast<const T *>(src + (int64_t)y * sstep); };
-  // ---- gray window, one 2 x 2 cell per thread and pass
-  for (int c = threadIdx.x; c < (BP_GH / 2) * (BP_GW / 2); c += 256) {
-    const int cy = c / (BP_GW / 2), cx = c - cy * (BP_GW / 2);
-    const int y0 = gy0 + 2 * cy, x0 = gx0 + 2 * cx;
-    if (y0 >= 0 && y0 + 1 < rows && x0 >= 0 && x0 + 1 < cols) {
+  // ---- gray window: one unit of 2 rows x 4 columns (two Bayer cells) per thread and pass, its 4 x 6 raw neighbourhood in
+  // registers (VEC: one aligned 4-sample load + the two neighbours per row); the passes are unrolled so that the loads of
+  // all of a thread's units are in flight together
+#pragma unroll
+  for (int it = 0; it < BP_NIT; ++it) {
+    const int c = threadIdx.x + it * 256;
+    if (c >= BP_UH * BP_UW) break;
+    const int uy = c / BP_UW, ux = c - uy * BP_UW;
+    const int y0 = gy0 + 2 * uy, x0 = gx0 + 4 * ux;
+    if (y0 >= 0 && y0 + 1 < rows && x0 >= 0 && x0 + 3 < cols) {
       // debayer_nn2's own border rule for the neighbourhood: row / column -1 -> 1, N -> N - 2
       const int yy[4] = {y0 == 0 ? 1 : y0 - 1, y0, y0 + 1, y0 + 2 == rows ? rows - 2 : y0 + 2};
-      const int xx[4] = {x0 == 0 ? 1 : x0 - 1, x0, x0 + 1, x0 + 2 == cols ? cols - 2 : x0 + 2};
-      W q[4][4];
+      const int xm = x0 == 0 ? 1 : x0 - 1, xp = x0 + 4 == cols ? cols - 2 : x0 + 4;
+      W q[4][6];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const T *rp = row_ptr(yy[i]);
+        if (VEC) {
+          const Pack<T, 4> v = *reinterpret_cast<const Pack<T, 4> *>(rp + x0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) q[i][k] = (W)__ldg(rp + xx[k]);
+          for (int k = 0; k < 4; ++k) q[i][k + 1] = (W)v.v[k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) q[i][k + 1] = (W)__ldg(rp + x0 + k);
+        }
+        q[i][0] = (W)__ldg(rp + xm);
+        q[i][5] = (W)__ldg(rp + xp);
       }
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
+        for (int dx = 0; dx < 4; ++dx) {
           W w[3][3];
 #pragma unroll
           for (int i = 0; i < 3; ++i)
 #pragma unroll
             for (int k = 0; k < 3; ++k) w[i][k] = q[dy + i][dx + k];
-          sg[2 * cy + dy][2 * cx + dx] = debayer_gray<T>(w, dy, dx, ry, rx, scale);      // y0, x0 are even
+          sg[2 * uy + dy][4 * ux + dx] = debayer_gray<T>(w, dy, dx & 1, ry, rx, scale);      // y0 is even, x0 a multiple of 4
         }
     } else {
       // positions outside the frame: cv::pyrDown's BORDER_REFLECT101 of the gray image, pixel by pixel
 #pragma unroll 1
-      for (int k4 = 0; k4 < 4; ++k4) {
-        const int y = border_idx(y0 + (k4 >> 1), rows, SSK_BORDER_REFLECT101), x = border_idx(x0 + (k4 & 1), cols, SSK_BORDER_REFLECT101);
+      for (int k8 = 0; k8 < 8; ++k8) {
+        const int y = border_idx(y0 + (k8 >> 2), rows, SSK_BORDER_REFLECT101), x = border_idx(x0 + (k8 & 3), cols, SSK_BORDER_REFLECT101);
         const int yy[3] = {y == 0 ? 1 : y - 1, y, y == rows - 1 ? rows - 2 : y + 1};
         const int xx[3] = {x == 0 ? 1 : x - 1, x, x == cols - 1 ? cols - 2 : x + 1};
         W w[3][3];
@@ -203,12 +218,12 @@ __global__ void __launch_bounds__(256) k_bayer_gray_pyrdown(const void *const *_
         for (int i = 0; i < 3; ++i)
 #pragma unroll
           for (int k = 0; k < 3; ++k) w[i][k] = (W)__ldg(row_ptr(yy[i]) + xx[k]);
-        sg[2 * cy + (k4 >> 1)][2 * cx + (k4 & 1)] = debayer_gray<T>(w, y & 1, x & 1, ry, rx, scale);
+        sg[2 * uy + (k8 >> 2)][4 * ux + (k8 & 3)] = debayer_gray<T>(w, y & 1, x & 1, ry, rx, scale);
       }
     }
   }
   __syncthreads();
-  // ---- pyrDown from the window (k_pyrdown's forms: ssk_prep.cu)
+  // ---- pyrDown from the window (k_pyrdown's forms: ssk_prep.cu); gray column 2 ox - 2 sits at window column 2 lx + 2
   const int lx = threadIdx.x & (BP_OW - 1), ly0 = (threadIdx.x / BP_OW) * BP_RPT;
   const int ox = blockIdx.x * BP_OW + lx, oy0 = blockIdx.y * BP_OH + ly0;
   if (ox >= dst_cols || oy0 >= dst_rows) return;
@@ -219,7 +234,7 @@ __global__ void __launch_bounds__(256) k_bayer_gray_pyrdown(const void *const *_
   float h[NR];
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
-    const float *g = &sg[2 * ly0 + r][2 * lx];
+    const float *g = &sg[2 * ly0 + r][2 * lx + 2];
     h[r] = pd_hform(g[0], g[1], g[2], g[3], g[4], hsimd);
   }
 #pragma unroll
@@ -227,6 +242,16 @@ __global__ void __launch_bounds__(256) k_bayer_gray_pyrdown(const void *const *_
     if (oy0 + j >= dst_rows) break;
     dst[(int64_t)(oy0 + j) * dst_cols + ox] = pd_vform(h[2 * j], h[2 * j + 1], h[2 * j + 2], h[2 * j + 3], h[2 * j + 4], vsimd);
   }
+}
+
+template <class T>
+void run_bayer_gray_pyrdown(const void *const *src_ptrs, bool aligned, int64_t sstep, int rows, int cols, int ry, int rx, float scale,
+                            float *const *dst_ptrs, int dr, int dc, int batch, cudaStream_t s) {
+  const dim3 grid(div_up(dc, BP_OW), div_up(dr, BP_OH), batch);
+  if (aligned && sstep % (int64_t)(4 * sizeof(T)) == 0)
+    k_bayer_gray_pyrdown<T, true><<<grid, 256, 0, s>>>(src_ptrs, sstep, rows, cols, ry, rx, scale, dst_ptrs, dr, dc);
+  else
+    k_bayer_gray_pyrdown<T, false><<<grid, 256, 0, s>>>(src_ptrs, sstep, rows, cols, ry, rx, scale, dst_ptrs, dr, dc);
 }
 
 }  // namespace
@@ -250,9 +275,9 @@ int launch_debayer_nn2(const void *src, int64_t sstep, int depth, int rows, int 
   return SSK_OK;
 }
 
-// batched: src_ptrs[b] raw Bayer frames (rows x cols, one channel, `depth`), dst_ptrs[b] dense CV_32FC1 images of
+// batched: src_ptrs[b] raw Bayer frames (rows x cols, one channel, `depth`; frames_aligned16: every pointer is a multiple of 16), dst_ptrs[b] dense CV_32FC1 images of
 // ((rows + 1) / 2) x ((cols + 1) / 2): pyrDown(gray(debayer_nn2(raw) * scale))
-int launch_bayer_gray_pyrdown(const void *const *src_ptrs, int64_t sstep, int depth, int rows, int cols, int colorid, float scale,
+int launch_bayer_gray_pyrdown(const void *const *src_ptrs, bool frames_aligned16, int64_t sstep, int depth, int rows, int cols, int colorid, float scale,
                               float *const *dst_ptrs, int batch, cudaStream_t s) {
   SSK_REQUIRE(!(rows & 1) && !(cols & 1), "debayer_nn2: Can not make debayer for uneven image size");
   SSK_REQUIRE(rows >= 4 && cols >= 4, "bayer_gray_pyrdown: frame too small");
@@ -265,10 +290,9 @@ int launch_bayer_gray_pyrdown(const void *const *src_ptrs, int64_t sstep, int de
     default: set_error("debayer_nn2: unsupported colorid (RGGB, GRBG, GBRG, BGGR)"); return SSK_ERR_INVALID;
   }
   const int dr = (rows + 1) / 2, dc = (cols + 1) / 2;
-  const dim3 grid(div_up(dc, BP_OW), div_up(dr, BP_OH), batch);
-  if (depth == SSK_8U) k_bayer_gray_pyrdown<uint8_t><<<grid, 256, 0, s>>>(src_ptrs, sstep, rows, cols, ry, rx, scale, dst_ptrs, dr, dc);
-  else if (depth == SSK_16U) k_bayer_gray_pyrdown<uint16_t><<<grid, 256, 0, s>>>(src_ptrs, sstep, rows, cols, ry, rx, scale, dst_ptrs, dr, dc);
-  else if (depth == SSK_32F) k_bayer_gray_pyrdown<float><<<grid, 256, 0, s>>>(src_ptrs, sstep, rows, cols, ry, rx, scale, dst_ptrs, dr, dc);
+  if (depth == SSK_8U) run_bayer_gray_pyrdown<uint8_t>(src_ptrs, frames_aligned16, sstep, rows, cols, ry, rx, scale, dst_ptrs, dr, dc, batch, s);
+  else if (depth == SSK_16U) run_bayer_gray_pyrdown<uint16_t>(src_ptrs, frames_aligned16, sstep, rows, cols, ry, rx, scale, dst_ptrs, dr, dc, batch, s);
+  else if (depth == SSK_32F) run_bayer_gray_pyrdown<float>(src_ptrs, frames_aligned16, sstep, rows, cols, ry, rx, scale, dst_ptrs, dr, dc, batch, s);
   else { set_error("bayer_gray_pyrdown: CV_8U, CV_16U or CV_32F"); return SSK_ERR_INVALID; }
   SSK_LAUNCH_CHECK();
   return SSK_OK;

@@ -130,7 +130,7 @@ int launch_add_weighted(const float *src, double alpha, const float *lpass, doub
 int launch_debayer_nn2(const void *src, int64_t sstep, int depth, int rows, int cols, int colorid, void *dst, int64_t dstep,
                        cudaStream_t s);
 // debayer_nn2 -> BGR2GRAY -> cv::pyrDown fused (the ECC image of a raw Bayer frame at ecc.scale 0.5), bit-identical to the chain
-int launch_bayer_gray_pyrdown(const void *const *src_ptrs, int64_t sstep, int depth, int rows, int cols, int colorid, float scale,
+int launch_bayer_gray_pyrdown(const void *const *src_ptrs, bool frames_aligned16, int64_t sstep, int depth, int rows, int cols, int colorid, float scale,
                               float *const *dst_ptrs, int batch, cudaStream_t s);
 
 // average_pyramid_inpaint (core/proc/inpaint/average_pyramid_inpaint.cc:97-127; ssk_inpaint.cu).  src: CV_32F with `cn`

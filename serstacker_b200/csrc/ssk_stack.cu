@@ -446,7 +446,7 @@ static int stack_process_chunk(ssk_stack *h, const ssk_mat *frames, int n, int s
       // ecc.scale 0.5: the registration only needs pyrDown(gray(debayer(raw))): one pass from the raw samples, the BGR frame
       // is never formed (bit-identical to the chain below)
       if (int e = h->reg_h.r.reserve_batch(n)) return e;
-      if (int e = launch_bayer_gray_pyrdown(d_frame_ptrs, geom.step, d, h->rows, h->cols, h->o.bayer_colorid, geom.scale,
+      if (int e = launch_bayer_gray_pyrdown(d_frame_ptrs, h->frames_aligned, geom.step, d, h->rows, h->cols, h->o.bayer_colorid, geom.scale,
                                             h->reg_h.r.ecch.level0_scratch_ptrs(), n, s)) return e;
       h->reg_h.r.ecc_images_ready = true;
       if (int e = h->reg_h.r.prepare(g3, nullptr, n)) return e;

@@ -300,6 +300,40 @@ def test_stack_bayer_average_other_depths(gpu, dtype):
     assert rel_l2(avg_g, avg_o, mask_o > 0) <= 1e-5
 
 
+@pytest.mark.parametrize("dtype", ["u8", "u16", "f32"])
+@pytest.mark.parametrize("size", [(192, 128), (190, 126), (66, 98)])
+@pytest.mark.parametrize("colorid", [8, 11])
+def test_stack_bayer_fused_ecc_image_is_bit_identical(gpu, dtype, size, colorid):
+    """ecc.scale 0.5: the one-pass raw -> pyrDown(gray(debayer_nn2)) kernel (k_bayer_gray_pyrdown, aligned 4-sample loads or
+    scalar loads by the row pitch) gives the registration the same ECC image as debayer_nn2 -> k_pyrdown: identical
+    transforms, sums and counters.  SSK_NO_BAYER_PYRDOWN selects the three-kernel chain."""
+    import os
+    from serstacker_b200 import api
+    w, h = size
+    frames, _, bpp = synth.make_bayer_sequence(w, h, 5, seed=17)
+    if dtype == "u8":
+        frames, bpp = [(f >> 8).astype(np.uint8) for f in frames], 8
+    elif dtype == "f32":
+        frames, bpp = [(f.astype(np.float32) / np.float32(65536.0)) for f in frames], 32
+    out = []
+    for chain in (False, True):
+        if chain:
+            os.environ["SSK_NO_BAYER_PYRDOWN"] = "1"
+        try:
+            p = api.c_image_stacking_pipeline(api.stack_options(registration=api.registration_options(motion_type=0), accumulation_method=2,
+                                                                bayer_colorid=colorid, max_batch=3))
+            p.set_reference(frames[0], bpp=bpp)
+            res = p.add_frames(frames)
+            avg, mask = p.compute()
+            out.append((res, avg, mask, p.accumulator().get_acc_counters()))
+        finally:
+            os.environ.pop("SSK_NO_BAYER_PYRDOWN", None)
+    (ra, avg_a, mask_a, cnt_a), (rb, avg_b, mask_b, cnt_b) = out
+    assert [r["ok"] for r in ra] == [r["ok"] for r in rb] and any(r["ok"] for r in ra[1:])
+    assert all(np.array_equal(x["params"], y["params"]) for x, y in zip(ra, rb))
+    assert np.array_equal(avg_a, avg_b) and np.array_equal(mask_a, mask_b) and np.array_equal(cnt_a, cnt_b)
+
+
 def test_stack_bayer_average_without_registration(gpu):
     """enable_registration = false: empty remap, every raw sample goes to its own colour plane (c_frame_accumulation.cc:998-1010)."""
     from serstacker_b200 import api
