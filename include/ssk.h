@@ -535,7 +535,9 @@ SSK_API ssk_reg *ssk_stack_registration(ssk_stack *h);
 /* CUDA stream the handle launches on (cudaStream_t as void*), for event timing by the caller. */
 SSK_API void *ssk_stack_stream(ssk_stack *h);
 /* Per-stage device time (ms) of the last ssk_stack_add_frames* call after ssk_stack_sync:
- * [0] prep (convert+pyrDown+smooth+pyramid) [1] weights [2] ECC [3] warp+accumulate. */
+ * [0] prep (convert+pyrDown+smooth+pyramid) [1] weights [2] ECC [3] warp+accumulate.
+ * The host-side enqueue of the same stages is bracketed by NVTX ranges ("ssk_stack: registration prep", "... sharpness
+ * weights", "... register_frame (ECC)", "... warp + accumulate") for timeline tools. */
 SSK_API int ssk_stack_stage_times(ssk_stack *h, float ms[4]);
 
 #ifdef __cplusplus
