@@ -101,7 +101,7 @@ def run(args, peaks, ClockSampler):
             ro = api.registration_options(motion_type=capi.MOTION_TRANSLATION, interpolation=capi.INTER_LINEAR,
                                           ecc=dict(ecc_method=capi.ECC_INVERSE_COMPOSITIONAL_LM, ecch_max_level=-1))
             so = api.stack_options(registration=ro, accumulation_method=capi.STACK_BAYER_AVERAGE, bayer_colorid=capi.COLORID_BAYER_RGGB,
-                                   max_batch=min(args.chunk, 32))
+                                   max_batch=min(args.chunk, int(os.environ.get("SSK_C3_CHUNK", "32"))))
             bytes_frame = W * H * (2 + 24 + 24)                  # N (s_in + 2*12 + 2*12)
             kname = "Bayer gather of the raw samples through the analytic map into acc / cntr (k_bayer_warp_accumulate)"
         CH = so.max_batch

@@ -8,7 +8,7 @@
 namespace ssk {
 namespace {
 
-template <class T> struct Wide { typedef int type; };
+template <class T> struct Wide { typedef unsigned type; };   // samples and their sums are non-negative: / 4, / 2 are shifts
 template <> struct Wide<float> { typedef float type; };
 
 template <class T> __device__ __forceinline__ T avg4(typename Wide<T>::type a, typename Wide<T>::type b, typename Wide<T>::type c,
@@ -157,12 +157,12 @@ __device__ __forceinline__ float debayer_gray(const typename Wide<T>::type (&w)[
   return bgr2gray(sample_f<T>(b, scale), sample_f<T>(g, scale), sample_f<T>(r, scale));
 }
 
-template <class T, bool VEC>
+template <class T, bool VEC, int RY, int RX>      // (RY, RX): parities of the R sample of the 2 x 2 cell, compile-time
 __global__ void __launch_bounds__(256) k_bayer_gray_pyrdown(const void *const *__restrict__ src_ptrs, int64_t sstep, int rows, int cols,
-                                                            int ry, int rx, float scale, float *const *__restrict__ dst_ptrs,
-                                                            int dst_rows, int dst_cols) {
+                                                            float scale, float *const *__restrict__ dst_ptrs, int dst_rows, int dst_cols) {
   typedef typename Wide<T>::type W;
-  __shared__ float sg[BP_GH][BP_GW + 1];
+  constexpr int ry = RY, rx = RX;
+  __shared__ __align__(16) float sg[BP_GH][BP_GW + 4];     // pitch a multiple of 4: 16-byte row stores, 8-byte row loads
   const char *src = static_cast<const char *>(src_ptrs[blockIdx.z]);
   float *dst = dst_ptrs[blockIdx.z];
   const int gx0 = 2 * (int)blockIdx.x * BP_OW - 4, gy0 = 2 * (int)blockIdx.y * BP_OH - 2;   // multiples of 4 / 2
@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(256) k_bayer_gray_pyrdown(const void *const *_
         q[i][5] = (W)__ldg(rp + xp);
       }
 #pragma unroll
-      for (int dy = 0; dy < 2; ++dy)
+      for (int dy = 0; dy < 2; ++dy) {
+        float gq[4];
 #pragma unroll
         for (int dx = 0; dx < 4; ++dx) {
           W w[3][3];
@@ -204,8 +205,10 @@ __global__ void __launch_bounds__(256) k_bayer_gray_pyrdown(const void *const *_
           for (int i = 0; i < 3; ++i)
 #pragma unroll
             for (int k = 0; k < 3; ++k) w[i][k] = q[dy + i][dx + k];
-          sg[2 * uy + dy][4 * ux + dx] = debayer_gray<T>(w, dy, dx & 1, ry, rx, scale);      // y0 is even, x0 a multiple of 4
+          gq[dx] = debayer_gray<T>(w, dy, dx & 1, ry, rx, scale);      // y0 is even, x0 a multiple of 4
         }
+        *reinterpret_cast<float4 *>(&sg[2 * uy + dy][4 * ux]) = make_float4(gq[0], gq[1], gq[2], gq[3]);
+      }
     } else {
       // positions outside the frame: cv::pyrDown's BORDER_REFLECT101 of the gray image, pixel by pixel
 #pragma unroll 1
@@ -235,7 +238,8 @@ __global__ void __launch_bounds__(256) k_bayer_gray_pyrdown(const void *const *_
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
     const float *g = &sg[2 * ly0 + r][2 * lx + 2];
-    h[r] = pd_hform(g[0], g[1], g[2], g[3], g[4], hsimd);
+    const float2 g01 = *reinterpret_cast<const float2 *>(g), g23 = *reinterpret_cast<const float2 *>(g + 2);
+    h[r] = pd_hform(g01.x, g01.y, g23.x, g23.y, g[4], hsimd);
   }
 #pragma unroll
   for (int j = 0; j < BP_RPT; ++j) {
@@ -244,14 +248,23 @@ __global__ void __launch_bounds__(256) k_bayer_gray_pyrdown(const void *const *_
   }
 }
 
+template <class T, bool VEC>
+void run_bayer_gray_pyrdown_p(const void *const *src_ptrs, int64_t sstep, int rows, int cols, int ry, int rx, float scale,
+                              float *const *dst_ptrs, int dr, int dc, int batch, cudaStream_t s) {
+  const dim3 grid(div_up(dc, BP_OW), div_up(dr, BP_OH), batch);
+  if (ry == 0 && rx == 0) k_bayer_gray_pyrdown<T, VEC, 0, 0><<<grid, 256, 0, s>>>(src_ptrs, sstep, rows, cols, scale, dst_ptrs, dr, dc);
+  else if (ry == 0) k_bayer_gray_pyrdown<T, VEC, 0, 1><<<grid, 256, 0, s>>>(src_ptrs, sstep, rows, cols, scale, dst_ptrs, dr, dc);
+  else if (rx == 0) k_bayer_gray_pyrdown<T, VEC, 1, 0><<<grid, 256, 0, s>>>(src_ptrs, sstep, rows, cols, scale, dst_ptrs, dr, dc);
+  else k_bayer_gray_pyrdown<T, VEC, 1, 1><<<grid, 256, 0, s>>>(src_ptrs, sstep, rows, cols, scale, dst_ptrs, dr, dc);
+}
+
 template <class T>
 void run_bayer_gray_pyrdown(const void *const *src_ptrs, bool aligned, int64_t sstep, int rows, int cols, int ry, int rx, float scale,
                             float *const *dst_ptrs, int dr, int dc, int batch, cudaStream_t s) {
-  const dim3 grid(div_up(dc, BP_OW), div_up(dr, BP_OH), batch);
   if (aligned && sstep % (int64_t)(4 * sizeof(T)) == 0)
-    k_bayer_gray_pyrdown<T, true><<<grid, 256, 0, s>>>(src_ptrs, sstep, rows, cols, ry, rx, scale, dst_ptrs, dr, dc);
+    run_bayer_gray_pyrdown_p<T, true>(src_ptrs, sstep, rows, cols, ry, rx, scale, dst_ptrs, dr, dc, batch, s);
   else
-    k_bayer_gray_pyrdown<T, false><<<grid, 256, 0, s>>>(src_ptrs, sstep, rows, cols, ry, rx, scale, dst_ptrs, dr, dc);
+    run_bayer_gray_pyrdown_p<T, false>(src_ptrs, sstep, rows, cols, ry, rx, scale, dst_ptrs, dr, dc, batch, s);
 }
 
 }  // namespace
