@@ -12,6 +12,7 @@
 //        src_x = (int)p[0]; ax = (src_x + 1 - p[0]) evaluated in float then widened; s = ax * ay * w in double;
 //        acc[c] += src * s and cntr[c] += s: float += double (sum formed in double, narrowed once), taps in the
 //        order 00, 01, 10, 11 (the two green taps of a 2x2 cell update the same channel one after the other).
+#include <cmath>
 #include "ssk_warp.cuh"
 
 namespace ssk {
@@ -84,9 +85,38 @@ __host__ __device__ inline unsigned pattern_code(int colorid) {
   }
 }
 
-template <int DEPTH>
+// (double)i for 0 <= i < 2^31 without a conversion instruction: 2^52 + i is exact in the low mantissa word
+__device__ __forceinline__ double int_as_double(int i) { return __hiloint2double(0x43300000, i) - 4503599627370496.0; }
+
+// The reference's tap weights along one axis: a = (double)((float)(s + 1) - u), b = (double)(u - (float)s), float differences
+// widened to double.  For s >= 1 (u in [s, s + 1)) both float differences are exact (Sterbenz), so they equal the double
+// differences of the widened operands: one widening of u instead of two, and no int -> float conversions.  s = 0 (u may be
+// negative or tiny: 1 - u rounds in float) keeps the literal form.
+__device__ __forceinline__ void tap_weights(float u, int s, double &a, double &b) {
+  if (s >= 1) {
+    const double du = (double)u, ds = int_as_double(s);
+    b = du - ds;
+    a = (ds + 1.0) - du;
+  } else {
+    a = (double)((float)(s + 1) - u);
+    b = (double)(u - (float)s);
+  }
+}
+
+// (double)(sample * scale) as the reference forms it (convertTo(CV_32F, 1 / (1 << bpp)), then widened).  EXACT: the scale is
+// a power of two, so the float product of an 8 / 16-bit sample is exact and equals the double product of the exactly
+// converted operands - no conversion instruction on the way.
+template <int DEPTH, bool EXACT>
+__device__ __forceinline__ double sample_d(const Img &im, int y, int x, double scale_d) {
+  if (DEPTH == SSK_32F || !EXACT) return (double)load_px<DEPTH>(im, y, x, 0);
+  typedef typename PixT<DEPTH>::type T;
+  const T *row = reinterpret_cast<const T *>(static_cast<const char *>(im.data) + (int64_t)y * im.step);
+  return int_as_double((int)__ldg(row + x)) * scale_d;
+}
+
+template <int DEPTH, bool EXACT>
 __global__ void __launch_bounds__(BTW * BTH) k_fused_bayer(const __grid_constant__ WarpAccArgs a, const __grid_constant__ Tables tab,
-                                                          const unsigned pcode) {
+                                                          const unsigned pcode, const double scale_d) {
   __shared__ signed char s_flag[BPLAN];
   const int bx0 = blockIdx.x * BTW, by0 = blockIdx.y * BTH;
   for (int jj = threadIdx.x; jj < a.njobs; jj += BTW * BTH)
@@ -120,8 +150,9 @@ __global__ void __launch_bounds__(BTW * BTH) k_fused_bayer(const __grid_constant
     remap_at(m, flow, x, y, a.src_cols, u, v);
     const int sx = (int)u, sy = (int)v;           // truncation toward zero, as the reference's (int) cast
     if (!(sx >= 0 && sx < a.src_cols - 1 && sy >= 0 && sy < a.src_rows - 1)) continue;
-    const double ax = (double)((float)(sx + 1) - u), ay = (double)((float)(sy + 1) - v);
-    const double bx = (double)(u - (float)sx), by = (double)(v - (float)sy);
+    double ax, bx, ay, by;
+    tap_weights(u, sx, ax, bx);
+    tap_weights(v, sy, ay, by);
     im.data = a.jobs[j].frame;
     // The 2x2 footprint holds one R, one B and two G samples whatever the parity of (sx, sy).  The reference walks the taps
     // in the order 00, 01, 10, 11 and updates the channel of each; channels do not interact, so only the order of the two G
@@ -129,7 +160,7 @@ __global__ void __launch_bounds__(BTW * BTH) k_fused_bayer(const __grid_constant
     // channel selects (the tap-order form compiled to three predicated copies of every conversion).
     auto update = [&](float &Ac, float &Nc, int dy, int dx) {
       const double w = (dx ? bx : ax) * (dy ? by : ay);
-      const double sv = (double)load_px<DEPTH>(im, sy + dy, sx + dx, 0);
+      const double sv = sample_d<DEPTH, EXACT>(im, sy + dy, sx + dx, scale_d);
       const double an = (double)Ac + sv * w;
       const double nn = (double)Nc + w;
       Ac = (float)an; Nc = (float)nn;
@@ -157,15 +188,19 @@ int launch_bayer_warp_accumulate(const WarpAccArgs &a_in, const Tables &tab, int
   SSK_REQUIRE(!(a.src_rows & 1) && !(a.src_cols & 1), "bayer_warp_accumulate: frame size must be even");
   SSK_REQUIRE(colorid >= SSK_COLORID_BAYER_RGGB && colorid <= SSK_COLORID_BAYER_BGGR, "bayer_warp_accumulate: RGGB/GRBG/GBRG/BGGR");
   const unsigned pcode = pattern_code(colorid);
+  int sexp = 0;
+  const bool exact = a.scale > 0.f && std::frexp(a.scale, &sexp) == 0.5f && sexp > -100 && !getenv("SSK_BAYER_LITERAL");   // 1 / (1 << bpp), or 1
   const dim3 grid(div_up(a.cols, BTW), div_up(a.rows, BTH));
   const FrameJob *jobs = a.jobs;
   const int njobs = a.njobs;
   for (int j0 = 0; j0 < njobs; j0 += BPLAN) {
     a.jobs = jobs + j0; a.njobs = std::min(BPLAN, njobs - j0);
     if (a_in.flow) a.flow = a_in.flow + (int64_t)j0 * a.flow_stride;
-    if (a.depth == SSK_32F) k_fused_bayer<SSK_32F><<<grid, BTW * BTH, 0, s>>>(a, tab, pcode);
-    else if (a.depth == SSK_16U) k_fused_bayer<SSK_16U><<<grid, BTW * BTH, 0, s>>>(a, tab, pcode);
-    else if (a.depth == SSK_8U) k_fused_bayer<SSK_8U><<<grid, BTW * BTH, 0, s>>>(a, tab, pcode);
+    if (a.depth == SSK_32F) k_fused_bayer<SSK_32F, false><<<grid, BTW * BTH, 0, s>>>(a, tab, pcode, (double)a.scale);
+    else if (a.depth == SSK_16U && exact) k_fused_bayer<SSK_16U, true><<<grid, BTW * BTH, 0, s>>>(a, tab, pcode, (double)a.scale);
+    else if (a.depth == SSK_16U) k_fused_bayer<SSK_16U, false><<<grid, BTW * BTH, 0, s>>>(a, tab, pcode, (double)a.scale);
+    else if (a.depth == SSK_8U && exact) k_fused_bayer<SSK_8U, true><<<grid, BTW * BTH, 0, s>>>(a, tab, pcode, (double)a.scale);
+    else if (a.depth == SSK_8U) k_fused_bayer<SSK_8U, false><<<grid, BTW * BTH, 0, s>>>(a, tab, pcode, (double)a.scale);
     else { set_error("bayer_warp_accumulate: unsupported frame depth"); return SSK_ERR_INVALID; }
     SSK_LAUNCH_CHECK();
   }
