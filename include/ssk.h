@@ -193,6 +193,12 @@ SSK_API int ssk_transform_init(ssk_transform *t, int motion_type);           /* 
 SSK_API int ssk_transform_create_remap(const ssk_transform *t, int rows, int cols, ssk_mat *rmap);
 /* c_image_transform::scale_transfrom(factor). */
 SSK_API int ssk_transform_scale(ssk_transform *t, double factor);
+/* c_image_transform::eps(dp, image_size): the size of a parameter step in pixels, as the solvers' convergence test reads it
+ * (c_image_transform.cc:136-139, 509-523, 917-924, 1196-1205).  Host arithmetic, no device call; ndp = t->nparams. */
+SSK_API int ssk_transform_eps(const ssk_transform *t, const float *dp, int ndp, int rows, int cols, double *eps);
+/* c_image_transform::invert_and_compose(parameters(), dp): the parameters of  W(p) o W(dp)^-1  (c_image_transform.h:164-167,
+ * 312-318, 379-384; c_image_transform.cc:736-833); out receives t->nparams floats (homography: a22 normalised to 1). Host arithmetic. */
+SSK_API int ssk_transform_invert_and_compose(const ssk_transform *t, const float *dp, int ndp, float *out);
 
 /* ---------------------------------------------------------------------------------------------
  * cv::remap as the reference calls it (c_frame_registration::base_remap, c_frame_registration.cc:1265-1386):

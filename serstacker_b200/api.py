@@ -38,6 +38,22 @@ class c_image_transform:
     def scale_transfrom(self, factor):
         check(capi.lib.ssk_transform_scale(C.byref(self.t), float(factor)))
 
+    def eps(self, dp, size):
+        """c_image_transform::eps(dp, image_size), size = (width, height)."""
+        dp = np.ascontiguousarray(dp, dtype=f32).reshape(-1)
+        out = C.c_double()
+        check(capi.lib.ssk_transform_eps(C.byref(self.t), dp.ctypes.data_as(C.POINTER(C.c_float)), dp.size, int(size[1]), int(size[0]),
+                                         C.byref(out)))
+        return out.value
+
+    def invert_and_compose(self, dp):
+        """c_image_transform::invert_and_compose(parameters(), dp) -> new parameter vector."""
+        dp = np.ascontiguousarray(dp, dtype=f32).reshape(-1)
+        out = np.empty(self.t.nparams, dtype=f32)
+        check(capi.lib.ssk_transform_invert_and_compose(C.byref(self.t), dp.ctypes.data_as(C.POINTER(C.c_float)), dp.size,
+                                                        out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
     def create_remap(self, size):
         w, h = size
         rmap = np.empty((h, w, 2), dtype=f32)

@@ -113,6 +113,17 @@ class c_image_transform {
     else if (t_.motion_type == SSK_MOTION_HOMOGRAPHY) { t_.params[2] = tx * t_.aux[2]; t_.params[5] = ty * t_.aux[2]; }
     else { t_.params[0] = tx; t_.params[1] = ty; }
   }
+  // eps(dp, image_size) and invert_and_compose(parameters(), dp) (c_image_transform.h:52, 107-110): host arithmetic in libssk
+  double eps(const std::vector<float> &dp, int cols, int rows) const {
+    double e = 0;
+    if (ssk_transform_eps(&t_, dp.data(), (int)dp.size(), rows, cols, &e) != SSK_OK) return -1;
+    return e;
+  }
+  std::vector<float> invert_and_compose(const std::vector<float> &dp) const {
+    std::vector<float> out((size_t)t_.nparams);
+    if (ssk_transform_invert_and_compose(&t_, dp.data(), (int)dp.size(), out.data()) != SSK_OK) out.clear();
+    return out;
+  }
   bool create_remap(int cols, int rows, image_t &rmap) const {
     create_like(rmap, rows, cols, SSK_32FC2);
     ssk_mat v = detail::view(rmap);

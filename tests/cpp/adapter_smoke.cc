@@ -41,6 +41,16 @@ int main(int argc, char **argv) {
     t.reset();
     t.translation(&tx, &ty);
     if (tx != 0.f || ty != 0.f || t.parameters()[0] != 1.f) return 3;
+    // eps(dp, size) / invert_and_compose(p, dp) (host arithmetic of libssk): a translation step of (3, 4) is 5 px long, and
+    // composing the identity with the inverse of a step (dx, dy) on the affine translation terms moves by (-dx, -dy)
+    ssk::c_image_transform tt(SSK_MOTION_TRANSLATION);
+    if (tt.eps({3.f, 4.f}, 640, 480) != 5.0) return 3;
+    tt.set_translation(10.f, -1.f);
+    const std::vector<float> tn = tt.invert_and_compose({0.5f, 0.25f});
+    if (tn.size() != 2 || tn[0] != 9.5f || tn[1] != -1.25f) return 3;
+    const std::vector<float> an = t.invert_and_compose({0.f, 0.f, 2.f, 0.f, 0.f, -3.f});
+    if (an.size() != 6 || an[0] != 1.f || an[4] != 1.f || an[2] != -2.f || an[5] != 3.f) return 3;
+    if (t.eps({0.f, 0.f, 3.f, 0.f, 0.f, 4.f}, 640, 480) != 5.0 || !t.invert_and_compose({1.f}).empty()) return 3;
     // the reference's option structs: defaults of c_frame_registration.h:47-64, 119-136 survive the conversion
     ssk::c_image_registration_options io;
     const ssk_registration_options so = ssk::to_ssk_options(io);
