@@ -407,6 +407,13 @@ class c_frame_registration {
   const c_image_transform::sptr &image_transform() const { return transform_; }
   const c_image_registration_status &status() const { return status_; }
   void set_input_bpp(int bpp) { bpp_ = bpp; }   // 8U/16U frames: c_image_stacking_pipeline_base.cc:271-276 scaling
+  // frame timestamps (c_frame_registration.h:230-236): carried for the caller, the ECC stages do not read them
+  void set_current_timestamp(double v, bool valid) { current_ts_ = v; current_ts_valid_ = valid; }
+  double current_timestamp() const { return current_ts_; }
+  bool has_valid_current_timestamp() const { return current_ts_valid_; }
+  void set_reference_timestamp(double v, bool valid) { reference_ts_ = v; reference_ts_valid_ = valid; }
+  double reference_timestamp() const { return reference_ts_; }
+  bool has_valid_reference_timestamp() const { return reference_ts_valid_; }
 
   bool setup_reference_frame(const image_t &image, const image_t &msk = image_t()) {
     if (other_stage_only_) return false;   // sparse-feature / eccflow registration without the ECC stage: not in this library
@@ -460,6 +467,8 @@ class c_frame_registration {
   c_image_registration_status status_;
   int bpp_ = 0;
   bool other_stage_only_ = false;
+  double current_ts_ = 0, reference_ts_ = 0;
+  bool current_ts_valid_ = false, reference_ts_valid_ = false;
 };
 
 // ---------------------------------------------------------------------------------------------------------
