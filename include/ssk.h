@@ -199,6 +199,9 @@ SSK_API int ssk_transform_eps(const ssk_transform *t, const float *dp, int ndp, 
 /* c_image_transform::invert_and_compose(parameters(), dp): the parameters of  W(p) o W(dp)^-1  (c_image_transform.h:164-167,
  * 312-318, 379-384; c_image_transform.cc:736-833); out receives t->nparams floats (homography: a22 normalised to 1). Host arithmetic. */
 SSK_API int ssk_transform_invert_and_compose(const ssk_transform *t, const float *dp, int ndp, float *out);
+/* c_image_transform::remap(parameters(), rpts, cpts): n reference points (x, y interleaved) -> their positions in the current frame
+ * (c_image_transform.cc:232-249, 557-585, 1019-1033, 1294-1306).  Host arithmetic. */
+SSK_API int ssk_transform_remap_points(const ssk_transform *t, const float *rpts_xy, int n, float *cpts_xy);
 
 /* ---------------------------------------------------------------------------------------------
  * cv::remap as the reference calls it (c_frame_registration::base_remap, c_frame_registration.cc:1265-1386):

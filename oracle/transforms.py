@@ -444,6 +444,37 @@ class HomographyTransform(ImageTransform):
         return aii.reshape(-1)[:8].copy()
 
 
+def remap_points(tr, rpts, p=None):
+    """c_image_transform::remap(params, rpts, cpts) (c_image_transform.cc:232-249 translation, 557-585 euclidean, 1019-1033
+    affine, 1294-1306 homography): float arithmetic in the reference's operand order.  The homography multiplies by 1/w where
+    create_remap divides by w; the euclidean form calls the float overloads of sin / cos."""
+    rpts = np.asarray(rpts, dtype=f32).reshape(-1, 2)
+    x, y = rpts[:, 0], rpts[:, 1]
+    out = np.empty_like(rpts)
+    if isinstance(tr, TranslationTransform):
+        q = tr.parameters() if p is None else np.asarray(p, dtype=f32).reshape(-1)
+        out[:, 0] = x + q[0]
+        out[:, 1] = y + q[1]
+    elif isinstance(tr, EuclideanTransform):
+        Tx, Ty, angle, scale, Cx, Cy = tr.get_parameters(tr.parameters() if p is None else p)
+        sa, ca = np.sin(f32(angle)), np.cos(f32(angle))          # float32 in, float32 out (sinf / cosf)
+        xx, yy = x - Cx, y - Cy
+        out[:, 0] = scale * (ca * xx - sa * yy) + Tx
+        out[:, 1] = scale * (sa * xx + ca * yy) + Ty
+    elif isinstance(tr, AffineTransform):
+        a = tr.parameters() if p is None else np.asarray(p, dtype=f32).reshape(-1)
+        out[:, 0] = a[0] * x + a[1] * y + a[2]
+        out[:, 1] = a[3] * x + a[4] * y + a[5]
+    elif isinstance(tr, HomographyTransform):
+        a = tr.matrix(p)
+        w = f32(1) / (a[2, 0] * x + a[2, 1] * y + a[2, 2])
+        out[:, 0] = (a[0, 0] * x + a[0, 1] * y + a[0, 2]) * w
+        out[:, 1] = (a[1, 0] * x + a[1, 1] * y + a[1, 2]) * w
+    else:
+        raise ValueError("unsupported transform")
+    return out
+
+
 def create_image_transform(motion_type):
     """image_transform.cc:34-63."""
     if motion_type == IMAGE_MOTION_TRANSLATION:

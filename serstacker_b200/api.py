@@ -54,6 +54,14 @@ class c_image_transform:
                                                         out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
 
+    def remap_points(self, rpts):
+        """c_image_transform::remap(parameters(), rpts, cpts): (n, 2) reference points -> current-frame points."""
+        rpts = np.ascontiguousarray(rpts, dtype=f32).reshape(-1, 2)
+        cpts = np.empty_like(rpts)
+        check(capi.lib.ssk_transform_remap_points(C.byref(self.t), rpts.ctypes.data_as(C.POINTER(C.c_float)), rpts.shape[0],
+                                                  cpts.ctypes.data_as(C.POINTER(C.c_float))))
+        return cpts
+
     def create_remap(self, size):
         w, h = size
         rmap = np.empty((h, w, 2), dtype=f32)

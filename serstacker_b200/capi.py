@@ -104,6 +104,7 @@ _sigs = {
     "ssk_transform_scale": (C.c_int, [_P(ssk_transform), C.c_double]),
     "ssk_transform_eps": (C.c_int, [_P(ssk_transform), _P(C.c_float), C.c_int, C.c_int, C.c_int, _P(C.c_double)]),
     "ssk_transform_invert_and_compose": (C.c_int, [_P(ssk_transform), _P(C.c_float), C.c_int, _P(C.c_float)]),
+    "ssk_transform_remap_points": (C.c_int, [_P(ssk_transform), _P(C.c_float), C.c_int, _P(C.c_float)]),
     "ssk_remap": (C.c_int, [_P(ssk_transform), _P(ssk_mat), _P(ssk_mat), _P(ssk_mat), _P(ssk_mat), _P(ssk_mat),
                             C.c_int, C.c_int, _P(C.c_double)]),
     "ssk_ecch_create": (C.c_int, [_P(ssk_ecch_options), _P(C.c_void_p)]),

@@ -134,4 +134,47 @@ int ssk_transform_invert_and_compose(const ssk_transform *t, const float *dp, in
   }
 }
 
+// c_image_transform::remap(params, rpts, cpts): reference points -> current-frame points (c_image_transform.cc:232-249,
+// 557-585, 1019-1033, 1294-1306); interleaved (x, y) floats.  The homography multiplies by the reciprocal of w, where
+// create_remap divides (c_image_transform.cc:1207-1223) - restated as written.
+int ssk_transform_remap_points(const ssk_transform *t, const float *rpts_xy, int n, float *cpts_xy) {
+  SSK_REQUIRE(t && (n == 0 || (rpts_xy && cpts_xy)) && n >= 0, "ssk_transform_remap_points: bad argument");
+  const float *p = t->params;
+  switch (t->motion_type) {
+    case SSK_MOTION_TRANSLATION:
+      for (int i = 0; i < n; ++i) { cpts_xy[2 * i] = rpts_xy[2 * i] + p[0]; cpts_xy[2 * i + 1] = rpts_xy[2 * i + 1] + p[1]; }
+      return SSK_OK;
+    case SSK_MOTION_EUCLIDEAN:
+    case SSK_MOTION_SCALED_EUCLIDEAN: {
+      const float Tx = p[0], Ty = p[1], angle = p[2], scale = t->motion_type == SSK_MOTION_EUCLIDEAN ? t->aux[3] : p[3];
+      const float Cx = t->aux[0], Cy = t->aux[1];
+      const float sa = std::sin(angle), ca = std::cos(angle);          // float overloads, as the reference calls them here
+      for (int i = 0; i < n; ++i) {
+        const float xx = rpts_xy[2 * i] - Cx, yy = rpts_xy[2 * i + 1] - Cy;
+        cpts_xy[2 * i] = scale * (ca * xx - sa * yy) + Tx;
+        cpts_xy[2 * i + 1] = scale * (sa * xx + ca * yy) + Ty;
+      }
+      return SSK_OK;
+    }
+    case SSK_MOTION_AFFINE:
+      for (int i = 0; i < n; ++i) {
+        const float x = rpts_xy[2 * i], y = rpts_xy[2 * i + 1];
+        cpts_xy[2 * i] = (p[0] * x + p[1] * y) + p[2];
+        cpts_xy[2 * i + 1] = (p[3] * x + p[4] * y) + p[5];
+      }
+      return SSK_OK;
+    case SSK_MOTION_HOMOGRAPHY:
+      for (int i = 0; i < n; ++i) {
+        const float x = rpts_xy[2 * i], y = rpts_xy[2 * i + 1];
+        const float w = 1.f / ((p[6] * x + p[7] * y) + t->aux[2]);
+        cpts_xy[2 * i] = ((p[0] * x + p[1] * y) + p[2]) * w;
+        cpts_xy[2 * i + 1] = ((p[3] * x + p[4] * y) + p[5]) * w;
+      }
+      return SSK_OK;
+    default:
+      set_error("unsupported motion type");
+      return SSK_ERR_INVALID;
+  }
+}
+
 }  // extern "C"

@@ -124,6 +124,11 @@ class c_image_transform {
     if (ssk_transform_invert_and_compose(&t_, dp.data(), (int)dp.size(), out.data()) != SSK_OK) out.clear();
     return out;
   }
+  // remap(rpts, cpts) (c_image_transform.h:79-82): interleaved (x, y) floats
+  bool remap(const std::vector<float> &rpts_xy, std::vector<float> &cpts_xy) const {
+    cpts_xy.resize(rpts_xy.size());
+    return ssk_transform_remap_points(&t_, rpts_xy.data(), (int)(rpts_xy.size() / 2), cpts_xy.data()) == SSK_OK;
+  }
   bool create_remap(int cols, int rows, image_t &rmap) const {
     create_like(rmap, rows, cols, SSK_32FC2);
     ssk_mat v = detail::view(rmap);

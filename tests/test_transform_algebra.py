@@ -59,3 +59,41 @@ def test_identity_step_and_bad_arguments():
         g.eps(np.zeros(5, f32), (640, 480))
     with pytest.raises(capi.SskError):
         g.invert_and_compose(np.zeros(8, f32))
+
+
+@pytest.mark.parametrize("motion", [0, 1, 2, 3, 4])
+def test_remap_points_matches_oracle(motion):
+    """c_image_transform::remap(params, rpts, cpts) (c_image_transform.cc:232-249, 557-585, 1019-1033, 1294-1306)."""
+    from serstacker_b200 import api
+    rng = np.random.default_rng(300 + motion)
+    for it in range(50):
+        p, _ = _random_case(motion, rng)
+        o = otf.create_image_transform(motion)
+        g = api.create_image_transform(motion)
+        o.set_parameters(p)
+        g.set_parameters(p)
+        if motion in (otf.IMAGE_MOTION_EUCLIDEAN, otf.IMAGE_MOTION_SCALED_EUCLIDEAN) and it % 2:
+            o.set_center((f32(320), f32(240)))
+            g.t.aux[0], g.t.aux[1] = 320.0, 240.0
+        pts = rng.uniform(-50, 2000, (257, 2)).astype(f32)
+        want = otf.remap_points(o, pts)
+        got = g.remap_points(pts)
+        assert np.array_equal(got, want), (motion, it, np.abs(got - want).max())
+    assert g.remap_points(np.zeros((0, 2), f32)).shape == (0, 2)
+
+
+@pytest.mark.parametrize("motion", [0, 3])
+def test_remap_points_on_the_pixel_grid_is_create_remap(motion):
+    """Translation and affine maps use the same expression for points and for the dense map (c_image_transform.cc:150-170,
+    926-946): the point form at integer positions must reproduce the oracle's create_remap, which the GPU parity tests pin."""
+    from serstacker_b200 import api
+    rng = np.random.default_rng(400 + motion)
+    p, _ = _random_case(motion, rng)
+    o = otf.create_image_transform(motion)
+    g = api.create_image_transform(motion)
+    o.set_parameters(p)
+    g.set_parameters(p)
+    w, h = 61, 47
+    yy, xx = np.mgrid[0:h, 0:w].astype(f32)
+    pts = np.stack([xx.ravel(), yy.ravel()], axis=1)
+    assert np.array_equal(g.remap_points(pts).reshape(h, w, 2), o.create_remap((w, h)))
